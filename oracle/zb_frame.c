@@ -1,0 +1,173 @@
+/* zb_frame.c — oracle frame driver (TEST INFRASTRUCTURE ONLY): parameter derivation, frame header,
+ * block loop and block headers, mirroring what ZSTD_compress / ZSTD_compress_usingDict do around
+ * the hot path (/root/reference/lib/compress/zstd_compress.c:5398-5440, :4527-4623, :4626-4672).
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "zb_oracle.h"
+
+static inline u32 hb32(u32 v) { return 31u - (u32)__builtin_clz(v); }
+
+/* compress/clevels.h:25-130, rows 0..4 of the four size classes (strategies fast=1 / dfast=2 only;
+ * rows whose reference strategy is greedy or above are served by the last dfast row of the class) */
+typedef struct { u8 W, C, H, S, L, TL, strat; } row;
+static const row kRows[4][5] = {
+    { {19,12,13,1,6,1,1}, {19,13,14,1,7,0,1}, {20,15,16,1,6,0,1}, {21,16,17,1,5,0,2}, {21,18,18,1,5,0,2} },   /* > 256 KB */
+    { {18,12,13,1,5,1,1}, {18,13,14,1,6,0,1}, {18,14,14,1,5,0,2}, {18,16,16,1,4,0,2}, {18,16,16,1,4,0,2} },   /* <= 256 KB (level 4 is greedy there -> row 3) */
+    { {17,12,12,1,5,1,1}, {17,12,13,1,6,0,1}, {17,13,15,1,5,0,1}, {17,15,16,2,5,0,2}, {17,17,17,2,4,0,2} },   /* <= 128 KB */
+    { {14,12,13,1,5,1,1}, {14,14,15,1,5,0,1}, {14,14,15,1,4,0,1}, {14,14,15,2,4,0,2}, {14,14,15,2,4,0,2} },   /* <= 16 KB (level 4 is greedy there -> row 3) */
+};
+
+/* zstd_compress.c:1432-1459 */
+static u32 dictAndWindowLog(u32 windowLog, u64 srcSize, u64 dictSize)
+{
+    u64 const maxWindowSize = 1ull << 31;
+    if (dictSize == 0) return windowLog;
+    {   u64 const windowSize = 1ull << windowLog;
+        u64 const dictAndWindowSize = dictSize + windowSize;
+        if (windowSize >= dictSize + srcSize) return windowLog;
+        if (dictAndWindowSize >= maxWindowSize) return 31;
+        return hb32((u32)dictAndWindowSize - 1) + 1;
+    }
+}
+
+/* zstd_compress.c:7123-7146 (row selection) + :1465-1602 (adjust, mode = cpm_noAttachDict) */
+zbo_cparams zbo_getCParams(int level, u64 srcSize, size_t dictSize)
+{
+    u64 const rSize = srcSize + dictSize;
+    u32 const tableID = (rSize <= 256u * 1024) + (rSize <= 128u * 1024) + (rSize <= 16u * 1024);
+    int r = level == 0 ? 3 : (level < 0 ? 0 : (level > 4 ? 4 : level));
+    zbo_cparams cp;
+    {   row const x = kRows[tableID][r];
+        cp.windowLog = x.W; cp.chainLog = x.C; cp.hashLog = x.H; cp.searchLog = x.S;
+        cp.minMatch = x.L; cp.targetLength = x.TL; cp.strategy = x.strat;
+    }
+    if (level < 0) {
+        int const minLevel = -(1 << 17);                       /* ZSTD_minCLevel, zstd_compress.c:7073 */
+        int const cl = level < minLevel ? minLevel : level;
+        cp.targetLength = (u32)(-cl);
+    }
+    {   u64 const maxWindowResize = 1ull << 30;
+        if (srcSize <= maxWindowResize && dictSize <= maxWindowResize) {
+            u32 const tSize = (u32)(srcSize + dictSize);
+            u32 const srcLog = (tSize < (1u << 6)) ? 6 : hb32(tSize - 1) + 1;
+            if (cp.windowLog > srcLog) cp.windowLog = srcLog;
+        }
+        {   u32 const dawl = dictAndWindowLog(cp.windowLog, srcSize, dictSize);
+            u32 const cycleLog = cp.chainLog;
+            if (cp.hashLog > dawl + 1) cp.hashLog = dawl + 1;
+            if (cycleLog > dawl) cp.chainLog -= (cycleLog - dawl);
+        }
+        if (cp.windowLog < 10) cp.windowLog = 10;
+    }
+    return cp;
+}
+
+/* lib/zstd.h:235 */
+size_t zbo_compressBound(size_t srcSize)
+{
+    if (srcSize >= 0xFF00FF00FF00FF00ull) return ZBO_ERR(ZBO_error_srcSize_wrong);
+    return srcSize + (srcSize >> 8) + ((srcSize < (128u << 10)) ? (((128u << 10) - srcSize) >> 11) : 0);
+}
+
+/* zstd_compress.c:4626-4672 : contentSizeFlag=1, no checksum */
+size_t zbo_writeFrameHeader(u8* dst, size_t cap, u32 windowLog, u64 srcSize, u32 dictID)
+{
+    u32 const dictIDSizeCode = (dictID > 0) + (dictID >= 256) + (dictID >= 65536);
+    u64 const windowSize = 1ull << windowLog;
+    u32 const singleSegment = windowSize >= srcSize;
+    u8  const windowLogByte = (u8)((windowLog - 10) << 3);
+    u32 const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256) + (srcSize >= 0xFFFFFFFFu);
+    size_t pos = 0;
+    if (cap < 18) return ZBO_ERR(ZBO_error_dstSize_tooSmall);      /* ZSTD_FRAMEHEADERSIZE_MAX */
+    dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD; pos = 4;
+    dst[pos++] = (u8)(dictIDSizeCode + (singleSegment << 5) + (fcsCode << 6));
+    if (!singleSegment) dst[pos++] = windowLogByte;
+    switch (dictIDSizeCode) {
+    case 1: dst[pos++] = (u8)dictID; break;
+    case 2: dst[pos++] = (u8)dictID; dst[pos++] = (u8)(dictID >> 8); break;
+    case 3: dst[pos++] = (u8)dictID; dst[pos++] = (u8)(dictID >> 8); dst[pos++] = (u8)(dictID >> 16); dst[pos++] = (u8)(dictID >> 24); break;
+    default: break;
+    }
+    switch (fcsCode) {
+    case 0: if (singleSegment) dst[pos++] = (u8)srcSize; break;
+    case 1: { u16 v = (u16)(srcSize - 256); dst[pos++] = (u8)v; dst[pos++] = (u8)(v >> 8); } break;
+    case 2: { u32 v = (u32)srcSize; for (int i = 0; i < 4; i++) dst[pos++] = (u8)(v >> (8 * i)); } break;
+    default: for (int i = 0; i < 8; i++) dst[pos++] = (u8)(srcSize >> (8 * i)); break;
+    }
+    return pos;
+}
+
+static int isRLE(const u8* src, size_t n)
+{
+    for (size_t i = 1; i < n; i++) if (src[i] != src[0]) return 0;
+    return 1;
+}
+
+/* One frame.  Blocks are independent (block-parallel plan); see zb_match.c. */
+size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t srcSize,
+                              const void* dict, size_t dictSize, int level)
+{
+    u8* const dst = (u8*)dstv;
+    const u8* const src = (const u8*)srcv;
+    zbo_cparams const cp = zbo_getCParams(level, srcSize, dict ? dictSize : 0);
+    zbo_plan plan;
+    size_t pos;
+    size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;  /* zstd_compress.c:2124 */
+    (void)dict; (void)dictSize;    /* dictionary path: see zb_dict.c (config 5) */
+
+    zbo_makePlan(&plan, &cp);
+    pos = zbo_writeFrameHeader(dst, cap, cp.windowLog, srcSize, 0);
+    if (zbo_isError(pos)) return pos;
+
+    if (srcSize == 0) {                                    /* zstd_compress.c:5279-5295 : empty last raw block */
+        if (cap - pos < 3) return ZBO_ERR(ZBO_error_dstSize_tooSmall);
+        dst[pos++] = 1; dst[pos++] = 0; dst[pos++] = 0;
+        return pos;
+    }
+    {   zbo_seq* seqs = (zbo_seq*)malloc((ZB_BLOCK_MAX / 4 + 1) * sizeof(zbo_seq));
+        u8* lit = (u8*)malloc(ZB_BLOCK_MAX + 64);
+        size_t const bodyCap = ZB_BLOCK_MAX * 4;
+        u8* body = (u8*)malloc(bodyCap);
+        size_t bs = 0;
+        size_t err = 0;
+        int first = 1;
+        while (bs < srcSize) {
+            size_t const blockSize = (srcSize - bs) < blockMax ? (srcSize - bs) : blockMax;
+            u32 const lastBlock = (bs + blockSize == srcSize);
+            size_t cSize = 0;
+            if (blockSize >= 7) {                                    /* zstd_compress.c:3216 */
+                size_t litSize = 0;
+                size_t const nbSeq = zbo_matchBlock(&plan, src, srcSize, bs, blockSize, seqs, lit, &litSize);
+                cSize = zbo_entropyCompressBlock(body, bodyCap, seqs, nbSeq, lit, litSize, blockSize,
+                                                 cp.strategy, (int)plan.litCompressionDisabled);
+                if (zbo_isError(cSize)) { err = cSize; break; }
+                if (!first && cSize < 25 && isRLE(src + bs, blockSize)) { cSize = 1; body[0] = src[bs]; }   /* :4365-4376 */
+            }
+            if (cSize == 0) {                                          /* raw block, zstd_compress_internal.h:586 */
+                if (cap - pos < 3 + blockSize) { err = ZBO_ERR(ZBO_error_dstSize_tooSmall); break; }
+                {   u32 const h = lastBlock + (0u << 1) + (u32)(blockSize << 3);
+                    dst[pos] = (u8)h; dst[pos + 1] = (u8)(h >> 8); dst[pos + 2] = (u8)(h >> 16); }
+                memcpy(dst + pos + 3, src + bs, blockSize);
+                pos += 3 + blockSize;
+            } else {
+                u32 const h = (cSize == 1) ? lastBlock + (1u << 1) + (u32)(blockSize << 3)
+                                           : lastBlock + (2u << 1) + (u32)(cSize << 3);           /* :4586-4590 */
+                if (cap - pos < 3 + cSize) { err = ZBO_ERR(ZBO_error_dstSize_tooSmall); break; }
+                dst[pos] = (u8)h; dst[pos + 1] = (u8)(h >> 8); dst[pos + 2] = (u8)(h >> 16);
+                memcpy(dst + pos + 3, body, cSize);
+                pos += 3 + cSize;
+            }
+            bs += blockSize;
+            first = 0;
+        }
+        free(seqs); free(lit); free(body);
+        if (err) return err;
+    }
+    return pos;
+}
+
+size_t zbo_compress(void* dst, size_t cap, const void* src, size_t srcSize, int level)
+{
+    return zbo_compress_usingDict(dst, cap, src, srcSize, NULL, 0, level);
+}

@@ -1,0 +1,121 @@
+/* zb_oracle.h — CPU oracle for the zstd_b200 hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (zstd_b200/) may include, link or call this.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg use it, and only as the
+ * checker.  It is a plain-C restatement of
+ *   (1) the reference's entropy stage (Huffman literals + FSE sequences), byte-exact with
+ *       /root/reference/lib/compress/{huf_compress.c,fse_compress.c,zstd_compress_literals.c,
+ *       zstd_compress_sequences.c,zstd_compress.c:2881-3035} given the same seqStore, and
+ *   (2) the block-parallel "warp-batch" greedy match-finder the CUDA kernels implement (a
+ *       deterministic data-parallel re-formulation of zstd_fast.c:192-423 /
+ *       zstd_double_fast.c:105-323; the parse differs from the serial CPU parse by design,
+ *       the compressed size must stay within +-0.5 % and every frame must decode with the
+ *       reference ZSTD_decompress).
+ * Parity pins (tests/test_oracle_*.py): (1) is compared byte-for-byte with the compiled reference
+ * (oracle/_ref/libzstd_ref.so + oracle/_ref/libref_shim.so); (2) is pinned by round-trip through
+ * the reference decoder and by size against the reference at the same level.
+ */
+#ifndef ZB_ORACLE_H
+#define ZB_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint8_t  u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+/* ---- error codes: same numbering as lib/zstd_errors.h:64-101 ---- */
+#define ZBO_ERR(code)            ((size_t)-(long)(code))
+#define ZBO_error_GENERIC            1
+#define ZBO_error_dictionary_corrupted 30
+#define ZBO_error_parameter_unsupported 40
+#define ZBO_error_memory_allocation 64
+#define ZBO_error_dstSize_tooSmall  70
+#define ZBO_error_srcSize_wrong     72
+#define ZBO_error_maxCode          120
+static inline int zbo_isError(size_t c) { return c > ZBO_ERR(ZBO_error_maxCode); }
+
+/* ---- compression parameters (lib/zstd.h:ZSTD_compressionParameters) ---- */
+typedef struct {
+    u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; /* 1=fast 2=dfast */
+} zbo_cparams;
+zbo_cparams zbo_getCParams(int level, u64 srcSize, size_t dictSize);
+
+/* ---- one sequence, as the match-finder emits it ---- */
+typedef struct { u32 offBase; u32 litLen; u32 matchLen; } zbo_seq;   /* matchLen = real length (>=3) */
+
+/* ---- block-parallel plan constants (shared with the CUDA side) ---- */
+#define ZB_BLOCK_MAX      (128u << 10)     /* ZSTD_BLOCKSIZE_MAX, lib/zstd.h:142 */
+#define ZB_PRIME_DEFAULT  (64u << 10)      /* history primed into a block's private table */
+#define ZB_WARP           32u
+
+typedef struct {
+    u32 mls;          /* bytes hashed (cParams.minMatch clamped to 4..8; short hash for dfast) */
+    u32 hashLog;      /* log2 entries of the (short) table */
+    u32 longHashLog;  /* dfast only: log2 entries of the 8-byte-hash table, else 0 */
+    u32 stepSize;     /* targetLength + !targetLength + 1 (zstd_fast.c:200); dfast: 1 */
+    u32 primeBytes;   /* history window primed before the block */
+    u32 strategy;     /* 1 fast, 2 dfast */
+    u32 windowLog;
+    u32 litCompressionDisabled; /* zstd_compress_internal.h:621-633 */
+} zbo_plan;
+void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp);
+
+/* ---- entropy primitives (exported so tests can pin each against the reference) ---- */
+u32    zbo_hist(const u8* src, size_t n, u32* count, u32* maxSymbolPtr);  /* hist.c:29 */
+u32    zbo_fse_optimalTableLog(u32 maxTableLog, size_t srcSize, u32 maxSymbolValue, u32 minus); /* fse_compress.c:357 */
+size_t zbo_fse_normalize(int16_t* norm, u32 tableLog, const u32* count, size_t total, u32 maxSymbolValue, u32 useLowProbCount); /* fse_compress.c:465 */
+size_t zbo_fse_writeNCount(u8* dst, size_t cap, const int16_t* norm, u32 maxSymbolValue, u32 tableLog); /* fse_compress.c:234 */
+
+typedef struct {           /* our own layout of an FSE compression table (fse.h:249 holds the reference's) */
+    u32 tableLog;
+    u32 maxSymbolValue;
+    u16 nextState[512];    /* sorted by symbol; value = tableSize + slot   (fse_compress.c:170-173) */
+    int32_t deltaFindState[64];
+    u32 deltaNbBits[64];
+} zbo_fse_ctable;
+size_t zbo_fse_buildCTable(zbo_fse_ctable* ct, const int16_t* norm, u32 maxSymbolValue, u32 tableLog); /* fse_compress.c:68 */
+void   zbo_fse_buildCTable_rle(zbo_fse_ctable* ct, u8 symbol);   /* fse_compress.c:528 */
+
+typedef struct { u8 nbBits[256]; u16 code[256]; u32 tableLog; u32 maxSymbolValue; } zbo_huf_ctable;
+size_t zbo_huf_buildCTable(zbo_huf_ctable* ct, const u32* count, u32 maxSymbolValue, u32 maxNbBits); /* huf_compress.c:756 */
+size_t zbo_huf_writeCTable(u8* dst, size_t cap, const zbo_huf_ctable* ct);    /* huf_compress.c:248 */
+size_t zbo_huf_encode1X(u8* dst, size_t cap, const u8* src, size_t n, const zbo_huf_ctable* ct); /* huf_compress.c:1056 */
+size_t zbo_huf_encode4X(u8* dst, size_t cap, const u8* src, size_t n, const zbo_huf_ctable* ct); /* huf_compress.c:1168 */
+
+/* literals section, fresh tables (no repeat/treeless): zstd_compress_literals.c:129 */
+size_t zbo_compressLiterals(u8* dst, size_t cap, const u8* lit, size_t litSize,
+                            u32 strategy, int disableLiteralCompression, int suspectUncompressible);
+
+/* whole compressed-block body (literals + sequences sections) with fresh entropy state:
+ * zstd_compress.c:2881-3035.  Returns 0 when the block must be emitted raw. */
+size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
+                                const zbo_seq* seqs, size_t nbSeq,
+                                const u8* lit, size_t litSize,
+                                size_t blockSrcSize, u32 strategy, int disableLiteralCompression);
+
+/* ---- match-finder model ---- */
+/* Parses block [blockStart, blockStart+blockSize) of `frame` (frameSize bytes, positions before
+ * blockStart are history).  Emits sequences + literal bytes.  Returns nbSeq; *litSizePtr gets the
+ * total literal count (including the trailing literals). */
+size_t zbo_matchBlock(const zbo_plan* plan, const u8* frame, size_t frameSize,
+                      size_t blockStart, size_t blockSize,
+                      zbo_seq* seqs, u8* lit, size_t* litSizePtr);
+
+/* ---- frame level: mirrors ZSTD_compress / ZSTD_compress_usingDict (lib/zstd.h:155,944) ---- */
+size_t zbo_compressBound(size_t srcSize);                             /* lib/zstd.h:235 */
+size_t zbo_compress(void* dst, size_t cap, const void* src, size_t srcSize, int level);
+size_t zbo_compress_usingDict(void* dst, size_t cap, const void* src, size_t srcSize,
+                              const void* dict, size_t dictSize, int level);
+/* per-block compressed sizes of the last zbo_compress call on this thread (diagnostics) */
+size_t zbo_writeFrameHeader(u8* dst, size_t cap, u32 windowLog, u64 srcSize, u32 dictID); /* zstd_compress.c:4626 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
