@@ -1,0 +1,95 @@
+/* zstd_b200.h — C ABI of libzstd_b200.so: the B200-native drop-in for zstd's per-block
+ * compression hot path (fast / doubleFast match-finder + Huffman literals + FSE sequences).
+ *
+ * Section 1 re-declares, with identical names, signatures, argument meaning and error
+ * behaviour, the reference entry points this library replaces (a language binding that
+ * dlopen()s libzstd for these symbols can be pointed at libzstd_b200.so unchanged).
+ * Section 2 adds device-pointer and many-frame entry points that have no reference
+ * counterpart (the reference has no device memory and no batch call); they are what the
+ * benchmark's device-resident `value` and the multi-GPU sharding use.
+ *
+ * All compression work is done by sm_100a CUDA kernels.  There is no CPU fallback: when no
+ * CUDA device is usable every compress call returns ZSTD_error_GENERIC (code 1).
+ */
+#ifndef ZSTD_B200_H
+#define ZSTD_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define ZSTDB200_API __attribute__((visibility("default")))
+#else
+#  define ZSTDB200_API
+#endif
+
+/* =====================  1. reference-identical entry points  ===================== */
+
+typedef struct ZSTD_CCtx_s ZSTD_CCtx;                 /* opaque, /root/reference/lib/zstd.h:262 */
+
+/* lib/zstd.h:155 — one call = one complete frame, content size in the header, no checksum.
+ * Returns compressed size, or an error code testable with ZSTD_isError(). */
+ZSTDB200_API size_t ZSTD_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int compressionLevel);
+
+/* lib/zstd.h:263-264 — context lifecycle; ZSTD_freeCCtx accepts NULL. */
+ZSTDB200_API ZSTD_CCtx* ZSTD_createCCtx(void);
+ZSTDB200_API size_t     ZSTD_freeCCtx(ZSTD_CCtx* cctx);
+
+/* lib/zstd.h:274 — same as ZSTD_compress with an explicit, reusable context. */
+ZSTDB200_API size_t ZSTD_compressCCtx(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                      const void* src, size_t srcSize, int compressionLevel);
+
+/* lib/zstd.h:944 — compression with a (raw-content or zstd-format) dictionary. */
+ZSTDB200_API size_t ZSTD_compress_usingDict(ZSTD_CCtx* ctx, void* dst, size_t dstCapacity,
+                                            const void* src, size_t srcSize,
+                                            const void* dict, size_t dictSize, int compressionLevel);
+
+/* lib/zstd.h:236,242-246,114-120 ; lib/zstd_errors.h:106 */
+ZSTDB200_API size_t      ZSTD_compressBound(size_t srcSize);
+ZSTDB200_API unsigned    ZSTD_isError(size_t code);
+ZSTDB200_API const char* ZSTD_getErrorName(size_t code);
+ZSTDB200_API int         ZSTD_getErrorCode(size_t functionResult);     /* ZSTD_ErrorCode as int */
+ZSTDB200_API int         ZSTD_minCLevel(void);
+ZSTDB200_API int         ZSTD_maxCLevel(void);
+ZSTDB200_API int         ZSTD_defaultCLevel(void);
+ZSTDB200_API unsigned    ZSTD_versionNumber(void);
+ZSTDB200_API const char* ZSTD_versionString(void);
+
+/* =====================  2. B200 extensions (no reference counterpart)  ===================== */
+
+/* Compress one frame whose input and output already live in device memory (HBM).
+ * `stream` is a cudaStream_t (NULL = default stream).  Synchronises once to read the size. */
+ZSTDB200_API size_t ZSTDB200_compressDevice(ZSTD_CCtx* cctx, void* d_dst, size_t dstCapacity,
+                                            const void* d_src, size_t srcSize, int compressionLevel, void* stream);
+
+/* Compress nbFrames independent inputs src[frameOffsets[i] .. +frameSizes[i]) into nbFrames
+ * complete frames written back to back into dst (the decoder accepts the concatenation,
+ * lib/zstd.h:160-162).  cSizes[i] (host array, may be NULL) receives each frame's size.
+ * With dict != NULL every frame is compressed as ZSTD_compress_usingDict would (config 5).
+ * `deviceMemory` != 0: src/dst are device pointers (dict and the offset arrays stay on the host). */
+ZSTDB200_API size_t ZSTDB200_compressFrames(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                            const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                            size_t nbFrames, const void* dict, size_t dictSize,
+                                            size_t* cSizes, int compressionLevel, int deviceMemory, void* stream);
+
+/* Timing / evidence of the last call on this context (CUDA events on the launching stream). */
+typedef struct {
+    float  kernel_ms;        /* first kernel start -> last kernel end */
+    float  match_ms;         /* match-finder kernel(s) only */
+    float  total_ms;         /* including host<->device copies, when the call made any */
+    unsigned launches;       /* kernels launched by the call */
+    unsigned nbBlocks;       /* 128 KiB blocks processed */
+    size_t h2d_bytes, d2h_bytes;
+} ZSTDB200_stats;
+ZSTDB200_API void ZSTDB200_getLastStats(const ZSTD_CCtx* cctx, ZSTDB200_stats* out);
+
+/* Which CUDA device new contexts bind to (default: current device / LOCAL_RANK). */
+ZSTDB200_API int  ZSTDB200_setDevice(int device);
+ZSTDB200_API int  ZSTDB200_deviceAvailable(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSTD_B200_H */

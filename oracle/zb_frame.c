@@ -171,3 +171,33 @@ size_t zbo_compress(void* dst, size_t cap, const void* src, size_t srcSize, int 
 {
     return zbo_compress_usingDict(dst, cap, src, srcSize, NULL, 0, level);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic LZ-style test data (our own generator, for tests that must run without the
+ * reference's datagen binary): literals from a skewed alphabet, matches copied from the last
+ * 32 KiB with probability matchProb/256, match lengths 4..~500.
+ * ---------------------------------------------------------------------------------------- */
+void zbo_synthetic(u8* buf, size_t n, u32 seed, u32 matchProb256)
+{
+    u64 s = 0x9E3779B97F4A7C15ull ^ ((u64)seed * 0xD1B54A32D192ED03ull);
+    size_t pos = 0;
+#define RND() (s ^= s << 13, s ^= s >> 7, s ^= s << 17, (u32)(s >> 32))
+    while (pos < n) {
+        u32 const r = RND();
+        if (pos > 16 && (r & 255u) < matchProb256) {
+            u32 const r2 = RND();
+            size_t len = 4 + ((r2 & 15u) ? (r2 >> 4) % 28u : (r2 >> 4) % 500u);
+            size_t const maxOff = pos < 32768 ? pos : 32768;
+            size_t const off = 1 + (RND() % maxOff);
+            if (len > n - pos) len = n - pos;
+            for (size_t i = 0; i < len; i++) buf[pos + i] = buf[pos + i - off];
+            pos += len;
+        } else {
+            u32 const r2 = RND();
+            u32 const k = r2 & 7u;       /* skew: small symbols far more likely */
+            u8 const c = (u8)(k < 5 ? (r2 >> 8) % 24u : (k < 7 ? (r2 >> 8) % 96u : (r2 >> 8)));
+            buf[pos++] = (u8)('a' + c);
+        }
+    }
+#undef RND
+}

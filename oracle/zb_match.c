@@ -161,7 +161,7 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
             while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
             mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + be);
             if (isRep && ms > anchor) offBase = 1;              /* REPCODE1_TO_OFFBASE, needs litLength > 0 */
-            else { offBase = offset + 3; if (!isRep) { rep2 = rep1; rep1 = offset; } }
+            else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }   /* decoder pushes every full offset */
             emit(&em, anchor, ms - anchor, mlen, offBase);
             ip = ms + mlen; anchor = ip;
 

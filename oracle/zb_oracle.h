@@ -114,6 +114,7 @@ size_t zbo_compress_usingDict(void* dst, size_t cap, const void* src, size_t src
                               const void* dict, size_t dictSize, int level);
 /* per-block compressed sizes of the last zbo_compress call on this thread (diagnostics) */
 size_t zbo_writeFrameHeader(u8* dst, size_t cap, u32 windowLog, u64 srcSize, u32 dictID); /* zstd_compress.c:4626 */
+void   zbo_synthetic(u8* buf, size_t n, u32 seed, u32 matchProb256);   /* test data generator (ours) */
 
 #ifdef __cplusplus
 }

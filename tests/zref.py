@@ -1,0 +1,139 @@
+"""Test helpers: ctypes views of the oracle (oracle/libzb_oracle.so), of the compiled reference
+(oracle/_ref/libzstd_ref.so, present only where /root/reference was available at build time or
+the prebuilt file travelled with the repo) and test-data generators.  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libzb_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libzstd_ref.so")
+DATAGEN = os.path.join(ROOT, "oracle", "_ref", "datagen")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_sz, _vp = ctypes.c_size_t, ctypes.c_void_p
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        O = ctypes.CDLL(ORACLE_SO, mode=ctypes.RTLD_LOCAL)
+        O.zbo_compress.restype = _sz
+        O.zbo_compress.argtypes = [_vp, _sz, _vp, _sz, ctypes.c_int]
+        O.zbo_compress_usingDict.restype = _sz
+        O.zbo_compress_usingDict.argtypes = [_vp, _sz, _vp, _sz, _vp, _sz, ctypes.c_int]
+        O.zbo_compressBound.restype = _sz
+        O.zbo_compressBound.argtypes = [_sz]
+        O.zbo_entropyCompressBlock.restype = _sz
+        O.zbo_entropyCompressBlock.argtypes = [_vp, _sz, _vp, _sz, _vp, _sz, _sz, ctypes.c_uint, ctypes.c_int]
+        O.zbo_synthetic.restype = None
+        O.zbo_synthetic.argtypes = [_vp, _sz, ctypes.c_uint, ctypes.c_uint]
+        O.zbo_getCParams_out = None
+        _oracle = O
+    return _oracle
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        R = ctypes.CDLL(REF_SO, mode=ctypes.RTLD_LOCAL)
+        R.ZSTD_compress.restype = _sz
+        R.ZSTD_compress.argtypes = [_vp, _sz, _vp, _sz, ctypes.c_int]
+        R.ZSTD_decompress.restype = _sz
+        R.ZSTD_decompress.argtypes = [_vp, _sz, _vp, _sz]
+        R.ZSTD_compressBound.restype = _sz
+        R.ZSTD_compressBound.argtypes = [_sz]
+        R.ZSTD_isError.restype = ctypes.c_uint
+        R.ZSTD_isError.argtypes = [_sz]
+        R.ZSTD_getErrorName.restype = ctypes.c_char_p
+        R.ZSTD_getErrorName.argtypes = [_sz]
+        R.ZSTD_getFrameContentSize.restype = ctypes.c_ulonglong
+        R.ZSTD_getFrameContentSize.argtypes = [_vp, _sz]
+        R.ZSTD_findFrameCompressedSize.restype = _sz
+        R.ZSTD_findFrameCompressedSize.argtypes = [_vp, _sz]
+        R.ZSTD_compress_usingDict.restype = _sz
+        R.ZSTD_compress_usingDict.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _sz, ctypes.c_int]
+        R.ZSTD_decompress_usingDict.restype = _sz
+        R.ZSTD_decompress_usingDict.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _sz]
+        R.ZSTD_createCCtx.restype = _vp
+        R.ZSTD_createDCtx.restype = _vp
+        R.ZSTD_freeCCtx.argtypes = [_vp]
+        R.ZSTD_freeDCtx.argtypes = [_vp]
+        R.ref_entropyCompressBlock.restype = _sz
+        R.ref_entropyCompressBlock.argtypes = [_vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _sz, ctypes.c_int, ctypes.c_uint]
+        R.ref_getCParams_simpleApi.restype = None
+        R.ref_getCParams_simpleApi.argtypes = [ctypes.c_int, ctypes.c_ulonglong, _sz, _vp]
+        _ref = R
+    return _ref
+
+
+def oracle_compress(src: bytes, level: int, cap: int = None) -> bytes:
+    O = oracle()
+    cap = O.zbo_compressBound(len(src)) if cap is None else cap
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = O.zbo_compress(dst, cap, src, len(src), level)
+    if r > (1 << 63):
+        raise RuntimeError(f"oracle error {-(r - (1 << 64))}")
+    return dst.raw[:r]
+
+
+def ref_compress(src: bytes, level: int) -> bytes:
+    R = ref()
+    cap = R.ZSTD_compressBound(len(src))
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = R.ZSTD_compress(dst, cap, src, len(src), level)
+    assert not R.ZSTD_isError(r), R.ZSTD_getErrorName(r)
+    return dst.raw[:r]
+
+
+def ref_decompress(frame: bytes, max_size: int) -> bytes:
+    """Decode (possibly concatenated) frames with the reference decoder; raises on any error."""
+    R = ref()
+    out = ctypes.create_string_buffer(max(max_size, 1))
+    r = R.ZSTD_decompress(out, max_size, frame, len(frame))
+    if R.ZSTD_isError(r):
+        raise ValueError("reference decoder: " + R.ZSTD_getErrorName(r).decode())
+    return out.raw[:r]
+
+
+def synthetic(n: int, seed: int = 0, match_prob: float = 0.5) -> bytes:
+    """Our own LZ-style generator (oracle/zb_frame.c:zbo_synthetic) — available everywhere."""
+    buf = ctypes.create_string_buffer(max(n, 1))
+    oracle().zbo_synthetic(buf, n, seed, int(match_prob * 256))
+    return buf.raw[:n]
+
+
+def datagen(size: int, p: int = 50, seed: int = 0) -> bytes:
+    """The reference's tests/datagen (compiled to oracle/_ref/datagen); cached under /tmp."""
+    path = f"/tmp/zb_datagen_g{size}_P{p}_s{seed}.bin"
+    if not (os.path.exists(path) and os.path.getsize(path) == size):
+        if not os.path.exists(DATAGEN):
+            raise FileNotFoundError(DATAGEN)
+        with open(path + ".tmp", "wb") as f:
+            subprocess.check_call([DATAGEN, f"-g{size}", f"-P{p}", f"-s{seed}"], stdout=f)
+        os.replace(path + ".tmp", path)
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def have_datagen() -> bool:
+    return os.path.exists(DATAGEN)
+
+
+def sha(b: bytes) -> str:
+    return hashlib.sha256(b).hexdigest()
+
+
+def random_bytes(n: int, seed: int = 0) -> bytes:
+    return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8).tobytes()

@@ -1,0 +1,177 @@
+"""zstd_b200 — Python host-side mirror of the libzstd C API served by libzstd_b200.so.
+
+The product is the C-ABI shared library (include/zstd_b200.h); this module is the thin ctypes
+binding a Python caller (tests, bench.py, torch.distributed sharding) uses.  Function names,
+argument meaning and error behaviour follow the reference's simple API
+(/root/reference/lib/zstd.h:155 ZSTD_compress, :274 ZSTD_compressCCtx, :944 ZSTD_compress_usingDict).
+
+There is no CPU fallback: importing works anywhere, but every compress call raises ZstdError
+when the CUDA library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzstd_b200.so")
+
+_lib = None
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+
+class ZstdError(RuntimeError):
+    """Raised with the reference's error name (lib/common/error_private.c:14-62)."""
+
+    def __init__(self, code: int, name: str):
+        super().__init__(f"zstd_b200 error {code}: {name}")
+        self.code = code
+        self.name = name
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("kernel_ms", ctypes.c_float), ("match_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("launches", ctypes.c_uint), ("nbBlocks", ctypes.c_uint),
+                ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
+
+
+def lib() -> ctypes.CDLL:
+    """Load libzstd_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). zstd_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    L.ZSTD_compress.restype = _sz
+    L.ZSTD_compress.argtypes = [_vp, _sz, _vp, _sz, ctypes.c_int]
+    L.ZSTD_createCCtx.restype = _vp
+    L.ZSTD_createCCtx.argtypes = []
+    L.ZSTD_freeCCtx.restype = _sz
+    L.ZSTD_freeCCtx.argtypes = [_vp]
+    L.ZSTD_compressCCtx.restype = _sz
+    L.ZSTD_compressCCtx.argtypes = [_vp, _vp, _sz, _vp, _sz, ctypes.c_int]
+    L.ZSTD_compress_usingDict.restype = _sz
+    L.ZSTD_compress_usingDict.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _sz, ctypes.c_int]
+    L.ZSTD_compressBound.restype = _sz
+    L.ZSTD_compressBound.argtypes = [_sz]
+    L.ZSTD_isError.restype = ctypes.c_uint
+    L.ZSTD_isError.argtypes = [_sz]
+    L.ZSTD_getErrorName.restype = ctypes.c_char_p
+    L.ZSTD_getErrorName.argtypes = [_sz]
+    L.ZSTD_getErrorCode.restype = ctypes.c_int
+    L.ZSTD_getErrorCode.argtypes = [_sz]
+    for f in ("ZSTD_minCLevel", "ZSTD_maxCLevel", "ZSTD_defaultCLevel"):
+        getattr(L, f).restype = ctypes.c_int
+        getattr(L, f).argtypes = []
+    L.ZSTD_versionNumber.restype = ctypes.c_uint
+    L.ZSTD_versionString.restype = ctypes.c_char_p
+    L.ZSTDB200_compressDevice.restype = _sz
+    L.ZSTDB200_compressDevice.argtypes = [_vp, _vp, _sz, _vp, _sz, ctypes.c_int, _vp]
+    L.ZSTDB200_compressFrames.restype = _sz
+    L.ZSTDB200_compressFrames.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, ctypes.c_int, ctypes.c_int, _vp]
+    L.ZSTDB200_getLastStats.restype = None
+    L.ZSTDB200_getLastStats.argtypes = [_vp, ctypes.POINTER(Stats)]
+    L.ZSTDB200_setDevice.restype = ctypes.c_int
+    L.ZSTDB200_setDevice.argtypes = [ctypes.c_int]
+    L.ZSTDB200_deviceAvailable.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def _check(code: int) -> int:
+    L = lib()
+    if L.ZSTD_isError(code):
+        raise ZstdError(L.ZSTD_getErrorCode(code), L.ZSTD_getErrorName(code).decode())
+    return code
+
+
+def ZSTD_compressBound(src_size: int) -> int:
+    return lib().ZSTD_compressBound(src_size)
+
+
+def _buf(data) -> Tuple[ctypes.c_void_p, int, object]:
+    """(pointer, nbytes, keepalive) for bytes / bytearray / memoryview / numpy arrays."""
+    if isinstance(data, (bytes, bytearray)):
+        keep = (ctypes.c_char * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (ctypes.c_char * len(data)).from_buffer(data)
+        return ctypes.cast(keep, _vp), len(data), keep
+    mv = memoryview(data).cast("B")
+    keep = (ctypes.c_char * len(mv)).from_buffer(mv) if not mv.readonly else (ctypes.c_char * len(mv)).from_buffer_copy(mv)
+    return ctypes.cast(keep, _vp), len(mv), keep
+
+
+class ZSTD_CCtx:
+    """Reusable compression context (lib/zstd.h:259-264): owns the device workspace and a stream."""
+
+    def __init__(self, device: Optional[int] = None):
+        L = lib()
+        if device is not None:
+            L.ZSTDB200_setDevice(int(device))
+        self._h = L.ZSTD_createCCtx()
+        if not self._h:
+            raise MemoryError("ZSTD_createCCtx failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ZSTD_freeCCtx(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- reference-identical calls (host buffers) --
+    def compress(self, src, level: int = 3, dst_capacity: Optional[int] = None) -> bytes:
+        """ZSTD_compressCCtx: one complete frame (content size in header, no checksum)."""
+        p, n, keep = _buf(src)
+        cap = ZSTD_compressBound(n) if dst_capacity is None else dst_capacity
+        dst = ctypes.create_string_buffer(max(cap, 1))
+        r = _check(lib().ZSTD_compressCCtx(self._h, dst, cap, p, n, level))
+        return dst.raw[:r]
+
+    def compress_using_dict(self, src, dict_bytes, level: int = 3) -> bytes:
+        p, n, keep = _buf(src)
+        dp, dn, dkeep = _buf(dict_bytes)
+        cap = ZSTD_compressBound(n)
+        dst = ctypes.create_string_buffer(max(cap, 1))
+        r = _check(lib().ZSTD_compress_usingDict(self._h, dst, cap, p, n, dp, dn, level))
+        return dst.raw[:r]
+
+    # -- B200 extensions --
+    def compress_device(self, d_dst: int, dst_capacity: int, d_src: int, src_size: int, level: int = 3, stream: int = 0) -> int:
+        """One frame, device pointers (ints, e.g. torch.Tensor.data_ptr()).  Returns compressed size."""
+        return _check(lib().ZSTDB200_compressDevice(self._h, d_dst, dst_capacity, d_src, src_size, level, stream))
+
+    def compress_frames(self, dst: int, dst_capacity: int, src: int, offsets: Sequence[int], sizes: Sequence[int],
+                        level: int = 3, device_memory: bool = True, dict_bytes=None, stream: int = 0):
+        """Many independent frames in one call.  Returns (total_bytes, [compressed size per frame])."""
+        n = len(sizes)
+        offs = (_sz * n)(*offsets)
+        szs = (_sz * n)(*sizes)
+        csz = (_sz * n)()
+        dp, dn, dkeep = (None, 0, None) if dict_bytes is None else _buf(dict_bytes)
+        r = _check(lib().ZSTDB200_compressFrames(self._h, dst, dst_capacity, src, offs, szs, n, dp, dn, csz, level,
+                                                1 if device_memory else 0, stream))
+        return r, list(csz)
+
+    def stats(self) -> Stats:
+        s = Stats()
+        lib().ZSTDB200_getLastStats(self._h, ctypes.byref(s))
+        return s
+
+
+def ZSTD_compress(src, level: int = 3) -> bytes:
+    """lib/zstd.h:155 — temporary context, host buffers."""
+    p, n, keep = _buf(src)
+    cap = ZSTD_compressBound(n)
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = _check(lib().ZSTD_compress(dst, cap, p, n, level))
+    return dst.raw[:r]
+
+
+def device_available() -> bool:
+    try:
+        return bool(lib().ZSTDB200_deviceAvailable())
+    except (ImportError, OSError):
+        return False

@@ -1,0 +1,370 @@
+/* zb_api.cu — host driver + C ABI of libzstd_b200.so.
+ *
+ * Mirrors what the reference does around the per-block hot path:
+ *   ZSTD_compress / ZSTD_compressCCtx / ZSTD_compress_usingDict  (/root/reference/lib/compress/zstd_compress.c:5398-5440)
+ *   parameter derivation   ZSTD_getCParams_internal :7123-7146 + ZSTD_adjustCParams_internal :1465-1602 (compress/clevels.h:25-130)
+ *   block planning         ZSTD_compress_frameChunk :4527-4623 (here: all blocks of a call at once)
+ * and hands every block to the CUDA kernels (zb_match.cu, zb_literals.cu, zb_sequences.cu,
+ * zb_stitch.cu).  No compression work is done on the host; without a CUDA device every compress
+ * entry point fails with ZSTD_error_GENERIC.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/zstd_b200.h"
+#include "zb_common.h"
+#include "zb_kernels.h"
+
+static inline u32 hb32(u32 v) { return 31u - (u32)__builtin_clz(v); }
+static inline bool zb_isErr(size_t c) { return c > ZB_ERR(ZB_error_maxCode); }
+
+/* ------------------------------------------------------------------ parameters */
+typedef struct { u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; } ZbCParams;
+struct Row { u8 W, C, H, S, L, TL, strat; };
+/* compress/clevels.h:25-130, rows 0..4; strategies above dfast are out of scope: a level whose
+ * reference strategy is greedy or stronger is served by the strongest dfast row of its size class */
+static const Row kRows[4][5] = {
+    { {19,12,13,1,6,1,1}, {19,13,14,1,7,0,1}, {20,15,16,1,6,0,1}, {21,16,17,1,5,0,2}, {21,18,18,1,5,0,2} },
+    { {18,12,13,1,5,1,1}, {18,13,14,1,6,0,1}, {18,14,14,1,5,0,2}, {18,16,16,1,4,0,2}, {18,16,16,1,4,0,2} },
+    { {17,12,12,1,5,1,1}, {17,12,13,1,6,0,1}, {17,13,15,1,5,0,1}, {17,15,16,2,5,0,2}, {17,17,17,2,4,0,2} },
+    { {14,12,13,1,5,1,1}, {14,14,15,1,5,0,1}, {14,14,15,1,4,0,1}, {14,14,15,2,4,0,2}, {14,14,15,2,4,0,2} },
+};
+
+static ZbCParams zb_getCParams(int level, u64 srcSize, size_t dictSize)
+{
+    u64 const rSize = srcSize + dictSize;
+    u32 const tableID = (rSize <= 256u * 1024) + (rSize <= 128u * 1024) + (rSize <= 16u * 1024);
+    int const r = level == 0 ? 3 : (level < 0 ? 0 : (level > 4 ? 4 : level));
+    Row const x = kRows[tableID][r];
+    ZbCParams cp = { x.W, x.C, x.H, x.S, x.L, x.TL, x.strat };
+    if (level < 0) {
+        int const minLevel = -(int)ZB_BLOCK_MAX;                 /* ZSTD_minCLevel, zstd_compress.c:7038 */
+        cp.targetLength = (u32)(-(level < minLevel ? minLevel : level));
+    }
+    {   u64 const maxWindowResize = 1ull << 30;                  /* zstd_compress.c:1537-1547 */
+        if (srcSize <= maxWindowResize && dictSize <= maxWindowResize) {
+            u32 const tSize = (u32)(srcSize + dictSize);
+            u32 const srcLog = (tSize < (1u << 6)) ? 6 : hb32(tSize - 1) + 1;
+            if (cp.windowLog > srcLog) cp.windowLog = srcLog;
+        }
+        u32 dawl = cp.windowLog;                                  /* ZSTD_dictAndWindowLog :1432-1459 */
+        if (dictSize) {
+            u64 const windowSize = 1ull << cp.windowLog;
+            u64 const dictAndWindowSize = dictSize + windowSize;
+            if (windowSize >= dictSize + srcSize) dawl = cp.windowLog;
+            else if (dictAndWindowSize >= (1ull << 31)) dawl = 31;
+            else dawl = hb32((u32)dictAndWindowSize - 1) + 1;
+        }
+        if (cp.hashLog > dawl + 1) cp.hashLog = dawl + 1;
+        if (cp.chainLog > dawl) cp.chainLog -= (cp.chainLog - dawl);
+        if (cp.windowLog < 10) cp.windowLog = 10;                 /* ZSTD_WINDOWLOG_ABSOLUTEMIN */
+    }
+    return cp;
+}
+
+static ZbParams zb_makeParams(const ZbCParams& cp)
+{
+    ZbParams p; memset(&p, 0, sizeof(p));
+    p.strategy = cp.strategy;
+    p.windowLog = cp.windowLog;
+    p.mls = cp.minMatch < 4 ? 4 : (cp.minMatch > 8 ? 8 : cp.minMatch);
+    if (cp.strategy == 1) {
+        p.hashLog = cp.hashLog > 14 ? 14 : cp.hashLog;          /* 2^14 u16 = 32 KiB of shared memory per block */
+        p.stepSize = cp.targetLength + !cp.targetLength + 1;     /* zstd_fast.c:200 */
+    } else {
+        p.hashLog = cp.chainLog; p.longHashLog = cp.hashLog; p.stepSize = 1;
+    }
+    p.litDisabled = (cp.strategy == 1) && (cp.targetLength > 0); /* zstd_compress_internal.h:621-633 */
+    return p;
+}
+
+/* ------------------------------------------------------------------ context */
+static int g_device = -1;
+
+struct ZSTD_CCtx_s {
+    int device;
+    cudaStream_t stream;
+    /* per-block workspace */
+    size_t capBlocks, capFrames;
+    ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
+    u64* d_seqs; u8* d_lits; u8* d_body; u16* d_state;
+    u64* d_outOffsets; u64* d_frameSizes; u64* d_total;
+    /* host-pointer path staging */
+    u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
+    u64* h_total;                  /* pinned */
+    cudaEvent_t evStart, evK0, evK1, evKEnd, evEnd;
+    ZSTDB200_stats stats;
+};
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    if (getenv("ZSTDB200_DEBUG")) fprintf(stderr, "zstd_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return ZB_ERR(e_ == cudaErrorMemoryAllocation ? ZB_error_memory_allocation : ZB_error_GENERIC); } } while (0)
+
+extern "C" int ZSTDB200_setDevice(int device) { g_device = device; return 0; }
+extern "C" int ZSTDB200_deviceAvailable(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0;
+}
+
+extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
+{
+    ZSTD_CCtx* c = (ZSTD_CCtx*)calloc(1, sizeof(ZSTD_CCtx));
+    if (!c) return NULL;
+    c->device = -1;
+    return c;
+}
+
+static size_t zb_ctxInit(ZSTD_CCtx* c)
+{
+    if (c->device >= 0) { CK(cudaSetDevice(c->device)); return 0; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZB_ERR(ZB_error_GENERIC); }
+    int dev = g_device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    CK(cudaSetDevice(dev));
+    c->device = dev;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evK0)); CK(cudaEventCreate(&c->evK1));
+    CK(cudaEventCreate(&c->evKEnd)); CK(cudaEventCreate(&c->evEnd));
+    CK(cudaMallocHost(&c->h_total, 64));
+    CK(cudaMalloc(&c->d_total, 64));
+    return 0;
+}
+
+static void zb_freeWorkspace(ZSTD_CCtx* c)
+{
+    cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
+    cudaFree(c->d_body); cudaFree(c->d_state); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes);
+    c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
+    c->d_body = NULL; c->d_state = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL;
+    c->capBlocks = 0; c->capFrames = 0;
+}
+
+extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
+{
+    if (!c) return 0;
+    if (c->device >= 0) {
+        cudaSetDevice(c->device);
+        zb_freeWorkspace(c);
+        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_total);
+        cudaFreeHost(c->h_total);
+        cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
+        cudaEventDestroy(c->evKEnd); cudaEventDestroy(c->evEnd);
+        cudaStreamDestroy(c->stream);
+    }
+    free(c);
+    return 0;
+}
+
+static size_t zb_ensureWorkspace(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames)
+{
+    if (nbBlocks > c->capBlocks || nbFrames > c->capFrames) {
+        size_t const nb = nbBlocks > c->capBlocks ? nbBlocks : c->capBlocks;
+        size_t const nf = nbFrames > c->capFrames ? nbFrames : c->capFrames;
+        zb_freeWorkspace(c);
+        CK(cudaMalloc(&c->d_blocks, nb * sizeof(ZbBlock)));
+        CK(cudaMalloc(&c->d_frames, nf * sizeof(ZbFrame)));
+        CK(cudaMalloc(&c->d_meta, nb * sizeof(ZbBlockMeta)));
+        CK(cudaMalloc(&c->d_seqs, nb * ZB_SEQ_STRIDE * sizeof(u64)));
+        CK(cudaMalloc(&c->d_lits, nb * (size_t)ZB_LIT_STRIDE));
+        CK(cudaMalloc(&c->d_body, nb * (size_t)ZB_BODY_STRIDE));
+        CK(cudaMalloc(&c->d_state, nb * 3 * (size_t)ZB_STATE_STRIDE * sizeof(u16)));
+        CK(cudaMalloc(&c->d_outOffsets, (nb + 1) * sizeof(u64)));
+        CK(cudaMalloc(&c->d_frameSizes, nf * sizeof(u64)));
+        c->capBlocks = nb; c->capFrames = nf;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ core: frames already in device memory */
+static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacity, const u8* d_src,
+                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
+                                      const void* dict, size_t dictSize, size_t* cSizes, int level, cudaStream_t stream)
+{
+    if (dict && dictSize) return ZB_ERR(ZB_error_parameter_unsupported);   /* dictionary path: next §8 row */
+    std::vector<ZbBlock> blocks;
+    std::vector<ZbFrame> frames(nbFrames);
+    struct Group { ZbParams prm; u32 b0, b1; };
+    std::vector<Group> groups;
+    for (size_t f = 0; f < nbFrames; f++) {
+        u64 const fsz = frameSizes[f];
+        ZbCParams const cp = zb_getCParams(level, fsz, 0);
+        ZbParams const prm = zb_makeParams(cp);
+        size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
+        ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)blocks.size();
+        fr.windowLog = cp.windowLog; fr.dictID = 0;
+        u64 pos = 0;
+        do {
+            u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
+            ZbBlock b; b.srcOff = fr.srcOff + pos; b.size = (u32)bsz;
+            b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
+            b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
+            blocks.push_back(b);
+            pos += bsz;
+        } while (pos < fsz);
+        fr.nbBlocks = (u32)blocks.size() - fr.firstBlock;
+        frames[f] = fr;
+        if (groups.empty() || memcmp(&groups.back().prm, &prm, sizeof(prm)) != 0) { Group g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)blocks.size(); groups.push_back(g); }
+        else groups.back().b1 = (u32)blocks.size();
+    }
+    u32 const nbBlocks = (u32)blocks.size();
+    {   size_t const e = zb_ensureWorkspace(c, nbBlocks, nbFrames); if (zb_isErr(e)) return e; }
+
+    CK(cudaMemcpyAsync(c->d_blocks, blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(c->d_frames, frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(c->evK0, stream));
+    unsigned launches = 0;
+    for (size_t g = 0; g < groups.size(); g++) {
+        Group const& G = groups[g];
+        CK(zb_launch_match(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
+                           c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE, c->d_meta + G.b0, stream));
+        launches++;
+    }
+    CK(cudaEventRecord(c->evK1, stream));
+    for (size_t g = 0; g < groups.size(); g++) {
+        Group const& G = groups[g];
+        CK(zb_launch_literals(c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE,
+                              c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE, c->d_meta + G.b0, stream));
+        CK(zb_launch_sequences(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
+                               c->d_state + (size_t)G.b0 * 3 * ZB_STATE_STRIDE, c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE,
+                               c->d_meta + G.b0, stream));
+        launches += 2;
+    }
+    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, (u32)nbFrames, c->d_body, c->d_meta,
+                        c->d_outOffsets, c->d_frameSizes, c->d_total, d_dst, dstCapacity, stream));
+    launches += 2;
+    CK(cudaEventRecord(c->evKEnd, stream));
+    CK(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    if (cSizes) {
+        std::vector<u64> tmp(nbFrames);
+        CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (size_t f = 0; f < nbFrames; f++) cSizes[f] = (size_t)tmp[f];
+    } else CK(cudaStreamSynchronize(stream));
+    c->stats.launches = launches;
+    c->stats.nbBlocks = nbBlocks;
+    {   float ms = 0; cudaEventElapsedTime(&ms, c->evK0, c->evKEnd); c->stats.kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c->evK0, c->evK1); c->stats.match_ms = ms; }
+    u64 const total = c->h_total[0];
+    if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    return (size_t)total;
+}
+
+extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
+                                          const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                          size_t nbFrames, const void* dict, size_t dictSize,
+                                          size_t* cSizes, int level, int deviceMemory, void* streamv)
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (nbFrames == 0) return 0;
+    {   size_t const e = zb_ctxInit(c); if (zb_isErr(e)) return e; }
+    cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
+    memset(&c->stats, 0, sizeof(c->stats));
+    if (deviceMemory) {
+        size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
+        c->stats.total_ms = c->stats.kernel_ms;
+        return r;
+    }
+    /* host pointers: stage input and output through device buffers */
+    size_t inEnd = 0, bound = 0;
+    for (size_t f = 0; f < nbFrames; f++) {
+        if (frameOffsets[f] + frameSizes[f] > inEnd) inEnd = frameOffsets[f] + frameSizes[f];
+        bound += ZSTD_compressBound(frameSizes[f]) + 32;
+    }
+    size_t const outCap = dstCapacity < bound ? dstCapacity : bound;
+    if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
+    if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
+    CK(cudaEventRecord(c->evStart, stream));
+    if (inEnd) CK(cudaMemcpyAsync(c->d_in, src, inEnd, cudaMemcpyHostToDevice, stream));
+    size_t const r = zb_compressFramesDevice(c, c->d_out, outCap, c->d_in, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
+    if (zb_isErr(r)) return r;
+    CK(cudaMemcpyAsync(dst, c->d_out, r, cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(c->evEnd, stream));
+    CK(cudaStreamSynchronize(stream));
+    {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; }
+    c->stats.h2d_bytes = inEnd; c->stats.d2h_bytes = r;
+    return r;
+}
+
+extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity,
+                                          const void* d_src, size_t srcSize, int level, void* stream)
+{
+    size_t const off = 0;
+    return ZSTDB200_compressFrames(c, d_dst, dstCapacity, d_src, &off, &srcSize, 1, NULL, 0, NULL, level, 1, stream);
+}
+
+extern "C" void ZSTDB200_getLastStats(const ZSTD_CCtx* c, ZSTDB200_stats* out) { if (c && out) *out = c->stats; }
+
+/* ------------------------------------------------------------------ reference-identical entry points */
+extern "C" size_t ZSTD_compress_usingDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                                          const void* dict, size_t dictSize, int level)
+{
+    size_t const off = 0;
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
+    if (dstCapacity < 18) return ZB_ERR(ZB_error_dstSize_tooSmall);             /* ZSTD_FRAMEHEADERSIZE_MAX, zstd_compress.c:4643 */
+    return ZSTDB200_compressFrames(c, dst, dstCapacity, src, &off, &srcSize, 1, dict, dict ? dictSize : 0, NULL, level, 0, NULL);
+}
+extern "C" size_t ZSTD_compressCCtx(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
+{
+    return ZSTD_compress_usingDict(c, dst, dstCapacity, src, srcSize, NULL, 0, level);
+}
+extern "C" size_t ZSTD_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
+{
+    ZSTD_CCtx* c = ZSTD_createCCtx();                                            /* zstd_compress.c:5423-5440: temporary context */
+    if (!c) return ZB_ERR(ZB_error_memory_allocation);
+    size_t const r = ZSTD_compressCCtx(c, dst, dstCapacity, src, srcSize, level);
+    ZSTD_freeCCtx(c);
+    return r;
+}
+
+extern "C" size_t ZSTD_compressBound(size_t srcSize)                             /* lib/zstd.h:235 */
+{
+    if (srcSize >= (sizeof(size_t) == 8 ? 0xFF00FF00FF00FF00ULL : 0xFF00FF00U)) return ZB_ERR(ZB_error_srcSize_wrong);
+    return srcSize + (srcSize >> 8) + ((srcSize < (128u << 10)) ? (((128u << 10) - srcSize) >> 11) : 0);
+}
+extern "C" unsigned ZSTD_isError(size_t code) { return code > ZB_ERR(ZB_error_maxCode); }
+extern "C" int ZSTD_getErrorCode(size_t code) { return ZSTD_isError(code) ? (int)(0 - code) : 0; }
+extern "C" const char* ZSTD_getErrorName(size_t code)                            /* common/error_private.c:14-62 */
+{
+    switch (ZSTD_getErrorCode(code)) {
+    case 0: return "No error detected";
+    case 1: return "Error (generic)";
+    case 10: return "Unknown frame descriptor";
+    case 12: return "Version not supported";
+    case 14: return "Unsupported frame parameter";
+    case 16: return "Frame requires too much memory for decoding";
+    case 20: return "Data corruption detected";
+    case 22: return "Restored data doesn't match checksum";
+    case 24: return "Header of Literals' block doesn't respect format specification";
+    case 30: return "Dictionary is corrupted";
+    case 32: return "Dictionary mismatch";
+    case 34: return "Cannot create Dictionary from provided samples";
+    case 40: return "Unsupported parameter";
+    case 41: return "Unsupported combination of parameters";
+    case 42: return "Parameter is out of bound";
+    case 44: return "tableLog requires too much memory : unsupported";
+    case 46: return "Unsupported max Symbol Value : too large";
+    case 48: return "Specified maxSymbolValue is too small";
+    case 50: return "pledged buffer stability condition is not respected";
+    case 60: return "Operation not authorized at current processing stage";
+    case 62: return "Context should be init first";
+    case 64: return "Allocation error : not enough memory";
+    case 66: return "workSpace buffer is not large enough";
+    case 70: return "Destination buffer is too small";
+    case 72: return "Src size is incorrect";
+    case 74: return "Operation on NULL destination buffer";
+    case 80: return "Operation made no progress over multiple calls, due to output buffer being full";
+    case 82: return "Operation made no progress over multiple calls, due to input being empty";
+    default: return "Unspecified error code";
+    }
+}
+extern "C" int ZSTD_minCLevel(void) { return -(int)ZB_BLOCK_MAX; }                /* zstd_compress.c:7038 */
+extern "C" int ZSTD_maxCLevel(void) { return 22; }
+extern "C" int ZSTD_defaultCLevel(void) { return 3; }
+extern "C" unsigned ZSTD_versionNumber(void) { return 10506; }                    /* lib/zstd.h:107-110 */
+extern "C" const char* ZSTD_versionString(void) { return "1.5.6"; }

@@ -1,0 +1,91 @@
+/* zb_common.h — shared host/device definitions of the block-parallel plan.
+ *
+ * Unit of work = one zstd block (<= 128 KiB, ZSTD_BLOCKSIZE_MAX, /root/reference/lib/zstd.h:142).
+ * Every block is compressed independently of its neighbours: private hash table primed from the
+ * history bytes that precede it, encoder repcodes start invalid, fresh entropy tables.  The
+ * per-block state the reference carries across blocks (ZSTD_blockState_t,
+ * lib/compress/zstd_compress_internal.h:263-267) therefore does not exist here.
+ */
+#ifndef ZB_COMMON_H
+#define ZB_COMMON_H
+#include <stdint.h>
+#include <stddef.h>
+
+typedef uint8_t  u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define ZB_BLOCK_MAX     (128u << 10)
+#define ZB_PRIME_BYTES   (64u << 10)         /* history primed into a block's table (ZSTDMT overlap idea, zstdmt_compress.c:1182-1227) */
+#define ZB_MAX_SEQ       (ZB_BLOCK_MAX / 4)  /* every sequence carries a match of >= 4 bytes */
+#define ZB_SEQ_STRIDE    (ZB_MAX_SEQ + 8)    /* u64 per block */
+#define ZB_LIT_STRIDE    (ZB_BLOCK_MAX + 256)/* bytes per block */
+#define ZB_BODY_STRIDE   (ZB_BLOCK_MAX + 1024)/* staging for one compressed block body */
+#define ZB_STATE_STRIDE  (ZB_MAX_SEQ)        /* u16 per FSE stream per block */
+
+/* block types, /root/reference/lib/common/zstd_internal.h:90 */
+#define ZB_BT_RAW 0
+#define ZB_BT_RLE 1
+#define ZB_BT_COMPRESSED 2
+
+#define ZB_FLAG_FIRST 1u       /* first block of its frame */
+#define ZB_FLAG_LAST  2u       /* last block of its frame  */
+
+/* error codes = lib/zstd_errors.h:64-101 */
+#define ZB_ERR(code) ((size_t)-(long)(code))
+#define ZB_error_GENERIC 1
+#define ZB_error_prefix_unknown 10
+#define ZB_error_dictionary_corrupted 30
+#define ZB_error_dictionary_wrong 32
+#define ZB_error_parameter_unsupported 40
+#define ZB_error_tableLog_tooLarge 44
+#define ZB_error_maxSymbolValue_tooLarge 46
+#define ZB_error_stage_wrong 60
+#define ZB_error_memory_allocation 64
+#define ZB_error_workSpace_tooSmall 66
+#define ZB_error_dstSize_tooSmall 70
+#define ZB_error_srcSize_wrong 72
+#define ZB_error_dstBuffer_null 74
+#define ZB_error_maxCode 120
+
+typedef struct {
+    u64 srcOff;        /* block start, byte offset into the input buffer */
+    u32 size;          /* block size */
+    u32 histLen;       /* bytes of same-frame history visible before the block (<= ZB_PRIME_BYTES) */
+    u32 frame;         /* index into ZbFrame[] */
+    u32 flags;         /* ZB_FLAG_* */
+} ZbBlock;
+
+typedef struct {
+    u64 srcOff;        /* frame input start */
+    u64 srcSize;
+    u32 firstBlock;    /* index of its first ZbBlock */
+    u32 nbBlocks;
+    u32 windowLog;
+    u32 dictID;
+} ZbFrame;
+
+typedef struct {       /* produced on the device, one per block */
+    u32 nbSeq;
+    u32 litSize;       /* all literals of the block incl. the trailing run */
+    u32 litSecSize;    /* bytes of the literals section written at body[0..) */
+    u32 bodySize;      /* final payload size (compressed body, 1 for RLE, block size for raw) */
+    u32 type;          /* ZB_BT_* */
+    u32 forceRaw;      /* block too small to try (zstd_compress.c:3216) or entropy stage gave up */
+    u32 rleByte;
+    u32 pad;
+} ZbBlockMeta;
+
+typedef struct {
+    u32 strategy;      /* 1 = fast, 2 = dfast */
+    u32 mls;           /* bytes hashed by the (short) table: 4..8 */
+    u32 hashLog;       /* log2 entries, short table */
+    u32 longHashLog;   /* dfast: log2 entries of the 8-byte table */
+    u32 stepSize;      /* zstd_fast.c:200 */
+    u32 litDisabled;   /* zstd_compress_internal.h:621-633 */
+    u32 windowLog;
+    u32 pad;
+} ZbParams;
+
+#endif

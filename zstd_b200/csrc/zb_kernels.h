@@ -1,0 +1,36 @@
+/* zb_kernels.h — launch shims of the CUDA kernels (C linkage, called by the host driver zb_api.cu). */
+#ifndef ZB_KERNELS_H
+#define ZB_KERNELS_H
+#include <cuda_runtime.h>
+#include "zb_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* K1: match-finder.  One warp per block. */
+cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+                            u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaStream_t stream);
+
+/* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block. */
+cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+                               const u8* d_lits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
+
+/* K3: sequences section (codes, histograms, FSE tables, tANS bit-stream) + block-type decision. */
+cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+                                const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
+
+/* K4: stitch — per-block output sizes -> exclusive scan -> frame/block headers + payload copy.
+ * d_outOffsets has nbBlocks+1 entries; d_frameSizes has nbFrames entries; *d_total receives the
+ * total number of bytes the call produces (even when it exceeds dstCapacity: nothing is written
+ * past dst + dstCapacity). */
+cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks,
+                             const ZbFrame* d_frames, u32 nbFrames,
+                             const u8* d_body, const ZbBlockMeta* d_meta,
+                             u64* d_outOffsets, u64* d_frameSizes, u64* d_total,
+                             u8* d_dst, u64 dstCapacity, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,292 @@
+/* zb_sequences.cu — K3: sequences section of one block per CTA + final block-type decision.
+ *
+ * Replaces, for a fresh entropy state, ZSTD_buildSequencesStatistics
+ * (/root/reference/lib/compress/zstd_compress.c:2755-2873), ZSTD_seqToCodes (:2686-2712),
+ * ZSTD_selectEncodingType / ZSTD_buildCTable (zstd_compress_sequences.c:157-288),
+ * ZSTD_encodeSequences_body (:291-382) and the block-level checks of
+ * ZSTD_entropyCompressSeqStore (zstd_compress.c:2987-2993, :3025-3028) and
+ * ZSTD_compressBlock_internal (:4365-4376).
+ *
+ *   1. LL/OF/ML codes + three histograms: all threads, shared-memory atomics
+ *   2. per stream (three threads in three different warps): encoding type, normalised counts,
+ *      NCount header, FSE table — serial, <=53 symbols, shared memory
+ *   3. tANS state chains: state(i) depends on state(i+1) (common/fse.h:463-470), so each of the three
+ *      chains is walked backwards by one thread; it records (bits, nbBits) per sequence
+ *   4. all threads: per-sequence bit counts -> suffix sum -> bit offsets -> pack (edge words atomicOr)
+ */
+#include "zb_entropy.cuh"
+#include "zb_kernels.h"
+#include "zb_bitpack.cuh"
+
+#define SEQ_THREADS 256
+#define MaxLL 35
+#define MaxML 52
+#define MaxOff 31
+#define DefaultMaxOff 28
+#define LLFSELog 9
+#define MLFSELog 9
+#define OffFSELog 8
+
+/* format constants, common/zstd_internal.h:123-168 (RFC 8878) */
+__constant__ u8 c_LL_bits[MaxLL + 1] = { 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 1,1,1,1,2,2,3,3, 4,6,7,8,9,10,11,12, 13,14,15,16 };
+__constant__ u8 c_ML_bits[MaxML + 1] = { 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0,
+                                         1,1,1,1,2,2,3,3, 4,4,5,7,8,9,10,11, 12,13,14,15,16 };
+__constant__ short c_LL_defaultNorm[MaxLL + 1] = { 4,3,2,2,2,2,2,2, 2,2,2,2,2,1,1,1, 2,2,2,2,2,2,2,2, 2,3,2,1,1,1,1,1, -1,-1,-1,-1 };
+__constant__ short c_ML_defaultNorm[MaxML + 1] = { 1,4,3,2,2,2,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1,
+                                                   1,1,1,1,1,1,1,1, 1,1,1,1,1,1,-1,-1, -1,-1,-1,-1,-1 };
+__constant__ short c_OF_defaultNorm[DefaultMaxOff + 1] = { 1,1,1,1,1,1,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, -1,-1,-1,-1,-1 };
+
+/* closed forms of the code tables in zstd_compress_internal.h:520-549 */
+__device__ __forceinline__ u32 zbd_ll_code(u32 ll)
+{
+    if (ll > 63u) return zb_hb32(ll) + 19u;
+    if (ll < 16u) return ll;
+    if (ll < 24u) return 16u + ((ll - 16u) >> 1);
+    if (ll < 32u) return 20u + ((ll - 24u) >> 2);
+    if (ll < 48u) return 22u + ((ll - 32u) >> 3);
+    return 24u;
+}
+__device__ __forceinline__ u32 zbd_ml_code(u32 mlBase)
+{
+    if (mlBase > 127u) return zb_hb32(mlBase) + 36u;
+    if (mlBase < 32u) return mlBase;
+    if (mlBase < 40u) return 32u + ((mlBase - 32u) >> 1);
+    if (mlBase < 48u) return 36u + ((mlBase - 40u) >> 2);
+    if (mlBase < 64u) return 38u + ((mlBase - 48u) >> 3);
+    if (mlBase < 96u) return 40u + ((mlBase - 64u) >> 4);
+    return 42u;
+}
+struct ZbdSeq { u32 offBase, litLen, mlBase, llc, ofc, mlc; };
+__device__ __forceinline__ ZbdSeq zbd_unpack(u64 q)
+{
+    ZbdSeq s;
+    s.offBase = (u32)(q & 0xFFFFFFu);
+    s.litLen = (u32)((q >> 24) & 0x3FFFFu);
+    s.mlBase = (u32)((q >> 42) & 0x3FFFFu) - 3u;
+    s.llc = zbd_ll_code(s.litLen);
+    s.ofc = zb_hb32(s.offBase);
+    s.mlc = zbd_ml_code(s.mlBase);
+    return s;
+}
+
+enum { set_basic = 0, set_rle = 1, set_compressed = 2 };
+
+/* zstd_compress_sequences.c:157-240, branch strategy < ZSTD_lazy with repeatMode == none */
+__device__ __forceinline__ u32 zbd_selectEncodingType(u32 mostFrequent, u32 nbSeq, u32 defaultNormLog, bool defaultAllowed, u32 strategy)
+{
+    if (mostFrequent == nbSeq) return (defaultAllowed && nbSeq <= 2u) ? set_basic : set_rle;
+    if (defaultAllowed) {
+        u32 const mult = 10u - strategy;
+        u32 const dynamicFse_nbSeq_min = ((1u << defaultNormLog) * mult) >> 3;
+        if (nbSeq < dynamicFse_nbSeq_min || mostFrequent < (nbSeq >> (defaultNormLog - 1u))) return set_basic;
+    }
+    return set_compressed;
+}
+
+struct ZbdStreamWork {
+    u32 count[64];
+    short norm[64];
+    u8  nc[136];            /* NCount bytes (or the single rle symbol) */
+    u8  scratch[512 + 136];
+    u32 ncSize;
+    u32 type;
+    u32 finalState;
+    u32 err;
+};
+
+__global__ void __launch_bounds__(SEQ_THREADS)
+zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm,
+                    const u64* __restrict__ seqs, u16* __restrict__ stateBits,
+                    u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
+{
+    __shared__ ZbdFseCTable ct[3];                 /* 0 = LL, 1 = OF, 2 = ML */
+    __shared__ ZbdStreamWork wk[3];
+    __shared__ u32 chunkBits[SEQ_THREADS];
+    __shared__ u32 sh_cSize, sh_hdrEnd, sh_streamSize;
+
+    u32 const tid = threadIdx.x;
+    u32 const b = blockIdx.x;
+    ZbBlockMeta const m = meta[b];
+    ZbBlock const bd = blocks[b];
+    if (m.forceRaw) return;
+    u32 const nbSeq = m.nbSeq;
+    const u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
+    u16* const myst = stateBits + (size_t)b * 3u * ZB_STATE_STRIDE;
+    u8* const out = body + (size_t)b * ZB_BODY_STRIDE;
+    u32 op = m.litSecSize;
+
+    /* nbSeq header, zstd_compress.c:2937-2947 */
+    u32 const nbSeqHdr = nbSeq < 128u ? 1u : (nbSeq < 0x7F00u ? 2u : 3u);
+    if (tid == 0) {
+        if (nbSeq < 128u) out[op] = (u8)nbSeq;
+        else if (nbSeq < 0x7F00u) { out[op] = (u8)((nbSeq >> 8) + 0x80u); out[op + 1] = (u8)nbSeq; }
+        else { out[op] = 0xFF; out[op + 1] = (u8)(nbSeq - 0x7F00u); out[op + 2] = (u8)((nbSeq - 0x7F00u) >> 8); }
+    }
+    op += nbSeqHdr;
+    u32 cSize;
+    if (nbSeq == 0) {
+        cSize = op;
+    } else {
+        /* ---- 1. codes + histograms ---- */
+        if (tid < 192u) wk[tid >> 6].count[tid & 63u] = 0;
+        __syncthreads();
+        for (u32 i = tid; i < nbSeq; i += SEQ_THREADS) {
+            ZbdSeq const s = zbd_unpack(myseq[i]);
+            atomicAdd(&wk[0].count[s.llc], 1u);
+            atomicAdd(&wk[1].count[s.ofc], 1u);
+            atomicAdd(&wk[2].count[s.mlc], 1u);
+        }
+        __syncthreads();
+        /* ---- 2. per-stream tables: threads 0, 32, 64 ---- */
+        if ((tid & 31u) == 0 && tid < 96u) {
+            u32 const st = tid >> 5;
+            ZbdStreamWork* const w = &wk[st];
+            u32 const maxAll = st == 0 ? MaxLL : (st == 1 ? MaxOff : MaxML);
+            u32 max = maxAll; while (w->count[max] == 0) max--;
+            u32 mostFrequent = 0; for (u32 s = 0; s <= max; s++) mostFrequent = w->count[s] > mostFrequent ? w->count[s] : mostFrequent;
+            u32 const defLog = st == 1 ? 5u : 6u;
+            bool const defAllowed = st == 1 ? (max <= DefaultMaxOff) : true;
+            u32 const type = zbd_selectEncodingType(mostFrequent, nbSeq, defLog, defAllowed, prm.strategy);
+            ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
+            u32 const lastCode = st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc);
+            w->type = type; w->err = 0; w->ncSize = 0;
+            if (type == set_rle) {                                   /* zstd_compress_sequences.c:254-259 */
+                ZbdSeq const first = zbd_unpack(myseq[0]);
+                u32 const sym = st == 0 ? first.llc : (st == 1 ? first.ofc : first.mlc);
+                zbd_fse_buildCTable_rle(&ct[st], max);
+                w->nc[0] = (u8)sym; w->ncSize = 1;
+            } else if (type == set_basic) {
+                const short* dn = st == 0 ? c_LL_defaultNorm : (st == 1 ? c_OF_defaultNorm : c_ML_defaultNorm);
+                u32 const dmax = st == 0 ? MaxLL : (st == 1 ? DefaultMaxOff : MaxML);
+                for (u32 s = 0; s <= dmax; s++) w->norm[s] = dn[s];
+                zbd_fse_buildCTable(&ct[st], w->norm, dmax, defLog, w->scratch);
+            } else {
+                u32 const FSELog = st == 1 ? OffFSELog : (st == 0 ? LLFSELog : MLFSELog);
+                u32 nbSeq_1 = nbSeq;
+                u32 const tableLog = zbd_fse_optimalTableLog(FSELog, nbSeq, max, 2);
+                if (w->count[lastCode] > 1u) { w->count[lastCode]--; nbSeq_1--; }     /* :271-274 */
+                u32 const r = zbd_fse_normalize(w->norm, tableLog, w->count, nbSeq_1, max, nbSeq_1 >= 2048u);
+                if (r == ZBD_ERR || r == 0) w->err = 1;
+                else {
+                    u32 const ncs = zbd_fse_writeNCount(w->nc, w->norm, max, tableLog);
+                    if (ncs == ZBD_ERR) w->err = 1;
+                    else { w->ncSize = ncs; zbd_fse_buildCTable(&ct[st], w->norm, max, tableLog, w->scratch); }
+                }
+            }
+        }
+        __syncthreads();
+        bool const err = wk[0].err | wk[1].err | wk[2].err;
+        if (err) { if (tid == 0) { meta[b].type = ZB_BT_RAW; meta[b].bodySize = bd.size; } return; }
+
+        /* ---- 3. state chains: threads 0, 32, 64 ---- */
+        if ((tid & 31u) == 0 && tid < 96u) {
+            u32 const st = tid >> 5;
+            const ZbdFseCTable* const t = &ct[st];
+            u16* const rec = myst + (size_t)st * ZB_STATE_STRIDE;
+            ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
+            u32 state = zbd_fse_initState2(t, st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc));
+            for (u32 i = nbSeq - 1; i-- > 0; ) {
+                ZbdSeq const s = zbd_unpack(myseq[i]);
+                u32 bits, nb;
+                state = zbd_fse_step(t, state, st == 0 ? s.llc : (st == 1 ? s.ofc : s.mlc), &bits, &nb);
+                rec[i] = (u16)(bits | (nb << 12));
+            }
+            wk[st].finalState = state;
+        }
+        __syncthreads();
+
+        /* ---- section header bytes: seqHead + NCounts (zstd_compress.c:2955-2966) ---- */
+        u32 const ncTotal = wk[0].ncSize + wk[1].ncSize + wk[2].ncSize;
+        u32 const hdrEnd = op + 1u + ncTotal;        /* first byte of the bit-stream */
+        u32 lastCountSize = 0;
+        if (wk[0].type == set_compressed) lastCountSize = wk[0].ncSize;
+        if (wk[1].type == set_compressed) lastCountSize = wk[1].ncSize;
+        if (wk[2].type == set_compressed) lastCountSize = wk[2].ncSize;
+
+        /* ---- 4. per-sequence bit counts, suffix sums ---- */
+        u32 const cs = (nbSeq + SEQ_THREADS - 1u) / SEQ_THREADS;
+        u32 const cBeg = min(tid * cs, nbSeq), cEnd = min((tid + 1u) * cs, nbSeq);
+        u32 bits = 0;
+        for (u32 i = cBeg; i < cEnd; i++) {
+            ZbdSeq const s = zbd_unpack(myseq[i]);
+            bits += c_LL_bits[s.llc] + c_ML_bits[s.mlc] + s.ofc;
+            if (i + 1u < nbSeq) bits += (myst[i] >> 12) + (myst[ZB_STATE_STRIDE + i] >> 12) + (myst[2u * ZB_STATE_STRIDE + i] >> 12);
+        }
+        chunkBits[tid] = bits;
+        __syncthreads();
+        u32 bitOff = 0;
+        for (u32 k = tid + 1u; k < SEQ_THREADS; k++) bitOff += chunkBits[k];
+        if (tid == 0) {
+            u32 const totalBits = bitOff + bits + ct[2].tableLog + ct[1].tableLog + ct[0].tableLog + 1u;
+            sh_streamSize = (totalBits + 7u) >> 3;
+        }
+        __syncthreads();
+        u32 const streamSize = sh_streamSize;
+        cSize = hdrEnd + streamSize;
+        /* the body staging area is ZB_BODY_STRIDE bytes; a block that large is emitted raw anyway */
+        bool const fits = (cSize + 16u <= ZB_BODY_STRIDE);
+        if (fits) {
+            /* zero the bit-stream words (the first may share bytes with the headers: keep those) */
+            u32 const w0 = hdrEnd >> 2, w1 = (cSize + 3u) >> 2;
+            u32* const ow = reinterpret_cast<u32*>(out);
+            for (u32 i = w0 + 1u + tid; i < w1; i += SEQ_THREADS) ow[i] = 0;
+            if (tid == 0) {
+                for (u32 i = hdrEnd; i < min((w0 + 1u) << 2, cSize + 4u); i++) out[i] = 0;
+                u8* p = out + op;
+                *p++ = (u8)((wk[0].type << 6) + (wk[1].type << 4) + (wk[2].type << 2));
+                for (u32 st = 0; st < 3; st++) for (u32 i = 0; i < wk[st].ncSize; i++) *p++ = wk[st].nc[i];
+            }
+            __syncthreads();
+            ZbdParW pw; zbd_pw_init(&pw, ow, (u64)hdrEnd * 8u + bitOff);
+            for (u32 i = cEnd; i-- > cBeg; ) {                 /* last sequence first, zstd_compress_sequences.c:311-370 */
+                ZbdSeq const s = zbd_unpack(myseq[i]);
+                if (i + 1u < nbSeq) {
+                    u32 const rOF = myst[ZB_STATE_STRIDE + i], rML = myst[2u * ZB_STATE_STRIDE + i], rLL = myst[i];
+                    zbd_pw_add(&pw, rOF & 0xFFFu, rOF >> 12);
+                    zbd_pw_add(&pw, rML & 0xFFFu, rML >> 12);
+                    zbd_pw_add(&pw, rLL & 0xFFFu, rLL >> 12);
+                }
+                u32 const llb = c_LL_bits[s.llc], mlb = c_ML_bits[s.mlc];
+                zbd_pw_add(&pw, s.litLen & ((1u << llb) - 1u), llb);
+                zbd_pw_add(&pw, s.mlBase & ((1u << mlb) - 1u), mlb);
+                zbd_pw_add(&pw, s.offBase & ((1u << s.ofc) - 1u), s.ofc);
+            }
+            if (tid == 0) {                                    /* :372-376 + end mark */
+                zbd_pw_add(&pw, wk[2].finalState & ((1u << ct[2].tableLog) - 1u), ct[2].tableLog);
+                zbd_pw_add(&pw, wk[1].finalState & ((1u << ct[1].tableLog) - 1u), ct[1].tableLog);
+                zbd_pw_add(&pw, wk[0].finalState & ((1u << ct[0].tableLog) - 1u), ct[0].tableLog);
+                zbd_pw_add(&pw, 1u, 1u);
+            }
+            zbd_pw_finish(&pw);
+        }
+        if (!fits || (lastCountSize && (lastCountSize + streamSize) < 4u)) cSize = 0;    /* zstd_compress.c:2987-2993 */
+    }
+
+    /* ---- block-level decision (zstd_compress.c:3025-3028, :4365-4376) ---- */
+    {   u32 const maxCSize = bd.size - ((bd.size >> 6) + 2u);
+        if (cSize >= maxCSize) cSize = 0;
+    }
+    bool rle = false;
+    if (!(bd.flags & ZB_FLAG_FIRST) && cSize < 25u) {
+        const u8* const bsrc = src + bd.srcOff;
+        u8 const v0 = bsrc[0];
+        int diff = 0;
+        for (u32 i = tid; i < bd.size; i += SEQ_THREADS) diff |= (bsrc[i] != v0);
+        rle = !__syncthreads_or(diff);
+    }
+    if (tid == 0) {
+        ZbBlockMeta mm = m;
+        if (rle) { mm.type = ZB_BT_RLE; mm.bodySize = 1; mm.rleByte = src[bd.srcOff]; }
+        else if (cSize == 0) { mm.type = ZB_BT_RAW; mm.bodySize = bd.size; }
+        else { mm.type = ZB_BT_COMPRESSED; mm.bodySize = cSize; }
+        meta[b] = mm;
+    }
+}
+
+extern "C" cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+                                           const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream)
+{
+    if (nbBlocks == 0) return cudaSuccess;
+    zb_sequences_kernel<<<nbBlocks, SEQ_THREADS, 0, stream>>>(d_src, d_blocks, *prm, d_seqs, d_stateBits, d_body, d_meta);
+    return cudaGetLastError();
+}

@@ -1,0 +1,141 @@
+/* zb_stitch.cu — K4: assemble frames from independently compressed blocks.
+ *
+ * The reference's block loop (ZSTD_compress_frameChunk, /root/reference/lib/compress/zstd_compress.c:4527-4623)
+ * appends blocks one after the other; here all blocks of a call were compressed at once, so the
+ * frame is assembled by (a) computing every block's output size (frame header for the first block
+ * of a frame, :4626-4672; 3-byte block header, :4586-4590; payload), (b) an exclusive prefix sum,
+ * (c) one CTA per block copying header + payload to its final place.
+ */
+#include "zb_device.cuh"
+#include "zb_kernels.h"
+
+/* zstd_compress.c:4626-4672, contentSizeFlag = 1, no checksum.  Returns header size (<= 18). */
+__device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, bool write)
+{
+    u32 const dictIDSizeCode = (dictID > 0) + (dictID >= 256) + (dictID >= 65536);
+    bool const singleSegment = ((u64)1 << windowLog) >= srcSize;
+    u32 const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256) + (srcSize >= 0xFFFFFFFFull);
+    u8 h[18]; u32 pos = 0;
+    h[pos++] = 0x28; h[pos++] = 0xB5; h[pos++] = 0x2F; h[pos++] = 0xFD;          /* ZSTD_MAGICNUMBER 0xFD2FB528 */
+    h[pos++] = (u8)(dictIDSizeCode + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));
+    if (!singleSegment) h[pos++] = (u8)((windowLog - 10u) << 3);
+    if (dictIDSizeCode == 1) h[pos++] = (u8)dictID;
+    else if (dictIDSizeCode == 2) { h[pos++] = (u8)dictID; h[pos++] = (u8)(dictID >> 8); }
+    else if (dictIDSizeCode == 3) { for (int i = 0; i < 4; i++) h[pos++] = (u8)(dictID >> (8 * i)); }
+    if (fcsCode == 0) { if (singleSegment) h[pos++] = (u8)srcSize; }
+    else if (fcsCode == 1) { u32 const v = (u32)(srcSize - 256); h[pos++] = (u8)v; h[pos++] = (u8)(v >> 8); }
+    else if (fcsCode == 2) { for (int i = 0; i < 4; i++) h[pos++] = (u8)(srcSize >> (8 * i)); }
+    else { for (int i = 0; i < 8; i++) h[pos++] = (u8)(srcSize >> (8 * i)); }
+    if (write) for (u32 i = 0; i < pos; i++) dst[i] = h[i];
+    return pos;
+}
+
+#define SCAN_THREADS 1024
+
+/* single-CTA exclusive scan over per-block output sizes (nbBlocks is a few thousand per wave) */
+__global__ void __launch_bounds__(SCAN_THREADS)
+zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames, u32 nbFrames,
+                     const ZbBlockMeta* __restrict__ meta, u64* __restrict__ outOffsets,
+                     u64* __restrict__ frameSizes, u64* __restrict__ total)
+{
+    __shared__ u64 part[SCAN_THREADS];
+    u32 const tid = threadIdx.x;
+    u32 const per = (nbBlocks + SCAN_THREADS - 1u) / SCAN_THREADS;
+    u32 const beg = min(tid * per, nbBlocks), end = min((tid + 1u) * per, nbBlocks);
+    u64 sum = 0;
+    for (u32 i = beg; i < end; i++) {
+        ZbBlock const bd = blocks[i];
+        u64 sz = 3u + meta[i].bodySize;
+        if (bd.flags & ZB_FLAG_FIRST) { ZbFrame const f = frames[bd.frame]; sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, false); }
+        sum += sz;
+    }
+    part[tid] = sum;
+    __syncthreads();
+    /* Hillis-Steele inclusive scan over the 1024 partial sums */
+    for (u32 off = 1; off < SCAN_THREADS; off <<= 1) {
+        u64 const v = (tid >= off) ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    u64 run = (tid == 0) ? 0 : part[tid - 1];
+    for (u32 i = beg; i < end; i++) {
+        ZbBlock const bd = blocks[i];
+        u64 sz = 3u + meta[i].bodySize;
+        if (bd.flags & ZB_FLAG_FIRST) { ZbFrame const f = frames[bd.frame]; sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, false); }
+        outOffsets[i] = run;
+        run += sz;
+    }
+    if (tid == SCAN_THREADS - 1) { outOffsets[nbBlocks] = part[SCAN_THREADS - 1]; *total = part[SCAN_THREADS - 1]; }
+    __syncthreads();
+    __threadfence_block();
+    /* per-frame compressed sizes: offsets are final after the barrier below */
+    __syncthreads();
+    for (u32 f = tid; f < nbFrames; f += SCAN_THREADS) {
+        ZbFrame const fr = frames[f];
+        frameSizes[f] = outOffsets[fr.firstBlock + fr.nbBlocks] - outOffsets[fr.firstBlock];
+    }
+}
+
+#define COPY_THREADS 256
+__global__ void __launch_bounds__(COPY_THREADS)
+zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, const ZbFrame* __restrict__ frames,
+               const u8* __restrict__ body, const ZbBlockMeta* __restrict__ meta,
+               const u64* __restrict__ outOffsets, u8* __restrict__ dst, u64 dstCapacity)
+{
+    u32 const b = blockIdx.x, tid = threadIdx.x;
+    ZbBlock const bd = blocks[b];
+    ZbBlockMeta const m = meta[b];
+    u64 const o0 = outOffsets[b], o1 = outOffsets[b + 1];
+    if (o1 > dstCapacity) return;                                   /* never write past dst + dstCapacity */
+    u8* out = dst + o0;
+    u32 hdr = 0;
+    if (bd.flags & ZB_FLAG_FIRST) {
+        ZbFrame const f = frames[bd.frame];
+        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, tid == 0);
+    }
+    out += hdr;
+    u32 const lastBlock = (bd.flags & ZB_FLAG_LAST) ? 1u : 0u;
+    if (tid == 0) {                                                 /* zstd_compress.c:4586-4590, zstd_compress_internal.h:586-610 */
+        u32 const h24 = (m.type == ZB_BT_COMPRESSED) ? lastBlock + (2u << 1) + (m.bodySize << 3)
+                      : (m.type == ZB_BT_RLE)        ? lastBlock + (1u << 1) + (bd.size << 3)
+                                                     : lastBlock + (0u << 1) + (bd.size << 3);
+        out[0] = (u8)h24; out[1] = (u8)(h24 >> 8); out[2] = (u8)(h24 >> 16);
+        if (m.type == ZB_BT_RLE) out[3] = (u8)m.rleByte;
+    }
+    out += 3;
+    if (m.type == ZB_BT_RLE) return;
+    const u8* const from = (m.type == ZB_BT_COMPRESSED) ? body + (size_t)b * ZB_BODY_STRIDE : src + bd.srcOff;
+    u32 const n = m.bodySize;
+    /* 16-byte vector body where source and destination can both be aligned: source is read through
+     * unaligned 32-bit words, destination peeled to 16-byte alignment */
+    u32 const head = (u32)((16u - ((uintptr_t)out & 15u)) & 15u);
+    u32 const headN = head < n ? head : n;
+    if (tid < headN) out[tid] = from[tid];
+    u32 const nvec = (n - headN) / 16u;
+    uint4* const o4 = reinterpret_cast<uint4*>(out + headN);
+    const u8* const f0 = from + headN;
+    if ((((uintptr_t)f0) & 15u) == 0) {
+        const uint4* const f4 = reinterpret_cast<const uint4*>(f0);
+        for (u32 i = tid; i < nvec; i += COPY_THREADS) o4[i] = f4[i];
+    } else {
+        for (u32 i = tid; i < nvec; i += COPY_THREADS) {
+            const u8* p = f0 + (size_t)i * 16u;
+            uint4 v; v.x = zb_ld32u(p); v.y = zb_ld32u(p + 4); v.z = zb_ld32u(p + 8); v.w = zb_ld32u(p + 12);
+            o4[i] = v;
+        }
+    }
+    for (u32 i = headN + nvec * 16u + tid; i < n; i += COPY_THREADS) out[i] = from[i];
+}
+
+extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks,
+                                        const ZbFrame* d_frames, u32 nbFrames,
+                                        const u8* d_body, const ZbBlockMeta* d_meta,
+                                        u64* d_outOffsets, u64* d_frameSizes, u64* d_total,
+                                        u8* d_dst, u64 dstCapacity, cudaStream_t stream)
+{
+    if (nbBlocks == 0) return cudaSuccess;
+    zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, nbFrames, d_meta, d_outOffsets, d_frameSizes, d_total);
+    zb_copy_kernel<<<nbBlocks, COPY_THREADS, 0, stream>>>(d_src, d_blocks, d_frames, d_body, d_meta, d_outOffsets, d_dst, dstCapacity);
+    return cudaGetLastError();
+}
