@@ -12,8 +12,9 @@
  *   - every block is parsed independently: private table, primed from the `primeBytes` of input
  *     preceding the block (the ZSTDMT overlap idea, zstdmt_compress.c:726-731), encoder repcodes
  *     start invalid (zstdmt_compress.c:737-742);
- *   - 32 probe positions ("lanes") are evaluated per step against the table state at the start
- *     of the step; the lowest matching position wins; only lanes up to the winner insert;
+ *   - candidate lookup is decoupled from the parse: a table walk inserts positions on a fixed
+ *     pattern and records, for every position, the distance to its candidate (phase 1); the greedy
+ *     selection (phase 2) then evaluates 32 probe positions ("lanes") per step, lowest hit wins;
  *   - table entries are 16-bit positions modulo 64 KiB (reach 65535 bytes), which is what lets
  *     7 blocks per SM keep their tables in shared memory.
  */
@@ -57,13 +58,20 @@ void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
     plan->windowLog = cp->windowLog;
     plan->mls = cp->minMatch < 4 ? 4 : (cp->minMatch > 8 ? 8 : cp->minMatch);
     if (cp->strategy == 1) {
-        plan->hashLog = cp->hashLog > 14 ? 14 : cp->hashLog;          /* 32 KiB of u16 per block */
-        plan->longHashLog = 0;
+        /* Every position pair of the pattern is inserted (also inside matches, where the reference
+         * inserts only 2 positions per match, zstd_fast.c:403-408), so a table of half the
+         * reference's size holds as many useful candidates: measured size delta vs the reference
+         * with (hashLog-1, period 4): -0.12 % (P50, level 1); (hashLog, period 8): -0.04 % (P30, --fast=3). */
         plan->stepSize = cp->targetLength + !cp->targetLength + 1;     /* zstd_fast.c:200 */
+        if (cp->targetLength == 0) { plan->hashLog = cp->hashLog - 1; plan->insPeriod = 4; }
+        else { plan->hashLog = cp->hashLog; plan->insPeriod = 2 * plan->stepSize < 4 ? 4 : 2 * plan->stepSize; }
+        if (plan->hashLog > 14) plan->hashLog = 14;                    /* 32 KiB of u16 per block */
+        plan->longHashLog = 0;
     } else {
         plan->hashLog = cp->chainLog;                                  /* short table, zstd_double_fast.c:113 */
         plan->longHashLog = cp->hashLog;
         plan->stepSize = 1;
+        plan->insPeriod = 4;
     }
     plan->primeBytes = ZB_PRIME_DEFAULT;
     if (plan->primeBytes > (1u << cp->windowLog)) plan->primeBytes = 1u << cp->windowLog;
@@ -71,17 +79,27 @@ void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
     plan->litCompressionDisabled = (cp->strategy == 1) && (cp->targetLength > 0);
 }
 
-/* ---- 16-bit modular table ---- */
-typedef struct { u16* t; u32 hashLog; size_t base; } ztable;   /* base = lowLimit (absolute) */
-
-static inline void zt_put(ztable* z, u32 h, size_t pos) { z->t[h] = (u16)(pos - z->base); }
-/* most recent position q < pos with (q - base) == stored (mod 65536); (size_t)-1 if none */
-static inline size_t zt_get(const ztable* z, u32 h, size_t pos)
+/* ---- phase 1: parse-independent candidate table walk ------------------------------------------
+ * dist[i] (i = position - blockStart) = distance to the most recent INSERTED earlier position of the
+ * visible history with the same hash, 0 if none.  Positions are inserted on a fixed pattern of the
+ * frame position ((pos % insPeriod) < 2 : the reference also probes/inserts position pairs spaced by
+ * `step`, zstd_fast.c:225-229), independent of the parse, which is what lets the walk run ahead of —
+ * and in parallel with — the greedy selection.  Table entries are 16-bit positions modulo 64 KiB
+ * relative to the oldest visible byte (reach 65535). */
+static void candidates_walk(const u8* frame, size_t lowLimit, size_t bs, size_t be,
+                            u32 mls, u32 hlog, u32 insPeriod, u16* dist)
 {
-    u32 const rel = (u32)(pos - z->base);
-    u32 const dist = (rel - z->t[h]) & 0xFFFFu;
-    if (dist == 0 || dist > rel) return (size_t)-1;
-    return pos - dist;
+    u16* const table = (u16*)calloc((size_t)1 << hlog, sizeof(u16));
+    for (size_t p = lowLimit; p + 8 <= be; p++) {
+        u32 const h = zb_hash(rd64(frame + p), mls, hlog);
+        u32 const rel = (u32)(p - lowLimit);
+        u32 d = (rel - table[h]) & 0xFFFFu;
+        if (d == 0 || d > rel) d = 0;
+        if (p >= bs) dist[p - bs] = (u16)d;
+        if ((p % insPeriod) < 2) table[h] = (u16)rel;
+    }
+    for (size_t p = (be >= 8 && be - 7 > bs) ? be - 7 : bs; p < be; p++) dist[p - bs] = 0;   /* no 8-byte read there */
+    free(table);
 }
 
 typedef struct { zbo_seq* seqs; size_t nbSeq; u8* lit; size_t litSize; const u8* frame; } emitter;
@@ -95,97 +113,55 @@ static void emit(emitter* e, size_t anchor, size_t litLen, size_t matchLen, u32 
     e->nbSeq++;
 }
 
-#define ZB_FILL_STEP 1u       /* priming inserts every position (the reference primes every 3rd: zstd_fast.c:63) */
-
+/* ---- phase 2: greedy selection, 32 probe positions per step ("lanes") ---------------------------- */
 static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t frameSize,
                               size_t bs, size_t blockSize, zbo_seq* seqs, u8* lit, size_t* litSizePtr)
 {
     size_t const be = bs + blockSize;
     size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
-    u32 const mls = plan->mls, hlog = plan->hashLog;
-    ztable zt;
     emitter em = { seqs, 0, lit, 0, frame };
     size_t ip = bs, anchor = bs, searchStart = bs;
     u32 rep1 = 0, rep2 = 0;
+    u16* const dist = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
 
-    zt.t = (u16*)calloc((size_t)1 << hlog, sizeof(u16));
-    zt.hashLog = hlog; zt.base = lowLimit;
+    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, dist);
 
-    /* ---- prime the table from history [lowLimit, bs) ; later positions overwrite earlier ones ---- */
-    for (size_t p = lowLimit; p < bs; p += ZB_FILL_STEP) {
-        if (p + 8 > be) break;                                   /* hash reads 8 bytes, stay inside the block end */
-        zt_put(&zt, zb_hash(rd64(frame + p), mls, hlog), p);
-    }
+    while (ip + 8 <= be) {
+        u32 const step = plan->stepSize + (u32)((ip - searchStart) >> 7);     /* kSearchStrength = 8, zstd_fast.c:234 */
+        int winner = -1, wtype = 0, l;
+        size_t probe = 0; u32 offset = 0;
 
-    while (1) {
-        u32 const step = plan->stepSize + (u32)((ip - searchStart) >> 7);     /* kSearchStrength = 8 */
-        size_t p[ZB_WARP]; u32 h[ZB_WARP]; size_t cand[ZB_WARP]; int act[ZB_WARP], hit[ZB_WARP];
-        int winner = -1, l, nact = 0;
-
-        for (l = 0; l < (int)ZB_WARP; l++) {
-            p[l] = ip + (size_t)(l >> 1) * step + (size_t)(l & 1);
-            act[l] = (p[l] + 8 <= be);
-            if (act[l]) nact = l + 1;
+        /* lowest lane with a hit wins.  Per lane: repcode-2 (only at lane 0 right after a match,
+         * zstd_fast.c:410-420), then repcode-1, then the table candidate (4-byte check, :102-141). */
+        for (l = 0; l < (int)ZB_WARP && winner < 0; l++) {
+            size_t const p = ip + (size_t)(l >> 1) * step + (size_t)(l & 1);
+            u32 cur;
+            if (p + 8 > be) break;
+            cur = rd32(frame + p);
+            if (l == 0 && ip == anchor && rep2 && rd32(frame + p - rep2) == cur) { winner = l; wtype = 3; probe = p; offset = rep2; }
+            else if (rep1 && p >= lowLimit + rep1 && rd32(frame + p - rep1) == cur) { winner = l; wtype = 2; probe = p; offset = rep1; }
+            else if (dist[p - bs] && rd32(frame + p - dist[p - bs]) == cur) { winner = l; wtype = 1; probe = p; offset = dist[p - bs]; }
         }
-        if (!act[0]) break;
-
-        /* all lanes look at the table as it was when the step began */
-        for (l = 0; l < nact; l++) {
-            hit[l] = 0;
-            if (!act[l]) continue;
-            h[l] = zb_hash(rd64(frame + p[l]), mls, hlog);
-            cand[l] = zt_get(&zt, h[l], p[l]);
-            {   u32 const cur = rd32(frame + p[l]);
-                if (rep1 && p[l] >= lowLimit + rep1 && rd32(frame + p[l] - rep1) == cur) hit[l] = 2;     /* repcode 1 */
-                else if (cand[l] != (size_t)-1 && rd32(frame + cand[l]) == cur) hit[l] = 1;                 /* table hit */
-            }
-            if (hit[l] && winner < 0) winner = l;
-        }
-
-        /* inserts: lanes up to the winner (all active lanes when nobody matched); highest lane wins a bucket */
-        {   int const last = winner >= 0 ? winner : nact - 1;
-            for (l = 0; l <= last; l++) if (act[l]) zt_put(&zt, h[l], p[l]);
-        }
-
         if (winner < 0) { ip += (size_t)(ZB_WARP / 2) * step; continue; }
 
-        {   size_t const probe = p[winner];
-            size_t ms = probe, mm;          /* match start / match source */
-            size_t mlen;
-            u32 offset, offBase;
-            int const isRep = (hit[winner] == 2);
-            offset = isRep ? rep1 : (u32)(probe - cand[winner]);
-            mm = ms - offset;
-            /* backward catch-up (zstd_fast.c:387-391) */
-            while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
+        {   size_t ms = probe, mm = probe - offset, mlen;
+            u32 offBase;
+            if (wtype != 3)           /* backward catch-up (zstd_fast.c:387-391); a repcode-2 hit starts at the anchor */
+                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
             mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + be);
-            if (isRep && ms > anchor) offBase = 1;              /* REPCODE1_TO_OFFBASE, needs litLength > 0 */
-            else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }   /* decoder pushes every full offset */
+            if (wtype == 3) { offBase = 1; { u32 const t = rep2; rep2 = rep1; rep1 = t; } }    /* litLength 0: code 1 means repcode 2 */
+            else if (wtype == 2 && ms > anchor) offBase = 1;                                     /* REPCODE1_TO_OFFBASE */
+            else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }                           /* decoder pushes every full offset */
             emit(&em, anchor, ms - anchor, mlen, offBase);
-            ip = ms + mlen; anchor = ip;
-
-            if (ip + 8 <= be) {
-                /* sparse fill (zstd_fast.c:403-408) */
-                zt_put(&zt, zb_hash(rd64(frame + probe + 2), mls, hlog), probe + 2);
-                zt_put(&zt, zb_hash(rd64(frame + ip - 2), mls, hlog), ip - 2);
-                /* immediate repcode-2 (zstd_fast.c:410-420) */
-                while (ip + 8 <= be && rep2 && rd32(frame + ip) == rd32(frame + ip - rep2)) {
-                    size_t const rlen = 4 + zb_count(frame + ip + 4, frame + ip + 4 - rep2, frame + be);
-                    { u32 const t = rep2; rep2 = rep1; rep1 = t; }
-                    zt_put(&zt, zb_hash(rd64(frame + ip), mls, hlog), ip);
-                    emit(&em, anchor, 0, rlen, 1);
-                    ip += rlen; anchor = ip;
-                }
-            }
-            searchStart = ip;
+            ip = ms + mlen; anchor = ip; searchStart = ip;
         }
     }
     /* trailing literals (zstd_compress.c:3365-3366) */
     memcpy(em.lit + em.litSize, frame + anchor, be - anchor);
     em.litSize += be - anchor;
     *litSizePtr = em.litSize;
-    free(zt.t);
+    free(dist);
     return em.nbSeq;
 }
 

@@ -71,10 +71,15 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
     p.windowLog = cp.windowLog;
     p.mls = cp.minMatch < 4 ? 4 : (cp.minMatch > 8 ? 8 : cp.minMatch);
     if (cp.strategy == 1) {
-        p.hashLog = cp.hashLog > 14 ? 14 : cp.hashLog;          /* 2^14 u16 = 32 KiB of shared memory per block */
         p.stepSize = cp.targetLength + !cp.targetLength + 1;     /* zstd_fast.c:200 */
+        /* every pattern position is inserted (also inside matches), so half the reference's table holds
+         * as many useful candidates; (hashLog, period) are tuned per level class to land within
+         * +-0.5 % of the reference size on the BASELINE configs ("size parity") */
+        if (cp.targetLength == 0) { p.hashLog = cp.hashLog - 1; p.insPeriod = 4; }
+        else { p.hashLog = cp.hashLog; p.insPeriod = 2 * p.stepSize < 4 ? 4 : 2 * p.stepSize; }
+        if (p.hashLog > 14) p.hashLog = 14;                       /* 2^14 u16 = 32 KiB of shared memory per block */
     } else {
-        p.hashLog = cp.chainLog; p.longHashLog = cp.hashLog; p.stepSize = 1;
+        p.hashLog = cp.chainLog; p.longHashLog = cp.hashLog; p.stepSize = 1; p.insPeriod = 4;
     }
     p.litDisabled = (cp.strategy == 1) && (cp.targetLength > 0); /* zstd_compress_internal.h:621-633 */
     return p;
@@ -89,7 +94,7 @@ struct ZSTD_CCtx_s {
     /* per-block workspace */
     size_t capBlocks, capFrames;
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
-    u64* d_seqs; u8* d_lits; u8* d_body; u16* d_state;
+    u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
     u64* d_outOffsets; u64* d_frameSizes; u64* d_total;
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
@@ -138,9 +143,9 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_state); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
-    c->d_body = NULL; c->d_state = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL;
+    c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL;
     c->capBlocks = 0; c->capFrames = 0;
 }
 
@@ -172,7 +177,7 @@ static size_t zb_ensureWorkspace(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames)
         CK(cudaMalloc(&c->d_seqs, nb * ZB_SEQ_STRIDE * sizeof(u64)));
         CK(cudaMalloc(&c->d_lits, nb * (size_t)ZB_LIT_STRIDE));
         CK(cudaMalloc(&c->d_body, nb * (size_t)ZB_BODY_STRIDE));
-        CK(cudaMalloc(&c->d_state, nb * 3 * (size_t)ZB_STATE_STRIDE * sizeof(u16)));
+        CK(cudaMalloc(&c->d_dist, nb * (size_t)ZB_BLOCK_MAX * sizeof(u16)));
         CK(cudaMalloc(&c->d_outOffsets, (nb + 1) * sizeof(u64)));
         CK(cudaMalloc(&c->d_frameSizes, nf * sizeof(u64)));
         c->capBlocks = nb; c->capFrames = nf;
@@ -202,6 +207,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
             u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
             ZbBlock b; b.srcOff = fr.srcOff + pos; b.size = (u32)bsz;
             b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
+            b.insPhase = (u32)((pos - b.histLen) % prm.insPeriod); b.pad = 0;
             b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
             blocks.push_back(b);
             pos += bsz;
@@ -220,9 +226,9 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     unsigned launches = 0;
     for (size_t g = 0; g < groups.size(); g++) {
         Group const& G = groups[g];
-        CK(zb_launch_match(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
+        CK(zb_launch_match(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
                            c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE, c->d_meta + G.b0, stream));
-        launches++;
+        launches += 2;
     }
     CK(cudaEventRecord(c->evK1, stream));
     for (size_t g = 0; g < groups.size(); g++) {
@@ -230,7 +236,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
         CK(zb_launch_literals(c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE,
                               c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE, c->d_meta + G.b0, stream));
         CK(zb_launch_sequences(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
-                               c->d_state + (size_t)G.b0 * 3 * ZB_STATE_STRIDE, c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE,
+                               c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE,
                                c->d_meta + G.b0, stream));
         launches += 2;
     }

@@ -22,7 +22,7 @@ typedef uint64_t u64;
 #define ZB_SEQ_STRIDE    (ZB_MAX_SEQ + 8)    /* u64 per block */
 #define ZB_LIT_STRIDE    (ZB_BLOCK_MAX + 256)/* bytes per block */
 #define ZB_BODY_STRIDE   (ZB_BLOCK_MAX + 1024)/* staging for one compressed block body */
-#define ZB_STATE_STRIDE  (ZB_MAX_SEQ)        /* u16 per FSE stream per block */
+#define ZB_STATE_STRIDE  (ZB_MAX_SEQ)        /* u16 per FSE stream per block (aliases the dist area: 3*32768 <= 131072) */
 
 /* block types, /root/reference/lib/common/zstd_internal.h:90 */
 #define ZB_BT_RAW 0
@@ -55,6 +55,8 @@ typedef struct {
     u32 histLen;       /* bytes of same-frame history visible before the block (<= ZB_PRIME_BYTES) */
     u32 frame;         /* index into ZbFrame[] */
     u32 flags;         /* ZB_FLAG_* */
+    u32 insPhase;      /* (frame position of the oldest visible byte) % insPeriod */
+    u32 pad;
 } ZbBlock;
 
 typedef struct {
@@ -85,7 +87,7 @@ typedef struct {
     u32 stepSize;      /* zstd_fast.c:200 */
     u32 litDisabled;   /* zstd_compress_internal.h:621-633 */
     u32 windowLog;
-    u32 pad;
+    u32 insPeriod;     /* positions with (framePos % insPeriod) < 2 enter the table */
 } ZbParams;
 
 #endif

@@ -2,18 +2,17 @@
  *
  * Replaces the CPU loop ZSTD_compressBlock_fast_noDict_generic
  * (/root/reference/lib/compress/zstd_fast.c:192-423) with a data-parallel formulation:
- *   - one warp owns one <=128 KiB block; its hash table (2^hashLog u16 entries, positions modulo
- *     64 KiB relative to the start of the visible history) lives in shared memory, so 7 blocks
- *     (hashLog 14) are resident per SM;
- *   - the table is primed from the history bytes in front of the block (zstd_fast.c:53-85 does this
- *     for dictionaries, zstdmt_compress.c:726-731 for job overlaps);
- *   - each step probes 32 positions at once — position pairs (p, p+1) spaced by `step` as in
- *     zstd_fast.c:225-229 — against the table state at the start of the step; repcode-1 is probed
- *     at every lane; the lowest matching lane wins (warp ballot);
- *   - backward catch-up (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771)
- *     are warp-cooperative: 32 x 8 bytes per round, first differing lane found by ballot;
- *   - sparse post-match inserts (:403-408) and the immediate repcode-2 loop (:410-420) follow.
- * Table writes are made deterministic with __match_any_sync (highest lane wins a bucket).
+ *   - one warp owns one <=128 KiB block;
+ *   - K1a walks a private hash table (2^hashLog u16 entries in shared memory, positions modulo
+ *     64 KiB relative to the start of the visible history, primed from the <=64 KiB in front of the
+ *     block: zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:726-731 for job overlaps)
+ *     and records every position's candidate distance; insertion follows a fixed position pattern,
+ *     so this walk does not depend on the parse;
+ *   - K1b does the greedy selection: 32 probe positions per step — pairs (p, p+1) spaced by `step`
+ *     as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward catch-up
+ *     (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are
+ *     warp-cooperative: 32 x 8 bytes per round, first differing lane found by ballot.
+ * Table writes are made deterministic with __match_any_sync (highest inserted lane wins a bucket).
  * The bit-exact CPU model of this kernel is oracle/zb_match.c (tests only).
  */
 #include "zb_device.cuh"
@@ -46,41 +45,86 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
     return (u64)offBase | ((u64)litLen << 24) | ((u64)matchLen << 42);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * K1a — candidate table walk (parse-independent).  One warp per block, table in shared memory.
+ * For every position p of the block: dist[p] = distance to the most recent earlier position that was
+ * inserted and has the same hash (0 = none).  32 consecutive positions per step; within a step the
+ * sequential semantics are kept with __match_any_sync (a lane sees the inserted lanes below it, the
+ * highest inserted lane of a hash group updates the table).  No load depends on the table, so input
+ * loads are issued one step ahead and the loop-carried chain is LDS -> STS only.
+ * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32)
-zb_match_fast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm,
-                     u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
 {
     extern __shared__ u16 table[];
     u32 const lane = threadIdx.x;
     ZbBlock const bd = blocks[blockIdx.x];
-    u64* const myseq = seqs + (size_t)blockIdx.x * ZB_SEQ_STRIDE;
-    u8*  const mylit = lits + (size_t)blockIdx.x * ZB_LIT_STRIDE;
-    const u8* const base = src + bd.srcOff - bd.histLen;      /* rel position 0 = oldest visible byte */
+    if (bd.size < 7u) return;                                    /* zstd_compress.c:3216 : block goes out raw */
+    u16* const mydist = dist + (size_t)blockIdx.x * ZB_BLOCK_MAX;
+    const u8* const base = src + bd.srcOff - bd.histLen;          /* rel position 0 = oldest visible byte */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
-    u32 const mls = prm.mls, hlog = prm.hashLog;
+    u32 const mls = prm.mls, hlog = prm.hashLog, period = prm.insPeriod;
 
-    if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
-        if (lane == 0) {
-            ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
-            m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
-            meta[blockIdx.x] = m;
-        }
-        return;
-    }
-
-    /* ---- clear, then prime the table from the visible history ---- */
     {   uint4* t4 = reinterpret_cast<uint4*>(table);
         u32 const n4 = (2u << hlog) / 16u;
         for (u32 i = lane; i < n4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
-    for (u32 p0 = 0; p0 < bs; p0 += 32) {
+
+    u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
+    u32 ph = (lane + bd.insPhase) % period;
+    u32 const inc = 32u % period;
+    u64 vcur = (lane < nPos) ? zb_ld64u(base + lane) : 0ull;
+    for (u32 p0 = 0; p0 < nPos; p0 += 32) {
         u32 const p = p0 + lane;
-        bool const act = (p < bs) && (p + 8u <= be);
-        u32 const h = act ? zb_hash(zb_ld64u(base + p), mls, hlog) : (0xFFFF0000u | lane);
-        u32 const mm = __match_any_sync(ZB_FULL, h);
-        if (act && (31u - (u32)__clz((int)mm)) == lane) table[h] = (u16)p;
+        bool const act = p < nPos;
+        u64 const vnext = (p + 32u < nPos) ? zb_ld64u(base + p + 32u) : 0ull;     /* next step's input, in flight during this one */
+        u32 const h = act ? zb_hash(vcur, mls, hlog) : (0xFFFF0000u | lane);
+        bool const ins = act && ph < 2u;
+        u32 const old = act ? table[h] : 0u;
+        u32 const grp = __match_any_sync(ZB_FULL, h) & __ballot_sync(ZB_FULL, ins);
+        u32 const lower = grp & ((1u << lane) - 1u);
+        u32 d;
+        if (lower) d = lane - (31u - (u32)__clz((int)lower));
+        else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
+        if (act && p >= bs) mydist[p - bs] = (u16)d;
+        if (ins && (31u - (u32)__clz((int)grp)) == lane) table[h] = (u16)p;
         __syncwarp();
+        vcur = vnext;
+        ph += inc; if (ph >= period) ph -= period;
+    }
+    for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1b — greedy selection + match extension + sequence/literal emission.  One warp per block, no
+ * shared memory (occupancy is register-bound, so the L2 latency of the candidate checks is hidden
+ * by other warps).  Per step 32 probe positions: pairs (p, p+1) spaced by `step` (zstd_fast.c:225-229,
+ * step acceleration :234,:342-347).  Hit priority per lane: repcode-2 (lane 0, directly after a match,
+ * :410-420), repcode-1 (:281-297), table candidate with 4-byte check (:102-141).  Lowest lane wins.
+ * ---------------------------------------------------------------------------------------------- */
+#define PARSE_WARPS 4
+__global__ void __launch_bounds__(32 * PARSE_WARPS)
+zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
+                const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+    if (b >= nbBlocks) return;
+    ZbBlock const bd = blocks[b];
+    u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
+    u8*  const mylit = lits + (size_t)b * ZB_LIT_STRIDE;
+    const u16* const mydist = dist + (size_t)b * ZB_BLOCK_MAX;
+    const u8* const base = src + bd.srcOff - bd.histLen;
+    u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+
+    if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
+        if (lane == 0) {
+            ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
+            m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
+            meta[b] = m;
+        }
+        return;
     }
 
     u32 ip = bs, anchor = bs, searchStart = bs;
@@ -90,74 +134,47 @@ zb_match_fast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blo
         u32 const step = prm.stepSize + ((ip - searchStart) >> 7);           /* kSearchStrength = 8 */
         u32 const p = ip + (lane >> 1) * step + (lane & 1u);
         bool const act = (p + 8u <= be);
-        u64 const v = act ? zb_ld64u(base + p) : 0ull;
-        u32 const cur = (u32)v;
-        u32 const h = act ? zb_hash(v, mls, hlog) : (0xFFFF0000u | lane);
-        u32 const stored = act ? table[h] : 0u;
-        u32 const dist = (p - stored) & 0xFFFFu;
-        bool const cvalid = act && dist != 0u && dist <= p;
-        bool const rvalid = act && rep1 != 0u && p >= rep1;
-        u32 const c4 = cvalid ? zb_ld32u(base + p - dist) : ~cur;
-        u32 const r4 = rvalid ? zb_ld32u(base + p - rep1) : ~cur;
-        u32 const hit = (r4 == cur) ? 2u : ((c4 == cur) ? 1u : 0u);
+        u32 const cur = act ? zb_ld32u(base + p) : 0u;
+        u32 const d = act ? (u32)mydist[p - bs] : 0u;
+        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
+        bool const v2 = act && rep1 != 0u && p >= rep1;
+        bool const v1 = act && d != 0u;
+        u32 const r3 = v3 ? zb_ld32u(base + p - rep2) : ~cur;
+        u32 const r2 = v2 ? zb_ld32u(base + p - rep1) : ~cur;
+        u32 const r1 = v1 ? zb_ld32u(base + p - d) : ~cur;
+        u32 const hit = (r3 == cur) ? 3u : ((r2 == cur) ? 2u : ((r1 == cur) ? 1u : 0u));
         u32 const bal = __ballot_sync(ZB_FULL, hit != 0u);
-        int const winner = bal ? (__ffs((int)bal) - 1) : -1;
-
-        /* inserts: lanes up to the winner; highest lane wins a bucket */
-        {   bool const ins = act && (winner < 0 || (int)lane <= winner);
-            u32 const insmask = __ballot_sync(ZB_FULL, ins);
-            u32 const mm = __match_any_sync(ZB_FULL, h) & insmask;
-            if (ins && (31u - (u32)__clz((int)mm)) == lane) table[h] = (u16)p;
-        }
-        __syncwarp();
-        if (winner < 0) { ip += 16u * step; continue; }
-
+        if (bal == 0u) { ip += 16u * step; continue; }
+        int const winner = __ffs((int)bal) - 1;
         u32 const probe = __shfl_sync(ZB_FULL, p, winner);
-        bool const isRep = __shfl_sync(ZB_FULL, hit, winner) == 2u;
-        u32 const offset = isRep ? rep1 : __shfl_sync(ZB_FULL, dist, winner);
+        u32 const wtype = __shfl_sync(ZB_FULL, hit, winner);
+        u32 const wd = __shfl_sync(ZB_FULL, d, winner);
+        u32 const offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
 
-        /* backward catch-up */
+        /* backward catch-up (zstd_fast.c:387-391) */
         u32 back = 0;
-        while (true) {
-            u32 const k = back + lane + 1u;                    /* compare bytes probe-k and probe-offset-k */
-            bool const ok = (probe >= anchor + k) && (probe >= offset + k)
-                         && (base[probe - k] == base[probe - offset - k]);
-            u32 const okb = __ballot_sync(ZB_FULL, ok);
-            u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
-            back += cnt;
-            if (cnt < 32u) break;
+        if (wtype != 3u) {
+            while (true) {
+                u32 const k = back + lane + 1u;                /* compare bytes probe-k and probe-offset-k */
+                bool const ok = (probe >= anchor + k) && (probe >= offset + k)
+                             && (base[probe - k] == base[probe - offset - k]);
+                u32 const okb = __ballot_sync(ZB_FULL, ok);
+                u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
+                back += cnt;
+                if (cnt < 32u) break;
+            }
         }
         u32 const ms = probe - back;
         u32 const mlen = back + 4u + zb_count_fwd(base, probe + 4u, offset, be, lane);
         u32 const litLen = ms - anchor;
         u32 offBase;
-        if (isRep && litLen > 0u) offBase = 1u;                 /* REPCODE1_TO_OFFBASE */
+        if (wtype == 3u) { offBase = 1u; u32 const t = rep2; rep2 = rep1; rep1 = t; }   /* litLength 0: code 1 = repcode 2 */
+        else if (wtype == 2u && litLen > 0u) offBase = 1u;                                 /* REPCODE1_TO_OFFBASE */
         else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
         if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
         for (u32 i = lane; i < litLen; i += 32) mylit[litPos + i] = base[anchor + i];
         litPos += litLen; nbSeq++;
-        ip = ms + mlen; anchor = ip;
-
-        if (ip + 8u <= be) {
-            if (lane == 0) {                                    /* zstd_fast.c:403-408 */
-                table[zb_hash(zb_ld64u(base + probe + 2u), mls, hlog)] = (u16)(probe + 2u);
-                table[zb_hash(zb_ld64u(base + ip - 2u), mls, hlog)] = (u16)(ip - 2u);
-            }
-            __syncwarp();
-            while (ip + 8u <= be && rep2 != 0u) {               /* zstd_fast.c:410-420 */
-                if (zb_ld32u(base + ip) != zb_ld32u(base + ip - rep2)) break;
-                u32 const rlen = 4u + zb_count_fwd(base, ip + 4u, rep2, be, lane);
-                { u32 const t = rep2; rep2 = rep1; rep1 = t; }
-                if (lane == 0) {
-                    table[zb_hash(zb_ld64u(base + ip), mls, hlog)] = (u16)ip;
-                    myseq[nbSeq] = zb_pack_seq(1u, 0u, rlen);
-                }
-                nbSeq++;
-                ip += rlen; anchor = ip;
-                __syncwarp();
-            }
-        }
-        searchStart = ip;
+        ip = ms + mlen; anchor = ip; searchStart = ip;
     }
 
     /* trailing literals (zstd_compress.c:3365-3366) */
@@ -168,21 +185,22 @@ zb_match_fast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blo
     if (lane == 0) {
         ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litPos; m.litSecSize = 0; m.bodySize = 0;
         m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
-        meta[blockIdx.x] = m;
+        meta[b] = m;
     }
 }
 
 extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
-                                       u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaStream_t stream)
+                                       u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
     size_t const smem = (size_t)2 << prm->hashLog;
     static int configured = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(zb_match_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(zb_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
         configured = 1;
     }
-    zb_match_fast_kernel<<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_seqs, d_lits, d_meta);
+    zb_cand_kernel<<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist);
+    zb_parse_kernel<<<(nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     return cudaGetLastError();
 }

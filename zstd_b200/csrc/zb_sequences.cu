@@ -111,7 +111,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     if (m.forceRaw) return;
     u32 const nbSeq = m.nbSeq;
     const u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
-    u16* const myst = stateBits + (size_t)b * 3u * ZB_STATE_STRIDE;
+    u16* const myst = stateBits + (size_t)b * ZB_BLOCK_MAX;       /* the block's (dead) candidate-distance area */
     u8* const out = body + (size_t)b * ZB_BODY_STRIDE;
     u32 op = m.litSecSize;
 
