@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — compression throughput of the zstd hot path on B200 (BASELINE.json metric).
+
+N=1 workload = BASELINE.json configs[1]: `datagen -g1GB -P50`, level 1, one frame, 128 KiB blocks.
+N>1: every rank compresses its own 1 GiB shard as independent frames (weak scaling, no data-path
+collective); the compressed buffers are gathered to rank 0 over NCCL inside the timed region.
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --steps K --warmup W    # reference libzstd on the host cores
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "compress GB/s (input) at level 1"
+GiB = 1 << 30
+
+
+def load_input(size, p=50, seed=0):
+    """(bytes, description).  Reference datagen when its binary travelled with the repo."""
+    import zref
+    if zref.have_datagen():
+        return zref.datagen(size, p, seed), f"synthetic: reference tests/datagen -g{size} -P{p} -s{seed}"
+    return zref.synthetic(size, seed, p / 100.0), f"synthetic: zbo_synthetic(n={size}, match_prob={p/100}) (datagen binary absent)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.index, self.proc = [], index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = max([int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def ref_lib():
+    import zref
+    R = zref.ref()
+    R.ZSTD_createCCtx.restype = ctypes.c_void_p
+    R.ZSTD_CCtx_setParameter.restype = ctypes.c_size_t
+    R.ZSTD_CCtx_setParameter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    R.ZSTD_compress2.restype = ctypes.c_size_t
+    R.ZSTD_compress2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+    return R
+
+
+def cpu_reference_time(src, level, threads, repeats=1):
+    """Seconds for one ZSTD_compress2(nbWorkers=threads) of `src` by the UNMODIFIED reference
+    (oracle/_ref/libzstd_ref.so, built -O3 -DZSTD_MULTITHREAD from /root/reference).  Best of `repeats`."""
+    R = ref_lib()
+    cctx = R.ZSTD_createCCtx()
+    R.ZSTD_CCtx_setParameter(cctx, 100, level)            # ZSTD_c_compressionLevel
+    if threads > 1:
+        R.ZSTD_CCtx_setParameter(cctx, 400, threads)      # ZSTD_c_nbWorkers
+    cap = R.ZSTD_compressBound(len(src))
+    dst = ctypes.create_string_buffer(cap)
+    best, csize = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        csize = R.ZSTD_compress2(cctx, dst, cap, src, len(src))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    R.ZSTD_freeCCtx(cctx)
+    return best, csize
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation with all host threads (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import zref
+    if not zref.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzstd_ref.so missing (reference not built on this box)"}))
+        return
+    cores = os.cpu_count() or 1
+    size = args.size
+    src, desc = load_input(size)
+    for _ in range(args.warmup):
+        cpu_reference_time(src[: 64 << 20], args.level, cores)
+    t0 = time.perf_counter()
+    csize = 0
+    for _ in range(args.steps):
+        _, csize = cpu_reference_time(src, args.level, cores)
+    dt = time.perf_counter() - t0
+    v = size * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": desc,
+            "config": {"workload": f"datagen -g{size} -P50, level {args.level}, single frame, ZSTD_compress2 nbWorkers={cores}", "compressed_bytes": csize},
+            "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": cores, "kind": "reference",
+                             "sample": f"whole {size}-byte buffer per step, ZSTD_compress2 with nbWorkers={cores}"},
+            "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import zstd_b200
+    import zref
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (zstd_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = args.size
+    src, desc = load_input(size, seed=rank)                 # weak scaling: every rank owns one shard
+    ctx = zstd_b200.ZSTD_CCtx(device=local)
+    cap = zstd_b200.ZSTD_compressBound(size)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).pin_memory()
+    h_dst = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    L = zstd_b200.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        n = ctx.compress_device(d_dst.data_ptr(), cap, d_src.data_ptr(), size, args.level)
+        if world > 1:
+            from zstd_b200.sharding import gather_compressed
+            gather_compressed(d_dst[:n], dst=0)
+        return n
+
+    def step_e2e():
+        r = L.ZSTD_compressCCtx(ctx._h, h_dst.data_ptr(), cap, h_src.data_ptr(), size, args.level)
+        assert not L.ZSTD_isError(r), L.ZSTD_getErrorName(r)
+        return r
+
+    # ---- device-resident throughput (`value`) ----
+    csize = 0
+    for _ in range(args.warmup):
+        csize = step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = []
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        csize = step_device()
+        stats.append(ctx.stats())
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    kern = {k: sum(getattr(s, k) for s in stats) / len(stats) for k in ("kernel_ms", "cand_ms", "parse_ms", "literals_ms", "sequences_ms", "stitch_ms")}
+    launches = sum(s.launches for s in stats)
+
+    # ---- end to end through the reference-facing C ABI with pinned HOST buffers ----
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    te0 = time.perf_counter()
+    ce = 0
+    for _ in range(args.steps):
+        ce = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - te0
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # parity spot-check of what was timed (outside the timed region)
+    got = bytes(d_dst[:csize].cpu().numpy())
+    ok_rt = zref.ref_decompress(got, size) == src if zref.have_ref() else None
+    hbm, peak_src = peaks()
+    value = size * world * args.steps / (ms / 1e3) / 1e9
+    e2e = size * world * args.steps / e2e_s / 1e9
+    dom = max(("cand_ms", "parse_ms", "literals_ms", "sequences_ms", "stitch_ms"), key=lambda k: kern[k])
+    achieved = (size + csize) / (kern[dom] / 1e3) / 1e9
+    # CPU baseline on this box: reference libzstd, bounded sample
+    cpu = None
+    if zref.have_ref() and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = src[: min(size, 256 << 20)]
+        t1, c1 = cpu_reference_time(sample, args.level, 1)
+        tn, cn = cpu_reference_time(src, args.level, cores)
+        cpu = {"value": round(size / tn / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": "reference",
+               "sample": f"ZSTD_compress2 nbWorkers={cores} on the whole {size}-byte input ({cn} B out); 1 thread on the first {len(sample)} bytes: {len(sample)/t1/1e9:.3f} GB/s ({c1} B out)",
+               "ref_compressed_bytes": cn}
+    line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": desc,
+            "config": {"workload": f"datagen -g{size} -P50 per GPU, level {args.level}, one frame per GPU, 128 KiB blocks", "l2": "input 1 GiB per step > 126 MB L2 (no reuse between steps)",
+                       "compressed_bytes": csize, "roundtrip_ok": ok_rt,
+                       "size_delta_vs_ref": (round((csize - cpu["ref_compressed_bytes"]) / cpu["ref_compressed_bytes"], 5) if cpu else None)},
+            "kernel_ms": {k: round(v, 3) for k, v in kern.items()},
+            "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                         "frac": round(achieved / hbm, 4), "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes": size + csize, "read_only_frac": round(size / (kern[dom] / 1e3) / 1e9 / hbm, 4)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": size, "d2h_bytes_per_step": int(ce), "api": "ZSTD_compressCCtx(host pinned src/dst)"},
+            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--level", type=int, default=1)
+    ap.add_argument("--size", type=int, default=GiB)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,11 @@ ZSTDB200_API size_t ZSTDB200_compressFrames(ZSTD_CCtx* cctx, void* dst, size_t d
 /* Timing / evidence of the last call on this context (CUDA events on the launching stream). */
 typedef struct {
     float  kernel_ms;        /* first kernel start -> last kernel end */
-    float  match_ms;         /* match-finder kernel(s) only */
+    float  match_ms;         /* K1a candidate walk + K1b parse */
+    float  cand_ms, parse_ms; /* K1a, K1b separately (single parameter group only, else 0) */
+    float  literals_ms;      /* K2 */
+    float  sequences_ms;     /* K3 */
+    float  stitch_ms;        /* K4 scan + copy */
     float  total_ms;         /* including host<->device copies, when the call made any */
     unsigned launches;       /* kernels launched by the call */
     unsigned nbBlocks;       /* 128 KiB blocks processed */

@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/zstd_b200.h declares (no compute call:
+this runs on the CPU-only box), and the non-compute helpers behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import zref
+import zstd_b200
+
+HEADER = os.path.join(zref.ROOT, "include", "zstd_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"ZSTDB200_API\s+[\w\s\*]+?\b(ZSTD\w+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_entry_points():
+    syms = declared_symbols()
+    for s in ("ZSTD_compress", "ZSTD_compressCCtx", "ZSTD_compress_usingDict", "ZSTD_createCCtx", "ZSTD_freeCCtx",
+              "ZSTD_compressBound", "ZSTD_isError", "ZSTD_getErrorName", "ZSTD_getErrorCode",
+              "ZSTD_minCLevel", "ZSTD_maxCLevel", "ZSTD_defaultCLevel", "ZSTD_versionNumber"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(zstd_b200.LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    for s in declared_symbols():
+        assert hasattr(L, s), f"{s} declared in include/zstd_b200.h but not exported"
+
+
+def test_helpers_match_reference_semantics():
+    L = zstd_b200.lib()
+    assert L.ZSTD_versionNumber() == 10506
+    assert L.ZSTD_minCLevel() == -(1 << 17) and L.ZSTD_maxCLevel() == 22 and L.ZSTD_defaultCLevel() == 3
+    assert L.ZSTD_freeCCtx(None) == 0                                   # lib/zstd.h:264 accepts NULL
+    for n in [0, 1, 100, 128 << 10, (128 << 10) + 1, 1 << 30]:
+        assert L.ZSTD_compressBound(n) == zref.oracle().zbo_compressBound(n)
+    assert L.ZSTD_isError(L.ZSTD_compressBound(0xFF00FF00FF00FF00))      # srcSize_wrong
+    assert L.ZSTD_getErrorCode(L.ZSTD_compressBound(0xFF00FF00FF00FF00)) == 72
+    assert not L.ZSTD_isError(12345)
+    if zref.have_ref():
+        R = zref.ref()
+        for code in (0, 1, 10, 30, 32, 40, 42, 44, 46, 60, 62, 64, 66, 70, 72, 74, 119):
+            v = (1 << 64) - code if code else 0
+            assert L.ZSTD_getErrorName(v) == R.ZSTD_getErrorName(v), code
+            assert bool(L.ZSTD_isError(v)) == bool(R.ZSTD_isError(v))
+
+
+def test_context_lifecycle_without_gpu():
+    L = zstd_b200.lib()
+    c = L.ZSTD_createCCtx()
+    assert c
+    assert L.ZSTD_freeCCtx(c) == 0
+
+
+@pytest.mark.skipif(zstd_b200.device_available(), reason="CUDA device present")
+def test_compress_fails_loudly_without_cuda():
+    """No CPU fallback: without a device the call must return an error, never data."""
+    with pytest.raises(zstd_b200.ZstdError):
+        zstd_b200.ZSTD_compress(b"hello world" * 100, 1)

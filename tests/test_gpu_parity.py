@@ -1,0 +1,156 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libzstd_b200.so.  The CUDA path must be bit-exact with the oracle, every frame must decode with the
+reference decoder (when its prebuilt .so travelled with the repo), sizes must stay within +-0.5 % of
+the reference on the BASELINE inputs."""
+import ctypes
+import json
+import os
+
+import pytest
+
+import zref
+import zstd_b200
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zstd_b200.ZSTD_CCtx()
+    yield c
+    c.close()
+
+
+def decode_ok(frame, src):
+    if zref.have_ref():
+        assert zref.ref_decompress(frame, len(src)) == src
+
+
+CASES = {
+    "empty": b"", "one": b"x", "six": b"abcdef", "seven": b"abcdefg", "tiny-rep": b"abcabcabc" * 10,
+    "zeros-300": bytes(300), "zeros-1M": bytes(1 << 20), "zeros-128k+1": bytes((128 << 10) + 1),
+    "rand-100k": zref.random_bytes(100_000, 1), "rand-300k": zref.random_bytes(300_000, 2),
+    "period3": b"abc" * 50_000, "period40": bytes(range(40)) * 9000,
+    "syn-100": zref.synthetic(100, 100), "syn-1000": zref.synthetic(1000, 1000), "syn-5000": zref.synthetic(5000, 5000),
+    "syn-70000": zref.synthetic(70_000, 7), "syn-128k": zref.synthetic(128 << 10, 3), "syn-128k+1": zref.synthetic((128 << 10) + 1, 3),
+    "syn-400000": zref.synthetic(400_000, 4), "syn-4M-p30": zref.synthetic(4 << 20, 5, 0.3), "syn-4M-p90": zref.synthetic(4 << 20, 6, 0.9),
+    "syn-2M-p10": zref.synthetic(2 << 20, 8, 0.1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("level", [1, -1, -3, -7])
+def test_bit_exact_with_oracle(ctx, name, level):
+    src = CASES[name]
+    got = ctx.compress(src, level)
+    assert got == zref.oracle_compress(src, level)
+    decode_ok(got, src)
+
+
+def test_simple_api_temporary_context():
+    """ZSTD_compress (lib/zstd.h:155) creates and frees its own context."""
+    src = zref.synthetic(300_000, 11)
+    assert zstd_b200.ZSTD_compress(src, 1) == zref.oracle_compress(src, 1)
+
+
+def test_context_reuse_and_determinism(ctx):
+    """fuzzer.c:1547-1589 "re-using a CCtx should compress the same"; fuzz/simple_round_trip.c determinism."""
+    a = zref.synthetic(1 << 20, 21)
+    b = zref.synthetic(200_000, 22, 0.8)
+    fa1 = ctx.compress(a, 1)
+    fb = ctx.compress(b, -3)
+    fa2 = ctx.compress(a, 1)
+    assert fa1 == fa2
+    c2 = zstd_b200.ZSTD_CCtx()
+    assert c2.compress(a, 1) == fa1 and c2.compress(b, -3) == fb
+    c2.close()
+
+
+def test_dst_too_small(ctx):
+    """fuzzer.c:4550-4562: too small a destination returns dstSize_tooSmall and never writes past it."""
+    src = zref.synthetic(300_000, 1)
+    full = ctx.compress(src, 1)
+    L = zstd_b200.lib()
+    for cap in (5, 17, 18, 100, len(full) - 1):
+        dst = ctypes.create_string_buffer(cap + 64)
+        ctypes.memset(dst, 0xA5, cap + 64)
+        r = L.ZSTD_compressCCtx(ctx._h, dst, cap, src, len(src), 1)
+        assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 70
+        assert dst.raw[cap:] == b"\xa5" * 64
+    dst = ctypes.create_string_buffer(len(full))
+    assert L.ZSTD_compressCCtx(ctx._h, dst, len(full), src, len(src), 1) == len(full)
+    assert dst.raw == full
+
+
+def test_golden_inputs(ctx):
+    """The reference's tests/golden-compression inputs through our entry points (cli-tests/compression/golden.sh)."""
+    frames = json.load(open(os.path.join(zref.GOLDEN, "frames.json")))
+    for key, rec in frames.items():
+        name, level = key.rsplit("@", 1)
+        path = os.path.join(zref.GOLDEN, "inputs", name)
+        if not os.path.exists(path) or int(level) == 3:
+            continue
+        data = open(path, "rb").read()
+        out = ctx.compress(data, int(level))
+        assert len(out) == rec["oracle_size"] and zref.sha(out) == rec["oracle_sha256"], key
+        decode_ok(out, data)
+
+
+@pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary absent")
+@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 64 << 20)])
+def test_baseline_configs_size_and_roundtrip(ctx, p, level, size):
+    """configs[0] (datagen -g16MB -P50, level 1) and a 64 MiB sample of config 3 (P30, --fast=3):
+    bit-exact with the oracle, decodes, size within +-0.5 % of the reference."""
+    src = zref.datagen(size, p)
+    got = ctx.compress(src, level)
+    assert got == zref.oracle_compress(src, level)
+    decode_ok(got, src)
+    if zref.have_ref():
+        ref = zref.ref_compress(src, level)
+        delta = (len(got) - len(ref)) / len(ref)
+        assert abs(delta) <= 0.005, f"{delta:+.4%}"
+
+
+@pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary absent")
+def test_full_size_config2_properties(ctx):
+    """configs[1] at full size (datagen -g1GB -P50, level 1), device-resident.  The oracle would need
+    ~10 s here, so this checks size-independent properties: the frame decodes to the input, the
+    run is deterministic, and cutting the same bytes into 64 MiB frames decodes to the same bytes."""
+    import torch
+    size = 1 << 30
+    src = zref.datagen(size, 50)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = zstd_b200.ZSTD_compressBound(size) + 64 * 32
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n1 = ctx.compress_device(d_dst.data_ptr(), cap, d_src.data_ptr(), size, 1)
+    f1 = bytes(d_dst[:n1].cpu().numpy())
+    n2 = ctx.compress_device(d_dst.data_ptr(), cap, d_src.data_ptr(), size, 1)
+    assert n1 == n2 and bytes(d_dst[:n2].cpu().numpy()) == f1
+    decode_ok(f1, src)
+    fs = 64 << 20
+    offs = list(range(0, size, fs))
+    total, csz = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), offs, [fs] * len(offs), level=1, device_memory=True)
+    assert sum(csz) == total
+    decode_ok(bytes(d_dst[:total].cpu().numpy()), src)          # concatenated frames, lib/zstd.h:160-162
+    if zref.have_ref():
+        ref = zref.ref_compress(src[: 256 << 20], 1)
+        part = ctx.compress(src[: 256 << 20], 1)
+        assert abs(len(part) - len(ref)) / len(ref) <= 0.005
+
+
+def test_many_small_frames(ctx):
+    """Independent small frames in one call (shape of config 5 without the dictionary)."""
+    import torch
+    rec = 1024
+    n = 2048
+    src = zref.synthetic(rec * n, 33, 0.5)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = sum(zstd_b200.ZSTD_compressBound(rec) + 32 for _ in range(n))
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    total, csz = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), [i * rec for i in range(n)], [rec] * n, level=1)
+    out = bytes(d_dst[:total].cpu().numpy())
+    pos = 0
+    for i in range(0, n, 97):
+        start = sum(csz[:i])
+        assert out[start:start + csz[i]] == zref.oracle_compress(src[i * rec:(i + 1) * rec], 1)
+    decode_ok(out, src)

@@ -1,0 +1,110 @@
+"""Oracle at frame level: every frame decodes with the reference decoder, sizes stay within the
++-0.5 % bar on the BASELINE inputs, parameter derivation equals the reference's, golden fixtures."""
+import ctypes
+import json
+import os
+
+import pytest
+
+import zref
+
+needs_ref = pytest.mark.skipif(not zref.have_ref(), reason="oracle/_ref/libzstd_ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 0, -1, -3, -7])
+@pytest.mark.parametrize("size", [0, 1, 100, 1000, 16 << 10, (16 << 10) + 1, 100_000, 128 << 10, (128 << 10) + 1,
+                                  256 << 10, (256 << 10) + 1, 1 << 20, 5 << 20, 600 << 20])
+def test_cparams_match_reference(level, size):
+    """zbo_getCParams restates ZSTD_getCParams_internal + ZSTD_adjustCParams_internal
+    (zstd_compress.c:7123-7146, :1465-1602) for rows whose strategy is fast/dfast."""
+    class CP(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_uint) for n in ("windowLog", "chainLog", "hashLog", "searchLog", "minMatch", "targetLength", "strategy")]
+    O = zref.oracle()
+    O.zbo_getCParams.restype = CP
+    O.zbo_getCParams.argtypes = [ctypes.c_int, ctypes.c_ulonglong, ctypes.c_size_t]
+    out = (ctypes.c_uint * 7)()
+    zref.ref().ref_getCParams_simpleApi(level, size, 0, out)
+    ours = O.zbo_getCParams(level, size, 0)
+    if out[6] > 2:
+        pytest.skip("reference strategy above dfast: out of scope, served by the dfast row")
+    assert [ours.windowLog, ours.chainLog, ours.hashLog, ours.searchLog, ours.minMatch, ours.targetLength, ours.strategy] == list(out)
+
+
+@needs_ref
+def test_compress_bound_matches_reference():
+    O, R = zref.oracle(), zref.ref()
+    for n in [0, 1, 100, 1 << 10, 128 << 10, (128 << 10) - 1, (128 << 10) + 1, 1 << 20, 1 << 30, 5 << 30]:
+        assert O.zbo_compressBound(n) == R.ZSTD_compressBound(n)
+
+
+EDGE = {
+    "empty": b"", "one": b"x", "six": b"abcdef", "seven": b"abcdefg",
+    "zeros-300": bytes(300), "zeros-1M": bytes(1 << 20), "zeros-128k+1": bytes((128 << 10) + 1),
+    "rand-100k": zref.random_bytes(100_000, 1), "rand-300k": zref.random_bytes(300_000, 2),
+    "period3": b"abc" * 50_000, "syn-128k": zref.synthetic(128 << 10, 3), "syn-128k+1": zref.synthetic((128 << 10) + 1, 3),
+    "syn-1M-p90": zref.synthetic(1 << 20, 5, 0.9), "syn-1M-p10": zref.synthetic(1 << 20, 6, 0.1),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(EDGE))
+@pytest.mark.parametrize("level", [1, -3, 3])
+def test_roundtrip_edge_cases(name, level):
+    src = EDGE[name]
+    frame = zref.oracle_compress(src, level)
+    assert zref.ref_decompress(frame, len(src)) == src
+    assert len(frame) <= zref.ref().ZSTD_compressBound(len(src))
+    assert zref.ref().ZSTD_getFrameContentSize(frame, len(frame)) == len(src)       # fuzzer.c:4565-4573
+    assert zref.oracle_compress(src, level) == frame                                  # determinism (fuzz/simple_round_trip.c)
+
+
+@needs_ref
+def test_dst_too_small_is_an_error_not_an_overflow():
+    src = zref.synthetic(300_000, 1)
+    full = zref.oracle_compress(src, 1)
+    O = zref.oracle()
+    for cap in (0, 5, 17, 18, 100, len(full) - 1):
+        dst = ctypes.create_string_buffer(cap + 64)
+        ctypes.memset(dst, 0xA5, cap + 64)
+        r = O.zbo_compress(dst, cap, src, len(src), 1)
+        assert r == (1 << 64) - 70, f"cap={cap}: expected dstSize_tooSmall"
+        assert dst.raw[cap:] == b"\xa5" * 64                                         # fuzzer.c:4550-4562
+    dst = ctypes.create_string_buffer(len(full))
+    assert O.zbo_compress(dst, len(full), src, len(src), 1) == len(full)
+
+
+def test_golden_frames_fixture():
+    """tests/golden/frames.json (from tests/golden/make_golden.py): the oracle reproduces its recorded
+    output on the reference's golden-compression inputs; recorded reference sizes document the gap."""
+    frames = json.load(open(os.path.join(zref.GOLDEN, "frames.json")))
+    for key, rec in frames.items():
+        name, level = key.rsplit("@", 1)
+        path = os.path.join(zref.GOLDEN, "inputs", name)
+        if os.path.exists(path):
+            data = open(path, "rb").read()
+        elif name == "synthetic-300k-seed9":
+            data = zref.synthetic(300000, 9)
+        elif name == "synthetic-1M-p30-seed4":
+            data = zref.synthetic(1 << 20, 4, 0.3)
+        else:
+            raise AssertionError(name)
+        assert zref.sha(data) == rec["input_sha256"]
+        out = zref.oracle_compress(data, int(level))
+        assert len(out) == rec["oracle_size"] and zref.sha(out) == rec["oracle_sha256"], key
+        if zref.have_ref():
+            assert zref.ref_decompress(out, len(data)) == data
+            assert len(zref.ref_compress(data, int(level))) == rec["ref_size"]
+
+
+@needs_ref
+@pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary not built")
+@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 16 << 20)])
+def test_size_within_half_percent_of_reference(p, level, size):
+    """BASELINE.json configs 1/2 (P50, level 1) and 3 (P30, --fast=3) on a 16 MiB sample."""
+    src = zref.datagen(size, p)
+    ours = zref.oracle_compress(src, level)
+    ref = zref.ref_compress(src, level)
+    assert zref.ref_decompress(ours, len(src)) == src
+    delta = (len(ours) - len(ref)) / len(ref)
+    assert abs(delta) <= 0.005, f"size delta {delta:+.4%} (ours {len(ours)}, reference {len(ref)})"

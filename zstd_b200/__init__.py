@@ -32,7 +32,8 @@ class ZstdError(RuntimeError):
 
 
 class Stats(ctypes.Structure):
-    _fields_ = [("kernel_ms", ctypes.c_float), ("match_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+    _fields_ = [("kernel_ms", ctypes.c_float), ("match_ms", ctypes.c_float), ("cand_ms", ctypes.c_float), ("parse_ms", ctypes.c_float), ("literals_ms", ctypes.c_float),
+                ("sequences_ms", ctypes.c_float), ("stitch_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("launches", ctypes.c_uint), ("nbBlocks", ctypes.c_uint),
                 ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
 
@@ -115,11 +116,15 @@ class ZSTD_CCtx:
             raise MemoryError("ZSTD_createCCtx failed")
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().ZSTD_freeCCtx(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ZSTD_freeCCtx(h)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter teardown
+            pass
 
     # -- reference-identical calls (host buffers) --
     def compress(self, src, level: int = 3, dst_capacity: Optional[int] = None) -> bytes:

@@ -99,7 +99,7 @@ struct ZSTD_CCtx_s {
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
     u64* h_total;                  /* pinned */
-    cudaEvent_t evStart, evK0, evK1, evKEnd, evEnd;
+    cudaEvent_t evStart, evK0, evMid, evK1, evK2, evK3, evKEnd, evEnd;
     ZSTDB200_stats stats;
 };
 
@@ -134,6 +134,7 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
     c->device = dev;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evK0)); CK(cudaEventCreate(&c->evK1));
+    CK(cudaEventCreate(&c->evK2)); CK(cudaEventCreate(&c->evK3)); CK(cudaEventCreate(&c->evMid));
     CK(cudaEventCreate(&c->evKEnd)); CK(cudaEventCreate(&c->evEnd));
     CK(cudaMallocHost(&c->h_total, 64));
     CK(cudaMalloc(&c->d_total, 64));
@@ -158,6 +159,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
         cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_total);
         cudaFreeHost(c->h_total);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
+        cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
         cudaEventDestroy(c->evKEnd); cudaEventDestroy(c->evEnd);
         cudaStreamDestroy(c->stream);
     }
@@ -227,7 +229,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     for (size_t g = 0; g < groups.size(); g++) {
         Group const& G = groups[g];
         CK(zb_launch_match(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
-                           c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE, c->d_meta + G.b0, stream));
+                           c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE, c->d_meta + G.b0, groups.size() == 1 ? c->evMid : (cudaEvent_t)0, stream));
         launches += 2;
     }
     CK(cudaEventRecord(c->evK1, stream));
@@ -235,11 +237,17 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
         Group const& G = groups[g];
         CK(zb_launch_literals(c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE,
                               c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE, c->d_meta + G.b0, stream));
+        launches++;
+    }
+    CK(cudaEventRecord(c->evK2, stream));
+    for (size_t g = 0; g < groups.size(); g++) {
+        Group const& G = groups[g];
         CK(zb_launch_sequences(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
                                c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE,
                                c->d_meta + G.b0, stream));
-        launches += 2;
+        launches++;
     }
+    CK(cudaEventRecord(c->evK3, stream));
     CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, (u32)nbFrames, c->d_body, c->d_meta,
                         c->d_outOffsets, c->d_frameSizes, c->d_total, d_dst, dstCapacity, stream));
     launches += 2;
@@ -254,7 +262,11 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     c->stats.launches = launches;
     c->stats.nbBlocks = nbBlocks;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evK0, c->evKEnd); c->stats.kernel_ms = ms;
-        cudaEventElapsedTime(&ms, c->evK0, c->evK1); c->stats.match_ms = ms; }
+        cudaEventElapsedTime(&ms, c->evK0, c->evK1); c->stats.match_ms = ms;
+        if (groups.size() == 1) { cudaEventElapsedTime(&ms, c->evK0, c->evMid); c->stats.cand_ms = ms; cudaEventElapsedTime(&ms, c->evMid, c->evK1); c->stats.parse_ms = ms; }
+        cudaEventElapsedTime(&ms, c->evK1, c->evK2); c->stats.literals_ms = ms;
+        cudaEventElapsedTime(&ms, c->evK2, c->evK3); c->stats.sequences_ms = ms;
+        cudaEventElapsedTime(&ms, c->evK3, c->evKEnd); c->stats.stitch_ms = ms; }
     u64 const total = c->h_total[0];
     if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
     return (size_t)total;

@@ -11,7 +11,7 @@ extern "C" {
 /* K1: match-finder = K1a candidate table walk + K1b greedy parse.  One warp per block each.
  * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records). */
 cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
-                            u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaStream_t stream);
+                            u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
 /* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block. */
 cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,

@@ -12,9 +12,10 @@
  *     as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward catch-up
  *     (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are
  *     warp-cooperative: 32 x 8 bytes per round, first differing lane found by ballot.
- * Table writes are made deterministic with __match_any_sync (highest inserted lane wins a bucket).
+ * Table writes are deterministic: the highest inserted lane of a step wins a bucket.
  * The bit-exact CPU model of this kernel is oracle/zb_match.c (tests only).
  */
+#include <cuda_pipeline.h>
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
@@ -49,14 +50,21 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
  * K1a — candidate table walk (parse-independent).  One warp per block, table in shared memory.
  * For every position p of the block: dist[p] = distance to the most recent earlier position that was
  * inserted and has the same hash (0 = none).  32 consecutive positions per step; within a step the
- * sequential semantics are kept with __match_any_sync (a lane sees the inserted lanes below it, the
- * highest inserted lane of a hash group updates the table).  No load depends on the table, so input
+ * sequential semantics are kept (a lane sees the inserted lanes below it, the highest inserted lane
+ * of a hash group updates the table) with a write / read-back of the bucket; __match_any_sync would do
+ * it in one instruction but costs ~400 cycles on sm_100a (profiles/r1_cand_match_any.txt).  No load depends on the table, so input
  * loads are issued one step ahead and the loop-carried chain is LDS -> STS only.
  * ---------------------------------------------------------------------------------------------- */
+#define CAND_CHUNK 512u                      /* bytes staged per cp.async group: 32 lanes x 16 B */
+#define CAND_STAGES 4u                       /* ring = 4 chunks = 2 KiB, 3 chunks in flight ahead of the consumer */
+#define CAND_RING (CAND_CHUNK * CAND_STAGES)
+
 __global__ void __launch_bounds__(32)
 zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
 {
-    extern __shared__ u16 table[];
+    extern __shared__ __align__(16) u8 smem[];
+    u8*  const ring = smem;                                       /* input staging, CAND_RING bytes */
+    u16* const table = reinterpret_cast<u16*>(smem + CAND_RING);
     u32 const lane = threadIdx.x;
     ZbBlock const bd = blocks[blockIdx.x];
     if (bd.size < 7u) return;                                    /* zstd_compress.c:3216 : block goes out raw */
@@ -65,33 +73,90 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     u32 const mls = prm.mls, hlog = prm.hashLog, period = prm.insPeriod;
 
+    /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
+    u32 const o0 = (u32)((uintptr_t)base & 15u);
+    const u8* const abase = base - o0;
+    u32 const qEnd = o0 + be;                                     /* one past the last byte we may read */
+    u32 const nChunks = (qEnd + CAND_CHUNK - 1u) / CAND_CHUNK;
+
     {   uint4* t4 = reinterpret_cast<uint4*>(table);
         u32 const n4 = (2u << hlog) / 16u;
         for (u32 i = lane; i < n4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
     }
+    /* prologue: chunks 0 .. STAGES-2 in flight */
+#pragma unroll
+    for (u32 c = 0; c < CAND_STAGES - 1u; c++) {
+        u32 const q = c * CAND_CHUNK + 16u * lane;
+        if (c < nChunks && q < qEnd) __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16);
+        __pipeline_commit();
+    }
     __syncwarp();
 
     u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
-    u32 ph = (lane + bd.insPhase) % period;
+    u32 ph = (lane + period - (o0 % period) + bd.insPhase) % period;   /* pattern phase of q = lane */
     u32 const inc = 32u % period;
-    u64 vcur = (lane < nPos) ? zb_ld64u(base + lane) : 0ull;
-    for (u32 p0 = 0; p0 < nPos; p0 += 32) {
-        u32 const p = p0 + lane;
-        bool const act = p < nPos;
-        u64 const vnext = (p + 32u < nPos) ? zb_ld64u(base + p + 32u) : 0ull;     /* next step's input, in flight during this one */
-        u32 const h = act ? zb_hash(vcur, mls, hlog) : (0xFFFF0000u | lane);
-        bool const ins = act && ph < 2u;
-        u32 const old = act ? table[h] : 0u;
-        u32 const grp = __match_any_sync(ZB_FULL, h) & __ballot_sync(ZB_FULL, ins);
-        u32 const lower = grp & ((1u << lane) - 1u);
-        u32 d;
-        if (lower) d = lane - (31u - (u32)__clz((int)lower));
-        else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
-        if (act && p >= bs) mydist[p - bs] = (u16)d;
-        if (ins && (31u - (u32)__clz((int)grp)) == lane) table[h] = (u16)p;
+    for (u32 c = 0; c < nChunks; c++) {
+        {   u32 const cn = c + CAND_STAGES - 1u;                  /* refill the slot consumed in the previous iteration */
+            u32 const q = cn * CAND_CHUNK + 16u * lane;
+            if (cn < nChunks && q < qEnd) __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16);
+            __pipeline_commit();
+        }
+        /* chunk c and (for the 8-byte reads that straddle its end) chunk c+1 must have landed */
+        __pipeline_wait_prior(CAND_STAGES - 2u);
         __syncwarp();
-        vcur = vnext;
-        ph += inc; if (ph >= period) ph -= period;
+#pragma unroll 4
+        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
+            u32 const q = c * CAND_CHUNK + 32u * j + lane;
+            bool const act = (q >= o0) && (q - o0 < nPos);
+            u32 const p = q - o0;
+            u32 const w = (q & ~3u) & (CAND_RING - 1u);
+            u32 const sh = (q & 3u) * 8u;
+            u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
+            u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
+            u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
+            u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
+            u32 const h = act ? zb_hash(v, mls, hlog) : 0u;
+            bool const ins = act && ph < 2u;
+            /* read the bucket, let every inserting lane write it, read it back: when no two inserting
+             * lanes share a bucket (the common case) the read-back alone resolves the step */
+            u32 const old = act ? table[h] : 0u;
+            __syncwarp();
+            if (ins) table[h] = (u16)p;
+            __syncwarp();
+            u32 const nw = act ? table[h] : 0u;
+            u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
+            u32 d = 0;
+            bool resolved = false;
+            if (losers) {
+                /* rare: some bucket has several inserting lanes.  Peel one hash group per round:
+                 * the highest inserting lane owns the bucket, every lane of the group takes the
+                 * nearest inserting lane below it as its candidate. */
+                u32 const insmask = __ballot_sync(ZB_FULL, ins);
+                while (losers) {
+                    int const L = __ffs((int)losers) - 1;
+                    u32 const hl = __shfl_sync(ZB_FULL, h, L);
+                    bool const mine = act && h == hl;
+                    u32 const grpAll = __ballot_sync(ZB_FULL, mine);
+                    u32 const grpIns = grpAll & insmask;
+                    if (mine) {
+                        u32 const lower = grpIns & ((1u << lane) - 1u);
+                        if (lower) d = lane - (31u - (u32)__clz((int)lower));
+                        else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
+                        resolved = true;
+                        if ((31u - (u32)__clz((int)grpIns)) == lane) table[h] = (u16)p;
+                    }
+                    losers &= ~grpAll;
+                }
+                __syncwarp();
+            }
+            if (!resolved) {
+                u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
+                if (dn >= 1u && dn <= lane) d = dn;
+                else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
+            }
+            if (act && p >= bs) mydist[p - bs] = (u16)d;
+            ph += inc; if (ph >= period) ph -= period;
+        }
     }
     for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
 }
@@ -190,10 +255,10 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
 }
 
 extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
-                                       u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaStream_t stream)
+                                       u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    size_t const smem = (size_t)2 << prm->hashLog;
+    size_t const smem = ((size_t)2 << prm->hashLog) + CAND_RING;
     static int configured = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(zb_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -201,6 +266,7 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks,
         configured = 1;
     }
     zb_cand_kernel<<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist);
+    if (evMid) cudaEventRecord(evMid, stream);
     zb_parse_kernel<<<(nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     return cudaGetLastError();
 }
