@@ -13,7 +13,7 @@ __device__ __forceinline__ u32 zb_ld32u(const u8* p)
     const u32* q = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
     u32 const sh = ((u32)(uintptr_t)p & 3u) * 8u;
     u32 const a = __ldg(q);
-    u32 const b = sh ? __ldg(q + 1) : 0u;
+    u32 const b = __ldg(sh ? q + 1 : q);                  /* select the address, not the load: no branch */
     return __funnelshift_r(a, b, sh);
 }
 __device__ __forceinline__ u64 zb_ld64u(const u8* p)
@@ -22,10 +22,36 @@ __device__ __forceinline__ u64 zb_ld64u(const u8* p)
     u32 const sh = ((u32)(uintptr_t)p & 3u) * 8u;
     u32 const a = __ldg(q);
     u32 const b = __ldg(q + 1);
-    u32 const c = sh ? __ldg(q + 2) : 0u;
+    u32 const c = __ldg(sh ? q + 2 : q + 1);
     u32 const lo = __funnelshift_r(a, b, sh);
     u32 const hi = __funnelshift_r(b, c, sh);
     return ((u64)hi << 32) | lo;
+}
+
+/* Branch-free variants: always touch 2 (resp. 3) words, so several of them can be in flight at
+ * once (the predicated forms above make ptxas fence each load in its own reconvergence region).
+ * Caller guarantees p + 8 (resp. p + 12 rounded down to a word) stays inside the input. */
+__device__ __forceinline__ u32 zb_ld32w2(const u8* p)
+{
+    const u32* q = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+    u32 const sh = ((u32)(uintptr_t)p & 3u) * 8u;
+    return __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+}
+__device__ __forceinline__ u64 zb_ld64w3(const u8* p)
+{
+    const u32* q = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+    u32 const sh = ((u32)(uintptr_t)p & 3u) * 8u;
+    u32 const a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    return ((u64)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
+}
+/* The 4 bytes at rel position x (`cur`) and the 4 bytes in front of it (`pre`, byte x-1 in the top
+ * byte; bytes in front of position 0 are undefined and must be masked by the caller's limits). */
+__device__ __forceinline__ void zb_ld_pre_cur(const u8* base, u32 x, u32* pre, u32* cur)
+{
+    u32 const s = x >= 4u ? 0u : 4u - x;
+    u64 const w = zb_ld64w3(base + (x + s - 4u));
+    *pre = (u32)(w << (8u * s));
+    *cur = (u32)(w >> (32u - 8u * s));
 }
 
 /* /root/reference/lib/compress/zstd_compress_internal.h:815-861 */

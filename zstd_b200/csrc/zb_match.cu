@@ -59,19 +59,19 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
 #define CAND_STAGES 4u                       /* ring = 4 chunks = 2 KiB, 3 chunks in flight ahead of the consumer */
 #define CAND_RING (CAND_CHUNK * CAND_STAGES)
 
+template <int MLS>
 __global__ void __launch_bounds__(32)
 zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
 {
-    extern __shared__ __align__(16) u8 smem[];
-    u8*  const ring = smem;                                       /* input staging, CAND_RING bytes */
-    u16* const table = reinterpret_cast<u16*>(smem + CAND_RING);
+    __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
+    extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog entries */
     u32 const lane = threadIdx.x;
     ZbBlock const bd = blocks[blockIdx.x];
     if (bd.size < 7u) return;                                    /* zstd_compress.c:3216 : block goes out raw */
     u16* const mydist = dist + (size_t)blockIdx.x * ZB_BLOCK_MAX;
     const u8* const base = src + bd.srcOff - bd.histLen;          /* rel position 0 = oldest visible byte */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
-    u32 const mls = prm.mls, hlog = prm.hashLog, period = prm.insPeriod;
+    u32 const hlog = prm.hashLog, period = prm.insPeriod;
 
     /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
     u32 const o0 = (u32)((uintptr_t)base & 15u);
@@ -104,18 +104,26 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
         /* chunk c and (for the 8-byte reads that straddle its end) chunk c+1 must have landed */
         __pipeline_wait_prior(CAND_STAGES - 2u);
         __syncwarp();
-#pragma unroll 4
+        /* phase A: the 16 steps' hashes are independent of the table: compute them back to back */
+        u32 hh[CAND_CHUNK / 32u];
+#pragma unroll
         for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
             u32 const q = c * CAND_CHUNK + 32u * j + lane;
-            bool const act = (q >= o0) && (q - o0 < nPos);
-            u32 const p = q - o0;
             u32 const w = (q & ~3u) & (CAND_RING - 1u);
             u32 const sh = (q & 3u) * 8u;
             u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
             u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
             u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
             u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-            u32 const h = act ? zb_hash(v, mls, hlog) : 0u;
+            hh[j] = zb_hash(v, MLS, hlog);
+        }
+        /* phase B: the table walk proper, one step after the other */
+#pragma unroll
+        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
+            u32 const q = c * CAND_CHUNK + 32u * j + lane;
+            bool const act = (q >= o0) && (q - o0 < nPos);
+            u32 const p = q - o0;
+            u32 const h = act ? hh[j] : 0u;
             bool const ins = act && ph < 2u;
             /* read the bucket, let every inserting lane write it, read it back: when no two inserting
              * lanes share a bucket (the common case) the read-back alone resolves the step */
@@ -199,26 +207,39 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
         u32 const step = prm.stepSize + ((ip - searchStart) >> 7);           /* kSearchStrength = 8 */
         u32 const p = ip + (lane >> 1) * step + (lane & 1u);
         bool const act = (p + 8u <= be);
-        u32 const cur = act ? zb_ld32u(base + p) : 0u;
-        u32 const d = act ? (u32)mydist[p - bs] : 0u;
+        u32 const pp = act ? p : ip;                         /* a position every lane may load from (ip + 8 <= be) */
+        u32 const d = act ? (u32)mydist[pp - bs] : 0u;
         bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
         bool const v2 = act && rep1 != 0u && p >= rep1;
         bool const v1 = act && d != 0u;
-        u32 const r3 = v3 ? zb_ld32u(base + p - rep2) : ~cur;
-        u32 const r2 = v2 ? zb_ld32u(base + p - rep1) : ~cur;
-        u32 const r1 = v1 ? zb_ld32u(base + p - d) : ~cur;
-        u32 const hit = (r3 == cur) ? 3u : ((r2 == cur) ? 2u : ((r1 == cur) ? 1u : 0u));
+        /* all loads of the step are issued back to back: current window, repcode windows, candidate window */
+        u32 pre, cur, pre2, cur2, pre1, cur1;
+        zb_ld_pre_cur(base, pp, &pre, &cur);
+        u32 const cur3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));
+        zb_ld_pre_cur(base, v2 ? pp - rep1 : pp, &pre2, &cur2);
+        zb_ld_pre_cur(base, v1 ? pp - d : pp, &pre1, &cur1);
+        u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : ((v1 && cur1 == cur) ? 1u : 0u));
         u32 const bal = __ballot_sync(ZB_FULL, hit != 0u);
         if (bal == 0u) { ip += 16u * step; continue; }
+        /* backward catch-up (zstd_fast.c:387-391), first 4 bytes in-lane from the windows already loaded */
+        u32 myback = 0, mymore = 0;
+        if (hit == 1u || hit == 2u) {
+            u32 const off = (hit == 2u) ? rep1 : d;
+            u32 const x = (hit == 2u) ? (pre ^ pre2) : (pre ^ pre1);
+            u32 const bm = x ? ((u32)__clz((int)x) >> 3) : 4u;
+            u32 lim = p - anchor; lim = lim < 4u ? lim : 4u;
+            u32 const src0 = p - off; lim = lim < src0 ? lim : src0;
+            myback = bm < lim ? bm : lim;
+            mymore = (bm == 4u && lim == 4u) ? 1u : 0u;
+        }
         int const winner = __ffs((int)bal) - 1;
         u32 const probe = __shfl_sync(ZB_FULL, p, winner);
         u32 const wtype = __shfl_sync(ZB_FULL, hit, winner);
         u32 const wd = __shfl_sync(ZB_FULL, d, winner);
+        u32 back = __shfl_sync(ZB_FULL, myback, winner);
+        u32 const more = __shfl_sync(ZB_FULL, mymore, winner);
         u32 const offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
-
-        /* backward catch-up (zstd_fast.c:387-391) */
-        u32 back = 0;
-        if (wtype != 3u) {
+        if (more) {                                             /* rare: more than 4 bytes of catch-up */
             while (true) {
                 u32 const k = back + lane + 1u;                /* compare bytes probe-k and probe-offset-k */
                 bool const ok = (probe >= anchor + k) && (probe >= offset + k)
@@ -258,14 +279,14 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks,
                                        u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    size_t const smem = ((size_t)2 << prm->hashLog) + CAND_RING;
-    static int configured = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(zb_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = 1;
+    size_t const smem = (size_t)2 << prm->hashLog;
+    switch (prm->mls) {        /* 2^hashLog u16 <= 32 KiB: below the 48 KiB default dynamic shared memory limit */
+    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
+    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
+    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
+    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
+    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
     }
-    zb_cand_kernel<<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist);
     if (evMid) cudaEventRecord(evMid, stream);
     zb_parse_kernel<<<(nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     return cudaGetLastError();
