@@ -93,8 +93,13 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     __syncwarp();
 
     u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
-    u32 ph = (lane + period - (o0 % period) + bd.insPhase) % period;   /* pattern phase of q = lane */
+    u32 const phase0 = (period - (o0 % period) + bd.insPhase) % period;   /* pattern phase of q = 0 */
+    u32 ph = (lane + phase0) % period;                            /* pattern phase of this lane's q in the current step */
     u32 const inc = 32u % period;
+    /* chunks that lie entirely inside the history only have to leave their inserted positions in the
+     * table (nobody asks for their candidates): they are walked pair-wise, 16 pairs = 16*period
+     * positions per step, without any look-up */
+    u32 const nPrimeChunks = (o0 + bs) / CAND_CHUNK;
     for (u32 c = 0; c < nChunks; c++) {
         {   u32 const cn = c + CAND_STAGES - 1u;                  /* refill the slot consumed in the previous iteration */
             u32 const q = cn * CAND_CHUNK + 16u * lane;
@@ -104,8 +109,54 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
         /* chunk c and (for the 8-byte reads that straddle its end) chunk c+1 must have landed */
         __pipeline_wait_prior(CAND_STAGES - 2u);
         __syncwarp();
+        if (c < nPrimeChunks) {
+            /* first pair start at or after the chunk start: q0 with (q0 + phase0) % period == 0 */
+            u32 const cq = c * CAND_CHUNK;
+            u32 const r = (cq + phase0) % period;
+            u32 const first = cq + (r ? period - r : 0u);
+            /* a pair that straddles the chunk start has its second element here: it precedes every
+             * pair of this chunk, so it is written first */
+            if (((cq + phase0) % period) == 1u && lane == 0u && cq >= o0 && cq - o0 < nPos) {
+                u32 const q = cq, p = q - o0;
+                u32 const w = (q & ~3u) & (CAND_RING - 1u);
+                u32 const sh = (q & 3u) * 8u;
+                u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
+                u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
+                u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
+                u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
+                table[zb_hash(v, MLS, hlog)] = (u16)p;
+            }
+            __syncwarp();
+            for (u32 g0 = first; g0 < cq + CAND_CHUNK; g0 += 16u * period) {
+                u32 const q = g0 + (lane >> 1) * period + (lane & 1u);
+                bool const act = (q >= o0) && (q < cq + CAND_CHUNK) && (q - o0 < nPos);
+                u32 const p = q - o0;
+                u32 const w = (q & ~3u) & (CAND_RING - 1u);
+                u32 const sh = (q & 3u) * 8u;
+                u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
+                u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
+                u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
+                u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
+                u32 const h = zb_hash(v, MLS, hlog);
+                if (act) table[h] = (u16)p;
+                __syncwarp();
+                /* the latest position must own the bucket: lanes that lost to an earlier one write again */
+                while (true) {
+                    u32 const diff = act ? ((p - (u32)table[h]) & 0xFFFFu) : 0u;      /* > 0 : an earlier position of this step is stored */
+                    bool const again = diff != 0u && diff <= 16u * period;
+                    if (!__any_sync(ZB_FULL, again)) break;
+                    __syncwarp();
+                    if (again) table[h] = (u16)p;
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            ph += (CAND_CHUNK % period); if (ph >= period) ph -= period;     /* keep the step phase in sync (CAND_CHUNK/32 steps skipped) */
+            continue;
+        }
         /* phase A: the 16 steps' hashes are independent of the table: compute them back to back */
         u32 hh[CAND_CHUNK / 32u];
+        u32 cur4[CAND_CHUNK / 32u];
 #pragma unroll
         for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
             u32 const q = c * CAND_CHUNK + 32u * j + lane;
@@ -116,8 +167,9 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
             u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
             u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
             hh[j] = zb_hash(v, MLS, hlog);
+            cur4[j] = (u32)v;
         }
-        /* phase B: the table walk proper, one step after the other */
+        /* phase B: the table walk proper, one step after the other; hh[j] becomes the candidate distance */
 #pragma unroll
         for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
             u32 const q = c * CAND_CHUNK + 32u * j + lane;
@@ -162,8 +214,23 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                 if (dn >= 1u && dn <= lane) d = dn;
                 else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
             }
-            if (act && p >= bs) mydist[p - bs] = (u16)d;
+            hh[j] = (act && p >= bs) ? d : 0u;
             ph += inc; if (ph >= period) ph -= period;
+        }
+        /* phase C: 4-byte verification of the 16 candidates (zstd_fast.c:102-141).  This walk keeps only
+         * ~12 blocks per SM in flight, so the <=64 KiB windows it reaches back into stay L2-resident;
+         * doing the check here leaves the (much wider) parse kernel without random loads. */
+        u32 cand4[CAND_CHUNK / 32u];
+#pragma unroll
+        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
+            u32 const p = c * CAND_CHUNK + 32u * j + lane - o0;      /* hh[j] != 0 implies an active lane with p >= hh[j] */
+            cand4[j] = zb_ld32w2(base + (hh[j] ? p - hh[j] : 0u));
+        }
+#pragma unroll
+        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
+            u32 const q = c * CAND_CHUNK + 32u * j + lane;
+            u32 const p = q - o0;
+            if ((q >= o0) && (p < nPos) && (p >= bs)) mydist[p - bs] = (hh[j] != 0u && cand4[j] == cur4[j]) ? (u16)hh[j] : (u16)0;
         }
     }
     for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
@@ -212,23 +279,23 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
         bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
         bool const v2 = act && rep1 != 0u && p >= rep1;
         bool const v1 = act && d != 0u;
-        /* all loads of the step are issued back to back: current window, repcode windows, candidate window */
-        u32 pre, cur, pre2, cur2, pre1, cur1;
+        /* dist[] only holds candidates K1a has already verified (4 equal bytes), so a step needs no random
+         * load: the current window and the repcode windows are contiguous across lanes */
+        u32 pre, cur, pre2, cur2;
         zb_ld_pre_cur(base, pp, &pre, &cur);
-        u32 const cur3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));
         zb_ld_pre_cur(base, v2 ? pp - rep1 : pp, &pre2, &cur2);
-        zb_ld_pre_cur(base, v1 ? pp - d : pp, &pre1, &cur1);
-        u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : ((v1 && cur1 == cur) ? 1u : 0u));
+        u32 cur3 = ~cur;
+        if (ip == anchor && rep2 != 0u) cur3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));     /* warp-uniform condition */
+        u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
         u32 const bal = __ballot_sync(ZB_FULL, hit != 0u);
         if (bal == 0u) { ip += 16u * step; continue; }
-        /* backward catch-up (zstd_fast.c:387-391), first 4 bytes in-lane from the windows already loaded */
-        u32 myback = 0, mymore = 0;
-        if (hit == 1u || hit == 2u) {
-            u32 const off = (hit == 2u) ? rep1 : d;
-            u32 const x = (hit == 2u) ? (pre ^ pre2) : (pre ^ pre1);
+        /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
+        u32 myback = 0, mymore = (hit == 1u) ? 1u : 0u;
+        if (hit == 2u) {
+            u32 const x = pre ^ pre2;
             u32 const bm = x ? ((u32)__clz((int)x) >> 3) : 4u;
             u32 lim = p - anchor; lim = lim < 4u ? lim : 4u;
-            u32 const src0 = p - off; lim = lim < src0 ? lim : src0;
+            u32 const src0 = p - rep1; lim = lim < src0 ? lim : src0;
             myback = bm < lim ? bm : lim;
             mymore = (bm == 4u && lim == 4u) ? 1u : 0u;
         }
@@ -239,7 +306,7 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
         u32 back = __shfl_sync(ZB_FULL, myback, winner);
         u32 const more = __shfl_sync(ZB_FULL, mymore, winner);
         u32 const offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
-        if (more) {                                             /* rare: more than 4 bytes of catch-up */
+        if (more) {                                             /* table hit, or a repcode hit with > 4 bytes of catch-up */
             while (true) {
                 u32 const k = back + lane + 1u;                /* compare bytes probe-k and probe-offset-k */
                 bool const ok = (probe >= anchor + k) && (probe >= offset + k)
