@@ -69,6 +69,26 @@ __device__ void zb_hist_stats(const u32* count, u32* red, u32* largestOut, u32* 
     __syncthreads();
 }
 
+
+/* Visit the symbols of lit[beg, end) from the LAST to the first (the order the Huffman stream is
+ * written in, huf_compress.c:1056-1118) with 16-byte aligned vector loads: a thread's run is
+ * contiguous, so byte loads would cost one request per symbol. */
+template <typename F>
+__device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ lit, u32 beg, u32 end, F f)
+{
+    u32 const aBeg = (beg + 15u) & ~15u, aEnd = end & ~15u;
+    if (aBeg >= aEnd) { for (u32 i = end; i-- > beg; ) f(lit[i]); return; }
+    for (u32 i = end; i-- > aEnd; ) f(lit[i]);
+    const uint4* v4 = reinterpret_cast<const uint4*>(lit);
+    for (u32 k = aEnd / 16u; k-- > aBeg / 16u; ) {
+        uint4 const q = __ldg(v4 + k);
+        u32 const w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int t = 3; t >= 0; t--) { f((u8)(w[t] >> 24)); f((u8)(w[t] >> 16)); f((u8)(w[t] >> 8)); f((u8)w[t]); }
+    }
+    for (u32 i = aBeg; i-- > beg; ) f(lit[i]);
+}
+
 __global__ void __launch_bounds__(LIT_THREADS)
 zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
                    const u8* __restrict__ lits, u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
@@ -150,7 +170,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
     if (mode == MODE_HUF) {
         hSize = sh_hSize;
         u32 bits = 0;
-        for (u32 i = cBeg; i < cEnd; i++) bits += enc[lit[i]] >> 16;
+        zb_for_each_symbol_rev(lit, cBeg, cEnd, [&](u8 sym) { bits += enc[sym] >> 16; });
         chunkBits[tid] = bits;
         __syncthreads();
         /* suffix sum inside the stream: symbols AFTER mine are written before mine */
@@ -217,7 +237,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
         u32 sOff = lhSize + hSize + (nbStreams == 4u ? 6u : 0u);
         for (u32 k = 0; k < s; k++) sOff += sh_streamSize[k];
         ZbdParW pw; zbd_pw_init(&pw, reinterpret_cast<u32*>(out), (u64)sOff * 8u + bitOff);
-        for (u32 i = cEnd; i-- > cBeg; ) { u32 const e = enc[lit[i]]; zbd_pw_add(&pw, e & 0xFFFFu, e >> 16); }
+        zb_for_each_symbol_rev(lit, cBeg, cEnd, [&](u8 sym) { u32 const e = enc[sym]; zbd_pw_add(&pw, e & 0xFFFFu, e >> 16); });
         if (j == 0) zbd_pw_add(&pw, 1u, 1u);
         zbd_pw_finish(&pw);
     }

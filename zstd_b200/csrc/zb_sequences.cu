@@ -18,7 +18,7 @@
 #include "zb_kernels.h"
 #include "zb_bitpack.cuh"
 
-#define SEQ_THREADS 256
+#define SEQ_THREADS 128
 #define MaxLL 35
 #define MaxML 52
 #define MaxOff 31
@@ -128,7 +128,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         cSize = op;
     } else {
         /* ---- 1. codes + histograms ---- */
-        if (tid < 192u) wk[tid >> 6].count[tid & 63u] = 0;
+        for (u32 i = tid; i < 192u; i += SEQ_THREADS) wk[i >> 6].count[i & 63u] = 0;
         __syncthreads();
         for (u32 i = tid; i < nbSeq; i += SEQ_THREADS) {
             ZbdSeq const s = zbd_unpack(myseq[i]);
@@ -185,11 +185,18 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             u16* const rec = myst + (size_t)st * ZB_STATE_STRIDE;
             ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
             u32 state = zbd_fse_initState2(t, st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc));
-            for (u32 i = nbSeq - 1; i-- > 0; ) {
-                ZbdSeq const s = zbd_unpack(myseq[i]);
-                u32 bits, nb;
-                state = zbd_fse_step(t, state, st == 0 ? s.llc : (st == 1 ? s.ofc : s.mlc), &bits, &nb);
-                rec[i] = (u16)(bits | (nb << 12));
+            /* the only loop-carried value is `state` (common/fse.h:463-470); the next sequence and its
+             * table row are fetched one step ahead so the chain is ALU + one LDS per symbol */
+            u64 nq = nbSeq >= 2u ? myseq[nbSeq - 2u] : 0ull;
+            for (u32 i = nbSeq - 1u; i-- > 0; ) {
+                ZbdSeq const s = zbd_unpack(nq);
+                if (i > 0) nq = myseq[i - 1u];
+                u32 const sym = st == 0 ? s.llc : (st == 1 ? s.ofc : s.mlc);
+                u32 const dnb = t->deltaNbBits[sym];
+                int const dfs = t->deltaFindState[sym];
+                u32 const nb = (state + dnb) >> 16;
+                rec[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+                state = t->nextState[(int)(state >> nb) + dfs];
             }
             wk[st].finalState = state;
         }
