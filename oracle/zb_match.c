@@ -85,21 +85,26 @@ void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
  * frame position ((pos % insPeriod) < 2 : the reference also probes/inserts position pairs spaced by
  * `step`, zstd_fast.c:225-229), independent of the parse, which is what lets the walk run ahead of —
  * and in parallel with — the greedy selection.  Table entries are 16-bit positions modulo 64 KiB
- * relative to the oldest visible byte (reach 65535). */
+ * relative to the oldest visible byte (reach 65535) plus an 8-bit tag (further hash bits). */
 static void candidates_walk(const u8* frame, size_t lowLimit, size_t bs, size_t be,
                             u32 mls, u32 hlog, u32 insPeriod, u16* dist)
 {
     u16* const table = (u16*)calloc((size_t)1 << hlog, sizeof(u16));
+    u8*  const tags  = (u8*)calloc((size_t)1 << hlog, 1);
     for (size_t p = lowLimit; p + 8 <= be; p++) {
-        u32 const h = zb_hash(rd64(frame + p), mls, hlog);
+        /* bucket = top hlog bits of the hash, tag = the next 8 bits: a bucket hit whose tag differs is a
+         * different string and is dropped here, so the parse never has to load it */
+        u32 const h24 = zb_hash(rd64(frame + p), mls, hlog + 8);
+        u32 const h = h24 >> 8;
+        u8  const tag = (u8)h24;
         u32 const rel = (u32)(p - lowLimit);
         u32 d = (rel - table[h]) & 0xFFFFu;
-        if (d == 0 || d > rel) d = 0;
+        if (d == 0 || d > rel || tags[h] != tag) d = 0;
         if (p >= bs) dist[p - bs] = (u16)d;
-        if ((p % insPeriod) < 2) table[h] = (u16)rel;
+        if ((p % insPeriod) < 2) { table[h] = (u16)rel; tags[h] = tag; }
     }
     for (size_t p = (be >= 8 && be - 7 > bs) ? be - 7 : bs; p < be; p++) dist[p - bs] = 0;   /* no 8-byte read there */
-    free(table);
+    free(table); free(tags);
 }
 
 typedef struct { zbo_seq* seqs; size_t nbSeq; u8* lit; size_t litSize; const u8* frame; } emitter;

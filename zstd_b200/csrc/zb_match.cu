@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32)
 zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
 {
     __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
-    extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog entries */
+    extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog positions, followed by 2^hashLog tags */
     u32 const lane = threadIdx.x;
     ZbBlock const bd = blocks[blockIdx.x];
     if (bd.size < 7u) return;                                    /* zstd_compress.c:3216 : block goes out raw */
@@ -72,6 +72,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     const u8* const base = src + bd.srcOff - bd.histLen;          /* rel position 0 = oldest visible byte */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     u32 const hlog = prm.hashLog, period = prm.insPeriod;
+    u8* const tags = reinterpret_cast<u8*>(table + ((size_t)1 << hlog));   /* 8 further hash bits per bucket */
 
     /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
     u32 const o0 = (u32)((uintptr_t)base & 15u);
@@ -80,7 +81,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     u32 const nChunks = (qEnd + CAND_CHUNK - 1u) / CAND_CHUNK;
 
     {   uint4* t4 = reinterpret_cast<uint4*>(table);
-        u32 const n4 = (2u << hlog) / 16u;
+        u32 const n4 = (3u << hlog) / 16u;
         for (u32 i = lane; i < n4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
     }
     /* prologue: chunks 0 .. STAGES-2 in flight */
@@ -124,7 +125,8 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                 u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
                 u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
                 u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-                table[zb_hash(v, MLS, hlog)] = (u16)p;
+                u32 const h24 = zb_hash(v, MLS, hlog + 8u);
+                table[h24 >> 8] = (u16)p; tags[h24 >> 8] = (u8)h24;
             }
             __syncwarp();
             for (u32 g0 = first; g0 < cq + CAND_CHUNK; g0 += 16u * period) {
@@ -137,7 +139,8 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                 u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
                 u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
                 u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-                u32 const h = zb_hash(v, MLS, hlog);
+                u32 const h24 = zb_hash(v, MLS, hlog + 8u);
+                u32 const h = h24 >> 8;
                 if (act) table[h] = (u16)p;
                 __syncwarp();
                 /* the latest position must own the bucket: lanes that lost to an earlier one write again */
@@ -149,6 +152,8 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                     if (again) table[h] = (u16)p;
                     __syncwarp();
                 }
+                if (act && table[h] == (u16)p) tags[h] = (u8)h24;       /* the bucket's owner sets its tag */
+                __syncwarp();
             }
             __syncwarp();
             ph += (CAND_CHUNK % period); if (ph >= period) ph -= period;     /* keep the step phase in sync (CAND_CHUNK/32 steps skipped) */
@@ -156,7 +161,6 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
         }
         /* phase A: the 16 steps' hashes are independent of the table: compute them back to back */
         u32 hh[CAND_CHUNK / 32u];
-        u32 cur4[CAND_CHUNK / 32u];
 #pragma unroll
         for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
             u32 const q = c * CAND_CHUNK + 32u * j + lane;
@@ -166,8 +170,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
             u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
             u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
             u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-            hh[j] = zb_hash(v, MLS, hlog);
-            cur4[j] = (u32)v;
+            hh[j] = zb_hash(v, MLS, hlog + 8u);                 /* bucket << 8 | tag */
         }
         /* phase B: the table walk proper, one step after the other; hh[j] becomes the candidate distance */
 #pragma unroll
@@ -175,15 +178,18 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
             u32 const q = c * CAND_CHUNK + 32u * j + lane;
             bool const act = (q >= o0) && (q - o0 < nPos);
             u32 const p = q - o0;
-            u32 const h = act ? hh[j] : 0u;
+            u32 const h = act ? (hh[j] >> 8) : 0u;
+            u32 const tag = hh[j] & 0xFFu;
             bool const ins = act && ph < 2u;
             /* read the bucket, let every inserting lane write it, read it back: when no two inserting
              * lanes share a bucket (the common case) the read-back alone resolves the step */
             u32 const old = act ? table[h] : 0u;
+            u32 const oldtag = act ? tags[h] : 0x100u;
             __syncwarp();
-            if (ins) table[h] = (u16)p;
+            if (ins) { table[h] = (u16)p; tags[h] = (u8)tag; }
             __syncwarp();
             u32 const nw = act ? table[h] : 0u;
+            u32 const nwtag = act ? tags[h] : 0x100u;
             u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
             u32 d = 0;
             bool resolved = false;
@@ -198,12 +204,14 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                     bool const mine = act && h == hl;
                     u32 const grpAll = __ballot_sync(ZB_FULL, mine);
                     u32 const grpIns = grpAll & insmask;
+                    u32 const lower = mine ? (grpIns & ((1u << lane) - 1u)) : 0u;
+                    u32 const lowLane = lower ? (31u - (u32)__clz((int)lower)) : lane;
+                    u32 const lowTag = __shfl_sync(ZB_FULL, tag, (int)lowLane);
                     if (mine) {
-                        u32 const lower = grpIns & ((1u << lane) - 1u);
-                        if (lower) d = lane - (31u - (u32)__clz((int)lower));
-                        else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
+                        if (lower) d = (lowTag == tag) ? lane - lowLane : 0u;
+                        else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
                         resolved = true;
-                        if ((31u - (u32)__clz((int)grpIns)) == lane) table[h] = (u16)p;
+                        if ((31u - (u32)__clz((int)grpIns)) == lane) { table[h] = (u16)p; tags[h] = (u8)tag; }
                     }
                     losers &= ~grpAll;
                 }
@@ -211,26 +219,11 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
             }
             if (!resolved) {
                 u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
-                if (dn >= 1u && dn <= lane) d = dn;
-                else { d = (p - old) & 0xFFFFu; if (d > p) d = 0u; }
+                if (dn >= 1u && dn <= lane) d = (nwtag == tag) ? dn : 0u;
+                else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
             }
-            hh[j] = (act && p >= bs) ? d : 0u;
+            if (act && p >= bs) mydist[p - bs] = (u16)d;
             ph += inc; if (ph >= period) ph -= period;
-        }
-        /* phase C: 4-byte verification of the 16 candidates (zstd_fast.c:102-141).  This walk keeps only
-         * ~12 blocks per SM in flight, so the <=64 KiB windows it reaches back into stay L2-resident;
-         * doing the check here leaves the (much wider) parse kernel without random loads. */
-        u32 cand4[CAND_CHUNK / 32u];
-#pragma unroll
-        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
-            u32 const p = c * CAND_CHUNK + 32u * j + lane - o0;      /* hh[j] != 0 implies an active lane with p >= hh[j] */
-            cand4[j] = zb_ld32w2(base + (hh[j] ? p - hh[j] : 0u));
-        }
-#pragma unroll
-        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
-            u32 const q = c * CAND_CHUNK + 32u * j + lane;
-            u32 const p = q - o0;
-            if ((q >= o0) && (p < nPos) && (p >= bs)) mydist[p - bs] = (hh[j] != 0u && cand4[j] == cur4[j]) ? (u16)hh[j] : (u16)0;
         }
     }
     for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
@@ -287,10 +280,9 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
         u32 cur3 = ~cur;
         if (ip == anchor && rep2 != 0u) cur3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));     /* warp-uniform condition */
         u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
-        u32 const bal = __ballot_sync(ZB_FULL, hit != 0u);
-        if (bal == 0u) { ip += 16u * step; continue; }
+        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
-        u32 myback = 0, mymore = (hit == 1u) ? 1u : 0u;
+        u32 myback = 0, mymore = 0;
         if (hit == 2u) {
             u32 const x = pre ^ pre2;
             u32 const bm = x ? ((u32)__clz((int)x) >> 3) : 4u;
@@ -299,26 +291,44 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
             myback = bm < lim ? bm : lim;
             mymore = (bm == 4u && lim == 4u) ? 1u : 0u;
         }
-        int const winner = __ffs((int)bal) - 1;
-        u32 const probe = __shfl_sync(ZB_FULL, p, winner);
-        u32 const wtype = __shfl_sync(ZB_FULL, hit, winner);
-        u32 const wd = __shfl_sync(ZB_FULL, d, winner);
-        u32 back = __shfl_sync(ZB_FULL, myback, winner);
-        u32 const more = __shfl_sync(ZB_FULL, mymore, winner);
-        u32 const offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
-        if (more) {                                             /* table hit, or a repcode hit with > 4 bytes of catch-up */
-            while (true) {
-                u32 const k = back + lane + 1u;                /* compare bytes probe-k and probe-offset-k */
-                bool const ok = (probe >= anchor + k) && (probe >= offset + k)
-                             && (base[probe - k] == base[probe - offset - k]);
-                u32 const okb = __ballot_sync(ZB_FULL, ok);
-                u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
-                back += cnt;
-                if (cnt < 32u) break;
+        /* lowest lane first.  A table hit (type 1) is only tag-verified by K1a: its bytes are checked while
+         * the match is extended (one round trip, this lane only); a false positive drops out and the next
+         * lane is tried — the result is "lowest lane whose hit is real", what the oracle computes. */
+        u32 probe = 0, wtype = 0, offset = 0, back = 0, fwdFrom4 = 0;
+        bool found = false;
+        while (tent) {
+            int const winner = __ffs((int)tent) - 1;
+            probe = __shfl_sync(ZB_FULL, p, winner);
+            wtype = __shfl_sync(ZB_FULL, hit, winner);
+            u32 const wd = __shfl_sync(ZB_FULL, d, winner);
+            back = __shfl_sync(ZB_FULL, myback, winner);
+            u32 more = __shfl_sync(ZB_FULL, mymore, winner);
+            offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
+            if (wtype == 1u) {
+                u32 const f0 = zb_count_fwd(base, probe, offset, be, lane);          /* from the probe itself */
+                if (f0 < 4u) { tent &= ~(1u << winner); continue; }                   /* tag collision */
+                fwdFrom4 = f0 - 4u;
+                more = 1u;
+            } else {
+                fwdFrom4 = zb_count_fwd(base, probe + 4u, offset, be, lane);
             }
+            if (more) {                                         /* table hit, or a repcode hit with > 4 bytes of catch-up */
+                while (true) {
+                    u32 const k = back + lane + 1u;            /* compare bytes probe-k and probe-offset-k */
+                    bool const ok = (probe >= anchor + k) && (probe >= offset + k)
+                                 && (base[probe - k] == base[probe - offset - k]);
+                    u32 const okb = __ballot_sync(ZB_FULL, ok);
+                    u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
+                    back += cnt;
+                    if (cnt < 32u) break;
+                }
+            }
+            found = true;
+            break;
         }
+        if (!found) { ip += 16u * step; continue; }
         u32 const ms = probe - back;
-        u32 const mlen = back + 4u + zb_count_fwd(base, probe + 4u, offset, be, lane);
+        u32 const mlen = back + 4u + fwdFrom4;
         u32 const litLen = ms - anchor;
         u32 offBase;
         if (wtype == 3u) { offBase = 1u; u32 const t = rep2; rep2 = rep1; rep1 = t; }   /* litLength 0: code 1 = repcode 2 */
@@ -346,7 +356,7 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks,
                                        u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    size_t const smem = (size_t)2 << prm->hashLog;
+    size_t const smem = (size_t)3 << prm->hashLog;       /* u16 positions + u8 tags */
     switch (prm->mls) {        /* 2^hashLog u16 <= 32 KiB: below the 48 KiB default dynamic shared memory limit */
     case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
     case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
