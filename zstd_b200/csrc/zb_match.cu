@@ -237,6 +237,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
  * :410-420), repcode-1 (:281-297), table candidate with 4-byte check (:102-141).  Lowest lane wins.
  * ---------------------------------------------------------------------------------------------- */
 #define PARSE_WARPS 4
+#define PARSE_PF_AHEAD 2048u
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
 zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
                 const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
@@ -262,8 +263,20 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
 
     u32 ip = bs, anchor = bs, searchStart = bs;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
+    u32 pf = bs;                                             /* input and dist[] below this position are on their way to L2 */
 
     while (ip + 8u <= be) {
+        /* the warp consumes its block front to back but every step waits for its loads: keep the next
+         * PARSE_PF_AHEAD bytes of input (and their dist[] entries) streaming into L2, one 128-byte line per lane */
+        if (ip + PARSE_PF_AHEAD > pf && pf < be) {
+            u32 const a = pf + 128u * lane;
+            if (a < be) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs)));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs) + 64));
+            }
+            pf += 128u * 32u;
+        }
         u32 const step = prm.stepSize + ((ip - searchStart) >> 7);           /* kSearchStrength = 8 */
         u32 const p = ip + (lane >> 1) * step + (lane & 1u);
         bool const act = (p + 8u <= be);
