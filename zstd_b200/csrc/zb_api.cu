@@ -92,13 +92,14 @@ struct ZSTD_CCtx_s {
     int device;
     cudaStream_t stream;
     /* per-block workspace */
-    size_t capBlocks, capFrames;
+    size_t capBlocks, capFrames, capHeavy, capWaves;
+    cudaStream_t waveStream[8];
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
-    u64* d_outOffsets; u64* d_frameSizes; u64* d_total;
+    u64* d_outOffsets; u64* d_frameSizes; u64* d_totals;    /* d_totals[w]: bytes produced up to and including wave w */
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
-    u64* h_total;                  /* pinned */
+    u64* h_totals;                 /* pinned mirror of d_totals */
     cudaEvent_t evStart, evK0, evMid, evK1, evK2, evK3, evKEnd, evEnd;
     ZSTDB200_stats stats;
 };
@@ -136,18 +137,17 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
     CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evK0)); CK(cudaEventCreate(&c->evK1));
     CK(cudaEventCreate(&c->evK2)); CK(cudaEventCreate(&c->evK3)); CK(cudaEventCreate(&c->evMid));
     CK(cudaEventCreate(&c->evKEnd)); CK(cudaEventCreate(&c->evEnd));
-    CK(cudaMallocHost(&c->h_total, 64));
-    CK(cudaMalloc(&c->d_total, 64));
     return 0;
 }
 
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
+    cudaFreeHost(c->h_totals);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
-    c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL;
-    c->capBlocks = 0; c->capFrames = 0;
+    c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL; c->d_totals = NULL; c->h_totals = NULL;
+    c->capBlocks = 0; c->capFrames = 0; c->capHeavy = 0; c->capWaves = 0;
 }
 
 extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
@@ -156,8 +156,8 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
-        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_total);
-        cudaFreeHost(c->h_total);
+        cudaFree(c->d_in); cudaFree(c->d_out);
+        for (int s = 0; s < 8; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
         cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
         cudaEventDestroy(c->evKEnd); cudaEventDestroy(c->evEnd);
@@ -167,42 +167,59 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     return 0;
 }
 
-static size_t zb_ensureWorkspace(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames)
+/* descriptors (per block / per frame, small) and the heavy per-block workspace are sized separately:
+ * the host-pointer path runs the blocks in waves that share a few workspace slots */
+static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size_t nbWaves)
 {
-    if (nbBlocks > c->capBlocks || nbFrames > c->capFrames) {
-        size_t const nb = nbBlocks > c->capBlocks ? nbBlocks : c->capBlocks;
-        size_t const nf = nbFrames > c->capFrames ? nbFrames : c->capFrames;
-        zb_freeWorkspace(c);
-        CK(cudaMalloc(&c->d_blocks, nb * sizeof(ZbBlock)));
-        CK(cudaMalloc(&c->d_frames, nf * sizeof(ZbFrame)));
+    if (nbBlocks > c->capBlocks) {
+        cudaFree(c->d_blocks); cudaFree(c->d_outOffsets); c->d_blocks = NULL; c->d_outOffsets = NULL; c->capBlocks = 0;
+        CK(cudaMalloc(&c->d_blocks, nbBlocks * sizeof(ZbBlock)));
+        CK(cudaMalloc(&c->d_outOffsets, (nbBlocks + 1) * sizeof(u64)));
+        c->capBlocks = nbBlocks;
+    }
+    if (nbFrames > c->capFrames) {
+        cudaFree(c->d_frames); cudaFree(c->d_frameSizes); c->d_frames = NULL; c->d_frameSizes = NULL; c->capFrames = 0;
+        CK(cudaMalloc(&c->d_frames, nbFrames * sizeof(ZbFrame)));
+        CK(cudaMalloc(&c->d_frameSizes, nbFrames * sizeof(u64)));
+        c->capFrames = nbFrames;
+    }
+    if (nbWaves > c->capWaves) {
+        cudaFree(c->d_totals); cudaFreeHost(c->h_totals); c->d_totals = NULL; c->h_totals = NULL; c->capWaves = 0;
+        CK(cudaMalloc(&c->d_totals, nbWaves * sizeof(u64)));
+        CK(cudaMallocHost(&c->h_totals, nbWaves * sizeof(u64)));
+        c->capWaves = nbWaves;
+    }
+    return 0;
+}
+static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks)
+{
+    if (nbSlotBlocks > c->capHeavy) {
+        cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits); cudaFree(c->d_body); cudaFree(c->d_dist);
+        c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL; c->d_body = NULL; c->d_dist = NULL; c->capHeavy = 0;
+        size_t const nb = nbSlotBlocks;
         CK(cudaMalloc(&c->d_meta, nb * sizeof(ZbBlockMeta)));
         CK(cudaMalloc(&c->d_seqs, nb * ZB_SEQ_STRIDE * sizeof(u64)));
         CK(cudaMalloc(&c->d_lits, nb * (size_t)ZB_LIT_STRIDE));
         CK(cudaMalloc(&c->d_body, nb * (size_t)ZB_BODY_STRIDE));
         CK(cudaMalloc(&c->d_dist, nb * (size_t)ZB_BLOCK_MAX * sizeof(u16)));
-        CK(cudaMalloc(&c->d_outOffsets, (nb + 1) * sizeof(u64)));
-        CK(cudaMalloc(&c->d_frameSizes, nf * sizeof(u64)));
-        c->capBlocks = nb; c->capFrames = nf;
+        c->capHeavy = nb;
     }
     return 0;
 }
 
-/* ------------------------------------------------------------------ core: frames already in device memory */
-static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacity, const u8* d_src,
-                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
-                                      const void* dict, size_t dictSize, size_t* cSizes, int level, cudaStream_t stream)
+/* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
+struct ZbGroup { ZbParams prm; u32 b0, b1; };
+struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; };
+
+static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level)
 {
-    if (dict && dictSize) return ZB_ERR(ZB_error_parameter_unsupported);   /* dictionary path: next §8 row */
-    std::vector<ZbBlock> blocks;
-    std::vector<ZbFrame> frames(nbFrames);
-    struct Group { ZbParams prm; u32 b0, b1; };
-    std::vector<Group> groups;
+    P.frames.resize(nbFrames);
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
         ZbCParams const cp = zb_getCParams(level, fsz, 0);
         ZbParams const prm = zb_makeParams(cp);
         size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
-        ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)blocks.size();
+        ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)P.blocks.size();
         fr.windowLog = cp.windowLog; fr.dictID = 0;
         u64 pos = 0;
         do {
@@ -211,48 +228,65 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
             b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
             b.insPhase = (u32)((pos - b.histLen) % prm.insPeriod); b.pad = 0;
             b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
-            blocks.push_back(b);
+            P.blocks.push_back(b);
             pos += bsz;
         } while (pos < fsz);
-        fr.nbBlocks = (u32)blocks.size() - fr.firstBlock;
-        frames[f] = fr;
-        if (groups.empty() || memcmp(&groups.back().prm, &prm, sizeof(prm)) != 0) { Group g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)blocks.size(); groups.push_back(g); }
-        else groups.back().b1 = (u32)blocks.size();
+        fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
+        P.frames[f] = fr;
+        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); P.groups.push_back(g); }
+        else P.groups.back().b1 = (u32)P.blocks.size();
     }
-    u32 const nbBlocks = (u32)blocks.size();
-    {   size_t const e = zb_ensureWorkspace(c, nbBlocks, nbFrames); if (zb_isErr(e)) return e; }
+}
 
-    CK(cudaMemcpyAsync(c->d_blocks, blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(c->d_frames, frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
+/* K1..K3 for blocks [b0, b1) using workspace slot positions [slot0, slot0 + (b1-b0)) */
+static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, u32 b0, u32 b1, size_t slot0,
+                           cudaStream_t stream, bool timed, unsigned* launches)
+{
+    for (int phase = 0; phase < 3; phase++) {
+        for (size_t g = 0; g < P.groups.size(); g++) {
+            ZbGroup const& G = P.groups[g];
+            u32 const lo = G.b0 > b0 ? G.b0 : b0, hi = G.b1 < b1 ? G.b1 : b1;
+            if (lo >= hi) continue;
+            size_t const s = slot0 + (lo - b0);
+            if (phase == 0) {
+                CK(zb_launch_match(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX, c->d_seqs + s * ZB_SEQ_STRIDE,
+                                   c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
+                *launches += 2;
+            } else if (phase == 1) {
+                CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, c->d_lits + s * ZB_LIT_STRIDE, c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
+                *launches += 1;
+            } else {
+                CK(zb_launch_sequences(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_seqs + s * ZB_SEQ_STRIDE, c->d_dist + s * ZB_BLOCK_MAX,
+                                       c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
+                *launches += 1;
+            }
+        }
+        if (timed) CK(cudaEventRecord(phase == 0 ? c->evK1 : (phase == 1 ? c->evK2 : c->evK3), stream));
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ core: frames already in device memory (one wave) */
+static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacity, const u8* d_src,
+                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
+                                      const void* dict, size_t dictSize, size_t* cSizes, int level, cudaStream_t stream)
+{
+    if (dict && dictSize) return ZB_ERR(ZB_error_parameter_unsupported);   /* dictionary path: next §8 row */
+    ZbPlan P;
+    zb_plan(P, frameOffsets, frameSizes, nbFrames, level);
+    u32 const nbBlocks = (u32)P.blocks.size();
+    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
+        e = zb_ensureHeavy(c, nbBlocks); if (zb_isErr(e)) return e; }
+    CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
     unsigned launches = 0;
-    for (size_t g = 0; g < groups.size(); g++) {
-        Group const& G = groups[g];
-        CK(zb_launch_match(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
-                           c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE, c->d_meta + G.b0, groups.size() == 1 ? c->evMid : (cudaEvent_t)0, stream));
-        launches += 2;
-    }
-    CK(cudaEventRecord(c->evK1, stream));
-    for (size_t g = 0; g < groups.size(); g++) {
-        Group const& G = groups[g];
-        CK(zb_launch_literals(c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_lits + (size_t)G.b0 * ZB_LIT_STRIDE,
-                              c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE, c->d_meta + G.b0, stream));
-        launches++;
-    }
-    CK(cudaEventRecord(c->evK2, stream));
-    for (size_t g = 0; g < groups.size(); g++) {
-        Group const& G = groups[g];
-        CK(zb_launch_sequences(d_src, c->d_blocks + G.b0, G.b1 - G.b0, &G.prm, c->d_seqs + (size_t)G.b0 * ZB_SEQ_STRIDE,
-                               c->d_dist + (size_t)G.b0 * ZB_BLOCK_MAX, c->d_body + (size_t)G.b0 * ZB_BODY_STRIDE,
-                               c->d_meta + G.b0, stream));
-        launches++;
-    }
-    CK(cudaEventRecord(c->evK3, stream));
-    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, (u32)nbFrames, c->d_body, c->d_meta,
-                        c->d_outOffsets, c->d_frameSizes, c->d_total, d_dst, dstCapacity, stream));
+    {   size_t const e = zb_runBlocks(c, P, d_src, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
+    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
+    if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
     CK(cudaEventRecord(c->evKEnd, stream));
-    CK(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(u64), cudaMemcpyDeviceToHost, stream));
     if (cSizes) {
         std::vector<u64> tmp(nbFrames);
         CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, stream));
@@ -263,11 +297,98 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     c->stats.nbBlocks = nbBlocks;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evK0, c->evKEnd); c->stats.kernel_ms = ms;
         cudaEventElapsedTime(&ms, c->evK0, c->evK1); c->stats.match_ms = ms;
-        if (groups.size() == 1) { cudaEventElapsedTime(&ms, c->evK0, c->evMid); c->stats.cand_ms = ms; cudaEventElapsedTime(&ms, c->evMid, c->evK1); c->stats.parse_ms = ms; }
+        if (P.groups.size() == 1) { cudaEventElapsedTime(&ms, c->evK0, c->evMid); c->stats.cand_ms = ms; cudaEventElapsedTime(&ms, c->evMid, c->evK1); c->stats.parse_ms = ms; }
         cudaEventElapsedTime(&ms, c->evK1, c->evK2); c->stats.literals_ms = ms;
         cudaEventElapsedTime(&ms, c->evK2, c->evK3); c->stats.sequences_ms = ms;
         cudaEventElapsedTime(&ms, c->evK3, c->evKEnd); c->stats.stitch_ms = ms; }
-    u64 const total = c->h_total[0];
+    u64 const total = c->h_totals[0];
+    if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    return (size_t)total;
+}
+
+/* ------------------------------------------------------------------ host pointers: pipelined waves
+ * H2D copy of wave w+1 | kernels of waves w, w-1, ... (one stream + workspace slot each) | D2H of finished waves.
+ * A block needs ~ms of latency end to end (one warp walks it), so several waves are kept in flight. */
+#define ZB_WAVE_BLOCKS 768u          /* 96 MiB of input per wave */
+#define ZB_WAVE_SLOTS  4u
+
+static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, const u8* src,
+                                    const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
+                                    const void* dict, size_t dictSize, size_t* cSizes, int level)
+{
+    if (dict && dictSize) return ZB_ERR(ZB_error_parameter_unsupported);
+    ZbPlan P;
+    zb_plan(P, frameOffsets, frameSizes, nbFrames, level);
+    u32 const nbBlocks = (u32)P.blocks.size();
+    u32 const nbWaves = (nbBlocks + ZB_WAVE_BLOCKS - 1u) / ZB_WAVE_BLOCKS;
+    u32 const slots = nbWaves < ZB_WAVE_SLOTS ? nbWaves : ZB_WAVE_SLOTS;
+    size_t inEnd = 0, bound = 0;
+    for (size_t f = 0; f < nbFrames; f++) {
+        if (frameOffsets[f] + frameSizes[f] > inEnd) inEnd = frameOffsets[f] + frameSizes[f];
+        bound += ZSTD_compressBound(frameSizes[f]) + 32;
+    }
+    size_t const outCap = dstCapacity < bound ? dstCapacity : bound;
+    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves); if (zb_isErr(e)) return e;
+        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks)); if (zb_isErr(e)) return e; }
+    if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
+    if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
+    for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));
+    cudaStream_t const sCopy = c->waveStream[ZB_WAVE_SLOTS], sD2H = c->waveStream[ZB_WAVE_SLOTS + 1u];
+    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evDone(nbWaves);
+    for (u32 w = 0; w < nbWaves; w++) {
+        CK(cudaEventCreateWithFlags(&evH2D[w], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evStitch[w], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evDone[w], cudaEventDisableTiming));
+    }
+    unsigned launches = 0;
+    size_t err = 0;
+    CK(cudaEventRecord(c->evStart, sCopy));
+    CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, sCopy));
+    CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, sCopy));
+    for (u32 w = 0; w < nbWaves && !err; w++) {
+        u32 const b0 = w * ZB_WAVE_BLOCKS, b1 = (b0 + ZB_WAVE_BLOCKS < nbBlocks) ? b0 + ZB_WAVE_BLOCKS : nbBlocks;
+        /* input bytes of the wave (frames are laid out in offset order; history was uploaded by earlier waves) */
+        u64 lo = ~0ull, hi = 0;
+        for (u32 b = b0; b < b1; b++) { u64 const a = P.blocks[b].srcOff, e = a + P.blocks[b].size; if (a < lo) lo = a; if (e > hi) hi = e; }
+        if (hi > lo) CK(cudaMemcpyAsync(c->d_in + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, sCopy));
+        CK(cudaEventRecord(evH2D[w], sCopy));
+        cudaStream_t const st = c->waveStream[w % slots];
+        CK(cudaStreamWaitEvent(st, evH2D[w], 0));
+        err = zb_runBlocks(c, P, c->d_in, b0, b1, (size_t)(w % slots) * ZB_WAVE_BLOCKS, st, false, &launches);
+        if (err) break;
+        if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
+        size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
+        CK(zb_launch_stitch(c->d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
+                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, c->d_out, outCap, st));
+        launches += 2;
+        CK(cudaEventRecord(evStitch[w], st));
+        CK(cudaMemcpyAsync(c->h_totals + w, c->d_totals + w, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(evDone[w], st));
+    }
+    /* drain: as each wave's size becomes known, ship its bytes */
+    u64 prev = 0, total = 0;
+    for (u32 w = 0; w < nbWaves && !err; w++) {
+        CK(cudaEventSynchronize(evDone[w]));
+        total = c->h_totals[w];
+        if (total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, c->d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
+        if (total <= outCap) prev = total;
+    }
+    if (!err && cSizes) {
+        cudaStream_t const st = c->waveStream[(nbWaves - 1) % slots];
+        CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, st));
+        std::vector<u64> tmp(nbFrames);
+        CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t f = 0; f < nbFrames; f++) cSizes[f] = (size_t)tmp[f];
+    }
+    CK(cudaEventRecord(c->evEnd, sD2H));
+    CK(cudaStreamSynchronize(sD2H));
+    for (u32 s = 0; s < slots; s++) CK(cudaStreamSynchronize(c->waveStream[s]));
+    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); cudaEventDestroy(evDone[w]); }
+    if (err) return err;
+    {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; c->stats.kernel_ms = ms; }
+    c->stats.launches = launches; c->stats.nbBlocks = nbBlocks;
+    c->stats.h2d_bytes = inEnd; c->stats.d2h_bytes = (size_t)total;
     if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
     return (size_t)total;
 }
@@ -280,32 +401,14 @@ extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCap
     if (!c) return ZB_ERR(ZB_error_GENERIC);
     if (nbFrames == 0) return 0;
     {   size_t const e = zb_ctxInit(c); if (zb_isErr(e)) return e; }
-    cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
     memset(&c->stats, 0, sizeof(c->stats));
     if (deviceMemory) {
+        cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
         size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
         c->stats.total_ms = c->stats.kernel_ms;
         return r;
     }
-    /* host pointers: stage input and output through device buffers */
-    size_t inEnd = 0, bound = 0;
-    for (size_t f = 0; f < nbFrames; f++) {
-        if (frameOffsets[f] + frameSizes[f] > inEnd) inEnd = frameOffsets[f] + frameSizes[f];
-        bound += ZSTD_compressBound(frameSizes[f]) + 32;
-    }
-    size_t const outCap = dstCapacity < bound ? dstCapacity : bound;
-    if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
-    if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
-    CK(cudaEventRecord(c->evStart, stream));
-    if (inEnd) CK(cudaMemcpyAsync(c->d_in, src, inEnd, cudaMemcpyHostToDevice, stream));
-    size_t const r = zb_compressFramesDevice(c, c->d_out, outCap, c->d_in, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
-    if (zb_isErr(r)) return r;
-    CK(cudaMemcpyAsync(dst, c->d_out, r, cudaMemcpyDeviceToHost, stream));
-    CK(cudaEventRecord(c->evEnd, stream));
-    CK(cudaStreamSynchronize(stream));
-    {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; }
-    c->stats.h2d_bytes = inEnd; c->stats.d2h_bytes = r;
-    return r;
+    return zb_compressFramesHost(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level);
 }
 
 extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity,

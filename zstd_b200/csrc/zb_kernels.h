@@ -21,15 +21,16 @@ cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbPa
 cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                                 const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
 
-/* K4: stitch — per-block output sizes -> exclusive scan -> frame/block headers + payload copy.
- * d_outOffsets has nbBlocks+1 entries; d_frameSizes has nbFrames entries; *d_total receives the
- * total number of bytes the call produces (even when it exceeds dstCapacity: nothing is written
- * past dst + dstCapacity). */
-cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks,
-                             const ZbFrame* d_frames, u32 nbFrames,
+/* K4: stitch — per-block output sizes -> exclusive scan -> frame/block headers + payload copy, for
+ * one wave of blocks.  d_blocks/d_meta/d_body/d_outOffsets point at the wave's first block;
+ * d_outOffsets gets nbBlocks+1 absolute offsets, starting at *d_base (NULL = 0); *d_total receives
+ * the running total after this wave (even past dstCapacity: nothing is written past dst+dstCapacity). */
+cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbFrame* d_frames,
                              const u8* d_body, const ZbBlockMeta* d_meta,
-                             u64* d_outOffsets, u64* d_frameSizes, u64* d_total,
+                             u64* d_outOffsets, const u64* d_base, u64* d_total,
                              u8* d_dst, u64 dstCapacity, cudaStream_t stream);
+cudaError_t zb_launch_frame_sizes(const ZbFrame* d_frames, u32 nbFrames, const u64* d_outOffsets,
+                                  u64* d_frameSizes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

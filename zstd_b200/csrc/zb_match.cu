@@ -59,6 +59,67 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
 #define CAND_STAGES 4u                       /* ring = 4 chunks = 2 KiB, 3 chunks in flight ahead of the consumer */
 #define CAND_RING (CAND_CHUNK * CAND_STAGES)
 
+/* One 16-step slice of the table walk (phase B of zb_cand_kernel).  INTERIOR: every lane of every
+ * step is an in-block position with 8 readable bytes, so the activity predicates fold away. */
+template <bool INTERIOR>
+__device__ __forceinline__ void zb_cand_walk16(u16* __restrict__ table, u8* __restrict__ tags, const u32* hh,
+                                               u32 q0, u32 o0, u32 nPos, u32 bs, u32 lane,
+                                               u32& ph, u32 inc, u32 period, u16* __restrict__ mydist)
+{
+#pragma unroll
+    for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
+        u32 const q = q0 + 32u * j + lane;
+        bool const act = INTERIOR ? true : ((q >= o0) && (q - o0 < nPos));
+        u32 const p = q - o0;
+        u32 const h = act ? (hh[j] >> 8) : 0u;
+        u32 const tag = hh[j] & 0xFFu;
+        bool const ins = act && ph < 2u;
+        /* read the bucket, let every inserting lane write it, read it back: when no two inserting
+         * lanes share a bucket (the common case) the read-back alone resolves the step */
+        u32 const old = act ? table[h] : 0u;
+        u32 const oldtag = act ? tags[h] : 0x100u;
+        __syncwarp();
+        if (ins) { table[h] = (u16)p; tags[h] = (u8)tag; }
+        __syncwarp();
+        u32 const nw = act ? table[h] : 0u;
+        u32 const nwtag = act ? tags[h] : 0x100u;
+        u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
+        u32 d = 0;
+        bool resolved = false;
+        if (losers) {
+            /* rare: some bucket has several inserting lanes.  Peel one hash group per round:
+             * the highest inserting lane owns the bucket, every lane of the group takes the
+             * nearest inserting lane below it as its candidate. */
+            u32 const insmask = __ballot_sync(ZB_FULL, ins);
+            while (losers) {
+                int const L = __ffs((int)losers) - 1;
+                u32 const hl = __shfl_sync(ZB_FULL, h, L);
+                bool const mine = act && h == hl;
+                u32 const grpAll = __ballot_sync(ZB_FULL, mine);
+                u32 const grpIns = grpAll & insmask;
+                u32 const lower = mine ? (grpIns & ((1u << lane) - 1u)) : 0u;
+                u32 const lowLane = lower ? (31u - (u32)__clz((int)lower)) : lane;
+                u32 const lowTag = __shfl_sync(ZB_FULL, tag, (int)lowLane);
+                if (mine) {
+                    if (lower) d = (lowTag == tag) ? lane - lowLane : 0u;
+                    else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
+                    resolved = true;
+                    if ((31u - (u32)__clz((int)grpIns)) == lane) { table[h] = (u16)p; tags[h] = (u8)tag; }
+                }
+                losers &= ~grpAll;
+            }
+            __syncwarp();
+        }
+        if (!resolved) {
+            u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
+            if (dn >= 1u && dn <= lane) d = (nwtag == tag) ? dn : 0u;
+            else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
+        }
+        if (INTERIOR || (act && p >= bs)) mydist[p - bs] = (u16)d;
+        ph += inc; if (ph >= period) ph -= period;
+    }
+}
+
 template <int MLS>
 __global__ void __launch_bounds__(32)
 zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
@@ -172,58 +233,11 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
             u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
             hh[j] = zb_hash(v, MLS, hlog + 8u);                 /* bucket << 8 | tag */
         }
-        /* phase B: the table walk proper, one step after the other; hh[j] becomes the candidate distance */
-#pragma unroll
-        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
-            u32 const q = c * CAND_CHUNK + 32u * j + lane;
-            bool const act = (q >= o0) && (q - o0 < nPos);
-            u32 const p = q - o0;
-            u32 const h = act ? (hh[j] >> 8) : 0u;
-            u32 const tag = hh[j] & 0xFFu;
-            bool const ins = act && ph < 2u;
-            /* read the bucket, let every inserting lane write it, read it back: when no two inserting
-             * lanes share a bucket (the common case) the read-back alone resolves the step */
-            u32 const old = act ? table[h] : 0u;
-            u32 const oldtag = act ? tags[h] : 0x100u;
-            __syncwarp();
-            if (ins) { table[h] = (u16)p; tags[h] = (u8)tag; }
-            __syncwarp();
-            u32 const nw = act ? table[h] : 0u;
-            u32 const nwtag = act ? tags[h] : 0x100u;
-            u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
-            u32 d = 0;
-            bool resolved = false;
-            if (losers) {
-                /* rare: some bucket has several inserting lanes.  Peel one hash group per round:
-                 * the highest inserting lane owns the bucket, every lane of the group takes the
-                 * nearest inserting lane below it as its candidate. */
-                u32 const insmask = __ballot_sync(ZB_FULL, ins);
-                while (losers) {
-                    int const L = __ffs((int)losers) - 1;
-                    u32 const hl = __shfl_sync(ZB_FULL, h, L);
-                    bool const mine = act && h == hl;
-                    u32 const grpAll = __ballot_sync(ZB_FULL, mine);
-                    u32 const grpIns = grpAll & insmask;
-                    u32 const lower = mine ? (grpIns & ((1u << lane) - 1u)) : 0u;
-                    u32 const lowLane = lower ? (31u - (u32)__clz((int)lower)) : lane;
-                    u32 const lowTag = __shfl_sync(ZB_FULL, tag, (int)lowLane);
-                    if (mine) {
-                        if (lower) d = (lowTag == tag) ? lane - lowLane : 0u;
-                        else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
-                        resolved = true;
-                        if ((31u - (u32)__clz((int)grpIns)) == lane) { table[h] = (u16)p; tags[h] = (u8)tag; }
-                    }
-                    losers &= ~grpAll;
-                }
-                __syncwarp();
-            }
-            if (!resolved) {
-                u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
-                if (dn >= 1u && dn <= lane) d = (nwtag == tag) ? dn : 0u;
-                else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
-            }
-            if (act && p >= bs) mydist[p - bs] = (u16)d;
-            ph += inc; if (ph >= period) ph -= period;
+        /* phase B: the table walk proper, one step after the other */
+        {   u32 const q0 = c * CAND_CHUNK;
+            bool const interior = (q0 >= o0 + bs) && (q0 + CAND_CHUNK <= o0 + nPos);
+            if (interior) zb_cand_walk16<true>(table, tags, hh, q0, o0, nPos, bs, lane, ph, inc, period, mydist);
+            else          zb_cand_walk16<false>(table, tags, hh, q0, o0, nPos, bs, lane, ph, inc, period, mydist);
         }
     }
     for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;

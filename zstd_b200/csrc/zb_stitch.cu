@@ -34,10 +34,11 @@ __device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, 
 
 /* single-CTA exclusive scan over per-block output sizes (nbBlocks is a few thousand per wave) */
 __global__ void __launch_bounds__(SCAN_THREADS)
-zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames, u32 nbFrames,
+zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames,
                      const ZbBlockMeta* __restrict__ meta, u64* __restrict__ outOffsets,
-                     u64* __restrict__ frameSizes, u64* __restrict__ total)
+                     const u64* __restrict__ basePtr, u64* __restrict__ total)
 {
+    u64 const base = basePtr ? *basePtr : 0;      /* bytes produced by the waves before this one */
     __shared__ u64 part[SCAN_THREADS];
     u32 const tid = threadIdx.x;
     u32 const per = (nbBlocks + SCAN_THREADS - 1u) / SCAN_THREADS;
@@ -58,7 +59,7 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
         part[tid] += v;
         __syncthreads();
     }
-    u64 run = (tid == 0) ? 0 : part[tid - 1];
+    u64 run = base + ((tid == 0) ? 0 : part[tid - 1]);
     for (u32 i = beg; i < end; i++) {
         ZbBlock const bd = blocks[i];
         u64 sz = 3u + meta[i].bodySize;
@@ -66,15 +67,17 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
         outOffsets[i] = run;
         run += sz;
     }
-    if (tid == SCAN_THREADS - 1) { outOffsets[nbBlocks] = part[SCAN_THREADS - 1]; *total = part[SCAN_THREADS - 1]; }
-    __syncthreads();
-    __threadfence_block();
-    /* per-frame compressed sizes: offsets are final after the barrier below */
-    __syncthreads();
-    for (u32 f = tid; f < nbFrames; f += SCAN_THREADS) {
-        ZbFrame const fr = frames[f];
-        frameSizes[f] = outOffsets[fr.firstBlock + fr.nbBlocks] - outOffsets[fr.firstBlock];
-    }
+    if (tid == SCAN_THREADS - 1) { outOffsets[nbBlocks] = base + part[SCAN_THREADS - 1]; *total = base + part[SCAN_THREADS - 1]; }
+}
+
+/* per-frame compressed sizes from the (final) block offsets */
+__global__ void zb_frame_sizes_kernel(const ZbFrame* __restrict__ frames, u32 nbFrames,
+                                      const u64* __restrict__ outOffsets, u64* __restrict__ frameSizes)
+{
+    u32 const f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nbFrames) return;
+    ZbFrame const fr = frames[f];
+    frameSizes[f] = outOffsets[fr.firstBlock + fr.nbBlocks] - outOffsets[fr.firstBlock];
 }
 
 #define COPY_THREADS 256
@@ -128,14 +131,21 @@ zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, c
     for (u32 i = headN + nvec * 16u + tid; i < n; i += COPY_THREADS) out[i] = from[i];
 }
 
-extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks,
-                                        const ZbFrame* d_frames, u32 nbFrames,
+extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbFrame* d_frames,
                                         const u8* d_body, const ZbBlockMeta* d_meta,
-                                        u64* d_outOffsets, u64* d_frameSizes, u64* d_total,
+                                        u64* d_outOffsets, const u64* d_base, u64* d_total,
                                         u8* d_dst, u64 dstCapacity, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, nbFrames, d_meta, d_outOffsets, d_frameSizes, d_total);
+    zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, d_meta, d_outOffsets, d_base, d_total);
     zb_copy_kernel<<<nbBlocks, COPY_THREADS, 0, stream>>>(d_src, d_blocks, d_frames, d_body, d_meta, d_outOffsets, d_dst, dstCapacity);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t zb_launch_frame_sizes(const ZbFrame* d_frames, u32 nbFrames, const u64* d_outOffsets,
+                                             u64* d_frameSizes, cudaStream_t stream)
+{
+    if (nbFrames == 0) return cudaSuccess;
+    zb_frame_sizes_kernel<<<(nbFrames + 255) / 256, 256, 0, stream>>>(d_frames, nbFrames, d_outOffsets, d_frameSizes);
     return cudaGetLastError();
 }
