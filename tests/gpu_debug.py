@@ -75,6 +75,8 @@ def main():
     cases.append(("tiny-rep", b"abcabcabcabcabcabcabcabcabcabc" * 3))
     cases.append(("zeros-300", bytes(300)))
     cases.append(("zeros-1M", bytes(1 << 20)))
+    cases.append(("period3", b"abc" * 50000))
+    cases.append(("period40", bytes(range(40)) * 9000))
     cases.append(("rand-100k", zref.random_bytes(100000, 1)))
     cases.append(("rand-300k", zref.random_bytes(300000, 2)))
     for n in (100, 1000, 5000, 20000, 70000, 131072, 131073, 200000, 262144, 400000):

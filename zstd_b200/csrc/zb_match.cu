@@ -60,9 +60,11 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
 #define CAND_RING (CAND_CHUNK * CAND_STAGES)
 
 /* One 16-step slice of the table walk (phase B of zb_cand_kernel).  INTERIOR: every lane of every
- * step is an in-block position with 8 readable bytes, so the activity predicates fold away. */
+ * step is an in-block position with 8 readable bytes, so the activity predicates fold away.
+ * table/tags are the warp's communication medium (lanes read what other lanes wrote in the same step):
+ * volatile, never __restrict__. */
 template <bool INTERIOR>
-__device__ __forceinline__ void zb_cand_walk16(u16* __restrict__ table, u8* __restrict__ tags, const u32* hh,
+__device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8* tags, const u32* hh,
                                                u32 q0, u32 o0, u32 nPos, u32 bs, u32 lane,
                                                u32& ph, u32 inc, u32 period, u16* __restrict__ mydist)
 {
@@ -134,6 +136,8 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     u32 const hlog = prm.hashLog, period = prm.insPeriod;
     u8* const tags = reinterpret_cast<u8*>(table + ((size_t)1 << hlog));   /* 8 further hash bits per bucket */
+    volatile u16* const vtable = table;     /* lanes communicate through the table inside a step: volatile accesses */
+    volatile u8*  const vtags = tags;
 
     /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
     u32 const o0 = (u32)((uintptr_t)base & 15u);
@@ -187,7 +191,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                 u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
                 u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
                 u32 const h24 = zb_hash(v, MLS, hlog + 8u);
-                table[h24 >> 8] = (u16)p; tags[h24 >> 8] = (u8)h24;
+                vtable[h24 >> 8] = (u16)p; vtags[h24 >> 8] = (u8)h24;
             }
             __syncwarp();
             for (u32 g0 = first; g0 < cq + CAND_CHUNK; g0 += 16u * period) {
@@ -202,18 +206,18 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
                 u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
                 u32 const h24 = zb_hash(v, MLS, hlog + 8u);
                 u32 const h = h24 >> 8;
-                if (act) table[h] = (u16)p;
+                if (act) vtable[h] = (u16)p;
                 __syncwarp();
                 /* the latest position must own the bucket: lanes that lost to an earlier one write again */
                 while (true) {
-                    u32 const diff = act ? ((p - (u32)table[h]) & 0xFFFFu) : 0u;      /* > 0 : an earlier position of this step is stored */
+                    u32 const diff = act ? ((p - (u32)vtable[h]) & 0xFFFFu) : 0u;      /* > 0 : an earlier position of this step is stored */
                     bool const again = diff != 0u && diff <= 16u * period;
                     if (!__any_sync(ZB_FULL, again)) break;
                     __syncwarp();
-                    if (again) table[h] = (u16)p;
+                    if (again) vtable[h] = (u16)p;
                     __syncwarp();
                 }
-                if (act && table[h] == (u16)p) tags[h] = (u8)h24;       /* the bucket's owner sets its tag */
+                if (act && vtable[h] == (u16)p) vtags[h] = (u8)h24;       /* the bucket's owner sets its tag */
                 __syncwarp();
             }
             __syncwarp();
