@@ -60,6 +60,7 @@ typedef struct {
     u32 longHashLog;  /* dfast only: log2 entries of the 8-byte-hash table, else 0 */
     u32 stepSize;     /* targetLength + !targetLength + 1 (zstd_fast.c:200); dfast: 1 */
     u32 insPeriod;    /* positions with (framePos % insPeriod) < 2 are inserted into the table */
+    u32 insPeriodLong;/* dfast: same for the 8-byte-hash table */
     u32 primeBytes;   /* history window primed before the block */
     u32 strategy;     /* 1 fast, 2 dfast */
     u32 windowLog;

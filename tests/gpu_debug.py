@@ -87,7 +87,7 @@ def main():
         cases.append(("datagen-16M-P50", zref.datagen(16 << 20, 50)))
     nbad = 0
     for name, src in cases:
-        for level in (1, -3):
+        for level in (1, -3, 3):
             nbad += not check(name, src, level, ctx)
     print("failures:", nbad)
     if mode == "full" and zref.have_datagen():

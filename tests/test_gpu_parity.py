@@ -39,7 +39,7 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("level", [1, -1, -3, -7])
+@pytest.mark.parametrize("level", [1, 2, 3, -1, -3, -7])
 def test_bit_exact_with_oracle(ctx, name, level):
     src = CASES[name]
     got = ctx.compress(src, level)
@@ -88,7 +88,7 @@ def test_golden_inputs(ctx):
     for key, rec in frames.items():
         name, level = key.rsplit("@", 1)
         path = os.path.join(zref.GOLDEN, "inputs", name)
-        if not os.path.exists(path) or int(level) == 3:
+        if not os.path.exists(path):
             continue
         data = open(path, "rb").read()
         out = ctx.compress(data, int(level))
@@ -97,9 +97,9 @@ def test_golden_inputs(ctx):
 
 
 @pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary absent")
-@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 64 << 20)])
+@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 64 << 20), (90, 3, 64 << 20)])
 def test_baseline_configs_size_and_roundtrip(ctx, p, level, size):
-    """configs[0] (datagen -g16MB -P50, level 1) and a 64 MiB sample of config 3 (P30, --fast=3):
+    """configs[0] (datagen -g16MB -P50, level 1), 64 MiB samples of config 3 (P30, --fast=3) and config 4 (P90, level 3):
     bit-exact with the oracle, decodes, size within +-0.5 % of the reference."""
     src = zref.datagen(size, p)
     got = ctx.compress(src, level)

@@ -79,7 +79,8 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
         else { p.hashLog = cp.hashLog; p.insPeriod = 2 * p.stepSize < 4 ? 4 : 2 * p.stepSize; }
         if (p.hashLog > 14) p.hashLog = 14;                       /* 2^14 u16 = 32 KiB of shared memory per block */
     } else {
-        p.hashLog = cp.chainLog; p.longHashLog = cp.hashLog; p.stepSize = 1; p.insPeriod = 4;
+        /* doubleFast: table shapes tuned so the output size meets the reference's on BASELINE config 4 */
+        p.stepSize = 1; p.hashLog = 10; p.insPeriod = 9; p.longHashLog = 11; p.insPeriodLong = 8;
     }
     p.litDisabled = (cp.strategy == 1) && (cp.targetLength > 0); /* zstd_compress_internal.h:621-633 */
     return p;
@@ -96,6 +97,7 @@ struct ZSTD_CCtx_s {
     cudaStream_t waveStream[8];
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
+    u16* d_dist2; size_t capDist2;                       /* dfast only: short-hash candidate distances */
     u64* d_outOffsets; u64* d_frameSizes; u64* d_totals;    /* d_totals[w]: bytes produced up to and including wave w */
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
@@ -143,7 +145,7 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; c->capDist2 = 0; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
     cudaFreeHost(c->h_totals);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
     c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL; c->d_totals = NULL; c->h_totals = NULL;
@@ -191,8 +193,13 @@ static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size
     }
     return 0;
 }
-static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks)
+static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
 {
+    if (needDist2 && nbSlotBlocks > c->capDist2) {
+        cudaFree(c->d_dist2); c->d_dist2 = NULL; c->capDist2 = 0;
+        CK(cudaMalloc(&c->d_dist2, nbSlotBlocks * (size_t)ZB_BLOCK_MAX * sizeof(u16)));
+        c->capDist2 = nbSlotBlocks;
+    }
     if (nbSlotBlocks > c->capHeavy) {
         cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits); cudaFree(c->d_body); cudaFree(c->d_dist);
         c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL; c->d_body = NULL; c->d_dist = NULL; c->capHeavy = 0;
@@ -226,7 +233,8 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
             u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
             ZbBlock b; b.srcOff = fr.srcOff + pos; b.size = (u32)bsz;
             b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
-            b.insPhase = (u32)((pos - b.histLen) % prm.insPeriod); b.pad = 0;
+            b.insPhase = (u32)((pos - b.histLen) % prm.insPeriod);
+            b.insPhaseLong = prm.insPeriodLong ? (u32)((pos - b.histLen) % prm.insPeriodLong) : 0u;
             b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
             P.blocks.push_back(b);
             pos += bsz;
@@ -249,9 +257,10 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, u32 b
             if (lo >= hi) continue;
             size_t const s = slot0 + (lo - b0);
             if (phase == 0) {
-                CK(zb_launch_match(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX, c->d_seqs + s * ZB_SEQ_STRIDE,
+                CK(zb_launch_match(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
+                                   G.prm.strategy == 2 ? c->d_dist2 + s * ZB_BLOCK_MAX : (u16*)0, c->d_seqs + s * ZB_SEQ_STRIDE,
                                    c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
-                *launches += 2;
+                *launches += (G.prm.strategy == 2) ? 3 : 2;
             } else if (phase == 1) {
                 CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, c->d_lits + s * ZB_LIT_STRIDE, c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
                 *launches += 1;
@@ -276,7 +285,8 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     zb_plan(P, frameOffsets, frameSizes, nbFrames, level);
     u32 const nbBlocks = (u32)P.blocks.size();
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
-        e = zb_ensureHeavy(c, nbBlocks); if (zb_isErr(e)) return e; }
+        bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
+        e = zb_ensureHeavy(c, nbBlocks, d2); if (zb_isErr(e)) return e; }
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
@@ -329,7 +339,8 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
     }
     size_t const outCap = dstCapacity < bound ? dstCapacity : bound;
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves); if (zb_isErr(e)) return e;
-        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks)); if (zb_isErr(e)) return e; }
+        bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
+        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks), d2); if (zb_isErr(e)) return e; }
     if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
     if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
     for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));

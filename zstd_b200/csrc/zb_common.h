@@ -56,7 +56,7 @@ typedef struct {
     u32 frame;         /* index into ZbFrame[] */
     u32 flags;         /* ZB_FLAG_* */
     u32 insPhase;      /* (frame position of the oldest visible byte) % insPeriod */
-    u32 pad;
+    u32 insPhaseLong;  /* same for insPeriodLong (dfast) */
 } ZbBlock;
 
 typedef struct {
@@ -88,6 +88,8 @@ typedef struct {
     u32 litDisabled;   /* zstd_compress_internal.h:621-633 */
     u32 windowLog;
     u32 insPeriod;     /* positions with (framePos % insPeriod) < 2 enter the table */
+    u32 insPeriodLong; /* dfast: same for the 8-byte-hash table */
+    u32 longPass;      /* set by the launcher for the candidate walk of the long table (uses insPhaseLong) */
 } ZbParams;
 
 #endif

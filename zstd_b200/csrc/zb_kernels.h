@@ -9,9 +9,10 @@ extern "C" {
 #endif
 
 /* K1: match-finder = K1a candidate table walk + K1b greedy parse.  One warp per block each.
- * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records). */
+ * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records);
+ * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates). */
 cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
-                            u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
+                            u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
 /* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block. */
 cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,

@@ -159,7 +159,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     __syncwarp();
 
     u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
-    u32 const phase0 = (period - (o0 % period) + bd.insPhase) % period;   /* pattern phase of q = 0 */
+    u32 const phase0 = (period - (o0 % period) + (prm.longPass ? bd.insPhaseLong : bd.insPhase)) % period;   /* pattern phase of q = 0 */
     u32 ph = (lane + phase0) % period;                            /* pattern phase of this lane's q in the current step */
     u32 const inc = 32u % period;
     /* chunks that lie entirely inside the history only have to leave their inserted positions in the
@@ -383,19 +383,167 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * K1b (doubleFast) — the greedy selection of ZSTD_compressBlock_doubleFast_noDict_generic
+ * (zstd_double_fast.c:105-323) over two candidate arrays: distL (8-byte hash) and distS (mls-byte hash).
+ * Per probe position p, in the reference's order: repcode-1 at p+1 (:190-195), long match at p
+ * (:206-213), short match at p (:222-225) upgraded to the long match at p+1 when longer (:254-271);
+ * probes are spaced by `step` (1, +1 per 256 bytes without a match, :131); lowest lane wins; immediate
+ * repcode-2 at lane 0 right after a match (:302-316).  Table candidates are tag-verified only: the
+ * winning lane's bytes are checked while the match is extended, a false positive drops out.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ u32 zb_back_coop(const u8* __restrict__ base, u32 probe, u32 offset, u32 anchor, u32 lane)
+{
+    u32 back = 0;
+    while (true) {
+        u32 const k = back + lane + 1u;                        /* compare bytes probe-k and probe-offset-k */
+        bool const ok = (probe >= anchor + k) && (probe >= offset + k) && (base[probe - k] == base[probe - offset - k]);
+        u32 const okb = __ballot_sync(ZB_FULL, ok);
+        u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
+        back += cnt;
+        if (cnt < 32u) return back;
+    }
+}
+
+__global__ void __launch_bounds__(32 * PARSE_WARPS)
+zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
+                      const u16* __restrict__ distLong, const u16* __restrict__ distShort,
+                      u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+    if (b >= nbBlocks) return;
+    ZbBlock const bd = blocks[b];
+    u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
+    u8*  const mylit = lits + (size_t)b * ZB_LIT_STRIDE;
+    const u16* const dLp = distLong + (size_t)b * ZB_BLOCK_MAX;
+    const u16* const dSp = distShort + (size_t)b * ZB_BLOCK_MAX;
+    const u8* const base = src + bd.srcOff - bd.histLen;
+    u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+
+    if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
+        if (lane == 0) {
+            ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
+            m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
+            meta[b] = m;
+        }
+        return;
+    }
+    u32 ip = bs, anchor = bs, searchStart = bs;
+    u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
+    u32 pf = bs;
+
+    while (ip + 9u <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
+        if (ip + PARSE_PF_AHEAD > pf && pf < be) {
+            u32 const a = pf + 128u * lane;
+            if (a < be) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dLp + (a - bs)));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dLp + (a - bs) + 64));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dSp + (a - bs)));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dSp + (a - bs) + 64));
+            }
+            pf += 128u * 32u;
+        }
+        u32 const step = 1u + ((ip - searchStart) >> 8);                     /* kStepIncr = 1 << kSearchStrength */
+        u32 const p = ip + lane * step;
+        bool const act = (p + 9u <= be);
+        u32 const pp = act ? p : ip;
+        u32 const dL = act ? (u32)dLp[pp - bs] : 0u;
+        u32 const dS = act ? (u32)dSp[pp - bs] : 0u;
+        u32 const dL1 = act ? (u32)dLp[pp + 1u - bs] : 0u;
+        u64 const w = zb_ld64w3(base + pp);                                  /* bytes p .. p+7 */
+        u32 const cur = (u32)w, cur1 = (u32)(w >> 8);
+        bool const v2 = act && rep1 != 0u && (p + 1u >= rep1);
+        u32 const r2 = zb_ld32w2(base + (v2 ? pp + 1u - rep1 : pp));
+        u32 r3 = ~cur;
+        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
+        if (ip == anchor && rep2 != 0u) r3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));
+        /* 3 repcode-2, 2 repcode-1 (at p+1), 1 long candidate, 4 short candidate */
+        u32 hit = (v3 && r3 == cur) ? 3u : ((v2 && r2 == cur1) ? 2u : (dL ? 1u : (dS ? 4u : 0u)));
+        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
+        u32 ms = 0, offset = 0, mlen = 0, wtype = 0;
+        bool found = false;
+        while (tent) {
+            int const winner = __ffs((int)tent) - 1;
+            u32 const probe = __shfl_sync(ZB_FULL, p, winner);
+            wtype = __shfl_sync(ZB_FULL, hit, winner);
+            u32 const wL = __shfl_sync(ZB_FULL, dL, winner), wS = __shfl_sync(ZB_FULL, dS, winner), wL1 = __shfl_sync(ZB_FULL, dL1, winner);
+            if (wtype == 3u) { ms = probe; offset = rep2; mlen = 4u + zb_count_fwd(base, probe + 4u, rep2, be, lane); found = true; break; }
+            if (wtype == 2u) { ms = probe + 1u; offset = rep1; mlen = 4u + zb_count_fwd(base, probe + 5u, rep1, be, lane); found = true; break; }
+            if (wtype == 1u) {
+                u32 const f0 = zb_count_fwd(base, probe, wL, be, lane);
+                if (f0 >= 8u) {
+                    u32 const back = zb_back_coop(base, probe, wL, anchor, lane);
+                    ms = probe - back; offset = wL; mlen = back + f0; found = true; break;
+                }
+                /* tag collision on the long table: the lane may still have a short candidate */
+                if (lane == (u32)winner) hit = dS ? 4u : 0u;
+                if (wS == 0u) { tent &= ~(1u << winner); }
+                continue;
+            }
+            /* short candidate */
+            {   u32 const f0 = zb_count_fwd(base, probe, wS, be, lane);
+                if (f0 < 4u) { tent &= ~(1u << winner); if (lane == (u32)winner) hit = 0u; continue; }
+                u32 mp = probe, mo = wS, ml = f0;
+                if (wL1) {
+                    u32 const f1 = zb_count_fwd(base, probe + 1u, wL1, be, lane);
+                    if (f1 >= 8u && f1 > ml) { mp = probe + 1u; mo = wL1; ml = f1; }
+                }
+                u32 const back = zb_back_coop(base, mp, mo, anchor, lane);
+                ms = mp - back; offset = mo; mlen = back + ml; wtype = 1u; found = true; break;
+            }
+        }
+        if (!found) { ip += 32u * step; continue; }
+        u32 const litLen = ms - anchor;
+        u32 offBase;
+        if (wtype == 3u) { offBase = 1u; u32 const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (wtype == 2u && litLen > 0u) offBase = 1u;
+        else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
+        if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
+        for (u32 i = lane; i < litLen; i += 32) mylit[litPos + i] = base[anchor + i];
+        litPos += litLen; nbSeq++;
+        ip = ms + mlen; anchor = ip; searchStart = ip;
+    }
+    {   u32 const lastLits = be - anchor;
+        for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
+        litPos += lastLits;
+    }
+    if (lane == 0) {
+        ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litPos; m.litSecSize = 0; m.bodySize = 0;
+        m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
+        meta[b] = m;
+    }
+}
+
+static void zb_launch_cand(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist, cudaStream_t stream)
+{
+    size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
+    switch (prm.mls) {        /* 2^hashLog x 3 B <= 48 KiB: within the default dynamic shared memory limit */
+    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    }
+}
+
 extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
-                                       u16* d_dist, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
+                                       u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    size_t const smem = (size_t)3 << prm->hashLog;       /* u16 positions + u8 tags */
-    switch (prm->mls) {        /* 2^hashLog u16 <= 32 KiB: below the 48 KiB default dynamic shared memory limit */
-    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
-    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
-    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
-    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
-    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, *prm, d_dist); break;
+    u32 const grid = (nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS;
+    if (prm->strategy == 2) {
+        /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
+        ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
+        zb_launch_cand(d_src, d_blocks, nbBlocks, pl, d_dist, stream);
+        zb_launch_cand(d_src, d_blocks, nbBlocks, *prm, d_dist2, stream);
+        if (evMid) cudaEventRecord(evMid, stream);
+        zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_dist2, d_seqs, d_lits, d_meta);
+    } else {
+        zb_launch_cand(d_src, d_blocks, nbBlocks, *prm, d_dist, stream);
+        if (evMid) cudaEventRecord(evMid, stream);
+        zb_parse_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     }
-    if (evMid) cudaEventRecord(evMid, stream);
-    zb_parse_kernel<<<(nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     return cudaGetLastError();
 }
