@@ -99,9 +99,9 @@ def test_golden_frames_fixture():
 
 @needs_ref
 @pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary not built")
-@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 16 << 20), (90, 3, 16 << 20)])
+@pytest.mark.parametrize("p,level,size", [(50, 1, 16 << 20), (30, -3, 16 << 20), (90, 3, 64 << 20)])
 def test_size_within_half_percent_of_reference(p, level, size):
-    """BASELINE.json configs 1/2 (P50, level 1), 3 (P30, --fast=3) and 4 (P90, level 3) on 16 MiB samples."""
+    """BASELINE.json configs 1/2 (P50, level 1), 3 (P30, --fast=3) and 4 (P90, level 3) on 16 / 64 MiB samples."""
     src = zref.datagen(size, p)
     ours = zref.oracle_compress(src, level)
     ref = zref.ref_compress(src, level)

@@ -519,7 +519,16 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
 static void zb_launch_cand(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist, cudaStream_t stream)
 {
     size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
-    switch (prm.mls) {        /* 2^hashLog x 3 B <= 48 KiB: within the default dynamic shared memory limit */
+    static bool optin = false;
+    if (!optin) {             /* hashLog 14: 48 KiB of table + the 2 KiB static ring exceeds the default 48 KiB limit */
+        cudaFuncSetAttribute(zb_cand_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(zb_cand_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(zb_cand_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(zb_cand_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(zb_cand_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        optin = true;
+    }
+    switch (prm.mls) {
     case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
     case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
     case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
