@@ -91,8 +91,11 @@ void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
  * and in parallel with — the greedy selection.  Table entries are 16-bit positions modulo 64 KiB
  * relative to the oldest visible byte (reach 65535) plus an 8-bit tag (further hash bits). */
 static void candidates_walk(const u8* frame, size_t lowLimit, size_t bs, size_t be,
-                            u32 mls, u32 hlog, u32 insPeriod, u16* dist)
+                            u32 mls, u32 hlog, u32 insPeriod, size_t frameStart, u16* dist)
 {
+    /* pattern phase is taken on the position relative to the frame start; history in front of the
+     * frame start (a dictionary) continues the pattern backwards */
+    size_t const patOff = (insPeriod - (frameStart % insPeriod)) % insPeriod;
     u16* const table = (u16*)calloc((size_t)1 << hlog, sizeof(u16));
     u8*  const tags  = (u8*)calloc((size_t)1 << hlog, 1);
     for (size_t p = lowLimit; p + 8 <= be; p++) {
@@ -105,7 +108,7 @@ static void candidates_walk(const u8* frame, size_t lowLimit, size_t bs, size_t 
         u32 d = (rel - table[h]) & 0xFFFFu;
         if (d == 0 || d > rel || tags[h] != tag) d = 0;
         if (p >= bs) dist[p - bs] = (u16)d;
-        if ((p % insPeriod) < 2) { table[h] = (u16)rel; tags[h] = tag; }
+        if (((p + patOff) % insPeriod) < 2) { table[h] = (u16)rel; tags[h] = tag; }
     }
     for (size_t p = (be >= 8 && be - 7 > bs) ? be - 7 : bs; p < be; p++) dist[p - bs] = 0;   /* no 8-byte read there */
     free(table); free(tags);
@@ -134,7 +137,7 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
     u16* const dist = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
 
-    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, dist);
+    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, dist);
 
     while (ip + 8 <= be) {
         u32 const step = plan->stepSize + (u32)((ip - searchStart) >> 7);     /* kSearchStrength = 8, zstd_fast.c:234 */
@@ -192,8 +195,8 @@ static size_t matchBlock_dfast(const zbo_plan* plan, const u8* frame, size_t fra
     u16* const distS = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
 
-    candidates_walk(frame, lowLimit, bs, be, 8, plan->longHashLog, plan->insPeriodLong, distL);
-    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, distS);
+    candidates_walk(frame, lowLimit, bs, be, 8, plan->longHashLog, plan->insPeriodLong, plan->frameStart, distL);
+    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, distS);
 
     while (ip + 9 <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
         u32 const step = 1 + (u32)((ip - searchStart) >> 8);

@@ -61,6 +61,7 @@ typedef struct {
     u32 stepSize;     /* targetLength + !targetLength + 1 (zstd_fast.c:200); dfast: 1 */
     u32 insPeriod;    /* positions with (framePos % insPeriod) < 2 are inserted into the table */
     u32 insPeriodLong;/* dfast: same for the 8-byte-hash table */
+    size_t frameStart;/* index of the frame's first byte inside the buffer handed to zbo_matchBlock (dictionary tail in front) */
     u32 primeBytes;   /* history window primed before the block */
     u32 strategy;     /* 1 fast, 2 dfast */
     u32 windowLog;

@@ -154,3 +154,39 @@ def test_many_small_frames(ctx):
         start = sum(csz[:i])
         assert out[start:start + csz[i]] == zref.oracle_compress(src[i * rec:(i + 1) * rec], 1)
     decode_ok(out, src)
+
+
+@pytest.mark.parametrize("dict_name", ["zdict-16k-synthetic-seed77", "http-dict-missing-symbols", "zero-weight-dict", "raw-32k"])
+def test_compress_using_dict(ctx, dict_name):
+    """ZSTD_compress_usingDict (lib/zstd.h:944), config-5 shape: 1 KiB records + shared dictionary; also
+    empty / tiny / multi-block inputs.  Bit-exact with the oracle, decodable by ZSTD_decompress_usingDict."""
+    d = zref.synthetic(32 << 10, 123, 0.5) if dict_name == "raw-32k" else zref.golden_input(dict_name)
+    data = zref.synthetic(1024 * 64, 5, 0.5)
+    srcs = [data[i * 1024:(i + 1) * 1024] for i in range(64)] + [b"", b"a", d[-2000:-900], zref.golden_input("http"), zref.synthetic(300_000, 8)]
+    for src in srcs:
+        got = ctx.compress_using_dict(src, d, 1)
+        assert got == zref.oracle_compress_using_dict(src, d, 1)
+        if zref.have_ref():
+            assert zref.ref_decompress_using_dict(got, d, len(src)) == src
+    assert ctx.compress_using_dict(srcs[0], b"1234567", 1) == ctx.compress(srcs[0], 1)        # < 8 bytes: ignored
+
+
+def test_many_records_with_dictionary(ctx):
+    """BASELINE config 5 in one call: N x 1 KiB records + one shared dictionary -> N frames."""
+    import torch
+    d = zref.golden_input("zdict-16k-synthetic-seed77")
+    rec, n = 1024, 4096
+    src = zref.synthetic(rec * n, 91, 0.5)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = n * (zstd_b200.ZSTD_compressBound(rec) + 32)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    total, csz = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), [i * rec for i in range(n)], [rec] * n, level=1, dict_bytes=d)
+    out = bytes(d_dst[:total].cpu().numpy())
+    assert sum(csz) == total
+    pos = 0
+    for i in range(n):
+        if i % 131 == 0:
+            assert out[pos:pos + csz[i]] == zref.oracle_compress_using_dict(src[i * rec:(i + 1) * rec], d, 1)
+            if zref.have_ref():
+                assert zref.ref_decompress_using_dict(out[pos:pos + csz[i]], d, rec) == src[i * rec:(i + 1) * rec]
+        pos += csz[i]

@@ -137,3 +137,40 @@ def sha(b: bytes) -> str:
 
 def random_bytes(n: int, seed: int = 0) -> bytes:
     return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
+def oracle_compress_using_dict(src: bytes, dict_bytes: bytes, level: int) -> bytes:
+    O = oracle()
+    cap = O.zbo_compressBound(len(src)) + 64
+    dst = ctypes.create_string_buffer(cap)
+    r = O.zbo_compress_usingDict(dst, cap, src, len(src), dict_bytes, len(dict_bytes), level)
+    if r > (1 << 63):
+        raise RuntimeError(f"oracle error {-(r - (1 << 64))}")
+    return dst.raw[:r]
+
+
+def ref_compress_using_dict(src: bytes, dict_bytes: bytes, level: int) -> bytes:
+    R = ref()
+    cctx = R.ZSTD_createCCtx()
+    cap = R.ZSTD_compressBound(len(src))
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = R.ZSTD_compress_usingDict(cctx, dst, cap, src, len(src), dict_bytes, len(dict_bytes), level)
+    R.ZSTD_freeCCtx(cctx)
+    assert not R.ZSTD_isError(r), R.ZSTD_getErrorName(r)
+    return dst.raw[:r]
+
+
+def ref_decompress_using_dict(frame: bytes, dict_bytes: bytes, max_size: int) -> bytes:
+    R = ref()
+    dctx = R.ZSTD_createDCtx()
+    out = ctypes.create_string_buffer(max(max_size, 1))
+    r = R.ZSTD_decompress_usingDict(dctx, out, max_size, frame, len(frame), dict_bytes, len(dict_bytes))
+    R.ZSTD_freeDCtx(dctx)
+    if R.ZSTD_isError(r):
+        raise ValueError("reference decoder: " + R.ZSTD_getErrorName(r).decode())
+    return out.raw[:r]
+
+
+def golden_input(name: str) -> bytes:
+    with open(os.path.join(GOLDEN, "inputs", name), "rb") as f:
+        return f.read()

@@ -54,6 +54,49 @@ __device__ __forceinline__ void zb_ld_pre_cur(const u8* base, u32 x, u32* pre, u
     *cur = (u32)(w >> (32u - 8u * s));
 }
 
+/* ---- two-segment addressing (dictionary content in front of a frame, zstd_compress_internal.h:797
+ * ZSTD_count_2segments is the reference's counterpart): rel positions < split live in `lo`, the rest
+ * in `hi`; both pointers are pre-biased so that ptr + rel is the byte's address. ---- */
+struct ZbSeg { const u8* lo; const u8* hi; u32 split; };
+
+template <bool DICT> __device__ __forceinline__ const u8* zb_seg_ptr(const ZbSeg& s, u32 rel)
+{
+    if (DICT) return (rel < s.split ? s.lo : s.hi) + rel;
+    return s.hi + rel;
+}
+template <bool DICT> __device__ __forceinline__ u8 zb_seg_byte(const ZbSeg& s, u32 rel) { return *zb_seg_ptr<DICT>(s, rel); }
+
+/* 8 bytes at rel (3-word form: the caller guarantees rel + 12 stays inside the input) */
+template <bool DICT> __device__ __forceinline__ u64 zb_seg_ld64(const ZbSeg& s, u32 rel)
+{
+    if (DICT && rel < s.split && rel + 12u > s.split) {          /* straddles the dictionary / frame boundary */
+        u64 v = 0;
+#pragma unroll
+        for (u32 i = 0; i < 8u; i++) v |= (u64)zb_seg_byte<true>(s, rel + i) << (8u * i);
+        return v;
+    }
+    return zb_ld64w3(zb_seg_ptr<DICT>(s, rel));
+}
+/* exact 8-byte load that never touches a byte past rel+7 (match extension up to the block end) */
+template <bool DICT> __device__ __forceinline__ u64 zb_seg_ld64x(const ZbSeg& s, u32 rel)
+{
+    if (DICT && rel < s.split && rel + 12u > s.split) {
+        u64 v = 0;
+#pragma unroll
+        for (u32 i = 0; i < 8u; i++) v |= (u64)zb_seg_byte<true>(s, rel + i) << (8u * i);
+        return v;
+    }
+    return zb_ld64u(zb_seg_ptr<DICT>(s, rel));
+}
+template <bool DICT> __device__ __forceinline__ u32 zb_seg_ld32(const ZbSeg& s, u32 rel) { return (u32)zb_seg_ld64<DICT>(s, rel); }
+template <bool DICT> __device__ __forceinline__ void zb_seg_pre_cur(const ZbSeg& sg, u32 x, u32* pre, u32* cur)
+{
+    u32 const s = x >= 4u ? 0u : 4u - x;
+    u64 const w = zb_seg_ld64<DICT>(sg, x + s - 4u);
+    *pre = (u32)(w << (8u * s));
+    *cur = (u32)(w >> (32u - 8u * s));
+}
+
 /* /root/reference/lib/compress/zstd_compress_internal.h:815-861 */
 __device__ __forceinline__ u32 zb_hash(u64 v, u32 mls, u32 hBits)
 {

@@ -10,8 +10,10 @@ extern "C" {
 
 /* K1: match-finder = K1a candidate table walk + K1b greedy parse.  One warp per block each.
  * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records);
- * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates). */
-cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+ * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates).
+ * d_dictEnd: one past the dictionary content in device memory (NULL = no dictionary); blocks flagged
+ * ZB_FLAG_DICT take their histLen bytes of history from in front of it. */
+cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                             u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
 /* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block. */

@@ -20,24 +20,40 @@
 #include "zb_kernels.h"
 
 /* matched bytes starting at rel positions (a, a - offset), never reading at or past `be` */
-__device__ __forceinline__ u32 zb_count_fwd(const u8* __restrict__ base, u32 a, u32 offset, u32 be, u32 lane)
+template <bool DICT>
+__device__ __forceinline__ u32 zb_count_fwd(const ZbSeg& sg, u32 a, u32 offset, u32 be, u32 lane)
 {
     u32 fwd = 0;
     while (true) {
         u32 const pa = a + fwd + 8u * lane;
         u32 m;
         if (pa + 8u <= be) {
-            u64 const x = zb_ld64u(base + pa) ^ zb_ld64u(base + pa - offset);
+            u64 const x = zb_seg_ld64x<DICT>(sg, pa) ^ zb_seg_ld64x<DICT>(sg, pa - offset);
             m = x ? (u32)((__ffsll((long long)x) - 1) >> 3) : 8u;
         } else {
             m = 0;
-            while (pa + m < be && base[pa + m] == base[pa + m - offset]) m++;
+            while (pa + m < be && zb_seg_byte<DICT>(sg, pa + m) == zb_seg_byte<DICT>(sg, pa + m - offset)) m++;
         }
         u32 const inc = __ballot_sync(ZB_FULL, m != 8u);
         if (inc == 0) { fwd += 256u; continue; }
         int const f = __ffs((int)inc) - 1;
         fwd += 8u * (u32)f + __shfl_sync(ZB_FULL, m, f);
         return fwd;
+    }
+}
+
+template <bool DICT>
+__device__ __forceinline__ u32 zb_back_coop(const ZbSeg& sg, u32 probe, u32 offset, u32 anchor, u32 lane)
+{
+    u32 back = 0;
+    while (true) {
+        u32 const k = back + lane + 1u;                        /* compare bytes probe-k and probe-offset-k */
+        bool const ok = (probe >= anchor + k) && (probe >= offset + k)
+                     && (zb_seg_byte<DICT>(sg, probe - k) == zb_seg_byte<DICT>(sg, probe - offset - k));
+        u32 const okb = __ballot_sync(ZB_FULL, ok);
+        u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
+        back += cnt;
+        if (cnt < 32u) return back;
     }
 }
 
@@ -124,7 +140,7 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
 
 template <int MLS>
 __global__ void __launch_bounds__(32)
-zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
+zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
 {
     __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
     extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog positions, followed by 2^hashLog tags */
@@ -142,6 +158,21 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
     u32 const o0 = (u32)((uintptr_t)base & 15u);
     const u8* const abase = base - o0;
+    /* history of a dictionary block lives in the dictionary buffer: 16-byte units that are not entirely
+     * frame bytes are assembled byte-wise (arbitrary mutual alignment), the rest goes through cp.async */
+    bool const dictBlk = dictEnd != nullptr && (bd.flags & ZB_FLAG_DICT);
+    const u8* const dlo = dictBlk ? dictEnd - bd.histLen : base;
+    auto stage = [&](u32 q) {
+        if (!dictBlk || q >= o0 + bd.histLen) { __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16); return; }
+        u32 w[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+        for (u32 k = 0; k < 16u; k++) {
+            u32 const rel = q + k - o0;                       /* wraps for q + k < o0 : treated as out of range */
+            u32 const byte = (q + k < o0 || rel >= bd.histLen + bd.size) ? 0u : (u32)(rel < bd.histLen ? dlo[rel] : base[rel]);
+            w[k >> 2] |= byte << (8u * (k & 3u));
+        }
+        *reinterpret_cast<uint4*>(ring + (q & (CAND_RING - 1u))) = make_uint4(w[0], w[1], w[2], w[3]);
+    };
     u32 const qEnd = o0 + be;                                     /* one past the last byte we may read */
     u32 const nChunks = (qEnd + CAND_CHUNK - 1u) / CAND_CHUNK;
 
@@ -153,7 +184,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
 #pragma unroll
     for (u32 c = 0; c < CAND_STAGES - 1u; c++) {
         u32 const q = c * CAND_CHUNK + 16u * lane;
-        if (c < nChunks && q < qEnd) __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16);
+        if (c < nChunks && q < qEnd) stage(q);
         __pipeline_commit();
     }
     __syncwarp();
@@ -169,7 +200,7 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
     for (u32 c = 0; c < nChunks; c++) {
         {   u32 const cn = c + CAND_STAGES - 1u;                  /* refill the slot consumed in the previous iteration */
             u32 const q = cn * CAND_CHUNK + 16u * lane;
-            if (cn < nChunks && q < qEnd) __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16);
+            if (cn < nChunks && q < qEnd) stage(q);
             __pipeline_commit();
         }
         /* chunk c and (for the 8-byte reads that straddle its end) chunk c+1 must have landed */
@@ -256,8 +287,9 @@ zb_cand_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, Z
  * ---------------------------------------------------------------------------------------------- */
 #define PARSE_WARPS 4
 #define PARSE_PF_AHEAD 2048u
+template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
-zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
+zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
                 const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
     u32 const lane = threadIdx.x & 31u;
@@ -267,8 +299,10 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
     u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
     u8*  const mylit = lits + (size_t)b * ZB_LIT_STRIDE;
     const u16* const mydist = dist + (size_t)b * ZB_BLOCK_MAX;
-    const u8* const base = src + bd.srcOff - bd.histLen;
+    const u8* const base = src + bd.srcOff - bd.histLen;          /* base + rel addresses the frame's own bytes */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+    ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
+    if (DICT && (bd.flags & ZB_FLAG_DICT)) { sg.lo = dictEnd - bd.histLen; sg.split = bd.histLen; }   /* history = dictionary tail */
 
     if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
         if (lane == 0) {
@@ -306,10 +340,10 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
         /* dist[] only holds candidates K1a has already verified (4 equal bytes), so a step needs no random
          * load: the current window and the repcode windows are contiguous across lanes */
         u32 pre, cur, pre2, cur2;
-        zb_ld_pre_cur(base, pp, &pre, &cur);
-        zb_ld_pre_cur(base, v2 ? pp - rep1 : pp, &pre2, &cur2);
+        zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
+        zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
         u32 cur3 = ~cur;
-        if (ip == anchor && rep2 != 0u) cur3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));     /* warp-uniform condition */
+        if (ip == anchor && rep2 != 0u) cur3 = zb_seg_ld32<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
         u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
         u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
@@ -336,24 +370,14 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
             u32 more = __shfl_sync(ZB_FULL, mymore, winner);
             offset = (wtype == 3u) ? rep2 : ((wtype == 2u) ? rep1 : wd);
             if (wtype == 1u) {
-                u32 const f0 = zb_count_fwd(base, probe, offset, be, lane);          /* from the probe itself */
+                u32 const f0 = zb_count_fwd<DICT>(sg, probe, offset, be, lane);          /* from the probe itself */
                 if (f0 < 4u) { tent &= ~(1u << winner); continue; }                   /* tag collision */
                 fwdFrom4 = f0 - 4u;
                 more = 1u;
             } else {
-                fwdFrom4 = zb_count_fwd(base, probe + 4u, offset, be, lane);
+                fwdFrom4 = zb_count_fwd<DICT>(sg, probe + 4u, offset, be, lane);
             }
-            if (more) {                                         /* table hit, or a repcode hit with > 4 bytes of catch-up */
-                while (true) {
-                    u32 const k = back + lane + 1u;            /* compare bytes probe-k and probe-offset-k */
-                    bool const ok = (probe >= anchor + k) && (probe >= offset + k)
-                                 && (base[probe - k] == base[probe - offset - k]);
-                    u32 const okb = __ballot_sync(ZB_FULL, ok);
-                    u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
-                    back += cnt;
-                    if (cnt < 32u) break;
-                }
-            }
+            if (more) back += zb_back_coop<DICT>(sg, probe - back, offset, anchor, lane);   /* table hit, or a repcode hit with > 4 bytes of catch-up */
             found = true;
             break;
         }
@@ -392,19 +416,6 @@ zb_parse_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, 
  * repcode-2 at lane 0 right after a match (:302-316).  Table candidates are tag-verified only: the
  * winning lane's bytes are checked while the match is extended, a false positive drops out.
  * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ u32 zb_back_coop(const u8* __restrict__ base, u32 probe, u32 offset, u32 anchor, u32 lane)
-{
-    u32 back = 0;
-    while (true) {
-        u32 const k = back + lane + 1u;                        /* compare bytes probe-k and probe-offset-k */
-        bool const ok = (probe >= anchor + k) && (probe >= offset + k) && (base[probe - k] == base[probe - offset - k]);
-        u32 const okb = __ballot_sync(ZB_FULL, ok);
-        u32 const cnt = (okb == ZB_FULL) ? 32u : (u32)(__ffs((int)~okb) - 1);
-        back += cnt;
-        if (cnt < 32u) return back;
-    }
-}
-
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
 zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
                       const u16* __restrict__ distLong, const u16* __restrict__ distShort,
@@ -420,6 +431,7 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     const u16* const dSp = distShort + (size_t)b * ZB_BLOCK_MAX;
     const u8* const base = src + bd.srcOff - bd.histLen;
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+    ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
 
     if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
         if (lane == 0) {
@@ -469,12 +481,12 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
             u32 const probe = __shfl_sync(ZB_FULL, p, winner);
             wtype = __shfl_sync(ZB_FULL, hit, winner);
             u32 const wL = __shfl_sync(ZB_FULL, dL, winner), wS = __shfl_sync(ZB_FULL, dS, winner), wL1 = __shfl_sync(ZB_FULL, dL1, winner);
-            if (wtype == 3u) { ms = probe; offset = rep2; mlen = 4u + zb_count_fwd(base, probe + 4u, rep2, be, lane); found = true; break; }
-            if (wtype == 2u) { ms = probe + 1u; offset = rep1; mlen = 4u + zb_count_fwd(base, probe + 5u, rep1, be, lane); found = true; break; }
+            if (wtype == 3u) { ms = probe; offset = rep2; mlen = 4u + zb_count_fwd<false>(sg, probe + 4u, rep2, be, lane); found = true; break; }
+            if (wtype == 2u) { ms = probe + 1u; offset = rep1; mlen = 4u + zb_count_fwd<false>(sg, probe + 5u, rep1, be, lane); found = true; break; }
             if (wtype == 1u) {
-                u32 const f0 = zb_count_fwd(base, probe, wL, be, lane);
+                u32 const f0 = zb_count_fwd<false>(sg, probe, wL, be, lane);
                 if (f0 >= 8u) {
-                    u32 const back = zb_back_coop(base, probe, wL, anchor, lane);
+                    u32 const back = zb_back_coop<false>(sg, probe, wL, anchor, lane);
                     ms = probe - back; offset = wL; mlen = back + f0; found = true; break;
                 }
                 /* tag collision on the long table: the lane may still have a short candidate */
@@ -483,14 +495,14 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
                 continue;
             }
             /* short candidate */
-            {   u32 const f0 = zb_count_fwd(base, probe, wS, be, lane);
+            {   u32 const f0 = zb_count_fwd<false>(sg, probe, wS, be, lane);
                 if (f0 < 4u) { tent &= ~(1u << winner); if (lane == (u32)winner) hit = 0u; continue; }
                 u32 mp = probe, mo = wS, ml = f0;
                 if (wL1) {
-                    u32 const f1 = zb_count_fwd(base, probe + 1u, wL1, be, lane);
+                    u32 const f1 = zb_count_fwd<false>(sg, probe + 1u, wL1, be, lane);
                     if (f1 >= 8u && f1 > ml) { mp = probe + 1u; mo = wL1; ml = f1; }
                 }
-                u32 const back = zb_back_coop(base, mp, mo, anchor, lane);
+                u32 const back = zb_back_coop<false>(sg, mp, mo, anchor, lane);
                 ms = mp - back; offset = mo; mlen = back + ml; wtype = 1u; found = true; break;
             }
         }
@@ -516,7 +528,7 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     }
 }
 
-static void zb_launch_cand(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist, cudaStream_t stream)
+static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist, cudaStream_t stream)
 {
     size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
     static bool optin = false;
@@ -529,15 +541,15 @@ static void zb_launch_cand(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlock
         optin = true;
     }
     switch (prm.mls) {
-    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
-    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
-    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
-    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
-    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_blocks, prm, d_dist); break;
+    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
+    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
+    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
+    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
+    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
     }
 }
 
-extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                                        u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
@@ -545,14 +557,15 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const ZbBlock* d_blocks,
     if (prm->strategy == 2) {
         /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
         ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
-        zb_launch_cand(d_src, d_blocks, nbBlocks, pl, d_dist, stream);
-        zb_launch_cand(d_src, d_blocks, nbBlocks, *prm, d_dist2, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, d_dist, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist2, stream);
         if (evMid) cudaEventRecord(evMid, stream);
         zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_dist2, d_seqs, d_lits, d_meta);
     } else {
-        zb_launch_cand(d_src, d_blocks, nbBlocks, *prm, d_dist, stream);
+        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, stream);
         if (evMid) cudaEventRecord(evMid, stream);
-        zb_parse_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
+        if (d_dictEnd) zb_parse_kernel<true><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
+        else           zb_parse_kernel<false><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
     }
     return cudaGetLastError();
 }
