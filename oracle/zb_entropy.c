@@ -637,8 +637,33 @@ size_t zbo_huf_encode4X(u8* dst, size_t cap, const u8* src, size_t n, const zbo_
     return (size_t)(op - dst);
 }
 
-/* huf_compress.c:1333-1430 with repeat==none (fresh table), flags = suspectUncompressible only */
-static size_t huf_compress_fresh(u8* dst, size_t cap, const u8* src, size_t n, int fourStreams, int suspectUncompressible)
+/* encode with a given table: huf_compress.c:1218-1233 (HUF_compressCTable_internal); `already` = header bytes in front */
+static size_t huf_encodeWith(u8* dst, u8* op, size_t capLeft, const u8* src, size_t n, int fourStreams, const zbo_huf_ctable* ct)
+{
+    size_t const c = fourStreams ? zbo_huf_encode4X(op, capLeft, src, n, ct) : zbo_huf_encode1X(op, capLeft, src, n, ct);
+    if (c == 0) return 0;
+    op += c;
+    if ((size_t)(op - dst) >= n - 1) return 0;
+    return (size_t)(op - dst);
+}
+static size_t huf_estimate(const zbo_huf_ctable* ct, const u32* count, u32 maxSymbolValue)      /* huf_compress.c:793 */
+{
+    size_t nbBits = 0;
+    for (u32 s = 0; s <= maxSymbolValue; s++) nbBits += (size_t)ct->nbBits[s] * count[s];
+    return nbBits >> 3;
+}
+static int huf_validate(const zbo_huf_ctable* ct, const u32* count, u32 maxSymbolValue)          /* huf_compress.c:804 */
+{
+    int bad = 0;
+    if (ct->maxSymbolValue < maxSymbolValue) return 0;
+    for (u32 s = 0; s <= maxSymbolValue; s++) bad |= (count[s] != 0) & (ct->nbBits[s] == 0);
+    return !bad;
+}
+
+/* huf_compress.c:1333-1430.  prev/repeatPtr describe the previous block's table (NULL / 0 = none);
+ * on return *repeatPtr != 0 means the previous table was used (treeless literals). */
+static size_t huf_compress_internal(u8* dst, size_t cap, const u8* src, size_t n, int fourStreams, int suspectUncompressible,
+                                    const zbo_huf_ctable* prev, u32* repeatPtr, int preferRepeat)
 {
     u32 count[256];
     u32 maxSymbolValue = HUF_SYMBOLVALUE_MAX;
@@ -646,9 +671,13 @@ static size_t huf_compress_fresh(u8* dst, size_t cap, const u8* src, size_t n, i
     zbo_huf_ctable ct;
     u8* op = dst;
     u8* const oend = dst + cap;
+    u32 repeat = (prev && repeatPtr) ? *repeatPtr : 0;
 
     if (!n || !cap) return 0;
     if (n > ZB_BLOCK_MAX) return ZBO_ERR(ZBO_error_srcSize_wrong);
+
+    if (preferRepeat && repeat == 2)                                            /* :1359-1363 */
+        return huf_encodeWith(dst, op, cap, src, n, fourStreams, prev);
 
     if (suspectUncompressible && n >= 4096 * 10) {            /* :1367-1379 */
         size_t largestTotal = 0;
@@ -661,6 +690,10 @@ static size_t huf_compress_fresh(u8* dst, size_t cap, const u8* src, size_t n, i
         if (largest == n) { *dst = src[0]; return 1; }
         if (largest <= (n >> 7) + 4) return 0;
     }
+    if (repeat == 1 && !huf_validate(prev, count, maxSymbolValue)) { repeat = 0; *repeatPtr = 0; }     /* :1389-1393 */
+    if (preferRepeat && repeat != 0)                                             /* :1395-1399 */
+        return huf_encodeWith(dst, op, cap, src, n, fourStreams, prev);
+
     huffLog = zbo_fse_optimalTableLog(huffLog, n, maxSymbolValue, 1);   /* :1402 -> :1284-1287 */
     {   size_t const maxBits = zbo_huf_buildCTable(&ct, count, maxSymbolValue, huffLog);
         if (zbo_isError(maxBits)) return maxBits;
@@ -668,16 +701,17 @@ static size_t huf_compress_fresh(u8* dst, size_t cap, const u8* src, size_t n, i
     }
     {   size_t const hSize = zbo_huf_writeCTable(op, cap, &ct);            /* :1412 */
         if (zbo_isError(hSize)) return hSize;
+        if (repeat != 0) {                                                   /* :1415-1422 */
+            size_t const oldSize = huf_estimate(prev, count, maxSymbolValue);
+            size_t const newSize = huf_estimate(&ct, count, maxSymbolValue);
+            if (oldSize <= hSize + newSize || hSize + 12 >= n)
+                return huf_encodeWith(dst, op, cap, src, n, fourStreams, prev);
+        }
         if (hSize + 12ul >= n) return 0;
         op += hSize;
+        if (repeatPtr) *repeatPtr = 0;
     }
-    {   size_t const c = fourStreams ? zbo_huf_encode4X(op, (size_t)(oend - op), src, n, &ct)   /* :1218-1233 */
-                                     : zbo_huf_encode1X(op, (size_t)(oend - op), src, n, &ct);
-        if (c == 0) return 0;
-        op += c;
-        if ((size_t)(op - dst) >= n - 1) return 0;
-    }
-    return (size_t)(op - dst);
+    return huf_encodeWith(dst, op, (size_t)(oend - op), src, n, fourStreams, &ct);
 }
 
 /* zstd_compress_literals.c:39-63 */
@@ -706,38 +740,53 @@ static size_t lit_rle(u8* dst, const u8* src, size_t n)
     return flSize + 1;
 }
 
-/* zstd_compress_literals.c:129-235 with prevHuf->repeatMode == HUF_repeat_none */
-size_t zbo_compressLiterals(u8* dst, size_t cap, const u8* lit, size_t n,
-                            u32 strategy, int disableLiteralCompression, int suspectUncompressible)
+/* zstd_compress_literals.c:129-235.  prev == NULL : previous table absent (HUF_repeat_none) */
+static size_t compressLiterals_prev(u8* dst, size_t cap, const u8* lit, size_t n,
+                                    u32 strategy, int disableLiteralCompression, int suspectUncompressible,
+                                    const zbo_huf_ctable* prev, u32 prevRepeat)
 {
     size_t const lhSize = 3 + (n >= 1024) + (n >= 16384);
-    u32 const singleStream = n < 256;
+    u32 singleStream = n < 256;
+    u32 hType = 2;                                         /* set_compressed */
     size_t cLitSize;
-    (void)strategy;
+    u32 repeat = prev ? prevRepeat : 0;
 
     if (disableLiteralCompression) return lit_raw(dst, cap, lit, n);
-    {   /* :114-127 : fast/dfast -> 8<<3 = 64 */
+    {   /* :114-127 */
         int const shift = (9 - (int)strategy) < 3 ? (9 - (int)strategy) : 3;
-        size_t const mintc = (size_t)8 << shift;
+        size_t const mintc = (repeat == 2) ? 6 : (size_t)8 << shift;
         if (n < mintc) return lit_raw(dst, cap, lit, n);
     }
     if (cap < lhSize + 1) return ZBO_ERR(ZBO_error_dstSize_tooSmall);
-    cLitSize = huf_compress_fresh(dst + lhSize, cap - lhSize, lit, n, !singleStream, suspectUncompressible);
+    {   int const preferRepeat = (strategy < 4 /* ZSTD_lazy */) && (n <= 1024);            /* :165 */
+        if (repeat == 2 && lhSize == 3) singleStream = 1;                                  /* :171 */
+        cLitSize = huf_compress_internal(dst + lhSize, cap - lhSize, lit, n, !singleStream, suspectUncompressible,
+                                         prev, &repeat, preferRepeat);
+        if (repeat != 0) hType = 3;                         /* set_repeat: reused the existing table */
+    }
     {   size_t const minGain = (n >> 6) + 2;             /* zstd_compress_internal.h:613 */
         if (cLitSize == 0 || zbo_isError(cLitSize) || cLitSize >= n - minGain) return lit_raw(dst, cap, lit, n);
     }
-    if (cLitSize == 1) return lit_rle(dst, lit, n);       /* n >= 64 here, so :197-205 always RLE */
-
+    if (cLitSize == 1) {                                    /* :193-205 */
+        int same = 1;
+        if (n < 8) for (size_t i = 1; i < n; i++) if (lit[i] != lit[0]) same = 0;
+        if (n >= 8 || same) return lit_rle(dst, lit, n);
+    }
     switch (lhSize) {
-    case 3: { u32 const lhc = 2 + ((u32)(!singleStream) << 2) + ((u32)n << 4) + ((u32)cLitSize << 14);
+    case 3: { u32 const lhc = hType + ((u32)(!singleStream) << 2) + ((u32)n << 4) + ((u32)cLitSize << 14);
               dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); } break;
-    case 4: { u32 const lhc = 2 + (2 << 2) + ((u32)n << 4) + ((u32)cLitSize << 18);
+    case 4: { u32 const lhc = hType + (2 << 2) + ((u32)n << 4) + ((u32)cLitSize << 18);
               dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); dst[3] = (u8)(lhc >> 24); } break;
-    default:{ u32 const lhc = 2 + (3 << 2) + ((u32)n << 4) + ((u32)cLitSize << 22);
+    default:{ u32 const lhc = hType + (3 << 2) + ((u32)n << 4) + ((u32)cLitSize << 22);
               dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); dst[3] = (u8)(lhc >> 24);
               dst[4] = (u8)(cLitSize >> 10); } break;
     }
     return lhSize + cLitSize;
+}
+size_t zbo_compressLiterals(u8* dst, size_t cap, const u8* lit, size_t n,
+                            u32 strategy, int disableLiteralCompression, int suspectUncompressible)
+{
+    return compressLiterals_prev(dst, cap, lit, n, strategy, disableLiteralCompression, suspectUncompressible, NULL, 0);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -784,8 +833,8 @@ static u32 ml_code(u32 mlBase)
 
 enum { set_basic = 0, set_rle = 1, set_compressed = 2, set_repeat = 3 };
 
-/* zstd_compress_sequences.c:157-240, branch strategy < ZSTD_lazy, repeatMode == none */
-static int seq_selectEncodingType(u32 mostFrequent, size_t nbSeq, u32 defaultNormLog, int isDefaultAllowed, u32 strategy)
+/* zstd_compress_sequences.c:157-240, branch strategy < ZSTD_lazy; prevRepeat = FSE_repeat of the previous table (2 = valid) */
+static int seq_selectEncodingType(u32 mostFrequent, size_t nbSeq, u32 defaultNormLog, int isDefaultAllowed, u32 strategy, u32 prevRepeat)
 {
     if (mostFrequent == nbSeq) {
         if (isDefaultAllowed && nbSeq <= 2) return set_basic;
@@ -794,6 +843,7 @@ static int seq_selectEncodingType(u32 mostFrequent, size_t nbSeq, u32 defaultNor
     if (isDefaultAllowed) {
         size_t const mult = 10 - strategy;
         size_t const dynamicFse_nbSeq_min = (((size_t)1 << defaultNormLog) * mult) >> 3;
+        if (prevRepeat == 2 && nbSeq < 1000) return set_repeat;                     /* :187-191 */
         if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return set_basic;
     }
     return set_compressed;
@@ -805,6 +855,8 @@ static size_t seq_buildCTable(u8* dst, size_t cap, zbo_fse_ctable* ct, u32 FSELo
                               const int16_t* defaultNorm, u32 defaultNormLog, u32 defaultMax)
 {
     switch (type) {
+    case set_repeat:
+        return 0;                                   /* caller already points at the previous table, :260-262 */
     case set_rle:
         zbo_fse_buildCTable_rle(ct, (u8)max);
         if (cap == 0) return ZBO_ERR(ZBO_error_dstSize_tooSmall);
@@ -834,6 +886,15 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
                                 const u8* lit, size_t litSize,
                                 size_t blockSrcSize, u32 strategy, int disableLiteralCompression)
 {
+    return zbo_entropyCompressBlock_prev(dst, cap, seqs, nbSeq, lit, litSize, blockSrcSize, strategy, disableLiteralCompression, NULL);
+}
+
+size_t zbo_entropyCompressBlock_prev(u8* dst, size_t cap,
+                                const zbo_seq* seqs, size_t nbSeq,
+                                const u8* lit, size_t litSize,
+                                size_t blockSrcSize, u32 strategy, int disableLiteralCompression,
+                                const zbo_dict_entropy* prev)
+{
     u8* op = dst;
     u8* const oend = dst + cap;
     size_t lastCountSize = 0;
@@ -841,7 +902,8 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
     size_t result = 0;
 
     {   int const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);          /* :2915-2917 */
-        size_t const c = zbo_compressLiterals(op, cap, lit, litSize, strategy, disableLiteralCompression, suspect);
+        size_t const c = compressLiterals_prev(op, cap, lit, litSize, strategy, disableLiteralCompression, suspect,
+                                               (prev && prev->present) ? &prev->huf : NULL, (prev && prev->present) ? prev->hufRepeat : 0);
         if (zbo_isError(c)) return (c == ZBO_ERR(ZBO_error_dstSize_tooSmall) && blockSrcSize <= cap) ? 0 : c;
         op += c;
     }
@@ -861,9 +923,12 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
         zbo_fse_ctable ctLL, ctOF, ctML;
         u32 count[MaxML + 1];
         int LLtype, Offtype, MLtype;
+        u32 const rLL = (prev && prev->present) ? prev->fseRepeat[0] : 0, rOF = (prev && prev->present) ? prev->fseRepeat[1] : 0,
+                  rML = (prev && prev->present) ? prev->fseRepeat[2] : 0;
         {   u32 max = MaxLL;
             u32 const mostFrequent = zbo_hist(llCode, nbSeq, count, &max);
-            LLtype = seq_selectEncodingType(mostFrequent, nbSeq, 6, 1, strategy);
+            LLtype = seq_selectEncodingType(mostFrequent, nbSeq, 6, 1, strategy, rLL);
+            if (LLtype == set_repeat) ctLL = prev->fse[0];
             size_t const cs = seq_buildCTable(op, (size_t)(oend - op), &ctLL, LLFSELog, LLtype, count, max, llCode, nbSeq, LL_defaultNorm, 6, MaxLL);
             if (zbo_isError(cs)) { result = cs; goto done; }
             if (LLtype == set_compressed) lastCountSize = cs;
@@ -872,7 +937,8 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
         {   u32 max = MaxOff;
             u32 const mostFrequent = zbo_hist(ofCode, nbSeq, count, &max);
             int const defaultAllowed = (max <= DefaultMaxOff);
-            Offtype = seq_selectEncodingType(mostFrequent, nbSeq, 5, defaultAllowed, strategy);
+            Offtype = seq_selectEncodingType(mostFrequent, nbSeq, 5, defaultAllowed, strategy, rOF);
+            if (Offtype == set_repeat) ctOF = prev->fse[1];
             size_t const cs = seq_buildCTable(op, (size_t)(oend - op), &ctOF, OffFSELog, Offtype, count, max, ofCode, nbSeq, OF_defaultNorm, 5, DefaultMaxOff);
             if (zbo_isError(cs)) { result = cs; goto done; }
             if (Offtype == set_compressed) lastCountSize = cs;
@@ -880,7 +946,8 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
         }
         {   u32 max = MaxML;
             u32 const mostFrequent = zbo_hist(mlCode, nbSeq, count, &max);
-            MLtype = seq_selectEncodingType(mostFrequent, nbSeq, 6, 1, strategy);
+            MLtype = seq_selectEncodingType(mostFrequent, nbSeq, 6, 1, strategy, rML);
+            if (MLtype == set_repeat) ctML = prev->fse[2];
             size_t const cs = seq_buildCTable(op, (size_t)(oend - op), &ctML, MLFSELog, MLtype, count, max, mlCode, nbSeq, ML_defaultNorm, 6, MaxML);
             if (zbo_isError(cs)) { result = cs; goto done; }
             if (MLtype == set_compressed) lastCountSize = cs;

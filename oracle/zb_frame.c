@@ -108,83 +108,10 @@ static int isRLE(const u8* src, size_t n)
  * Dictionaries (zstd_compress.c:5119-5156).  A dictionary shorter than 8 bytes is ignored (:5132);
  * without the magic number 0xEC30A437 it is raw content (:5143-5148); with it, it is a zstd-format
  * dictionary: magic, dictID, Huffman table, 3 FSE tables (OF, ML, LL), 3 repcodes, content
- * (ZSTD_loadCEntropy :4987-5076).  This path uses the CONTENT of either kind as history of the
- * frame's first block; a zstd-format dictionary's entropy tables and repcodes are skipped over
- * (their byte sizes are parsed), which is valid — blocks then carry fresh tables and never use a
- * repcode the encoder has not set itself — but gives up the table-reuse saving.
+ * (ZSTD_loadCEntropy :4987-5076, restated in zb_dict.c).  The content of either kind is the history of
+ * the frame's first block; a zstd-format dictionary's Huffman / FSE tables are that block's "previous"
+ * entropy state (treeless literals, set_repeat sequence tables) and its repcodes start the block.
  * ---------------------------------------------------------------------------------------- */
-/* bytes of an FSE table description (normalised counts), 0 if malformed: doc/zstd_compression_format.md:1063 */
-static size_t ncount_bytes(const u8* p, size_t avail, u32 maxSymbol, u32 maxLog)
-{
-    u64 bits = 0; size_t have = 0, pos = 0; u32 nb = 0;        /* little-endian bit reader */
-    u32 tableLog, symbol = 0;
-    int remaining, threshold, nbBits;
-    size_t used = 0;
-#define NEED(k) do { while (nb < (k)) { u64 const byte = pos < avail ? p[pos] : 0; bits |= byte << nb; nb += 8; pos++; } } while (0)
-#define TAKE(k) do { bits >>= (k); nb -= (k); used += (k); } while (0)
-    (void)have;
-    NEED(4); tableLog = (u32)(bits & 15) + 5; TAKE(4);
-    if (tableLog > maxLog) return 0;
-    remaining = (1 << tableLog) + 1; threshold = 1 << tableLog; nbBits = (int)tableLog + 1;
-    while (remaining > 1 && symbol <= maxSymbol) {
-        int const max = (2 * threshold - 1) - remaining;
-        int count;
-        NEED((u32)nbBits);
-        if ((int)(bits & (u32)(threshold - 1)) < max) { count = (int)(bits & (u32)(threshold - 1)); TAKE((u32)nbBits - 1); }
-        else { count = (int)(bits & (u32)(2 * threshold - 1)); if (count >= threshold) count -= max; TAKE((u32)nbBits); }
-        count--;
-        remaining -= count < 0 ? -count : count;
-        symbol++;
-        if (count == 0) {                                /* zero run: 2-bit repeat flags */
-            while (1) {
-                u32 r;
-                NEED(2); r = (u32)(bits & 3); TAKE(2);
-                symbol += r;
-                if (r != 3) break;
-            }
-        }
-        while (remaining < threshold && threshold > 1) { nbBits--; threshold >>= 1; }
-    }
-#undef NEED
-#undef TAKE
-    if (remaining != 1 || symbol > maxSymbol + 1) return 0;
-    {   size_t const bytes = (used + 7) / 8;
-        return bytes <= avail ? bytes : 0; }
-}
-
-/* returns 0 (no dictionary / raw content: *contentOff = 0, *dictID = 0), or an error */
-static size_t dict_parse(const u8* dict, size_t dictSize, size_t* contentOff, u32* dictID)
-{
-    *contentOff = 0; *dictID = 0;
-    if (dictSize < 8) return 0;
-    if (!(dict[0] == 0x37 && dict[1] == 0xA4 && dict[2] == 0x30 && dict[3] == 0xEC)) return 0;     /* ZSTD_MAGIC_DICTIONARY */
-    {   size_t pos = 8;
-        *dictID = (u32)dict[4] | ((u32)dict[5] << 8) | ((u32)dict[6] << 16) | ((u32)dict[7] << 24);
-        if (pos >= dictSize) return ZBO_ERR(ZBO_error_dictionary_corrupted);
-        {   u32 const hb = dict[pos];                                           /* Huffman tree description, huf_compress.c:292 */
-            size_t const hsz = hb >= 128 ? 1 + ((hb - 127) + 1) / 2 : 1 + (size_t)hb;
-            pos += hsz;
-            if (pos >= dictSize) return ZBO_ERR(ZBO_error_dictionary_corrupted);
-        }
-        {   static const u32 maxSym[3] = { 31, 52, 35 }, maxLog[3] = { 8, 9, 9 };  /* OF, ML, LL */
-            for (int t = 0; t < 3; t++) {
-                size_t const n = ncount_bytes(dict + pos, dictSize - pos, maxSym[t], maxLog[t]);
-                if (n == 0) return ZBO_ERR(ZBO_error_dictionary_corrupted);
-                pos += n;
-            }
-        }
-        if (pos + 12 > dictSize) return ZBO_ERR(ZBO_error_dictionary_corrupted);
-        {   size_t const contentSize = dictSize - (pos + 12);
-            for (int r = 0; r < 3; r++) {
-                u32 const rep = (u32)dict[pos + 4 * r] | ((u32)dict[pos + 4 * r + 1] << 8) | ((u32)dict[pos + 4 * r + 2] << 16) | ((u32)dict[pos + 4 * r + 3] << 24);
-                if (rep == 0 || rep > contentSize) return ZBO_ERR(ZBO_error_dictionary_corrupted);
-            }
-        }
-        *contentOff = pos + 12;
-    }
-    return 0;
-}
-
 /* One frame.  Blocks are independent (block-parallel plan); see zb_match.c. */
 size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t srcSize,
                               const void* dictv, size_t dictSize, int level)
@@ -202,11 +129,14 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
     size_t D = 0;                    /* bytes of dictionary content in front of the frame */
 
     zbo_makePlan(&plan, &cp);
+    zbo_dict_entropy* de = NULL;
     if (useDict) {
-        size_t contentOff = 0;
-        size_t const e = dict_parse(dict, dictSize, &contentOff, &dictID);
-        if (zbo_isError(e)) return e;
-        if (cp.strategy != 1) return ZBO_ERR(ZBO_error_parameter_unsupported);     /* dictionaries: fast strategy only for now */
+        size_t contentOff;
+        de = (zbo_dict_entropy*)malloc(sizeof(*de));
+        contentOff = zbo_loadDictEntropy(de, dict, dictSize);
+        if (zbo_isError(contentOff)) { free(de); return contentOff; }
+        dictID = de->dictID;
+        if (cp.strategy != 1) { free(de); return ZBO_ERR(ZBO_error_parameter_unsupported); }     /* dictionaries: fast strategy only for now */
         {   size_t const contentSize = dictSize - contentOff;
             D = contentSize < plan.primeBytes ? contentSize : plan.primeBytes;
             vbuf = (u8*)malloc(D + srcSize + 16);
@@ -216,11 +146,13 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
         }
     }
     plan.frameStart = D;
+    plan.startRep[0] = plan.startRep[1] = 0;
+    if (de && de->present) { plan.startRep[0] = de->rep[0] <= D ? de->rep[0] : 0; plan.startRep[1] = de->rep[1] <= D ? de->rep[1] : 0; }   /* zstd_compress.c:5054-5056 */
     pos = zbo_writeFrameHeader(dst, cap, cp.windowLog, srcSize, dictID);
-    if (zbo_isError(pos)) { free(vbuf); return pos; }
+    if (zbo_isError(pos)) { free(vbuf); free(de); return pos; }
 
     if (srcSize == 0) {                                    /* zstd_compress.c:5279-5295 : empty last raw block */
-        free(vbuf);
+        free(vbuf); free(de);
         if (cap - pos < 3) return ZBO_ERR(ZBO_error_dstSize_tooSmall);
         dst[pos++] = 1; dst[pos++] = 0; dst[pos++] = 0;
         return pos;
@@ -241,8 +173,8 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
                 /* the buffer handed to the matcher starts D bytes in front of the frame: only the first
                  * block's history window reaches back into the dictionary */
                 size_t const nbSeq = zbo_matchBlock(&plan, src - D, srcSize + D, bs + D, blockSize, seqs, lit, &litSize);
-                cSize = zbo_entropyCompressBlock(body, bodyCap, seqs, nbSeq, lit, litSize, blockSize,
-                                                 cp.strategy, (int)plan.litCompressionDisabled);
+                cSize = zbo_entropyCompressBlock_prev(body, bodyCap, seqs, nbSeq, lit, litSize, blockSize,
+                                                      cp.strategy, (int)plan.litCompressionDisabled, first ? de : NULL);
                 if (zbo_isError(cSize)) { err = cSize; break; }
                 if (!first && cSize < 25 && isRLE(src + bs, blockSize)) { cSize = 1; body[0] = src[bs]; }   /* :4365-4376 */
             }
@@ -263,7 +195,7 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
             bs += blockSize;
             first = 0;
         }
-        free(seqs); free(lit); free(body); free(vbuf);
+        free(seqs); free(lit); free(body); free(vbuf); free(de);
         if (err) return err;
     }
     return pos;

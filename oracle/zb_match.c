@@ -133,7 +133,8 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
     size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
     emitter em = { seqs, 0, lit, 0, frame };
     size_t ip = bs, anchor = bs, searchStart = bs;
-    u32 rep1 = 0, rep2 = 0;
+    /* encoder repcodes start invalid, except in a frame's first block behind a zstd-format dictionary */
+    u32 rep1 = (bs == plan->frameStart) ? plan->startRep[0] : 0, rep2 = (bs == plan->frameStart) ? plan->startRep[1] : 0;
     u16* const dist = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
 

@@ -61,6 +61,7 @@ typedef struct {
     u32 stepSize;     /* targetLength + !targetLength + 1 (zstd_fast.c:200); dfast: 1 */
     u32 insPeriod;    /* positions with (framePos % insPeriod) < 2 are inserted into the table */
     u32 insPeriodLong;/* dfast: same for the 8-byte-hash table */
+    u32 startRep[2];  /* repcodes the frame's first block starts with (a zstd-format dictionary's), 0 = invalid */
     size_t frameStart;/* index of the frame's first byte inside the buffer handed to zbo_matchBlock (dictionary tail in front) */
     u32 primeBytes;   /* history window primed before the block */
     u32 strategy;     /* 1 fast, 2 dfast */
@@ -91,6 +92,16 @@ size_t zbo_huf_writeCTable(u8* dst, size_t cap, const zbo_huf_ctable* ct);    /*
 size_t zbo_huf_encode1X(u8* dst, size_t cap, const u8* src, size_t n, const zbo_huf_ctable* ct); /* huf_compress.c:1056 */
 size_t zbo_huf_encode4X(u8* dst, size_t cap, const u8* src, size_t n, const zbo_huf_ctable* ct); /* huf_compress.c:1168 */
 
+/* entropy state a zstd-format dictionary installs as "previous block" (zstd_compress.c:4987-5076) */
+typedef struct {
+    u32 present, dictID;
+    zbo_huf_ctable huf; u32 hufRepeat;          /* 0 none, 1 check, 2 valid (HUF_repeat) */
+    zbo_fse_ctable fse[3]; u32 fseRepeat[3];     /* 0 = LL, 1 = OF, 2 = ML ; FSE_repeat */
+    u32 rep[3];
+} zbo_dict_entropy;
+size_t zbo_readNCount(int16_t* norm, u32* maxSymbolPtr, u32* tableLogPtr, const u8* p, size_t avail);  /* entropy_common.c:42 */
+size_t zbo_loadDictEntropy(zbo_dict_entropy* de, const u8* dict, size_t dictSize);
+
 /* literals section, fresh tables (no repeat/treeless): zstd_compress_literals.c:129 */
 size_t zbo_compressLiterals(u8* dst, size_t cap, const u8* lit, size_t litSize,
                             u32 strategy, int disableLiteralCompression, int suspectUncompressible);
@@ -101,6 +112,12 @@ size_t zbo_entropyCompressBlock(u8* dst, size_t cap,
                                 const zbo_seq* seqs, size_t nbSeq,
                                 const u8* lit, size_t litSize,
                                 size_t blockSrcSize, u32 strategy, int disableLiteralCompression);
+/* same with a dictionary's tables as the previous block's entropy state (prev may be NULL) */
+size_t zbo_entropyCompressBlock_prev(u8* dst, size_t cap,
+                                const zbo_seq* seqs, size_t nbSeq,
+                                const u8* lit, size_t litSize,
+                                size_t blockSrcSize, u32 strategy, int disableLiteralCompression,
+                                const zbo_dict_entropy* prev);
 
 /* ---- match-finder model ---- */
 /* Parses block [blockStart, blockStart+blockSize) of `frame` (frameSize bytes, positions before

@@ -1,7 +1,8 @@
 """ZSTD_compress_usingDict path of the oracle (BASELINE config 5 shape: small records + shared dictionary).
-Frames must decode with the reference's ZSTD_decompress_usingDict; raw-content dictionaries must stay
-within +-0.5 % of the reference's size; zstd-format dictionaries are used for their content only (the
-entropy-table reuse the reference gets from them is a documented gap)."""
+Frames must decode with the reference's ZSTD_decompress_usingDict and stay within +-0.5 % of the
+reference's size for raw-content and zstd-format dictionaries; the dictionary entropy stage (treeless
+literals, set_repeat tables, start repcodes) is pinned byte-for-byte against ZSTD_loadCEntropy +
+ZSTD_entropyCompressSeqStore of the compiled reference."""
 import pytest
 
 import zref
@@ -27,7 +28,10 @@ def test_zstd_format_dictionaries_roundtrip(dict_name):
         assert f[4] & 3, "dictID must be present in the frame header for a zstd-format dictionary"
         tot_o += len(f)
         tot_r += len(zref.ref_compress_using_dict(src, d, 1))
-    assert tot_o < tot_r * 1.06          # content-only use of the dictionary: a few % behind the reference
+    if dict_name.startswith('zdict'):
+        assert abs(tot_o - tot_r) / tot_r <= 0.005, (tot_o, tot_r)
+    else:
+        assert tot_o < tot_r * 1.03          # tiny hand-made dictionaries of the reference's test suite
 
 
 @needs_ref
@@ -61,3 +65,52 @@ def test_short_and_corrupted_dictionaries():
     bad = bytes.fromhex("37a430ec01000000") + bytes(40)
     with pytest.raises(RuntimeError, match="30"):                                                     # dictionary_corrupted
         zref.oracle_compress_using_dict(src, bad, 1)
+
+
+@needs_ref
+@pytest.mark.parametrize("dict_name", ["zdict-16k-synthetic-seed77", "http-dict-missing-symbols", "zero-weight-dict"])
+def test_dictionary_entropy_stage_byte_exact(dict_name):
+    """oracle/zb_dict.c + zbo_entropyCompressBlock_prev vs the reference's ZSTD_loadCEntropy (zstd_compress.c:4987)
+    + ZSTD_entropyCompressSeqStore (:3001) on randomised seqStores, through oracle/ref_shim.c."""
+    import ctypes
+    import numpy as np
+    from test_oracle_entropy import make_seqstore
+    R, O = zref.ref(), zref.oracle()
+    c_sz, vp = ctypes.c_size_t, ctypes.c_void_p
+    R.ref_entropyCompressBlock_dict.restype = c_sz
+    R.ref_entropyCompressBlock_dict.argtypes = [vp, c_sz, vp, vp, vp, c_sz, vp, c_sz, c_sz, ctypes.c_int, ctypes.c_uint, vp, c_sz]
+    O.zbo_loadDictEntropy.restype = c_sz
+    O.zbo_loadDictEntropy.argtypes = [vp, vp, c_sz]
+    O.zbo_entropyCompressBlock_prev.restype = c_sz
+    O.zbo_entropyCompressBlock_prev.argtypes = [vp, c_sz, vp, c_sz, vp, c_sz, c_sz, ctypes.c_uint, ctypes.c_int, vp]
+    d = zref.golden_input(dict_name)
+    de = ctypes.create_string_buffer(16384)
+    assert 8 < O.zbo_loadDictEntropy(de, d, len(d)) < len(d)
+    rng = np.random.default_rng(5)
+    compressed = 0
+    for t in range(250):
+        case = make_seqstore(rng)
+        if case is None:
+            continue
+        offb, ll, ml, lits, block, strategy, tl = case
+        if t % 2 == 0:                                             # the small-record regime (preferRepeat, set_repeat)
+            k = max(1, min(len(offb), 40))
+            offb, ll, ml = offb[:k], ll[:k], ml[:k]
+            lits = lits[:min(len(lits), int(ll.sum()) + 50)]
+            if int(ll.sum()) > len(lits):
+                continue
+            block = max(7, min(131072, len(lits) + int(ml.sum())))
+        nseq = len(offb)
+        cap = 1 << 20
+        d1, d2 = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(cap)
+        seqs = np.ascontiguousarray(np.stack([offb, ll, ml], axis=1).astype(np.uint32)) if nseq else np.zeros((0, 3), np.uint32)
+        offb, ll, ml = (np.ascontiguousarray(a, dtype=np.uint32) for a in (offb, ll, ml))
+        lits = np.ascontiguousarray(lits)
+        tlv = tl if strategy == 1 else 0
+        r1 = R.ref_entropyCompressBlock_dict(d1, cap, offb.ctypes.data, ll.ctypes.data, ml.ctypes.data, nseq, lits.ctypes.data, len(lits), block, 1, tlv, d, len(d))
+        r2 = O.zbo_entropyCompressBlock_prev(d2, cap, seqs.ctypes.data, nseq, lits.ctypes.data, len(lits), block, 1, 1 if tlv > 0 else 0, de)
+        assert r1 == r2
+        if r1 < (1 << 60):
+            assert d1.raw[:r1] == d2.raw[:r2]
+            compressed += r1 > 0
+    assert compressed > 80

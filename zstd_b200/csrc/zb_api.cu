@@ -102,6 +102,9 @@ struct ZSTD_CCtx_s {
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
     u8* d_dict;                    /* dictionary content tail (<= 64 KiB), 32 bytes of padding on both sides */
+    ZbDictEntropy dictEntropy;     /* host copy of the current call's dictionary entropy state */
+    ZbDictEntropy* d_de;           /* device copy */
+    const ZbDictEntropy* d_deActive; /* d_de when the current call's dictionary is zstd-format, else NULL */
     u64* h_totals;                 /* pinned mirror of d_totals */
     cudaEvent_t evStart, evK0, evMid, evK1, evK2, evK3, evKEnd, evEnd;
     ZSTDB200_stats stats;
@@ -159,7 +162,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
-        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict);
+        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de);
         for (int s = 0; s < 8; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
         cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
@@ -218,73 +221,23 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
 /* ------------------------------------------------------------------ dictionaries (zstd_compress.c:5119-5156)
  * < 8 bytes: ignored (:5132).  No magic 0xEC30A437: raw content (:5143-5148).  With it: zstd-format
  * dictionary = magic, dictID, Huffman table, OF/ML/LL FSE tables, 3 repcodes, content (:4987-5076).
- * The CONTENT of either kind is used as history of each frame's first block; a zstd-format dictionary's
- * entropy tables and repcodes are skipped (sizes parsed), which stays a valid frame (fresh tables, no
- * repcode the encoder has not set itself) but gives up the table-reuse saving. */
-static size_t zb_ncountBytes(const u8* p, size_t avail, u32 maxSymbol, u32 maxLog)      /* doc/zstd_compression_format.md:1063 */
-{
-    u64 bits = 0; size_t pos = 0, used = 0; u32 nb = 0, symbol = 0;
-    auto need = [&](u32 k) { while (nb < k) { u64 const byte = pos < avail ? p[pos] : 0; bits |= byte << nb; nb += 8; pos++; } };
-    auto take = [&](u32 k) { bits >>= k; nb -= k; used += k; };
-    need(4); u32 const tableLog = (u32)(bits & 15) + 5; take(4);
-    if (tableLog > maxLog) return 0;
-    int remaining = (1 << tableLog) + 1, threshold = 1 << tableLog, nbBits = (int)tableLog + 1;
-    while (remaining > 1 && symbol <= maxSymbol) {
-        int const max = (2 * threshold - 1) - remaining;
-        int count;
-        need((u32)nbBits);
-        if ((int)(bits & (u32)(threshold - 1)) < max) { count = (int)(bits & (u32)(threshold - 1)); take((u32)nbBits - 1); }
-        else { count = (int)(bits & (u32)(2 * threshold - 1)); if (count >= threshold) count -= max; take((u32)nbBits); }
-        count--;
-        remaining -= count < 0 ? -count : count;
-        symbol++;
-        if (count == 0) { for (;;) { need(2); u32 const r = (u32)(bits & 3); take(2); symbol += r; if (r != 3) break; } }
-        while (remaining < threshold && threshold > 1) { nbBits--; threshold >>= 1; }
-    }
-    if (remaining != 1 || symbol > maxSymbol + 1) return 0;
-    size_t const bytes = (used + 7) / 8;
-    return bytes <= avail ? bytes : 0;
-}
-static size_t zb_dictParse(const u8* dict, size_t dictSize, size_t* contentOff, u32* dictID)
-{
-    *contentOff = 0; *dictID = 0;
-    if (dictSize < 8) return 0;
-    if (!(dict[0] == 0x37 && dict[1] == 0xA4 && dict[2] == 0x30 && dict[3] == 0xEC)) return 0;
-    size_t pos = 8;
-    *dictID = (u32)dict[4] | ((u32)dict[5] << 8) | ((u32)dict[6] << 16) | ((u32)dict[7] << 24);
-    if (pos >= dictSize) return ZB_ERR(ZB_error_dictionary_corrupted);
-    {   u32 const hb = dict[pos];
-        pos += hb >= 128 ? 1 + ((hb - 127) + 1) / 2 : 1 + (size_t)hb;
-        if (pos >= dictSize) return ZB_ERR(ZB_error_dictionary_corrupted); }
-    static const u32 maxSym[3] = { 31, 52, 35 }, maxLog[3] = { 8, 9, 9 };      /* OF, ML, LL */
-    for (int t = 0; t < 3; t++) {
-        size_t const n = zb_ncountBytes(dict + pos, dictSize - pos, maxSym[t], maxLog[t]);
-        if (n == 0) return ZB_ERR(ZB_error_dictionary_corrupted);
-        pos += n;
-    }
-    if (pos + 12 > dictSize) return ZB_ERR(ZB_error_dictionary_corrupted);
-    size_t const contentSize = dictSize - (pos + 12);
-    for (int r = 0; r < 3; r++) {
-        u32 const rep = (u32)dict[pos + 4 * r] | ((u32)dict[pos + 4 * r + 1] << 8) | ((u32)dict[pos + 4 * r + 2] << 16) | ((u32)dict[pos + 4 * r + 3] << 24);
-        if (rep == 0 || rep > contentSize) return ZB_ERR(ZB_error_dictionary_corrupted);
-    }
-    *contentOff = pos + 12;
-    return 0;
-}
-
+ * The CONTENT of either kind is the history of each frame's first block; a zstd-format dictionary's Huffman /
+ * FSE tables are that block's "previous" entropy state (treeless literals, set_repeat sequence tables) and
+ * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
 struct ZbGroup { ZbParams prm; u32 b0, b1; };
 struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; bool unsupported; };
 
 static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
-                    size_t dictSize, size_t dictTail, u32 dictID)
+                    size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
 {
     P.frames.resize(nbFrames);
     P.unsupported = false;
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
         ZbCParams const cp = zb_getCParams(level, fsz, dictSize);
-        ZbParams const prm = zb_makeParams(cp);
+        ZbParams prm = zb_makeParams(cp);
+        if (dictRep) { prm.startRep[0] = dictRep[0] <= dictTail ? dictRep[0] : 0u; prm.startRep[1] = dictRep[1] <= dictTail ? dictRep[1] : 0u; }
         if (dictSize && cp.strategy != 1) P.unsupported = true;           /* dictionaries: fast strategy only for now */
         size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
         ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)P.blocks.size();
@@ -316,16 +269,22 @@ static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, cu
                              size_t* effDictSize, size_t* dictTail, u32* dictID, const u8** d_dictEnd)
 {
     *effDictSize = 0; *dictTail = 0; *dictID = 0; *d_dictEnd = NULL;
+    c->dictEntropy.present = 0; c->d_deActive = NULL;
     if (!dict || dictSize < 8) return 0;
-    size_t contentOff = 0;
-    {   size_t const e = zb_dictParse((const u8*)dict, dictSize, &contentOff, dictID); if (zb_isErr(e)) return e; }
+    size_t const contentOff = zb_loadDictionary(&c->dictEntropy, (const u8*)dict, dictSize);
+    if (zb_isErr(contentOff)) return contentOff;
+    *dictID = c->dictEntropy.present ? c->dictEntropy.dictID : 0u;
     size_t const contentSize = dictSize - contentOff;
     size_t const tail = contentSize < ZB_PRIME_BYTES ? contentSize : ZB_PRIME_BYTES;
     *effDictSize = dictSize; *dictTail = tail;
-    if (!c->d_dict) CK(cudaMalloc(&c->d_dict, ZB_PRIME_BYTES + 64));
+    if (!c->d_dict) { CK(cudaMalloc(&c->d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(&c->d_de, sizeof(ZbDictEntropy))); }
     CK(cudaMemsetAsync(c->d_dict, 0, ZB_PRIME_BYTES + 64, stream));
     if (tail) CK(cudaMemcpyAsync(c->d_dict + 32, (const u8*)dict + contentOff + (contentSize - tail), tail, cudaMemcpyHostToDevice, stream));
     *d_dictEnd = c->d_dict + 32 + tail;
+    if (c->dictEntropy.present) {
+        CK(cudaMemcpyAsync(c->d_de, &c->dictEntropy, sizeof(ZbDictEntropy), cudaMemcpyHostToDevice, stream));
+        c->d_deActive = c->d_de;
+    }
     return 0;
 }
 
@@ -345,10 +304,10 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
                                    c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
                 *launches += (G.prm.strategy == 2) ? 3 : 2;
             } else if (phase == 1) {
-                CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, c->d_lits + s * ZB_LIT_STRIDE, c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
+                CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, c->d_deActive, c->d_lits + s * ZB_LIT_STRIDE, c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
                 *launches += 1;
             } else {
-                CK(zb_launch_sequences(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_seqs + s * ZB_SEQ_STRIDE, c->d_dist + s * ZB_BLOCK_MAX,
+                CK(zb_launch_sequences(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_deActive, c->d_seqs + s * ZB_SEQ_STRIDE, c->d_dist + s * ZB_BLOCK_MAX,
                                        c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
                 *launches += 1;
             }
@@ -366,7 +325,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID);
+    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
@@ -415,7 +374,7 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, c->waveStream[ZB_WAVE_SLOTS], &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID);
+    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
     u32 const nbWaves = (nbBlocks + ZB_WAVE_BLOCKS - 1u) / ZB_WAVE_BLOCKS;

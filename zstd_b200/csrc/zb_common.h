@@ -80,6 +80,28 @@ typedef struct {       /* produced on the device, one per block */
     u32 pad;
 } ZbBlockMeta;
 
+/* FSE compression table in our own layout (the reference's is common/fse.h:249) */
+typedef struct {
+    u32 tableLog;
+    u32 maxSymbolValue;
+    u16 nextState[512];
+    int deltaFindState[64];
+    u32 deltaNbBits[64];
+} ZbdFseCTable;
+
+/* entropy state a zstd-format dictionary installs as the "previous block" of a frame's first block
+ * (ZSTD_loadCEntropy, /root/reference/lib/compress/zstd_compress.c:4987-5076); built on the host (zb_dict.cu) */
+typedef struct {
+    u32 present;
+    u32 hufRepeat;             /* HUF_repeat: 0 none, 1 check, 2 valid */
+    u32 hufMaxSymbol;
+    u32 fseRepeat[3];          /* FSE_repeat per stream: 0 = LL, 1 = OF, 2 = ML */
+    u32 rep[3];
+    u32 dictID;
+    u32 hufEnc[256];           /* code | nbBits << 16 */
+    ZbdFseCTable fse[3];
+} ZbDictEntropy;
+
 typedef struct {
     u32 strategy;      /* 1 = fast, 2 = dfast */
     u32 mls;           /* bytes hashed by the (short) table: 4..8 */
@@ -91,6 +113,7 @@ typedef struct {
     u32 insPeriod;     /* positions with (framePos % insPeriod) < 2 enter the table */
     u32 insPeriodLong; /* dfast: same for the 8-byte-hash table */
     u32 longPass;      /* set by the launcher for the candidate walk of the long table (uses insPhaseLong) */
+    u32 startRep[2];   /* repcodes a ZB_FLAG_DICT block starts with (zstd-format dictionary), 0 = invalid */
 } ZbParams;
 
 #endif

@@ -30,13 +30,7 @@ __device__ __forceinline__ u32 zbd_bw_close(ZbdBitW* w)              /* common/b
 }
 
 /* ------------------------------------------------------------------ FSE */
-struct ZbdFseCTable {                 /* our layout; the reference's is common/fse.h:249 */
-    u32 tableLog;
-    u32 maxSymbolValue;
-    u16 nextState[512];
-    int deltaFindState[64];
-    u32 deltaNbBits[64];
-};
+/* ZbdFseCTable: zb_common.h */
 
 /* compress/fse_compress.c:347-374 */
 __device__ __forceinline__ u32 zbd_fse_minTableLog(u32 srcSize, u32 maxSymbolValue)

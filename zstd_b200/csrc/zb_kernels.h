@@ -16,12 +16,16 @@ extern "C" {
 cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                             u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
-/* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block. */
-cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+/* host: parse a dictionary (zb_dict.cu).  Returns the content offset, 0 for raw content, or an error code */
+size_t zb_loadDictionary(ZbDictEntropy* de, const u8* dict, size_t dictSize);
+
+/* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block.
+ * d_de (may be NULL): dictionary entropy state used by ZB_FLAG_DICT blocks. */
+cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
                                const u8* d_lits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
 
 /* K3: sequences section (codes, histograms, FSE tables, tANS bit-stream) + block-type decision. */
-cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
                                 const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
 
 /* K4: stitch — per-block output sizes -> exclusive scan -> frame/block headers + payload copy, for

@@ -90,7 +90,7 @@ __device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ li
 }
 
 __global__ void __launch_bounds__(LIT_THREADS)
-zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
+zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDictEntropy* __restrict__ de,
                    const u8* __restrict__ lits, u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
     __shared__ u32 whist[8][256];
@@ -100,7 +100,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
     __shared__ __align__(16) u8 hdr[144];
     __shared__ u32 red[16];
     __shared__ u32 chunkBits[LIT_THREADS];
-    __shared__ u32 sh_largest, sh_maxSym, sh_mode, sh_hSize;
+    __shared__ u32 sh_largest, sh_maxSym, sh_mode, sh_hSize, sh_usePrev;
     __shared__ u32 sh_streamSize[4];
 
     u32 const tid = threadIdx.x;
@@ -112,10 +112,18 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
     u8* const out = body + (size_t)b * ZB_BODY_STRIDE;
     enum { MODE_RAW = 0, MODE_RLE = 1, MODE_HUF = 2 };
 
-    /* ---------------- decisions (zstd_compress_literals.c:129-191, huf_compress.c:1359-1420) ---------------- */
+    /* ---------------- decisions (zstd_compress_literals.c:129-191, huf_compress.c:1359-1420) ----------------
+     * `repeat` is the HUF_repeat mode of the previous block's table: only a frame's first block behind a
+     * zstd-format dictionary has one (ZSTD_loadCEntropy, zstd_compress.c:4997-5005); 0 none, 1 check, 2 valid. */
+    u32 repeat = (de != nullptr && (blocks[b].flags & ZB_FLAG_DICT) && de->present) ? de->hufRepeat : 0u;
+    bool const preferRepeat = (n <= 1024u);                      /* strategy < lazy, zstd_compress_literals.c:165 */
+    u32 const lhSize = 3u + (n >= 1024u) + (n >= 16384u);
+    u32 const nbStreams = (n < 256u || (repeat == 2u && lhSize == 3u)) ? 1u : 4u;     /* :142, :171 */
     u32 mode = MODE_HUF;
-    if (prm.litDisabled || n < 64u) mode = MODE_RAW;             /* ZSTD_minLiteralsToCompress: 8<<3 for fast/dfast */
-    if (mode == MODE_HUF) {
+    bool usePrev = false;
+    if (prm.litDisabled || n < (repeat == 2u ? 6u : 64u)) mode = MODE_RAW;   /* ZSTD_minLiteralsToCompress :114-127 */
+    if (mode == MODE_HUF && preferRepeat && repeat == 2u) usePrev = true;     /* huf_compress.c:1359-1363 : no statistics at all */
+    if (mode == MODE_HUF && !usePrev) {
         bool const suspect = (m.nbSeq == 0) || (n / m.nbSeq >= 20u);    /* zstd_compress.c:2915-2917 */
         if (suspect && n >= 4096u * 10u) {                               /* huf_compress.c:1367-1379 */
             u32 l1, l2;
@@ -130,33 +138,53 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
             if (l1 + l2 <= ((2u * 4096u) >> 7) + 4u) mode = MODE_RAW;
         }
     }
-    if (mode == MODE_HUF) {
+    if (mode == MODE_HUF && !usePrev) {
         zb_hist256(lit, n, whist, count);
         zb_hist_stats(count, red, &sh_largest, &sh_maxSym);
         u32 const largest = sh_largest;
         if (largest == n) mode = MODE_RLE;
         else if (largest <= (n >> 7) + 4u) mode = MODE_RAW;
     }
-    u32 const nbStreams = (n < 256u) ? 1u : 4u;
-    u32 const lhSize = 3u + (n >= 1024u) + (n >= 16384u);
-    if (mode == MODE_HUF) {
+    if (mode == MODE_HUF && !usePrev && repeat == 1u) {                     /* HUF_validateCTable, huf_compress.c:804, :1389-1393 */
+        int const bad = (tid <= sh_maxSym) && count[tid] != 0u && (de->hufEnc[tid] >> 16) == 0u;
+        if (__syncthreads_or(bad) || de->hufMaxSymbol < sh_maxSym) repeat = 0u;
+    }
+    if (mode == MODE_HUF && !usePrev && preferRepeat && repeat != 0u) usePrev = true;      /* :1395-1399 */
+    if (mode == MODE_HUF && !usePrev) {
         if (tid == 0) {
             u32 md = MODE_HUF, hSize = 0;
             u32 const maxSym = sh_maxSym;
             u32 huffLog = zbd_fse_optimalTableLog(11, n, maxSym, 1);        /* huf_compress.c:1284-1287 */
             u32 const maxBits = zbd_huf_build(&wk, count, maxSym, huffLog, enc);
+            u32 prev = 0;
             if (maxBits == ZBD_ERR) md = MODE_RAW;
             else {
                 hSize = zbd_huf_writeHeader(&wk, hdr, enc, maxSym, maxBits);
-                if (hSize == ZBD_ERR || hSize + 12u >= n) md = MODE_RAW;     /* huf_compress.c:1426 */
+                if (hSize == ZBD_ERR) md = MODE_RAW;
+                else {
+                    if (repeat != 0u) {                                        /* :1415-1422 : is the old table cheaper? */
+                        u32 oldBits = 0, newBits = 0;
+                        for (u32 sy = 0; sy <= maxSym; sy++) { oldBits += (de->hufEnc[sy] >> 16) * count[sy]; newBits += (enc[sy] >> 16) * count[sy]; }
+                        if ((oldBits >> 3) <= hSize + (newBits >> 3) || hSize + 12u >= n) prev = 1;
+                    }
+                    if (!prev && hSize + 12u >= n) md = MODE_RAW;              /* :1426 */
+                }
             }
-            sh_mode = md; sh_hSize = hSize;
+            sh_mode = md; sh_hSize = hSize; sh_usePrev = prev;
         }
         __syncthreads();
         mode = sh_mode;
+        usePrev = sh_usePrev != 0u;
+    }
+    if (mode == MODE_HUF && usePrev) {                                         /* treeless: encode with the dictionary's table */
+        __syncthreads();
+        enc[tid] = de->hufEnc[tid];
+        if (tid == 0) sh_hSize = 0;
+        __syncthreads();
     }
 
     /* ---------------- stream geometry + bit counts ---------------- */
+    u32 const hType = usePrev ? 3u : 2u;              /* set_repeat (treeless) : set_compressed */
     u32 const T = LIT_THREADS / nbStreams;           /* threads per stream */
     u32 const s = tid / T, j = tid % T;
     u32 const seg = (n + 3u) / 4u;                   /* huf_compress.c:1172 */
@@ -184,6 +212,11 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
         if (nbStreams == 4u && tooBig) mode = MODE_RAW;                       /* huf_compress.c:1185 */
         else if (total >= n - 1u) mode = MODE_RAW;                            /* huf_compress.c:1232 */
         else if (total >= n - ((n >> 6) + 2u)) mode = MODE_RAW;               /* zstd_compress_literals.c:187-191 */
+        else if (total == 1u) {                                               /* :193-205 : a 1-byte result is read as "single symbol" */
+            int diff = 0;
+            if (n < 8u) for (u32 i = tid; i < n; i += LIT_THREADS) diff |= (lit[i] != lit[0]);
+            if (!__syncthreads_or(diff)) mode = MODE_RLE;
+        }
     }
 
     /* ---------------- emit ---------------- */
@@ -218,11 +251,11 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
     __syncthreads();
     if (tid == 0) {                                                           /* zstd_compress_literals.c:209-232 */
         u32 const cLitSize = total;
-        if (lhSize == 3) { u32 const lhc = 2u + ((nbStreams == 4u ? 1u : 0u) << 2) + (n << 4) + (cLitSize << 14);
+        if (lhSize == 3) { u32 const lhc = hType + ((nbStreams == 4u ? 1u : 0u) << 2) + (n << 4) + (cLitSize << 14);
                            out[0] = (u8)lhc; out[1] = (u8)(lhc >> 8); out[2] = (u8)(lhc >> 16); }
-        else if (lhSize == 4) { u32 const lhc = 2u + (2u << 2) + (n << 4) + (cLitSize << 18);
+        else if (lhSize == 4) { u32 const lhc = hType + (2u << 2) + (n << 4) + (cLitSize << 18);
                            out[0] = (u8)lhc; out[1] = (u8)(lhc >> 8); out[2] = (u8)(lhc >> 16); out[3] = (u8)(lhc >> 24); }
-        else { u32 const lhc = 2u + (3u << 2) + (n << 4) + (cLitSize << 22);
+        else { u32 const lhc = hType + (3u << 2) + (n << 4) + (cLitSize << 22);
                            out[0] = (u8)lhc; out[1] = (u8)(lhc >> 8); out[2] = (u8)(lhc >> 16); out[3] = (u8)(lhc >> 24);
                            out[4] = (u8)(cLitSize >> 10); }
         if (nbStreams == 4u) {
@@ -243,10 +276,10 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm,
     }
 }
 
-extern "C" cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+extern "C" cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
                                           const u8* d_lits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_literals_kernel<<<nbBlocks, LIT_THREADS, 0, stream>>>(d_blocks, *prm, d_lits, d_body, d_meta);
+    zb_literals_kernel<<<nbBlocks, LIT_THREADS, 0, stream>>>(d_blocks, *prm, d_de, d_lits, d_body, d_meta);
     return cudaGetLastError();
 }

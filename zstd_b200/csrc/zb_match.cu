@@ -315,6 +315,7 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
 
     u32 ip = bs, anchor = bs, searchStart = bs;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
+    if (DICT && (bd.flags & ZB_FLAG_DICT)) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
     u32 pf = bs;                                             /* input and dist[] below this position are on their way to L2 */
 
     while (ip + 8u <= be) {

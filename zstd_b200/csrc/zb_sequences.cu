@@ -69,15 +69,16 @@ __device__ __forceinline__ ZbdSeq zbd_unpack(u64 q)
     return s;
 }
 
-enum { set_basic = 0, set_rle = 1, set_compressed = 2 };
+enum { set_basic = 0, set_rle = 1, set_compressed = 2, set_repeat = 3 };
 
 /* zstd_compress_sequences.c:157-240, branch strategy < ZSTD_lazy with repeatMode == none */
-__device__ __forceinline__ u32 zbd_selectEncodingType(u32 mostFrequent, u32 nbSeq, u32 defaultNormLog, bool defaultAllowed, u32 strategy)
+__device__ __forceinline__ u32 zbd_selectEncodingType(u32 mostFrequent, u32 nbSeq, u32 defaultNormLog, bool defaultAllowed, u32 strategy, u32 prevRepeat)
 {
     if (mostFrequent == nbSeq) return (defaultAllowed && nbSeq <= 2u) ? set_basic : set_rle;
     if (defaultAllowed) {
         u32 const mult = 10u - strategy;
         u32 const dynamicFse_nbSeq_min = ((1u << defaultNormLog) * mult) >> 3;
+        if (prevRepeat == 2u && nbSeq < 1000u) return set_repeat;             /* :187-191 : the dictionary's table */
         if (nbSeq < dynamicFse_nbSeq_min || mostFrequent < (nbSeq >> (defaultNormLog - 1u))) return set_basic;
     }
     return set_compressed;
@@ -95,7 +96,7 @@ struct ZbdStreamWork {
 };
 
 __global__ void __launch_bounds__(SEQ_THREADS)
-zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm,
+zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDictEntropy* __restrict__ de,
                     const u64* __restrict__ seqs, u16* __restrict__ stateBits,
                     u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
@@ -146,11 +147,16 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             u32 mostFrequent = 0; for (u32 s = 0; s <= max; s++) mostFrequent = w->count[s] > mostFrequent ? w->count[s] : mostFrequent;
             u32 const defLog = st == 1 ? 5u : 6u;
             bool const defAllowed = st == 1 ? (max <= DefaultMaxOff) : true;
-            u32 const type = zbd_selectEncodingType(mostFrequent, nbSeq, defLog, defAllowed, prm.strategy);
+            u32 const prevRepeat = (de != nullptr && (bd.flags & ZB_FLAG_DICT) && de->present) ? de->fseRepeat[st] : 0u;
+            u32 const type = zbd_selectEncodingType(mostFrequent, nbSeq, defLog, defAllowed, prm.strategy, prevRepeat);
             ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
             u32 const lastCode = st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc);
             w->type = type; w->err = 0; w->ncSize = 0;
-            if (type == set_rle) {                                   /* zstd_compress_sequences.c:254-259 */
+            if (type == set_repeat) {                                /* zstd_compress_sequences.c:260-262 : no table description */
+                const u32* from = reinterpret_cast<const u32*>(&de->fse[st]);
+                u32* to = reinterpret_cast<u32*>(&ct[st]);
+                for (u32 i = 0; i < sizeof(ZbdFseCTable) / 4u; i++) to[i] = from[i];
+            } else if (type == set_rle) {                            /* zstd_compress_sequences.c:254-259 */
                 ZbdSeq const first = zbd_unpack(myseq[0]);
                 u32 const sym = st == 0 ? first.llc : (st == 1 ? first.ofc : first.mlc);
                 zbd_fse_buildCTable_rle(&ct[st], max);
@@ -290,10 +296,10 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     }
 }
 
-extern "C" cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+extern "C" cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
                                            const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_sequences_kernel<<<nbBlocks, SEQ_THREADS, 0, stream>>>(d_src, d_blocks, *prm, d_seqs, d_stateBits, d_body, d_meta);
+    zb_sequences_kernel<<<nbBlocks, SEQ_THREADS, 0, stream>>>(d_src, d_blocks, *prm, d_de, d_seqs, d_stateBits, d_body, d_meta);
     return cudaGetLastError();
 }
