@@ -102,6 +102,8 @@ struct ZSTD_CCtx_s {
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
     u8* d_dict;                    /* dictionary content tail (<= 64 KiB), 32 bytes of padding on both sides */
+    u8* d_image;                   /* tables primed from the dictionary tail, one per parameter group (ZB_MAX_IMAGES) */
+    ZbBlock* d_dictBlock;          /* pseudo block descriptors for zb_launch_dict_image */
     ZbDictEntropy dictEntropy;     /* host copy of the current call's dictionary entropy state */
     ZbDictEntropy* d_de;           /* device copy */
     const ZbDictEntropy* d_deActive; /* d_de when the current call's dictionary is zstd-format, else NULL */
@@ -162,7 +164,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
-        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de);
+        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de); cudaFree(c->d_image); cudaFree(c->d_dictBlock);
         for (int s = 0; s < 8; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
         cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
@@ -225,7 +227,9 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
  * FSE tables are that block's "previous" entropy state (treeless literals, set_repeat sequence tables) and
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
-struct ZbGroup { ZbParams prm; u32 b0, b1; };
+struct ZbGroup { ZbParams prm; u32 b0, b1; bool imageReady; };
+#define ZB_IMAGE_BYTES (3u << 14)      /* largest table: 2^14 positions + tags */
+#define ZB_MAX_IMAGES 4
 struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; bool unsupported; };
 
 static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
@@ -259,7 +263,7 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
         } while (pos < fsz);
         fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
         P.frames[f] = fr;
-        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); P.groups.push_back(g); }
+        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.imageReady = false; P.groups.push_back(g); }
         else P.groups.back().b1 = (u32)P.blocks.size();
     }
 }
@@ -277,13 +281,35 @@ static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, cu
     size_t const contentSize = dictSize - contentOff;
     size_t const tail = contentSize < ZB_PRIME_BYTES ? contentSize : ZB_PRIME_BYTES;
     *effDictSize = dictSize; *dictTail = tail;
-    if (!c->d_dict) { CK(cudaMalloc(&c->d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(&c->d_de, sizeof(ZbDictEntropy))); }
+    if (!c->d_dict) { CK(cudaMalloc(&c->d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(&c->d_de, sizeof(ZbDictEntropy)));
+                      CK(cudaMalloc(&c->d_image, (size_t)ZB_IMAGE_BYTES * ZB_MAX_IMAGES)); CK(cudaMalloc(&c->d_dictBlock, ZB_MAX_IMAGES * sizeof(ZbBlock))); }
     CK(cudaMemsetAsync(c->d_dict, 0, ZB_PRIME_BYTES + 64, stream));
     if (tail) CK(cudaMemcpyAsync(c->d_dict + 32, (const u8*)dict + contentOff + (contentSize - tail), tail, cudaMemcpyHostToDevice, stream));
     *d_dictEnd = c->d_dict + 32 + tail;
     if (c->dictEntropy.present) {
         CK(cudaMemcpyAsync(c->d_de, &c->dictEntropy, sizeof(ZbDictEntropy), cudaMemcpyHostToDevice, stream));
         c->d_deActive = c->d_de;
+    }
+    return 0;
+}
+
+/* One table image per parameter group (many small frames share one dictionary: priming its tail once
+ * instead of once per frame is what the reference's CDict does on the CPU, zstd_compress.c:5477). */
+static size_t zb_buildDictImages(ZSTD_CCtx* c, ZbPlan& P, const u8* d_dictEnd, size_t dictTail, cudaStream_t stream)
+{
+    if (!d_dictEnd || dictTail < 8 || P.groups.size() > ZB_MAX_IMAGES) return 0;
+    std::vector<ZbBlock> pb(P.groups.size());
+    for (size_t g = 0; g < P.groups.size(); g++) {
+        ZbParams const& prm = P.groups[g].prm;
+        ZbBlock b; memset(&b, 0, sizeof(b));
+        b.histLen = (u32)dictTail; b.size = 0; b.flags = ZB_FLAG_DICT;
+        b.insPhase = (u32)((prm.insPeriod - dictTail % prm.insPeriod) % prm.insPeriod);
+        pb[g] = b;
+    }
+    CK(cudaMemcpyAsync(c->d_dictBlock, pb.data(), pb.size() * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
+    for (size_t g = 0; g < P.groups.size(); g++) {
+        CK(zb_launch_dict_image(d_dictEnd, c->d_dictBlock + g, &P.groups[g].prm, c->d_image + g * ZB_IMAGE_BYTES, stream));
+        P.groups[g].imageReady = true;
     }
     return 0;
 }
@@ -299,7 +325,7 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
             if (lo >= hi) continue;
             size_t const s = slot0 + (lo - b0);
             if (phase == 0) {
-                CK(zb_launch_match(d_src, d_dictEnd, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
+                CK(zb_launch_match(d_src, d_dictEnd, (d_dictEnd && G.imageReady) ? c->d_image + g * ZB_IMAGE_BYTES : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
                                    G.prm.strategy == 2 ? c->d_dist2 + s * ZB_BLOCK_MAX : (u16*)0, c->d_seqs + s * ZB_SEQ_STRIDE,
                                    c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
                 *launches += (G.prm.strategy == 2) ? 3 : 2;
@@ -335,6 +361,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
     unsigned launches = 0;
+    if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
     {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
     CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
@@ -403,6 +430,7 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
     CK(cudaEventRecord(c->evStart, sCopy));
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, sCopy));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, sCopy));
+    if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, sCopy); if (zb_isErr(e)) return e; }
     for (u32 w = 0; w < nbWaves && !err; w++) {
         u32 const b0 = w * ZB_WAVE_BLOCKS, b1 = (b0 + ZB_WAVE_BLOCKS < nbBlocks) ? b0 + ZB_WAVE_BLOCKS : nbBlocks;
         /* input bytes of the wave (frames are laid out in offset order; history was uploaded by earlier waves) */

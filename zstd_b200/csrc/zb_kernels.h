@@ -12,8 +12,10 @@ extern "C" {
  * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records);
  * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates).
  * d_dictEnd: one past the dictionary content in device memory (NULL = no dictionary); blocks flagged
- * ZB_FLAG_DICT take their histLen bytes of history from in front of it. */
-cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+ * ZB_FLAG_DICT take their histLen bytes of history from in front of it.  d_image (may be NULL): table
+ * already primed from that dictionary tail by zb_launch_dict_image (same ZbParams), 3 << hashLog bytes. */
+cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream);
+cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                             u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
 /* host: parse a dictionary (zb_dict.cu).  Returns the content offset, 0 for raw content, or an error code */

@@ -81,13 +81,13 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
  * volatile, never __restrict__. */
 template <bool INTERIOR>
 __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8* tags, const u32* hh,
-                                               u32 q0, u32 o0, u32 nPos, u32 bs, u32 lane,
+                                               u32 q0, u32 o0, u32 pmin, u32 nPos, u32 bs, u32 lane,
                                                u32& ph, u32 inc, u32 period, u16* __restrict__ mydist)
 {
 #pragma unroll
     for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
         u32 const q = q0 + 32u * j + lane;
-        bool const act = INTERIOR ? true : ((q >= o0) && (q - o0 < nPos));
+        bool const act = INTERIOR ? true : ((q >= o0 + pmin) && (q - o0 < nPos));
         u32 const p = q - o0;
         u32 const h = act ? (hh[j] >> 8) : 0u;
         u32 const tag = hh[j] & 0xFFu;
@@ -140,16 +140,24 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
 
 template <int MLS>
 __global__ void __launch_bounds__(32)
-zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist)
+zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist,
+               const u8* __restrict__ imageIn, u8* __restrict__ imageOut)
 {
     __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
     extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog positions, followed by 2^hashLog tags */
     u32 const lane = threadIdx.x;
-    ZbBlock const bd = blocks[blockIdx.x];
-    if (bd.size < 7u) return;                                    /* zstd_compress.c:3216 : block goes out raw */
+    ZbBlock bd = blocks[blockIdx.x];
+    /* imageOut != NULL: this launch only walks the dictionary tail (positions whose 8 hashed bytes lie inside
+     * the dictionary) and saves the table; imageIn != NULL: dictionary blocks start from that saved table and
+     * walk only the last 7 dictionary positions (their hashes reach into the frame) and the block itself. */
+    bool const buildImage = imageOut != nullptr;
+    if (buildImage) bd.size = 0;
+    if (!buildImage && bd.size < 7u) return;                      /* zstd_compress.c:3216 : block goes out raw */
     u16* const mydist = dist + (size_t)blockIdx.x * ZB_BLOCK_MAX;
-    const u8* const base = src + bd.srcOff - bd.histLen;          /* rel position 0 = oldest visible byte */
+    const u8* const base = buildImage ? dictEnd - bd.histLen : src + bd.srcOff - bd.histLen;   /* rel position 0 = oldest visible byte */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+    bool const fromImage = imageIn != nullptr && (bd.flags & ZB_FLAG_DICT) && bd.histLen >= 8u;
+    u32 const pmin = fromImage ? bd.histLen - 7u : 0u;            /* history positions below pmin are already in the image */
     u32 const hlog = prm.hashLog, period = prm.insPeriod;
     u8* const tags = reinterpret_cast<u8*>(table + ((size_t)1 << hlog));   /* 8 further hash bits per bucket */
     volatile u16* const vtable = table;     /* lanes communicate through the table inside a step: volatile accesses */
@@ -178,26 +186,28 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
 
     {   uint4* t4 = reinterpret_cast<uint4*>(table);
         u32 const n4 = (3u << hlog) / 16u;
-        for (u32 i = lane; i < n4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        const uint4* im = reinterpret_cast<const uint4*>(imageIn);
+        for (u32 i = lane; i < n4; i += 32) t4[i] = fromImage ? __ldg(im + i) : make_uint4(0, 0, 0, 0);
     }
-    /* prologue: chunks 0 .. STAGES-2 in flight */
+    u32 const c0 = (o0 + pmin) / CAND_CHUNK;                      /* first chunk with a position to insert */
+    /* prologue: chunks c0 .. c0+STAGES-2 in flight */
 #pragma unroll
-    for (u32 c = 0; c < CAND_STAGES - 1u; c++) {
-        u32 const q = c * CAND_CHUNK + 16u * lane;
-        if (c < nChunks && q < qEnd) stage(q);
+    for (u32 k = 0; k < CAND_STAGES - 1u; k++) {
+        u32 const q = (c0 + k) * CAND_CHUNK + 16u * lane;
+        if (c0 + k < nChunks && q < qEnd) stage(q);
         __pipeline_commit();
     }
     __syncwarp();
 
     u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
     u32 const phase0 = (period - (o0 % period) + (prm.longPass ? bd.insPhaseLong : bd.insPhase)) % period;   /* pattern phase of q = 0 */
-    u32 ph = (lane + phase0) % period;                            /* pattern phase of this lane's q in the current step */
+    u32 ph = (c0 * CAND_CHUNK + lane + phase0) % period;          /* pattern phase of this lane's q in the current step */
     u32 const inc = 32u % period;
     /* chunks that lie entirely inside the history only have to leave their inserted positions in the
      * table (nobody asks for their candidates): they are walked pair-wise, 16 pairs = 16*period
      * positions per step, without any look-up */
     u32 const nPrimeChunks = (o0 + bs) / CAND_CHUNK;
-    for (u32 c = 0; c < nChunks; c++) {
+    for (u32 c = c0; c < nChunks; c++) {
         {   u32 const cn = c + CAND_STAGES - 1u;                  /* refill the slot consumed in the previous iteration */
             u32 const q = cn * CAND_CHUNK + 16u * lane;
             if (cn < nChunks && q < qEnd) stage(q);
@@ -213,7 +223,7 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
             u32 const first = cq + (r ? period - r : 0u);
             /* a pair that straddles the chunk start has its second element here: it precedes every
              * pair of this chunk, so it is written first */
-            if (((cq + phase0) % period) == 1u && lane == 0u && cq >= o0 && cq - o0 < nPos) {
+            if (((cq + phase0) % period) == 1u && lane == 0u && cq >= o0 + pmin && cq - o0 < nPos) {
                 u32 const q = cq, p = q - o0;
                 u32 const w = (q & ~3u) & (CAND_RING - 1u);
                 u32 const sh = (q & 3u) * 8u;
@@ -227,7 +237,7 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
             __syncwarp();
             for (u32 g0 = first; g0 < cq + CAND_CHUNK; g0 += 16u * period) {
                 u32 const q = g0 + (lane >> 1) * period + (lane & 1u);
-                bool const act = (q >= o0) && (q < cq + CAND_CHUNK) && (q - o0 < nPos);
+                bool const act = (q >= o0 + pmin) && (q < cq + CAND_CHUNK) && (q - o0 < nPos);
                 u32 const p = q - o0;
                 u32 const w = (q & ~3u) & (CAND_RING - 1u);
                 u32 const sh = (q & 3u) * 8u;
@@ -271,9 +281,16 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
         /* phase B: the table walk proper, one step after the other */
         {   u32 const q0 = c * CAND_CHUNK;
             bool const interior = (q0 >= o0 + bs) && (q0 + CAND_CHUNK <= o0 + nPos);
-            if (interior) zb_cand_walk16<true>(table, tags, hh, q0, o0, nPos, bs, lane, ph, inc, period, mydist);
-            else          zb_cand_walk16<false>(table, tags, hh, q0, o0, nPos, bs, lane, ph, inc, period, mydist);
+            if (interior) zb_cand_walk16<true>(table, tags, hh, q0, o0, pmin, nPos, bs, lane, ph, inc, period, mydist);
+            else          zb_cand_walk16<false>(table, tags, hh, q0, o0, pmin, nPos, bs, lane, ph, inc, period, mydist);
         }
+    }
+    if (buildImage) {                                             /* save the primed table (positions + tags) */
+        __syncwarp();
+        const uint4* t4 = reinterpret_cast<const uint4*>(table);
+        uint4* im = reinterpret_cast<uint4*>(imageOut);
+        for (u32 i = lane; i < (3u << hlog) / 16u; i += 32) im[i] = t4[i];
+        return;
     }
     for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
 }
@@ -529,7 +546,8 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     }
 }
 
-static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist, cudaStream_t stream)
+static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist,
+                           const u8* d_imageIn, u8* d_imageOut, cudaStream_t stream)
 {
     size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
     static bool optin = false;
@@ -542,15 +560,22 @@ static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* 
         optin = true;
     }
     switch (prm.mls) {
-    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
-    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
-    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
-    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
-    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist); break;
+    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
+    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
+    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
+    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
+    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
     }
 }
 
-extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+/* one-warp launch that primes a table from the dictionary tail and stores it (positions + tags) in d_image */
+extern "C" cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream)
+{
+    zb_launch_cand(nullptr, d_dictEnd, d_dictBlock, 1, *prm, nullptr, nullptr, d_image, stream);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
                                        u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
@@ -558,12 +583,12 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
     if (prm->strategy == 2) {
         /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
         ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, d_dist, stream);
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist2, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, d_dist, nullptr, nullptr, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist2, nullptr, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
         zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_dist2, d_seqs, d_lits, d_meta);
     } else {
-        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, stream);
+        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, d_image, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
         if (d_dictEnd) zb_parse_kernel<true><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
         else           zb_parse_kernel<false><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
