@@ -94,6 +94,7 @@ struct ZSTD_CCtx_s {
     cudaStream_t stream;
     /* per-block workspace */
     size_t capBlocks, capFrames, capHeavy, capWaves;
+    u32 devWaveBlocks;             /* device-memory calls: blocks per wave (0 = always one wave) */
     cudaStream_t waveStream[8];
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
@@ -129,6 +130,8 @@ extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
     ZSTD_CCtx* c = (ZSTD_CCtx*)calloc(1, sizeof(ZSTD_CCtx));
     if (!c) return NULL;
     c->device = -1;
+    {   const char* s = getenv("ZSTDB200_SERIAL"); const char* w = getenv("ZSTDB200_WAVE_BLOCKS");
+        c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 2048u); }
     return c;
 }
 
@@ -390,13 +393,14 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
 /* ------------------------------------------------------------------ host pointers: pipelined waves
  * H2D copy of wave w+1 | kernels of waves w, w-1, ... (one stream + workspace slot each) | D2H of finished waves.
  * A block needs ~ms of latency end to end (one warp walks it), so several waves are kept in flight. */
-#define ZB_WAVE_BLOCKS 768u          /* 96 MiB of input per wave */
+#define ZB_HOST_WAVE_BLOCKS 768u     /* 96 MiB of input per wave */
 #define ZB_WAVE_SLOTS  4u
 
-static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, const u8* src,
-                                    const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
-                                    const void* dict, size_t dictSize, size_t* cSizes, int level)
+static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, const u8* src,
+                                     const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
+                                     const void* dict, size_t dictSize, size_t* cSizes, int level, bool deviceMemory)
 {
+    u32 const ZB_WAVE_BLOCKS = deviceMemory ? c->devWaveBlocks : ZB_HOST_WAVE_BLOCKS;
     for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, c->waveStream[ZB_WAVE_SLOTS], &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
@@ -411,12 +415,17 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
         if (frameOffsets[f] + frameSizes[f] > inEnd) inEnd = frameOffsets[f] + frameSizes[f];
         bound += ZSTD_compressBound(frameSizes[f]) + 32;
     }
-    size_t const outCap = dstCapacity < bound ? dstCapacity : bound;
+    size_t const outCap = deviceMemory ? dstCapacity : (dstCapacity < bound ? dstCapacity : bound);
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves); if (zb_isErr(e)) return e;
         bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
         e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks), d2); if (zb_isErr(e)) return e; }
-    if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
-    if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
+    u8* d_in; u8* d_out;
+    if (deviceMemory) { d_in = (u8*)src; d_out = dst; }
+    else {
+        if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
+        if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
+        d_in = c->d_in; d_out = c->d_out;
+    }
     for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));
     cudaStream_t const sCopy = c->waveStream[ZB_WAVE_SLOTS], sD2H = c->waveStream[ZB_WAVE_SLOTS + 1u];
     std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evDone(nbWaves);
@@ -436,16 +445,16 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
         /* input bytes of the wave (frames are laid out in offset order; history was uploaded by earlier waves) */
         u64 lo = ~0ull, hi = 0;
         for (u32 b = b0; b < b1; b++) { u64 const a = P.blocks[b].srcOff, e = a + P.blocks[b].size; if (a < lo) lo = a; if (e > hi) hi = e; }
-        if (hi > lo) CK(cudaMemcpyAsync(c->d_in + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, sCopy));
+        if (hi > lo && !deviceMemory) CK(cudaMemcpyAsync(d_in + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, sCopy));
         CK(cudaEventRecord(evH2D[w], sCopy));
         cudaStream_t const st = c->waveStream[w % slots];
         CK(cudaStreamWaitEvent(st, evH2D[w], 0));
-        err = zb_runBlocks(c, P, c->d_in, d_dictEnd, b0, b1, (size_t)(w % slots) * ZB_WAVE_BLOCKS, st, false, &launches);
+        err = zb_runBlocks(c, P, d_in, d_dictEnd, b0, b1, (size_t)(w % slots) * ZB_WAVE_BLOCKS, st, false, &launches);
         if (err) break;
         if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
         size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
-        CK(zb_launch_stitch(c->d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
-                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, c->d_out, outCap, st));
+        CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
+                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, d_out, outCap, st));
         launches += 2;
         CK(cudaEventRecord(evStitch[w], st));
         CK(cudaMemcpyAsync(c->h_totals + w, c->d_totals + w, sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -456,7 +465,7 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
     for (u32 w = 0; w < nbWaves && !err; w++) {
         CK(cudaEventSynchronize(evDone[w]));
         total = c->h_totals[w];
-        if (total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, c->d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
+        if (!deviceMemory && total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
         if (total <= outCap) prev = total;
     }
     if (!err && cSizes) {
@@ -474,7 +483,7 @@ static size_t zb_compressFramesHost(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, c
     if (err) return err;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; c->stats.kernel_ms = ms; }
     c->stats.launches = launches; c->stats.nbBlocks = nbBlocks;
-    c->stats.h2d_bytes = inEnd; c->stats.d2h_bytes = (size_t)total;
+    if (!deviceMemory) { c->stats.h2d_bytes = inEnd; c->stats.d2h_bytes = (size_t)total; }
     if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
     return (size_t)total;
 }
@@ -489,12 +498,19 @@ extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCap
     {   size_t const e = zb_ctxInit(c); if (zb_isErr(e)) return e; }
     memset(&c->stats, 0, sizeof(c->stats));
     if (deviceMemory) {
+        /* device-resident input: large calls are cut into waves on several streams, so that the shared-memory
+         * bound candidate walk of one wave overlaps the register-only parse / entropy kernels of another;
+         * ZSTDB200_SERIAL=1 (or a caller-supplied stream) keeps one wave on one stream — the mode whose
+         * per-kernel event times are meaningful */
+        size_t nb = 0; for (size_t f = 0; f < nbFrames; f++) nb += (frameSizes[f] + ZB_BLOCK_MAX - 1) / ZB_BLOCK_MAX;
+        if (!streamv && c->devWaveBlocks && nb >= 2u * c->devWaveBlocks)
+            return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, true);
         cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
         size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
         c->stats.total_ms = c->stats.kernel_ms;
         return r;
     }
-    return zb_compressFramesHost(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level);
+    return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, false);
 }
 
 extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity,
