@@ -1,0 +1,23 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck): every kernel, every mode, tiny inputs."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch, zref, zstd_b200
+ctx = zstd_b200.ZSTD_CCtx()
+cases = [b"", b"abcdefg", zref.synthetic(1000, 1), zref.synthetic(70_000, 2), zref.synthetic(300_000, 3, 0.8), bytes(200_000),
+         zref.random_bytes(150_000, 4), b"abc" * 30_000]
+for src in cases:
+    for level in (1, -3, 3):
+        got = ctx.compress(src, level)
+        assert got == zref.oracle_compress(src, level)
+d = zref.golden_input("zdict-16k-synthetic-seed77")
+recs = zref.synthetic(1024 * 16, 5)
+for i in range(16):
+    r = recs[i * 1024:(i + 1) * 1024]
+    assert ctx.compress_using_dict(r, d, 1) == zref.oracle_compress_using_dict(r, d, 1)
+src = zref.synthetic(1024 * 64, 9)
+t = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+cap = 64 * (zstd_b200.ZSTD_compressBound(1024) + 32)
+out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+total, csz = ctx.compress_frames(out.data_ptr(), cap, t.data_ptr(), [i * 1024 for i in range(64)], [1024] * 64, level=1, dict_bytes=d)
+print("sanitize workload ok", total)
