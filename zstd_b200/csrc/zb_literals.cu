@@ -14,13 +14,14 @@
 #include "zb_kernels.h"
 #include "zb_bitpack.cuh"
 
-#define LIT_THREADS 256
+#define LIT_THREADS 128
+#define LIT_WARPS (LIT_THREADS / 32)
 
 /* block-wide histogram of src[0..n) into count[256]; returns nothing, count valid after the call */
-__device__ void zb_hist256(const u8* __restrict__ src, u32 n, u32 (*whist)[256], u32* count)
+__device__ void zb_hist256(const u8* __restrict__ src, u32 n, u32 (*whist)[256], u32* count)   /* whist: LIT_WARPS private histograms */
 {
     u32 const tid = threadIdx.x, warp = tid >> 5;
-    for (u32 i = tid; i < 8 * 256; i += LIT_THREADS) (&whist[0][0])[i] = 0;
+    for (u32 i = tid; i < LIT_WARPS * 256; i += LIT_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
     u32 const head = (u32)((16u - ((uintptr_t)src & 15u)) & 15u);       /* bytes before 16-byte alignment */
     u32 const headN = head < n ? head : n;
@@ -40,10 +41,11 @@ __device__ void zb_hist256(const u8* __restrict__ src, u32 n, u32 (*whist)[256],
     }
     for (u32 i = headN + nvec * 16u + tid; i < n; i += LIT_THREADS) atomicAdd(&whist[warp][src[i]], 1u);
     __syncthreads();
-    {   u32 s = 0;
+    for (u32 sym = tid; sym < 256u; sym += LIT_THREADS) {
+        u32 s = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) s += whist[w][tid];
-        count[tid] = s;
+        for (int w = 0; w < LIT_WARPS; w++) s += whist[w][sym];
+        count[sym] = s;
     }
     __syncthreads();
 }
@@ -52,8 +54,8 @@ __device__ void zb_hist256(const u8* __restrict__ src, u32 n, u32 (*whist)[256],
 __device__ void zb_hist_stats(const u32* count, u32* red, u32* largestOut, u32* maxSymOut)
 {
     u32 const tid = threadIdx.x;
-    u32 c = count[tid];
-    u32 key = c ? tid : 0u;
+    u32 c = 0, key = 0;
+    for (u32 sym = tid; sym < 256u; sym += LIT_THREADS) { u32 const v = count[sym]; c = max(c, v); key = max(key, v ? sym : 0u); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         c = max(c, __shfl_xor_sync(ZB_FULL, c, o));
@@ -63,7 +65,7 @@ __device__ void zb_hist_stats(const u32* count, u32* red, u32* largestOut, u32* 
     __syncthreads();
     if (tid == 0) {
         u32 l = 0, m = 0;
-        for (int w = 0; w < 8; w++) { l = max(l, red[w]); m = max(m, red[8 + w]); }
+        for (int w = 0; w < LIT_WARPS; w++) { l = max(l, red[w]); m = max(m, red[8 + w]); }
         *largestOut = l; *maxSymOut = m;
     }
     __syncthreads();
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(LIT_THREADS)
 zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDictEntropy* __restrict__ de,
                    const u8* __restrict__ lits, u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
-    __shared__ u32 whist[8][256];
+    __shared__ u32 whist[LIT_WARPS][256];
     __shared__ u32 count[256];
     __shared__ u32 enc[256];
     __shared__ ZbdHufWksp wk;
@@ -146,7 +148,8 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDic
         else if (largest <= (n >> 7) + 4u) mode = MODE_RAW;
     }
     if (mode == MODE_HUF && !usePrev && repeat == 1u) {                     /* HUF_validateCTable, huf_compress.c:804, :1389-1393 */
-        int const bad = (tid <= sh_maxSym) && count[tid] != 0u && (de->hufEnc[tid] >> 16) == 0u;
+        int bad = 0;
+        for (u32 sym = tid; sym < 256u; sym += LIT_THREADS) bad |= (sym <= sh_maxSym) && count[sym] != 0u && (de->hufEnc[sym] >> 16) == 0u;
         if (__syncthreads_or(bad) || de->hufMaxSymbol < sh_maxSym) repeat = 0u;
     }
     if (mode == MODE_HUF && !usePrev && preferRepeat && repeat != 0u) usePrev = true;      /* :1395-1399 */
@@ -178,7 +181,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDic
     }
     if (mode == MODE_HUF && usePrev) {                                         /* treeless: encode with the dictionary's table */
         __syncthreads();
-        enc[tid] = de->hufEnc[tid];
+        for (u32 sym = tid; sym < 256u; sym += LIT_THREADS) enc[sym] = de->hufEnc[sym];
         if (tid == 0) sh_hSize = 0;
         __syncthreads();
     }
@@ -264,7 +267,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDic
         }
         meta[b].litSecSize = lhSize + total;
     }
-    if (tid < hSize) out[lhSize + tid] = hdr[tid];
+    for (u32 i = tid; i < hSize; i += LIT_THREADS) out[lhSize + i] = hdr[i];
     __syncthreads();          /* byte stores above share words with the streams' first bits: order them before the ORs */
     {
         u32 sOff = lhSize + hSize + (nbStreams == 4u ? 6u : 0u);

@@ -19,6 +19,7 @@
 #include "zb_bitpack.cuh"
 
 #define SEQ_THREADS 128
+#define SEQ_TILE 2048u
 #define MaxLL 35
 #define MaxML 52
 #define MaxOff 31
@@ -103,6 +104,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     __shared__ ZbdFseCTable ct[3];                 /* 0 = LL, 1 = OF, 2 = ML */
     __shared__ ZbdStreamWork wk[3];
     __shared__ u32 chunkBits[SEQ_THREADS];
+    __shared__ u32 codeTile[SEQ_TILE];             /* llCode | ofCode << 8 | mlCode << 16 of one tile of sequences */
     __shared__ u32 sh_cSize, sh_hdrEnd, sh_streamSize;
 
     u32 const tid = threadIdx.x;
@@ -184,27 +186,39 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         bool const err = wk[0].err | wk[1].err | wk[2].err;
         if (err) { if (tid == 0) { meta[b].type = ZB_BT_RAW; meta[b].bodySize = bd.size; } return; }
 
-        /* ---- 3. state chains: threads 0, 32, 64 ---- */
-        if ((tid & 31u) == 0 && tid < 96u) {
+        /* ---- 3. state chains: threads 0, 32, 64.  The only loop-carried value of a chain is `state`
+         * (common/fse.h:463-470); everything else is prepared in parallel: the sequences are walked last to
+         * first in tiles whose LL/OF/ML codes all threads put into shared memory, so a chain step is two
+         * shared-memory look-ups of the table row plus the next-state look-up. ---- */
+        {
+            u32 state = 0;
             u32 const st = tid >> 5;
-            const ZbdFseCTable* const t = &ct[st];
-            u16* const rec = myst + (size_t)st * ZB_STATE_STRIDE;
-            ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
-            u32 state = zbd_fse_initState2(t, st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc));
-            /* the only loop-carried value is `state` (common/fse.h:463-470); the next sequence and its
-             * table row are fetched one step ahead so the chain is ALU + one LDS per symbol */
-            u64 nq = nbSeq >= 2u ? myseq[nbSeq - 2u] : 0ull;
-            for (u32 i = nbSeq - 1u; i-- > 0; ) {
-                ZbdSeq const s = zbd_unpack(nq);
-                if (i > 0) nq = myseq[i - 1u];
-                u32 const sym = st == 0 ? s.llc : (st == 1 ? s.ofc : s.mlc);
-                u32 const dnb = t->deltaNbBits[sym];
-                int const dfs = t->deltaFindState[sym];
-                u32 const nb = (state + dnb) >> 16;
-                rec[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-                state = t->nextState[(int)(state >> nb) + dfs];
+            bool const chain = ((tid & 31u) == 0) && tid < 96u;
+            const ZbdFseCTable* const t = &ct[st < 3u ? st : 0u];
+            u16* const rec = myst + (size_t)(st < 3u ? st : 0u) * ZB_STATE_STRIDE;
+            u32 const nbTiles = (nbSeq + SEQ_TILE - 1u) / SEQ_TILE;
+            for (u32 tile = nbTiles; tile-- > 0; ) {
+                u32 const t0 = tile * SEQ_TILE, t1 = min(t0 + SEQ_TILE, nbSeq);
+                for (u32 i = t0 + tid; i < t1; i += SEQ_THREADS) {
+                    ZbdSeq const s = zbd_unpack(myseq[i]);
+                    codeTile[i - t0] = s.llc | (s.ofc << 8) | (s.mlc << 16);
+                }
+                __syncthreads();
+                if (chain) {
+                    u32 i = t1;
+                    if (t1 == nbSeq) { i--; state = zbd_fse_initState2(t, (codeTile[i - t0] >> (8u * st)) & 0xFFu); }   /* last sequence: no bits */
+                    while (i-- > t0) {
+                        u32 const sym = (codeTile[i - t0] >> (8u * st)) & 0xFFu;
+                        u32 const dnb = t->deltaNbBits[sym];
+                        int const dfs = t->deltaFindState[sym];
+                        u32 const nb = (state + dnb) >> 16;
+                        rec[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+                        state = t->nextState[(int)(state >> nb) + dfs];
+                    }
+                }
+                __syncthreads();
             }
-            wk[st].finalState = state;
+            if (chain) wk[st].finalState = state;
         }
         __syncthreads();
 
