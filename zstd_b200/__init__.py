@@ -15,7 +15,7 @@ import os
 from typing import Optional, Sequence, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzstd_b200.so")
+LIB_PATH = os.environ.get("ZSTDB200_LIB") or os.path.join(_HERE, "libzstd_b200.so")   # override: development variants only
 
 _lib = None
 _sz = ctypes.c_size_t

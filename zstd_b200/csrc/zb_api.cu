@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <time.h>
 #include "../../include/zstd_b200.h"
 #include "zb_common.h"
 #include "zb_kernels.h"
@@ -89,13 +90,21 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
 /* ------------------------------------------------------------------ context */
 static int g_device = -1;
 
+#define ZB_WAVE_SLOTS_MAX 14u
+#define ZB_WAVE_SLOTS_DEFAULT 4u
+#define ZB_HOST_WAVE_SLOTS_DEFAULT 8u   /* measured best with 512-block waves (tests/e2e_sweep.py, profiles/r1_e2e_timeline.md) */
+#define ZB_HOST_WAVE_BLOCKS 512u     /* 64 MiB of input per wave */
 struct ZSTD_CCtx_s {
     int device;
     cudaStream_t stream;
     /* per-block workspace */
     size_t capBlocks, capFrames, capHeavy, capWaves;
     u32 devWaveBlocks;             /* device-memory calls: blocks per wave (0 = always one wave) */
-    cudaStream_t waveStream[8];
+    cudaStream_t waveStream[ZB_WAVE_SLOTS_MAX + 2];
+    u32 waveSlots;                 /* waves in flight, device-memory calls */
+    u32 hostWaveSlots;             /* waves in flight, host-memory calls */
+    u64* h_totalsDev;              /* device alias of h_totals (mapped pinned memory): the scan kernel reports sizes there */
+    u32 hostWaveBlocks;            /* host-memory calls: blocks per wave */
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
     u16* d_dist2; size_t capDist2;                       /* dfast only: short-hash candidate distances */
@@ -117,6 +126,8 @@ struct ZSTD_CCtx_s {
     if (getenv("ZSTDB200_DEBUG")) fprintf(stderr, "zstd_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
     return ZB_ERR(e_ == cudaErrorMemoryAllocation ? ZB_error_memory_allocation : ZB_error_GENERIC); } } while (0)
 
+static double zb_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+
 extern "C" int ZSTDB200_setDevice(int device) { g_device = device; return 0; }
 extern "C" int ZSTDB200_deviceAvailable(void)
 {
@@ -131,7 +142,15 @@ extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
     if (!c) return NULL;
     c->device = -1;
     {   const char* s = getenv("ZSTDB200_SERIAL"); const char* w = getenv("ZSTDB200_WAVE_BLOCKS");
-        c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 2048u); }
+        c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 2048u);
+        const char* n = getenv("ZSTDB200_WAVE_SLOTS"); const char* h = getenv("ZSTDB200_HOST_WAVE_BLOCKS");
+        c->waveSlots = n ? (u32)atoi(n) : ZB_WAVE_SLOTS_DEFAULT;
+        c->hostWaveSlots = n ? (u32)atoi(n) : ZB_HOST_WAVE_SLOTS_DEFAULT;
+        if (c->waveSlots < 1u) c->waveSlots = 1u;
+        if (c->waveSlots > ZB_WAVE_SLOTS_MAX) c->waveSlots = ZB_WAVE_SLOTS_MAX;
+        if (c->hostWaveSlots < 1u) c->hostWaveSlots = 1u;
+        if (c->hostWaveSlots > ZB_WAVE_SLOTS_MAX) c->hostWaveSlots = ZB_WAVE_SLOTS_MAX;
+        c->hostWaveBlocks = (h && atoi(h) > 0) ? (u32)atoi(h) : ZB_HOST_WAVE_BLOCKS; }
     return c;
 }
 
@@ -168,7 +187,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
         cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de); cudaFree(c->d_image); cudaFree(c->d_dictBlock);
-        for (int s = 0; s < 8; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
+        for (u32 s = 0; s < ZB_WAVE_SLOTS_MAX + 2u; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
         cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
         cudaEventDestroy(c->evKEnd); cudaEventDestroy(c->evEnd);
@@ -197,7 +216,8 @@ static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size
     if (nbWaves > c->capWaves) {
         cudaFree(c->d_totals); cudaFreeHost(c->h_totals); c->d_totals = NULL; c->h_totals = NULL; c->capWaves = 0;
         CK(cudaMalloc(&c->d_totals, nbWaves * sizeof(u64)));
-        CK(cudaMallocHost(&c->h_totals, nbWaves * sizeof(u64)));
+        CK(cudaHostAlloc(&c->h_totals, nbWaves * sizeof(u64), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&c->h_totalsDev, c->h_totals, 0));
         c->capWaves = nbWaves;
     }
     return 0;
@@ -256,6 +276,7 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
             b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
             b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
             if (pos == 0 && dictTail) { b.histLen = (u32)dictTail; b.flags |= ZB_FLAG_DICT; }     /* history = dictionary content tail */
+            else if (b.srcOff >= (u64)b.histLen + 4u) b.flags |= ZB_FLAG_FRONTSAFE;
             /* pattern phase of the oldest visible byte: its frame position is pos - histLen (negative inside a dictionary) */
             {   u64 const back = (u64)b.histLen > pos ? (u64)b.histLen - pos : 0;                 /* bytes in front of the frame start */
                 u64 const fpos = pos > b.histLen ? pos - b.histLen : 0;
@@ -366,7 +387,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     unsigned launches = 0;
     if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
     {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
-    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
+    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, NULL, d_dst, dstCapacity, stream));
     launches += 2;
     if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
     CK(cudaEventRecord(c->evKEnd, stream));
@@ -393,22 +414,40 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
 /* ------------------------------------------------------------------ host pointers: pipelined waves
  * H2D copy of wave w+1 | kernels of waves w, w-1, ... (one stream + workspace slot each) | D2H of finished waves.
  * A block needs ~ms of latency end to end (one warp walks it), so several waves are kept in flight. */
-#define ZB_HOST_WAVE_BLOCKS 768u     /* 96 MiB of input per wave */
-#define ZB_WAVE_SLOTS  4u
 
 static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, const u8* src,
                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
                                      const void* dict, size_t dictSize, size_t* cSizes, int level, bool deviceMemory)
 {
-    u32 const ZB_WAVE_BLOCKS = deviceMemory ? c->devWaveBlocks : ZB_HOST_WAVE_BLOCKS;
-    for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));
+    u32 const ZB_WAVE_BLOCKS = deviceMemory ? c->devWaveBlocks : c->hostWaveBlocks;
+    u32 const ZB_WAVE_SLOTS = deviceMemory ? c->waveSlots : c->hostWaveSlots;
+    /* streams are created on first use: every stream beyond the hardware queue count (8 by default) shares a
+     * queue with another one, and a download queued behind another wave's kernels stalls the whole pipeline
+     * (measured: 16 streams -> every download waited for the last upload; profiles/r1_e2e_timeline.md) */
+    auto getStream = [&](u32 i, cudaStream_t* out) -> size_t {
+        if (!c->waveStream[i]) CK(cudaStreamCreateWithFlags(&c->waveStream[i], cudaStreamNonBlocking));
+        *out = c->waveStream[i];
+        return 0;
+    };
+    cudaStream_t sCopy, sD2H = (cudaStream_t)0;
+    {   size_t const e = getStream(ZB_WAVE_SLOTS_MAX, &sCopy); if (zb_isErr(e)) return e; }
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
-    {   size_t const e = zb_prepareDict(c, dict, dictSize, c->waveStream[ZB_WAVE_SLOTS], &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_prepareDict(c, dict, dictSize, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
     zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
-    u32 const nbWaves = (nbBlocks + ZB_WAVE_BLOCKS - 1u) / ZB_WAVE_BLOCKS;
+    /* wave boundaries.  Host path: the call ends when the LAST wave has gone through every kernel, so the
+     * final waves shrink (1/2, 1/4, 1/8 of a wave): less work behind the last upload. */
+    std::vector<u32> wb;
+    {   std::vector<u32> tail;
+        u32 left = nbBlocks;
+        if (!deviceMemory) for (u32 sz = ZB_WAVE_BLOCKS / 8u; sz >= 32u && sz < ZB_WAVE_BLOCKS && left > 2u * sz; sz *= 2u) { tail.push_back(sz); left -= sz; }
+        wb.push_back(0);
+        for (u32 b = 0; b < left; ) { u32 const e = (left - b > ZB_WAVE_BLOCKS) ? b + ZB_WAVE_BLOCKS : left; wb.push_back(e); b = e; }
+        for (size_t i = tail.size(); i-- > 0; ) wb.push_back(wb.back() + tail[i]);
+    }
+    u32 const nbWaves = (u32)wb.size() - 1u;
     u32 const slots = nbWaves < ZB_WAVE_SLOTS ? nbWaves : ZB_WAVE_SLOTS;
     size_t inEnd = 0, bound = 0;
     for (size_t f = 0; f < nbFrames; f++) {
@@ -425,14 +464,18 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         if (inEnd + 16 > c->d_inCap) { cudaFree(c->d_in); c->d_in = NULL; c->d_inCap = 0; CK(cudaMalloc(&c->d_in, inEnd + 16)); c->d_inCap = inEnd + 16; }
         if (outCap + 16 > c->d_outCap) { cudaFree(c->d_out); c->d_out = NULL; c->d_outCap = 0; CK(cudaMalloc(&c->d_out, outCap + 16)); c->d_outCap = outCap + 16; }
         d_in = c->d_in; d_out = c->d_out;
+        size_t const e = getStream(ZB_WAVE_SLOTS_MAX + 1u, &sD2H); if (zb_isErr(e)) return e;
     }
-    for (u32 s = 0; s < ZB_WAVE_SLOTS + 2u; s++) if (!c->waveStream[s]) CK(cudaStreamCreateWithFlags(&c->waveStream[s], cudaStreamNonBlocking));
-    cudaStream_t const sCopy = c->waveStream[ZB_WAVE_SLOTS], sD2H = c->waveStream[ZB_WAVE_SLOTS + 1u];
-    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evDone(nbWaves);
+    bool const download = !deviceMemory;
+    bool const timeline = getenv("ZSTDB200_TIMELINE") != NULL;      /* development: print each wave's milestones */
+    unsigned const evFlags = timeline ? cudaEventDefault : cudaEventDisableTiming;
+    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evD2H(timeline ? nbWaves : 0);
+    std::vector<double> hostDone(nbWaves, 0.0);
+    double const hostT0 = zb_now();
     for (u32 w = 0; w < nbWaves; w++) {
-        CK(cudaEventCreateWithFlags(&evH2D[w], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&evStitch[w], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&evDone[w], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evH2D[w], evFlags));
+        CK(cudaEventCreateWithFlags(&evStitch[w], evFlags));
+        if (timeline) CK(cudaEventCreate(&evD2H[w]));
     }
     unsigned launches = 0;
     size_t err = 0;
@@ -440,46 +483,66 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, sCopy));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, sCopy));
     if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, sCopy); if (zb_isErr(e)) return e; }
+    cudaStream_t lastStream = sCopy;
     for (u32 w = 0; w < nbWaves && !err; w++) {
-        u32 const b0 = w * ZB_WAVE_BLOCKS, b1 = (b0 + ZB_WAVE_BLOCKS < nbBlocks) ? b0 + ZB_WAVE_BLOCKS : nbBlocks;
+        u32 const b0 = wb[w], b1 = wb[w + 1];
         /* input bytes of the wave (frames are laid out in offset order; history was uploaded by earlier waves) */
         u64 lo = ~0ull, hi = 0;
         for (u32 b = b0; b < b1; b++) { u64 const a = P.blocks[b].srcOff, e = a + P.blocks[b].size; if (a < lo) lo = a; if (e > hi) hi = e; }
         if (hi > lo && !deviceMemory) CK(cudaMemcpyAsync(d_in + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, sCopy));
         CK(cudaEventRecord(evH2D[w], sCopy));
-        cudaStream_t const st = c->waveStream[w % slots];
+        cudaStream_t st;
+        {   size_t const e = getStream(w % slots, &st); if (zb_isErr(e)) return e; }
+        lastStream = st;
         CK(cudaStreamWaitEvent(st, evH2D[w], 0));
         err = zb_runBlocks(c, P, d_in, d_dictEnd, b0, b1, (size_t)(w % slots) * ZB_WAVE_BLOCKS, st, false, &launches);
         if (err) break;
         if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
         size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
         CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
-                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, d_out, outCap, st));
+                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, c->h_totalsDev + w, d_out, outCap, st));
         launches += 2;
         CK(cudaEventRecord(evStitch[w], st));
-        CK(cudaMemcpyAsync(c->h_totals + w, c->d_totals + w, sizeof(u64), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(evDone[w], st));
     }
-    /* drain: as each wave's size becomes known, ship its bytes */
+    double const hostEnq = zb_now() - hostT0;
     u64 prev = 0, total = 0;
-    for (u32 w = 0; w < nbWaves && !err; w++) {
-        CK(cudaEventSynchronize(evDone[w]));
-        total = c->h_totals[w];
-        if (!deviceMemory && total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
-        if (total <= outCap) prev = total;
+    if (download || timeline) {
+        /* drain: as each wave's size becomes known, ship its bytes */
+        for (u32 w = 0; w < nbWaves && !err; w++) {
+            CK(cudaEventSynchronize(evStitch[w]));
+            hostDone[w] = zb_now() - hostT0;
+            total = c->h_totals[w];
+            if (download && total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
+            if (total <= outCap) prev = total;
+            if (timeline) CK(cudaEventRecord(evD2H[w], download ? sD2H : lastStream));
+        }
     }
     if (!err && cSizes) {
-        cudaStream_t const st = c->waveStream[(nbWaves - 1) % slots];
-        CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, st));
+        CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, lastStream));
         std::vector<u64> tmp(nbFrames);
-        CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, lastStream));
+        CK(cudaStreamSynchronize(lastStream));
         for (size_t f = 0; f < nbFrames; f++) cSizes[f] = (size_t)tmp[f];
     }
-    CK(cudaEventRecord(c->evEnd, sD2H));
-    CK(cudaStreamSynchronize(sD2H));
-    for (u32 s = 0; s < slots; s++) CK(cudaStreamSynchronize(c->waveStream[s]));
-    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); cudaEventDestroy(evDone[w]); }
+    /* the last wave's stitch is ordered behind every earlier one (evStitch chain) */
+    if (download) { CK(cudaEventRecord(c->evEnd, sD2H)); CK(cudaStreamSynchronize(sD2H)); }
+    else CK(cudaEventRecord(c->evEnd, lastStream));
+    for (u32 s = 0; s < slots; s++) if (c->waveStream[s]) CK(cudaStreamSynchronize(c->waveStream[s]));
+    CK(cudaStreamSynchronize(sCopy));
+    if (!err && nbWaves) total = c->h_totals[nbWaves - 1];
+    if (timeline) {
+        fprintf(stderr, "zstd_b200 timeline (ms after the call's first enqueue; host enqueue loop took %.3f ms; %s)\n", 1e3 * hostEnq,
+                deviceMemory ? "device buffers" : "per-wave downloads");
+        for (u32 w = 0; w < nbWaves; w++) {
+            float a = 0, b = 0, e = 0;
+            cudaEventElapsedTime(&a, c->evStart, evH2D[w]); cudaEventElapsedTime(&b, c->evStart, evStitch[w]);
+            cudaEventElapsedTime(&e, c->evStart, evD2H[w]);
+            fprintf(stderr, "  wave %2u blocks %5u..%5u : uploaded %7.3f  stitched %7.3f (host saw it %7.3f)  downloaded %7.3f\n",
+                    w, wb[w], wb[w + 1], a, b, 1e3 * hostDone[w], e);
+            cudaEventDestroy(evD2H[w]);
+        }
+    }
+    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); }
     if (err) return err;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; c->stats.kernel_ms = ms; }
     c->stats.launches = launches; c->stats.nbBlocks = nbBlocks;

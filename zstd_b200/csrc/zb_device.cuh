@@ -44,16 +44,6 @@ __device__ __forceinline__ u64 zb_ld64w3(const u8* p)
     u32 const a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     return ((u64)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
 }
-/* The 4 bytes at rel position x (`cur`) and the 4 bytes in front of it (`pre`, byte x-1 in the top
- * byte; bytes in front of position 0 are undefined and must be masked by the caller's limits). */
-__device__ __forceinline__ void zb_ld_pre_cur(const u8* base, u32 x, u32* pre, u32* cur)
-{
-    u32 const s = x >= 4u ? 0u : 4u - x;
-    u64 const w = zb_ld64w3(base + (x + s - 4u));
-    *pre = (u32)(w << (8u * s));
-    *cur = (u32)(w >> (32u - 8u * s));
-}
-
 /* ---- two-segment addressing (dictionary content in front of a frame, zstd_compress_internal.h:797
  * ZSTD_count_2segments is the reference's counterpart): rel positions < split live in `lo`, the rest
  * in `hi`; both pointers are pre-biased so that ptr + rel is the byte's address. ---- */
@@ -89,6 +79,8 @@ template <bool DICT> __device__ __forceinline__ u64 zb_seg_ld64x(const ZbSeg& s,
     return zb_ld64u(zb_seg_ptr<DICT>(s, rel));
 }
 template <bool DICT> __device__ __forceinline__ u32 zb_seg_ld32(const ZbSeg& s, u32 rel) { return (u32)zb_seg_ld64<DICT>(s, rel); }
+/* The 4 bytes at rel position x (`cur`) and the 4 bytes in front of it (`pre`, byte x-1 in the top byte;
+ * bytes in front of position 0 are undefined and must be masked by the caller's limits). */
 template <bool DICT> __device__ __forceinline__ void zb_seg_pre_cur(const ZbSeg& sg, u32 x, u32* pre, u32* cur)
 {
     u32 const s = x >= 4u ? 0u : 4u - x;
