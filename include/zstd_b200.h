@@ -46,6 +46,21 @@ ZSTDB200_API size_t ZSTD_compress_usingDict(ZSTD_CCtx* ctx, void* dst, size_t ds
                                             const void* src, size_t srcSize,
                                             const void* dict, size_t dictSize, int compressionLevel);
 
+/* lib/zstd.h:967-995 — digested dictionary: the dictionary is parsed once, its content tail, entropy tables
+ * and primed match-finder tables stay resident on the GPU across calls (the reference's CDict keeps the
+ * same things in host memory, zstd_compress.c:5477-5642).  A CDict may be shared by any number of contexts
+ * on one device.  ZSTD_createCDict returns NULL for a zstd-format dictionary whose entropy tables are
+ * corrupted; ZSTD_freeCDict accepts NULL.  ZSTD_compress_usingCDict compresses at the CDict's level
+ * (zstd_compress.c:5836) and produces the bytes ZSTD_compress_usingDict produces for the same inputs. */
+typedef struct ZSTD_CDict_s ZSTD_CDict;
+ZSTDB200_API ZSTD_CDict* ZSTD_createCDict(const void* dictBuffer, size_t dictSize, int compressionLevel);
+ZSTDB200_API size_t      ZSTD_freeCDict(ZSTD_CDict* cdict);
+ZSTDB200_API size_t      ZSTD_compress_usingCDict(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                                  const void* src, size_t srcSize, const ZSTD_CDict* cdict);
+/* lib/zstd.h:1099-1111 */
+ZSTDB200_API unsigned    ZSTD_getDictID_fromCDict(const ZSTD_CDict* cdict);
+ZSTDB200_API unsigned    ZSTD_getDictID_fromDict(const void* dict, size_t dictSize);
+
 /* lib/zstd.h:236,242-246,114-120 ; lib/zstd_errors.h:106 */
 ZSTDB200_API size_t      ZSTD_compressBound(size_t srcSize);
 ZSTDB200_API unsigned    ZSTD_isError(size_t code);
@@ -73,6 +88,13 @@ ZSTDB200_API size_t ZSTDB200_compressFrames(ZSTD_CCtx* cctx, void* dst, size_t d
                                             const void* src, const size_t* frameOffsets, const size_t* frameSizes,
                                             size_t nbFrames, const void* dict, size_t dictSize,
                                             size_t* cSizes, int compressionLevel, int deviceMemory, void* stream);
+
+/* Same with a digested dictionary (level = the CDict's): what a record store calling
+ * ZSTD_compress_usingCDict in a loop would batch (contrib/largeNbDicts/largeNbDicts.c:553). */
+ZSTDB200_API size_t ZSTDB200_compressFrames_usingCDict(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                            const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                            size_t nbFrames, const ZSTD_CDict* cdict,
+                                            size_t* cSizes, int deviceMemory, void* stream);
 
 /* Timing / evidence of the last call on this context (CUDA events on the launching stream). */
 typedef struct {

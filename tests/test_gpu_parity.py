@@ -190,3 +190,67 @@ def test_many_records_with_dictionary(ctx):
             if zref.have_ref():
                 assert zref.ref_decompress_using_dict(out[pos:pos + csz[i]], d, rec) == src[i * rec:(i + 1) * rec]
         pos += csz[i]
+
+
+@pytest.mark.parametrize("level", [1, 3, -3])
+@pytest.mark.parametrize("dict_name", ["zdict-16k-synthetic-seed77", "raw-32k"])
+def test_compress_using_cdict(ctx, dict_name, level):
+    """ZSTD_createCDict / ZSTD_compress_usingCDict (lib/zstd.h:967-995): same bytes as
+    ZSTD_compress_usingDict at the CDict's level = the oracle's, decodable by the reference, stable across
+    repeated calls and across contexts sharing the CDict."""
+    d = zref.synthetic(32 << 10, 123, 0.5) if dict_name == "raw-32k" else zref.golden_input(dict_name)
+    data = zref.synthetic(1024 * 48, 15, 0.5)
+    srcs = [data[i * 1024:(i + 1) * 1024] for i in range(48)] + [b"", b"a", d[-2000:-900], zref.synthetic(300_000, 8)]
+    cd = zstd_b200.ZSTD_CDict(d, level)
+    ctx2 = zstd_b200.ZSTD_CCtx()
+    assert cd.dict_id == (zstd_b200.lib().ZSTD_getDictID_fromDict(d, len(d)))
+    assert (cd.dict_id != 0) == (dict_name != "raw-32k")
+    for k, src in enumerate(srcs):
+        got = (ctx if k % 2 else ctx2).compress_using_cdict(src, cd)
+        assert got == zref.oracle_compress_using_dict(src, d, level)
+        if k < 4:
+            assert got == ctx.compress_using_dict(src, d, level)
+            assert got == ctx.compress_using_cdict(src, cd)
+        if zref.have_ref():
+            assert zref.ref_decompress_using_dict(got, d, len(src)) == src
+    ctx2.close()
+    cd.close()
+
+
+def test_many_records_with_cdict(ctx):
+    """Config 5 through the digested dictionary: one batch call, host and device buffers, equals per-record calls."""
+    import torch
+    d = zref.golden_input("zdict-16k-synthetic-seed77")
+    rec, n = 1024, 2048
+    src = zref.synthetic(rec * n, 92, 0.5)
+    cd = zstd_b200.ZSTD_CDict(d, 1)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = n * (zstd_b200.ZSTD_compressBound(rec) + 32)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    offs, sizes = [i * rec for i in range(n)], [rec] * n
+    for rep in range(2):                                  # second call reuses the cached table image
+        total, csz = ctx.compress_frames_using_cdict(d_dst.data_ptr(), cap, d_src.data_ptr(), offs, sizes, cd)
+        out = bytes(d_dst[:total].cpu().numpy())
+        assert sum(csz) == total
+        pos = 0
+        for i in range(n):
+            if i % 97 == 0:
+                assert out[pos:pos + csz[i]] == zref.oracle_compress_using_dict(src[i * rec:(i + 1) * rec], d, 1)
+            pos += csz[i]
+    total2, csz2 = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), offs, sizes, level=1, dict_bytes=d)
+    assert (total2, csz2) == (total, csz) and bytes(d_dst[:total2].cpu().numpy()) == out
+    cd.close()
+
+
+def test_cdict_errors():
+    bad = bytearray(zref.golden_input("zdict-16k-synthetic-seed77")); bad[12:40] = b"\xff" * 28      # entropy tables destroyed
+    with pytest.raises(zstd_b200.ZstdError):
+        zstd_b200.ZSTD_CDict(bytes(bad), 1)
+    L = zstd_b200.lib()
+    c = zstd_b200.ZSTD_CCtx()
+    import ctypes
+    dst = ctypes.create_string_buffer(64)
+    r = L.ZSTD_compress_usingCDict(c._h, dst, 64, b"abc", 3, None)
+    assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 32           # dictionary_wrong, zstd_compress.c:5753
+    assert L.ZSTD_freeCDict(None) == 0
+    c.close()

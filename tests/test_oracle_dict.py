@@ -114,3 +114,26 @@ def test_dictionary_entropy_stage_byte_exact(dict_name):
             assert d1.raw[:r1] == d2.raw[:r2]
             compressed += r1 > 0
     assert compressed > 80
+
+
+@needs_ref
+@pytest.mark.skipif(not zref.have_datagen(), reason="oracle/_ref/datagen not built")
+@pytest.mark.parametrize("level", [1, 3, -3])
+def test_size_parity_with_reference_cdict(level):
+    """ZSTD_compress_usingCDict is the production form of config 5.  The GPU CDict path
+    emits the bytes of the usingDict path, so the oracle's usingDict output must sit within +-0.5 % of what the
+    reference's ZSTD_compress_usingCDict produces on config 5's data (datagen -P50 cut into 1 KiB records,
+    16 KiB ZDICT dictionary) — including level 3, where the reference runs doubleFast and this implementation
+    the two-segment fast match-finder with level 3's window / hash / minMatch."""
+    data = zref.datagen(REC * 6000, 50)
+    d = zref.train_dict(data, REC, 4000, 16 << 10)
+    srcs = [data[i * REC:(i + 1) * REC] for i in range(4000, 5000)]
+    ref_frames = zref.ref_compress_using_cdict(srcs, d, level)
+    tot_o = 0
+    for k, src in enumerate(srcs):
+        f = zref.oracle_compress_using_dict(src, d, level)
+        if k % 25 == 0:
+            assert zref.ref_decompress_using_dict(f, d, len(src)) == src
+        tot_o += len(f)
+    tot_r = sum(len(f) for f in ref_frames)
+    assert abs(tot_o - tot_r) / tot_r <= 0.005, (tot_o, tot_r)

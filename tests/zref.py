@@ -160,6 +160,41 @@ def ref_compress_using_dict(src: bytes, dict_bytes: bytes, level: int) -> bytes:
     return dst.raw[:r]
 
 
+def ref_compress_using_cdict(srcs, dict_bytes: bytes, level: int):
+    """Reference ZSTD_createCDict + ZSTD_compress_usingCDict over a list of inputs -> list of frames."""
+    R = ref()
+    R.ZSTD_createCDict.restype = ctypes.c_void_p
+    R.ZSTD_createCDict.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    R.ZSTD_freeCDict.argtypes = [ctypes.c_void_p]
+    R.ZSTD_compress_usingCDict.restype = ctypes.c_size_t
+    R.ZSTD_compress_usingCDict.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    cd = R.ZSTD_createCDict(dict_bytes, len(dict_bytes), level)
+    assert cd
+    cctx = R.ZSTD_createCCtx()
+    out = []
+    for src in srcs:
+        cap = R.ZSTD_compressBound(len(src))
+        dst = ctypes.create_string_buffer(max(cap, 1))
+        r = R.ZSTD_compress_usingCDict(cctx, dst, cap, src, len(src), cd)
+        assert not R.ZSTD_isError(r), R.ZSTD_getErrorName(r)
+        out.append(dst.raw[:r])
+    R.ZSTD_freeCCtx(cctx)
+    R.ZSTD_freeCDict(cd)
+    return out
+
+
+def train_dict(samples: bytes, sample_size: int, nb_samples: int, dict_size: int) -> bytes:
+    """ZDICT_trainFromBuffer (lib/zdict.h:210) of the compiled reference: how BASELINE config 5 makes its dictionary."""
+    R = ref()
+    R.ZDICT_trainFromBuffer.restype = ctypes.c_size_t
+    R.ZDICT_trainFromBuffer.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint]
+    sizes = (ctypes.c_size_t * nb_samples)(*([sample_size] * nb_samples))
+    dbuf = ctypes.create_string_buffer(dict_size)
+    n = R.ZDICT_trainFromBuffer(dbuf, dict_size, samples, sizes, nb_samples)
+    assert not R.ZSTD_isError(n)
+    return dbuf.raw[:n]
+
+
 def ref_decompress_using_dict(frame: bytes, dict_bytes: bytes, max_size: int) -> bytes:
     R = ref()
     dctx = R.ZSTD_createDCtx()

@@ -79,6 +79,21 @@ def lib() -> ctypes.CDLL:
     L.ZSTDB200_setDevice.restype = ctypes.c_int
     L.ZSTDB200_setDevice.argtypes = [ctypes.c_int]
     L.ZSTDB200_deviceAvailable.restype = ctypes.c_int
+    if os.environ.get("ZSTDB200_LIB") and not hasattr(L, "ZSTD_createCDict"):      # an older development build
+        _lib = L
+        return L
+    L.ZSTD_createCDict.restype = _vp
+    L.ZSTD_createCDict.argtypes = [_vp, _sz, ctypes.c_int]
+    L.ZSTD_freeCDict.restype = _sz
+    L.ZSTD_freeCDict.argtypes = [_vp]
+    L.ZSTD_compress_usingCDict.restype = _sz
+    L.ZSTD_compress_usingCDict.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp]
+    L.ZSTD_getDictID_fromCDict.restype = ctypes.c_uint
+    L.ZSTD_getDictID_fromCDict.argtypes = [_vp]
+    L.ZSTD_getDictID_fromDict.restype = ctypes.c_uint
+    L.ZSTD_getDictID_fromDict.argtypes = [_vp, _sz]
+    L.ZSTDB200_compressFrames_usingCDict.restype = _sz
+    L.ZSTDB200_compressFrames_usingCDict.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_int, _vp]
     _lib = L
     return L
 
@@ -102,6 +117,31 @@ def _buf(data) -> Tuple[ctypes.c_void_p, int, object]:
     mv = memoryview(data).cast("B")
     keep = (ctypes.c_char * len(mv)).from_buffer(mv) if not mv.readonly else (ctypes.c_char * len(mv)).from_buffer_copy(mv)
     return ctypes.cast(keep, _vp), len(mv), keep
+
+
+class ZSTD_CDict:
+    """Digested dictionary (lib/zstd.h:967-995): parsed once, resident on the GPU from its first use."""
+
+    def __init__(self, dict_bytes, level: int = 3):
+        p, n, keep = _buf(dict_bytes)
+        self._h = lib().ZSTD_createCDict(p, n, level)
+        if not self._h:
+            raise ZstdError(30, "ZSTD_createCDict failed (dictionary corrupted or out of memory)")
+
+    @property
+    def dict_id(self) -> int:
+        return int(lib().ZSTD_getDictID_fromCDict(self._h))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ZSTD_freeCDict(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter teardown
+            pass
 
 
 class ZSTD_CCtx:
@@ -143,6 +183,14 @@ class ZSTD_CCtx:
         r = _check(lib().ZSTD_compress_usingDict(self._h, dst, cap, p, n, dp, dn, level))
         return dst.raw[:r]
 
+    def compress_using_cdict(self, src, cdict: "ZSTD_CDict") -> bytes:
+        """ZSTD_compress_usingCDict (lib/zstd.h:987): level and dictionary come from the CDict."""
+        p, n, keep = _buf(src)
+        cap = ZSTD_compressBound(n)
+        dst = ctypes.create_string_buffer(max(cap, 1))
+        r = _check(lib().ZSTD_compress_usingCDict(self._h, dst, cap, p, n, cdict._h))
+        return dst.raw[:r]
+
     # -- B200 extensions --
     def compress_device(self, d_dst: int, dst_capacity: int, d_src: int, src_size: int, level: int = 3, stream: int = 0) -> int:
         """One frame, device pointers (ints, e.g. torch.Tensor.data_ptr()).  Returns compressed size."""
@@ -158,6 +206,17 @@ class ZSTD_CCtx:
         dp, dn, dkeep = (None, 0, None) if dict_bytes is None else _buf(dict_bytes)
         r = _check(lib().ZSTDB200_compressFrames(self._h, dst, dst_capacity, src, offs, szs, n, dp, dn, csz, level,
                                                 1 if device_memory else 0, stream))
+        return r, list(csz)
+
+    def compress_frames_using_cdict(self, dst: int, dst_capacity: int, src: int, offsets: Sequence[int], sizes: Sequence[int],
+                                    cdict: "ZSTD_CDict", device_memory: bool = True, stream: int = 0):
+        """Many independent frames against one digested dictionary.  Returns (total_bytes, [size per frame])."""
+        n = len(sizes)
+        offs = (_sz * n)(*offsets)
+        szs = (_sz * n)(*sizes)
+        csz = (_sz * n)()
+        r = _check(lib().ZSTDB200_compressFrames_usingCDict(self._h, dst, dst_capacity, src, offs, szs, n, cdict._h, csz,
+                                                           1 if device_memory else 0, stream))
         return r, list(csz)
 
     def stats(self) -> Stats:

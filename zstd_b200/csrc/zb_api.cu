@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
 #include <time.h>
 #include "../../include/zstd_b200.h"
 #include "zb_common.h"
@@ -87,6 +88,9 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
     return p;
 }
 
+#define ZB_IMAGE_BYTES (3u << 14)      /* largest table: 2^14 positions + tags */
+#define ZB_MAX_IMAGES 4
+
 /* ------------------------------------------------------------------ context */
 static int g_device = -1;
 
@@ -94,6 +98,20 @@ static int g_device = -1;
 #define ZB_WAVE_SLOTS_DEFAULT 4u
 #define ZB_HOST_WAVE_SLOTS_DEFAULT 8u   /* measured best with 512-block waves (tests/e2e_sweep.py, profiles/r1_e2e_timeline.md) */
 #define ZB_HOST_WAVE_BLOCKS 512u     /* 64 MiB of input per wave */
+/* Digested dictionary (lib/zstd.h:979, zstd_compress.c:5477-5642): the content tail, its entropy tables and
+ * the primed hash-table images live on the device across calls; any number of contexts may use it. */
+struct ZSTD_CDict_s {
+    int level;
+    u8* content;                   /* host copy of the whole dictionary (ZSTD_dlm_byCopy) */
+    size_t size;
+    size_t contentOff, tail;       /* entropy header size, bytes of content that blocks can see */
+    ZbDictEntropy entropy;         /* parsed on the host at creation */
+    std::mutex* lock;              /* guards the lazily created device state below */
+    int device;                    /* -1 until first use */
+    u8* d_dict; ZbDictEntropy* d_de; u8* d_image; ZbBlock* d_dictBlock;
+    u32 nbImages; ZbParams imagePrm[ZB_MAX_IMAGES];
+};
+
 struct ZSTD_CCtx_s {
     int device;
     cudaStream_t stream;
@@ -103,7 +121,6 @@ struct ZSTD_CCtx_s {
     cudaStream_t waveStream[ZB_WAVE_SLOTS_MAX + 2];
     u32 waveSlots;                 /* waves in flight, device-memory calls */
     u32 hostWaveSlots;             /* waves in flight, host-memory calls */
-    u64* h_totalsDev;              /* device alias of h_totals (mapped pinned memory): the scan kernel reports sizes there */
     u32 hostWaveBlocks;            /* host-memory calls: blocks per wave */
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
@@ -216,8 +233,7 @@ static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size
     if (nbWaves > c->capWaves) {
         cudaFree(c->d_totals); cudaFreeHost(c->h_totals); c->d_totals = NULL; c->h_totals = NULL; c->capWaves = 0;
         CK(cudaMalloc(&c->d_totals, nbWaves * sizeof(u64)));
-        CK(cudaHostAlloc(&c->h_totals, nbWaves * sizeof(u64), cudaHostAllocMapped));
-        CK(cudaHostGetDevicePointer((void**)&c->h_totalsDev, c->h_totals, 0));
+        CK(cudaMallocHost(&c->h_totals, nbWaves * sizeof(u64)));
         c->capWaves = nbWaves;
     }
     return 0;
@@ -250,9 +266,7 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
  * FSE tables are that block's "previous" entropy state (treeless literals, set_repeat sequence tables) and
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
-struct ZbGroup { ZbParams prm; u32 b0, b1; bool imageReady; };
-#define ZB_IMAGE_BYTES (3u << 14)      /* largest table: 2^14 positions + tags */
-#define ZB_MAX_IMAGES 4
+struct ZbGroup { ZbParams prm; u32 b0, b1; const u8* image; };   /* image: table primed from the dictionary tail, or NULL */
 struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; bool unsupported; };
 
 static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
@@ -262,10 +276,12 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
     P.unsupported = false;
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
-        ZbCParams const cp = zb_getCParams(level, fsz, dictSize);
+        ZbCParams cp = zb_getCParams(level, fsz, dictSize);
+        /* the two-segment (dictionary) match-finder exists for the fast strategy only (zstd_fast.c:709): a
+         * dictionary call at a doubleFast level runs it with that level's window / hash / minMatch */
+        if (dictSize && cp.strategy != 1) cp.strategy = 1;
         ZbParams prm = zb_makeParams(cp);
         if (dictRep) { prm.startRep[0] = dictRep[0] <= dictTail ? dictRep[0] : 0u; prm.startRep[1] = dictRep[1] <= dictTail ? dictRep[1] : 0u; }
-        if (dictSize && cp.strategy != 1) P.unsupported = true;           /* dictionaries: fast strategy only for now */
         size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
         ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)P.blocks.size();
         fr.windowLog = cp.windowLog; fr.dictID = dictID;
@@ -276,7 +292,6 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
             b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
             b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
             if (pos == 0 && dictTail) { b.histLen = (u32)dictTail; b.flags |= ZB_FLAG_DICT; }     /* history = dictionary content tail */
-            else if (b.srcOff >= (u64)b.histLen + 4u) b.flags |= ZB_FLAG_FRONTSAFE;
             /* pattern phase of the oldest visible byte: its frame position is pos - histLen (negative inside a dictionary) */
             {   u64 const back = (u64)b.histLen > pos ? (u64)b.histLen - pos : 0;                 /* bytes in front of the frame start */
                 u64 const fpos = pos > b.histLen ? pos - b.histLen : 0;
@@ -287,17 +302,54 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
         } while (pos < fsz);
         fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
         P.frames[f] = fr;
-        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.imageReady = false; P.groups.push_back(g); }
+        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.image = NULL; P.groups.push_back(g); }
         else P.groups.back().b1 = (u32)P.blocks.size();
     }
 }
 
 /* parse + upload the dictionary content tail; returns 0 or an error.  *d_dictEnd = NULL when no dictionary applies */
-static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, cudaStream_t stream,
+/* device buffers of one dictionary: content tail with 32 bytes of padding on both sides, entropy state,
+ * table images, pseudo block descriptors */
+static size_t zb_allocDictBuffers(u8** d_dict, ZbDictEntropy** d_de, u8** d_image, ZbBlock** d_dictBlock)
+{
+    if (*d_dict) return 0;
+    CK(cudaMalloc(d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(d_de, sizeof(ZbDictEntropy)));
+    CK(cudaMalloc(d_image, (size_t)ZB_IMAGE_BYTES * ZB_MAX_IMAGES)); CK(cudaMalloc(d_dictBlock, ZB_MAX_IMAGES * sizeof(ZbBlock)));
+    return 0;
+}
+static size_t zb_uploadDict(u8* d_dict, ZbDictEntropy* d_de, const ZbDictEntropy* de, const u8* content, size_t contentSize, size_t tail, cudaStream_t stream)
+{
+    CK(cudaMemsetAsync(d_dict, 0, ZB_PRIME_BYTES + 64, stream));
+    if (tail) CK(cudaMemcpyAsync(d_dict + 32, content + (contentSize - tail), tail, cudaMemcpyHostToDevice, stream));
+    if (de->present) CK(cudaMemcpyAsync(d_de, de, sizeof(ZbDictEntropy), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+/* Makes the call's dictionary resident: either the caller's raw bytes (parsed and uploaded now, into the
+ * context's buffers) or a digested ZSTD_CDict (uploaded on its first use, then only referenced). */
+static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, const ZSTD_CDict* cdictC, cudaStream_t stream,
                              size_t* effDictSize, size_t* dictTail, u32* dictID, const u8** d_dictEnd)
 {
     *effDictSize = 0; *dictTail = 0; *dictID = 0; *d_dictEnd = NULL;
     c->dictEntropy.present = 0; c->d_deActive = NULL;
+    if (cdictC) {
+        ZSTD_CDict* const cd = const_cast<ZSTD_CDict*>(cdictC);      /* the lazily created device state is guarded by cd->lock */
+        if (cd->size < 8) return 0;                                  /* zstd_compress.c:5130 : tiny dictionaries are ignored */
+        std::lock_guard<std::mutex> g(*cd->lock);
+        if (cd->device >= 0 && cd->device != c->device) return ZB_ERR(ZB_error_parameter_unsupported);   /* one device per CDict */
+        if (cd->device < 0) {
+            {   size_t const e = zb_allocDictBuffers(&cd->d_dict, &cd->d_de, &cd->d_image, &cd->d_dictBlock); if (zb_isErr(e)) return e; }
+            {   size_t const e = zb_uploadDict(cd->d_dict, cd->d_de, &cd->entropy, cd->content + cd->contentOff, cd->size - cd->contentOff, cd->tail, stream); if (zb_isErr(e)) return e; }
+            CK(cudaStreamSynchronize(stream));                       /* other contexts (other streams) may use it right away */
+            cd->device = c->device;
+        }
+        c->dictEntropy = cd->entropy;
+        *dictID = cd->entropy.present ? cd->entropy.dictID : 0u;
+        *effDictSize = cd->size; *dictTail = cd->tail;
+        *d_dictEnd = cd->d_dict + 32 + cd->tail;
+        if (cd->entropy.present) c->d_deActive = cd->d_de;
+        return 0;
+    }
     if (!dict || dictSize < 8) return 0;
     size_t const contentOff = zb_loadDictionary(&c->dictEntropy, (const u8*)dict, dictSize);
     if (zb_isErr(contentOff)) return contentOff;
@@ -305,36 +357,44 @@ static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, cu
     size_t const contentSize = dictSize - contentOff;
     size_t const tail = contentSize < ZB_PRIME_BYTES ? contentSize : ZB_PRIME_BYTES;
     *effDictSize = dictSize; *dictTail = tail;
-    if (!c->d_dict) { CK(cudaMalloc(&c->d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(&c->d_de, sizeof(ZbDictEntropy)));
-                      CK(cudaMalloc(&c->d_image, (size_t)ZB_IMAGE_BYTES * ZB_MAX_IMAGES)); CK(cudaMalloc(&c->d_dictBlock, ZB_MAX_IMAGES * sizeof(ZbBlock))); }
-    CK(cudaMemsetAsync(c->d_dict, 0, ZB_PRIME_BYTES + 64, stream));
-    if (tail) CK(cudaMemcpyAsync(c->d_dict + 32, (const u8*)dict + contentOff + (contentSize - tail), tail, cudaMemcpyHostToDevice, stream));
+    {   size_t const e = zb_allocDictBuffers(&c->d_dict, &c->d_de, &c->d_image, &c->d_dictBlock); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_uploadDict(c->d_dict, c->d_de, &c->dictEntropy, (const u8*)dict + contentOff, contentSize, tail, stream); if (zb_isErr(e)) return e; }
     *d_dictEnd = c->d_dict + 32 + tail;
-    if (c->dictEntropy.present) {
-        CK(cudaMemcpyAsync(c->d_de, &c->dictEntropy, sizeof(ZbDictEntropy), cudaMemcpyHostToDevice, stream));
-        c->d_deActive = c->d_de;
-    }
+    if (c->dictEntropy.present) c->d_deActive = c->d_de;
     return 0;
 }
 
 /* One table image per parameter group (many small frames share one dictionary: priming its tail once
- * instead of once per frame is what the reference's CDict does on the CPU, zstd_compress.c:5477). */
-static size_t zb_buildDictImages(ZSTD_CCtx* c, ZbPlan& P, const u8* d_dictEnd, size_t dictTail, cudaStream_t stream)
+ * instead of once per frame is what the reference's CDict does on the CPU, zstd_compress.c:5477).
+ * A ZSTD_CDict keeps its images across calls. */
+static size_t zb_buildDictImages(ZSTD_CCtx* c, ZbPlan& P, const ZSTD_CDict* cdictC, const u8* d_dictEnd, size_t dictTail, cudaStream_t stream)
 {
-    if (!d_dictEnd || dictTail < 8 || P.groups.size() > ZB_MAX_IMAGES) return 0;
-    std::vector<ZbBlock> pb(P.groups.size());
-    for (size_t g = 0; g < P.groups.size(); g++) {
-        ZbParams const& prm = P.groups[g].prm;
-        ZbBlock b; memset(&b, 0, sizeof(b));
-        b.histLen = (u32)dictTail; b.size = 0; b.flags = ZB_FLAG_DICT;
-        b.insPhase = (u32)((prm.insPeriod - dictTail % prm.insPeriod) % prm.insPeriod);
-        pb[g] = b;
+    if (!d_dictEnd || dictTail < 8) return 0;
+    ZSTD_CDict* const cd = const_cast<ZSTD_CDict*>(cdictC);
+    if (!cd && P.groups.size() > ZB_MAX_IMAGES) return 0;
+    u8* const images = cd ? cd->d_image : c->d_image;
+    ZbBlock* const dblk = cd ? cd->d_dictBlock : c->d_dictBlock;
+    std::unique_lock<std::mutex> g;
+    if (cd) g = std::unique_lock<std::mutex>(*cd->lock);
+    u32 next = cd ? cd->nbImages : 0u;
+    bool built = false;
+    for (size_t gi = 0; gi < P.groups.size(); gi++) {
+        ZbParams const& prm = P.groups[gi].prm;
+        u32 slot = ~0u;
+        if (cd) for (u32 i = 0; i < cd->nbImages; i++) if (memcmp(&cd->imagePrm[i], &prm, sizeof(prm)) == 0) slot = i;
+        if (slot == ~0u) {
+            if (next >= ZB_MAX_IMAGES) continue;                         /* no room: this group primes per block */
+            slot = next++;
+            ZbBlock b; memset(&b, 0, sizeof(b));
+            b.histLen = (u32)dictTail; b.size = 0; b.flags = ZB_FLAG_DICT;
+            b.insPhase = (u32)((prm.insPeriod - dictTail % prm.insPeriod) % prm.insPeriod);
+            CK(cudaMemcpyAsync(dblk + slot, &b, sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));      /* pageable source: staged before the call returns */
+            CK(zb_launch_dict_image(d_dictEnd, dblk + slot, &prm, images + (size_t)slot * ZB_IMAGE_BYTES, stream));
+            if (cd) { cd->imagePrm[slot] = prm; cd->nbImages = next; built = true; }
+        }
+        P.groups[gi].image = images + (size_t)slot * ZB_IMAGE_BYTES;
     }
-    CK(cudaMemcpyAsync(c->d_dictBlock, pb.data(), pb.size() * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
-    for (size_t g = 0; g < P.groups.size(); g++) {
-        CK(zb_launch_dict_image(d_dictEnd, c->d_dictBlock + g, &P.groups[g].prm, c->d_image + g * ZB_IMAGE_BYTES, stream));
-        P.groups[g].imageReady = true;
-    }
+    if (built) CK(cudaStreamSynchronize(stream));                        /* a cached image must be complete before another context reads it */
     return 0;
 }
 
@@ -349,7 +409,7 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
             if (lo >= hi) continue;
             size_t const s = slot0 + (lo - b0);
             if (phase == 0) {
-                CK(zb_launch_match(d_src, d_dictEnd, (d_dictEnd && G.imageReady) ? c->d_image + g * ZB_IMAGE_BYTES : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
+                CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
                                    G.prm.strategy == 2 ? c->d_dist2 + s * ZB_BLOCK_MAX : (u16*)0, c->d_seqs + s * ZB_SEQ_STRIDE,
                                    c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
                 *launches += (G.prm.strategy == 2) ? 3 : 2;
@@ -370,10 +430,10 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
 /* ------------------------------------------------------------------ core: frames already in device memory (one wave) */
 static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacity, const u8* d_src,
                                       const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
-                                      const void* dict, size_t dictSize, size_t* cSizes, int level, cudaStream_t stream)
+                                      const void* dict, size_t dictSize, const ZSTD_CDict* cdict, size_t* cSizes, int level, cudaStream_t stream)
 {
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
-    {   size_t const e = zb_prepareDict(c, dict, dictSize, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
     zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
@@ -385,9 +445,9 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
     unsigned launches = 0;
-    if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
+    if (nbFrames >= 8 || cdict) { size_t const e = zb_buildDictImages(c, P, cdict, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
     {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
-    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, NULL, d_dst, dstCapacity, stream));
+    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
     if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
     CK(cudaEventRecord(c->evKEnd, stream));
@@ -417,7 +477,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
 
 static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, const u8* src,
                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
-                                     const void* dict, size_t dictSize, size_t* cSizes, int level, bool deviceMemory)
+                                     const void* dict, size_t dictSize, const ZSTD_CDict* cdict, size_t* cSizes, int level, bool deviceMemory)
 {
     u32 const ZB_WAVE_BLOCKS = deviceMemory ? c->devWaveBlocks : c->hostWaveBlocks;
     u32 const ZB_WAVE_SLOTS = deviceMemory ? c->waveSlots : c->hostWaveSlots;
@@ -430,9 +490,13 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         return 0;
     };
     cudaStream_t sCopy, sD2H = (cudaStream_t)0;
+    if (deviceMemory) {                                           /* creation order as measured: wave streams first */
+        cudaStream_t t;
+        for (u32 i = 0; i < ZB_WAVE_SLOTS; i++) { size_t const e = getStream(i, &t); if (zb_isErr(e)) return e; }
+    }
     {   size_t const e = getStream(ZB_WAVE_SLOTS_MAX, &sCopy); if (zb_isErr(e)) return e; }
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
-    {   size_t const e = zb_prepareDict(c, dict, dictSize, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
     zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
@@ -469,12 +533,13 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     bool const download = !deviceMemory;
     bool const timeline = getenv("ZSTDB200_TIMELINE") != NULL;      /* development: print each wave's milestones */
     unsigned const evFlags = timeline ? cudaEventDefault : cudaEventDisableTiming;
-    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evD2H(timeline ? nbWaves : 0);
+    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evSize(nbWaves), evD2H(timeline ? nbWaves : 0);
     std::vector<double> hostDone(nbWaves, 0.0);
     double const hostT0 = zb_now();
     for (u32 w = 0; w < nbWaves; w++) {
         CK(cudaEventCreateWithFlags(&evH2D[w], evFlags));
         CK(cudaEventCreateWithFlags(&evStitch[w], evFlags));
+        CK(cudaEventCreateWithFlags(&evSize[w], cudaEventDisableTiming));
         if (timeline) CK(cudaEventCreate(&evD2H[w]));
     }
     unsigned launches = 0;
@@ -482,7 +547,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     CK(cudaEventRecord(c->evStart, sCopy));
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, sCopy));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, sCopy));
-    if (nbFrames >= 8) { size_t const e = zb_buildDictImages(c, P, d_dictEnd, dictTail, sCopy); if (zb_isErr(e)) return e; }
+    if (nbFrames >= 8 || cdict) { size_t const e = zb_buildDictImages(c, P, cdict, d_dictEnd, dictTail, sCopy); if (zb_isErr(e)) return e; }
     cudaStream_t lastStream = sCopy;
     for (u32 w = 0; w < nbWaves && !err; w++) {
         u32 const b0 = wb[w], b1 = wb[w + 1];
@@ -500,16 +565,22 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
         size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
         CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
-                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, c->h_totalsDev + w, d_out, outCap, st));
+                            c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, d_out, outCap, st));
         launches += 2;
         CK(cudaEventRecord(evStitch[w], st));
+        /* the wave's size goes to the host behind the event the next wave's stitch waits for: a store into mapped
+         * host memory from inside the scan kernel would add a PCIe round trip to every link of that chain */
+        if (download || timeline || w + 1 == nbWaves) {
+            CK(cudaMemcpyAsync(c->h_totals + w, c->d_totals + w, sizeof(u64), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(evSize[w], st));
+        }
     }
     double const hostEnq = zb_now() - hostT0;
     u64 prev = 0, total = 0;
     if (download || timeline) {
         /* drain: as each wave's size becomes known, ship its bytes */
         for (u32 w = 0; w < nbWaves && !err; w++) {
-            CK(cudaEventSynchronize(evStitch[w]));
+            CK(cudaEventSynchronize(evSize[w]));
             hostDone[w] = zb_now() - hostT0;
             total = c->h_totals[w];
             if (download && total <= outCap && total > prev) CK(cudaMemcpyAsync(dst + prev, d_out + prev, total - prev, cudaMemcpyDeviceToHost, sD2H));
@@ -542,7 +613,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
             cudaEventDestroy(evD2H[w]);
         }
     }
-    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); }
+    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); cudaEventDestroy(evSize[w]); }
     if (err) return err;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; c->stats.kernel_ms = ms; }
     c->stats.launches = launches; c->stats.nbBlocks = nbBlocks;
@@ -551,10 +622,10 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     return (size_t)total;
 }
 
-extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
-                                          const void* src, const size_t* frameOffsets, const size_t* frameSizes,
-                                          size_t nbFrames, const void* dict, size_t dictSize,
-                                          size_t* cSizes, int level, int deviceMemory, void* streamv)
+static size_t zb_compressFramesAny(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
+                                   const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                   size_t nbFrames, const void* dict, size_t dictSize, const ZSTD_CDict* cdict,
+                                   size_t* cSizes, int level, int deviceMemory, void* streamv)
 {
     if (!c) return ZB_ERR(ZB_error_GENERIC);
     if (nbFrames == 0) return 0;
@@ -567,13 +638,89 @@ extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCap
          * per-kernel event times are meaningful */
         size_t nb = 0; for (size_t f = 0; f < nbFrames; f++) nb += (frameSizes[f] + ZB_BLOCK_MAX - 1) / ZB_BLOCK_MAX;
         if (!streamv && c->devWaveBlocks && nb >= 2u * c->devWaveBlocks)
-            return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, true);
+            return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, true);
         cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
-        size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, stream);
+        size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, stream);
         c->stats.total_ms = c->stats.kernel_ms;
         return r;
     }
-    return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cSizes, level, false);
+    return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, false);
+}
+
+extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
+                                          const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                          size_t nbFrames, const void* dict, size_t dictSize,
+                                          size_t* cSizes, int level, int deviceMemory, void* streamv)
+{
+    return zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, dict, dictSize, NULL, cSizes, level, deviceMemory, streamv);
+}
+
+extern "C" size_t ZSTDB200_compressFrames_usingCDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
+                                                     const void* src, const size_t* frameOffsets, const size_t* frameSizes,
+                                                     size_t nbFrames, const ZSTD_CDict* cdict,
+                                                     size_t* cSizes, int deviceMemory, void* streamv)
+{
+    if (!cdict) return ZB_ERR(ZB_error_dictionary_wrong);                        /* zstd_compress.c:5753 */
+    return zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, NULL, 0, cdict, cSizes, cdict->level, deviceMemory, streamv);
+}
+
+/* ------------------------------------------------------------------ digested dictionaries (lib/zstd.h:967-995) */
+extern "C" ZSTD_CDict* ZSTD_createCDict(const void* dict, size_t dictSize, int level)     /* zstd_compress.c:5633 */
+{
+    ZSTD_CDict* cd = (ZSTD_CDict*)calloc(1, sizeof(ZSTD_CDict));
+    if (!cd) return NULL;
+    cd->level = level == 0 ? 3 : level;                                          /* ZSTD_CLEVEL_DEFAULT, :5640 */
+    cd->device = -1;
+    cd->size = dict ? dictSize : 0;
+    cd->content = (u8*)malloc(cd->size ? cd->size : 1);
+    cd->lock = new (std::nothrow) std::mutex();
+    if (!cd->content || !cd->lock) { free(cd->content); delete cd->lock; free(cd); return NULL; }
+    if (cd->size) memcpy(cd->content, dict, cd->size);                           /* ZSTD_dlm_byCopy */
+    if (cd->size >= 8) {
+        size_t const off = zb_loadDictionary(&cd->entropy, cd->content, cd->size);
+        if (zb_isErr(off)) { free(cd->content); delete cd->lock; free(cd); return NULL; }   /* corrupted entropy tables: creation fails (:5600-5612) */
+        cd->contentOff = off;
+        size_t const contentSize = cd->size - off;
+        cd->tail = contentSize < ZB_PRIME_BYTES ? contentSize : ZB_PRIME_BYTES;
+    }
+    return cd;
+}
+
+extern "C" size_t ZSTD_freeCDict(ZSTD_CDict* cd)                                            /* accepts NULL, zstd_compress.c:5655 */
+{
+    if (!cd) return 0;
+    if (cd->device >= 0) {
+        int prev = -1; cudaGetDevice(&prev);
+        cudaSetDevice(cd->device);
+        cudaFree(cd->d_dict); cudaFree(cd->d_de); cudaFree(cd->d_image); cudaFree(cd->d_dictBlock);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    free(cd->content); delete cd->lock; free(cd);
+    return 0;
+}
+
+extern "C" unsigned ZSTD_getDictID_fromCDict(const ZSTD_CDict* cd)                           /* zstd_compress.c:5738 */
+{
+    return (cd && cd->size >= 8 && cd->entropy.present) ? cd->entropy.dictID : 0u;
+}
+
+extern "C" unsigned ZSTD_getDictID_fromDict(const void* dict, size_t dictSize)              /* lib/decompress/zstd_ddict.c:227, zstd.h:1105 */
+{
+    const u8* d = (const u8*)dict;
+    if (!d || dictSize < 8) return 0;
+    if ((d[0] | (d[1] << 8) | (d[2] << 16) | ((u32)d[3] << 24)) != 0xEC30A437u) return 0;  /* ZSTD_MAGIC_DICTIONARY */
+    return d[4] | (d[5] << 8) | (d[6] << 16) | ((u32)d[7] << 24);
+}
+
+extern "C" size_t ZSTD_compress_usingCDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                                           const ZSTD_CDict* cdict)                          /* zstd_compress.c:5836 */
+{
+    size_t const off = 0;
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (!cdict) return ZB_ERR(ZB_error_dictionary_wrong);
+    if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
+    if (dstCapacity < 18) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    return zb_compressFramesAny(c, dst, dstCapacity, src, &off, &srcSize, 1, NULL, 0, cdict, NULL, cdict->level, 0, NULL);
 }
 
 extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity,

@@ -32,7 +32,6 @@ typedef uint64_t u64;
 #define ZB_FLAG_FIRST 1u       /* first block of its frame */
 #define ZB_FLAG_LAST  2u       /* last block of its frame  */
 #define ZB_FLAG_DICT  4u       /* its history (histLen bytes) is the tail of the call's dictionary content */
-#define ZB_FLAG_FRONTSAFE 8u   /* at least 4 readable input bytes lie in front of the oldest visible byte (same buffer) */
 
 /* error codes = lib/zstd_errors.h:64-101 */
 #define ZB_ERR(code) ((size_t)-(long)(code))

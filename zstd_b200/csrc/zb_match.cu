@@ -302,15 +302,19 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * step acceleration :234,:342-347).  Hit priority per lane: repcode-2 (lane 0, directly after a match,
  * :410-420), repcode-1 (:281-297), table candidate with 4-byte check (:102-141).  Lowest lane wins.
  * ---------------------------------------------------------------------------------------------- */
+#ifndef PARSE_WARPS
 #define PARSE_WARPS 4
+#endif
 #ifndef PARSE_MIN_CTAS
-#define PARSE_MIN_CTAS 16          /* 64 warps per SM = 32 registers (a few spills): measured 3.7 % faster than 48 warps at 40 */
+#define PARSE_MIN_CTAS 12          /* 48 warps per SM at 40 registers.  16 (= 32 registers, 64 warps) is 3.7 % faster when the parse
+                                    * runs alone, but fills every warp slot: the candidate walk of the next wave no longer fits beside
+                                    * it and a whole device-resident call gets 4 % slower (profiles/r1_history.md) */
 #endif
 #ifndef PARSE_PF_AHEAD
 #define PARSE_PF_AHEAD 2048u
 #endif
 template <bool DICT>
-__global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? 10 : PARSE_MIN_CTAS)
+__global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
 zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
                 const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
@@ -339,7 +343,6 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
     u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
     if (DICT && (bd.flags & ZB_FLAG_DICT)) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
     u32 pf = bs;                                             /* input and dist[] below this position are on their way to L2 */
-    bool const frontSafe = (bd.flags & ZB_FLAG_FRONTSAFE) != 0u;
 
     while (ip + 8u <= be) {
         /* the warp consumes its block front to back but every step waits for its loads: keep the next
@@ -364,14 +367,8 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         /* dist[] only holds candidates K1a has already verified (4 equal bytes), so a step needs no random
          * load: the current window and the repcode windows are contiguous across lanes */
         u32 pre, cur, pre2, cur2;
-        if (!DICT && frontSafe) {                            /* all blocks but a buffer's first: the 4 bytes in front of any position are readable */
-            u64 const w = zb_ld64w3(base + pp - 4u);
-            u64 const w2 = zb_ld64w3(base + (v2 ? pp - rep1 : pp) - 4u);
-            pre = (u32)w; cur = (u32)(w >> 32); pre2 = (u32)w2; cur2 = (u32)(w2 >> 32);
-        } else {
-            zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
-            zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
-        }
+        zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
+        zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
         u32 cur3 = ~cur;
         if (ip == anchor && rep2 != 0u) cur3 = zb_seg_ld32<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
         u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));

@@ -36,7 +36,7 @@ __device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, 
 __global__ void __launch_bounds__(SCAN_THREADS)
 zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames,
                      const ZbBlockMeta* __restrict__ meta, u64* __restrict__ outOffsets,
-                     const u64* __restrict__ basePtr, u64* __restrict__ total, u64* __restrict__ hostTotal)
+                     const u64* __restrict__ basePtr, u64* __restrict__ total)
 {
     u64 const base = basePtr ? *basePtr : 0;      /* bytes produced by the waves before this one */
     __shared__ u64 part[SCAN_THREADS];
@@ -67,11 +67,7 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
         outOffsets[i] = run;
         run += sz;
     }
-    if (tid == SCAN_THREADS - 1) {
-        u64 const t = base + part[SCAN_THREADS - 1];
-        outOffsets[nbBlocks] = t; *total = t;
-        if (hostTotal) *hostTotal = t;                /* mapped pinned memory: the host reads it after the stream's next event */
-    }
+    if (tid == SCAN_THREADS - 1) { outOffsets[nbBlocks] = base + part[SCAN_THREADS - 1]; *total = base + part[SCAN_THREADS - 1]; }
 }
 
 /* per-frame compressed sizes from the (final) block offsets */
@@ -137,11 +133,11 @@ zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, c
 
 extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbFrame* d_frames,
                                         const u8* d_body, const ZbBlockMeta* d_meta,
-                                        u64* d_outOffsets, const u64* d_base, u64* d_total, u64* d_hostTotal,
+                                        u64* d_outOffsets, const u64* d_base, u64* d_total,
                                         u8* d_dst, u64 dstCapacity, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, d_meta, d_outOffsets, d_base, d_total, d_hostTotal);
+    zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, d_meta, d_outOffsets, d_base, d_total);
     zb_copy_kernel<<<nbBlocks, COPY_THREADS, 0, stream>>>(d_src, d_blocks, d_frames, d_body, d_meta, d_outOffsets, d_dst, dstCapacity);
     return cudaGetLastError();
 }
