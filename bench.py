@@ -12,6 +12,11 @@ import argparse
 import ctypes
 import json
 import os
+
+# the host path keeps ~10 streams busy (8 wave streams + upload + download): give every one its own hardware
+# queue, else a download can sit behind another wave's kernels (profiles/r1_e2e_timeline.md).  Must be set
+# before the CUDA context exists; INTEGRATION.md tells embedders to do the same.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -46,7 +51,7 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.samples, self.index, self.proc = [], index, None
+        self.samples, self.index, self.proc, self.windows = [], index, None, []
 
     def start(self):
         try:
@@ -58,16 +63,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+            self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Start (or restart) a timed window: only samples taken inside windows are reported."""
+        self.windows.append([time.perf_counter(), None])
+
+    def unmark(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = max([int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()] or [0])
+        inside = [s for t, s in self.samples if any(a <= t <= (b or 1e30) for a, b in self.windows)]
+        sm = sorted(int(s[0]) for s in inside if s and s[0].isdigit())
+        mx = max([int(s[1]) for s in inside if len(s) > 1 and s[1].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for s in inside for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "sampled": "nvidia-smi -lms 20 during the timed device-resident and end-to-end loops"}
 
 
 def ref_lib():
@@ -217,12 +231,13 @@ def run_ours(args):
 
     # ---- device-resident throughput (`value`) ----
     csize = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                     # nvidia-smi needs a moment to start: launch it before the warm-up
     for _ in range(args.warmup):
         csize = step_device()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     t0 = time.perf_counter()
@@ -233,8 +248,8 @@ def run_ours(args):
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
+    sampler.unmark()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = sum(s.launches for s in stats)
     # per-kernel CUDA-event times come from a serial-mode context (one wave, one stream): in the default
     # mode waves on several streams overlap and a kernel's start->end no longer measures that kernel alone
@@ -250,16 +265,23 @@ def run_ours(args):
     sctx.close()
     torch.cuda.synchronize()
 
-    # ---- end to end through the reference-facing C ABI with pinned HOST buffers ----
-    for _ in range(max(1, args.warmup // 2)):
+    # ---- end to end through the reference-facing C ABI with pinned HOST buffers (a context of its own, as an
+    # application that only ever passes host pointers would have) ----
+    got_dev = d_dst[:csize].clone()
+    ctx.close()
+    ctx = zstd_b200.ZSTD_CCtx(device=local)
+    for _ in range(max(3, args.warmup)):
         step_e2e()
     barrier()
+    sampler.mark()
     te0 = time.perf_counter()
     ce = 0
     for _ in range(args.steps):
         ce = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - te0
+    sampler.unmark()
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -271,13 +293,24 @@ def run_ours(args):
         return
 
     # parity spot-check of what was timed (outside the timed region)
-    got = bytes(d_dst[:csize].cpu().numpy())
+    got = bytes(got_dev.cpu().numpy())
+    assert bytes(h_dst[:ce].numpy()) == got, "host-path and device-path frames differ"
     ok_rt = zref.ref_decompress(got, size) == src if zref.have_ref() else None
     hbm, peak_src = peaks()
     value = size * world * args.steps / (ms / 1e3) / 1e9
     e2e = size * world * args.steps / e2e_s / 1e9
     dom = max(("cand_ms", "parse_ms", "literals_ms", "sequences_ms", "stitch_ms"), key=lambda k: kern[k])
     achieved = (size + csize) / (kern[dom] / 1e3) / 1e9
+    # DRAM bytes of that kernel per launch: from the committed ncu capture of this workload (not measured live)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        k = tj["kernels"][dom.replace("_ms", "")]
+        if size == GiB and args.level == 1:
+            traffic, traffic_src = k["dram_read_bytes"] + k["dram_write_bytes"], "profiles/r1_traffic.json (ncu, same workload)"
+    except Exception:
+        pass
     # CPU baseline on this box: reference libzstd, bounded sample
     cpu = None
     if zref.have_ref() and not args.no_cpu:
@@ -301,7 +334,7 @@ def run_ours(args):
                        "size_delta_vs_ref": (round((csize - cpu["ref_compressed_bytes"]) / cpu["ref_compressed_bytes"], 5) if cpu else None)},
             "kernel_ms": dict({k: round(v, 3) for k, v in kern.items()}, mode="serial (ZSTDB200_SERIAL=1): one wave on one stream, CUDA events around each kernel"),
             "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
-                         "frac": round(achieved / hbm, 4), "peak_source": peak_src, "traffic": None,
+                         "frac": round(achieved / hbm, 4), "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": size + csize, "read_only_frac": round(size / (kern[dom] / 1e3) / 1e9 / hbm, 4)},
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": size, "d2h_bytes_per_step": int(ce), "api": "ZSTD_compressCCtx(host pinned src/dst)"},

@@ -65,6 +65,12 @@ def main():
         dbuf = ctypes.create_string_buffer(16 << 10)
         dn = R.ZDICT_trainFromBuffer(dbuf, 16 << 10, src, sizes, 20000)
         run("C5 131072 x 1 KiB records (P50) + 16 KiB ZDICT dictionary, level 1", src, 1, frame_size=rec, dict_bytes=dbuf.raw[:dn], ref_sample=512)
+    if "c5full" in which:                                   # BASELINE config 5 at its full size: 1 Mi records
+        R = zref.ref()
+        rec, nrec = 1024, 1 << 20
+        src = zref.datagen(rec * nrec, 50)
+        d = zref.train_dict(src, rec, 20000, 16 << 10)
+        run("C5 full: 1048576 x 1 KiB records (P50) + 16 KiB ZDICT dictionary, level 1", src, 1, frame_size=rec, dict_bytes=d, ref_sample=512)
 
 
 if __name__ == "__main__":

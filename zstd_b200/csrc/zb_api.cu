@@ -116,7 +116,8 @@ struct ZSTD_CCtx_s {
     int device;
     cudaStream_t stream;
     /* per-block workspace */
-    size_t capBlocks, capFrames, capHeavy, capWaves;
+    size_t capBlocks, capFrames, capWaves;
+    size_t capHeavyBytes[6];       /* meta, seqs, lits, body, dist, dist2 */
     u32 devWaveBlocks;             /* device-memory calls: blocks per wave (0 = always one wave) */
     cudaStream_t waveStream[ZB_WAVE_SLOTS_MAX + 2];
     u32 waveSlots;                 /* waves in flight, device-memory calls */
@@ -124,7 +125,7 @@ struct ZSTD_CCtx_s {
     u32 hostWaveBlocks;            /* host-memory calls: blocks per wave */
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
-    u16* d_dist2; size_t capDist2;                       /* dfast only: short-hash candidate distances */
+    u16* d_dist2;                                        /* dfast only: short-hash candidate distances */
     u64* d_outOffsets; u64* d_frameSizes; u64* d_totals;    /* d_totals[w]: bytes produced up to and including wave w */
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
@@ -190,11 +191,11 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; c->capDist2 = 0; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
     cudaFreeHost(c->h_totals);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
     c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL; c->d_totals = NULL; c->h_totals = NULL;
-    c->capBlocks = 0; c->capFrames = 0; c->capHeavy = 0; c->capWaves = 0;
+    c->capBlocks = 0; c->capFrames = 0; c->capWaves = 0; memset(c->capHeavyBytes, 0, sizeof(c->capHeavyBytes));
 }
 
 extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
@@ -238,23 +239,24 @@ static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size
     }
     return 0;
 }
-static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
+static ZbStrides zb_strides(u32 maxBlock)
 {
-    if (needDist2 && nbSlotBlocks > c->capDist2) {
-        cudaFree(c->d_dist2); c->d_dist2 = NULL; c->capDist2 = 0;
-        CK(cudaMalloc(&c->d_dist2, nbSlotBlocks * (size_t)ZB_BLOCK_MAX * sizeof(u16)));
-        c->capDist2 = nbSlotBlocks;
-    }
-    if (nbSlotBlocks > c->capHeavy) {
-        cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits); cudaFree(c->d_body); cudaFree(c->d_dist);
-        c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL; c->d_body = NULL; c->d_dist = NULL; c->capHeavy = 0;
-        size_t const nb = nbSlotBlocks;
-        CK(cudaMalloc(&c->d_meta, nb * sizeof(ZbBlockMeta)));
-        CK(cudaMalloc(&c->d_seqs, nb * ZB_SEQ_STRIDE * sizeof(u64)));
-        CK(cudaMalloc(&c->d_lits, nb * (size_t)ZB_LIT_STRIDE));
-        CK(cudaMalloc(&c->d_body, nb * (size_t)ZB_BODY_STRIDE));
-        CK(cudaMalloc(&c->d_dist, nb * (size_t)ZB_BLOCK_MAX * sizeof(u16)));
-        c->capHeavy = nb;
+    u32 const M = ((maxBlock < 64u ? 64u : maxBlock) + 63u) & ~63u;
+    ZbStrides sd; sd.dist = M; sd.seq = M / 4u + 8u; sd.lit = M + 256u; sd.body = M + 1024u; sd.state = M / 4u;
+    return sd;
+}
+/* workspace for nbSlotBlocks blocks laid out with the strides `sd` (capacities are kept in bytes) */
+static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides& sd, bool needDist2)
+{
+    size_t const nb = nbSlotBlocks;
+    size_t const need[6] = { nb * sizeof(ZbBlockMeta), nb * sd.seq * sizeof(u64), nb * (size_t)sd.lit, nb * (size_t)sd.body,
+                             nb * (size_t)sd.dist * sizeof(u16), needDist2 ? nb * (size_t)sd.dist * sizeof(u16) : 0 };
+    void** const ptr[6] = { (void**)&c->d_meta, (void**)&c->d_seqs, (void**)&c->d_lits, (void**)&c->d_body, (void**)&c->d_dist, (void**)&c->d_dist2 };
+    for (int i = 0; i < 6; i++) {
+        if (need[i] <= c->capHeavyBytes[i]) continue;
+        cudaFree(*ptr[i]); *ptr[i] = NULL; c->capHeavyBytes[i] = 0;
+        CK(cudaMalloc(ptr[i], need[i] + 256));
+        c->capHeavyBytes[i] = need[i];
     }
     return 0;
 }
@@ -267,13 +269,14 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, bool needDist2)
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
 struct ZbGroup { ZbParams prm; u32 b0, b1; const u8* image; };   /* image: table primed from the dictionary tail, or NULL */
-struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; bool unsupported; };
+struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported; };
 
 static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
                     size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
 {
     P.frames.resize(nbFrames);
     P.unsupported = false;
+    u32 maxBlock = 0;
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
         ZbCParams cp = zb_getCParams(level, fsz, dictSize);
@@ -298,6 +301,7 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
                 b.insPhase = (u32)(back ? (prm.insPeriod - back % prm.insPeriod) % prm.insPeriod : fpos % prm.insPeriod);
                 b.insPhaseLong = prm.insPeriodLong ? (u32)(back ? (prm.insPeriodLong - back % prm.insPeriodLong) % prm.insPeriodLong : fpos % prm.insPeriodLong) : 0u; }
             P.blocks.push_back(b);
+            if (b.size > maxBlock) maxBlock = b.size;
             pos += bsz;
         } while (pos < fsz);
         fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
@@ -305,6 +309,7 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
         if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.image = NULL; P.groups.push_back(g); }
         else P.groups.back().b1 = (u32)P.blocks.size();
     }
+    P.sd = zb_strides(maxBlock);
 }
 
 /* parse + upload the dictionary content tail; returns 0 or an error.  *d_dictEnd = NULL when no dictionary applies */
@@ -409,16 +414,16 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
             if (lo >= hi) continue;
             size_t const s = slot0 + (lo - b0);
             if (phase == 0) {
-                CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, c->d_dist + s * ZB_BLOCK_MAX,
-                                   G.prm.strategy == 2 ? c->d_dist2 + s * ZB_BLOCK_MAX : (u16*)0, c->d_seqs + s * ZB_SEQ_STRIDE,
-                                   c->d_lits + s * ZB_LIT_STRIDE, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
+                CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_dist + s * P.sd.dist,
+                                   G.prm.strategy == 2 ? c->d_dist2 + s * P.sd.dist : (u16*)0, c->d_seqs + s * P.sd.seq,
+                                   c->d_lits + s * P.sd.lit, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
                 *launches += (G.prm.strategy == 2) ? 3 : 2;
             } else if (phase == 1) {
-                CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, c->d_deActive, c->d_lits + s * ZB_LIT_STRIDE, c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
+                CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_deActive, c->d_lits + s * P.sd.lit, c->d_body + s * P.sd.body, c->d_meta + s, stream));
                 *launches += 1;
             } else {
-                CK(zb_launch_sequences(d_src, c->d_blocks + lo, hi - lo, &G.prm, c->d_deActive, c->d_seqs + s * ZB_SEQ_STRIDE, c->d_dist + s * ZB_BLOCK_MAX,
-                                       c->d_body + s * ZB_BODY_STRIDE, c->d_meta + s, stream));
+                CK(zb_launch_sequences(d_src, c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_deActive, c->d_seqs + s * P.sd.seq, c->d_dist + s * P.sd.dist,
+                                       c->d_body + s * P.sd.body, c->d_meta + s, stream));
                 *launches += 1;
             }
         }
@@ -440,14 +445,14 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     u32 const nbBlocks = (u32)P.blocks.size();
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
         bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
-        e = zb_ensureHeavy(c, nbBlocks, d2); if (zb_isErr(e)) return e; }
+        e = zb_ensureHeavy(c, nbBlocks, P.sd, d2); if (zb_isErr(e)) return e; }
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
     unsigned launches = 0;
     if (nbFrames >= 8 || cdict) { size_t const e = zb_buildDictImages(c, P, cdict, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
     {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
-    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
+    CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, P.sd.body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
     if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
     CK(cudaEventRecord(c->evKEnd, stream));
@@ -479,7 +484,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
                                      const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
                                      const void* dict, size_t dictSize, const ZSTD_CDict* cdict, size_t* cSizes, int level, bool deviceMemory)
 {
-    u32 const ZB_WAVE_BLOCKS = deviceMemory ? c->devWaveBlocks : c->hostWaveBlocks;
+    u32 const waveBlocks128 = deviceMemory ? c->devWaveBlocks : c->hostWaveBlocks;       /* wave size in 128 KiB blocks */
     u32 const ZB_WAVE_SLOTS = deviceMemory ? c->waveSlots : c->hostWaveSlots;
     /* streams are created on first use: every stream beyond the hardware queue count (8 by default) shares a
      * queue with another one, and a download queued behind another wave's kernels stalls the whole pipeline
@@ -501,6 +506,8 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
+    /* a wave is sized in bytes of input (and of workspace): calls made of small blocks get proportionally more blocks per wave */
+    u32 const ZB_WAVE_BLOCKS = (u32)((u64)waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist) > (1u << 22) ? (1u << 22) : waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist));
     /* wave boundaries.  Host path: the call ends when the LAST wave has gone through every kernel, so the
      * final waves shrink (1/2, 1/4, 1/8 of a wave): less work behind the last upload. */
     std::vector<u32> wb;
@@ -521,7 +528,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     size_t const outCap = deviceMemory ? dstCapacity : (dstCapacity < bound ? dstCapacity : bound);
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves); if (zb_isErr(e)) return e;
         bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
-        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks), d2); if (zb_isErr(e)) return e; }
+        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks), P.sd, d2); if (zb_isErr(e)) return e; }
     u8* d_in; u8* d_out;
     if (deviceMemory) { d_in = (u8*)src; d_out = dst; }
     else {
@@ -564,7 +571,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         if (err) break;
         if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
         size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
-        CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * ZB_BODY_STRIDE, c->d_meta + s0,
+        CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * P.sd.body, P.sd.body, c->d_meta + s0,
                             c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, d_out, outCap, st));
         launches += 2;
         CK(cudaEventRecord(evStitch[w], st));
@@ -636,8 +643,14 @@ static size_t zb_compressFramesAny(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
          * bound candidate walk of one wave overlaps the register-only parse / entropy kernels of another;
          * ZSTDB200_SERIAL=1 (or a caller-supplied stream) keeps one wave on one stream — the mode whose
          * per-kernel event times are meaningful */
-        size_t nb = 0; for (size_t f = 0; f < nbFrames; f++) nb += (frameSizes[f] + ZB_BLOCK_MAX - 1) / ZB_BLOCK_MAX;
-        if (!streamv && c->devWaveBlocks && nb >= 2u * c->devWaveBlocks)
+        u64 bytes = 0, nb = 0; u32 maxBlock = 0;
+        for (size_t f = 0; f < nbFrames; f++) {
+            bytes += frameSizes[f]; nb += (frameSizes[f] + ZB_BLOCK_MAX - 1) / ZB_BLOCK_MAX + (frameSizes[f] == 0);
+            u32 const m = frameSizes[f] < ZB_BLOCK_MAX ? (u32)frameSizes[f] : ZB_BLOCK_MAX; if (m > maxBlock) maxBlock = m;
+        }
+        ZbStrides const sd = zb_strides(maxBlock);
+        u64 const wsBytes = nb * ((u64)sd.dist * 2u + (u64)sd.seq * 8u + sd.lit + sd.body);        /* one-wave workspace */
+        if (!streamv && c->devWaveBlocks && (bytes >= 2ull * c->devWaveBlocks * ZB_BLOCK_MAX || wsBytes > (12ull << 30)))
             return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, true);
         cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
         size_t const r = zb_compressFramesDevice(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, stream);

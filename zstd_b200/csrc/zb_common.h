@@ -116,4 +116,14 @@ typedef struct {
     u32 startRep[2];   /* repcodes a ZB_FLAG_DICT block starts with (zstd-format dictionary), 0 = invalid */
 } ZbParams;
 
+/* Per-block strides of the workspace arrays of one call, derived from its largest block (M = that size
+ * rounded up to 64): 128 KiB blocks use the ZB_*_STRIDE values above, a call of 1 KiB records 1/128 of them. */
+typedef struct {
+    u32 dist;          /* u16 per block : candidate distances; K3 reuses the area for 3 x state records */
+    u32 seq;           /* u64 per block : packed sequences */
+    u32 lit;           /* bytes per block : literal bytes (multiple of 16) */
+    u32 body;          /* bytes per block : compressed block body staging (multiple of 16) */
+    u32 state;         /* u16 per FSE stream per block inside the dist area (3 * state <= dist) */
+} ZbStrides;
+
 #endif

@@ -9,13 +9,14 @@ extern "C" {
 #endif
 
 /* K1: match-finder = K1a candidate table walk + K1b greedy parse.  One warp per block each.
- * d_dist: ZB_BLOCK_MAX u16 per block (dead after this call; K3 reuses it for the FSE state records);
+ * Per-block workspace strides come in `sd` (ZbStrides, derived from the call's largest block).
+ * d_dist: sd->dist u16 per block (dead after this call; K3 reuses it for the FSE state records);
  * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates).
  * d_dictEnd: one past the dictionary content in device memory (NULL = no dictionary); blocks flagged
  * ZB_FLAG_DICT take their histLen bytes of history from in front of it.  d_image (may be NULL): table
  * already primed from that dictionary tail by zb_launch_dict_image (same ZbParams), 3 << hashLog bytes. */
 cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream);
-cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd,
                             u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
 
 /* host: parse a dictionary (zb_dict.cu).  Returns the content offset, 0 for raw content, or an error code */
@@ -23,11 +24,11 @@ size_t zb_loadDictionary(ZbDictEntropy* de, const u8* dict, size_t dictSize);
 
 /* K2: literals section (histogram, Huffman table, 1/4-stream encode).  One CTA per block.
  * d_de (may be NULL): dictionary entropy state used by ZB_FLAG_DICT blocks. */
-cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
+cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd, const ZbDictEntropy* d_de,
                                const u8* d_lits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
 
 /* K3: sequences section (codes, histograms, FSE tables, tANS bit-stream) + block-type decision. */
-cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
+cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd, const ZbDictEntropy* d_de,
                                 const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream);
 
 /* K4: stitch — per-block output sizes -> exclusive scan -> frame/block headers + payload copy, for
@@ -35,7 +36,7 @@ cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nb
  * d_outOffsets gets nbBlocks+1 absolute offsets, starting at *d_base (NULL = 0); *d_total receives
  * the running total after this wave (even past dstCapacity: nothing is written past dst+dstCapacity). */
 cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbFrame* d_frames,
-                             const u8* d_body, const ZbBlockMeta* d_meta,
+                             const u8* d_body, u32 bodyStride, const ZbBlockMeta* d_meta,
                              u64* d_outOffsets, const u64* d_base, u64* d_total,
                              u8* d_dst, u64 dstCapacity, cudaStream_t stream);
 cudaError_t zb_launch_frame_sizes(const ZbFrame* d_frames, u32 nbFrames, const u64* d_outOffsets,

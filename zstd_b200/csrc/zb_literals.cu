@@ -92,7 +92,7 @@ __device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ li
 }
 
 __global__ void __launch_bounds__(LIT_THREADS)
-zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDictEntropy* __restrict__ de,
+zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, const ZbDictEntropy* __restrict__ de,
                    const u8* __restrict__ lits, u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
     __shared__ u32 whist[LIT_WARPS][256];
@@ -110,8 +110,8 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDic
     ZbBlockMeta const m = meta[b];
     if (m.forceRaw) return;
     u32 const n = m.litSize;
-    const u8* const lit = lits + (size_t)b * ZB_LIT_STRIDE;
-    u8* const out = body + (size_t)b * ZB_BODY_STRIDE;
+    const u8* const lit = lits + (size_t)b * sd.lit;
+    u8* const out = body + (size_t)b * sd.body;
     enum { MODE_RAW = 0, MODE_RLE = 1, MODE_HUF = 2 };
 
     /* ---------------- decisions (zstd_compress_literals.c:129-191, huf_compress.c:1359-1420) ----------------
@@ -279,10 +279,10 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDic
     }
 }
 
-extern "C" cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
+extern "C" cudaError_t zb_launch_literals(const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd, const ZbDictEntropy* d_de,
                                           const u8* d_lits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_literals_kernel<<<nbBlocks, LIT_THREADS, 0, stream>>>(d_blocks, *prm, d_de, d_lits, d_body, d_meta);
+    zb_literals_kernel<<<nbBlocks, LIT_THREADS, 0, stream>>>(d_blocks, *prm, *sd, d_de, d_lits, d_body, d_meta);
     return cudaGetLastError();
 }

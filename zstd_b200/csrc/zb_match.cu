@@ -140,7 +140,7 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
 
 template <int MLS>
 __global__ void __launch_bounds__(32)
-zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, u16* __restrict__ dist,
+zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, u16* __restrict__ dist,
                const u8* __restrict__ imageIn, u8* __restrict__ imageOut)
 {
     __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
@@ -153,7 +153,7 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     bool const buildImage = imageOut != nullptr;
     if (buildImage) bd.size = 0;
     if (!buildImage && bd.size < 7u) return;                      /* zstd_compress.c:3216 : block goes out raw */
-    u16* const mydist = dist + (size_t)blockIdx.x * ZB_BLOCK_MAX;
+    u16* const mydist = dist + (size_t)blockIdx.x * sd.dist;
     const u8* const base = buildImage ? dictEnd - bd.histLen : src + bd.srcOff - bd.histLen;   /* rel position 0 = oldest visible byte */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     bool const fromImage = imageIn != nullptr && (bd.flags & ZB_FLAG_DICT) && bd.histLen >= 8u;
@@ -310,21 +310,27 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
                                     * runs alone, but fills every warp slot: the candidate walk of the next wave no longer fits beside
                                     * it and a whole device-resident call gets 4 % slower (profiles/r1_history.md) */
 #endif
+#ifndef PARSE_PF_INPUT
+#define PARSE_PF_INPUT 1
+#endif
+#ifndef PARSE_PF_DIST
+#define PARSE_PF_DIST 1
+#endif
 #ifndef PARSE_PF_AHEAD
-#define PARSE_PF_AHEAD 2048u
+#define PARSE_PF_AHEAD 512u            /* bytes: ~20 us of parsing; further ahead the lines are evicted from L2 before use */
 #endif
 template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
-zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
+zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
                 const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
-    u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
-    u8*  const mylit = lits + (size_t)b * ZB_LIT_STRIDE;
-    const u16* const mydist = dist + (size_t)b * ZB_BLOCK_MAX;
+    u64* const myseq = seqs + (size_t)b * sd.seq;
+    u8*  const mylit = lits + (size_t)b * sd.lit;
+    const u16* const mydist = dist + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;          /* base + rel addresses the frame's own bytes */
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
@@ -350,9 +356,13 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         if (ip + PARSE_PF_AHEAD > pf && pf < be) {
             u32 const a = pf + 128u * lane;
             if (a < be) {
+#if PARSE_PF_INPUT
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
+#endif
+#if PARSE_PF_DIST
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs)));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs) + 64));
+#endif
             }
             pf += 128u * 32u;
         }
@@ -444,7 +454,7 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
  * winning lane's bytes are checked while the match is extended, a false positive drops out.
  * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
-zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm,
+zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
                       const u16* __restrict__ distLong, const u16* __restrict__ distShort,
                       u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
@@ -452,10 +462,10 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
-    u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
-    u8*  const mylit = lits + (size_t)b * ZB_LIT_STRIDE;
-    const u16* const dLp = distLong + (size_t)b * ZB_BLOCK_MAX;
-    const u16* const dSp = distShort + (size_t)b * ZB_BLOCK_MAX;
+    u64* const myseq = seqs + (size_t)b * sd.seq;
+    u8*  const mylit = lits + (size_t)b * sd.lit;
+    const u16* const dLp = distLong + (size_t)b * sd.dist;
+    const u16* const dSp = distShort + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;
     u32 const bs = bd.histLen, be = bd.histLen + bd.size;
     ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
@@ -555,7 +565,7 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     }
 }
 
-static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, u16* d_dist,
+static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, const ZbStrides& sd, u16* d_dist,
                            const u8* d_imageIn, u8* d_imageOut, cudaStream_t stream)
 {
     size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
@@ -569,38 +579,40 @@ static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* 
         optin = true;
     }
     switch (prm.mls) {
-    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
-    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
-    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
-    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
-    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, d_dist, d_imageIn, d_imageOut); break;
+    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
+    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
+    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
+    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
+    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
     }
 }
 
 /* one-warp launch that primes a table from the dictionary tail and stores it (positions + tags) in d_image */
 extern "C" cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream)
 {
-    zb_launch_cand(nullptr, d_dictEnd, d_dictBlock, 1, *prm, nullptr, nullptr, d_image, stream);
+    ZbStrides sd; sd.dist = ZB_BLOCK_MAX; sd.seq = ZB_SEQ_STRIDE; sd.lit = ZB_LIT_STRIDE; sd.body = ZB_BODY_STRIDE; sd.state = ZB_STATE_STRIDE;   /* unused: no block is walked */
+    zb_launch_cand(nullptr, d_dictEnd, d_dictBlock, 1, *prm, sd, nullptr, nullptr, d_image, stream);
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm,
+extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sdp,
                                        u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
+    ZbStrides const sd = *sdp;
     u32 const grid = (nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS;
     if (prm->strategy == 2) {
         /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
         ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, d_dist, nullptr, nullptr, stream);
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist2, nullptr, nullptr, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, sd, d_dist, nullptr, nullptr, stream);
+        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist2, nullptr, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
-        zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, d_dist, d_dist2, d_seqs, d_lits, d_meta);
+        zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_lits, d_meta);
     } else {
-        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, d_image, nullptr, stream);
+        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_image, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
-        if (d_dictEnd) zb_parse_kernel<true><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
-        else           zb_parse_kernel<false><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, d_dist, d_seqs, d_lits, d_meta);
+        if (d_dictEnd) zb_parse_kernel<true><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta);
+        else           zb_parse_kernel<false><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta);
     }
     return cudaGetLastError();
 }

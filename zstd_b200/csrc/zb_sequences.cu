@@ -97,7 +97,7 @@ struct ZbdStreamWork {
 };
 
 __global__ void __launch_bounds__(SEQ_THREADS)
-zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, const ZbDictEntropy* __restrict__ de,
+zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, const ZbDictEntropy* __restrict__ de,
                     const u64* __restrict__ seqs, u16* __restrict__ stateBits,
                     u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
@@ -113,9 +113,9 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     ZbBlock const bd = blocks[b];
     if (m.forceRaw) return;
     u32 const nbSeq = m.nbSeq;
-    const u64* const myseq = seqs + (size_t)b * ZB_SEQ_STRIDE;
-    u16* const myst = stateBits + (size_t)b * ZB_BLOCK_MAX;       /* the block's (dead) candidate-distance area */
-    u8* const out = body + (size_t)b * ZB_BODY_STRIDE;
+    const u64* const myseq = seqs + (size_t)b * sd.seq;
+    u16* const myst = stateBits + (size_t)b * sd.dist;       /* the block's (dead) candidate-distance area */
+    u8* const out = body + (size_t)b * sd.body;
     u32 op = m.litSecSize;
 
     /* nbSeq header, zstd_compress.c:2937-2947 */
@@ -195,7 +195,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             u32 const st = tid >> 5;
             bool const chain = ((tid & 31u) == 0) && tid < 96u;
             const ZbdFseCTable* const t = &ct[st < 3u ? st : 0u];
-            u16* const rec = myst + (size_t)(st < 3u ? st : 0u) * ZB_STATE_STRIDE;
+            u16* const rec = myst + (size_t)(st < 3u ? st : 0u) * sd.state;
             u32 const nbTiles = (nbSeq + SEQ_TILE - 1u) / SEQ_TILE;
             for (u32 tile = nbTiles; tile-- > 0; ) {
                 u32 const t0 = tile * SEQ_TILE, t1 = min(t0 + SEQ_TILE, nbSeq);
@@ -237,7 +237,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         for (u32 i = cBeg; i < cEnd; i++) {
             ZbdSeq const s = zbd_unpack(myseq[i]);
             bits += c_LL_bits[s.llc] + c_ML_bits[s.mlc] + s.ofc;
-            if (i + 1u < nbSeq) bits += (myst[i] >> 12) + (myst[ZB_STATE_STRIDE + i] >> 12) + (myst[2u * ZB_STATE_STRIDE + i] >> 12);
+            if (i + 1u < nbSeq) bits += (myst[i] >> 12) + (myst[sd.state + i] >> 12) + (myst[2u * sd.state + i] >> 12);
         }
         chunkBits[tid] = bits;
         __syncthreads();
@@ -250,8 +250,8 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         __syncthreads();
         u32 const streamSize = sh_streamSize;
         cSize = hdrEnd + streamSize;
-        /* the body staging area is ZB_BODY_STRIDE bytes; a block that large is emitted raw anyway */
-        bool const fits = (cSize + 16u <= ZB_BODY_STRIDE);
+        /* the body staging area is sd.body bytes; a block that large is emitted raw anyway */
+        bool const fits = (cSize + 16u <= sd.body);
         if (fits) {
             /* zero the bit-stream words (the first may share bytes with the headers: keep those) */
             u32 const w0 = hdrEnd >> 2, w1 = (cSize + 3u) >> 2;
@@ -268,7 +268,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             for (u32 i = cEnd; i-- > cBeg; ) {                 /* last sequence first, zstd_compress_sequences.c:311-370 */
                 ZbdSeq const s = zbd_unpack(myseq[i]);
                 if (i + 1u < nbSeq) {
-                    u32 const rOF = myst[ZB_STATE_STRIDE + i], rML = myst[2u * ZB_STATE_STRIDE + i], rLL = myst[i];
+                    u32 const rOF = myst[sd.state + i], rML = myst[2u * sd.state + i], rLL = myst[i];
                     zbd_pw_add(&pw, rOF & 0xFFFu, rOF >> 12);
                     zbd_pw_add(&pw, rML & 0xFFFu, rML >> 12);
                     zbd_pw_add(&pw, rLL & 0xFFFu, rLL >> 12);
@@ -310,10 +310,10 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     }
 }
 
-extern "C" cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbDictEntropy* d_de,
+extern "C" cudaError_t zb_launch_sequences(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd, const ZbDictEntropy* d_de,
                                            const u64* d_seqs, u16* d_stateBits, u8* d_body, ZbBlockMeta* d_meta, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
-    zb_sequences_kernel<<<nbBlocks, SEQ_THREADS, 0, stream>>>(d_src, d_blocks, *prm, d_de, d_seqs, d_stateBits, d_body, d_meta);
+    zb_sequences_kernel<<<nbBlocks, SEQ_THREADS, 0, stream>>>(d_src, d_blocks, *prm, *sd, d_de, d_seqs, d_stateBits, d_body, d_meta);
     return cudaGetLastError();
 }

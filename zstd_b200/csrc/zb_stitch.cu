@@ -32,7 +32,9 @@ __device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, 
 
 #define SCAN_THREADS 1024
 
-/* single-CTA exclusive scan over per-block output sizes (nbBlocks is a few thousand per wave) */
+/* single-CTA exclusive scan over per-block output sizes (a wave is a few thousand 128 KiB blocks, or a few
+ * hundred thousand blocks of a call made of short frames).  Pass 0 computes every block's size with coalesced,
+ * thread-strided reads and parks it in outOffsets[i]; passes 1 and 2 then walk contiguous chunks of plain u64. */
 __global__ void __launch_bounds__(SCAN_THREADS)
 zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames,
                      const ZbBlockMeta* __restrict__ meta, u64* __restrict__ outOffsets,
@@ -41,15 +43,17 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
     u64 const base = basePtr ? *basePtr : 0;      /* bytes produced by the waves before this one */
     __shared__ u64 part[SCAN_THREADS];
     u32 const tid = threadIdx.x;
-    u32 const per = (nbBlocks + SCAN_THREADS - 1u) / SCAN_THREADS;
-    u32 const beg = min(tid * per, nbBlocks), end = min((tid + 1u) * per, nbBlocks);
-    u64 sum = 0;
-    for (u32 i = beg; i < end; i++) {
+    for (u32 i = tid; i < nbBlocks; i += SCAN_THREADS) {
         ZbBlock const bd = blocks[i];
         u64 sz = 3u + meta[i].bodySize;
         if (bd.flags & ZB_FLAG_FIRST) { ZbFrame const f = frames[bd.frame]; sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, false); }
-        sum += sz;
+        outOffsets[i] = sz;
     }
+    __syncthreads();
+    u32 const per = (nbBlocks + SCAN_THREADS - 1u) / SCAN_THREADS;
+    u32 const beg = min(tid * per, nbBlocks), end = min((tid + 1u) * per, nbBlocks);
+    u64 sum = 0;
+    for (u32 i = beg; i < end; i++) sum += outOffsets[i];
     part[tid] = sum;
     __syncthreads();
     /* Hillis-Steele inclusive scan over the 1024 partial sums */
@@ -60,13 +64,7 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
         __syncthreads();
     }
     u64 run = base + ((tid == 0) ? 0 : part[tid - 1]);
-    for (u32 i = beg; i < end; i++) {
-        ZbBlock const bd = blocks[i];
-        u64 sz = 3u + meta[i].bodySize;
-        if (bd.flags & ZB_FLAG_FIRST) { ZbFrame const f = frames[bd.frame]; sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, false); }
-        outOffsets[i] = run;
-        run += sz;
-    }
+    for (u32 i = beg; i < end; i++) { u64 const sz = outOffsets[i]; outOffsets[i] = run; run += sz; }
     if (tid == SCAN_THREADS - 1) { outOffsets[nbBlocks] = base + part[SCAN_THREADS - 1]; *total = base + part[SCAN_THREADS - 1]; }
 }
 
@@ -83,7 +81,7 @@ __global__ void zb_frame_sizes_kernel(const ZbFrame* __restrict__ frames, u32 nb
 #define COPY_THREADS 256
 __global__ void __launch_bounds__(COPY_THREADS)
 zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, const ZbFrame* __restrict__ frames,
-               const u8* __restrict__ body, const ZbBlockMeta* __restrict__ meta,
+               const u8* __restrict__ body, u32 bodyStride, const ZbBlockMeta* __restrict__ meta,
                const u64* __restrict__ outOffsets, u8* __restrict__ dst, u64 dstCapacity)
 {
     u32 const b = blockIdx.x, tid = threadIdx.x;
@@ -108,7 +106,7 @@ zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, c
     }
     out += 3;
     if (m.type == ZB_BT_RLE) return;
-    const u8* const from = (m.type == ZB_BT_COMPRESSED) ? body + (size_t)b * ZB_BODY_STRIDE : src + bd.srcOff;
+    const u8* const from = (m.type == ZB_BT_COMPRESSED) ? body + (size_t)b * bodyStride : src + bd.srcOff;
     u32 const n = m.bodySize;
     /* 16-byte vector body where source and destination can both be aligned: source is read through
      * unaligned 32-bit words, destination peeled to 16-byte alignment */
@@ -131,14 +129,52 @@ zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, c
     for (u32 i = headN + nvec * 16u + tid; i < n; i += COPY_THREADS) out[i] = from[i];
 }
 
+/* Small blocks (calls made of many short frames, BASELINE config 5): a 256-thread CTA per block would move a
+ * few hundred bytes each, so one warp takes a block — 8 blocks per CTA, bytes copied lane-strided. */
+__global__ void __launch_bounds__(COPY_THREADS)
+zb_copy_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbFrame* __restrict__ frames,
+                     const u8* __restrict__ body, u32 bodyStride, const ZbBlockMeta* __restrict__ meta,
+                     const u64* __restrict__ outOffsets, u8* __restrict__ dst, u64 dstCapacity)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const b = blockIdx.x * (COPY_THREADS / 32u) + (threadIdx.x >> 5);
+    if (b >= nbBlocks) return;
+    ZbBlock const bd = blocks[b];
+    ZbBlockMeta const m = meta[b];
+    u64 const o0 = outOffsets[b], o1 = outOffsets[b + 1];
+    if (o1 > dstCapacity) return;                                   /* never write past dst + dstCapacity */
+    u8* out = dst + o0;
+    u32 hdr = 0;
+    if (bd.flags & ZB_FLAG_FIRST) {
+        ZbFrame const f = frames[bd.frame];
+        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, lane == 0);
+    }
+    out += hdr;
+    u32 const lastBlock = (bd.flags & ZB_FLAG_LAST) ? 1u : 0u;
+    if (lane == 0) {                                                /* zstd_compress.c:4586-4590 */
+        u32 const h24 = (m.type == ZB_BT_COMPRESSED) ? lastBlock + (2u << 1) + (m.bodySize << 3)
+                      : (m.type == ZB_BT_RLE)        ? lastBlock + (1u << 1) + (bd.size << 3)
+                                                     : lastBlock + (0u << 1) + (bd.size << 3);
+        out[0] = (u8)h24; out[1] = (u8)(h24 >> 8); out[2] = (u8)(h24 >> 16);
+        if (m.type == ZB_BT_RLE) out[3] = (u8)m.rleByte;
+    }
+    out += 3;
+    if (m.type == ZB_BT_RLE) return;
+    const u8* const from = (m.type == ZB_BT_COMPRESSED) ? body + (size_t)b * bodyStride : src + bd.srcOff;
+    for (u32 i = lane; i < m.bodySize; i += 32u) out[i] = from[i];
+}
+
 extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks, u32 nbBlocks, const ZbFrame* d_frames,
-                                        const u8* d_body, const ZbBlockMeta* d_meta,
+                                        const u8* d_body, u32 bodyStride, const ZbBlockMeta* d_meta,
                                         u64* d_outOffsets, const u64* d_base, u64* d_total,
                                         u8* d_dst, u64 dstCapacity, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
     zb_sizes_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_blocks, nbBlocks, d_frames, d_meta, d_outOffsets, d_base, d_total);
-    zb_copy_kernel<<<nbBlocks, COPY_THREADS, 0, stream>>>(d_src, d_blocks, d_frames, d_body, d_meta, d_outOffsets, d_dst, dstCapacity);
+    if (bodyStride <= 8192u + 1024u)
+        zb_copy_small_kernel<<<(nbBlocks + COPY_THREADS / 32u - 1u) / (COPY_THREADS / 32u), COPY_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, d_frames, d_body, bodyStride, d_meta, d_outOffsets, d_dst, dstCapacity);
+    else
+        zb_copy_kernel<<<nbBlocks, COPY_THREADS, 0, stream>>>(d_src, d_blocks, d_frames, d_body, bodyStride, d_meta, d_outOffsets, d_dst, dstCapacity);
     return cudaGetLastError();
 }
 
