@@ -95,57 +95,76 @@ def ref_lib():
     return R
 
 
+class RefMT:
+    """One ZSTD_CCtx with nbWorkers = threads (ZSTDMT, zstdmt_compress.c) and one destination buffer, both kept
+    across calls: the unmodified reference from oracle/_ref/libzstd_ref.so (-O3 -DZSTD_MULTITHREAD)."""
+
+    def __init__(self, size, level, threads):
+        self.R = ref_lib()
+        self.cctx = self.R.ZSTD_createCCtx()
+        self.R.ZSTD_CCtx_setParameter(self.cctx, 100, level)            # ZSTD_c_compressionLevel
+        if threads > 1:
+            self.R.ZSTD_CCtx_setParameter(self.cctx, 400, threads)      # ZSTD_c_nbWorkers
+        self.cap = self.R.ZSTD_compressBound(size)
+        self.dst = ctypes.create_string_buffer(self.cap)
+
+    def run(self, src):
+        """(seconds, compressed size) of one ZSTD_compress2 over `src`."""
+        t0 = time.perf_counter()
+        csize = self.R.ZSTD_compress2(self.cctx, self.dst, self.cap, src, len(src))
+        return time.perf_counter() - t0, csize
+
+    def close(self):
+        self.R.ZSTD_freeCCtx(self.cctx)
+
+
 def cpu_reference_time(src, level, threads, repeats=1):
-    """Seconds for one ZSTD_compress2(nbWorkers=threads) of `src` by the UNMODIFIED reference
-    (oracle/_ref/libzstd_ref.so, built -O3 -DZSTD_MULTITHREAD from /root/reference).  Best of `repeats`."""
-    R = ref_lib()
-    cctx = R.ZSTD_createCCtx()
-    R.ZSTD_CCtx_setParameter(cctx, 100, level)            # ZSTD_c_compressionLevel
-    if threads > 1:
-        R.ZSTD_CCtx_setParameter(cctx, 400, threads)      # ZSTD_c_nbWorkers
-    cap = R.ZSTD_compressBound(len(src))
-    dst = ctypes.create_string_buffer(cap)
+    """Seconds for one ZSTD_compress2(nbWorkers=threads) of `src`; the context is warmed by one untimed call."""
+    m = RefMT(len(src), level, threads)
+    m.run(src)
     best, csize = None, 0
     for _ in range(repeats):
-        t0 = time.perf_counter()
-        csize = R.ZSTD_compress2(cctx, dst, cap, src, len(src))
-        dt = time.perf_counter() - t0
+        dt, csize = m.run(src)
         best = dt if best is None else min(best, dt)
-    R.ZSTD_freeCCtx(cctx)
+    m.close()
     return best, csize
 
 
-def cpu_reference_sliced_time(src, level, threads):
-    """Seconds for `threads` host threads, each with a private ZSTD_CCtx, compressing equal contiguous
-    slices of `src` into independent frames (contrib/pzstd's decomposition)."""
-    R = ref_lib()
-    R.ZSTD_compressCCtx.restype = ctypes.c_size_t
-    R.ZSTD_compressCCtx.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
-    n = len(src)
-    per = (n + threads - 1) // threads
-    buf = (ctypes.c_char * n).from_buffer_copy(src) if not isinstance(src, ctypes.Array) else src
-    addr = ctypes.addressof(buf)
-    ctxs = [R.ZSTD_createCCtx() for _ in range(threads)]
-    caps = [R.ZSTD_compressBound(min(per, n - i * per)) if i * per < n else 0 for i in range(threads)]
-    dsts = [ctypes.create_string_buffer(max(c, 1)) for c in caps]
-    out = [0] * threads
+class RefSliced:
+    """`threads` host threads, each with a private ZSTD_CCtx and destination buffer (kept across calls),
+    compressing equal contiguous slices of the input into independent frames (contrib/pzstd's decomposition)."""
 
-    def work(i):
-        lo = i * per
-        if lo >= n:
-            return
-        out[i] = R.ZSTD_compressCCtx(ctxs[i], dsts[i], caps[i], addr + lo, min(per, n - lo), level)
+    def __init__(self, buf, level, threads):
+        R = self.R = ref_lib()
+        R.ZSTD_compressCCtx.restype = ctypes.c_size_t
+        R.ZSTD_compressCCtx.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        self.buf, self.level, self.threads = buf, level, threads
+        self.n = len(buf)
+        self.per = (self.n + threads - 1) // threads
+        self.addr = ctypes.addressof(buf)
+        self.ctxs = [R.ZSTD_createCCtx() for _ in range(threads)]
+        self.caps = [R.ZSTD_compressBound(min(self.per, self.n - i * self.per)) if i * self.per < self.n else 0 for i in range(threads)]
+        self.dsts = [ctypes.create_string_buffer(max(c, 1)) for c in self.caps]
 
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    dt = time.perf_counter() - t0
-    for c in ctxs:
-        R.ZSTD_freeCCtx(c)
-    return dt, sum(out)
+    def run(self):
+        out = [0] * self.threads
+
+        def work(i):
+            lo = i * self.per
+            if lo < self.n:
+                out[i] = self.R.ZSTD_compressCCtx(self.ctxs[i], self.dsts[i], self.caps[i], self.addr + lo, min(self.per, self.n - lo), self.level)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(self.threads)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0, sum(out)
+
+    def close(self):
+        for c in self.ctxs:
+            self.R.ZSTD_freeCCtx(c)
 
 
 def run_reference(args):
@@ -159,20 +178,23 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     size = args.size
     src, desc = load_input(size)
-    pinned = (ctypes.c_char * size).from_buffer_copy(src)
-    for _ in range(max(1, args.warmup)):                       # warm: thread pools, page tables, allocator
-        cpu_reference_time(src, args.level, cores)
-        cpu_reference_sliced_time(pinned, args.level, cores)
+    hbuf = (ctypes.c_char * size).from_buffer_copy(src)
+    mt, sl = RefMT(size, args.level, cores), RefSliced(hbuf, args.level, cores)
+    # contexts, thread pools and destination buffers live across steps (as our own arm's do); at least two untimed
+    # passes whatever --warmup says: the first pass of a 128-thread run pays first-touch page faults of ~1.3 GiB
+    for _ in range(max(2, args.warmup)):
+        mt.run(src)
+        sl.run()
     # two stock ways to use every host thread: one frame through ZSTDMT (nbWorkers), or N independent frames
-    t0 = time.perf_counter()
-    csize = 0
+    dt_mt = dt_sl = 0.0
+    csize = csl = 0
     for _ in range(args.steps):
-        _, csize = cpu_reference_time(src, args.level, cores)
-    dt_mt = time.perf_counter() - t0
-    t0 = time.perf_counter()
+        dt, csize = mt.run(src)
+        dt_mt += dt
     for _ in range(args.steps):
-        _, csl = cpu_reference_sliced_time(pinned, args.level, cores)
-    dt_sl = time.perf_counter() - t0
+        dt, csl = sl.run()
+        dt_sl += dt
+    mt.close(); sl.close()
     mode = "ZSTD_compress2 nbWorkers" if dt_mt <= dt_sl else "independent frames, one ZSTD_compressCCtx thread per slice"
     dt = min(dt_mt, dt_sl)
     if dt_sl < dt_mt:
@@ -317,11 +339,12 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         sample = src[: min(size, 256 << 20)]
         t1, c1 = cpu_reference_time(sample, args.level, 1)
-        cpu_reference_time(src, args.level, cores)                 # warm
-        tn, cn = cpu_reference_time(src, args.level, cores)
+        tn, cn = cpu_reference_time(src, args.level, cores)        # warmed inside
         hbuf = (ctypes.c_char * size).from_buffer_copy(src)
-        cpu_reference_sliced_time(hbuf, args.level, cores)
-        ts, _ = cpu_reference_sliced_time(hbuf, args.level, cores)
+        sl = RefSliced(hbuf, args.level, cores)
+        sl.run(); sl.run()
+        ts, _ = sl.run()
+        sl.close()
         _, cref = cpu_reference_time(src, args.level, 1) if size <= (256 << 20) else (0, None)
         cpu = {"value": round(size / min(tn, ts) / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": "reference",
                "sample": f"whole {size}-byte input, {cores} threads: ZSTD_compress2 nbWorkers {size/tn/1e9:.2f} GB/s, independent slices {size/ts/1e9:.2f} GB/s; 1 thread on the first {len(sample)} bytes: {len(sample)/t1/1e9:.3f} GB/s",
