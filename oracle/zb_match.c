@@ -132,15 +132,23 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
     size_t const be = bs + blockSize;
     size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
     emitter em = { seqs, 0, lit, 0, frame };
-    size_t ip = bs, anchor = bs, searchStart = bs;
-    /* encoder repcodes start invalid, except in a frame's first block behind a zstd-format dictionary */
-    u32 rep1 = (bs == plan->frameStart) ? plan->startRep[0] : 0, rep2 = (bs == plan->frameStart) ? plan->startRep[1] : 0;
+    size_t anchor = bs, ss;
     u16* const dist = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
 
     candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, dist);
 
-    while (ip + 8 <= be) {
+    /* The block is parsed in segments of ZB_PARSE_SEG bytes, each by its own warp on the GPU: a segment behaves
+     * like a block for the parse (repcodes start invalid, step acceleration restarts, no match crosses its end, the
+     * backward catch-up stops at its start) while candidates (dist[]), literals and sequences stay the block's —
+     * the literals a segment leaves behind its last match simply lengthen the next segment's first sequence. */
+    for (ss = bs; ss < be; ss += ZB_PARSE_SEG) {
+    size_t const se = (be - ss > ZB_PARSE_SEG) ? ss + ZB_PARSE_SEG : be;
+    size_t ip = ss, searchStart = ss;
+    /* encoder repcodes start invalid, except at the start of a frame's first block behind a zstd-format dictionary */
+    u32 rep1 = (ss == plan->frameStart) ? plan->startRep[0] : 0, rep2 = (ss == plan->frameStart) ? plan->startRep[1] : 0;
+
+    while (ip + 8 <= se) {
         u32 const step = plan->stepSize + (u32)((ip - searchStart) >> 7);     /* kSearchStrength = 8, zstd_fast.c:234 */
         int winner = -1, wtype = 0, l;
         size_t probe = 0; u32 offset = 0;
@@ -150,7 +158,7 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
         for (l = 0; l < (int)ZB_WARP && winner < 0; l++) {
             size_t const p = ip + (size_t)(l >> 1) * step + (size_t)(l & 1);
             u32 cur;
-            if (p + 8 > be) break;
+            if (p + 8 > se) break;
             cur = rd32(frame + p);
             if (l == 0 && ip == anchor && rep2 && rd32(frame + p - rep2) == cur) { winner = l; wtype = 3; probe = p; offset = rep2; }
             else if (rep1 && p >= lowLimit + rep1 && rd32(frame + p - rep1) == cur) { winner = l; wtype = 2; probe = p; offset = rep1; }
@@ -159,16 +167,18 @@ static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t fram
         if (winner < 0) { ip += (size_t)(ZB_WARP / 2) * step; continue; }
 
         {   size_t ms = probe, mm = probe - offset, mlen;
+            size_t const backLimit = anchor > ss ? anchor : ss;
             u32 offBase;
             if (wtype != 3)           /* backward catch-up (zstd_fast.c:387-391); a repcode-2 hit starts at the anchor */
-                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
-            mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + be);
+                while (ms > backLimit && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
+            mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + se);
             if (wtype == 3) { offBase = 1; { u32 const t = rep2; rep2 = rep1; rep1 = t; } }    /* litLength 0: code 1 means repcode 2 */
-            else if (wtype == 2 && ms > anchor) offBase = 1;                                     /* REPCODE1_TO_OFFBASE */
+            else if (wtype == 2 && ms > backLimit) offBase = 1;                                  /* REPCODE1_TO_OFFBASE */
             else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }                           /* decoder pushes every full offset */
             emit(&em, anchor, ms - anchor, mlen, offBase);
             ip = ms + mlen; anchor = ip; searchStart = ip;
         }
+    }
     }
     /* trailing literals (zstd_compress.c:3365-3366) */
     memcpy(em.lit + em.litSize, frame + anchor, be - anchor);

@@ -53,6 +53,7 @@ typedef struct { u32 offBase; u32 litLen; u32 matchLen; } zbo_seq;   /* matchLen
 #define ZB_BLOCK_MAX      (128u << 10)     /* ZSTD_BLOCKSIZE_MAX, lib/zstd.h:142 */
 #define ZB_PRIME_DEFAULT  (64u << 10)      /* history primed into a block's private table */
 #define ZB_WARP           32u
+#define ZB_PARSE_SEG      (16u << 10)      /* fast strategy: bytes of a block parsed by one warp (8 segments per 128 KiB block) */
 
 typedef struct {
     u32 mls;          /* bytes hashed (cParams.minMatch clamped to 4..8; short hash for dfast) */

@@ -1,6 +1,6 @@
 """Device-resident wave-executor sweep on one GPU (development tool, not the bench.py headline):
    python tests/wave_sweep.py [c2|c4] [iters]
-For every (priority streams, blocks per wave, waves in flight) combination: best / median total ms of
+For every (blocks per wave, waves in flight) combination: best / median total ms of
 one call and a check that the output bytes equal the serial (one wave, one stream) output."""
 import os, sys, statistics, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ import torch, zref, zstd_b200
 
 
 def one(d_src, n, level, env, iters):
-    for k in ("ZSTDB200_SERIAL", "ZSTDB200_WAVE_BLOCKS", "ZSTDB200_WAVE_SLOTS", "ZSTDB200_WAVE_PRIO"):
+    for k in ("ZSTDB200_SERIAL", "ZSTDB200_WAVE_BLOCKS", "ZSTDB200_WAVE_SLOTS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ctx = zstd_b200.ZSTD_CCtx()
@@ -33,14 +33,11 @@ def main():
     d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
     base = one(d_src, G, level, {"ZSTDB200_SERIAL": "1"}, iters)
     print(f"serial: best {base[0]:.2f} ms  median {base[1]:.2f} ms  {G/base[0]/1e6:.1f} GB/s  size {base[2]}", flush=True)
-    for prio in (0, 1):
-        for wb in (512, 1024, 2048):
-            for slots in (2, 4, 6):
-                if prio == 0 and (wb, slots) not in ((2048, 4), (1024, 4)):
-                    continue
-                r = one(d_src, G, level, {"ZSTDB200_WAVE_PRIO": str(prio), "ZSTDB200_WAVE_BLOCKS": str(wb), "ZSTDB200_WAVE_SLOTS": str(slots)}, iters)
-                same = (r[2], r[3]) == (base[2], base[3])
-                print(f"prio {prio} wave {wb:5d} slots {slots}: best {r[0]:.2f} ms  median {r[1]:.2f} ms  {G/r[0]/1e6:.1f} GB/s  same bytes: {same}", flush=True)
+    for wb in (256, 512, 1024, 2048, 4096):
+        for slots in (2, 4, 8):
+            r = one(d_src, G, level, {"ZSTDB200_WAVE_BLOCKS": str(wb), "ZSTDB200_WAVE_SLOTS": str(slots)}, iters)
+            same = (r[2], r[3]) == (base[2], base[3])
+            print(f"wave {wb:5d} slots {slots}: best {r[0]:.2f} ms  median {r[1]:.2f} ms  {G/r[0]/1e6:.1f} GB/s  same bytes: {same}", flush=True)
 
 
 if __name__ == "__main__":

@@ -117,7 +117,8 @@ struct ZSTD_CCtx_s {
     cudaStream_t stream;
     /* per-block workspace */
     size_t capBlocks, capFrames, capWaves;
-    size_t capHeavyBytes[6];       /* meta, seqs, lits, body, dist, dist2 */
+    size_t capHeavyBytes[7];       /* meta, seqs, lits, body, dist, dist2, segmeta */
+    ZbSegMeta* d_segmeta;          /* K1b -> K1c: per parse segment counts */
     u32 devWaveBlocks;             /* device-memory calls: blocks per wave (0 = always one wave) */
     cudaStream_t waveStream[ZB_WAVE_SLOTS_MAX + 2];
     u32 waveSlots;                 /* waves in flight, device-memory calls */
@@ -191,7 +192,7 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; cudaFree(c->d_segmeta); c->d_segmeta = NULL; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
     cudaFreeHost(c->h_totals);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
     c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL; c->d_totals = NULL; c->h_totals = NULL;
@@ -249,10 +250,12 @@ static ZbStrides zb_strides(u32 maxBlock)
 static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides& sd, bool needDist2)
 {
     size_t const nb = nbSlotBlocks;
-    size_t const need[6] = { nb * sizeof(ZbBlockMeta), nb * sd.seq * sizeof(u64), nb * (size_t)sd.lit, nb * (size_t)sd.body,
-                             nb * (size_t)sd.dist * sizeof(u16), needDist2 ? nb * (size_t)sd.dist * sizeof(u16) : 0 };
-    void** const ptr[6] = { (void**)&c->d_meta, (void**)&c->d_seqs, (void**)&c->d_lits, (void**)&c->d_body, (void**)&c->d_dist, (void**)&c->d_dist2 };
-    for (int i = 0; i < 6; i++) {
+    size_t const need[7] = { nb * sizeof(ZbBlockMeta), nb * sd.seq * sizeof(u64), nb * (size_t)sd.lit, nb * (size_t)sd.body,
+                             nb * (size_t)sd.dist * sizeof(u16), needDist2 ? nb * (size_t)sd.dist * sizeof(u16) : 0,
+                             nb * ((sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG) * sizeof(ZbSegMeta) };
+    void** const ptr[7] = { (void**)&c->d_meta, (void**)&c->d_seqs, (void**)&c->d_lits, (void**)&c->d_body, (void**)&c->d_dist, (void**)&c->d_dist2,
+                            (void**)&c->d_segmeta };
+    for (int i = 0; i < 7; i++) {
         if (need[i] <= c->capHeavyBytes[i]) continue;
         cudaFree(*ptr[i]); *ptr[i] = NULL; c->capHeavyBytes[i] = 0;
         CK(cudaMalloc(ptr[i], need[i] + 256));
@@ -416,8 +419,8 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
             if (phase == 0) {
                 CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_dist + s * P.sd.dist,
                                    G.prm.strategy == 2 ? c->d_dist2 + s * P.sd.dist : (u16*)0, c->d_seqs + s * P.sd.seq,
-                                   c->d_lits + s * P.sd.lit, c->d_meta + s, (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
-                *launches += (G.prm.strategy == 2) ? 3 : 2;
+                                   c->d_lits + s * P.sd.lit, c->d_meta + s, c->d_segmeta + s * ((P.sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG), (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
+                *launches += 3;                                   /* fast: walk, parse, merge; doubleFast: two walks, parse */
             } else if (phase == 1) {
                 CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_deActive, c->d_lits + s * P.sd.lit, c->d_body + s * P.sd.body, c->d_meta + s, stream));
                 *launches += 1;

@@ -118,6 +118,17 @@ typedef struct {
 
 /* Per-block strides of the workspace arrays of one call, derived from its largest block (M = that size
  * rounded up to 64): 128 KiB blocks use the ZB_*_STRIDE values above, a call of 1 KiB records 1/128 of them. */
+/* fast strategy: a block is parsed in segments of ZB_PARSE_SEG bytes, one warp each (a segment behaves like a block
+ * for the parse; candidates, literals and sequences stay the block's).  Per segment, for the merge kernel: */
+#define ZB_PARSE_SEG   (16u << 10)
+#define ZB_PARSE_SEGS  (ZB_BLOCK_MAX / ZB_PARSE_SEG)
+typedef struct {
+    u32 nbSeq;         /* sequences of the segment, stored from seq slot k * ZB_PARSE_SEG / 4 */
+    u32 litSize;       /* literal bytes of the segment (incl. the trailing ones), stored from literal offset k * ZB_PARSE_SEG */
+    u32 trail;         /* literals behind the segment's last match: they lengthen the next sequence of the block */
+    u32 pad;
+} ZbSegMeta;
+
 typedef struct {
     u32 dist;          /* u16 per block : candidate distances; K3 reuses the area for 3 x state records */
     u32 seq;           /* u64 per block : packed sequences */

@@ -8,7 +8,8 @@
 extern "C" {
 #endif
 
-/* K1: match-finder = K1a candidate table walk + K1b greedy parse.  One warp per block each.
+/* K1: match-finder = K1a candidate table walk (one warp per block) + K1b greedy parse (fast strategy: one warp per
+ * 16 KiB segment, joined by K1c; d_segmeta: ZB_PARSE_SEGS records per block).
  * Per-block workspace strides come in `sd` (ZbStrides, derived from the call's largest block).
  * d_dist: sd->dist u16 per block (dead after this call; K3 reuses it for the FSE state records);
  * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates).
@@ -17,7 +18,8 @@ extern "C" {
  * already primed from that dictionary tail by zb_launch_dict_image (same ZbParams), 3 << hashLog bytes. */
 cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream);
 cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd,
-                            u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream);
+                            u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta,
+                            cudaEvent_t evMid, cudaStream_t stream);
 
 /* host: parse a dictionary (zb_dict.cu).  Returns the content offset, 0 for raw content, or an error code */
 size_t zb_loadDictionary(ZbDictEntropy* de, const u8* dict, size_t dictSize);

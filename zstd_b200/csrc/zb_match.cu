@@ -303,10 +303,10 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * :410-420), repcode-1 (:281-297), table candidate with 4-byte check (:102-141).  Lowest lane wins.
  * ---------------------------------------------------------------------------------------------- */
 #ifndef PARSE_WARPS
-#define PARSE_WARPS 4
+#define PARSE_WARPS 8            /* = ZB_PARSE_SEGS: the eight segments of a full block share a CTA */
 #endif
 #ifndef PARSE_MIN_CTAS
-#define PARSE_MIN_CTAS 12          /* 48 warps per SM at 40 registers.  16 (= 32 registers, 64 warps) is 3.7 % faster when the parse
+#define PARSE_MIN_CTAS 6           /* 48 warps per SM at 40 registers.  8 (= 32 registers, 64 warps) is 3.7 % faster when the parse
                                     * runs alone, but fills every warp slot: the candidate walk of the next wave no longer fits beside
                                     * it and a whole device-resident call gets 4 % slower (profiles/r1_history.md) */
 #endif
@@ -322,33 +322,41 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
 template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
 zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
-                const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+                const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
 {
     u32 const lane = threadIdx.x & 31u;
-    u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+    u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment: the warps of a CTA share a block's history in L1/L2 */
+    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;   /* segments of the call's largest block (1 for calls of short frames) */
+    u32 const b = g / segs, k = g % segs;
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
-    u64* const myseq = seqs + (size_t)b * sd.seq;
-    u8*  const mylit = lits + (size_t)b * sd.lit;
+    u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
+    u8*  const mylit = lits + (size_t)b * sd.lit + (size_t)k * ZB_PARSE_SEG;
     const u16* const mydist = dist + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;          /* base + rel addresses the frame's own bytes */
-    u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+    u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
     ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
     if (DICT && (bd.flags & ZB_FLAG_DICT)) { sg.lo = dictEnd - bd.histLen; sg.split = bd.histLen; }   /* history = dictionary tail */
 
     if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
-        if (lane == 0) {
+        if (lane == 0 && k == 0) {
             ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
             m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
             meta[b] = m;
         }
         return;
     }
+    u32 const ss = bs + k * ZB_PARSE_SEG;                      /* this warp's segment [ss, be) */
+    if (ss >= blockEnd) {
+        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.litSize = 0; z.trail = 0; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+        return;
+    }
+    u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
 
-    u32 ip = bs, anchor = bs, searchStart = bs;
+    u32 ip = ss, anchor = ss, searchStart = ss;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
-    if (DICT && (bd.flags & ZB_FLAG_DICT)) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
-    u32 pf = bs;                                             /* input and dist[] below this position are on their way to L2 */
+    if (DICT && (bd.flags & ZB_FLAG_DICT) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
+    u32 pf = ss;                                             /* input and dist[] below this position are on their way to L2 */
 
     while (ip + 8u <= be) {
         /* the warp consumes its block front to back but every step waits for its loads: keep the next
@@ -432,13 +440,61 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         ip = ms + mlen; anchor = ip; searchStart = ip;
     }
 
-    /* trailing literals (zstd_compress.c:3365-3366) */
-    {   u32 const lastLits = be - anchor;
-        for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
-        litPos += lastLits;
+    /* trailing literals (zstd_compress.c:3365-3366): the block's last literals, or the head of the next segment's first sequence */
+    u32 const lastLits = be - anchor;
+    for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
+    litPos += lastLits;
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = litPos; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+}
+
+/* K1c — joins a block's segments: sequences and literals move down to be contiguous (in place, ascending, every
+ * chunk read completely before it is written: the destination never lies above the source), the first sequence of a
+ * segment takes over the literals the segments before it left behind, and the block's meta record is written. */
+#define MERGE_THREADS 256
+__global__ void __launch_bounds__(MERGE_THREADS)
+zb_merge_segments_kernel(const ZbBlock* __restrict__ blocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
+                         u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+{
+    u32 const b = blockIdx.x, tid = threadIdx.x;
+    if (blocks[b].size < 7u) return;                             /* raw block: meta written by the parse kernel */
+    u64* const myseq = seqs + (size_t)b * sd.seq;
+    u8*  const mylit = lits + (size_t)b * sd.lit;
+    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    ZbSegMeta sm[ZB_PARSE_SEGS];
+#pragma unroll
+    for (u32 k = 0; k < ZB_PARSE_SEGS; k++) if (k < segs) sm[k] = segmeta[(size_t)b * segs + k];
+    u32 seqOff = sm[0].nbSeq, litOff = sm[0].litSize;
+    u32 carry = sm[0].trail;                                     /* literals waiting for the next sequence */
+#pragma unroll 1
+    for (u32 k = 1; k < segs; k++) {
+        u32 const ns = sm[k].nbSeq, nl = sm[k].litSize;
+        u64* const sfrom = myseq + (size_t)k * (ZB_PARSE_SEG / 4u);
+        const u8* const lfrom = mylit + (size_t)k * ZB_PARSE_SEG;
+        for (u32 c0 = 0; c0 < ns; c0 += MERGE_THREADS) {
+            u32 const i = c0 + tid;
+            u64 v = 0;
+            if (i < ns) { v = sfrom[i]; if (i == 0u) v += (u64)carry << 24; }        /* litLength field, zb_pack_seq */
+            __syncthreads();
+            if (i < ns) myseq[seqOff + i] = v;
+            __syncthreads();
+        }
+        if (litOff != k * ZB_PARSE_SEG) {
+            for (u32 c0 = 0; c0 < nl; c0 += MERGE_THREADS * 16u) {
+                u32 const i0 = c0 + tid * 16u;
+                u8 t[16];
+#pragma unroll
+                for (u32 j = 0; j < 16u; j++) t[j] = (i0 + j < nl) ? lfrom[i0 + j] : (u8)0;
+                __syncthreads();
+#pragma unroll
+                for (u32 j = 0; j < 16u; j++) if (i0 + j < nl) mylit[litOff + i0 + j] = t[j];
+                __syncthreads();
+            }
+        }
+        carry = ns ? sm[k].trail : carry + sm[k].trail;
+        seqOff += ns; litOff += nl;
     }
-    if (lane == 0) {
-        ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litPos; m.litSecSize = 0; m.bodySize = 0;
+    if (tid == 0) {
+        ZbBlockMeta m; m.nbSeq = seqOff; m.litSize = litOff; m.litSecSize = 0; m.bodySize = 0;
         m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
         meta[b] = m;
     }
@@ -596,7 +652,7 @@ extern "C" cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* 
 }
 
 extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sdp,
-                                       u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, cudaEvent_t evMid, cudaStream_t stream)
+                                       u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta, cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
     ZbStrides const sd = *sdp;
@@ -611,8 +667,11 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
     } else {
         zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_image, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
-        if (d_dictEnd) zb_parse_kernel<true><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta);
-        else           zb_parse_kernel<false><<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta);
+        u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+        u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);                   /* one warp per segment */
+        if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
+        else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
+        zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
     }
     return cudaGetLastError();
 }
