@@ -200,8 +200,7 @@ static size_t matchBlock_dfast(const zbo_plan* plan, const u8* frame, size_t fra
     size_t const be = bs + blockSize;
     size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
     emitter em = { seqs, 0, lit, 0, frame };
-    size_t ip = bs, anchor = bs, searchStart = bs;
-    u32 rep1 = 0, rep2 = 0;
+    size_t anchor = bs, ss;
     u16* const distL = (u16*)malloc((blockSize + 8) * sizeof(u16));
     u16* const distS = (u16*)malloc((blockSize + 8) * sizeof(u16));
     (void)frameSize;
@@ -209,46 +208,52 @@ static size_t matchBlock_dfast(const zbo_plan* plan, const u8* frame, size_t fra
     candidates_walk(frame, lowLimit, bs, be, 8, plan->longHashLog, plan->insPeriodLong, plan->frameStart, distL);
     candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, distS);
 
-    while (ip + 9 <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
+    /* parsed in segments of ZB_PARSE_SEG bytes like the fast strategy (see matchBlock_fast) */
+    for (ss = bs; ss < be; ss += ZB_PARSE_SEG) {
+    size_t const se = (be - ss > ZB_PARSE_SEG) ? ss + ZB_PARSE_SEG : be;
+    size_t ip = ss, searchStart = ss;
+    u32 rep1 = 0, rep2 = 0;
+    while (ip + 9 <= se) {                                   /* a lane reads 8 bytes at p and at p+1 */
         u32 const step = 1 + (u32)((ip - searchStart) >> 8);
         int found = 0, wtype = 0, l;
         size_t ms = 0; u32 offset = 0; size_t mlen = 0;
         for (l = 0; l < (int)ZB_WARP && !found; l++) {
             size_t const p = ip + (size_t)l * step;
-            if (p + 9 > be) break;
+            if (p + 9 > se) break;
             if (l == 0 && ip == anchor && rep2 && rd32(frame + p - rep2) == rd32(frame + p)) {
                 found = 1; wtype = 3; ms = p; offset = rep2;
-                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - rep2, frame + be);
+                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - rep2, frame + se);
             } else if (rep1 && p + 1 >= lowLimit + rep1 && rd32(frame + p + 1 - rep1) == rd32(frame + p + 1)) {
                 found = 1; wtype = 2; ms = p + 1; offset = rep1;
-                mlen = 4 + zb_count(frame + p + 5, frame + p + 5 - rep1, frame + be);
+                mlen = 4 + zb_count(frame + p + 5, frame + p + 5 - rep1, frame + se);
             } else if (distL[p - bs] && rd64(frame + p - distL[p - bs]) == rd64(frame + p)) {
                 size_t mm;
                 found = 1; wtype = 1; ms = p; offset = distL[p - bs];
-                mlen = 8 + zb_count(frame + p + 8, frame + p + 8 - offset, frame + be);
+                mlen = 8 + zb_count(frame + p + 8, frame + p + 8 - offset, frame + se);
                 mm = ms - offset;
-                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
+                while (ms > (anchor > ss ? anchor : ss) && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
             } else if (distS[p - bs] && rd32(frame + p - distS[p - bs]) == rd32(frame + p)) {
                 size_t mm;
                 found = 1; wtype = 1; ms = p; offset = distS[p - bs];
-                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - offset, frame + be);
+                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - offset, frame + se);
                 if (distL[p + 1 - bs] && rd64(frame + p + 1 - distL[p + 1 - bs]) == rd64(frame + p + 1)) {
                     u32 const o1 = distL[p + 1 - bs];
-                    size_t const l1 = 8 + zb_count(frame + p + 9, frame + p + 9 - o1, frame + be);
+                    size_t const l1 = 8 + zb_count(frame + p + 9, frame + p + 9 - o1, frame + se);
                     if (l1 > mlen) { ms = p + 1; offset = o1; mlen = l1; }
                 }
                 mm = ms - offset;
-                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
+                while (ms > (anchor > ss ? anchor : ss) && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
             }
         }
         if (!found) { ip += (size_t)ZB_WARP * step; continue; }
         {   u32 offBase;
             if (wtype == 3) { offBase = 1; { u32 const t = rep2; rep2 = rep1; rep1 = t; } }
-            else if (wtype == 2 && ms > anchor) offBase = 1;
+            else if (wtype == 2 && ms > (anchor > ss ? anchor : ss)) offBase = 1;
             else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }
             emit(&em, anchor, ms - anchor, mlen, offBase);
             ip = ms + mlen; anchor = ip; searchStart = ip;
         }
+    }
     }
     memcpy(em.lit + em.litSize, frame + anchor, be - anchor);
     em.litSize += be - anchor;

@@ -161,7 +161,7 @@ extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
     if (!c) return NULL;
     c->device = -1;
     {   const char* s = getenv("ZSTDB200_SERIAL"); const char* w = getenv("ZSTDB200_WAVE_BLOCKS");
-        c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 2048u);
+        c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 1024u);     /* 128 MiB waves: tests/wave_sweep.py */
         const char* n = getenv("ZSTDB200_WAVE_SLOTS"); const char* h = getenv("ZSTDB200_HOST_WAVE_BLOCKS");
         c->waveSlots = n ? (u32)atoi(n) : ZB_WAVE_SLOTS_DEFAULT;
         c->hostWaveSlots = n ? (u32)atoi(n) : ZB_HOST_WAVE_SLOTS_DEFAULT;
@@ -420,7 +420,7 @@ static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const
                 CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_dist + s * P.sd.dist,
                                    G.prm.strategy == 2 ? c->d_dist2 + s * P.sd.dist : (u16*)0, c->d_seqs + s * P.sd.seq,
                                    c->d_lits + s * P.sd.lit, c->d_meta + s, c->d_segmeta + s * ((P.sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG), (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
-                *launches += 3;                                   /* fast: walk, parse, merge; doubleFast: two walks, parse */
+                *launches += (G.prm.strategy == 2) ? 4 : 3;       /* walk(s), parse, merge */
             } else if (phase == 1) {
                 CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_deActive, c->d_lits + s * P.sd.lit, c->d_body + s * P.sd.body, c->d_meta + s, stream));
                 *launches += 1;

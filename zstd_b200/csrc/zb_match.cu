@@ -84,23 +84,36 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
                                                u32 q0, u32 o0, u32 pmin, u32 nPos, u32 bs, u32 lane,
                                                u32& ph, u32 inc, u32 period, u16* __restrict__ mydist)
 {
+    /* The bucket of step j+1 is read in the same shared-memory round as the read-back of step j (nothing writes
+     * the table in between, except the rare peel below, which reads it again): one LDS round trip per step
+     * instead of two on the loop-carried chain. */
+    bool act_c = INTERIOR ? true : ((q0 + lane >= o0 + pmin) && (q0 + lane - o0 < nPos));
+    u32 old_c = act_c ? table[hh[0] >> 8] : 0u;
+    u32 oldtag_c = act_c ? tags[hh[0] >> 8] : 0x100u;
 #pragma unroll
     for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
         u32 const q = q0 + 32u * j + lane;
-        bool const act = INTERIOR ? true : ((q >= o0 + pmin) && (q - o0 < nPos));
+        bool const act = act_c;
         u32 const p = q - o0;
         u32 const h = act ? (hh[j] >> 8) : 0u;
         u32 const tag = hh[j] & 0xFFu;
         bool const ins = act && ph < 2u;
-        /* read the bucket, let every inserting lane write it, read it back: when no two inserting
-         * lanes share a bucket (the common case) the read-back alone resolves the step */
-        u32 const old = act ? table[h] : 0u;
-        u32 const oldtag = act ? tags[h] : 0x100u;
+        u32 const old = old_c, oldtag = oldtag_c;
+        /* let every inserting lane write its bucket, read it back: when no two inserting lanes share a bucket
+         * (the common case) the read-back alone resolves the step */
         __syncwarp();
         if (ins) { table[h] = (u16)p; tags[h] = (u8)tag; }
         __syncwarp();
         u32 const nw = act ? table[h] : 0u;
         u32 const nwtag = act ? tags[h] : 0x100u;
+        u32 hn = 0; bool act_n = false;
+        if (j + 1u < CAND_CHUNK / 32u) {
+            u32 const qn = q + 32u;
+            act_n = INTERIOR ? true : ((qn >= o0 + pmin) && (qn - o0 < nPos));
+            hn = act_n ? (hh[(j + 1u) % (CAND_CHUNK / 32u)] >> 8) : 0u;
+            old_c = act_n ? table[hn] : 0u;
+            oldtag_c = act_n ? tags[hn] : 0x100u;
+        }
         u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
         u32 d = 0;
         bool resolved = false;
@@ -127,6 +140,10 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
                 losers &= ~grpAll;
             }
             __syncwarp();
+            if (j + 1u < CAND_CHUNK / 32u) {                    /* the peel rewrote buckets: read the next step's again */
+                old_c = act_n ? table[hn] : 0u;
+                oldtag_c = act_n ? tags[hn] : 0x100u;
+            }
         }
         if (!resolved) {
             u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
@@ -135,6 +152,7 @@ __device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8*
         }
         if (INTERIOR || (act && p >= bs)) mydist[p - bs] = (u16)d;
         ph += inc; if (ph >= period) ph -= period;
+        act_c = act_n;
     }
 }
 
@@ -512,31 +530,39 @@ zb_merge_segments_kernel(const ZbBlock* __restrict__ blocks, ZbStrides sd, const
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
 zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
                       const u16* __restrict__ distLong, const u16* __restrict__ distShort,
-                      u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+                      u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
 {
     u32 const lane = threadIdx.x & 31u;
-    u32 const b = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);
+    u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment, as in zb_parse_kernel */
+    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    u32 const b = g / segs, k = g % segs;
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
-    u64* const myseq = seqs + (size_t)b * sd.seq;
-    u8*  const mylit = lits + (size_t)b * sd.lit;
+    u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
+    u8*  const mylit = lits + (size_t)b * sd.lit + (size_t)k * ZB_PARSE_SEG;
     const u16* const dLp = distLong + (size_t)b * sd.dist;
     const u16* const dSp = distShort + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;
-    u32 const bs = bd.histLen, be = bd.histLen + bd.size;
+    u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
     ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
 
     if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
-        if (lane == 0) {
+        if (lane == 0 && k == 0) {
             ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
             m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
             meta[b] = m;
         }
         return;
     }
-    u32 ip = bs, anchor = bs, searchStart = bs;
+    u32 const ss = bs + k * ZB_PARSE_SEG;                      /* this warp's segment [ss, be) */
+    if (ss >= blockEnd) {
+        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.litSize = 0; z.trail = 0; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+        return;
+    }
+    u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
+    u32 ip = ss, anchor = ss, searchStart = ss;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
-    u32 pf = bs;
+    u32 pf = ss;
 
     while (ip + 9u <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
         if (ip + PARSE_PF_AHEAD > pf && pf < be) {
@@ -610,15 +636,10 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
         litPos += litLen; nbSeq++;
         ip = ms + mlen; anchor = ip; searchStart = ip;
     }
-    {   u32 const lastLits = be - anchor;
-        for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
-        litPos += lastLits;
-    }
-    if (lane == 0) {
-        ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litPos; m.litSecSize = 0; m.bodySize = 0;
-        m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
-        meta[b] = m;
-    }
+    u32 const lastLits = be - anchor;
+    for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
+    litPos += lastLits;
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = litPos; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
 }
 
 static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, const ZbStrides& sd, u16* d_dist,
@@ -656,14 +677,16 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
 {
     if (nbBlocks == 0) return cudaSuccess;
     ZbStrides const sd = *sdp;
-    u32 const grid = (nbBlocks + PARSE_WARPS - 1) / PARSE_WARPS;
     if (prm->strategy == 2) {
         /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
         ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
         zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, sd, d_dist, nullptr, nullptr, stream);
         zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist2, nullptr, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
-        zb_parse_dfast_kernel<<<grid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_lits, d_meta);
+        u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+        u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);
+        zb_parse_dfast_kernel<<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_lits, d_meta, d_segmeta);
+        zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
     } else {
         zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_image, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
