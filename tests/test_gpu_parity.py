@@ -36,6 +36,12 @@ CASES = {
     "syn-400000": zref.synthetic(400_000, 4), "syn-4M-p30": zref.synthetic(4 << 20, 5, 0.3), "syn-4M-p90": zref.synthetic(4 << 20, 6, 0.9),
     "syn-2M-p10": zref.synthetic(2 << 20, 8, 0.1),
 }
+# sizes around the 16 KiB parse-segment boundaries, and matches that want to cross every segment end
+SEG = 16 << 10
+for _n in (SEG - 1, SEG, SEG + 1, SEG + 6, SEG + 7, SEG + 8, 2 * SEG + 3, 8 * SEG - 1, 8 * SEG + SEG + 5, 3 * 8 * SEG + 9):
+    CASES[f"seg-{_n}"] = zref.synthetic(_n, 40 + _n % 7, 0.6)
+CASES["seg-rep"] = (zref.synthetic(5000, 77, 0.3) * 30)[: 9 * SEG + 123]
+CASES["seg-zeros"] = bytes(5 * SEG + 11)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

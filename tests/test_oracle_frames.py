@@ -45,6 +45,11 @@ EDGE = {
     "period3": b"abc" * 50_000, "syn-128k": zref.synthetic(128 << 10, 3), "syn-128k+1": zref.synthetic((128 << 10) + 1, 3),
     "syn-1M-p90": zref.synthetic(1 << 20, 5, 0.9), "syn-1M-p10": zref.synthetic(1 << 20, 6, 0.1),
 }
+# sizes around the 16 KiB parse-segment boundaries (a segment end within 8 bytes of the block end, one byte past it, ...)
+SEG = 16 << 10
+for _n in (SEG - 1, SEG, SEG + 1, SEG + 6, SEG + 7, SEG + 8, 2 * SEG + 3, 8 * SEG - 1, 8 * SEG + SEG + 5, 3 * 8 * SEG + 9):
+    EDGE[f"seg-{_n}"] = zref.synthetic(_n, 40 + _n % 7, 0.6)
+EDGE["seg-rep"] = (zref.synthetic(5000, 77, 0.3) * 30)[: 9 * SEG + 123]        # matches that want to run across every segment end
 
 
 @needs_ref
