@@ -349,7 +349,6 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
     u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
-    u8*  const mylit = lits + (size_t)b * sd.lit + (size_t)k * ZB_PARSE_SEG;
     const u16* const mydist = dist + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;          /* base + rel addresses the frame's own bytes */
     u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
@@ -372,7 +371,7 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
     u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
 
     u32 ip = ss, anchor = ss, searchStart = ss;
-    u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
+    u32 rep1 = 0, rep2 = 0, nbSeq = 0;
     if (DICT && (bd.flags & ZB_FLAG_DICT) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
     u32 pf = ss;                                             /* input and dist[] below this position are on their way to L2 */
 
@@ -453,41 +452,49 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         else if (wtype == 2u && litLen > 0u) offBase = 1u;                                 /* REPCODE1_TO_OFFBASE */
         else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
         if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
-        for (u32 i = lane; i < litLen; i += 32) mylit[litPos + i] = base[anchor + i];
-        litPos += litLen; nbSeq++;
+        nbSeq++;                                               /* the literal bytes are gathered by the merge kernel */
         ip = ms + mlen; anchor = ip; searchStart = ip;
     }
 
     /* trailing literals (zstd_compress.c:3365-3366): the block's last literals, or the head of the next segment's first sequence */
     u32 const lastLits = be - anchor;
-    for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
-    litPos += lastLits;
-    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = litPos; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = 0; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
 }
 
-/* K1c — joins a block's segments: sequences and literals move down to be contiguous (in place, ascending, every
- * chunk read completely before it is written: the destination never lies above the source), the first sequence of a
- * segment takes over the literals the segments before it left behind, and the block's meta record is written. */
+/* K1c — joins a block's segments and materialises its literals.
+ * 1. sequences move down to be contiguous (in place, ascending, every chunk read completely before it is written: the
+ *    destination never lies above the source); the first sequence of a segment takes over the literals the segments
+ *    before it left behind their last match;
+ * 2. a scan over (litLength, litLength + matchLength) gives every sequence the block position its literals start at
+ *    and their offset in the literal buffer; warps copy them straight from the input (the parse kernels emit no
+ *    literal bytes at all), then the block's last literals;
+ * 3. the block's meta record is written. */
 #define MERGE_THREADS 256
+#define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
 __global__ void __launch_bounds__(MERGE_THREADS)
-zb_merge_segments_kernel(const ZbBlock* __restrict__ blocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
+zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
                          u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
-    u32 const b = blockIdx.x, tid = threadIdx.x;
-    if (blocks[b].size < 7u) return;                             /* raw block: meta written by the parse kernel */
+    __shared__ u32 sPos[MERGE_TILE], sLit[MERGE_TILE], sLen[MERGE_TILE];
+    __shared__ u32 wsumL[MERGE_THREADS / 32], wsumA[MERGE_THREADS / 32];
+    __shared__ u32 baseL, baseA;
+    u32 const b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    ZbBlock const bd = blocks[b];
+    if (bd.size < 7u) return;                                    /* raw block: meta written by the parse kernel */
     u64* const myseq = seqs + (size_t)b * sd.seq;
     u8*  const mylit = lits + (size_t)b * sd.lit;
+    const u8* const in = src + bd.srcOff;                        /* literals always lie inside the block itself */
     u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
     ZbSegMeta sm[ZB_PARSE_SEGS];
 #pragma unroll
     for (u32 k = 0; k < ZB_PARSE_SEGS; k++) if (k < segs) sm[k] = segmeta[(size_t)b * segs + k];
-    u32 seqOff = sm[0].nbSeq, litOff = sm[0].litSize;
+    /* ---- 1. sequences ---- */
+    u32 seqOff = sm[0].nbSeq;
     u32 carry = sm[0].trail;                                     /* literals waiting for the next sequence */
 #pragma unroll 1
     for (u32 k = 1; k < segs; k++) {
-        u32 const ns = sm[k].nbSeq, nl = sm[k].litSize;
+        u32 const ns = sm[k].nbSeq;
         u64* const sfrom = myseq + (size_t)k * (ZB_PARSE_SEG / 4u);
-        const u8* const lfrom = mylit + (size_t)k * ZB_PARSE_SEG;
         for (u32 c0 = 0; c0 < ns; c0 += MERGE_THREADS) {
             u32 const i = c0 + tid;
             u64 v = 0;
@@ -496,23 +503,97 @@ zb_merge_segments_kernel(const ZbBlock* __restrict__ blocks, ZbStrides sd, const
             if (i < ns) myseq[seqOff + i] = v;
             __syncthreads();
         }
-        if (litOff != k * ZB_PARSE_SEG) {
-            for (u32 c0 = 0; c0 < nl; c0 += MERGE_THREADS * 16u) {
-                u32 const i0 = c0 + tid * 16u;
-                u8 t[16];
-#pragma unroll
-                for (u32 j = 0; j < 16u; j++) t[j] = (i0 + j < nl) ? lfrom[i0 + j] : (u8)0;
-                __syncthreads();
-#pragma unroll
-                for (u32 j = 0; j < 16u; j++) if (i0 + j < nl) mylit[litOff + i0 + j] = t[j];
-                __syncthreads();
-            }
-        }
         carry = ns ? sm[k].trail : carry + sm[k].trail;
-        seqOff += ns; litOff += nl;
+        seqOff += ns;
     }
+    u32 const nbSeq = seqOff;
+    if (tid == 0) { baseL = 0; baseA = 0; }
+    __syncthreads();
+    /* ---- 2. literals ---- */
+    for (u32 t0 = 0; t0 < nbSeq; t0 += MERGE_TILE) {
+        u32 const n = min(MERGE_TILE, nbSeq - t0);
+        /* every thread owns 4 consecutive sequences of the tile */
+        u32 ll[4], adv[4], myL = 0, myA = 0;
+#pragma unroll
+        for (u32 j = 0; j < 4u; j++) {
+            u32 const i = tid * 4u + j;
+            u64 const q = (i < n) ? myseq[t0 + i] : 0ull;
+            ll[j] = (u32)((q >> 24) & 0x3FFFFu);
+            adv[j] = ll[j] + (u32)(q >> 42);
+            myL += ll[j]; myA += adv[j];
+        }
+        u32 inL = myL, inA = myA;                                /* inclusive scan over the warp, then over the warps */
+#pragma unroll
+        for (u32 o = 1; o < 32u; o <<= 1) {
+            u32 const a = __shfl_up_sync(ZB_FULL, inL, o), c = __shfl_up_sync(ZB_FULL, inA, o);
+            if (lane >= o) { inL += a; inA += c; }
+        }
+        if (lane == 31u) { wsumL[warp] = inL; wsumA[warp] = inA; }
+        __syncthreads();
+        u32 offL = baseL + inL - myL, offA = baseA + inA - myA;
+        for (u32 w = 0; w < warp; w++) { offL += wsumL[w]; offA += wsumA[w]; }
+#pragma unroll
+        for (u32 j = 0; j < 4u; j++) {
+            u32 const i = tid * 4u + j;
+            if (i < n) { sPos[i] = offA; sLit[i] = offL; sLen[i] = ll[j]; }
+            offL += ll[j]; offA += adv[j];
+        }
+        __syncthreads();
+        if (tid == MERGE_THREADS - 1u) { baseL = offL; baseA = offA; }     /* totals up to the end of this tile */
+        for (u32 i = warp; i < n; i += MERGE_THREADS / 32u) {
+            u32 const len = sLen[i];
+            const u8* const from = in + sPos[i];
+            u8* const to = mylit + sLit[i];
+            for (u32 x = lane; x < len; x += 32u) to[x] = from[x];
+        }
+        __syncthreads();
+    }
+    u32 const litSeq = baseL, consumed = baseA;                   /* literals in sequences, bytes covered by sequences */
+    u32 const lastLits = bd.size - consumed;
+    for (u32 x = tid; x < lastLits; x += MERGE_THREADS) mylit[litSeq + x] = in[consumed + x];
+    /* ---- 3. meta ---- */
     if (tid == 0) {
-        ZbBlockMeta m; m.nbSeq = seqOff; m.litSize = litOff; m.litSecSize = 0; m.bodySize = 0;
+        ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litSeq + lastLits; m.litSecSize = 0; m.bodySize = 0;
+        m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
+        meta[b] = m;
+    }
+}
+
+/* K1c for calls made of short frames (one segment per block, so the sequences are already in place): one warp per
+ * block, 8 blocks per CTA; every lane gathers the literals of its own sequences. */
+__global__ void __launch_bounds__(MERGE_THREADS)
+zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
+                      const u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const b = blockIdx.x * (MERGE_THREADS / 32u) + (threadIdx.x >> 5);
+    if (b >= nbBlocks) return;
+    ZbBlock const bd = blocks[b];
+    if (bd.size < 7u) return;
+    const u64* const myseq = seqs + (size_t)b * sd.seq;
+    u8* const mylit = lits + (size_t)b * sd.lit;
+    const u8* const in = src + bd.srcOff;
+    u32 const nbSeq = segmeta[b].nbSeq;
+    u32 posL = 0, posA = 0;
+    for (u32 t0 = 0; t0 < nbSeq; t0 += 32u) {
+        u32 const i = t0 + lane;
+        u64 const q = (i < nbSeq) ? myseq[i] : 0ull;
+        u32 const ll = (u32)((q >> 24) & 0x3FFFFu), adv = ll + (u32)(q >> 42);
+        u32 inL = ll, inA = adv;
+#pragma unroll
+        for (u32 o = 1; o < 32u; o <<= 1) {
+            u32 const x = __shfl_up_sync(ZB_FULL, inL, o), y = __shfl_up_sync(ZB_FULL, inA, o);
+            if (lane >= o) { inL += x; inA += y; }
+        }
+        const u8* const from = in + posA + inA - adv;
+        u8* const to = mylit + posL + inL - ll;
+        for (u32 x = 0; x < ll; x++) to[x] = from[x];
+        posL += __shfl_sync(ZB_FULL, inL, 31); posA += __shfl_sync(ZB_FULL, inA, 31);
+    }
+    u32 const lastLits = bd.size - posA;
+    for (u32 x = lane; x < lastLits; x += 32u) mylit[posL + x] = in[posA + x];
+    if (lane == 0) {
+        ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = posL + lastLits; m.litSecSize = 0; m.bodySize = 0;
         m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
         meta[b] = m;
     }
@@ -539,7 +620,6 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
     u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
-    u8*  const mylit = lits + (size_t)b * sd.lit + (size_t)k * ZB_PARSE_SEG;
     const u16* const dLp = distLong + (size_t)b * sd.dist;
     const u16* const dSp = distShort + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;
@@ -561,7 +641,7 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     }
     u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
     u32 ip = ss, anchor = ss, searchStart = ss;
-    u32 rep1 = 0, rep2 = 0, nbSeq = 0, litPos = 0;
+    u32 rep1 = 0, rep2 = 0, nbSeq = 0;
     u32 pf = ss;
 
     while (ip + 9u <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
@@ -632,14 +712,11 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
         else if (wtype == 2u && litLen > 0u) offBase = 1u;
         else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
         if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
-        for (u32 i = lane; i < litLen; i += 32) mylit[litPos + i] = base[anchor + i];
-        litPos += litLen; nbSeq++;
+        nbSeq++;                                               /* the literal bytes are gathered by the merge kernel */
         ip = ms + mlen; anchor = ip; searchStart = ip;
     }
     u32 const lastLits = be - anchor;
-    for (u32 i = lane; i < lastLits; i += 32) mylit[litPos + i] = base[anchor + i];
-    litPos += lastLits;
-    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = litPos; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = 0; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
 }
 
 static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, const ZbStrides& sd, u16* d_dist,
@@ -686,7 +763,10 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
         u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
         u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);
         zb_parse_dfast_kernel<<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_lits, d_meta, d_segmeta);
-        zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        if (segs == 1u && sd.dist <= 8192u)
+            zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        else
+            zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_src, d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
     } else {
         zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_image, nullptr, stream);
         if (evMid) cudaEventRecord(evMid, stream);
@@ -694,7 +774,10 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
         u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);                   /* one warp per segment */
         if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
         else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
-        zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        if (segs == 1u && sd.dist <= 8192u)
+            zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        else
+            zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_src, d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
     }
     return cudaGetLastError();
 }
