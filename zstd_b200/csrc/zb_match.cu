@@ -1,19 +1,20 @@
-/* zb_match.cu — K1: warp-per-block greedy LZ77 match-finder ("fast" strategy).
+/* zb_match.cu — K1: LZ77 match-finder ("fast" and "doubleFast" strategies) = K1a candidate walk, K1b greedy parse, K1c merge.
  *
- * Replaces the CPU loop ZSTD_compressBlock_fast_noDict_generic
- * (/root/reference/lib/compress/zstd_fast.c:192-423) with a data-parallel formulation:
- *   - one warp owns one <=128 KiB block;
- *   - K1a walks a private hash table (2^hashLog u16 entries in shared memory, positions modulo
- *     64 KiB relative to the start of the visible history, primed from the <=64 KiB in front of the
- *     block: zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:726-731 for job overlaps)
- *     and records every position's candidate distance; insertion follows a fixed position pattern,
- *     so this walk does not depend on the parse;
- *   - K1b does the greedy selection: 32 probe positions per step — pairs (p, p+1) spaced by `step`
- *     as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward catch-up
- *     (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are
- *     warp-cooperative: 32 x 8 bytes per round, first differing lane found by ballot.
+ * Replaces the CPU loops ZSTD_compressBlock_fast_noDict_generic / _extDict_generic
+ * (/root/reference/lib/compress/zstd_fast.c:192-423, :709-960) and ZSTD_compressBlock_doubleFast_noDict_generic
+ * (zstd_double_fast.c:105-323) with a data-parallel formulation; a <=128 KiB block is the independent unit:
+ *   - K1a (one warp per block) walks a private hash table in shared memory (2^hashLog buckets: 16-bit position
+ *     modulo 64 KiB relative to the start of the visible history + 8-bit tag), primed from the <=64 KiB in front of
+ *     the block (zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:726-731 for job overlaps), and
+ *     records every position's candidate distance; insertion follows a fixed position pattern, so the walk does not
+ *     depend on the parse;
+ *   - K1b (one warp per 16 KiB segment of the block) does the greedy selection: 32 probe positions per step — pairs
+ *     (p, p+1) spaced by `step` as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward
+ *     catch-up (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are warp-cooperative:
+ *     32 x 8 bytes per round, first differing lane found by ballot.  It emits packed sequences only;
+ *   - K1c (one CTA per block) joins the segments' sequences and gathers the literal bytes from the input.
  * Table writes are deterministic: the highest inserted lane of a step wins a bucket.
- * The bit-exact CPU model of this kernel is oracle/zb_match.c (tests only).
+ * The bit-exact CPU model of these kernels is oracle/zb_match.c (tests only).
  */
 #include <cuda_pipeline.h>
 #include "zb_device.cuh"
@@ -340,7 +341,7 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
 template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
 zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
-                const u16* __restrict__ dist, u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
+                const u16* __restrict__ dist, u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment: the warps of a CTA share a block's history in L1/L2 */
@@ -611,7 +612,7 @@ zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
 __global__ void __launch_bounds__(32 * PARSE_WARPS)
 zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
                       const u16* __restrict__ distLong, const u16* __restrict__ distShort,
-                      u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
+                      u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment, as in zb_parse_kernel */
@@ -762,7 +763,7 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
         if (evMid) cudaEventRecord(evMid, stream);
         u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
         u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);
-        zb_parse_dfast_kernel<<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_lits, d_meta, d_segmeta);
+        zb_parse_dfast_kernel<<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_meta, d_segmeta);
         if (segs == 1u && sd.dist <= 8192u)
             zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
         else
@@ -772,8 +773,8 @@ extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, con
         if (evMid) cudaEventRecord(evMid, stream);
         u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
         u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);                   /* one warp per segment */
-        if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
-        else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_lits, d_meta, d_segmeta);
+        if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_meta, d_segmeta);
+        else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_meta, d_segmeta);
         if (segs == 1u && sd.dist <= 8192u)
             zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
         else
