@@ -5,6 +5,7 @@ flight) settings; plus a plain pinned H2D / D2H copy of the same bytes as the PC
 import os, sys, time, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch, zref, zstd_b200
 
 
@@ -31,7 +32,7 @@ def main():
         torch.cuda.synchronize(); t2 = time.perf_counter()
     print(f"PCIe floor: H2D 1 GiB {1e3*(t1-t0):.2f} ms ({G/(t1-t0)/1e9:.1f} GB/s); H2D 1 GiB + D2H 341 MiB concurrently {1e3*(t2-t1):.2f} ms", flush=True)
     base = None
-    for wbk, slots in ((768, 4), (768, 6), (512, 6), (512, 8), (384, 6), (384, 8), (256, 8), (256, 12)):
+    for wbk, slots in ((512, 8), (512, 6), (384, 8), (256, 8), (256, 12), (128, 12), (768, 6)):
         os.environ["ZSTDB200_HOST_WAVE_BLOCKS"] = str(wbk); os.environ["ZSTDB200_WAVE_SLOTS"] = str(slots)
         ctx = zstd_b200.ZSTD_CCtx()
         ts = []

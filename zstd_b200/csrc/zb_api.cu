@@ -96,8 +96,8 @@ static int g_device = -1;
 
 #define ZB_WAVE_SLOTS_MAX 14u
 #define ZB_WAVE_SLOTS_DEFAULT 4u
-#define ZB_HOST_WAVE_SLOTS_DEFAULT 8u   /* measured best with 512-block waves (tests/e2e_sweep.py, profiles/r1_e2e_timeline.md) */
-#define ZB_HOST_WAVE_BLOCKS 512u     /* 64 MiB of input per wave */
+#define ZB_HOST_WAVE_SLOTS_DEFAULT 8u   /* measured best with 384-block waves (tests/e2e_sweep.py, profiles/r1_e2e_timeline.md) */
+#define ZB_HOST_WAVE_BLOCKS 384u     /* 48 MiB of input per wave */
 /* Digested dictionary (lib/zstd.h:979, zstd_compress.c:5477-5642): the content tail, its entropy tables and
  * the primed hash-table images live on the device across calls; any number of contexts may use it. */
 struct ZSTD_CDict_s {

@@ -471,7 +471,10 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
  *    literal bytes at all), then the block's last literals;
  * 3. the block's meta record is written. */
 #define MERGE_THREADS 256
+#ifndef MERGE_TILE
 #define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
+#endif
+#define MERGE_PER (MERGE_TILE / MERGE_THREADS)  /* consecutive sequences of a tile owned by one thread */
 __global__ void __launch_bounds__(MERGE_THREADS)
 zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
                          u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
@@ -513,11 +516,11 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
     /* ---- 2. literals ---- */
     for (u32 t0 = 0; t0 < nbSeq; t0 += MERGE_TILE) {
         u32 const n = min(MERGE_TILE, nbSeq - t0);
-        /* every thread owns 4 consecutive sequences of the tile */
-        u32 ll[4], adv[4], myL = 0, myA = 0;
+        /* every thread owns MERGE_PER consecutive sequences of the tile */
+        u32 ll[MERGE_PER], adv[MERGE_PER], myL = 0, myA = 0;
 #pragma unroll
-        for (u32 j = 0; j < 4u; j++) {
-            u32 const i = tid * 4u + j;
+        for (u32 j = 0; j < MERGE_PER; j++) {
+            u32 const i = tid * MERGE_PER + j;
             u64 const q = (i < n) ? myseq[t0 + i] : 0ull;
             ll[j] = (u32)((q >> 24) & 0x3FFFFu);
             adv[j] = ll[j] + (u32)(q >> 42);
@@ -534,8 +537,8 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
         u32 offL = baseL + inL - myL, offA = baseA + inA - myA;
         for (u32 w = 0; w < warp; w++) { offL += wsumL[w]; offA += wsumA[w]; }
 #pragma unroll
-        for (u32 j = 0; j < 4u; j++) {
-            u32 const i = tid * 4u + j;
+        for (u32 j = 0; j < MERGE_PER; j++) {
+            u32 const i = tid * MERGE_PER + j;
             if (i < n) { sPos[i] = offA; sLit[i] = offL; sLen[i] = ll[j]; }
             offL += ll[j]; offA += adv[j];
         }
