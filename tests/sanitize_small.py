@@ -20,4 +20,17 @@ t = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
 cap = 64 * (zstd_b200.ZSTD_compressBound(1024) + 32)
 out = torch.empty(cap, dtype=torch.uint8, device="cuda")
 total, csz = ctx.compress_frames(out.data_ptr(), cap, t.data_ptr(), [i * 1024 for i in range(64)], [1024] * 64, level=1, dict_bytes=d)
+# digested dictionary: single calls and a batch (cached table image, warp-per-block merge / copy kernels)
+cd = zstd_b200.ZSTD_CDict(d, 1)
+for i in range(4):
+    r = recs[i * 1024:(i + 1) * 1024]
+    assert ctx.compress_using_cdict(r, cd) == zref.oracle_compress_using_dict(r, d, 1)
+total2, csz2 = ctx.compress_frames_using_cdict(out.data_ptr(), cap, t.data_ptr(), [i * 1024 for i in range(64)], [1024] * 64, cd)
+assert (total2, csz2) == (total, csz)
+cd.close()
+# sizes around the parse-segment boundaries, several blocks, host path (waves) and device path
+for n in (16383, 16385, 16391, 131071, 131073, 147461, 400_003):
+    src = zref.synthetic(n, n % 11, 0.6)
+    for level in (1, 3):
+        assert ctx.compress(src, level) == zref.oracle_compress(src, level)
 print("sanitize workload ok", total)
