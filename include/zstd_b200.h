@@ -61,6 +61,36 @@ ZSTDB200_API size_t      ZSTD_compress_usingCDict(ZSTD_CCtx* cctx, void* dst, si
 ZSTDB200_API unsigned    ZSTD_getDictID_fromCDict(const ZSTD_CDict* cdict);
 ZSTDB200_API unsigned    ZSTD_getDictID_fromDict(const void* dict, size_t dictSize);
 
+/* lib/zstd.h:337-603 — the advanced one-shot API most bindings use today: sticky parameters on the context, then
+ * ZSTD_compress2.  Honoured: ZSTD_c_compressionLevel, ZSTD_c_checksumFlag (XXH64 of the content, computed on the
+ * host while the GPU compresses — such a frame is bound by that serial pass, ~10 GB/s; host buffers only),
+ * ZSTD_c_dictIDFlag, ZSTD_c_contentSizeFlag (the size is always written).  Accepted and ignored: ZSTD_c_nbWorkers,
+ * ZSTD_c_jobSize, ZSTD_c_overlapLog.  windowLog .. strategy and the long-distance-matching parameters only at 0;
+ * anything else returns ZSTD_error_parameter_unsupported (40).  ZSTD_CCtx_loadDictionary copies and digests the
+ * dictionary (lib/zstd.h:1088); ZSTD_CCtx_refCDict borrows a CDict, whose level then applies (:1102). */
+typedef enum {
+    ZSTD_c_compressionLevel = 100, ZSTD_c_windowLog = 101, ZSTD_c_hashLog = 102, ZSTD_c_chainLog = 103, ZSTD_c_searchLog = 104,
+    ZSTD_c_minMatch = 105, ZSTD_c_targetLength = 106, ZSTD_c_strategy = 107,
+    ZSTD_c_enableLongDistanceMatching = 160,
+    ZSTD_c_contentSizeFlag = 200, ZSTD_c_checksumFlag = 201, ZSTD_c_dictIDFlag = 202,
+    ZSTD_c_nbWorkers = 400, ZSTD_c_jobSize = 401, ZSTD_c_overlapLog = 402
+} ZSTD_cParameter;
+typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
+ZSTDB200_API size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, ZSTD_cParameter param, int value);
+ZSTDB200_API size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* cctx, unsigned long long pledgedSrcSize);
+ZSTDB200_API size_t ZSTD_CCtx_reset(ZSTD_CCtx* cctx, ZSTD_ResetDirective reset);
+ZSTDB200_API size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, size_t dictSize);
+ZSTDB200_API size_t ZSTD_CCtx_refCDict(ZSTD_CCtx* cctx, const ZSTD_CDict* cdict);
+ZSTDB200_API size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+
+/* lib/zstd.h:681-803 — only the one-shot form of the streaming call (:787): the first call carries the whole input,
+ * asks for ZSTD_e_end and offers at least ZSTD_compressBound(input) bytes of room; it then behaves like
+ * ZSTD_compress2 and returns 0.  Any other use returns ZSTD_error_stage_wrong (60): streaming is out of scope. */
+typedef struct ZSTD_inBuffer_s  { const void* src; size_t size; size_t pos; } ZSTD_inBuffer;
+typedef struct ZSTD_outBuffer_s { void* dst; size_t size; size_t pos; } ZSTD_outBuffer;
+typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;
+ZSTDB200_API size_t ZSTD_compressStream2(ZSTD_CCtx* cctx, ZSTD_outBuffer* output, ZSTD_inBuffer* input, ZSTD_EndDirective endOp);
+
 /* lib/zstd.h:236,242-246,114-120 ; lib/zstd_errors.h:106 */
 ZSTDB200_API size_t      ZSTD_compressBound(size_t srcSize);
 ZSTDB200_API unsigned    ZSTD_isError(size_t code);

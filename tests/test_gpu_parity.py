@@ -260,3 +260,77 @@ def test_cdict_errors():
     assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 32           # dictionary_wrong, zstd_compress.c:5753
     assert L.ZSTD_freeCDict(None) == 0
     c.close()
+
+
+def _with_checksum(frame: bytes, src: bytes) -> bytes:
+    """What a checksummed frame must be, given the same frame without checksum: Content_Checksum_flag set in the frame
+    header descriptor and the low 32 bits of XXH64(content, 0) behind the last block (zstd_compress.c:4629, :5297-5303);
+    XXH64 taken from the compiled reference (ZSTD_XXH64, lib/common/xxhash.h)."""
+    R = zref.ref()
+    R.ZSTD_XXH64.restype = ctypes.c_ulonglong
+    R.ZSTD_XXH64.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_ulonglong]
+    h = R.ZSTD_XXH64(src, len(src), 0) & 0xFFFFFFFF
+    return frame[:4] + bytes([frame[4] | 4]) + frame[5:] + h.to_bytes(4, "little")
+
+
+@pytest.mark.parametrize("name", ["empty", "seven", "syn-5000", "syn-128k+1", "syn-400000", "seg-rep", "rand-100k"])
+def test_compress2_parameters_and_checksum(name):
+    """ZSTD_CCtx_setParameter + ZSTD_compress2 (lib/zstd.h:337-603): level and checksum parameters are sticky, the frame
+    equals the simple API's frame (plus flag and XXH64 word when the checksum is on), the reference decoder accepts it
+    (it verifies the checksum), unsupported parameters answer parameter_unsupported."""
+    src = CASES[name]
+    c = zstd_b200.ZSTD_CCtx()
+    for level in (1, -3, 3):
+        c.set_parameter("compression_level", level)
+        plain = c.compress2(src)
+        assert plain == zref.oracle_compress(src, level)
+        c.set_parameter("checksum_flag", 1)
+        c.set_parameter("nb_workers", 4)                       # accepted, ignored
+        got = c.compress2(src)
+        if zref.have_ref():
+            assert got == _with_checksum(plain, src)
+            assert zref.ref_decompress(got, len(src)) == src
+        assert got == c.compress2(src)                         # sticky + deterministic
+        c.reset(2)                                              # parameters back to defaults (level 3, no checksum)
+        assert c.compress2(src) == zref.oracle_compress(src, 3)
+    with pytest.raises(zstd_b200.ZstdError) as e:
+        c.set_parameter(101, 20)                                # ZSTD_c_windowLog
+    assert e.value.code == 40
+    c.close()
+
+
+def test_compress2_dictionaries_and_stream2_oneshot(ctx):
+    d = zref.golden_input("zdict-16k-synthetic-seed77")
+    src = zref.synthetic(3000, 31, 0.5)
+    c = zstd_b200.ZSTD_CCtx()
+    c.set_parameter("compression_level", 1)
+    c.load_dictionary(d)                                        # ZSTD_CCtx_loadDictionary: sticky
+    want = zref.oracle_compress_using_dict(src, d, 1)
+    assert c.compress2(src) == want and c.compress2(src) == want
+    c.set_parameter("dict_id_flag", 0)                          # same frame without the dictID field
+    got = c.compress2(src)
+    assert (got[4] & 3) == 0 and len(got) < len(want)
+    if zref.have_ref():
+        assert zref.ref_decompress_using_dict(got, d, len(src)) == src
+    c.set_parameter("dict_id_flag", 1)
+    c.load_dictionary(None)
+    assert c.compress2(src) == zref.oracle_compress(src, 1)
+    cd = zstd_b200.ZSTD_CDict(d, -3)
+    c.ref_cdict(cd)                                             # the CDict's level applies (zstd_compress.c:5836)
+    assert c.compress2(src) == zref.oracle_compress_using_dict(src, d, -3)
+    c.ref_cdict(None)
+    # ZSTD_compressStream2, one-shot form (lib/zstd.h:787)
+    L = zstd_b200.lib()
+
+    class Buf(ctypes.Structure):
+        _fields_ = [("p", ctypes.c_void_p), ("size", ctypes.c_size_t), ("pos", ctypes.c_size_t)]
+    cap = zstd_b200.ZSTD_compressBound(len(src))
+    dst = ctypes.create_string_buffer(cap)
+    sbuf = ctypes.create_string_buffer(src, len(src))
+    o = Buf(ctypes.cast(dst, ctypes.c_void_p), cap, 0); i = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(src), 0)
+    r = L.ZSTD_compressStream2(c._h, ctypes.byref(o), ctypes.byref(i), 2)
+    assert r == 0 and i.pos == len(src) and dst.raw[:o.pos] == zref.oracle_compress(src, 1)
+    o2 = Buf(ctypes.cast(dst, ctypes.c_void_p), 10, 0); i2 = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(src), 0)
+    r = L.ZSTD_compressStream2(c._h, ctypes.byref(o2), ctypes.byref(i2), 0)          # ZSTD_e_continue: not served
+    assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 60
+    cd.close(); c.close()

@@ -92,6 +92,18 @@ def lib() -> ctypes.CDLL:
     L.ZSTD_getDictID_fromCDict.argtypes = [_vp]
     L.ZSTD_getDictID_fromDict.restype = ctypes.c_uint
     L.ZSTD_getDictID_fromDict.argtypes = [_vp, _sz]
+    L.ZSTD_CCtx_setParameter.restype = _sz
+    L.ZSTD_CCtx_setParameter.argtypes = [_vp, ctypes.c_int, ctypes.c_int]
+    L.ZSTD_CCtx_reset.restype = _sz
+    L.ZSTD_CCtx_reset.argtypes = [_vp, ctypes.c_int]
+    L.ZSTD_CCtx_loadDictionary.restype = _sz
+    L.ZSTD_CCtx_loadDictionary.argtypes = [_vp, _vp, _sz]
+    L.ZSTD_CCtx_refCDict.restype = _sz
+    L.ZSTD_CCtx_refCDict.argtypes = [_vp, _vp]
+    L.ZSTD_compress2.restype = _sz
+    L.ZSTD_compress2.argtypes = [_vp, _vp, _sz, _vp, _sz]
+    L.ZSTD_compressStream2.restype = _sz
+    L.ZSTD_compressStream2.argtypes = [_vp, _vp, _vp, ctypes.c_int]
     L.ZSTDB200_compressFrames_usingCDict.restype = _sz
     L.ZSTDB200_compressFrames_usingCDict.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_int, _vp]
     _lib = L
@@ -189,6 +201,33 @@ class ZSTD_CCtx:
         cap = ZSTD_compressBound(n)
         dst = ctypes.create_string_buffer(max(cap, 1))
         r = _check(lib().ZSTD_compress_usingCDict(self._h, dst, cap, p, n, cdict._h))
+        return dst.raw[:r]
+
+    # -- advanced one-shot API (lib/zstd.h:337-603) --
+    PARAMS = {"compression_level": 100, "content_size_flag": 200, "checksum_flag": 201, "dict_id_flag": 202, "nb_workers": 400}
+
+    def set_parameter(self, name_or_id, value: int) -> None:
+        """ZSTD_CCtx_setParameter: sticky until ZSTD_CCtx_reset(parameters)."""
+        pid = self.PARAMS.get(name_or_id, name_or_id)
+        _check(lib().ZSTD_CCtx_setParameter(self._h, int(pid), int(value)))
+
+    def reset(self, directive: int = 3) -> None:
+        """ZSTD_CCtx_reset: 1 session only, 2 parameters, 3 both."""
+        _check(lib().ZSTD_CCtx_reset(self._h, directive))
+
+    def load_dictionary(self, dict_bytes) -> None:
+        p, n, keep = (None, 0, None) if not dict_bytes else _buf(dict_bytes)
+        _check(lib().ZSTD_CCtx_loadDictionary(self._h, p, n))
+
+    def ref_cdict(self, cdict: Optional["ZSTD_CDict"]) -> None:
+        _check(lib().ZSTD_CCtx_refCDict(self._h, cdict._h if cdict is not None else None))
+
+    def compress2(self, src) -> bytes:
+        """ZSTD_compress2 with the context's sticky parameters / dictionary."""
+        p, n, keep = _buf(src)
+        cap = ZSTD_compressBound(n) + 8
+        dst = ctypes.create_string_buffer(max(cap, 1))
+        r = _check(lib().ZSTD_compress2(self._h, dst, cap, p, n))
         return dst.raw[:r]
 
     # -- B200 extensions --

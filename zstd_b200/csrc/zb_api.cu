@@ -139,6 +139,12 @@ struct ZSTD_CCtx_s {
     u64* h_totals;                 /* pinned mirror of d_totals */
     cudaEvent_t evStart, evK0, evMid, evK1, evK2, evK3, evKEnd, evEnd;
     ZSTDB200_stats stats;
+    /* advanced one-shot API (ZSTD_CCtx_setParameter + ZSTD_compress2, lib/zstd.h:337-603): sticky parameters */
+    int advLevel, advChecksum, advNoDictID;
+    ZSTD_CDict* advLocalDict;      /* ZSTD_CCtx_loadDictionary: owned copy, digested at its first use */
+    const ZSTD_CDict* advRefCDict; /* ZSTD_CCtx_refCDict: borrowed */
+    /* per-call frame options, consumed by the planner */
+    u32 callChecksum, callNoDictID;
 };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -160,6 +166,7 @@ extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
     ZSTD_CCtx* c = (ZSTD_CCtx*)calloc(1, sizeof(ZSTD_CCtx));
     if (!c) return NULL;
     c->device = -1;
+    c->advLevel = 3;                                                         /* ZSTD_CLEVEL_DEFAULT */
     {   const char* s = getenv("ZSTDB200_SERIAL"); const char* w = getenv("ZSTDB200_WAVE_BLOCKS");
         c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 1024u);     /* 128 MiB waves: tests/wave_sweep.py */
         const char* n = getenv("ZSTDB200_WAVE_SLOTS"); const char* h = getenv("ZSTDB200_HOST_WAVE_BLOCKS");
@@ -199,9 +206,11 @@ static void zb_freeWorkspace(ZSTD_CCtx* c)
     c->capBlocks = 0; c->capFrames = 0; c->capWaves = 0; memset(c->capHeavyBytes, 0, sizeof(c->capHeavyBytes));
 }
 
+extern "C" size_t ZSTD_freeCDict(ZSTD_CDict* cd);
 extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 {
     if (!c) return 0;
+    ZSTD_freeCDict(c->advLocalDict);
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
@@ -274,7 +283,7 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides&
 struct ZbGroup { ZbParams prm; u32 b0, b1; const u8* image; };   /* image: table primed from the dictionary tail, or NULL */
 struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported; };
 
-static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
+static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
                     size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
 {
     P.frames.resize(nbFrames);
@@ -290,7 +299,7 @@ static void zb_plan(ZbPlan& P, const size_t* frameOffsets, const size_t* frameSi
         if (dictRep) { prm.startRep[0] = dictRep[0] <= dictTail ? dictRep[0] : 0u; prm.startRep[1] = dictRep[1] <= dictTail ? dictRep[1] : 0u; }
         size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
         ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)P.blocks.size();
-        fr.windowLog = cp.windowLog; fr.dictID = dictID;
+        fr.windowLog = cp.windowLog; fr.dictID = dictID; fr.checksum = frameChecksum; fr.pad = 0;
         u64 pos = 0;
         do {
             u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
@@ -440,10 +449,11 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
                                       const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
                                       const void* dict, size_t dictSize, const ZSTD_CDict* cdict, size_t* cSizes, int level, cudaStream_t stream)
 {
+    if (c->callChecksum) return ZB_ERR(ZB_error_parameter_unsupported);      /* the frame checksum is computed by the host: host-buffer calls only */
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
+    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
@@ -479,6 +489,34 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     return (size_t)total;
 }
 
+/* XXH64 (lib/common/xxhash.h: XXH64_update / XXH64_digest, seed 0) of the frame's content: the frame checksum is
+ * its low 32 bits (zstd_compress.c:5297-5303).  A serial recurrence over 32-byte stripes: it runs on the calling
+ * host thread while the GPU works (about 10 GB/s — a checksummed frame is bound by this pass, not by the GPU). */
+static u64 zb_xxh64(const u8* p, size_t len)
+{
+    u64 const P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    auto rotl = [](u64 x, int r) { return (x << r) | (x >> (64 - r)); };
+    auto rd64 = [](const u8* q) { u64 v; memcpy(&v, q, 8); return v; };
+    auto rd32 = [](const u8* q) { u32 v; memcpy(&v, q, 4); return v; };
+    auto round = [&](u64 acc, u64 in) { return rotl(acc + in * P2, 31) * P1; };
+    auto merge = [&](u64 acc, u64 v) { return (acc ^ round(0, v)) * P1 + P4; };
+    const u8* const end = p + len;
+    u64 h;
+    if (len >= 32) {
+        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        const u8* const limit = end - 32;
+        do { v1 = round(v1, rd64(p)); v2 = round(v2, rd64(p + 8)); v3 = round(v3, rd64(p + 16)); v4 = round(v4, rd64(p + 24)); p += 32; } while (p <= limit);
+        h = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+        h = merge(h, v1); h = merge(h, v2); h = merge(h, v3); h = merge(h, v4);
+    } else h = P5;
+    h += (u64)len;
+    while (p + 8 <= end) { h ^= round(0, rd64(p)); h = rotl(h, 27) * P1 + P4; p += 8; }
+    if (p + 4 <= end) { h ^= (u64)rd32(p) * P1; h = rotl(h, 23) * P2 + P3; p += 4; }
+    while (p < end) { h ^= (u64)(*p) * P5; h = rotl(h, 11) * P1; p++; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 /* ------------------------------------------------------------------ host pointers: pipelined waves
  * H2D copy of wave w+1 | kernels of waves w, w-1, ... (one stream + workspace slot each) | D2H of finished waves.
  * A block needs ~ms of latency end to end (one warp walks it), so several waves are kept in flight. */
@@ -506,9 +544,10 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
+    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
+    if (c->callChecksum && (deviceMemory || nbFrames != 1)) return ZB_ERR(ZB_error_parameter_unsupported);   /* the checksum is a host pass over one frame */
     /* a wave is sized in bytes of input (and of workspace): calls made of small blocks get proportionally more blocks per wave */
     u32 const ZB_WAVE_BLOCKS = (u32)((u64)waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist) > (1u << 22) ? (1u << 22) : waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist));
     /* wave boundaries.  Host path: the call ends when the LAST wave has gone through every kernel, so the
@@ -586,6 +625,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         }
     }
     double const hostEnq = zb_now() - hostT0;
+    u64 const xxh = (c->callChecksum && !err) ? zb_xxh64(src + frameOffsets[0], frameSizes[0]) : 0;      /* while the GPU works */
     u64 prev = 0, total = 0;
     if (download || timeline) {
         /* drain: as each wave's size becomes known, ship its bytes */
@@ -611,6 +651,10 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     for (u32 s = 0; s < slots; s++) if (c->waveStream[s]) CK(cudaStreamSynchronize(c->waveStream[s]));
     CK(cudaStreamSynchronize(sCopy));
     if (!err && nbWaves) total = c->h_totals[nbWaves - 1];
+    if (!err && c->callChecksum && total >= 4 && total <= dstCapacity) {                                  /* the 4 bytes the stitch kernel left free */
+        u32 const ck = (u32)xxh;
+        dst[total - 4] = (u8)ck; dst[total - 3] = (u8)(ck >> 8); dst[total - 2] = (u8)(ck >> 16); dst[total - 1] = (u8)(ck >> 24);
+    }
     if (timeline) {
         fprintf(stderr, "zstd_b200 timeline (ms after the call's first enqueue; host enqueue loop took %.3f ms; %s)\n", 1e3 * hostEnq,
                 deviceMemory ? "device buffers" : "per-wave downloads");
@@ -747,6 +791,87 @@ extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstC
 }
 
 extern "C" void ZSTDB200_getLastStats(const ZSTD_CCtx* c, ZSTDB200_stats* out) { if (c && out) *out = c->stats; }
+
+
+/* ------------------------------------------------------------------ advanced one-shot API (lib/zstd.h:337-603, :1088-1102)
+ * ZSTD_CCtx_setParameter + ZSTD_compress2 is how python-zstandard, zstd-jni and the zstd CLI drive the library today.
+ * Supported: compressionLevel, checksumFlag (XXH64 of the content on the host), contentSizeFlag (always written),
+ * dictIDFlag, nbWorkers / jobSize / overlapLog (accepted and ignored: parallelism is the GPU's), the cParams only at
+ * their default 0; everything else answers parameter_unsupported.  ZSTD_compressStream2 serves the one-shot form
+ * (first call, ZSTD_e_end, output room >= ZSTD_compressBound: lib/zstd.h:787) — real streaming is out of scope. */
+extern "C" size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* c, ZSTD_cParameter paramE, int value)                 /* zstd_compress.c:720 */
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    int const param = (int)paramE;
+    switch (param) {
+    case 100: c->advLevel = value == 0 ? 3 : (value > 22 ? 22 : (value < -(int)ZB_BLOCK_MAX ? -(int)ZB_BLOCK_MAX : value)); return 0;   /* ZSTD_c_compressionLevel */
+    case 200: return 0;                                                                      /* ZSTD_c_contentSizeFlag: the size is always written */
+    case 201: c->advChecksum = value != 0; return 0;                                         /* ZSTD_c_checksumFlag */
+    case 202: c->advNoDictID = value == 0; return 0;                                         /* ZSTD_c_dictIDFlag */
+    case 400: case 401: case 402: return 0;                                                  /* nbWorkers, jobSize, overlapLog */
+    case 101: case 102: case 103: case 104: case 105: case 106: case 107:                    /* windowLog .. strategy: default only */
+    case 160: case 161: case 162: case 163: case 164:                                        /* long distance matching: off only */
+        return value == 0 ? 0 : ZB_ERR(ZB_error_parameter_unsupported);
+    default: return ZB_ERR(ZB_error_parameter_unsupported);
+    }
+}
+
+extern "C" size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* c, unsigned long long) { return c ? 0 : ZB_ERR(ZB_error_GENERIC); }   /* one-shot calls know their size */
+
+extern "C" size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective reset)                                   /* zstd_compress.c:1390; 1 session, 2 parameters, 3 both */
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (reset == 2 || reset == 3) {
+        c->advLevel = 3; c->advChecksum = 0; c->advNoDictID = 0;
+        ZSTD_freeCDict(c->advLocalDict); c->advLocalDict = NULL; c->advRefCDict = NULL;
+    }
+    return 0;
+}
+
+extern "C" size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* c, const void* dict, size_t dictSize)  /* zstd_compress.c:1260: copied, sticky */
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    ZSTD_freeCDict(c->advLocalDict); c->advLocalDict = NULL; c->advRefCDict = NULL;
+    if (!dict || dictSize == 0) return 0;                                                    /* NULL / 0: back to no dictionary */
+    c->advLocalDict = ZSTD_createCDict(dict, dictSize, c->advLevel);
+    return c->advLocalDict ? 0 : ZB_ERR(ZB_error_dictionary_corrupted);
+}
+
+extern "C" size_t ZSTD_CCtx_refCDict(ZSTD_CCtx* c, const ZSTD_CDict* cdict)                  /* zstd_compress.c:1330: borrowed, sticky */
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    ZSTD_freeCDict(c->advLocalDict); c->advLocalDict = NULL;
+    c->advRefCDict = cdict;
+    return 0;
+}
+
+extern "C" size_t ZSTD_compress2(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize)     /* zstd_compress.c:6365 */
+{
+    size_t const off = 0;
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
+    if (dstCapacity < 18) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    const ZSTD_CDict* const cd = c->advRefCDict ? c->advRefCDict : c->advLocalDict;
+    int const level = c->advRefCDict ? c->advRefCDict->level : c->advLevel;                  /* a referenced CDict brings its own level (:5836) */
+    c->callChecksum = (u32)c->advChecksum; c->callNoDictID = (u32)c->advNoDictID;
+    size_t const r = zb_compressFramesAny(c, dst, dstCapacity, src, &off, &srcSize, 1, NULL, 0, cd, NULL, level, 0, NULL);
+    c->callChecksum = 0; c->callNoDictID = 0;
+    return r;
+}
+
+extern "C" size_t ZSTD_compressStream2(ZSTD_CCtx* c, ZSTD_outBuffer* out, ZSTD_inBuffer* in, ZSTD_EndDirective endOp)       /* zstd_compress.c:6176 */
+{
+    if (!c || !out || !in) return ZB_ERR(ZB_error_GENERIC);
+    if (out->pos > out->size) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    if (in->pos > in->size) return ZB_ERR(ZB_error_srcSize_wrong);
+    size_t const n = in->size - in->pos, room = out->size - out->pos;
+    /* the one-shot form of lib/zstd.h:787: everything is here, the frame ends now, and the output surely fits */
+    if (endOp != ZSTD_e_end || room < ZSTD_compressBound(n)) return ZB_ERR(ZB_error_stage_wrong);
+    size_t const r = ZSTD_compress2(c, (u8*)out->dst + out->pos, room, (const u8*)in->src + in->pos, n);
+    if (ZSTD_isError(r)) return r;
+    in->pos = in->size; out->pos += r;
+    return 0;                                                                                /* frame complete, nothing left to flush */
+}
 
 /* ------------------------------------------------------------------ reference-identical entry points */
 extern "C" size_t ZSTD_compress_usingDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize,

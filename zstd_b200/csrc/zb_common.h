@@ -67,6 +67,8 @@ typedef struct {
     u32 nbBlocks;
     u32 windowLog;
     u32 dictID;
+    u32 checksum;      /* 1: Content_Checksum_flag set, 4 bytes are reserved behind the last block (filled in by the host) */
+    u32 pad;
 } ZbFrame;
 
 typedef struct {       /* produced on the device, one per block */

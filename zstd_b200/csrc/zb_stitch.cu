@@ -9,15 +9,15 @@
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
-/* zstd_compress.c:4626-4672, contentSizeFlag = 1, no checksum.  Returns header size (<= 18). */
-__device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, bool write)
+/* zstd_compress.c:4626-4672, contentSizeFlag = 1.  Returns header size (<= 18). */
+__device__ u32 zbd_frameHeader(u8* dst, u32 windowLog, u64 srcSize, u32 dictID, u32 checksum, bool write)
 {
     u32 const dictIDSizeCode = (dictID > 0) + (dictID >= 256) + (dictID >= 65536);
     bool const singleSegment = ((u64)1 << windowLog) >= srcSize;
     u32 const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256) + (srcSize >= 0xFFFFFFFFull);
     u8 h[18]; u32 pos = 0;
     h[pos++] = 0x28; h[pos++] = 0xB5; h[pos++] = 0x2F; h[pos++] = 0xFD;          /* ZSTD_MAGICNUMBER 0xFD2FB528 */
-    h[pos++] = (u8)(dictIDSizeCode + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));
+    h[pos++] = (u8)(dictIDSizeCode + ((checksum ? 1u : 0u) << 2) + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));
     if (!singleSegment) h[pos++] = (u8)((windowLog - 10u) << 3);
     if (dictIDSizeCode == 1) h[pos++] = (u8)dictID;
     else if (dictIDSizeCode == 2) { h[pos++] = (u8)dictID; h[pos++] = (u8)(dictID >> 8); }
@@ -46,7 +46,11 @@ zb_sizes_scan_kernel(const ZbBlock* __restrict__ blocks, u32 nbBlocks, const ZbF
     for (u32 i = tid; i < nbBlocks; i += SCAN_THREADS) {
         ZbBlock const bd = blocks[i];
         u64 sz = 3u + meta[i].bodySize;
-        if (bd.flags & ZB_FLAG_FIRST) { ZbFrame const f = frames[bd.frame]; sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, false); }
+        if (bd.flags & (ZB_FLAG_FIRST | ZB_FLAG_LAST)) {
+            ZbFrame const f = frames[bd.frame];
+            if (bd.flags & ZB_FLAG_FIRST) sz += zbd_frameHeader(nullptr, f.windowLog, f.srcSize, f.dictID, f.checksum, false);
+            if ((bd.flags & ZB_FLAG_LAST) && f.checksum) sz += 4u;          /* room for the XXH64 low word, zstd_compress.c:5297-5303 */
+        }
         outOffsets[i] = sz;
     }
     __syncthreads();
@@ -93,7 +97,7 @@ zb_copy_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, c
     u32 hdr = 0;
     if (bd.flags & ZB_FLAG_FIRST) {
         ZbFrame const f = frames[bd.frame];
-        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, tid == 0);
+        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, f.checksum, tid == 0);
     }
     out += hdr;
     u32 const lastBlock = (bd.flags & ZB_FLAG_LAST) ? 1u : 0u;
@@ -147,7 +151,7 @@ zb_copy_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blo
     u32 hdr = 0;
     if (bd.flags & ZB_FLAG_FIRST) {
         ZbFrame const f = frames[bd.frame];
-        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, lane == 0);
+        hdr = zbd_frameHeader(out, f.windowLog, f.srcSize, f.dictID, f.checksum, lane == 0);
     }
     out += hdr;
     u32 const lastBlock = (bd.flags & ZB_FLAG_LAST) ? 1u : 0u;
