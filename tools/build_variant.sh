@@ -11,7 +11,7 @@ objs=""
 for f in zb_api zb_dict zb_match zb_literals zb_sequences zb_stitch; do
   if [ "$f.cu" == "$file" ]; then
     nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v $flags -c $f.cu -o /tmp/zbv_$name/$f.o 2> /tmp/zbv_$name/$f.log
-    grep -A1 "zb_parse_kernelILb0\|zb_cand_kernelILi6" /tmp/zbv_$name/$f.log | grep "Used\|spill" || true
+    grep "Used\|spill" /tmp/zbv_$name/$f.log | head -4 || true
     objs="$objs /tmp/zbv_$name/$f.o"
   else objs="$objs $f.o"; fi
 done

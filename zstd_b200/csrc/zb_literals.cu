@@ -15,6 +15,7 @@
 #include "zb_bitpack.cuh"
 
 #define LIT_THREADS 128
+#define LIT_MIN_CTAS 12               /* 16 (32 registers) measured slower: 1.56 vs 1.40 ms */
 #define LIT_WARPS (LIT_THREADS / 32)
 
 /* block-wide histogram of src[0..n) into count[256]; returns nothing, count valid after the call */
@@ -91,14 +92,16 @@ __device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ li
     for (u32 i = aBeg; i-- > beg; ) f(lit[i]);
 }
 
-__global__ void __launch_bounds__(LIT_THREADS)
+__global__ void __launch_bounds__(LIT_THREADS, LIT_MIN_CTAS)
 zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, const ZbDictEntropy* __restrict__ de,
                    const u8* __restrict__ lits, u8* __restrict__ body, ZbBlockMeta* __restrict__ meta)
 {
-    __shared__ u32 whist[LIT_WARPS][256];
+    /* the per-warp histograms are dead once count[] is merged, the Huffman workspace only lives after that: one area */
+    __shared__ __align__(16) u8 scratch[sizeof(ZbdHufWksp) > sizeof(u32) * LIT_WARPS * 256 ? sizeof(ZbdHufWksp) : sizeof(u32) * LIT_WARPS * 256];
+    u32 (* const whist)[256] = reinterpret_cast<u32 (*)[256]>(scratch);
+    ZbdHufWksp& wk = *reinterpret_cast<ZbdHufWksp*>(scratch);
     __shared__ u32 count[256];
     __shared__ u32 enc[256];
-    __shared__ ZbdHufWksp wk;
     __shared__ __align__(16) u8 hdr[144];
     __shared__ u32 red[16];
     __shared__ u32 chunkBits[LIT_THREADS];
