@@ -1,5 +1,5 @@
 set -x
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3; python -c "import __graft_entry__ as g; g.smoke()"; timeout 200 python tests/variant_sweep.py c2 default pfnone 2>&1 | tail -2
 timeout 300 python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; tail -c 2500 gpurun_out/bench_r1_final.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_final.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/b_ncu.log 2>&1; tail -3 gpurun_out/r1_launches_final.csv
 ZSTDB200_SERIAL=1 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:zb_ --csv --log-file gpurun_out/r1_traffic.csv python tests/profile_one.py 1024 50 1 1 > gpurun_out/t_ncu.log 2>&1; cat gpurun_out/r1_traffic.csv | tail -9

@@ -329,15 +329,6 @@ zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
                                     * runs alone, but fills every warp slot: the candidate walk of the next wave no longer fits beside
                                     * it and a whole device-resident call gets 4 % slower (profiles/r1_history.md) */
 #endif
-#ifndef PARSE_PF_INPUT
-#define PARSE_PF_INPUT 1
-#endif
-#ifndef PARSE_PF_DIST
-#define PARSE_PF_DIST 1
-#endif
-#ifndef PARSE_PF_AHEAD
-#define PARSE_PF_AHEAD 512u            /* bytes: ~20 us of parsing; further ahead the lines are evicted from L2 before use */
-#endif
 template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
 zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
@@ -374,24 +365,8 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
     u32 ip = ss, anchor = ss, searchStart = ss;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0;
     if (DICT && (bd.flags & ZB_FLAG_DICT) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
-    u32 pf = ss;                                             /* input and dist[] below this position are on their way to L2 */
 
     while (ip + 8u <= be) {
-        /* the warp consumes its block front to back but every step waits for its loads: keep the next
-         * PARSE_PF_AHEAD bytes of input (and their dist[] entries) streaming into L2, one 128-byte line per lane */
-        if (ip + PARSE_PF_AHEAD > pf && pf < be) {
-            u32 const a = pf + 128u * lane;
-            if (a < be) {
-#if PARSE_PF_INPUT
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
-#endif
-#if PARSE_PF_DIST
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs)));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(mydist + (a - bs) + 64));
-#endif
-            }
-            pf += 128u * 32u;
-        }
         u32 const step = prm.stepSize + ((ip - searchStart) >> 7);           /* kSearchStrength = 8 */
         u32 const p = ip + (lane >> 1) * step + (lane & 1u);
         bool const act = (p + 8u <= be);
@@ -646,20 +621,8 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
     u32 ip = ss, anchor = ss, searchStart = ss;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0;
-    u32 pf = ss;
 
     while (ip + 9u <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
-        if (ip + PARSE_PF_AHEAD > pf && pf < be) {
-            u32 const a = pf + 128u * lane;
-            if (a < be) {
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(dLp + (a - bs)));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(dLp + (a - bs) + 64));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(dSp + (a - bs)));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(dSp + (a - bs) + 64));
-            }
-            pf += 128u * 32u;
-        }
         u32 const step = 1u + ((ip - searchStart) >> 8);                     /* kStepIncr = 1 << kSearchStrength */
         u32 const p = ip + lane * step;
         bool const act = (p + 9u <= be);
