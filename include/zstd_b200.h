@@ -141,6 +141,13 @@ typedef struct {
 } ZSTDB200_stats;
 ZSTDB200_API void ZSTDB200_getLastStats(const ZSTD_CCtx* cctx, ZSTDB200_stats* out);
 
+/* The host planner's view of a call, computed without a GPU (test hook: tests/test_plan.py compares it with the
+ * oracle's plan).  out: nbFrames x 14 unsigned = strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
+ * insPeriod, insPeriodLong, blocks of the frame, first block's size and flags, last block's history length and insertion
+ * phase.  Returns the total number of blocks. */
+ZSTDB200_API size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFrames, int compressionLevel,
+                                          size_t dictSize, size_t dictTail, unsigned* out);
+
 /* Which CUDA device new contexts bind to (default: current device / LOCAL_RANK). */
 ZSTDB200_API int  ZSTDB200_setDevice(int device);
 ZSTDB200_API int  ZSTDB200_deviceAvailable(void);

@@ -334,3 +334,24 @@ def test_compress2_dictionaries_and_stream2_oneshot(ctx):
     r = L.ZSTD_compressStream2(c._h, ctypes.byref(o2), ctypes.byref(i2), 0)          # ZSTD_e_continue: not served
     assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 60
     cd.close(); c.close()
+
+
+def test_mixed_frame_lists(ctx):
+    """Batch call over runs of equal single-block frames (the planner's template path), odd sizes, empty frames and a
+    multi-block frame in between: every frame equals the single-call frame."""
+    import torch
+    sizes = [1024] * 50 + [5000] + [1024] * 3 + [0, 0] + [200_000] + [1024] * 10 + [7, 6, 6, 131072, 131072, 131073]
+    src = zref.synthetic(sum(sizes) + 16, 123, 0.5)
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o); o += n
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = sum(zstd_b200.ZSTD_compressBound(n) + 32 for n in sizes)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    total, csz = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), offs, sizes, level=1)
+    out = bytes(d_dst[:total].cpu().numpy())
+    pos = 0
+    for off, n, c in zip(offs, sizes, csz):
+        assert out[pos:pos + c] == zref.oracle_compress(src[off:off + n], 1), (off, n)
+        pos += c
+    assert pos == total

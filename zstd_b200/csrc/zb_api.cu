@@ -287,10 +287,21 @@ static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, co
                     size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
 {
     P.frames.resize(nbFrames);
+    P.blocks.reserve(nbFrames);
     P.unsupported = false;
     u32 maxBlock = 0;
+    /* calls made of many equal, single-block frames (config 5: a million 1 KiB records): the frame before is the template */
+    u64 tplSize = ~0ull; ZbFrame tplFrame; ZbBlock tplBlock; memset(&tplFrame, 0, sizeof(tplFrame)); memset(&tplBlock, 0, sizeof(tplBlock));
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
+        if (fsz == tplSize) {
+            ZbFrame fr = tplFrame; fr.srcOff = frameOffsets[f]; fr.firstBlock = (u32)P.blocks.size();
+            ZbBlock b = tplBlock; b.srcOff = fr.srcOff; b.frame = (u32)f;
+            P.blocks.push_back(b);
+            P.frames[f] = fr;
+            P.groups.back().b1 = (u32)P.blocks.size();
+            continue;
+        }
         ZbCParams cp = zb_getCParams(level, fsz, dictSize);
         /* the two-segment (dictionary) match-finder exists for the fast strategy only (zstd_fast.c:709): a
          * dictionary call at a doubleFast level runs it with that level's window / hash / minMatch */
@@ -318,6 +329,7 @@ static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, co
         } while (pos < fsz);
         fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
         P.frames[f] = fr;
+        if (fr.nbBlocks == 1u) { tplSize = fsz; tplFrame = fr; tplBlock = P.blocks.back(); } else tplSize = ~0ull;
         if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.image = NULL; P.groups.push_back(g); }
         else P.groups.back().b1 = (u32)P.blocks.size();
     }
@@ -788,6 +800,29 @@ extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstC
 {
     size_t const off = 0;
     return ZSTDB200_compressFrames(c, d_dst, dstCapacity, d_src, &off, &srcSize, 1, NULL, 0, NULL, level, 1, stream);
+}
+
+/* Host-side planning of one call, without touching a GPU (what the CPU tests compare with the oracle's plan).
+ * Per frame, `out` receives ZSTDB200_PLAN_FIELDS values: strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
+ * insPeriod, insPeriodLong, number of blocks, size of the first block, flags of the first block, history of the last
+ * block, insertion phase of the last block.  Returns the total number of blocks. */
+extern "C" size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFrames, int level, size_t dictSize, size_t dictTail, unsigned* out)
+{
+    std::vector<size_t> offs(nbFrames);
+    size_t o = 0; for (size_t f = 0; f < nbFrames; f++) { offs[f] = o; o += frameSizes[f]; }
+    ZbPlan P;
+    zb_plan(P, 0, offs.data(), frameSizes, nbFrames, level, dictSize, dictTail, 0, NULL);
+    for (size_t f = 0; f < nbFrames && out; f++) {
+        ZbFrame const& fr = P.frames[f];
+        const ZbParams* prm = NULL;
+        for (size_t g = 0; g < P.groups.size(); g++) if (P.groups[g].b0 <= fr.firstBlock && fr.firstBlock < P.groups[g].b1) prm = &P.groups[g].prm;
+        ZbBlock const& b0 = P.blocks[fr.firstBlock]; ZbBlock const& bl = P.blocks[fr.firstBlock + fr.nbBlocks - 1];
+        unsigned* r = out + f * 14;
+        r[0] = prm->strategy; r[1] = prm->mls; r[2] = prm->hashLog; r[3] = prm->longHashLog; r[4] = prm->stepSize; r[5] = prm->litDisabled;
+        r[6] = fr.windowLog; r[7] = prm->insPeriod; r[8] = prm->insPeriodLong; r[9] = fr.nbBlocks; r[10] = b0.size; r[11] = b0.flags;
+        r[12] = bl.histLen; r[13] = bl.insPhase;
+    }
+    return P.blocks.size();
 }
 
 extern "C" void ZSTDB200_getLastStats(const ZSTD_CCtx* c, ZSTDB200_stats* out) { if (c && out) *out = c->stats; }

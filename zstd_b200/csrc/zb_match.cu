@@ -690,7 +690,9 @@ static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* 
                            const u8* d_imageIn, u8* d_imageOut, cudaStream_t stream)
 {
     size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
-    static bool optin = false;
+    static bool optinDev[64];                                     /* the attribute is per device */
+    int dev = 0; cudaGetDevice(&dev);
+    bool& optin = optinDev[dev & 63];
     if (!optin) {             /* hashLog 14: 48 KiB of table + the 2 KiB static ring exceeds the default 48 KiB limit */
         cudaFuncSetAttribute(zb_cand_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(zb_cand_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
