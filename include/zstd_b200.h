@@ -141,6 +141,9 @@ typedef struct {
 } ZSTDB200_stats;
 ZSTDB200_API void ZSTDB200_getLastStats(const ZSTD_CCtx* cctx, ZSTDB200_stats* out);
 
+/* XXH64 (seed 0) as used for the frame checksum (lib/common/xxhash.h); host code, no GPU (test hook). */
+ZSTDB200_API unsigned long long ZSTDB200_xxh64(const void* data, size_t size);
+
 /* The host planner's view of a call, computed without a GPU (test hook: tests/test_plan.py compares it with the
  * oracle's plan).  out: nbFrames x 14 unsigned = strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
  * insPeriod, insPeriodLong, blocks of the frame, first block's size and flags, last block's history length and insertion

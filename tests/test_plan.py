@@ -82,3 +82,16 @@ def test_planner_template_path_equals_slow_path():
         one = (ctypes.c_uint * 14)()
         L.ZSTDB200_describePlan((ctypes.c_size_t * 1)(size), 1, 1, 16 << 10, 16 << 10, one)
         assert list(out[14 * f:14 * f + 14]) == list(one), (f, size)
+
+
+@pytest.mark.skipif(not zref.have_ref(), reason="oracle/_ref/libzstd_ref.so not built")
+def test_xxh64_matches_reference():
+    """The checksum of ZSTD_c_checksumFlag frames is XXH64(content, 0) & 0xFFFFFFFF (zstd_compress.c:5297-5303)."""
+    L, R = zstd_b200.lib(), zref.ref()
+    L.ZSTDB200_xxh64.restype = ctypes.c_ulonglong
+    L.ZSTDB200_xxh64.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    R.ZSTD_XXH64.restype = ctypes.c_ulonglong
+    R.ZSTD_XXH64.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_ulonglong]
+    data = zref.random_bytes(100_000, 3)
+    for n in list(range(0, 70)) + [255, 256, 257, 4095, 4096, 65537, 100_000]:
+        assert L.ZSTDB200_xxh64(data[:n], n) == R.ZSTD_XXH64(data[:n], n, 0), n

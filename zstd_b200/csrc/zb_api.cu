@@ -802,6 +802,9 @@ extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstC
     return ZSTDB200_compressFrames(c, d_dst, dstCapacity, d_src, &off, &srcSize, 1, NULL, 0, NULL, level, 1, stream);
 }
 
+/* the frame checksum's hash, exported for the CPU tests (compared with the reference's ZSTD_XXH64) */
+extern "C" unsigned long long ZSTDB200_xxh64(const void* p, size_t len) { return zb_xxh64((const u8*)p, len); }
+
 /* Host-side planning of one call, without touching a GPU (what the CPU tests compare with the oracle's plan).
  * Per frame, `out` receives ZSTDB200_PLAN_FIELDS values: strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
  * insPeriod, insPeriodLong, number of blocks, size of the first block, flags of the first block, history of the last
