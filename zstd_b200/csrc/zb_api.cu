@@ -501,6 +501,14 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     return (size_t)total;
 }
 
+/* events of one call: destroyed on every exit path (the CK() macro returns early on a CUDA error) */
+struct ZbEventSet {
+    std::vector<cudaEvent_t> v;
+    explicit ZbEventSet(size_t n) : v(n, (cudaEvent_t)0) {}
+    ~ZbEventSet() { for (size_t i = 0; i < v.size(); i++) if (v[i]) cudaEventDestroy(v[i]); }
+    cudaEvent_t& operator[](size_t i) { return v[i]; }
+};
+
 /* XXH64 (lib/common/xxhash.h: XXH64_update / XXH64_digest, seed 0) of the frame's content: the frame checksum is
  * its low 32 bits (zstd_compress.c:5297-5303).  A serial recurrence over 32-byte stripes: it runs on the calling
  * host thread while the GPU works (about 10 GB/s — a checksummed frame is bound by this pass, not by the GPU). */
@@ -594,7 +602,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     bool const download = !deviceMemory;
     bool const timeline = getenv("ZSTDB200_TIMELINE") != NULL;      /* development: print each wave's milestones */
     unsigned const evFlags = timeline ? cudaEventDefault : cudaEventDisableTiming;
-    std::vector<cudaEvent_t> evH2D(nbWaves), evStitch(nbWaves), evSize(nbWaves), evD2H(timeline ? nbWaves : 0);
+    ZbEventSet evH2D(nbWaves), evStitch(nbWaves), evSize(nbWaves), evD2H(timeline ? nbWaves : 0);
     std::vector<double> hostDone(nbWaves, 0.0);
     double const hostT0 = zb_now();
     for (u32 w = 0; w < nbWaves; w++) {
@@ -676,10 +684,8 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
             cudaEventElapsedTime(&e, c->evStart, evD2H[w]);
             fprintf(stderr, "  wave %2u blocks %5u..%5u : uploaded %7.3f  stitched %7.3f (host saw it %7.3f)  downloaded %7.3f\n",
                     w, wb[w], wb[w + 1], a, b, 1e3 * hostDone[w], e);
-            cudaEventDestroy(evD2H[w]);
         }
     }
-    for (u32 w = 0; w < nbWaves; w++) { cudaEventDestroy(evH2D[w]); cudaEventDestroy(evStitch[w]); cudaEventDestroy(evSize[w]); }
     if (err) return err;
     {   float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evEnd); c->stats.total_ms = ms; c->stats.kernel_ms = ms; }
     c->stats.launches = launches; c->stats.nbBlocks = nbBlocks;
