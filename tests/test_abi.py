@@ -61,3 +61,33 @@ def test_compress_fails_loudly_without_cuda():
     """No CPU fallback: without a device the call must return an error, never data."""
     with pytest.raises(zstd_b200.ZstdError):
         zstd_b200.ZSTD_compress(b"hello world" * 100, 1)
+
+
+def test_header_is_valid_c99_and_links(tmp_path):
+    """A C caller (what INTEGRATION.md shows) compiles against include/zstd_b200.h with a C99 compiler and links against
+    the shared library without a GPU present (no call is made)."""
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "caller.c"
+    src.write_text('#include "zstd_b200.h"\n'
+                   '#include <stdio.h>\n'
+                   'int main(int argc, char** argv) {\n'
+                   '    if (argc > 1000) {  /* never true: only the link matters */\n'
+                   '        ZSTD_CCtx* c = ZSTD_createCCtx(); ZSTD_CDict* d = ZSTD_createCDict(argv[0], 8, 1); char dst[64];\n'
+                   '        ZSTD_CCtx_setParameter(c, ZSTD_c_checksumFlag, 1);\n'
+                   '        printf("%zu %zu %zu\\n", ZSTD_compress2(c, dst, sizeof dst, argv[0], 4), ZSTD_compress_usingCDict(c, dst, sizeof dst, argv[0], 4, d),\n'
+                   '               ZSTD_compress(dst, sizeof dst, argv[0], 4, 1));\n'
+                   '        ZSTD_freeCDict(d); ZSTD_freeCCtx(c);\n'
+                   '    }\n'
+                   '    printf("%u %s\\n", ZSTD_versionNumber(), ZSTD_getErrorName((size_t)-70));\n'
+                   '    return 0;\n}\n')
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    exe = tmp_path / "caller"
+    libdir = os.path.join(root, "zstd_b200")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lzstd_b200", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    out = subprocess.check_output([str(exe)], text=True)
+    assert out.split()[0] == "10506" and "too small" in out
