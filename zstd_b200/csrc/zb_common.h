@@ -126,7 +126,7 @@ typedef struct {
 #define ZB_PARSE_SEGS  (ZB_BLOCK_MAX / ZB_PARSE_SEG)
 typedef struct {
     u32 nbSeq;         /* sequences of the segment, stored from seq slot k * ZB_PARSE_SEG / 4 */
-    u32 litSize;       /* literal bytes of the segment (incl. the trailing ones), stored from literal offset k * ZB_PARSE_SEG */
+    u32 litSize;       /* unused (0): the parse kernels emit no literal bytes, K1c gathers them from the input */
     u32 trail;         /* literals behind the segment's last match: they lengthen the next sequence of the block */
     u32 pad;
 } ZbSegMeta;
