@@ -141,6 +141,13 @@ typedef struct {
 } ZSTDB200_stats;
 ZSTDB200_API void ZSTDB200_getLastStats(const ZSTD_CCtx* cctx, ZSTDB200_stats* out);
 
+/* Seek table for the frames of a ZSTDB200_compressFrames call (or of several ranks' outputs laid end to end): the
+ * reference's seekable format (contrib/seekable_format/zstd_seekable_compression_format.md; its writer is
+ * ZSTD_seekable_writeSeekTable, zstdseek_compress.c:297).  Append the bytes behind the frames and the reference's
+ * ZSTD_seekable_* readers can decompress any range.  cSizes / dSizes: compressed and decompressed size of every frame
+ * (each < 4 GiB).  Host code.  Returns 17 + 8 * nbFrames, or an error code. */
+ZSTDB200_API size_t ZSTDB200_writeSeekTable(void* dst, size_t dstCapacity, const size_t* cSizes, const size_t* dSizes, size_t nbFrames);
+
 /* XXH64 (seed 0) as used for the frame checksum (lib/common/xxhash.h); host code, no GPU (test hook). */
 ZSTDB200_API unsigned long long ZSTDB200_xxh64(const void* data, size_t size);
 

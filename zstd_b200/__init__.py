@@ -273,6 +273,19 @@ def ZSTD_compress(src, level: int = 3) -> bytes:
     return dst.raw[:r]
 
 
+def seek_table(c_sizes: Sequence[int], d_sizes: Sequence[int]) -> bytes:
+    """ZSTDB200_writeSeekTable: the seekable-format footer for a run of frames (append it behind them)."""
+    n = len(c_sizes)
+    cs, ds = (_sz * n)(*c_sizes), (_sz * n)(*d_sizes)
+    cap = 17 + 8 * n
+    dst = ctypes.create_string_buffer(cap)
+    L = lib()
+    L.ZSTDB200_writeSeekTable.restype = _sz
+    L.ZSTDB200_writeSeekTable.argtypes = [_vp, _sz, _vp, _vp, _sz]
+    r = _check(L.ZSTDB200_writeSeekTable(dst, cap, cs, ds, n))
+    return dst.raw[:r]
+
+
 def device_available() -> bool:
     try:
         return bool(lib().ZSTDB200_deviceAvailable())

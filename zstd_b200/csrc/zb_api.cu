@@ -808,6 +808,29 @@ extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstC
     return ZSTDB200_compressFrames(c, d_dst, dstCapacity, d_src, &off, &srcSize, 1, NULL, 0, NULL, level, 1, stream);
 }
 
+/* Seek table of a run of frames, in the reference's seekable format (contrib/seekable_format/
+ * zstd_seekable_compression_format.md; writer: zstdseek_compress.c:268-360): a skippable frame holding one
+ * (compressed size, decompressed size) pair per frame and the 9-byte footer.  Appended behind the frames a batch or a
+ * multi-GPU call produced, it makes the output randomly accessible for the reference's ZSTD_seekable_* readers.  Host
+ * code, no GPU.  Returns the number of bytes written (17 + 8 * nbFrames) or an error code. */
+extern "C" size_t ZSTDB200_writeSeekTable(void* dstv, size_t dstCapacity, const size_t* cSizes, const size_t* dSizes, size_t nbFrames)
+{
+    u8* const dst = (u8*)dstv;
+    if (nbFrames > 0x8000000u) return ZB_ERR(ZB_error_srcSize_wrong);                         /* ZSTD_SEEKABLE_MAXFRAMES, zstd_seekable.h:20 */
+    size_t const need = 8 + 8 * nbFrames + 9;
+    if (dstCapacity < need) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    if (!dst || (nbFrames && (!cSizes || !dSizes))) return ZB_ERR(ZB_error_GENERIC);
+    auto w32 = [](u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); };
+    for (size_t f = 0; f < nbFrames; f++) if (cSizes[f] > 0xFFFFFFFFull || dSizes[f] > 0xFFFFFFFFull) return ZB_ERR(ZB_error_srcSize_wrong);   /* 32-bit fields */
+    w32(dst, 0x184D2A5Eu);                                                                     /* Skippable_Magic_Number */
+    w32(dst + 4, (u32)(need - 8));                                                             /* Frame_Size */
+    u8* p = dst + 8;
+    for (size_t f = 0; f < nbFrames; f++) { w32(p, (u32)cSizes[f]); w32(p + 4, (u32)dSizes[f]); p += 8; }
+    w32(p, (u32)nbFrames); p[4] = 0;                                                           /* Number_Of_Frames, descriptor: no checksums */
+    w32(p + 5, 0x8F92EAB1u);                                                                   /* Seekable_Magic_Number */
+    return need;
+}
+
 /* the frame checksum's hash, exported for the CPU tests (compared with the reference's ZSTD_XXH64) */
 extern "C" unsigned long long ZSTDB200_xxh64(const void* p, size_t len) { return zb_xxh64((const u8*)p, len); }
 
