@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import zref
-from zstd_b200.sharding import gather_compressed, partition_frames, split_into_frames
+from zstd_b200.sharding import gather_frame_sizes, gather_compressed, partition_frames, split_into_frames
 
 
 def test_partition_is_contiguous_and_balanced():
@@ -34,12 +34,22 @@ def _worker(rank, world, port, q):
     b, e = partition_frames([s for _, s in frames], world)[rank]
     local = b"".join(zref.oracle_compress(src[o:o + s], 1) for o, s in frames[b:e])
     sizes, cat = gather_compressed(torch.frombuffer(bytearray(local), dtype=torch.uint8), dst=0)
+    # per-frame sizes of all ranks, for one seek table over the gathered frames (contrib/seekable_format)
+    mine = [zref.oracle_compress(src[o:o + s], 1) for o, s in frames[b:e]]
+    gathered = gather_frame_sizes([len(f) for f in mine], [s for _, s in frames[b:e]], dst=0)
     if rank == 0:
         out = bytes(cat.numpy())
         ok = sum(sizes) == len(out)
         if zref.have_ref():
             ok = ok and zref.ref_decompress(out, len(src)) == src
         whole = b"".join(zref.oracle_compress(src[o:o + s], 1) for o, s in frames)
+        cs, ds = gathered
+        ok = ok and sum(cs) == len(out) and ds == [s for _, s in frames]
+        import zstd_b200
+        seekable = out + zstd_b200.seek_table(cs, ds)
+        ok = ok and seekable[-4:] == bytes.fromhex("b1ea928f")
+        if zref.have_ref():
+            ok = ok and zref.ref_decompress(seekable, len(src)) == src       # the table is a skippable frame
         q.put(bool(ok and out == whole))
     dist.destroy_process_group()
 

@@ -50,3 +50,17 @@ def gather_compressed(local: torch.Tensor, dst: int = 0, group=None):
     if rank != dst:
         return sizes, None
     return sizes, torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def gather_frame_sizes(c_sizes: Sequence[int], d_sizes: Sequence[int], dst: int = 0, group=None):
+    """All ranks' per-frame (compressed, decompressed) sizes in rank order on rank `dst` (None elsewhere): what the seek
+    table over the gathered frames needs (zstd_b200.seek_table, contrib/seekable_format)."""
+    ws = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    objs = [None] * ws if rank == dst else None
+    dist.gather_object((list(c_sizes), list(d_sizes)), objs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    cs = [c for o in objs for c in o[0]]
+    ds = [d for o in objs for d in o[1]]
+    return cs, ds
