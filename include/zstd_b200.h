@@ -152,11 +152,19 @@ ZSTDB200_API size_t ZSTDB200_writeSeekTable(void* dst, size_t dstCapacity, const
 ZSTDB200_API unsigned long long ZSTDB200_xxh64(const void* data, size_t size);
 
 /* The host planner's view of a call, computed without a GPU (test hook: tests/test_plan.py compares it with the
- * oracle's plan).  out: nbFrames x 14 unsigned = strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
- * insPeriod, insPeriodLong, blocks of the frame, first block's size and flags, last block's history length and insertion
- * phase.  Returns the total number of blocks. */
+ * oracle's plan).  out: nbFrames x 16 unsigned = strategy, mls, tableN, tableNLong, stepSize, litDisabled, windowLog,
+ * insStep, blocks of the frame, first block's size and flags, last block's history reach, dictionary part of the first
+ * block's history, chunks of the frame, history walked by the last chunk, size of the last chunk.
+ * Returns the total number of blocks. */
 ZSTDB200_API size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFrames, int compressionLevel,
                                           size_t dictSize, size_t dictTail, unsigned* out);
+
+/* COMPRESSION LEVELS.  This library implements the reference's `fast` and `doubleFast` strategies, i.e. negative
+ * levels and levels 1-4 (clevels.h:25-50; level 4 only for inputs > 256 KiB).  A level whose reference strategy is
+ * greedy or stronger (5 ... 22) is NOT implemented: by default such a call is served by the strongest doubleFast row
+ * of its size class and returns a valid frame that is LARGER (typically 20-40 %) than what the reference produces at
+ * that level.  ZSTDB200_setStrictLevels(1) turns that into ZSTD_error_parameter_unsupported for the whole process. */
+ZSTDB200_API void ZSTDB200_setStrictLevels(int on);
 
 /* Which CUDA device new contexts bind to (default: current device / LOCAL_RANK). */
 ZSTDB200_API int  ZSTDB200_setDevice(int device);

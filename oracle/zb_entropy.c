@@ -147,6 +147,7 @@ size_t zbo_fse_normalize(int16_t* norm, u32 tableLog, const u32* count, size_t t
     if (tableLog < FSE_MIN_TABLELOG) return ZBO_ERR(ZBO_error_GENERIC);
     if (tableLog > FSE_MAX_TABLELOG) return ZBO_ERR(44);
     if (tableLog < fse_minTableLog(total, maxSymbolValue)) return ZBO_ERR(ZBO_error_GENERIC);
+    if (zbo_entropy_model) return zbo_fse_normalize_lr(norm, tableLog, count, total, maxSymbolValue);    /* the product's own normalisation, zb_tables.c */
     {
         int16_t const lowProbCount = useLowProbCount ? -1 : 1;
         u64 const scale = 62 - tableLog;
@@ -513,6 +514,21 @@ size_t zbo_huf_buildCTable(zbo_huf_ctable* ct, const u32* count, u32 maxSymbolVa
 
     if (maxNbBits == 0) maxNbBits = 11;
     if (maxSymbolValue > HUF_SYMBOLVALUE_MAX) return ZBO_ERR(46);
+    if (zbo_entropy_model) {                                     /* the product's own code lengths (zb_tables.c) + the format's canonical codes */
+        u16 nbPerRank[HUF_TABLELOG_MAX + 2] = {0};
+        u16 valPerRank[HUF_TABLELOG_MAX + 2] = {0};
+        size_t const ml = zbo_huf_lengths_mk(ct->nbBits, count, maxSymbolValue, maxNbBits);
+        if (ml == 0 || ml > HUF_TABLELOG_MAX) return ZBO_ERR(ZBO_error_GENERIC);
+        for (n = 0; n <= (int)maxSymbolValue; n++) nbPerRank[ct->nbBits[n]]++;
+        {   u16 min = 0;
+            for (n = (int)ml; n > 0; n--) { valPerRank[n] = min; min += nbPerRank[n]; min >>= 1; }
+        }
+        memset(ct->code, 0, sizeof(ct->code));
+        for (n = 0; n <= (int)maxSymbolValue; n++) if (ct->nbBits[n]) ct->code[n] = valPerRank[ct->nbBits[n]]++;
+        ct->tableLog = (u32)ml;
+        ct->maxSymbolValue = maxSymbolValue;
+        return ml;
+    }
     memset(table, 0, sizeof(table));
     huf_sort(node, count, maxSymbolValue);
 

@@ -113,6 +113,7 @@ static int isRLE(const u8* src, size_t n)
  * entropy state (treeless literals, set_repeat sequence tables) and its repcodes start the block.
  * ---------------------------------------------------------------------------------------- */
 /* One frame.  Blocks are independent (block-parallel plan); see zb_match.c. */
+u64 zbo_dbg[8];
 size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t srcSize,
                               const void* dictv, size_t dictSize, int level)
 {
@@ -128,10 +129,6 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
     u8* vbuf = NULL;                 /* [dictionary content tail | src] when a dictionary is in use */
     size_t D = 0;                    /* bytes of dictionary content in front of the frame */
 
-    /* the two-segment (dictionary) match-finder exists for the fast strategy only (zstd_fast.c:709): a
-     * dictionary call at a doubleFast level runs it with that level's window / hash / minMatch
-     * (measured: within +-0.3 % of the reference's doubleFast output on 1 KiB records, tests/test_oracle_dict.py) */
-    if (useDict && cp.strategy != 1) cp.strategy = 1;
     zbo_makePlan(&plan, &cp);
     zbo_dict_entropy* de = NULL;
     if (useDict) {
@@ -150,7 +147,9 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
     }
     plan.frameStart = D;
     plan.startRep[0] = plan.startRep[1] = 0;
-    if (de && de->present) { plan.startRep[0] = de->rep[0] <= D ? de->rep[0] : 0; plan.startRep[1] = de->rep[1] <= D ? de->rep[1] : 0; }   /* zstd_compress.c:5054-5056 */
+    plan.codeRep[0] = 1; plan.codeRep[1] = 4; plan.codeRep[2] = 8;                  /* zstd_internal.h:69 */
+    if (de && de->present) { plan.codeRep[0] = de->rep[0]; plan.codeRep[1] = de->rep[1]; plan.codeRep[2] = de->rep[2];
+        plan.startRep[0] = de->rep[0] <= D ? de->rep[0] : 0; plan.startRep[1] = de->rep[1] <= D ? de->rep[1] : 0; }   /* zstd_compress.c:5054-5056 */
     pos = zbo_writeFrameHeader(dst, cap, cp.windowLog, srcSize, dictID);
     if (zbo_isError(pos)) { free(vbuf); free(de); return pos; }
 
@@ -167,6 +166,8 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
         size_t bs = 0;
         size_t err = 0;
         int first = 1;
+        zbo_chunkCand cc; size_t const chunkBytes = (size_t)plan.chunkBlocks * blockMax;
+        memset(&cc, 0, sizeof(cc));
         while (bs < srcSize) {
             size_t const blockSize = (srcSize - bs) < blockMax ? (srcSize - bs) : blockMax;
             u32 const lastBlock = (bs + blockSize == srcSize);
@@ -175,7 +176,15 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
                 size_t litSize = 0;
                 /* the buffer handed to the matcher starts D bytes in front of the frame: only the first
                  * block's history window reaches back into the dictionary */
-                size_t const nbSeq = zbo_matchBlock(&plan, src - D, srcSize + D, bs + D, blockSize, seqs, lit, &litSize);
+                size_t nbSeq;
+                if (cc.dS == NULL || bs + D >= cc.end) {       /* next chunk: walk it */
+                    size_t const cs = bs - bs % chunkBytes;
+                    size_t const ce = cs + chunkBytes < srcSize ? cs + chunkBytes : srcSize;
+                    zbo_freeChunk(&cc);
+                    zbo_walkChunk(&plan, src - D, srcSize + D, cs + D, ce + D, &cc);
+                }
+                nbSeq = zbo_parseBlock(&plan, src - D, &cc, bs + D, blockSize, seqs, lit, &litSize);
+                zbo_dbg[0] += nbSeq; zbo_dbg[1] += litSize; { size_t i; for (i = 0; i < nbSeq; i++) { zbo_dbg[2] += seqs[i].offBase <= 3; zbo_dbg[3] += seqs[i].matchLen; } }
                 cSize = zbo_entropyCompressBlock_prev(body, bodyCap, seqs, nbSeq, lit, litSize, blockSize,
                                                       cp.strategy, (int)plan.litCompressionDisabled, first ? de : NULL);
                 if (zbo_isError(cSize)) { err = cSize; break; }
@@ -198,6 +207,7 @@ size_t zbo_compress_usingDict(void* dstv, size_t cap, const void* srcv, size_t s
             bs += blockSize;
             first = 0;
         }
+        zbo_freeChunk(&cc);
         free(seqs); free(lit); free(body); free(vbuf); free(de);
         if (err) return err;
     }

@@ -1,22 +1,32 @@
-/* zb_match.c — oracle model of the block-parallel "warp-batch" greedy match-finder
- * (TEST INFRASTRUCTURE ONLY; the CUDA kernel in zstd_b200/csrc must reproduce it bit-for-bit).
+/* zb_match.c — oracle model of the chunk-parallel, batch-synchronous greedy match-finder
+ * (TEST INFRASTRUCTURE ONLY; the CUDA kernels in zstd_b200/csrc/zb_match.cu must reproduce it bit-for-bit).
  *
  * What it restates: the greedy single-probe LZ77 parse of ZSTD_compressBlock_fast
- * (/root/reference/lib/compress/zstd_fast.c:192-423): multiplicative hash of `mls` bytes
- * (zstd_compress_internal.h:821-861), one candidate per bucket, 4-byte verification, repcode-1
- * probe, backward catch-up (:387-391), forward count (:396), sparse post-match inserts
- * (:403-408), immediate repcode-2 loop (:410-420), step acceleration every 128 bytes without a
- * match (:234,342-347), position pairs (p, p+1) spaced by `step` (:225-229).
+ * (/root/reference/lib/compress/zstd_fast.c:192-423) and ZSTD_compressBlock_doubleFast
+ * (zstd_double_fast.c:105-323): multiplicative hash of `mls` bytes (zstd_compress_internal.h:821-861), one
+ * candidate per bucket, 4-byte verification, repcode-1 probe, backward catch-up (:387-391), forward count
+ * (:396), immediate repcode-2 loop (:410-420), step acceleration every 128 bytes without a match
+ * (:234,342-347), position pairs (p, p+1) spaced by `step` (:225-229).
  *
- * What is different by design (block-parallel, data-parallel within a block):
- *   - every block is parsed independently: private table, primed from the `primeBytes` of input
- *     preceding the block (the ZSTDMT overlap idea, zstdmt_compress.c:726-731), encoder repcodes
- *     start invalid (zstdmt_compress.c:737-742);
- *   - candidate lookup is decoupled from the parse: a table walk inserts positions on a fixed
- *     pattern and records, for every position, the distance to its candidate (phase 1); the greedy
- *     selection (phase 2) then evaluates 32 probe positions ("lanes") per step, lowest hit wins;
- *   - table entries are 16-bit positions modulo 64 KiB (reach 65535 bytes), which is what lets
- *     7 blocks per SM keep their tables in shared memory.
+ * What is different by design (the data-parallel formulation):
+ *   - the frame is cut into CHUNKS of `chunkBlocks` blocks.  A chunk has a private hash table that is primed
+ *     from the `primeBytes` of input in front of it (the ZSTDMT overlap idea, zstdmt_compress.c:1182-1227) and
+ *     then lives through all blocks of the chunk, as the reference's table lives through a frame;
+ *   - candidate lookup (phase 1, "walk") is decoupled from the greedy selection (phase 2, "parse"): the walk
+ *     visits every position in BATCHES of ZB_BATCH consecutive positions.  All positions of a batch first read
+ *     their bucket, then the batch's insertions are applied (highest position wins a bucket), then a position
+ *     whose bucket now holds an insertion of the same batch that lies below it takes that one instead.  A batch
+ *     is what one CTA does between two barriers; batches are sequential;
+ *   - which positions a batch inserts depends on the data, not on the parse: a position whose candidate
+ *     continues the candidate of its predecessor (same distance) lies inside a repeated region — the reference
+ *     does not insert match interiors either (zstd_fast.c:403-408 inserts 2 positions per match) — and is
+ *     skipped; the others follow the pattern (pos % step) < 2 where step grows by one per 128 bytes walked
+ *     since the last such interior position (the reference's acceleration, :234,:342-347, which makes it leave
+ *     the table alone inside incompressible regions), rounded down to a power of two;
+ *   - table entries are (position + 1) << tagBits | tag: positions relative to the start of the chunk's
+ *     history (21 bits: primeBytes + chunk <= 2 MiB), tag = the next hash bits; a candidate whose tag differs
+ *     is dropped by the walk, so the parse never loads it;
+ *   - encoder repcodes start invalid in every parse segment; entropy tables are fresh per block.
  */
 #include <string.h>
 #include <stdlib.h>
@@ -51,220 +61,287 @@ static size_t zb_count(const u8* ip, const u8* match, const u8* iend)
     return (size_t)(ip - start);
 }
 
+/* experiment knobs (tools/exp_size.py only; all zero = what the product implements) */
+zbo_tunables zbo_tun = { 0, 0, 0, 0, 0, 0, 0, 0 };
+
 void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
 {
     memset(plan, 0, sizeof(*plan));
     plan->strategy = cp->strategy;
     plan->windowLog = cp->windowLog;
     plan->mls = cp->minMatch < 4 ? 4 : (cp->minMatch > 8 ? 8 : cp->minMatch);
+    /* Table sizes and the insertion pattern are set against the reference's compressed size on datagen P30 / P50 / P90
+     * (tools/exp_size.py).  An occurrence stays in the table until a different string takes its
+     * bucket (positions that find a candidate are not inserted), so a table somewhat smaller than the reference's
+     * holds as many useful candidates. */
     if (cp->strategy == 1) {
-        /* Every position pair of the pattern is inserted (also inside matches, where the reference
-         * inserts only 2 positions per match, zstd_fast.c:403-408), so a table of half the
-         * reference's size holds as many useful candidates: measured size delta vs the reference
-         * with (hashLog-1, period 4): -0.12 % (P50, level 1); (hashLog, period 8): -0.04 % (P30, --fast=3). */
+        u32 const hl = cp->hashLog > ZB_FAST_HASHLOG_MAX ? ZB_FAST_HASHLOG_MAX : cp->hashLog;
         plan->stepSize = cp->targetLength + !cp->targetLength + 1;     /* zstd_fast.c:200 */
-        if (cp->targetLength == 0) { plan->hashLog = cp->hashLog - 1; plan->insPeriod = 4; }
-        else { plan->hashLog = cp->hashLog; plan->insPeriod = 2 * plan->stepSize < 4 ? 4 : 2 * plan->stepSize; }
-        if (plan->hashLog > 14) plan->hashLog = 14;                    /* 32 KiB of u16 per block */
-        plan->longHashLog = 0;
+        if (cp->targetLength == 0) { plan->tableN = 3u << (hl - 2); plan->insStep = 3; }
+        else                       { plan->tableN = 7u << (hl - 3); plan->insStep = plan->stepSize; }
+        plan->tableNLong = 0;
     } else {
         plan->stepSize = 1;
-        /* Dense pattern insertion + tagged buckets find far more matches than the reference's dfast does
-         * with its sparse, parse-driven inserts (P90, level 3: -15 % output with tables of the reference's
-         * shape).  The size bar is two-sided, so the tables are shrunk until the output size meets the
-         * reference's on BASELINE config 4: long 2^11 / period 8, short 2^10 / period 9 -> -0.44 % and -0.23 %
-         * on two 64 MiB datagen -P90 samples.  (Tuned on P90 only: P50 at level 3 comes out +4.5 %.) */
-        plan->hashLog = 10; plan->insPeriod = 9;
-        plan->longHashLog = 11; plan->insPeriodLong = 8;
+        plan->tableN = 1u << cp->chainLog;                        /* short table (zstd_double_fast.c:116) */
+        if (plan->tableN > ZB_DFAST_SHORT_MAX) plan->tableN = ZB_DFAST_SHORT_MAX;
+        plan->tableNLong = 1u << (cp->hashLog > ZB_DFAST_LONGLOG_MAX ? ZB_DFAST_LONGLOG_MAX : cp->hashLog);
+        plan->insStep = 2;
     }
-    plan->primeBytes = ZB_PRIME_DEFAULT;
-    if (plan->primeBytes > (1u << cp->windowLog)) plan->primeBytes = 1u << cp->windowLog;
+    if (zbo_tun.tableN) plan->tableN = zbo_tun.tableN;
+    if (zbo_tun.tableNLong) plan->tableNLong = zbo_tun.tableNLong;
+    if (zbo_tun.insStep) plan->insStep = zbo_tun.insStep;
+    plan->primeBytes = zbo_tun.primeBytes ? zbo_tun.primeBytes : ZB_PRIME_DEFAULT;
+    plan->chunkBlocks = zbo_tun.chunkBlocks ? zbo_tun.chunkBlocks : ZB_CHUNK_BLOCKS;
     /* zstd_compress_internal.h:621-633 */
     plan->litCompressionDisabled = (cp->strategy == 1) && (cp->targetLength > 0);
 }
 
-/* ---- phase 1: parse-independent candidate table walk ------------------------------------------
- * dist[i] (i = position - blockStart) = distance to the most recent INSERTED earlier position of the
- * visible history with the same hash, 0 if none.  Positions are inserted on a fixed pattern of the
- * frame position ((pos % insPeriod) < 2 : the reference also probes/inserts position pairs spaced by
- * `step`, zstd_fast.c:225-229), independent of the parse, which is what lets the walk run ahead of —
- * and in parallel with — the greedy selection.  Table entries are 16-bit positions modulo 64 KiB
- * relative to the oldest visible byte (reach 65535) plus an 8-bit tag (further hash bits). */
-static void candidates_walk(const u8* frame, size_t lowLimit, size_t bs, size_t be,
-                            u32 mls, u32 hlog, u32 insPeriod, size_t frameStart, u16* dist)
+/* ---- phase 1: batch-synchronous candidate walk over [low, end) of buf ------------------------------
+ * dist[p - outStart] for p in [outStart, end) = distance to the candidate of p, 0 if none.
+ * D = index of the frame's first byte in buf (a dictionary's content lies in front of it); batches are aligned
+ * on frame positions.  readEnd = one past the last readable byte.  A position is active when its 8 bytes are
+ * readable and do not straddle the dictionary / frame border.
+ * A bucket is one u32: (position + 1) << 11 | 11 tag bits, positions relative to `low`, 0 = empty.
+ * Bucket = (hash32 * N) >> 32 (N need not be a power of two), tag = the low 11 bits of hash32. */
+static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t readEnd, size_t D,
+                 u32 mls, u32 N, u32 insStep, u32* dist)
 {
-    /* pattern phase is taken on the position relative to the frame start; history in front of the
-     * frame start (a dictionary) continues the pattern backwards */
-    size_t const patOff = (insPeriod - (frameStart % insPeriod)) % insPeriod;
-    u16* const table = (u16*)calloc((size_t)1 << hlog, sizeof(u16));
-    u8*  const tags  = (u8*)calloc((size_t)1 << hlog, 1);
-    for (size_t p = lowLimit; p + 8 <= be; p++) {
-        /* bucket = top hlog bits of the hash, tag = the next 8 bits: a bucket hit whose tag differs is a
-         * different string and is dropped here, so the parse never has to load it */
-        u32 const h24 = zb_hash(rd64(frame + p), mls, hlog + 8);
-        u32 const h = h24 >> 8;
-        u8  const tag = (u8)h24;
-        u32 const rel = (u32)(p - lowLimit);
-        u32 d = (rel - table[h]) & 0xFFFFu;
-        if (d == 0 || d > rel || tags[h] != tag) d = 0;
-        if (p >= bs) dist[p - bs] = (u16)d;
-        if (((p + patOff) % insPeriod) < 2) { table[h] = (u16)rel; tags[h] = tag; }
+    u32* const table = (u32*)calloc((size_t)N, sizeof(u32));
+    u32 const B = zbo_tun.batch ? zbo_tun.batch : ZB_BATCH;
+    u32 hh[ZB_BATCH_MAX], dOld[ZB_BATCH_MAX];
+    u8 act[ZB_BATCH_MAX], ins[ZB_BATCH_MAX];
+    size_t lastInt = low;                 /* last position seen whose candidate was a hit (the walk's start counts as one) */
+    size_t s = low;
+#define BKT(h) ((u32)(((u64)(h) * N) >> 32))
+#define CAND(c, h, me) (((c) && (((c) ^ (h)) & 0x7FFu) == 0) ? (me) - ((c) >> 11) : 0u)
+#define ENTRY(h, me) (((me) << 11) | ((h) & 0x7FFu))
+    while (s < end) {
+        /* batch = [s, e): e = next multiple of B in frame coordinates (frame position = p - D; dictionary positions count backwards) */
+        size_t e, n, i;
+        u32 step;
+        if (s >= D) e = s + B - ((s - D) % B);
+        else { e = s + ((D - s) % B ? (D - s) % B : B); }
+        if (e > end) e = end;
+        if (s == D) lastInt = D;          /* the frame starts with a fresh acceleration state behind a dictionary */
+        n = e - s;
+        /* 1. every position reads its bucket (the table as the previous batch left it) */
+        for (i = 0; i < n; i++) {
+            size_t const q = s + i;
+            act[i] = (q + 8 <= readEnd) && !(q < D && q + 8 > D);
+            dOld[i] = 0; hh[i] = 0;
+            if (act[i]) {
+                u32 const h = zb_hash(rd64(buf + q), mls, 32);
+                u32 const me = (u32)(q - low) + 1u;
+                hh[i] = h;
+                dOld[i] = CAND(table[BKT(h)], h, me);
+            }
+        }
+        /* 2. which positions enter the table: those without a candidate, on the pattern ((p - low) % step) < 2,
+         *    step = insStep + one per 128 positions walked since the last hit (zstd_fast.c:234,:342-347) */
+        step = insStep + (u32)((s - lastInt) >> 7);
+        for (i = 0; i < n; i++) {
+            size_t const q = s + i;
+            size_t const u = q - low;
+            ins[i] = act[i] && dOld[i] == 0 && (u % step) < 2;
+            if (dOld[i]) lastInt = q;
+        }
+        /* 3. look-ups see the old table plus the batch's insertions at lower positions (exact sequential order
+         *    inside a batch; only the decisions of 2. were taken on the old state) */
+        for (i = 0; i < n; i++) {
+            size_t const q = s + i;
+            u32 d = 0;
+            if (act[i]) {
+                u32 const me = (u32)(q - low) + 1u;
+                d = CAND(table[BKT(hh[i])], hh[i], me);
+                if (ins[i]) table[BKT(hh[i])] = ENTRY(hh[i], me);
+            }
+            if (q >= outStart) dist[q - outStart] = d;
+        }
+        s = e;
     }
-    for (size_t p = (be >= 8 && be - 7 > bs) ? be - 7 : bs; p < be; p++) dist[p - bs] = 0;   /* no 8-byte read there */
-    free(table); free(tags);
+    free(table);
+#undef BKT
+#undef CAND
+#undef ENTRY
 }
 
-typedef struct { zbo_seq* seqs; size_t nbSeq; u8* lit; size_t litSize; const u8* frame; } emitter;
-static void emit(emitter* e, size_t anchor, size_t litLen, size_t matchLen, u32 offBase)
+void zbo_walkChunk(const zbo_plan* plan, const u8* buf, size_t bufSize, size_t chunkStart, size_t chunkEnd, zbo_chunkCand* cc)
 {
-    memcpy(e->lit + e->litSize, e->frame + anchor, litLen);
-    e->litSize += litLen;
-    e->seqs[e->nbSeq].offBase = offBase;
-    e->seqs[e->nbSeq].litLen = (u32)litLen;
-    e->seqs[e->nbSeq].matchLen = (u32)matchLen;
-    e->nbSeq++;
+    size_t const D = plan->frameStart;
+    size_t low = chunkStart > plan->primeBytes ? chunkStart - plan->primeBytes : 0;
+    size_t const n = chunkEnd - chunkStart;
+    cc->low = low; cc->start = chunkStart; cc->end = chunkEnd;
+    cc->dS = (u32*)malloc((n + 8) * sizeof(u32));
+    cc->dL = NULL;
+    if (plan->strategy == 2) {
+        cc->dL = (u32*)malloc((n + 8) * sizeof(u32));
+        walk(buf, low, chunkStart, chunkEnd, chunkEnd, D, 8, plan->tableNLong, plan->insStep, cc->dL);
+    }
+    walk(buf, low, chunkStart, chunkEnd, chunkEnd, D, plan->mls, plan->tableN, plan->insStep, cc->dS);
+    (void)bufSize;
+}
+void zbo_freeChunk(zbo_chunkCand* cc) { free(cc->dS); free(cc->dL); cc->dS = cc->dL = NULL; }
+
+/* ---- phase 2: greedy selection ----------------------------------------------------------------------
+ * A block is parsed in segments of ZB_PARSE_SEG bytes, each by its own warp on the GPU.  A segment owns the
+ * match START positions inside it: its parse begins at the segment's first byte with an empty repcode history,
+ * but a match may run past the segment's end (up to the block's end).  The segments' raw sequences
+ * (literal run, match start, length, real offset) are then joined by the merge step below. */
+typedef struct { u32 ms, mlen, off; } rawseq;            /* match start (absolute), length, real offset */
+typedef struct { rawseq* q; size_t n; } rawlist;
+
+/* oldest position a match of this block may reach: the chunk's history start, and the window
+ * (ZSTD_window_enforceMaxDist, zstd_compress_internal.h:1173, evaluated at the block's end like the reference) */
+static size_t block_low(const zbo_plan* plan, const zbo_chunkCand* cc, size_t be)
+{
+    size_t const W = (size_t)1 << plan->windowLog;
+    size_t low = cc->low;
+    /* positions are buffer positions: with a dictionary in front, frame position 0 sits at plan->frameStart and the
+     * dictionary's content is reachable while the window still covers it */
+    if (be > W && be - W > low) low = be - W;
+    return low;
 }
 
-/* ---- phase 2: greedy selection, 32 probe positions per step ("lanes") ---------------------------- */
-static size_t matchBlock_fast(const zbo_plan* plan, const u8* frame, size_t frameSize,
-                              size_t bs, size_t blockSize, zbo_seq* seqs, u8* lit, size_t* litSizePtr)
+/* fast: 32 probe positions per step ("lanes"): pairs (p, p+1) spaced by `step` */
+static void parse_fast_segment(const zbo_plan* plan, const u8* frame, const u32* dist, size_t bs, size_t be,
+                               size_t ss, size_t se, size_t lowLimit, rawlist* out)
 {
-    size_t const be = bs + blockSize;
-    size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
-    emitter em = { seqs, 0, lit, 0, frame };
-    size_t anchor = bs, ss;
-    u16* const dist = (u16*)malloc((blockSize + 8) * sizeof(u16));
-    (void)frameSize;
-
-    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, dist);
-
-    /* The block is parsed in segments of ZB_PARSE_SEG bytes, each by its own warp on the GPU: a segment behaves
-     * like a block for the parse (repcodes start invalid, step acceleration restarts, no match crosses its end, the
-     * backward catch-up stops at its start) while candidates (dist[]), literals and sequences stay the block's —
-     * the literals a segment leaves behind its last match simply lengthen the next segment's first sequence. */
-    for (ss = bs; ss < be; ss += ZB_PARSE_SEG) {
-    size_t const se = (be - ss > ZB_PARSE_SEG) ? ss + ZB_PARSE_SEG : be;
-    size_t ip = ss, searchStart = ss;
-    /* encoder repcodes start invalid, except at the start of a frame's first block behind a zstd-format dictionary */
+    size_t ip = ss, anchor = ss, searchStart = ss;
+    /* repcodes of the search start empty, except at the start of a frame's first block behind a zstd-format dictionary */
     u32 rep1 = (ss == plan->frameStart) ? plan->startRep[0] : 0, rep2 = (ss == plan->frameStart) ? plan->startRep[1] : 0;
-
-    while (ip + 8 <= se) {
+    while (ip < se && ip + 8 <= be) {
         u32 const step = plan->stepSize + (u32)((ip - searchStart) >> 7);     /* kSearchStrength = 8, zstd_fast.c:234 */
         int winner = -1, wtype = 0, l;
         size_t probe = 0; u32 offset = 0;
-
         /* lowest lane with a hit wins.  Per lane: repcode-2 (only at lane 0 right after a match,
          * zstd_fast.c:410-420), then repcode-1, then the table candidate (4-byte check, :102-141). */
         for (l = 0; l < (int)ZB_WARP && winner < 0; l++) {
             size_t const p = ip + (size_t)(l >> 1) * step + (size_t)(l & 1);
-            u32 cur;
-            if (p + 8 > se) break;
+            u32 cur, d;
+            if (p >= se || p + 8 > be) break;
             cur = rd32(frame + p);
+            d = dist[p - bs];
             if (l == 0 && ip == anchor && rep2 && rd32(frame + p - rep2) == cur) { winner = l; wtype = 3; probe = p; offset = rep2; }
             else if (rep1 && p >= lowLimit + rep1 && rd32(frame + p - rep1) == cur) { winner = l; wtype = 2; probe = p; offset = rep1; }
-            else if (dist[p - bs] && rd32(frame + p - dist[p - bs]) == cur) { winner = l; wtype = 1; probe = p; offset = dist[p - bs]; }
+            else if (d && p >= lowLimit + d && rd32(frame + p - d) == cur) { winner = l; wtype = 1; probe = p; offset = d; }
         }
         if (winner < 0) { ip += (size_t)(ZB_WARP / 2) * step; continue; }
-
         {   size_t ms = probe, mm = probe - offset, mlen;
-            size_t const backLimit = anchor > ss ? anchor : ss;
-            u32 offBase;
             if (wtype != 3)           /* backward catch-up (zstd_fast.c:387-391); a repcode-2 hit starts at the anchor */
-                while (ms > backLimit && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
-            mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + se);
-            if (wtype == 3) { offBase = 1; { u32 const t = rep2; rep2 = rep1; rep1 = t; } }    /* litLength 0: code 1 means repcode 2 */
-            else if (wtype == 2 && ms > backLimit) offBase = 1;                                  /* REPCODE1_TO_OFFBASE */
-            else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }                           /* decoder pushes every full offset */
-            emit(&em, anchor, ms - anchor, mlen, offBase);
+                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; }
+            mlen = (probe - ms) + 4 + zb_count(frame + probe + 4, frame + probe - offset + 4, frame + be);
+            if (wtype == 3) { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+            else if (wtype == 1) { rep2 = rep1; rep1 = offset; }
+            out->q[out->n].ms = (u32)ms; out->q[out->n].mlen = (u32)mlen; out->q[out->n].off = offset; out->n++;
             ip = ms + mlen; anchor = ip; searchStart = ip;
         }
     }
-    }
-    /* trailing literals (zstd_compress.c:3365-3366) */
-    memcpy(em.lit + em.litSize, frame + anchor, be - anchor);
-    em.litSize += be - anchor;
-    *litSizePtr = em.litSize;
-    free(dist);
-    return em.nbSeq;
 }
 
-/* ---- doubleFast (zstd_double_fast.c:105-323) in the same two-phase form ------------------------------
- * Two candidate walks: "long" = 8-byte hash, "short" = mls-byte hash.  Per probe position p the
- * reference's order is kept: repcode-1 at p+1 (:190-195), long match at p (8 equal bytes, :206-213),
- * short match at p (4 equal bytes, :222-225) upgraded to the long match at p+1 when that one is longer
- * (:254-271).  32 probe positions per step, spaced by `step` (1, +1 every 256 bytes without a match,
- * kStepIncr :131), lowest lane wins; immediate repcode-2 at lane 0 right after a match (:302-316). */
-static size_t matchBlock_dfast(const zbo_plan* plan, const u8* frame, size_t frameSize,
-                               size_t bs, size_t blockSize, zbo_seq* seqs, u8* lit, size_t* litSizePtr)
+/* doubleFast (zstd_double_fast.c:105-323): per probe position p the reference's order is kept: repcode-1 at p+1
+ * (:190-195), long match at p (8 equal bytes, :206-213), short match at p (4 equal bytes, :222-225) upgraded to the
+ * long match at p+1 when that one is longer (:254-271).  32 probe positions per step, spaced by `step` (1, +1 every
+ * 256 bytes without a match, kStepIncr :131), lowest lane wins; immediate repcode-2 at lane 0 right after a match
+ * (:302-316). */
+static void parse_dfast_segment(const zbo_plan* plan, const u8* frame, const u32* distL, const u32* distS, size_t bs, size_t be,
+                                size_t ss, size_t se, size_t lowLimit, rawlist* out)
 {
-    size_t const be = bs + blockSize;
-    size_t const lowLimit = bs > plan->primeBytes ? bs - plan->primeBytes : 0;
-    emitter em = { seqs, 0, lit, 0, frame };
-    size_t anchor = bs, ss;
-    u16* const distL = (u16*)malloc((blockSize + 8) * sizeof(u16));
-    u16* const distS = (u16*)malloc((blockSize + 8) * sizeof(u16));
-    (void)frameSize;
-
-    candidates_walk(frame, lowLimit, bs, be, 8, plan->longHashLog, plan->insPeriodLong, plan->frameStart, distL);
-    candidates_walk(frame, lowLimit, bs, be, plan->mls, plan->hashLog, plan->insPeriod, plan->frameStart, distS);
-
-    /* parsed in segments of ZB_PARSE_SEG bytes like the fast strategy (see matchBlock_fast) */
-    for (ss = bs; ss < be; ss += ZB_PARSE_SEG) {
-    size_t const se = (be - ss > ZB_PARSE_SEG) ? ss + ZB_PARSE_SEG : be;
-    size_t ip = ss, searchStart = ss;
-    u32 rep1 = 0, rep2 = 0;
-    while (ip + 9 <= se) {                                   /* a lane reads 8 bytes at p and at p+1 */
+    size_t ip = ss, anchor = ss, searchStart = ss;
+    u32 rep1 = (ss == plan->frameStart) ? plan->startRep[0] : 0, rep2 = (ss == plan->frameStart) ? plan->startRep[1] : 0;
+    while (ip < se && ip + 9 <= be) {                        /* a lane reads 8 bytes at p and at p+1 */
         u32 const step = 1 + (u32)((ip - searchStart) >> 8);
         int found = 0, wtype = 0, l;
         size_t ms = 0; u32 offset = 0; size_t mlen = 0;
         for (l = 0; l < (int)ZB_WARP && !found; l++) {
             size_t const p = ip + (size_t)l * step;
-            if (p + 9 > se) break;
+            u32 dl, ds, dl1;
+            if (p >= se || p + 9 > be) break;
+            dl = distL[p - bs]; ds = distS[p - bs]; dl1 = distL[p + 1 - bs];
+            if (dl && p < lowLimit + dl) dl = 0;
+            if (ds && p < lowLimit + ds) ds = 0;
+            if (dl1 && p + 1 < lowLimit + dl1) dl1 = 0;
             if (l == 0 && ip == anchor && rep2 && rd32(frame + p - rep2) == rd32(frame + p)) {
                 found = 1; wtype = 3; ms = p; offset = rep2;
-                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - rep2, frame + se);
+                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - rep2, frame + be);
             } else if (rep1 && p + 1 >= lowLimit + rep1 && rd32(frame + p + 1 - rep1) == rd32(frame + p + 1)) {
                 found = 1; wtype = 2; ms = p + 1; offset = rep1;
-                mlen = 4 + zb_count(frame + p + 5, frame + p + 5 - rep1, frame + se);
-            } else if (distL[p - bs] && rd64(frame + p - distL[p - bs]) == rd64(frame + p)) {
+                mlen = 4 + zb_count(frame + p + 5, frame + p + 5 - rep1, frame + be);
+            } else if (dl && rd64(frame + p - dl) == rd64(frame + p)) {
                 size_t mm;
-                found = 1; wtype = 1; ms = p; offset = distL[p - bs];
-                mlen = 8 + zb_count(frame + p + 8, frame + p + 8 - offset, frame + se);
+                found = 1; wtype = 1; ms = p; offset = dl;
+                mlen = 8 + zb_count(frame + p + 8, frame + p + 8 - offset, frame + be);
                 mm = ms - offset;
-                while (ms > (anchor > ss ? anchor : ss) && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
-            } else if (distS[p - bs] && rd32(frame + p - distS[p - bs]) == rd32(frame + p)) {
+                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
+            } else if (ds && rd32(frame + p - ds) == rd32(frame + p)) {
                 size_t mm;
-                found = 1; wtype = 1; ms = p; offset = distS[p - bs];
-                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - offset, frame + se);
-                if (distL[p + 1 - bs] && rd64(frame + p + 1 - distL[p + 1 - bs]) == rd64(frame + p + 1)) {
-                    u32 const o1 = distL[p + 1 - bs];
-                    size_t const l1 = 8 + zb_count(frame + p + 9, frame + p + 9 - o1, frame + se);
-                    if (l1 > mlen) { ms = p + 1; offset = o1; mlen = l1; }
+                found = 1; wtype = 1; ms = p; offset = ds;
+                mlen = 4 + zb_count(frame + p + 4, frame + p + 4 - offset, frame + be);
+                if (dl1 && rd64(frame + p + 1 - dl1) == rd64(frame + p + 1)) {
+                    size_t const l1 = 8 + zb_count(frame + p + 9, frame + p + 9 - dl1, frame + be);
+                    if (l1 > mlen) { ms = p + 1; offset = dl1; mlen = l1; }
                 }
                 mm = ms - offset;
-                while (ms > (anchor > ss ? anchor : ss) && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
+                while (ms > anchor && mm > lowLimit && frame[ms - 1] == frame[mm - 1]) { ms--; mm--; mlen++; }
             }
         }
         if (!found) { ip += (size_t)ZB_WARP * step; continue; }
-        {   u32 offBase;
-            if (wtype == 3) { offBase = 1; { u32 const t = rep2; rep2 = rep1; rep1 = t; } }
-            else if (wtype == 2 && ms > (anchor > ss ? anchor : ss)) offBase = 1;
-            else { offBase = offset + 3; rep2 = rep1; rep1 = offset; }
-            emit(&em, anchor, ms - anchor, mlen, offBase);
-            ip = ms + mlen; anchor = ip; searchStart = ip;
-        }
+        if (wtype == 3) { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (wtype == 1) { rep2 = rep1; rep1 = offset; }
+        out->q[out->n].ms = (u32)ms; out->q[out->n].mlen = (u32)mlen; out->q[out->n].off = offset; out->n++;
+        ip = ms + mlen; anchor = ip; searchStart = ip;
     }
-    }
-    memcpy(em.lit + em.litSize, frame + anchor, be - anchor);
-    em.litSize += be - anchor;
-    *litSizePtr = em.litSize;
-    free(distL); free(distS);
-    return em.nbSeq;
 }
 
-size_t zbo_matchBlock(const zbo_plan* plan, const u8* frame, size_t frameSize,
-                      size_t blockStart, size_t blockSize, zbo_seq* seqs, u8* lit, size_t* litSizePtr)
+/* ---- merge: joins the segments of a block -----------------------------------------------------------
+ * `cur` = first byte not yet covered by a sequence.  A raw sequence that ends at or before `cur` (it lies under a
+ * match that ran over from an earlier segment) is dropped; one that straddles `cur` keeps its tail when that is at
+ * least 3 bytes (MINMATCH, zstd_internal.h:102), else it is dropped too; the others take their literals from `cur`.
+ * Then the repcode history is run over the whole block (what ZSTD_storeSeq / ZSTD_updateRep do sequence by sequence
+ * in the reference, zstd_compress_internal.h:671-760): it starts as {1,4,8} in the first block of a frame (zstd_internal.h:69;
+ * the dictionary's repcodes behind a zstd-format dictionary) and unknown (0 = never matches) in every other block,
+ * because blocks are compressed independently of each other. */
+size_t zbo_parseBlock(const zbo_plan* plan, const u8* frame, const zbo_chunkCand* cc,
+                      size_t bs, size_t blockSize, zbo_seq* seqs, u8* lit, size_t* litSizePtr)
 {
-    if (plan->strategy == 2) return matchBlock_dfast(plan, frame, frameSize, blockStart, blockSize, seqs, lit, litSizePtr);
-    return matchBlock_fast(plan, frame, frameSize, blockStart, blockSize, seqs, lit, litSizePtr);
+    size_t const be = bs + blockSize;
+    size_t const lowLimit = block_low(plan, cc, be);
+    rawlist rl;
+    size_t ss, cur = bs, nbSeq = 0, litSize = 0, i, first = 0;
+    u32 r1 = 0, r2 = 0, r3 = 0;
+    rl.q = (rawseq*)malloc((blockSize / 3 + 64) * sizeof(rawseq)); rl.n = 0;
+    if (bs == plan->frameStart) { r1 = plan->codeRep[0]; r2 = plan->codeRep[1]; r3 = plan->codeRep[2]; }
+    for (ss = bs; ss < be; ss += ZB_PARSE_SEG) {
+        size_t const se = (be - ss > ZB_PARSE_SEG) ? ss + ZB_PARSE_SEG : be;
+        first = rl.n;
+        if (plan->strategy == 2) parse_dfast_segment(plan, frame, cc->dL + (bs - cc->start), cc->dS + (bs - cc->start), bs, be, ss, se, lowLimit, &rl);
+        else                     parse_fast_segment(plan, frame, cc->dS + (bs - cc->start), bs, be, ss, se, lowLimit, &rl);
+        for (i = first; i < rl.n; i++) {
+            size_t ms = rl.q[i].ms, mlen = rl.q[i].mlen;
+            u32 const off = rl.q[i].off;
+            size_t ll;
+            u32 offBase;
+            if (ms + mlen <= cur) continue;
+            if (ms < cur) { if (ms + mlen - cur < 3) continue; mlen = ms + mlen - cur; ms = cur; }
+            ll = ms - cur;
+            if (ll > 0) {
+                if (off == r1) offBase = 1;
+                else if (off == r2) { offBase = 2; r2 = r1; r1 = off; }
+                else if (off == r3) { offBase = 3; r3 = r2; r2 = r1; r1 = off; }
+                else { offBase = off + 3; r3 = r2; r2 = r1; r1 = off; }
+            } else {
+                if (off == r2) { offBase = 1; r2 = r1; r1 = off; }
+                else if (off == r3) { offBase = 2; r3 = r2; r2 = r1; r1 = off; }
+                else if (r1 > 1 && off == r1 - 1) { offBase = 3; r3 = r2; r2 = r1; r1 = off; }
+                else { offBase = off + 3; r3 = r2; r2 = r1; r1 = off; }
+            }
+            memcpy(lit + litSize, frame + cur, ll); litSize += ll;
+            seqs[nbSeq].offBase = offBase; seqs[nbSeq].litLen = (u32)ll; seqs[nbSeq].matchLen = (u32)mlen; nbSeq++;
+            cur = ms + mlen;
+        }
+    }
+    /* trailing literals (zstd_compress.c:3365-3366) */
+    memcpy(lit + litSize, frame + cur, be - cur); litSize += be - cur;
+    *litSizePtr = litSize;
+    free(rl.q);
+    return nbSeq;
 }

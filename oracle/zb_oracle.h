@@ -51,20 +51,27 @@ typedef struct { u32 offBase; u32 litLen; u32 matchLen; } zbo_seq;   /* matchLen
 
 /* ---- block-parallel plan constants (shared with the CUDA side) ---- */
 #define ZB_BLOCK_MAX      (128u << 10)     /* ZSTD_BLOCKSIZE_MAX, lib/zstd.h:142 */
-#define ZB_PRIME_DEFAULT  (64u << 10)      /* history primed into a block's private table */
+#define ZB_PRIME_DEFAULT  (128u << 10)     /* history primed into a chunk's private table */
+#define ZB_CHUNK_BLOCKS   4u               /* blocks per chunk (one table lives through a chunk) */
+#define ZB_BATCH          1024u            /* positions of one walk batch (= threads of the walk CTA) */
+#define ZB_BATCH_MAX      4096u
+#define ZB_FAST_HASHLOG_MAX  14u           /* fast: <= 12288 u32 buckets = 48 KiB of shared memory */
+#define ZB_DFAST_SHORT_MAX 51200u          /* dfast short table: 51200 x u32 = 200 KiB of shared memory */
+#define ZB_DFAST_LONGLOG_MAX  15u          /* dfast long table: 32768 x u32 = 128 KiB */
 #define ZB_WARP           32u
 #define ZB_PARSE_SEG      (16u << 10)      /* fast strategy: bytes of a block parsed by one warp (8 segments per 128 KiB block) */
 
 typedef struct {
     u32 mls;          /* bytes hashed (cParams.minMatch clamped to 4..8; short hash for dfast) */
-    u32 hashLog;      /* log2 entries of the (short) table */
-    u32 longHashLog;  /* dfast only: log2 entries of the 8-byte-hash table, else 0 */
+    u32 tableN;       /* buckets of the (short) table */
+    u32 tableNLong;   /* dfast only: buckets of the 8-byte-hash table, else 0 */
     u32 stepSize;     /* targetLength + !targetLength + 1 (zstd_fast.c:200); dfast: 1 */
-    u32 insPeriod;    /* positions with (framePos % insPeriod) < 2 are inserted into the table */
-    u32 insPeriodLong;/* dfast: same for the 8-byte-hash table */
-    u32 startRep[2];  /* repcodes the frame's first block starts with (a zstd-format dictionary's), 0 = invalid */
-    size_t frameStart;/* index of the frame's first byte inside the buffer handed to zbo_matchBlock (dictionary tail in front) */
-    u32 primeBytes;   /* history window primed before the block */
+    u32 insStep;      /* positions without a candidate enter the table when ((pos - low) % step) < 2, step = insStep + walked/128 */
+    u32 chunkBlocks;  /* blocks per chunk */
+    u32 startRep[2];  /* repcodes the search of the frame's first segment starts with (a zstd-format dictionary's), 0 = none */
+    u32 codeRep[3];   /* repcode history the decoder holds at the frame's first block: {1,4,8} or the dictionary's */
+    size_t frameStart;/* index of the frame's first byte inside the buffer handed to the matcher (dictionary tail in front) */
+    u32 primeBytes;   /* history window primed before a chunk */
     u32 strategy;     /* 1 fast, 2 dfast */
     u32 windowLog;
     u32 litCompressionDisabled; /* zstd_compress_internal.h:621-633 */
@@ -103,6 +110,13 @@ typedef struct {
 size_t zbo_readNCount(int16_t* norm, u32* maxSymbolPtr, u32* tableLogPtr, const u8* p, size_t avail);  /* entropy_common.c:42 */
 size_t zbo_loadDictEntropy(zbo_dict_entropy* de, const u8* dict, size_t dictSize);
 
+/* the product's own table builders (zb_tables.c); zbo_entropy_model selects them (1, default) or the restatement of the
+ * reference's (0: what tests/test_oracle_entropy.py pins byte-for-byte against the compiled reference) inside
+ * zbo_fse_normalize / zbo_huf_buildCTable and everything built on them */
+extern int zbo_entropy_model;
+size_t zbo_fse_normalize_lr(int16_t* norm, u32 tableLog, const u32* count, size_t total, u32 maxSymbolValue);
+size_t zbo_huf_lengths_mk(u8* nbBits, const u32* count, u32 maxSymbolValue, u32 target);
+
 /* literals section, fresh tables (no repeat/treeless): zstd_compress_literals.c:129 */
 size_t zbo_compressLiterals(u8* dst, size_t cap, const u8* lit, size_t litSize,
                             u32 strategy, int disableLiteralCompression, int suspectUncompressible);
@@ -121,12 +135,18 @@ size_t zbo_entropyCompressBlock_prev(u8* dst, size_t cap,
                                 const zbo_dict_entropy* prev);
 
 /* ---- match-finder model ---- */
-/* Parses block [blockStart, blockStart+blockSize) of `frame` (frameSize bytes, positions before
- * blockStart are history).  Emits sequences + literal bytes.  Returns nbSeq; *litSizePtr gets the
- * total literal count (including the trailing literals). */
-size_t zbo_matchBlock(const zbo_plan* plan, const u8* frame, size_t frameSize,
+/* candidates of one chunk [start, end) of buf (phase 1); dS/dL indexed by position - start */
+typedef struct { u32* dS; u32* dL; size_t low, start, end; } zbo_chunkCand;
+void zbo_walkChunk(const zbo_plan* plan, const u8* buf, size_t bufSize, size_t chunkStart, size_t chunkEnd, zbo_chunkCand* cc);
+void zbo_freeChunk(zbo_chunkCand* cc);
+/* Parses block [blockStart, blockStart+blockSize) of its chunk (phase 2).  Emits sequences + literal bytes.
+ * Returns nbSeq; *litSizePtr gets the total literal count (including the trailing literals). */
+size_t zbo_parseBlock(const zbo_plan* plan, const u8* buf, const zbo_chunkCand* cc,
                       size_t blockStart, size_t blockSize,
                       zbo_seq* seqs, u8* lit, size_t* litSizePtr);
+/* experiment knobs (0 = default), only set by tools/ scripts */
+typedef struct { u32 tableN, tableNLong, tableFmt, insStep, primeBytes, chunkBlocks, batch, spare; } zbo_tunables;
+extern zbo_tunables zbo_tun;
 
 /* ---- frame level: mirrors ZSTD_compress / ZSTD_compress_usingDict (lib/zstd.h:155,944) ---- */
 size_t zbo_compressBound(size_t srcSize);                             /* lib/zstd.h:235 */

@@ -72,23 +72,29 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
     p.strategy = cp.strategy;
     p.windowLog = cp.windowLog;
     p.mls = cp.minMatch < 4 ? 4 : (cp.minMatch > 8 ? 8 : cp.minMatch);
+    /* Table sizes and the insertion pattern are set against the reference's compressed size on datagen P30 / P50 / P90
+     * (tools/exp_size.py): an occurrence stays in the table until a different string takes its
+     * bucket (positions that find a candidate are not inserted), so a table somewhat smaller than the reference's holds
+     * as many useful candidates.  The oracle's zbo_makePlan is the same rule (tests/test_plan.py). */
     if (cp.strategy == 1) {
+        u32 const hl = cp.hashLog > ZB_FAST_HASHLOG_MAX ? ZB_FAST_HASHLOG_MAX : cp.hashLog;
         p.stepSize = cp.targetLength + !cp.targetLength + 1;     /* zstd_fast.c:200 */
-        /* every pattern position is inserted (also inside matches), so half the reference's table holds
-         * as many useful candidates; (hashLog, period) are tuned per level class to land within
-         * +-0.5 % of the reference size on the BASELINE configs ("size parity") */
-        if (cp.targetLength == 0) { p.hashLog = cp.hashLog - 1; p.insPeriod = 4; }
-        else { p.hashLog = cp.hashLog; p.insPeriod = 2 * p.stepSize < 4 ? 4 : 2 * p.stepSize; }
-        if (p.hashLog > 14) p.hashLog = 14;                       /* 2^14 u16 = 32 KiB of shared memory per block */
+        if (cp.targetLength == 0) { p.tableN = 3u << (hl - 2); p.insStep = 3; }
+        else                      { p.tableN = 7u << (hl - 3); p.insStep = p.stepSize; }
     } else {
-        /* doubleFast: table shapes tuned so the output size meets the reference's on BASELINE config 4 */
-        p.stepSize = 1; p.hashLog = 10; p.insPeriod = 9; p.longHashLog = 11; p.insPeriodLong = 8;
+        p.stepSize = 1;
+        p.tableN = 1u << cp.chainLog;                            /* short table (zstd_double_fast.c:116) */
+        if (p.tableN > ZB_DFAST_SHORT_MAX) p.tableN = ZB_DFAST_SHORT_MAX;
+        p.tableNLong = 1u << (cp.hashLog > ZB_DFAST_LONGLOG_MAX ? ZB_DFAST_LONGLOG_MAX : cp.hashLog);
+        p.insStep = 2;
     }
+    p.codeRep[0] = 1; p.codeRep[1] = 4; p.codeRep[2] = 8;        /* zstd_internal.h:69 */
     p.litDisabled = (cp.strategy == 1) && (cp.targetLength > 0); /* zstd_compress_internal.h:621-633 */
     return p;
 }
 
-#define ZB_IMAGE_BYTES (3u << 14)      /* largest table: 2^14 positions + tags */
+#define ZB_IMAGE_WORDS (ZB_DFAST_SHORT_MAX + (1u << ZB_DFAST_LONGLOG_MAX))   /* largest table pair: short table, then (doubleFast) the long table */
+#define ZB_IMAGE_BYTES (ZB_IMAGE_WORDS * 4u)
 #define ZB_MAX_IMAGES 4
 
 /* ------------------------------------------------------------------ context */
@@ -108,7 +114,7 @@ struct ZSTD_CDict_s {
     ZbDictEntropy entropy;         /* parsed on the host at creation */
     std::mutex* lock;              /* guards the lazily created device state below */
     int device;                    /* -1 until first use */
-    u8* d_dict; ZbDictEntropy* d_de; u8* d_image; ZbBlock* d_dictBlock;
+    u8* d_dict; ZbDictEntropy* d_de; u8* d_image; ZbChunk* d_dictChunk;
     u32 nbImages; ZbParams imagePrm[ZB_MAX_IMAGES];
 };
 
@@ -117,7 +123,8 @@ struct ZSTD_CCtx_s {
     cudaStream_t stream;
     /* per-block workspace */
     size_t capBlocks, capFrames, capWaves;
-    size_t capHeavyBytes[7];       /* meta, seqs, lits, body, dist, dist2, segmeta */
+    size_t capHeavyBytes[9];       /* meta, seqs, lits, body, dist, dist2, segmeta, far, far2 */
+    size_t capChunks; ZbChunk* d_chunks;
     ZbSegMeta* d_segmeta;          /* K1b -> K1c: per parse segment counts */
     u32 devWaveBlocks;             /* device-memory calls: blocks per wave (0 = always one wave) */
     cudaStream_t waveStream[ZB_WAVE_SLOTS_MAX + 2];
@@ -127,12 +134,13 @@ struct ZSTD_CCtx_s {
     ZbBlock* d_blocks; ZbFrame* d_frames; ZbBlockMeta* d_meta;
     u64* d_seqs; u8* d_lits; u8* d_body; u16* d_dist;   /* d_dist: K1a->K1b candidate distances, then K3's FSE state records */
     u16* d_dist2;                                        /* dfast only: short-hash candidate distances */
+    u32* d_far; u32* d_far2;                             /* candidate distances >= 0xFFFF (dist16 = ZB_FAR) */
     u64* d_outOffsets; u64* d_frameSizes; u64* d_totals;    /* d_totals[w]: bytes produced up to and including wave w */
     /* host-pointer path staging */
     u8* d_in; size_t d_inCap; u8* d_out; size_t d_outCap;
-    u8* d_dict;                    /* dictionary content tail (<= 64 KiB), 32 bytes of padding on both sides */
+    u8* d_dict;                    /* dictionary content tail (<= ZB_PRIME_BYTES), 32 bytes of padding on both sides */
     u8* d_image;                   /* tables primed from the dictionary tail, one per parameter group (ZB_MAX_IMAGES) */
-    ZbBlock* d_dictBlock;          /* pseudo block descriptors for zb_launch_dict_image */
+    ZbChunk* d_dictChunk;          /* pseudo chunk descriptors for zb_launch_dict_image */
     ZbDictEntropy dictEntropy;     /* host copy of the current call's dictionary entropy state */
     ZbDictEntropy* d_de;           /* device copy */
     const ZbDictEntropy* d_deActive; /* d_de when the current call's dictionary is zstd-format, else NULL */
@@ -190,6 +198,12 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
     CK(cudaSetDevice(dev));
     c->device = dev;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   /* the predefined FSE tables live in device memory (one copy per device; re-uploading the same bytes is harmless) */
+        static ZbdFseCTable defaults[3]; static std::once_flag once;
+        std::call_once(once, [] { zb_buildDefaultTables(defaults); });
+        CK(zb_upload_default_tables(defaults, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evK0)); CK(cudaEventCreate(&c->evK1));
     CK(cudaEventCreate(&c->evK2)); CK(cudaEventCreate(&c->evK3)); CK(cudaEventCreate(&c->evMid));
     CK(cudaEventCreate(&c->evKEnd)); CK(cudaEventCreate(&c->evEnd));
@@ -199,7 +213,8 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
 static void zb_freeWorkspace(ZSTD_CCtx* c)
 {
     cudaFree(c->d_blocks); cudaFree(c->d_frames); cudaFree(c->d_meta); cudaFree(c->d_seqs); cudaFree(c->d_lits);
-    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; cudaFree(c->d_segmeta); c->d_segmeta = NULL; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
+    cudaFree(c->d_body); cudaFree(c->d_dist); cudaFree(c->d_dist2); c->d_dist2 = NULL; cudaFree(c->d_segmeta); c->d_segmeta = NULL;
+    cudaFree(c->d_far); cudaFree(c->d_far2); c->d_far = NULL; c->d_far2 = NULL; cudaFree(c->d_chunks); c->d_chunks = NULL; c->capChunks = 0; cudaFree(c->d_outOffsets); cudaFree(c->d_frameSizes); cudaFree(c->d_totals);
     cudaFreeHost(c->h_totals);
     c->d_blocks = NULL; c->d_frames = NULL; c->d_meta = NULL; c->d_seqs = NULL; c->d_lits = NULL;
     c->d_body = NULL; c->d_dist = NULL; c->d_outOffsets = NULL; c->d_frameSizes = NULL; c->d_totals = NULL; c->h_totals = NULL;
@@ -214,7 +229,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
-        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de); cudaFree(c->d_image); cudaFree(c->d_dictBlock);
+        cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_dict); cudaFree(c->d_de); cudaFree(c->d_image); cudaFree(c->d_dictChunk);
         for (u32 s = 0; s < ZB_WAVE_SLOTS_MAX + 2u; s++) if (c->waveStream[s]) cudaStreamDestroy(c->waveStream[s]);
         cudaEventDestroy(c->evStart); cudaEventDestroy(c->evK0); cudaEventDestroy(c->evK1);
         cudaEventDestroy(c->evK2); cudaEventDestroy(c->evK3); cudaEventDestroy(c->evMid);
@@ -227,8 +242,13 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 
 /* descriptors (per block / per frame, small) and the heavy per-block workspace are sized separately:
  * the host-pointer path runs the blocks in waves that share a few workspace slots */
-static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size_t nbWaves)
+static size_t zb_ensureDesc(ZSTD_CCtx* c, size_t nbBlocks, size_t nbFrames, size_t nbWaves, size_t nbChunks)
 {
+    if (nbChunks > c->capChunks) {
+        cudaFree(c->d_chunks); c->d_chunks = NULL; c->capChunks = 0;
+        CK(cudaMalloc(&c->d_chunks, nbChunks * sizeof(ZbChunk)));
+        c->capChunks = nbChunks;
+    }
     if (nbBlocks > c->capBlocks) {
         cudaFree(c->d_blocks); cudaFree(c->d_outOffsets); c->d_blocks = NULL; c->d_outOffsets = NULL; c->capBlocks = 0;
         CK(cudaMalloc(&c->d_blocks, nbBlocks * sizeof(ZbBlock)));
@@ -259,12 +279,13 @@ static ZbStrides zb_strides(u32 maxBlock)
 static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides& sd, bool needDist2)
 {
     size_t const nb = nbSlotBlocks;
-    size_t const need[7] = { nb * sizeof(ZbBlockMeta), nb * sd.seq * sizeof(u64), nb * (size_t)sd.lit, nb * (size_t)sd.body,
+    size_t const need[9] = { nb * sizeof(ZbBlockMeta), nb * sd.seq * sizeof(u64), nb * (size_t)sd.lit, nb * (size_t)sd.body,
                              nb * (size_t)sd.dist * sizeof(u16), needDist2 ? nb * (size_t)sd.dist * sizeof(u16) : 0,
-                             nb * ((sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG) * sizeof(ZbSegMeta) };
-    void** const ptr[7] = { (void**)&c->d_meta, (void**)&c->d_seqs, (void**)&c->d_lits, (void**)&c->d_body, (void**)&c->d_dist, (void**)&c->d_dist2,
-                            (void**)&c->d_segmeta };
-    for (int i = 0; i < 7; i++) {
+                             nb * ((sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG) * sizeof(ZbSegMeta),
+                             nb * (size_t)sd.dist * sizeof(u32), needDist2 ? nb * (size_t)sd.dist * sizeof(u32) : 0 };
+    void** const ptr[9] = { (void**)&c->d_meta, (void**)&c->d_seqs, (void**)&c->d_lits, (void**)&c->d_body, (void**)&c->d_dist, (void**)&c->d_dist2,
+                            (void**)&c->d_segmeta, (void**)&c->d_far, (void**)&c->d_far2 };
+    for (int i = 0; i < 9; i++) {
         if (need[i] <= c->capHeavyBytes[i]) continue;
         cudaFree(*ptr[i]); *ptr[i] = NULL; c->capHeavyBytes[i] = 0;
         CK(cudaMalloc(ptr[i], need[i] + 256));
@@ -280,58 +301,84 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides&
  * FSE tables are that block's "previous" entropy state (treeless literals, set_repeat sequence tables) and
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
-struct ZbGroup { ZbParams prm; u32 b0, b1; const u8* image; };   /* image: table primed from the dictionary tail, or NULL */
-struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported; };
+struct ZbGroup { ZbParams prm; u32 b0, b1, c0, c1; const u32* image; };   /* image: tables walked over the dictionary tail, or NULL */
+struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbChunk> chunks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported; };
+
+static int g_strictLevels = 0;
+/* Levels whose reference strategy is greedy or stronger (>= 5; 4 for frames <= 256 KiB / <= 16 KiB) have no counterpart here:
+ * by default they are served by the strongest doubleFast row of their size class (larger output than the reference's at
+ * that level); after ZSTDB200_setStrictLevels(1) such calls fail with parameter_unsupported instead. */
+extern "C" void ZSTDB200_setStrictLevels(int on) { g_strictLevels = on; }
 
 static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
                     size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
 {
     P.frames.resize(nbFrames);
     P.blocks.reserve(nbFrames);
-    P.unsupported = false;
+    P.chunks.reserve(nbFrames);
+    P.unsupported = g_strictLevels && level > 4;
     u32 maxBlock = 0;
     /* calls made of many equal, single-block frames (config 5: a million 1 KiB records): the frame before is the template */
-    u64 tplSize = ~0ull; ZbFrame tplFrame; ZbBlock tplBlock; memset(&tplFrame, 0, sizeof(tplFrame)); memset(&tplBlock, 0, sizeof(tplBlock));
+    u64 tplSize = ~0ull; ZbFrame tplFrame; ZbBlock tplBlock; ZbChunk tplChunk;
+    memset(&tplFrame, 0, sizeof(tplFrame)); memset(&tplBlock, 0, sizeof(tplBlock)); memset(&tplChunk, 0, sizeof(tplChunk));
     for (size_t f = 0; f < nbFrames; f++) {
         u64 const fsz = frameSizes[f];
         if (fsz == tplSize) {
             ZbFrame fr = tplFrame; fr.srcOff = frameOffsets[f]; fr.firstBlock = (u32)P.blocks.size();
             ZbBlock b = tplBlock; b.srcOff = fr.srcOff; b.frame = (u32)f;
+            ZbChunk ch = tplChunk; ch.srcOff = fr.srcOff; ch.firstBlock = fr.firstBlock;
             P.blocks.push_back(b);
+            P.chunks.push_back(ch);
             P.frames[f] = fr;
             P.groups.back().b1 = (u32)P.blocks.size();
+            P.groups.back().c1 = (u32)P.chunks.size();
             continue;
         }
         ZbCParams cp = zb_getCParams(level, fsz, dictSize);
-        /* the two-segment (dictionary) match-finder exists for the fast strategy only (zstd_fast.c:709): a
-         * dictionary call at a doubleFast level runs it with that level's window / hash / minMatch */
-        if (dictSize && cp.strategy != 1) cp.strategy = 1;
         ZbParams prm = zb_makeParams(cp);
-        if (dictRep) { prm.startRep[0] = dictRep[0] <= dictTail ? dictRep[0] : 0u; prm.startRep[1] = dictRep[1] <= dictTail ? dictRep[1] : 0u; }
+        if (dictRep) {                                           /* a zstd-format dictionary's repcodes (zstd_compress.c:5054-5056) */
+            prm.codeRep[0] = dictRep[0]; prm.codeRep[1] = dictRep[1]; prm.codeRep[2] = dictRep[2];
+            prm.startRep[0] = dictRep[0] <= dictTail ? dictRep[0] : 0u; prm.startRep[1] = dictRep[1] <= dictTail ? dictRep[1] : 0u;
+        }
         size_t const blockMax = ((size_t)1 << cp.windowLog) < ZB_BLOCK_MAX ? ((size_t)1 << cp.windowLog) : ZB_BLOCK_MAX;   /* zstd_compress.c:2124 */
+        u64 const chunkBytes = (u64)ZB_CHUNK_BLOCKS * blockMax;
+        u64 const W = 1ull << cp.windowLog;
         ZbFrame fr; fr.srcOff = frameOffsets[f]; fr.srcSize = fsz; fr.firstBlock = (u32)P.blocks.size();
         fr.windowLog = cp.windowLog; fr.dictID = dictID; fr.checksum = frameChecksum; fr.pad = 0;
+        u32 const firstChunk = (u32)P.chunks.size();
         u64 pos = 0;
         do {
             u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
-            ZbBlock b; b.srcOff = fr.srcOff + pos; b.size = (u32)bsz;
-            b.histLen = (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
-            b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u);
-            if (pos == 0 && dictTail) { b.histLen = (u32)dictTail; b.flags |= ZB_FLAG_DICT; }     /* history = dictionary content tail */
-            /* pattern phase of the oldest visible byte: its frame position is pos - histLen (negative inside a dictionary) */
-            {   u64 const back = (u64)b.histLen > pos ? (u64)b.histLen - pos : 0;                 /* bytes in front of the frame start */
-                u64 const fpos = pos > b.histLen ? pos - b.histLen : 0;
-                b.insPhase = (u32)(back ? (prm.insPeriod - back % prm.insPeriod) % prm.insPeriod : fpos % prm.insPeriod);
-                b.insPhaseLong = prm.insPeriodLong ? (u32)(back ? (prm.insPeriodLong - back % prm.insPeriodLong) % prm.insPeriodLong : fpos % prm.insPeriodLong) : 0u; }
+            if (pos % chunkBytes == 0) {                         /* a new chunk starts with this block */
+                ZbChunk ch; memset(&ch, 0, sizeof(ch));
+                ch.srcOff = fr.srcOff + pos; ch.size = (u32)((fsz - pos) < chunkBytes ? (fsz - pos) : chunkBytes);
+                ch.histLen = pos == 0 ? (u32)dictTail : (u32)(pos < ZB_PRIME_BYTES ? pos : ZB_PRIME_BYTES);
+                ch.dictLen = pos == 0 ? (u32)dictTail : 0u;
+                ch.firstBlock = (u32)P.blocks.size(); ch.blockLog = hb32((u32)blockMax);
+                P.chunks.push_back(ch);
+            }
+            ZbChunk const& ch = P.chunks.back();
+            /* positions in [dictionary tail | frame] coordinates: the frame starts at dictTail */
+            u64 const chunkPos = ch.srcOff - fr.srcOff;
+            u64 const chunkLow = dictTail + chunkPos - ch.histLen;
+            u64 const bsBuf = dictTail + pos, beBuf = bsBuf + bsz;
+            u64 low = chunkLow;
+            if (beBuf > W && beBuf - W > low) low = beBuf - W;   /* ZSTD_window_enforceMaxDist at the block's end, zstd_compress_internal.h:1173 */
+            ZbBlock b; memset(&b, 0, sizeof(b));
+            b.srcOff = fr.srcOff + pos; b.size = (u32)bsz;
+            b.histLen = (u32)(bsBuf - low);
+            b.dictLen = low < dictTail ? (u32)(dictTail - low) : 0u;
+            b.frame = (u32)f; b.flags = (pos == 0 ? ZB_FLAG_FIRST : 0u) | (pos + bsz == fsz ? ZB_FLAG_LAST : 0u) | (b.dictLen ? ZB_FLAG_DICT : 0u);
             P.blocks.push_back(b);
             if (b.size > maxBlock) maxBlock = b.size;
             pos += bsz;
         } while (pos < fsz);
         fr.nbBlocks = (u32)P.blocks.size() - fr.firstBlock;
         P.frames[f] = fr;
-        if (fr.nbBlocks == 1u) { tplSize = fsz; tplFrame = fr; tplBlock = P.blocks.back(); } else tplSize = ~0ull;
-        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) { ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.image = NULL; P.groups.push_back(g); }
-        else P.groups.back().b1 = (u32)P.blocks.size();
+        if (fr.nbBlocks == 1u) { tplSize = fsz; tplFrame = fr; tplBlock = P.blocks.back(); tplChunk = P.chunks.back(); } else tplSize = ~0ull;
+        if (P.groups.empty() || memcmp(&P.groups.back().prm, &prm, sizeof(prm)) != 0) {
+            ZbGroup g; g.prm = prm; g.b0 = fr.firstBlock; g.b1 = (u32)P.blocks.size(); g.c0 = firstChunk; g.c1 = (u32)P.chunks.size(); g.image = NULL; P.groups.push_back(g);
+        } else { P.groups.back().b1 = (u32)P.blocks.size(); P.groups.back().c1 = (u32)P.chunks.size(); }
     }
     P.sd = zb_strides(maxBlock);
 }
@@ -339,11 +386,11 @@ static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, co
 /* parse + upload the dictionary content tail; returns 0 or an error.  *d_dictEnd = NULL when no dictionary applies */
 /* device buffers of one dictionary: content tail with 32 bytes of padding on both sides, entropy state,
  * table images, pseudo block descriptors */
-static size_t zb_allocDictBuffers(u8** d_dict, ZbDictEntropy** d_de, u8** d_image, ZbBlock** d_dictBlock)
+static size_t zb_allocDictBuffers(u8** d_dict, ZbDictEntropy** d_de, u8** d_image, ZbChunk** d_dictChunk)
 {
     if (*d_dict) return 0;
     CK(cudaMalloc(d_dict, ZB_PRIME_BYTES + 64)); CK(cudaMalloc(d_de, sizeof(ZbDictEntropy)));
-    CK(cudaMalloc(d_image, (size_t)ZB_IMAGE_BYTES * ZB_MAX_IMAGES)); CK(cudaMalloc(d_dictBlock, ZB_MAX_IMAGES * sizeof(ZbBlock)));
+    CK(cudaMalloc(d_image, (size_t)ZB_IMAGE_BYTES * ZB_MAX_IMAGES)); CK(cudaMalloc(d_dictChunk, ZB_MAX_IMAGES * sizeof(ZbChunk)));
     return 0;
 }
 static size_t zb_uploadDict(u8* d_dict, ZbDictEntropy* d_de, const ZbDictEntropy* de, const u8* content, size_t contentSize, size_t tail, cudaStream_t stream)
@@ -367,7 +414,7 @@ static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, co
         std::lock_guard<std::mutex> g(*cd->lock);
         if (cd->device >= 0 && cd->device != c->device) return ZB_ERR(ZB_error_parameter_unsupported);   /* one device per CDict */
         if (cd->device < 0) {
-            {   size_t const e = zb_allocDictBuffers(&cd->d_dict, &cd->d_de, &cd->d_image, &cd->d_dictBlock); if (zb_isErr(e)) return e; }
+            {   size_t const e = zb_allocDictBuffers(&cd->d_dict, &cd->d_de, &cd->d_image, &cd->d_dictChunk); if (zb_isErr(e)) return e; }
             {   size_t const e = zb_uploadDict(cd->d_dict, cd->d_de, &cd->entropy, cd->content + cd->contentOff, cd->size - cd->contentOff, cd->tail, stream); if (zb_isErr(e)) return e; }
             CK(cudaStreamSynchronize(stream));                       /* other contexts (other streams) may use it right away */
             cd->device = c->device;
@@ -386,7 +433,7 @@ static size_t zb_prepareDict(ZSTD_CCtx* c, const void* dict, size_t dictSize, co
     size_t const contentSize = dictSize - contentOff;
     size_t const tail = contentSize < ZB_PRIME_BYTES ? contentSize : ZB_PRIME_BYTES;
     *effDictSize = dictSize; *dictTail = tail;
-    {   size_t const e = zb_allocDictBuffers(&c->d_dict, &c->d_de, &c->d_image, &c->d_dictBlock); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_allocDictBuffers(&c->d_dict, &c->d_de, &c->d_image, &c->d_dictChunk); if (zb_isErr(e)) return e; }
     {   size_t const e = zb_uploadDict(c->d_dict, c->d_de, &c->dictEntropy, (const u8*)dict + contentOff, contentSize, tail, stream); if (zb_isErr(e)) return e; }
     *d_dictEnd = c->d_dict + 32 + tail;
     if (c->dictEntropy.present) c->d_deActive = c->d_de;
@@ -402,7 +449,7 @@ static size_t zb_buildDictImages(ZSTD_CCtx* c, ZbPlan& P, const ZSTD_CDict* cdic
     ZSTD_CDict* const cd = const_cast<ZSTD_CDict*>(cdictC);
     if (!cd && P.groups.size() > ZB_MAX_IMAGES) return 0;
     u8* const images = cd ? cd->d_image : c->d_image;
-    ZbBlock* const dblk = cd ? cd->d_dictBlock : c->d_dictBlock;
+    ZbChunk* const dchk = cd ? cd->d_dictChunk : c->d_dictChunk;
     std::unique_lock<std::mutex> g;
     if (cd) g = std::unique_lock<std::mutex>(*cd->lock);
     u32 next = cd ? cd->nbImages : 0u;
@@ -412,36 +459,39 @@ static size_t zb_buildDictImages(ZSTD_CCtx* c, ZbPlan& P, const ZSTD_CDict* cdic
         u32 slot = ~0u;
         if (cd) for (u32 i = 0; i < cd->nbImages; i++) if (memcmp(&cd->imagePrm[i], &prm, sizeof(prm)) == 0) slot = i;
         if (slot == ~0u) {
-            if (next >= ZB_MAX_IMAGES) continue;                         /* no room: this group primes per block */
+            if (next >= ZB_MAX_IMAGES) continue;                         /* no room: this group walks the dictionary per frame */
             slot = next++;
-            ZbBlock b; memset(&b, 0, sizeof(b));
-            b.histLen = (u32)dictTail; b.size = 0; b.flags = ZB_FLAG_DICT;
-            b.insPhase = (u32)((prm.insPeriod - dictTail % prm.insPeriod) % prm.insPeriod);
-            CK(cudaMemcpyAsync(dblk + slot, &b, sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));      /* pageable source: staged before the call returns */
-            CK(zb_launch_dict_image(d_dictEnd, dblk + slot, &prm, images + (size_t)slot * ZB_IMAGE_BYTES, stream));
+            ZbChunk ch; memset(&ch, 0, sizeof(ch));
+            ch.histLen = (u32)dictTail; ch.dictLen = (u32)dictTail; ch.size = 0; ch.blockLog = 17;
+            CK(cudaMemcpyAsync(dchk + slot, &ch, sizeof(ZbChunk), cudaMemcpyHostToDevice, stream));      /* pageable source: staged before the call returns */
+            u32* const img = (u32*)(images + (size_t)slot * ZB_IMAGE_BYTES);
+            CK(zb_launch_dict_image(d_dictEnd, dchk + slot, &prm, img, stream));
             if (cd) { cd->imagePrm[slot] = prm; cd->nbImages = next; built = true; }
         }
-        P.groups[gi].image = images + (size_t)slot * ZB_IMAGE_BYTES;
+        P.groups[gi].image = (const u32*)(images + (size_t)slot * ZB_IMAGE_BYTES);
     }
     if (built) CK(cudaStreamSynchronize(stream));                        /* a cached image must be complete before another context reads it */
     return 0;
 }
 
-/* K1..K3 for blocks [b0, b1) using workspace slot positions [slot0, slot0 + (b1-b0)) */
-static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const u8* d_dictEnd, u32 b0, u32 b1, size_t slot0,
+/* K1..K3 for blocks [b0, b1) = chunks [c0, c1) using workspace slot positions [slot0, slot0 + (b1-b0)) */
+static size_t zb_runBlocks(ZSTD_CCtx* c, const ZbPlan& P, const u8* d_src, const u8* d_dictEnd, u32 b0, u32 b1, u32 c0, u32 c1, size_t slot0,
                            cudaStream_t stream, bool timed, unsigned* launches)
 {
     for (int phase = 0; phase < 3; phase++) {
         for (size_t g = 0; g < P.groups.size(); g++) {
             ZbGroup const& G = P.groups[g];
             u32 const lo = G.b0 > b0 ? G.b0 : b0, hi = G.b1 < b1 ? G.b1 : b1;
+            u32 const clo = G.c0 > c0 ? G.c0 : c0, chi = G.c1 < c1 ? G.c1 : c1;
             if (lo >= hi) continue;
             size_t const s = slot0 + (lo - b0);
             if (phase == 0) {
-                CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u8*)0, c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_dist + s * P.sd.dist,
-                                   G.prm.strategy == 2 ? c->d_dist2 + s * P.sd.dist : (u16*)0, c->d_seqs + s * P.sd.seq,
-                                   c->d_lits + s * P.sd.lit, c->d_meta + s, c->d_segmeta + s * ((P.sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG), (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
-                *launches += (G.prm.strategy == 2) ? 4 : 3;       /* walk(s), parse, merge */
+                bool const df = G.prm.strategy == 2;
+                CK(zb_launch_match(d_src, d_dictEnd, d_dictEnd ? G.image : (const u32*)0, c->d_blocks + lo, hi - lo, c->d_chunks + clo, chi - clo, lo, &G.prm, &P.sd,
+                                   c->d_dist + s * P.sd.dist, c->d_far + s * P.sd.dist, df ? c->d_dist2 + s * P.sd.dist : (u16*)0, df ? c->d_far2 + s * P.sd.dist : (u32*)0,
+                                   c->d_seqs + s * P.sd.seq, c->d_lits + s * P.sd.lit, c->d_meta + s, c->d_segmeta + s * ((P.sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG),
+                                   (timed && P.groups.size() == 1) ? c->evMid : (cudaEvent_t)0, stream));
+                *launches += df ? 4 : 3;       /* walk(s), parse, merge */
             } else if (phase == 1) {
                 CK(zb_launch_literals(c->d_blocks + lo, hi - lo, &G.prm, &P.sd, c->d_deActive, c->d_lits + s * P.sd.lit, c->d_body + s * P.sd.body, c->d_meta + s, stream));
                 *launches += 1;
@@ -468,15 +518,16 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
-    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1); if (zb_isErr(e)) return e;
+    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1, P.chunks.size()); if (zb_isErr(e)) return e;
         bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
         e = zb_ensureHeavy(c, nbBlocks, P.sd, d2); if (zb_isErr(e)) return e; }
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(c->d_chunks, P.chunks.data(), P.chunks.size() * sizeof(ZbChunk), cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->evK0, stream));
     unsigned launches = 0;
     if (nbFrames >= 8 || cdict) { size_t const e = zb_buildDictImages(c, P, cdict, d_dictEnd, dictTail, stream); if (zb_isErr(e)) return e; }
-    {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, stream, true, &launches); if (zb_isErr(e)) return e; }
+    {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, (u32)P.chunks.size(), 0, stream, true, &launches); if (zb_isErr(e)) return e; }
     CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, P.sd.body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
     if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
@@ -572,14 +623,24 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     u32 const ZB_WAVE_BLOCKS = (u32)((u64)waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist) > (1u << 22) ? (1u << 22) : waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist));
     /* wave boundaries.  Host path: the call ends when the LAST wave has gone through every kernel, so the
      * final waves shrink (1/2, 1/4, 1/8 of a wave): less work behind the last upload. */
-    std::vector<u32> wb;
-    {   std::vector<u32> tail;
+    std::vector<u32> wb, wc;                                      /* wave w = blocks [wb[w], wb[w+1]) = chunks [wc[w], wc[w+1]) */
+    {   std::vector<u32> tail, target;
         u32 left = nbBlocks;
         if (!deviceMemory) for (u32 sz = ZB_WAVE_BLOCKS / 8u; sz >= 32u && sz < ZB_WAVE_BLOCKS && left > 2u * sz; sz *= 2u) { tail.push_back(sz); left -= sz; }
-        wb.push_back(0);
-        for (u32 b = 0; b < left; ) { u32 const e = (left - b > ZB_WAVE_BLOCKS) ? b + ZB_WAVE_BLOCKS : left; wb.push_back(e); b = e; }
-        for (size_t i = tail.size(); i-- > 0; ) wb.push_back(wb.back() + tail[i]);
+        for (u32 b = 0; b < left; ) { u32 const e = (left - b > ZB_WAVE_BLOCKS) ? b + ZB_WAVE_BLOCKS : left; target.push_back(e - b); b = e; }
+        for (size_t i = tail.size(); i-- > 0; ) target.push_back(tail[i]);
+        /* a chunk is never split between waves: waves are filled chunk by chunk up to their target size */
+        wb.push_back(0); wc.push_back(0);
+        u32 acc = 0; size_t ti = 0;
+        for (u32 ci = 0; ci < (u32)P.chunks.size(); ci++) {
+            u32 const nextFirst = ci + 1u < (u32)P.chunks.size() ? P.chunks[ci + 1u].firstBlock : nbBlocks;
+            acc += nextFirst - P.chunks[ci].firstBlock;
+            if (ti < target.size() && acc >= target[ti] && ci + 1u < (u32)P.chunks.size()) { wb.push_back(nextFirst); wc.push_back(ci + 1u); acc = 0; ti++; }
+        }
+        wb.push_back(nbBlocks); wc.push_back((u32)P.chunks.size());
     }
+    u32 maxWaveBlocks = 0;
+    for (size_t w = 0; w + 1 < wb.size(); w++) if (wb[w + 1] - wb[w] > maxWaveBlocks) maxWaveBlocks = wb[w + 1] - wb[w];
     u32 const nbWaves = (u32)wb.size() - 1u;
     u32 const slots = nbWaves < ZB_WAVE_SLOTS ? nbWaves : ZB_WAVE_SLOTS;
     size_t inEnd = 0, bound = 0;
@@ -588,9 +649,9 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         bound += ZSTD_compressBound(frameSizes[f]) + 32;
     }
     size_t const outCap = deviceMemory ? dstCapacity : (dstCapacity < bound ? dstCapacity : bound);
-    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves); if (zb_isErr(e)) return e;
+    {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, nbWaves, P.chunks.size()); if (zb_isErr(e)) return e;
         bool d2 = false; for (size_t g = 0; g < P.groups.size(); g++) d2 |= (P.groups[g].prm.strategy == 2);
-        e = zb_ensureHeavy(c, (size_t)slots * (nbWaves > 1 ? ZB_WAVE_BLOCKS : nbBlocks), P.sd, d2); if (zb_isErr(e)) return e; }
+        e = zb_ensureHeavy(c, (size_t)slots * maxWaveBlocks, P.sd, d2); if (zb_isErr(e)) return e; }
     u8* d_in; u8* d_out;
     if (deviceMemory) { d_in = (u8*)src; d_out = dst; }
     else {
@@ -616,6 +677,7 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     CK(cudaEventRecord(c->evStart, sCopy));
     CK(cudaMemcpyAsync(c->d_blocks, P.blocks.data(), nbBlocks * sizeof(ZbBlock), cudaMemcpyHostToDevice, sCopy));
     CK(cudaMemcpyAsync(c->d_frames, P.frames.data(), nbFrames * sizeof(ZbFrame), cudaMemcpyHostToDevice, sCopy));
+    CK(cudaMemcpyAsync(c->d_chunks, P.chunks.data(), P.chunks.size() * sizeof(ZbChunk), cudaMemcpyHostToDevice, sCopy));
     if (nbFrames >= 8 || cdict) { size_t const e = zb_buildDictImages(c, P, cdict, d_dictEnd, dictTail, sCopy); if (zb_isErr(e)) return e; }
     cudaStream_t lastStream = sCopy;
     for (u32 w = 0; w < nbWaves && !err; w++) {
@@ -629,10 +691,10 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         {   size_t const e = getStream(w % slots, &st); if (zb_isErr(e)) return e; }
         lastStream = st;
         CK(cudaStreamWaitEvent(st, evH2D[w], 0));
-        err = zb_runBlocks(c, P, d_in, d_dictEnd, b0, b1, (size_t)(w % slots) * ZB_WAVE_BLOCKS, st, false, &launches);
+        err = zb_runBlocks(c, P, d_in, d_dictEnd, b0, b1, wc[w], wc[w + 1], (size_t)(w % slots) * maxWaveBlocks, st, false, &launches);
         if (err) break;
         if (w > 0) CK(cudaStreamWaitEvent(st, evStitch[w - 1], 0));
-        size_t const s0 = (size_t)(w % slots) * ZB_WAVE_BLOCKS;
+        size_t const s0 = (size_t)(w % slots) * maxWaveBlocks;
         CK(zb_launch_stitch(d_in, c->d_blocks + b0, b1 - b0, c->d_frames, c->d_body + s0 * P.sd.body, P.sd.body, c->d_meta + s0,
                             c->d_outOffsets + b0, w > 0 ? c->d_totals + (w - 1) : NULL, c->d_totals + w, d_out, outCap, st));
         launches += 2;
@@ -714,7 +776,7 @@ static size_t zb_compressFramesAny(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
             u32 const m = frameSizes[f] < ZB_BLOCK_MAX ? (u32)frameSizes[f] : ZB_BLOCK_MAX; if (m > maxBlock) maxBlock = m;
         }
         ZbStrides const sd = zb_strides(maxBlock);
-        u64 const wsBytes = nb * ((u64)sd.dist * 2u + (u64)sd.seq * 8u + sd.lit + sd.body);        /* one-wave workspace */
+        u64 const wsBytes = nb * ((u64)sd.dist * 6u + (u64)sd.seq * 8u + sd.lit + sd.body);        /* one-wave workspace */
         if (!streamv && c->devWaveBlocks && (bytes >= 2ull * c->devWaveBlocks * ZB_BLOCK_MAX || wsBytes > (12ull << 30)))
             return zb_compressFramesWaves(c, (u8*)dst, dstCapacity, (const u8*)src, frameOffsets, frameSizes, nbFrames, dict, dictSize, cdict, cSizes, level, true);
         cudaStream_t stream = streamv ? (cudaStream_t)streamv : c->stream;
@@ -770,7 +832,7 @@ extern "C" size_t ZSTD_freeCDict(ZSTD_CDict* cd)                                
     if (cd->device >= 0) {
         int prev = -1; cudaGetDevice(&prev);
         cudaSetDevice(cd->device);
-        cudaFree(cd->d_dict); cudaFree(cd->d_de); cudaFree(cd->d_image); cudaFree(cd->d_dictBlock);
+        cudaFree(cd->d_dict); cudaFree(cd->d_de); cudaFree(cd->d_image); cudaFree(cd->d_dictChunk);
         if (prev >= 0) cudaSetDevice(prev);
     }
     free(cd->content); delete cd->lock; free(cd);
@@ -835,9 +897,10 @@ extern "C" size_t ZSTDB200_writeSeekTable(void* dstv, size_t dstCapacity, const 
 extern "C" unsigned long long ZSTDB200_xxh64(const void* p, size_t len) { return zb_xxh64((const u8*)p, len); }
 
 /* Host-side planning of one call, without touching a GPU (what the CPU tests compare with the oracle's plan).
- * Per frame, `out` receives ZSTDB200_PLAN_FIELDS values: strategy, mls, hashLog, longHashLog, stepSize, litDisabled, windowLog,
- * insPeriod, insPeriodLong, number of blocks, size of the first block, flags of the first block, history of the last
- * block, insertion phase of the last block.  Returns the total number of blocks. */
+ * Per frame, `out` receives 16 values: strategy, mls, tableN, tableNLong, stepSize, litDisabled, windowLog, insStep,
+ * number of blocks, size of the first block, flags of the first block, history of the last block, dictionary part of
+ * the first block's history, number of chunks, history walked by the last chunk, size of the last chunk.
+ * Returns the total number of blocks. */
 extern "C" size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFrames, int level, size_t dictSize, size_t dictTail, unsigned* out)
 {
     std::vector<size_t> offs(nbFrames);
@@ -849,10 +912,12 @@ extern "C" size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFrame
         const ZbParams* prm = NULL;
         for (size_t g = 0; g < P.groups.size(); g++) if (P.groups[g].b0 <= fr.firstBlock && fr.firstBlock < P.groups[g].b1) prm = &P.groups[g].prm;
         ZbBlock const& b0 = P.blocks[fr.firstBlock]; ZbBlock const& bl = P.blocks[fr.firstBlock + fr.nbBlocks - 1];
-        unsigned* r = out + f * 14;
-        r[0] = prm->strategy; r[1] = prm->mls; r[2] = prm->hashLog; r[3] = prm->longHashLog; r[4] = prm->stepSize; r[5] = prm->litDisabled;
-        r[6] = fr.windowLog; r[7] = prm->insPeriod; r[8] = prm->insPeriodLong; r[9] = fr.nbBlocks; r[10] = b0.size; r[11] = b0.flags;
-        r[12] = bl.histLen; r[13] = bl.insPhase;
+        u32 nc = 0; const ZbChunk* lastChunk = NULL;
+        for (size_t ci = 0; ci < P.chunks.size(); ci++) if (P.chunks[ci].firstBlock >= fr.firstBlock && P.chunks[ci].firstBlock < fr.firstBlock + fr.nbBlocks) { nc++; lastChunk = &P.chunks[ci]; }
+        unsigned* r = out + f * 16;
+        r[0] = prm->strategy; r[1] = prm->mls; r[2] = prm->tableN; r[3] = prm->tableNLong; r[4] = prm->stepSize; r[5] = prm->litDisabled;
+        r[6] = fr.windowLog; r[7] = prm->insStep; r[8] = fr.nbBlocks; r[9] = b0.size; r[10] = b0.flags;
+        r[11] = bl.histLen; r[12] = b0.dictLen; r[13] = nc; r[14] = lastChunk ? lastChunk->histLen : 0; r[15] = lastChunk ? lastChunk->size : 0;
     }
     return P.blocks.size();
 }

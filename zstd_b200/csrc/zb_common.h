@@ -17,7 +17,14 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 
 #define ZB_BLOCK_MAX     (128u << 10)
-#define ZB_PRIME_BYTES   (64u << 10)         /* history primed into a block's table (ZSTDMT overlap idea, zstdmt_compress.c:1182-1227) */
+#define ZB_PRIME_BYTES   (128u << 10)        /* history primed into a chunk's table (ZSTDMT overlap idea, zstdmt_compress.c:1182-1227) */
+#define ZB_CHUNK_BLOCKS  4u                  /* blocks per chunk: one hash table lives through a chunk */
+#define ZB_BATCH         1024u               /* positions of one walk batch = threads of the walk CTA */
+#define ZB_TAG_BITS      11u                 /* table entry = (position + 1) << 11 | tag, positions relative to the chunk's history start */
+#define ZB_FAST_HASHLOG_MAX   14u
+#define ZB_DFAST_SHORT_MAX    51200u         /* buckets: 200 KiB of shared memory */
+#define ZB_DFAST_LONGLOG_MAX  15u
+#define ZB_FAR           0xFFFFu             /* dist16 value: the distance is in the far array */
 #define ZB_MAX_SEQ       (ZB_BLOCK_MAX / 4)  /* every sequence carries a match of >= 4 bytes */
 #define ZB_SEQ_STRIDE    (ZB_MAX_SEQ + 8)    /* u64 per block */
 #define ZB_LIT_STRIDE    (ZB_BLOCK_MAX + 256)/* bytes per block */
@@ -53,12 +60,23 @@ typedef uint64_t u64;
 typedef struct {
     u64 srcOff;        /* block start, byte offset into the input buffer */
     u32 size;          /* block size */
-    u32 histLen;       /* bytes of same-frame history visible before the block (<= ZB_PRIME_BYTES) */
+    u32 histLen;       /* bytes of history a match of this block may reach back into (chunk history and window) */
     u32 frame;         /* index into ZbFrame[] */
     u32 flags;         /* ZB_FLAG_* */
-    u32 insPhase;      /* (frame position of the oldest visible byte) % insPeriod */
-    u32 insPhaseLong;  /* same for insPeriodLong (dfast) */
+    u32 dictLen;       /* the oldest dictLen bytes of that history are the tail of the call's dictionary content (ZB_FLAG_DICT) */
+    u32 pad;
 } ZbBlock;
+
+/* one chunk = up to ZB_CHUNK_BLOCKS consecutive blocks of a frame: the unit of the candidate walk */
+typedef struct {
+    u64 srcOff;        /* chunk start, byte offset into the input buffer */
+    u32 size;          /* bytes in the chunk */
+    u32 histLen;       /* bytes walked in front of the chunk to prime the table (<= ZB_PRIME_BYTES) */
+    u32 dictLen;       /* the oldest dictLen of them are the dictionary content's tail (first chunk of a frame only) */
+    u32 firstBlock;    /* index of the chunk's first block in the call's block array */
+    u32 blockLog;      /* log2 of the frame's block size: block k of the chunk starts at k << blockLog */
+    u32 pad;
+} ZbChunk;
 
 typedef struct {
     u64 srcOff;        /* frame input start */
@@ -107,15 +125,14 @@ typedef struct {
 typedef struct {
     u32 strategy;      /* 1 = fast, 2 = dfast */
     u32 mls;           /* bytes hashed by the (short) table: 4..8 */
-    u32 hashLog;       /* log2 entries, short table */
-    u32 longHashLog;   /* dfast: log2 entries of the 8-byte table */
+    u32 tableN;        /* buckets of the (short) table; bucket = (hash32 * tableN) >> 32 */
+    u32 tableNLong;    /* dfast: buckets of the 8-byte-hash table */
     u32 stepSize;      /* zstd_fast.c:200 */
     u32 litDisabled;   /* zstd_compress_internal.h:621-633 */
     u32 windowLog;
-    u32 insPeriod;     /* positions with (framePos % insPeriod) < 2 enter the table */
-    u32 insPeriodLong; /* dfast: same for the 8-byte-hash table */
-    u32 longPass;      /* set by the launcher for the candidate walk of the long table (uses insPhaseLong) */
-    u32 startRep[2];   /* repcodes a ZB_FLAG_DICT block starts with (zstd-format dictionary), 0 = invalid */
+    u32 insStep;       /* positions without a candidate enter the table when ((pos - low) % step) < 2, step = insStep + walked / 128 */
+    u32 startRep[2];   /* repcodes the search of a frame's first segment starts with (zstd-format dictionary), 0 = none */
+    u32 codeRep[3];    /* repcode history the decoder holds at a frame's first block: {1,4,8} or the dictionary's */
 } ZbParams;
 
 /* Per-block strides of the workspace arrays of one call, derived from its largest block (M = that size
@@ -125,14 +142,12 @@ typedef struct {
 #define ZB_PARSE_SEG   (16u << 10)
 #define ZB_PARSE_SEGS  (ZB_BLOCK_MAX / ZB_PARSE_SEG)
 typedef struct {
-    u32 nbSeq;         /* sequences of the segment, stored from seq slot k * ZB_PARSE_SEG / 4 */
-    u32 litSize;       /* unused (0): the parse kernels emit no literal bytes, K1c gathers them from the input */
-    u32 trail;         /* literals behind the segment's last match: they lengthen the next sequence of the block */
-    u32 pad;
+    u32 nbSeq;         /* raw sequences of the segment, stored from seq slot k * ZB_PARSE_SEG / 4 */
+    u32 pad[3];
 } ZbSegMeta;
 
 typedef struct {
-    u32 dist;          /* u16 per block : candidate distances; K3 reuses the area for 3 x state records */
+    u32 dist;          /* u16 per block : candidate distances (+ as many u32 of "far" distances); K3 reuses the u16 area for 3 x state records */
     u32 seq;           /* u64 per block : packed sequences */
     u32 lit;           /* bytes per block : literal bytes (multiple of 16) */
     u32 body;          /* bytes per block : compressed block body staging (multiple of 16) */

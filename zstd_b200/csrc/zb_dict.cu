@@ -51,40 +51,45 @@ size_t readNCount(short* norm, u32* maxSymbolPtr, u32* tableLogPtr, const u8* p,
     return bytes <= avail ? bytes : 0;
 }
 
-/* fse_compress.c:68-214 (host copy of the table builder the kernels use for fresh tables) */
+/* Compression table of a normalised distribution that may hold low-probability (-1) symbols: dictionaries and the
+ * format's predefined distributions have them (format "FSE decoding table": such a symbol owns one cell at the top of
+ * the table, the spread walk steps over that area).  Host code; the kernels build the tables of fresh distributions,
+ * which never hold -1, with zbw_fse_buildCTable (zb_entropy.cuh).  The reference's builder is FSE_buildCTable_wksp
+ * (lib/compress/fse_compress.c:68). */
 void buildCTable(ZbdFseCTable* ct, const short* norm, u32 maxSymbolValue, u32 tableLog)
 {
-    u32 const tableSize = 1u << tableLog, tableMask = tableSize - 1;
-    u32 const step = (tableSize >> 1) + (tableSize >> 3) + 3;
-    u32 const maxSV1 = maxSymbolValue + 1;
-    u16 cumul[66]; u8 tableSymbol[512];
-    u32 highThreshold = tableSize - 1;
+    u32 const size = 1u << tableLog, mask = size - 1u, step = (size >> 1) + (size >> 3) + 3u;
+    u32 const nbSym = maxSymbolValue + 1u;
+    u8 owner[512];                      /* symbol of every cell */
+    u32 weight[64], first[65];
     memset(ct, 0, sizeof(*ct));
     ct->tableLog = tableLog; ct->maxSymbolValue = maxSymbolValue;
-    cumul[0] = 0;
-    for (u32 u = 1; u <= maxSV1; u++) {
-        if (norm[u - 1] == -1) { cumul[u] = cumul[u - 1] + 1; tableSymbol[highThreshold--] = (u8)(u - 1); }
-        else cumul[u] = cumul[u - 1] + (u16)norm[u - 1];
-    }
-    cumul[maxSV1] = (u16)(tableSize + 1);
-    u32 position = 0;
-    for (u32 s = 0; s < maxSV1; s++) for (int i = 0; i < norm[s]; i++) {
-        tableSymbol[position] = (u8)s;
-        position = (position + step) & tableMask;
-        while (position > highThreshold) position = (position + step) & tableMask;
-    }
-    for (u32 u = 0; u < tableSize; u++) { u8 const s = tableSymbol[u]; ct->nextState[cumul[s]++] = (u16)(tableSize + u); }
-    u32 total = 0;
-    for (u32 s = 0; s <= maxSymbolValue; s++) {
-        int const n = norm[s];
-        if (n == 0) { ct->deltaNbBits[s] = ((tableLog + 1) << 16) - (1u << tableLog); ct->deltaFindState[s] = 0; }
-        else if (n == -1 || n == 1) { ct->deltaNbBits[s] = (tableLog << 16) - (1u << tableLog); ct->deltaFindState[s] = (int)(total - 1); total++; }
-        else {
-            u32 const maxBitsOut = tableLog - hb32((u32)n - 1);
-            ct->deltaNbBits[s] = (maxBitsOut << 16) - ((u32)n << maxBitsOut);
-            ct->deltaFindState[s] = (int)(total - (u32)n);
-            total += (u32)n;
+    /* cells a symbol owns, and where its sub-states start in nextState[] */
+    first[0] = 0;
+    for (u32 s = 0; s < nbSym; s++) { weight[s] = norm[s] == -1 ? 1u : (u32)norm[s]; first[s + 1] = first[s] + weight[s]; }
+    /* low-probability symbols: the top cells, highest first, in symbol order */
+    u32 top = size;
+    for (u32 s = 0; s < nbSym; s++) if (norm[s] == -1) owner[--top] = (u8)s;
+    /* the walk: every cell below `top` exactly once (step is odd), handed to the other symbols occurrence by occurrence */
+    {   u32 cell = 0, s = 0, left = 0;
+        for (u32 visited = 0; visited < top; ) {
+            while (left == 0) { left = norm[s] > 0 ? (u32)norm[s] : 0u; if (left == 0) s++; }
+            if (cell < top) { owner[cell] = (u8)s; visited++; if (--left == 0) s++; }
+            cell = (cell + step) & mask;
         }
+    }
+    /* sub-states in ascending cell order */
+    {   u32 given[64];
+        for (u32 s = 0; s < nbSym; s++) given[s] = 0;
+        for (u32 cell = 0; cell < size; cell++) { u32 const s = owner[cell]; ct->nextState[first[s] + given[s]++] = (u16)(size + cell); }
+    }
+    /* per-symbol transform: bits shed before a state lands in [weight, 2 * weight), offset of the sub-states */
+    for (u32 s = 0; s < nbSym; s++) {
+        u32 const n = weight[s];
+        if (n == 0) { ct->deltaNbBits[s] = ((tableLog + 1u) << 16) - size; ct->deltaFindState[s] = 0; continue; }
+        u32 const shed = n == 1u ? tableLog : tableLog - hb32(n - 1u);
+        ct->deltaNbBits[s] = (shed << 16) - (n << shed);
+        ct->deltaFindState[s] = (int)first[s] - (int)n;
     }
 }
 
@@ -125,6 +130,19 @@ size_t decodeWeights(u8* out, size_t maxOut, const u8* src, size_t srcSize)
 
 /* Returns the offset of the dictionary content inside `dict` (0 for raw content / ignored dictionaries:
  * then de->present == 0), or a zstd error code (dictionary_corrupted). */
+/* the format's predefined distributions (doc/zstd_compression_format.md "Default Distributions"; RFC 8878 3.1.1.3.2.2):
+ * literal lengths and match lengths with 64 states, offsets with 32.  out[0] = LL, out[1] = OF, out[2] = ML. */
+extern "C" void zb_buildDefaultTables(ZbdFseCTable* out)
+{
+    static const short ll[36] = { 4,3,2,2,2,2,2,2, 2,2,2,2,2,1,1,1, 2,2,2,2,2,2,2,2, 2,3,2,1,1,1,1,1, -1,-1,-1,-1 };
+    static const short of[29] = { 1,1,1,1,1,1,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, -1,-1,-1,-1,-1 };
+    static const short ml[53] = { 1,4,3,2,2,2,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1,
+                                  1,1,1,1,1,1,1,1, 1,1,1,1,1,1,-1,-1, -1,-1,-1,-1,-1 };
+    buildCTable(&out[0], ll, 35, 6);
+    buildCTable(&out[1], of, 28, 5);
+    buildCTable(&out[2], ml, 52, 6);
+}
+
 extern "C" size_t zb_loadDictionary(ZbDictEntropy* de, const u8* dict, size_t dictSize)
 {
     size_t const corrupted = ZB_ERR(ZB_error_dictionary_corrupted);

@@ -8,18 +8,24 @@
 extern "C" {
 #endif
 
-/* K1: match-finder = K1a candidate table walk (one warp per block) + K1b greedy parse (fast strategy: one warp per
- * 16 KiB segment, joined by K1c; d_segmeta: ZB_PARSE_SEGS records per block).
- * Per-block workspace strides come in `sd` (ZbStrides, derived from the call's largest block).
- * d_dist: sd->dist u16 per block (dead after this call; K3 reuses it for the FSE state records);
- * d_dist2: same size, only used by the doubleFast strategy (short-hash candidates).
- * d_dictEnd: one past the dictionary content in device memory (NULL = no dictionary); blocks flagged
- * ZB_FLAG_DICT take their histLen bytes of history from in front of it.  d_image (may be NULL): table
- * already primed from that dictionary tail by zb_launch_dict_image (same ZbParams), 3 << hashLog bytes. */
-cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream);
-cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sd,
-                            u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta,
+/* K1: match-finder = K1a candidate walk (one CTA per chunk) + K1b greedy parse (one warp per 16 KiB segment) + K1c merge
+ * (d_segmeta: ZB_PARSE_SEGS records per block).  d_blocks / d_chunks point at the first block / chunk of the launch;
+ * the launch's blocks use the workspace rows [0, nbBlocks) of the arrays passed in, slotFirstBlock = index (in the
+ * call's block array) of the block that owns row 0.  Per-block workspace strides come in `sd` (ZbStrides).
+ * d_dist / d_far: sd->dist u16 + u32 per block (dead after this call; K3 reuses d_dist for the FSE state records);
+ * d_dist2 / d_far2: same, only used by the doubleFast strategy (short-hash candidates).
+ * d_dictEnd: one past the dictionary content in device memory (NULL = no dictionary); chunks / blocks with dictLen > 0
+ * take the oldest dictLen bytes of their history from in front of it.  d_image (may be NULL): table already walked
+ * over that dictionary tail by zb_launch_dict_image (same ZbParams), prm->tableN u32. */
+cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbChunk* d_dictChunk, const ZbParams* prm, u32* d_image, cudaStream_t stream);
+cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u32* d_image, const ZbBlock* d_blocks, u32 nbBlocks,
+                            const ZbChunk* d_chunks, u32 nbChunks, u32 slotFirstBlock, const ZbParams* prm, const ZbStrides* sd,
+                            u16* d_dist, u32* d_far, u16* d_dist2, u32* d_far2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta,
                             cudaEvent_t evMid, cudaStream_t stream);
+
+/* host: the format's predefined FSE tables (zb_dict.cu), and their upload to the current device (zb_sequences.cu) */
+void zb_buildDefaultTables(ZbdFseCTable* out3);
+cudaError_t zb_upload_default_tables(const ZbdFseCTable* host3, cudaStream_t stream);
 
 /* host: parse a dictionary (zb_dict.cu).  Returns the content offset, 0 for raw content, or an error code */
 size_t zb_loadDictionary(ZbDictEntropy* de, const u8* dict, size_t dictSize);

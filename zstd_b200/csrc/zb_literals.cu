@@ -4,7 +4,7 @@
  * and HUF_compress_internal (huf_compress.c:1333-1430) for a fresh entropy state:
  *   1. 256-bin histogram: per-warp privatised bins in shared memory + merge (hist.c:66-133)
  *   2. raw / RLE / compressed decision with the reference's thresholds
- *   3. Huffman table + tree description: serial, one thread, shared memory (zb_entropy.cuh)
+ *   3. Huffman table + tree description: the whole CTA (zb_entropy.cuh)
  *   4. 1 or 4 streams (huf_compress.c:1056-1118, :1168-1215): every thread owns a contiguous run of
  *      symbols, a suffix sum over per-thread bit counts gives its bit offset (streams grow from the
  *      LAST symbol), then bits are packed straight into the output words (edge words by atomicOr).
@@ -102,7 +102,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides s
     ZbdHufWksp& wk = *reinterpret_cast<ZbdHufWksp*>(scratch);
     __shared__ u32 count[256];
     __shared__ u32 enc[256];
-    __shared__ __align__(16) u8 hdr[144];
+    __shared__ __align__(16) u8 hdr[288];                         /* the FSE form of the tree description is written before it is known to be short */
     __shared__ u32 red[16];
     __shared__ u32 chunkBits[LIT_THREADS];
     __shared__ u32 sh_largest, sh_maxSym, sh_mode, sh_hSize, sh_usePrev;
@@ -157,24 +157,21 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides s
     }
     if (mode == MODE_HUF && !usePrev && preferRepeat && repeat != 0u) usePrev = true;      /* :1395-1399 */
     if (mode == MODE_HUF && !usePrev) {
+        u32 const maxSym = sh_maxSym;
+        u32 const huffLog = zbd_fse_optimalTableLog(11, n, maxSym, 1);              /* huf_compress.c:1284-1287 */
+        u32 const maxBits = zbc_huf_build<LIT_THREADS>(&wk, count, maxSym, huffLog, enc);
+        u32 const hSizeNew = (maxBits == ZBD_ERR) ? ZBD_ERR : zbc_huf_writeHeader<LIT_THREADS>(&wk, hdr, enc, maxSym, maxBits, &sh_hSize);
         if (tid == 0) {
-            u32 md = MODE_HUF, hSize = 0;
-            u32 const maxSym = sh_maxSym;
-            u32 huffLog = zbd_fse_optimalTableLog(11, n, maxSym, 1);        /* huf_compress.c:1284-1287 */
-            u32 const maxBits = zbd_huf_build(&wk, count, maxSym, huffLog, enc);
-            u32 prev = 0;
-            if (maxBits == ZBD_ERR) md = MODE_RAW;
+            u32 md = MODE_HUF, hSize = 0, prev = 0;
+            if (hSizeNew == ZBD_ERR) md = MODE_RAW;
             else {
-                hSize = zbd_huf_writeHeader(&wk, hdr, enc, maxSym, maxBits);
-                if (hSize == ZBD_ERR) md = MODE_RAW;
-                else {
-                    if (repeat != 0u) {                                        /* :1415-1422 : is the old table cheaper? */
-                        u32 oldBits = 0, newBits = 0;
-                        for (u32 sy = 0; sy <= maxSym; sy++) { oldBits += (de->hufEnc[sy] >> 16) * count[sy]; newBits += (enc[sy] >> 16) * count[sy]; }
-                        if ((oldBits >> 3) <= hSize + (newBits >> 3) || hSize + 12u >= n) prev = 1;
-                    }
-                    if (!prev && hSize + 12u >= n) md = MODE_RAW;              /* :1426 */
+                hSize = hSizeNew;
+                if (repeat != 0u) {                                        /* huf_compress.c:1415-1422 : is the old table cheaper? */
+                    u32 oldBits = 0, newBits = 0;
+                    for (u32 sy = 0; sy <= maxSym; sy++) { oldBits += (de->hufEnc[sy] >> 16) * count[sy]; newBits += (enc[sy] >> 16) * count[sy]; }
+                    if ((oldBits >> 3) <= hSize + (newBits >> 3) || hSize + 12u >= n) prev = 1;
                 }
+                if (!prev && hSize + 12u >= n) md = MODE_RAW;              /* :1426 */
             }
             sh_mode = md; sh_hSize = hSize; sh_usePrev = prev;
         }

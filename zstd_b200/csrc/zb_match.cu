@@ -2,21 +2,23 @@
  *
  * Replaces the CPU loops ZSTD_compressBlock_fast_noDict_generic / _extDict_generic
  * (/root/reference/lib/compress/zstd_fast.c:192-423, :709-960) and ZSTD_compressBlock_doubleFast_noDict_generic
- * (zstd_double_fast.c:105-323) with a data-parallel formulation; a <=128 KiB block is the independent unit:
- *   - K1a (one warp per block) walks a private hash table in shared memory (2^hashLog buckets: 16-bit position
- *     modulo 64 KiB relative to the start of the visible history + 8-bit tag), primed from the <=64 KiB in front of
- *     the block (zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:726-731 for job overlaps), and
- *     records every position's candidate distance; insertion follows a fixed position pattern, so the walk does not
- *     depend on the parse;
- *   - K1b (one warp per 16 KiB segment of the block) does the greedy selection: 32 probe positions per step — pairs
+ * (zstd_double_fast.c:105-323) with a data-parallel formulation:
+ *   - K1a (one 1024-thread CTA per CHUNK of up to 4 blocks) keeps the chunk's hash table in shared memory — primed from
+ *     the <=128 KiB in front of the chunk (zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:1182-1227 for
+ *     job overlaps), then alive through all blocks of the chunk — and visits the positions in BATCHES of 1024: every
+ *     position of a batch reads its bucket, positions that found no candidate are inserted, and look-ups see the batch's
+ *     own insertions at lower positions through a per-batch chained index, so the result equals a sequential walk whose
+ *     insertion decisions were taken on the table as the previous batch left it.  Two barriers per batch, no dependent
+ *     global load: the walk does not depend on the parse;
+ *   - K1b (one warp per 16 KiB segment of a block) does the greedy selection: 32 probe positions per step — pairs
  *     (p, p+1) spaced by `step` as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward
  *     catch-up (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are warp-cooperative:
- *     32 x 8 bytes per round, first differing lane found by ballot.  It emits packed sequences only;
- *   - K1c (one CTA per block) joins the segments' sequences and gathers the literal bytes from the input.
- * Table writes are deterministic: the highest inserted lane of a step wins a bucket.
+ *     32 x 8 bytes per round, first differing lane found by ballot.  A match may run past its segment's end;
+ *   - K1c (one CTA per block) joins the segments: drops what lies under a match that ran over from an earlier segment,
+ *     runs the repcode history over the block's sequences and gathers the literal bytes from the input.
+ * Everything is deterministic: no result depends on the order in which threads reach an atomic.
  * The bit-exact CPU model of these kernels is oracle/zb_match.c (tests only).
  */
-#include <cuda_pipeline.h>
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
@@ -58,281 +60,153 @@ __device__ __forceinline__ u32 zb_back_coop(const ZbSeg& sg, u32 probe, u32 offs
     }
 }
 
+/* raw sequence of the parse kernels: real offset, match length, match start relative to the block */
+__device__ __forceinline__ u64 zb_pack_raw(u32 off, u32 mlen, u32 msRel) { return (u64)off | ((u64)mlen << 24) | ((u64)msRel << 42); }
+#define ZB_RAW_OFF(r)  ((u32)(r) & 0xFFFFFFu)
+#define ZB_RAW_MLEN(r) ((u32)((r) >> 24) & 0x3FFFFu)
+#define ZB_RAW_MS(r)   ((u32)((r) >> 42))
+/* final sequence, read by the sequences kernel */
 __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen)
 {
     return (u64)offBase | ((u64)litLen << 24) | ((u64)matchLen << 42);
 }
 
 /* ------------------------------------------------------------------------------------------------
- * K1a — candidate table walk (parse-independent).  One warp per block, table in shared memory.
- * For every position p of the block: dist[p] = distance to the most recent earlier position that was
- * inserted and has the same hash (0 = none).  32 consecutive positions per step; within a step the
- * sequential semantics are kept (a lane sees the inserted lanes below it, the highest inserted lane
- * of a hash group updates the table) with a write / read-back of the bucket; __match_any_sync would do
- * it in one instruction but costs ~400 cycles on sm_100a (profiles/r1_cand_match_any.txt).  No load depends on the table, so input
- * loads are issued one step ahead and the loop-carried chain is LDS -> STS only.
+ * K1a — candidate walk (parse-independent).  One CTA per chunk, table in shared memory.
+ * dist[p] = distance from p to its candidate: the latest earlier position that was inserted into p's bucket and has
+ * p's tag, 0 if none.  Distances >= 0xFFFF go to the `far` array (dist16 = ZB_FAR).
  * ---------------------------------------------------------------------------------------------- */
-#define CAND_CHUNK 512u                      /* bytes staged per cp.async group: 32 lanes x 16 B */
-#define CAND_STAGES 4u                       /* ring = 4 chunks = 2 KiB, 3 chunks in flight ahead of the consumer */
-#define CAND_RING (CAND_CHUNK * CAND_STAGES)
+#define WALK_HEADS 1024u
+#define WALK_NONE  0xFFFFFFFFu
+#define WALK_AUX_BYTES (2u * ZB_BATCH * 4u + 2u * WALK_HEADS * 4u + 2u * ZB_BATCH * 2u)     /* hsh + heads + nxt */
 
-/* One 16-step slice of the table walk (phase B of zb_cand_kernel).  INTERIOR: every lane of every
- * step is an in-block position with 8 readable bytes, so the activity predicates fold away.
- * table/tags are the warp's communication medium (lanes read what other lanes wrote in the same step):
- * volatile, never __restrict__. */
-template <bool INTERIOR>
-__device__ __forceinline__ void zb_cand_walk16(volatile u16* table, volatile u8* tags, const u32* hh,
-                                               u32 q0, u32 o0, u32 pmin, u32 nPos, u32 bs, u32 lane,
-                                               u32& ph, u32 inc, u32 period, u16* __restrict__ mydist)
+/* candidate distance of the position `me` - 1 given a bucket's content c (0 = no candidate) */
+__device__ __forceinline__ u32 zb_cand(u32 c, u32 h, u32 me)
 {
-    /* The bucket of step j+1 is read in the same shared-memory round as the read-back of step j (nothing writes
-     * the table in between, except the rare peel below, which reads it again): one LDS round trip per step
-     * instead of two on the loop-carried chain. */
-    bool act_c = INTERIOR ? true : ((q0 + lane >= o0 + pmin) && (q0 + lane - o0 < nPos));
-    u32 old_c = act_c ? table[hh[0] >> 8] : 0u;
-    u32 oldtag_c = act_c ? tags[hh[0] >> 8] : 0x100u;
-#pragma unroll
-    for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
-        u32 const q = q0 + 32u * j + lane;
-        bool const act = act_c;
-        u32 const p = q - o0;
-        u32 const h = act ? (hh[j] >> 8) : 0u;
-        u32 const tag = hh[j] & 0xFFu;
-        bool const ins = act && ph < 2u;
-        u32 const old = old_c, oldtag = oldtag_c;
-        /* let every inserting lane write its bucket, read it back: when no two inserting lanes share a bucket
-         * (the common case) the read-back alone resolves the step */
-        __syncwarp();
-        if (ins) { table[h] = (u16)p; tags[h] = (u8)tag; }
-        __syncwarp();
-        u32 const nw = act ? table[h] : 0u;
-        u32 const nwtag = act ? tags[h] : 0x100u;
-        u32 hn = 0; bool act_n = false;
-        if (j + 1u < CAND_CHUNK / 32u) {
-            u32 const qn = q + 32u;
-            act_n = INTERIOR ? true : ((qn >= o0 + pmin) && (qn - o0 < nPos));
-            hn = act_n ? (hh[(j + 1u) % (CAND_CHUNK / 32u)] >> 8) : 0u;
-            old_c = act_n ? table[hn] : 0u;
-            oldtag_c = act_n ? tags[hn] : 0x100u;
-        }
-        u32 losers = __ballot_sync(ZB_FULL, ins && nw != (p & 0xFFFFu));
-        u32 d = 0;
-        bool resolved = false;
-        if (losers) {
-            /* rare: some bucket has several inserting lanes.  Peel one hash group per round:
-             * the highest inserting lane owns the bucket, every lane of the group takes the
-             * nearest inserting lane below it as its candidate. */
-            u32 const insmask = __ballot_sync(ZB_FULL, ins);
-            while (losers) {
-                int const L = __ffs((int)losers) - 1;
-                u32 const hl = __shfl_sync(ZB_FULL, h, L);
-                bool const mine = act && h == hl;
-                u32 const grpAll = __ballot_sync(ZB_FULL, mine);
-                u32 const grpIns = grpAll & insmask;
-                u32 const lower = mine ? (grpIns & ((1u << lane) - 1u)) : 0u;
-                u32 const lowLane = lower ? (31u - (u32)__clz((int)lower)) : lane;
-                u32 const lowTag = __shfl_sync(ZB_FULL, tag, (int)lowLane);
-                if (mine) {
-                    if (lower) d = (lowTag == tag) ? lane - lowLane : 0u;
-                    else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
-                    resolved = true;
-                    if ((31u - (u32)__clz((int)grpIns)) == lane) { table[h] = (u16)p; tags[h] = (u8)tag; }
-                }
-                losers &= ~grpAll;
-            }
-            __syncwarp();
-            if (j + 1u < CAND_CHUNK / 32u) {                    /* the peel rewrote buckets: read the next step's again */
-                old_c = act_n ? table[hn] : 0u;
-                oldtag_c = act_n ? tags[hn] : 0x100u;
-            }
-        }
-        if (!resolved) {
-            u32 const dn = (p - nw) & 0xFFFFu;                  /* written by a lane below me in this step? */
-            if (dn >= 1u && dn <= lane) d = (nwtag == tag) ? dn : 0u;
-            else { d = (p - old) & 0xFFFFu; if (d > p || oldtag != tag) d = 0u; }
-        }
-        if (INTERIOR || (act && p >= bs)) mydist[p - bs] = (u16)d;
-        ph += inc; if (ph >= period) ph -= period;
-        act_c = act_n;
-    }
+    return (c != 0u && ((c ^ h) & ((1u << ZB_TAG_BITS) - 1u)) == 0u) ? me - (c >> ZB_TAG_BITS) : 0u;
 }
+__device__ __forceinline__ u32 zb_entry(u32 h, u32 me) { return (me << ZB_TAG_BITS) | (h & ((1u << ZB_TAG_BITS) - 1u)); }
 
 template <int MLS>
-__global__ void __launch_bounds__(32)
-zb_cand_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, u16* __restrict__ dist,
-               const u8* __restrict__ imageIn, u8* __restrict__ imageOut)
+__global__ void __launch_bounds__(ZB_BATCH, 2)
+zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbChunk* __restrict__ chunks, u32 insStep, u32 N, ZbStrides sd,
+               u32 slotFirstBlock, u16* __restrict__ dist, u32* __restrict__ far,
+               const u32* __restrict__ imageIn, u32* __restrict__ imageOut)
 {
-    __shared__ __align__(16) u8 ring[CAND_RING];                  /* input staging */
-    extern __shared__ __align__(16) u16 table[];                  /* 2^hashLog positions, followed by 2^hashLog tags */
-    u32 const lane = threadIdx.x;
-    ZbBlock bd = blocks[blockIdx.x];
-    /* imageOut != NULL: this launch only walks the dictionary tail (positions whose 8 hashed bytes lie inside
-     * the dictionary) and saves the table; imageIn != NULL: dictionary blocks start from that saved table and
-     * walk only the last 7 dictionary positions (their hashes reach into the frame) and the block itself. */
+    extern __shared__ __align__(16) u32 smem[];
+    __shared__ u32 sLastHit[2];                                   /* rel position of the latest candidate hit, per batch parity */
+    u32 const t = threadIdx.x;
+    ZbChunk const cd = chunks[blockIdx.x];
     bool const buildImage = imageOut != nullptr;
-    if (buildImage) bd.size = 0;
-    if (!buildImage && bd.size < 7u) return;                      /* zstd_compress.c:3216 : block goes out raw */
-    u16* const mydist = dist + (size_t)blockIdx.x * sd.dist;
-    const u8* const base = buildImage ? dictEnd - bd.histLen : src + bd.srcOff - bd.histLen;   /* rel position 0 = oldest visible byte */
-    u32 const bs = bd.histLen, be = bd.histLen + bd.size;
-    bool const fromImage = imageIn != nullptr && (bd.flags & ZB_FLAG_DICT) && bd.histLen >= 8u;
-    u32 const pmin = fromImage ? bd.histLen - 7u : 0u;            /* history positions below pmin are already in the image */
-    u32 const hlog = prm.hashLog, period = prm.insPeriod;
-    u8* const tags = reinterpret_cast<u8*>(table + ((size_t)1 << hlog));   /* 8 further hash bits per bucket */
-    volatile u16* const vtable = table;     /* lanes communicate through the table inside a step: volatile accesses */
-    volatile u8*  const vtags = tags;
+    u32 const D = cd.dictLen;                                     /* rel position of the frame's first byte when a dictionary is in front */
+    u32 const H = cd.histLen;                                     /* rel position of the chunk's first byte */
+    u32 const total = buildImage ? D : H + cd.size;               /* positions [0, total) are walked; no read at or past total */
+    bool const fromImage = imageIn != nullptr && D != 0u && !buildImage;
+    /* a frame that is a single batch behind a dictionary image never reads its own insertions from the table:
+     * the image stays in global memory (config 5: a million 1 KiB records) */
+    bool const direct = fromImage && H == D && cd.size <= ZB_BATCH;
+    u32* const table = smem;
+    u32* const hsh   = table + (direct ? 0u : N);                 /* [2][ZB_BATCH] hash of each position of the batch */
+    u32* const heads = hsh + 2u * ZB_BATCH;                       /* [2][WALK_HEADS] chain heads of the batch index */
+    u16* const nxt   = reinterpret_cast<u16*>(heads + 2u * WALK_HEADS);   /* [2][ZB_BATCH] */
 
-    /* input is staged through shared memory in 16-byte aligned units: q = position relative to abase */
-    u32 const o0 = (u32)((uintptr_t)base & 15u);
-    const u8* const abase = base - o0;
-    /* history of a dictionary block lives in the dictionary buffer: 16-byte units that are not entirely
-     * frame bytes are assembled byte-wise (arbitrary mutual alignment), the rest goes through cp.async */
-    bool const dictBlk = dictEnd != nullptr && (bd.flags & ZB_FLAG_DICT);
-    const u8* const dlo = dictBlk ? dictEnd - bd.histLen : base;
-    auto stage = [&](u32 q) {
-        if (!dictBlk || q >= o0 + bd.histLen) { __pipeline_memcpy_async(ring + (q & (CAND_RING - 1u)), abase + q, 16); return; }
-        u32 w[4] = { 0u, 0u, 0u, 0u };
-#pragma unroll
-        for (u32 k = 0; k < 16u; k++) {
-            u32 const rel = q + k - o0;                       /* wraps for q + k < o0 : treated as out of range */
-            u32 const byte = (q + k < o0 || rel >= bd.histLen + bd.size) ? 0u : (u32)(rel < bd.histLen ? dlo[rel] : base[rel]);
-            w[k >> 2] |= byte << (8u * (k & 3u));
-        }
-        *reinterpret_cast<uint4*>(ring + (q & (CAND_RING - 1u))) = make_uint4(w[0], w[1], w[2], w[3]);
-    };
-    u32 const qEnd = o0 + be;                                     /* one past the last byte we may read */
-    u32 const nChunks = (qEnd + CAND_CHUNK - 1u) / CAND_CHUNK;
+    const u8* const fbase = src + cd.srcOff - H;                  /* fbase + rel = the byte's address for rel >= D */
+    const u8* const dbase = dictEnd - D;                          /* same for rel < D */
 
-    {   uint4* t4 = reinterpret_cast<uint4*>(table);
-        u32 const n4 = (3u << hlog) / 16u;
-        const uint4* im = reinterpret_cast<const uint4*>(imageIn);
-        for (u32 i = lane; i < n4; i += 32) t4[i] = fromImage ? __ldg(im + i) : make_uint4(0, 0, 0, 0);
+    if (!direct) {
+        if (fromImage) for (u32 i = t; i < N; i += ZB_BATCH) table[i] = __ldg(imageIn + i);
+        else           for (u32 i = t; i < N; i += ZB_BATCH) table[i] = 0u;
     }
-    u32 const c0 = (o0 + pmin) / CAND_CHUNK;                      /* first chunk with a position to insert */
-    /* prologue: chunks c0 .. c0+STAGES-2 in flight */
-#pragma unroll
-    for (u32 k = 0; k < CAND_STAGES - 1u; k++) {
-        u32 const q = (c0 + k) * CAND_CHUNK + 16u * lane;
-        if (c0 + k < nChunks && q < qEnd) stage(q);
-        __pipeline_commit();
-    }
-    __syncwarp();
+    for (u32 i = t; i < 2u * WALK_HEADS; i += ZB_BATCH) heads[i] = WALK_NONE;
+    if (t < 2u) sLastHit[t] = 0u;
+    __syncthreads();
 
-    u32 const nPos = be - 7u;                                     /* positions with 8 readable bytes inside the block */
-    u32 const phase0 = (period - (o0 % period) + (prm.longPass ? bd.insPhaseLong : bd.insPhase)) % period;   /* pattern phase of q = 0 */
-    u32 ph = (c0 * CAND_CHUNK + lane + phase0) % period;          /* pattern phase of this lane's q in the current step */
-    u32 const inc = 32u % period;
-    /* chunks that lie entirely inside the history only have to leave their inserted positions in the
-     * table (nobody asks for their candidates): they are walked pair-wise, 16 pairs = 16*period
-     * positions per step, without any look-up */
-    u32 const nPrimeChunks = (o0 + bs) / CAND_CHUNK;
-    for (u32 c = c0; c < nChunks; c++) {
-        {   u32 const cn = c + CAND_STAGES - 1u;                  /* refill the slot consumed in the previous iteration */
-            u32 const q = cn * CAND_CHUNK + 16u * lane;
-            if (cn < nChunks && q < qEnd) stage(q);
-            __pipeline_commit();
-        }
-        /* chunk c and (for the 8-byte reads that straddle its end) chunk c+1 must have landed */
-        __pipeline_wait_prior(CAND_STAGES - 2u);
-        __syncwarp();
-        if (c < nPrimeChunks) {
-            /* first pair start at or after the chunk start: q0 with (q0 + phase0) % period == 0 */
-            u32 const cq = c * CAND_CHUNK;
-            u32 const r = (cq + phase0) % period;
-            u32 const first = cq + (r ? period - r : 0u);
-            /* a pair that straddles the chunk start has its second element here: it precedes every
-             * pair of this chunk, so it is written first */
-            if (((cq + phase0) % period) == 1u && lane == 0u && cq >= o0 + pmin && cq - o0 < nPos) {
-                u32 const q = cq, p = q - o0;
-                u32 const w = (q & ~3u) & (CAND_RING - 1u);
-                u32 const sh = (q & 3u) * 8u;
-                u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
-                u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
-                u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
-                u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-                u32 const h24 = zb_hash(v, MLS, hlog + 8u);
-                vtable[h24 >> 8] = (u16)p; vtags[h24 >> 8] = (u8)h24;
-            }
-            __syncwarp();
-            for (u32 g0 = first; g0 < cq + CAND_CHUNK; g0 += 16u * period) {
-                u32 const q = g0 + (lane >> 1) * period + (lane & 1u);
-                bool const act = (q >= o0 + pmin) && (q < cq + CAND_CHUNK) && (q - o0 < nPos);
-                u32 const p = q - o0;
-                u32 const w = (q & ~3u) & (CAND_RING - 1u);
-                u32 const sh = (q & 3u) * 8u;
-                u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
-                u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
-                u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
-                u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-                u32 const h24 = zb_hash(v, MLS, hlog + 8u);
-                u32 const h = h24 >> 8;
-                if (act) vtable[h] = (u16)p;
-                __syncwarp();
-                /* the latest position must own the bucket: lanes that lost to an earlier one write again */
-                while (true) {
-                    u32 const diff = act ? ((p - (u32)vtable[h]) & 0xFFFFu) : 0u;      /* > 0 : an earlier position of this step is stored */
-                    bool const again = diff != 0u && diff <= 16u * period;
-                    if (!__any_sync(ZB_FULL, again)) break;
-                    __syncwarp();
-                    if (again) vtable[h] = (u16)p;
-                    __syncwarp();
+    /* batch borders lie at D + k * ZB_BATCH: frame positions that are multiples of the batch */
+    u32 const phase = (ZB_BATCH - (D % ZB_BATCH)) % ZB_BATCH;
+    auto batchEnd = [&](u32 s0) { u32 const e0 = s0 + ZB_BATCH - ((s0 + phase) % ZB_BATCH); return e0 < total ? e0 : total; };
+    auto active = [&](u32 q) { return (q + 8u <= total) && !(q < D && q + 8u > D); };
+    auto load8 = [&](u32 q) { return zb_ld64u((q < D ? dbase : fbase) + q); };
+    u32 s = fromImage ? D : 0u;
+    u32 e = s < total ? batchEnd(s) : s;
+    u64 w = (s + t < e && active(s + t)) ? load8(s + t) : 0ull;
+    u32 const blockMask = (1u << cd.blockLog) - 1u;
+    for (u32 k = 0; s < total; k++) {
+        u32 const par = k & 1u;
+        u32 const q = s + t;
+        bool const act = (q < e) && active(q);
+        u32 const h = act ? zb_hash(w, MLS, 32u) : 0u;
+        u32 const bkt = __umulhi(h, N);
+        u32 const me = q + 1u;
+        u32 const old = act ? (direct ? __ldg(imageIn + bkt) : table[bkt]) : 0u;
+        u32 const dOld = zb_cand(old, h, me);
+        u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
+        if (D != 0u && s >= D && li < D) li = D;                  /* the frame starts with a fresh acceleration state behind a dictionary */
+        u32 const step = insStep + ((s - li) >> 7);
+        bool const ins = act && dOld == 0u && (q % step) < 2u;
+        u32* const myHeads = heads + par * WALK_HEADS;
+        u16* const myNxt = nxt + par * ZB_BATCH;
+        u32* const myHsh = hsh + par * ZB_BATCH;
+        u32 const slot = bkt & (WALK_HEADS - 1u);
+        myHsh[t] = h;
+        if (ins) myNxt[t] = (u16)atomicExch(&myHeads[slot], t);   /* 0xFFFF = end of chain */
+        {   u32 const hits = __ballot_sync(ZB_FULL, act && dOld != 0u);
+            if (hits && (t & 31u) == 31u - (u32)__clz((int)hits)) atomicMax(&sLastHit[par], q); }
+        /* next batch's bytes: in flight across the barriers */
+        u32 const sn = e, en = sn < total ? batchEnd(sn) : sn;
+        if (sn + t < en && active(sn + t)) w = load8(sn + t);
+        __syncthreads();
+        /* look-ups: the nearest inserted position below me in my bucket, else what the table held before the batch */
+        u32 best = WALK_NONE; bool higher = false;
+        if (act) {
+            u32 j = myHeads[slot];
+            while (j != WALK_NONE && j != 0xFFFFu) {
+                if (__umulhi(myHsh[j], N) == bkt) {
+                    if (j < t) { if (best == WALK_NONE || j > best) best = j; }
+                    else if (j > t) higher = true;
                 }
-                if (act && vtable[h] == (u16)p) vtags[h] = (u8)h24;       /* the bucket's owner sets its tag */
-                __syncwarp();
+                j = myNxt[j];
             }
-            __syncwarp();
-            ph += (CAND_CHUNK % period); if (ph >= period) ph -= period;     /* keep the step phase in sync (CAND_CHUNK/32 steps skipped) */
-            continue;
         }
-        /* phase A: the 16 steps' hashes are independent of the table: compute them back to back */
-        u32 hh[CAND_CHUNK / 32u];
-#pragma unroll
-        for (u32 j = 0; j < CAND_CHUNK / 32u; j++) {
-            u32 const q = c * CAND_CHUNK + 32u * j + lane;
-            u32 const w = (q & ~3u) & (CAND_RING - 1u);
-            u32 const sh = (q & 3u) * 8u;
-            u32 const a0 = *reinterpret_cast<const u32*>(ring + w);
-            u32 const a1 = *reinterpret_cast<const u32*>(ring + ((w + 4u) & (CAND_RING - 1u)));
-            u32 const a2 = *reinterpret_cast<const u32*>(ring + ((w + 8u) & (CAND_RING - 1u)));
-            u64 const v = ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
-            hh[j] = zb_hash(v, MLS, hlog + 8u);                 /* bucket << 8 | tag */
+        u32 const c = (best != WALK_NONE) ? zb_entry(myHsh[best], s + best + 1u) : old;
+        u32 const d = act ? zb_cand(c, h, me) : 0u;
+        if (!buildImage && q < e && q >= H) {
+            u32 const qb = q - H;                                 /* offset in the chunk */
+            size_t const idx = (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask);
+            if (d >= ZB_FAR) { dist[idx] = (u16)ZB_FAR; far[idx] = d; } else dist[idx] = (u16)d;
         }
-        /* phase B: the table walk proper, one step after the other */
-        {   u32 const q0 = c * CAND_CHUNK;
-            bool const interior = (q0 >= o0 + bs) && (q0 + CAND_CHUNK <= o0 + nPos);
-            if (interior) zb_cand_walk16<true>(table, tags, hh, q0, o0, pmin, nPos, bs, lane, ph, inc, period, mydist);
-            else          zb_cand_walk16<false>(table, tags, hh, q0, o0, pmin, nPos, bs, lane, ph, inc, period, mydist);
-        }
+        if (ins && !higher && !direct) table[bkt] = zb_entry(h, me);   /* the highest inserted position of the batch owns the bucket */
+        heads[(par ^ 1u) * WALK_HEADS + t] = WALK_NONE;           /* WALK_HEADS == ZB_BATCH: one slot per thread */
+        if (t == 0u) { u32 const a = sLastHit[par], b = sLastHit[par ^ 1u]; if (b > a) sLastHit[par] = b; }
+        __syncthreads();
+        s = e; e = en;
     }
-    if (buildImage) {                                             /* save the primed table (positions + tags) */
-        __syncwarp();
-        const uint4* t4 = reinterpret_cast<const uint4*>(table);
-        uint4* im = reinterpret_cast<uint4*>(imageOut);
-        for (u32 i = lane; i < (3u << hlog) / 16u; i += 32) im[i] = t4[i];
-        return;
-    }
-    for (u32 p = (nPos > bs ? nPos : bs) + lane; p < be; p += 32) mydist[p - bs] = 0;
+    if (buildImage) for (u32 i = t; i < N; i += ZB_BATCH) imageOut[i] = table[i];
 }
 
 /* ------------------------------------------------------------------------------------------------
- * K1b — greedy selection + match extension + sequence/literal emission.  One warp per block, no
- * shared memory (occupancy is register-bound, so the L2 latency of the candidate checks is hidden
- * by other warps).  Per step 32 probe positions: pairs (p, p+1) spaced by `step` (zstd_fast.c:225-229,
- * step acceleration :234,:342-347).  Hit priority per lane: repcode-2 (lane 0, directly after a match,
- * :410-420), repcode-1 (:281-297), table candidate with 4-byte check (:102-141).  Lowest lane wins.
+ * K1b — greedy selection + match extension.  One warp per 16 KiB segment, no shared memory (occupancy is
+ * register-bound, so the L2 latency of the candidate checks is hidden by other warps).  Per step 32 probe
+ * positions: pairs (p, p+1) spaced by `step` (zstd_fast.c:225-229, step acceleration :234,:342-347).  Hit
+ * priority per lane: repcode-2 (lane 0, directly after a match, :410-420), repcode-1 (:281-297), table candidate
+ * with 4-byte check (:102-141).  Lowest lane wins.  A segment owns the match starts inside it; a match may run
+ * past the segment's end up to the block's end (the merge kernel resolves what that covers).
  * ---------------------------------------------------------------------------------------------- */
 #ifndef PARSE_WARPS
 #define PARSE_WARPS 8            /* = ZB_PARSE_SEGS: the eight segments of a full block share a CTA */
 #endif
 #ifndef PARSE_MIN_CTAS
-#define PARSE_MIN_CTAS 6           /* 48 warps per SM at 40 registers.  8 (= 32 registers, 64 warps) is 3.7 % faster when the parse
-                                    * runs alone, but fills every warp slot: the candidate walk of the next wave no longer fits beside
-                                    * it and a whole device-resident call gets 4 % slower (profiles/r1_history.md) */
+#define PARSE_MIN_CTAS 6         /* 48 warps per SM at 40 registers (profiles/r1_history.md) */
 #endif
+__device__ __forceinline__ u32 zb_dist_at(const u16* __restrict__ d16, const u32* __restrict__ far, u32 i)
+{
+    u32 const d = d16[i];
+    return d == ZB_FAR ? far[i] : d;
+}
+
 template <bool DICT>
 __global__ void __launch_bounds__(32 * PARSE_WARPS, DICT ? (40 / PARSE_WARPS) : PARSE_MIN_CTAS)
 zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
-                const u16* __restrict__ dist, u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
+                const u16* __restrict__ dist, const u32* __restrict__ far, u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment: the warps of a CTA share a block's history in L1/L2 */
@@ -342,10 +216,11 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
     ZbBlock const bd = blocks[b];
     u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
     const u16* const mydist = dist + (size_t)b * sd.dist;
+    const u32* const myfar = far + (size_t)b * sd.dist;
     const u8* const base = src + bd.srcOff - bd.histLen;          /* base + rel addresses the frame's own bytes */
     u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
     ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
-    if (DICT && (bd.flags & ZB_FLAG_DICT)) { sg.lo = dictEnd - bd.histLen; sg.split = bd.histLen; }   /* history = dictionary tail */
+    if (DICT && (bd.flags & ZB_FLAG_DICT)) { sg.lo = dictEnd - bd.dictLen; sg.split = bd.dictLen; }   /* oldest history = dictionary tail */
 
     if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
         if (lane == 0 && k == 0) {
@@ -355,33 +230,34 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         }
         return;
     }
-    u32 const ss = bs + k * ZB_PARSE_SEG;                      /* this warp's segment [ss, be) */
+    u32 const ss = bs + k * ZB_PARSE_SEG;                      /* this warp owns the match starts in [ss, se) */
     if (ss >= blockEnd) {
-        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.litSize = 0; z.trail = 0; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0; segmeta[(size_t)b * segs + k] = z; }
         return;
     }
-    u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
+    u32 const se = min(ss + ZB_PARSE_SEG, blockEnd);
+    u32 const be = blockEnd;
 
     u32 ip = ss, anchor = ss, searchStart = ss;
     u32 rep1 = 0, rep2 = 0, nbSeq = 0;
-    if (DICT && (bd.flags & ZB_FLAG_DICT) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
+    if ((bd.flags & ZB_FLAG_FIRST) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }   /* a zstd-format dictionary's repcodes, zstd_compress.c:5054-5056 */
 
-    while (ip + 8u <= be) {
+    while (ip < se && ip + 8u <= be) {
         u32 const step = prm.stepSize + ((ip - searchStart) >> 7);           /* kSearchStrength = 8 */
         u32 const p = ip + (lane >> 1) * step + (lane & 1u);
-        bool const act = (p + 8u <= be);
+        bool const act = (p < se) && (p + 8u <= be);
         u32 const pp = act ? p : ip;                         /* a position every lane may load from (ip + 8 <= be) */
-        u32 const d = act ? (u32)mydist[pp - bs] : 0u;
+        u32 const d = act ? zb_dist_at(mydist, myfar, pp - bs) : 0u;
         bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
         bool const v2 = act && rep1 != 0u && p >= rep1;
-        bool const v1 = act && d != 0u;
-        /* dist[] only holds candidates K1a has already verified (4 equal bytes), so a step needs no random
-         * load: the current window and the repcode windows are contiguous across lanes */
+        bool const v1 = act && d != 0u && p >= d;
+        /* dist[] only holds tag-verified candidates, so a step needs no random load: the current window and the
+         * repcode windows are contiguous across lanes */
         u32 pre, cur, pre2, cur2;
         zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
         zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
         u32 cur3 = ~cur;
-        if (ip == anchor && rep2 != 0u) cur3 = zb_seg_ld32<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
+        if (ip == anchor && rep2 != 0u) cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
         u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
         u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
@@ -422,83 +298,239 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         if (!found) { ip += 16u * step; continue; }
         u32 const ms = probe - back;
         u32 const mlen = back + 4u + fwdFrom4;
-        u32 const litLen = ms - anchor;
-        u32 offBase;
-        if (wtype == 3u) { offBase = 1u; u32 const t = rep2; rep2 = rep1; rep1 = t; }   /* litLength 0: code 1 = repcode 2 */
-        else if (wtype == 2u && litLen > 0u) offBase = 1u;                                 /* REPCODE1_TO_OFFBASE */
-        else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
-        if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
-        nbSeq++;                                               /* the literal bytes are gathered by the merge kernel */
+        if (wtype == 3u) { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (wtype == 1u) { rep2 = rep1; rep1 = offset; }
+        if (lane == 0) myseq[nbSeq] = zb_pack_raw(offset, mlen, ms - bs);
+        nbSeq++;
         ip = ms + mlen; anchor = ip; searchStart = ip;
     }
-
-    /* trailing literals (zstd_compress.c:3365-3366): the block's last literals, or the head of the next segment's first sequence */
-    u32 const lastLits = be - anchor;
-    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = 0; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.pad[0] = z.pad[1] = z.pad[2] = 0; segmeta[(size_t)b * segs + k] = z; }
 }
 
-/* K1c — joins a block's segments and materialises its literals.
- * 1. sequences move down to be contiguous (in place, ascending, every chunk read completely before it is written: the
- *    destination never lies above the source); the first sequence of a segment takes over the literals the segments
- *    before it left behind their last match;
- * 2. a scan over (litLength, litLength + matchLength) gives every sequence the block position its literals start at
- *    and their offset in the literal buffer; warps copy them straight from the input (the parse kernels emit no
- *    literal bytes at all), then the block's last literals;
- * 3. the block's meta record is written. */
+/* ------------------------------------------------------------------------------------------------
+ * K1b (doubleFast) — the greedy selection of ZSTD_compressBlock_doubleFast_noDict_generic
+ * (zstd_double_fast.c:105-323) over two candidate arrays: distL (8-byte hash) and distS (mls-byte hash).
+ * Per probe position p, in the reference's order: repcode-1 at p+1 (:190-195), long match at p
+ * (:206-213), short match at p (:222-225) upgraded to the long match at p+1 when longer (:254-271);
+ * probes are spaced by `step` (1, +1 per 256 bytes without a match, :131); lowest lane wins; immediate
+ * repcode-2 at lane 0 right after a match (:302-316).  Table candidates are tag-verified only: the
+ * winning lane's bytes are checked while the match is extended, a false positive drops out.
+ * ---------------------------------------------------------------------------------------------- */
+template <bool DICT>
+__global__ void __launch_bounds__(32 * PARSE_WARPS)
+zb_parse_dfast_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
+                      const u16* __restrict__ distLong, const u32* __restrict__ farLong, const u16* __restrict__ distShort, const u32* __restrict__ farShort,
+                      u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment, as in zb_parse_kernel */
+    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    u32 const b = g / segs, k = g % segs;
+    if (b >= nbBlocks) return;
+    ZbBlock const bd = blocks[b];
+    u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
+    const u16* const dLp = distLong + (size_t)b * sd.dist;
+    const u32* const fLp = farLong + (size_t)b * sd.dist;
+    const u16* const dSp = distShort + (size_t)b * sd.dist;
+    const u32* const fSp = farShort + (size_t)b * sd.dist;
+    const u8* const base = src + bd.srcOff - bd.histLen;
+    u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
+    ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
+    if (DICT && (bd.flags & ZB_FLAG_DICT)) { sg.lo = dictEnd - bd.dictLen; sg.split = bd.dictLen; }
+
+    if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
+        if (lane == 0 && k == 0) {
+            ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
+            m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
+            meta[b] = m;
+        }
+        return;
+    }
+    u32 const ss = bs + k * ZB_PARSE_SEG;
+    if (ss >= blockEnd) {
+        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0; segmeta[(size_t)b * segs + k] = z; }
+        return;
+    }
+    u32 const se = min(ss + ZB_PARSE_SEG, blockEnd);
+    u32 const be = blockEnd;
+    u32 ip = ss, anchor = ss, searchStart = ss;
+    u32 rep1 = 0, rep2 = 0, nbSeq = 0;
+    if ((bd.flags & ZB_FLAG_FIRST) && k == 0u) { rep1 = prm.startRep[0]; rep2 = prm.startRep[1]; }
+
+    while (ip < se && ip + 9u <= be) {                        /* a lane reads 8 bytes at p and at p+1 */
+        u32 const step = 1u + ((ip - searchStart) >> 8);                     /* kStepIncr = 1 << kSearchStrength */
+        u32 const p = ip + lane * step;
+        bool const act = (p < se) && (p + 9u <= be);
+        u32 const pp = act ? p : ip;
+        u32 dL = act ? zb_dist_at(dLp, fLp, pp - bs) : 0u;
+        u32 dS = act ? zb_dist_at(dSp, fSp, pp - bs) : 0u;
+        u32 dL1 = act ? zb_dist_at(dLp, fLp, pp + 1u - bs) : 0u;
+        if (dL > pp) dL = 0u;                                  /* reaches past the visible history (window) */
+        if (dS > pp) dS = 0u;
+        if (dL1 > pp + 1u) dL1 = 0u;
+        u64 const w = zb_seg_ld64x<DICT>(sg, pp);                            /* bytes p .. p+7 */
+        u32 const cur = (u32)w, cur1 = (u32)(w >> 8);
+        bool const v2 = act && rep1 != 0u && (p + 1u >= rep1);
+        u32 const r2 = (u32)zb_seg_ld64x<DICT>(sg, v2 ? pp + 1u - rep1 : pp);
+        u32 r3 = ~cur;
+        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
+        if (ip == anchor && rep2 != 0u) r3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);
+        /* 3 repcode-2, 2 repcode-1 (at p+1), 1 long candidate, 4 short candidate */
+        u32 hit = (v3 && r3 == cur) ? 3u : ((v2 && r2 == cur1) ? 2u : (dL ? 1u : (dS ? 4u : 0u)));
+        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
+        u32 ms = 0, offset = 0, mlen = 0, wtype = 0;
+        bool found = false;
+        while (tent) {
+            int const winner = __ffs((int)tent) - 1;
+            u32 const probe = __shfl_sync(ZB_FULL, p, winner);
+            wtype = __shfl_sync(ZB_FULL, hit, winner);
+            u32 const wL = __shfl_sync(ZB_FULL, dL, winner), wS = __shfl_sync(ZB_FULL, dS, winner), wL1 = __shfl_sync(ZB_FULL, dL1, winner);
+            if (wtype == 3u) { ms = probe; offset = rep2; mlen = 4u + zb_count_fwd<DICT>(sg, probe + 4u, rep2, be, lane); found = true; break; }
+            if (wtype == 2u) { ms = probe + 1u; offset = rep1; mlen = 4u + zb_count_fwd<DICT>(sg, probe + 5u, rep1, be, lane); found = true; break; }
+            if (wtype == 1u) {
+                u32 const f0 = zb_count_fwd<DICT>(sg, probe, wL, be, lane);
+                if (f0 >= 8u) {
+                    u32 const back = zb_back_coop<DICT>(sg, probe, wL, anchor, lane);
+                    ms = probe - back; offset = wL; mlen = back + f0; found = true; break;
+                }
+                /* tag collision on the long table: the lane may still have a short candidate */
+                if (lane == (u32)winner) hit = dS ? 4u : 0u;
+                if (wS == 0u) { tent &= ~(1u << winner); }
+                continue;
+            }
+            /* short candidate */
+            {   u32 const f0 = zb_count_fwd<DICT>(sg, probe, wS, be, lane);
+                if (f0 < 4u) { tent &= ~(1u << winner); if (lane == (u32)winner) hit = 0u; continue; }
+                u32 mp = probe, mo = wS, ml = f0;
+                if (wL1) {
+                    u32 const f1 = zb_count_fwd<DICT>(sg, probe + 1u, wL1, be, lane);
+                    if (f1 >= 8u && f1 > ml) { mp = probe + 1u; mo = wL1; ml = f1; }
+                }
+                u32 const back = zb_back_coop<DICT>(sg, mp, mo, anchor, lane);
+                ms = mp - back; offset = mo; mlen = back + ml; wtype = 1u; found = true; break;
+            }
+        }
+        if (!found) { ip += 32u * step; continue; }
+        if (wtype == 3u) { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (wtype == 1u) { rep2 = rep1; rep1 = offset; }
+        if (lane == 0) myseq[nbSeq] = zb_pack_raw(offset, mlen, ms - bs);
+        nbSeq++;
+        ip = ms + mlen; anchor = ip; searchStart = ip;
+    }
+    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.pad[0] = z.pad[1] = z.pad[2] = 0; segmeta[(size_t)b * segs + k] = z; }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1c — joins a block's segments, assigns repcodes, materialises the literals.
+ * `cur` = first byte of the block not yet covered by a sequence.  A raw sequence that ends at or before `cur` lies
+ * under a match that ran over from an earlier segment and is dropped; one that straddles `cur` keeps its tail when
+ * that is at least 3 bytes (MINMATCH, zstd_internal.h:102); the others take their literals from `cur`.
+ * The repcode history (ZSTD_storeSeq / ZSTD_updateRep, zstd_compress_internal.h:671-760) then runs over the whole
+ * block: it starts as {1,4,8} (or the dictionary's) in a frame's first block and unknown in every other block.
+ * ---------------------------------------------------------------------------------------------- */
+struct ZbRepHist { u32 r1, r2, r3; };
+__device__ __forceinline__ u32 zb_rep_code(ZbRepHist& h, u32 off, u32 ll)
+{
+    u32 code;
+    if (ll > 0u) {
+        if (off == h.r1) return 1u;
+        if (off == h.r2) { code = 2u; h.r2 = h.r1; h.r1 = off; return code; }
+        if (off == h.r3) { code = 3u; h.r3 = h.r2; h.r2 = h.r1; h.r1 = off; return code; }
+    } else {
+        if (off == h.r2) { code = 1u; h.r2 = h.r1; h.r1 = off; return code; }
+        if (off == h.r3) { code = 2u; h.r3 = h.r2; h.r2 = h.r1; h.r1 = off; return code; }
+        if (h.r1 > 1u && off == h.r1 - 1u) { code = 3u; h.r3 = h.r2; h.r2 = h.r1; h.r1 = off; return code; }
+    }
+    h.r3 = h.r2; h.r2 = h.r1; h.r1 = off;
+    return off + 3u;
+}
+
 #define MERGE_THREADS 256
-#ifndef MERGE_TILE
 #define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
-#endif
 #define MERGE_PER (MERGE_TILE / MERGE_THREADS)  /* consecutive sequences of a tile owned by one thread */
+#define SEG_SLOTS (ZB_PARSE_SEG / 4u)
 __global__ void __launch_bounds__(MERGE_THREADS)
-zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
+zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
                          u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
-    __shared__ u32 sPos[MERGE_TILE], sLit[MERGE_TILE], sLen[MERGE_TILE];
+    __shared__ u32 sPos[MERGE_TILE], sLit[MERGE_TILE], sLen[MERGE_TILE], sOff[MERGE_TILE];
     __shared__ u32 wsumL[MERGE_THREADS / 32], wsumA[MERGE_THREADS / 32];
-    __shared__ u32 baseL, baseA;
+    __shared__ u32 baseL, baseA, carryEnd;
+    __shared__ u32 gFirst[ZB_PARSE_SEGS], gCnt[ZB_PARSE_SEGS], gBase[ZB_PARSE_SEGS], gCur[ZB_PARSE_SEGS], gPm[ZB_PARSE_SEGS], gPl[ZB_PARSE_SEGS];
+    __shared__ u32 gTotal;
     u32 const b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     ZbBlock const bd = blocks[b];
     if (bd.size < 7u) return;                                    /* raw block: meta written by the parse kernel */
     u64* const myseq = seqs + (size_t)b * sd.seq;
     u8*  const mylit = lits + (size_t)b * sd.lit;
     const u8* const in = src + bd.srcOff;                        /* literals always lie inside the block itself */
-    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
-    ZbSegMeta sm[ZB_PARSE_SEGS];
-#pragma unroll
-    for (u32 k = 0; k < ZB_PARSE_SEGS; k++) if (k < segs) sm[k] = segmeta[(size_t)b * segs + k];
-    /* ---- 1. sequences ---- */
-    u32 seqOff = sm[0].nbSeq;
-    u32 carry = sm[0].trail;                                     /* literals waiting for the next sequence */
+    u32 const segs = (bd.size + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    u32 const segStride = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    /* ---- 1. which raw sequences survive (warp 0; positions are relative to the block) ---- */
+    if (warp == 0u) {
+        u32 nb = 0; u64 r0 = 0, rl = 0;
+        if (lane < segs) {
+            nb = segmeta[(size_t)b * segStride + lane].nbSeq;
+            if (nb) { r0 = myseq[(size_t)lane * SEG_SLOTS]; rl = myseq[(size_t)lane * SEG_SLOTS + nb - 1u]; }
+        }
+        u32 cur = 0, total = 0;
+        for (u32 k = 0; k < segs; k++) {
+            u32 const n = __shfl_sync(ZB_FULL, nb, (int)k);
+            u64 r = __shfl_sync(ZB_FULL, r0, (int)k);
+            u64 const last = __shfl_sync(ZB_FULL, rl, (int)k);
+            u32 f = 0, pm = 0, pl = 0;
+            while (f < n) {
+                u32 const ms = ZB_RAW_MS(r), ml = ZB_RAW_MLEN(r);
+                if (ms + ml <= cur || (ms < cur && ms + ml - cur < 3u)) { f++; if (f < n) r = myseq[(size_t)k * SEG_SLOTS + f]; continue; }
+                if (ms < cur) { pm = cur; pl = ms + ml - cur; } else { pm = ms; pl = ml; }
+                break;
+            }
+            if (lane == 0u) { gFirst[k] = f; gCnt[k] = n - f; gBase[k] = total; gCur[k] = cur; gPm[k] = pm; gPl[k] = pl; }
+            if (f < n) { cur = (f == n - 1u) ? pm + pl : ZB_RAW_MS(last) + ZB_RAW_MLEN(last); total += n - f; }
+        }
+        if (lane == 0u) gTotal = total;
+    }
+    __syncthreads();
+    /* ---- 2. survivors move down to be contiguous (in place: a destination never lies above its source) and become
+     *         (offset, litLength, matchLength) ---- */
 #pragma unroll 1
-    for (u32 k = 1; k < segs; k++) {
-        u32 const ns = sm[k].nbSeq;
-        u64* const sfrom = myseq + (size_t)k * (ZB_PARSE_SEG / 4u);
-        for (u32 c0 = 0; c0 < ns; c0 += MERGE_THREADS) {
+    for (u32 k = 0; k < segs; k++) {
+        u32 const f = gFirst[k], cnt = gCnt[k];
+        const u64* const sfrom = myseq + (size_t)k * SEG_SLOTS + f;
+        u64* const sto = myseq + gBase[k];
+        for (u32 c0 = 0; c0 < cnt; c0 += MERGE_THREADS) {
             u32 const i = c0 + tid;
-            u64 v = 0;
-            if (i < ns) { v = sfrom[i]; if (i == 0u) v += (u64)carry << 24; }        /* litLength field, zb_pack_seq */
+            u64 r = 0; u32 ms = 0, ml = 0;
+            if (i < cnt) { r = sfrom[i]; ms = ZB_RAW_MS(r); ml = ZB_RAW_MLEN(r); if (i == 0u) { ms = gPm[k]; ml = gPl[k]; } }
+            u32 const myEnd = ms + ml;
+            u32 prevEnd = __shfl_up_sync(ZB_FULL, myEnd, 1);
+            if (lane == 31u) wsumL[warp] = myEnd;
             __syncthreads();
-            if (i < ns) myseq[seqOff + i] = v;
+            if (lane == 0u) prevEnd = warp ? wsumL[warp - 1u] : (c0 ? carryEnd : gCur[k]);
+            __syncthreads();
+            if (i < cnt) sto[i] = zb_pack_seq(ZB_RAW_OFF(r), ms - prevEnd, ml);
+            if (tid == MERGE_THREADS - 1u) carryEnd = myEnd;
             __syncthreads();
         }
-        carry = ns ? sm[k].trail : carry + sm[k].trail;
-        seqOff += ns;
     }
-    u32 const nbSeq = seqOff;
+    u32 const nbSeq = gTotal;
     if (tid == 0) { baseL = 0; baseA = 0; }
+    ZbRepHist hist; hist.r1 = 0; hist.r2 = 0; hist.r3 = 0;
+    if (bd.flags & ZB_FLAG_FIRST) { hist.r1 = prm.codeRep[0]; hist.r2 = prm.codeRep[1]; hist.r3 = prm.codeRep[2]; }
     __syncthreads();
-    /* ---- 2. literals ---- */
+    /* ---- 3. literals + repcodes, a tile of sequences at a time ---- */
     for (u32 t0 = 0; t0 < nbSeq; t0 += MERGE_TILE) {
         u32 const n = min(MERGE_TILE, nbSeq - t0);
         /* every thread owns MERGE_PER consecutive sequences of the tile */
-        u32 ll[MERGE_PER], adv[MERGE_PER], myL = 0, myA = 0;
+        u32 ll[MERGE_PER], adv[MERGE_PER], ml[MERGE_PER], myL = 0, myA = 0;
 #pragma unroll
         for (u32 j = 0; j < MERGE_PER; j++) {
             u32 const i = tid * MERGE_PER + j;
             u64 const q = (i < n) ? myseq[t0 + i] : 0ull;
             ll[j] = (u32)((q >> 24) & 0x3FFFFu);
-            adv[j] = ll[j] + (u32)(q >> 42);
+            ml[j] = (u32)(q >> 42);
+            adv[j] = ll[j] + ml[j];
+            if (i < n) sOff[i] = (u32)q & 0xFFFFFFu;
             myL += ll[j]; myA += adv[j];
         }
         u32 inL = myL, inA = myA;                                /* inclusive scan over the warp, then over the warps */
@@ -519,18 +551,29 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
         }
         __syncthreads();
         if (tid == MERGE_THREADS - 1u) { baseL = offL; baseA = offA; }     /* totals up to the end of this tile */
-        for (u32 i = warp; i < n; i += MERGE_THREADS / 32u) {
-            u32 const len = sLen[i];
-            const u8* const from = in + sPos[i];
-            u8* const to = mylit + sLit[i];
-            for (u32 x = lane; x < len; x += 32u) to[x] = from[x];
+        if (warp == 0u) {
+            /* the repcode history is a serial recurrence: lane 0 walks the tile while the other warps move literals */
+            if (lane == 0u) for (u32 i = 0; i < n; i++) sOff[i] = zb_rep_code(hist, sOff[i], sLen[i]);
+        } else {
+            for (u32 i = warp - 1u; i < n; i += MERGE_THREADS / 32u - 1u) {
+                u32 const len = sLen[i];
+                const u8* const from = in + sPos[i];
+                u8* const to = mylit + sLit[i];
+                for (u32 x = lane; x < len; x += 32u) to[x] = from[x];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < MERGE_PER; j++) {
+            u32 const i = tid * MERGE_PER + j;
+            if (i < n) myseq[t0 + i] = zb_pack_seq(sOff[i], ll[j], ml[j]);
         }
         __syncthreads();
     }
     u32 const litSeq = baseL, consumed = baseA;                   /* literals in sequences, bytes covered by sequences */
     u32 const lastLits = bd.size - consumed;
     for (u32 x = tid; x < lastLits; x += MERGE_THREADS) mylit[litSeq + x] = in[consumed + x];
-    /* ---- 3. meta ---- */
+    /* ---- 4. meta ---- */
     if (tid == 0) {
         ZbBlockMeta m; m.nbSeq = nbSeq; m.litSize = litSeq + lastLits; m.litSecSize = 0; m.bodySize = 0;
         m.type = ZB_BT_COMPRESSED; m.forceRaw = 0; m.rleByte = 0; m.pad = 0;
@@ -538,36 +581,53 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
     }
 }
 
-/* K1c for calls made of short frames (one segment per block, so the sequences are already in place): one warp per
- * block, 8 blocks per CTA; every lane gathers the literals of its own sequences. */
+/* K1c for calls made of short frames (one segment per block: nothing to join): one warp per block, 8 blocks per CTA;
+ * every lane converts and gathers the literals of its own sequences, the repcode history runs through the warp. */
 __global__ void __launch_bounds__(MERGE_THREADS)
-zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
-                      const u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
+zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
+                      u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const b = blockIdx.x * (MERGE_THREADS / 32u) + (threadIdx.x >> 5);
     if (b >= nbBlocks) return;
     ZbBlock const bd = blocks[b];
     if (bd.size < 7u) return;
-    const u64* const myseq = seqs + (size_t)b * sd.seq;
+    u64* const myseq = seqs + (size_t)b * sd.seq;
     u8* const mylit = lits + (size_t)b * sd.lit;
     const u8* const in = src + bd.srcOff;
     u32 const nbSeq = segmeta[b].nbSeq;
+    ZbRepHist hist; hist.r1 = 0; hist.r2 = 0; hist.r3 = 0;
+    if (bd.flags & ZB_FLAG_FIRST) { hist.r1 = prm.codeRep[0]; hist.r2 = prm.codeRep[1]; hist.r3 = prm.codeRep[2]; }
     u32 posL = 0, posA = 0;
     for (u32 t0 = 0; t0 < nbSeq; t0 += 32u) {
         u32 const i = t0 + lane;
-        u64 const q = (i < nbSeq) ? myseq[i] : 0ull;
-        u32 const ll = (u32)((q >> 24) & 0x3FFFFu), adv = ll + (u32)(q >> 42);
-        u32 inL = ll, inA = adv;
+        u64 const r = (i < nbSeq) ? myseq[i] : 0ull;
+        u32 const ms = ZB_RAW_MS(r), ml = ZB_RAW_MLEN(r), off = ZB_RAW_OFF(r);
+        u32 const myEnd = (i < nbSeq) ? ms + ml : 0u;
+        u32 prevEnd = __shfl_up_sync(ZB_FULL, myEnd, 1);
+        if (lane == 0u) prevEnd = posA;
+        u32 const ll = (i < nbSeq) ? ms - prevEnd : 0u;
+        u32 const adv = ll + ((i < nbSeq) ? ml : 0u);
+        u32 inL = ll;
 #pragma unroll
-        for (u32 o = 1; o < 32u; o <<= 1) {
-            u32 const x = __shfl_up_sync(ZB_FULL, inL, o), y = __shfl_up_sync(ZB_FULL, inA, o);
-            if (lane >= o) { inL += x; inA += y; }
+        for (u32 o = 1; o < 32u; o <<= 1) { u32 const x = __shfl_up_sync(ZB_FULL, inL, o); if (lane >= o) inL += x; }
+        /* repcodes: the history is uniform across the warp, lane j keeps sequence j's code */
+        u32 code = 0;
+        u32 const cnt = min(32u, nbSeq - t0);
+        for (u32 j = 0; j < cnt; j++) {
+            u32 const o = __shfl_sync(ZB_FULL, off, (int)j), l = __shfl_sync(ZB_FULL, ll, (int)j);
+            u32 const c = zb_rep_code(hist, o, l);
+            if (lane == j) code = c;
         }
-        const u8* const from = in + posA + inA - adv;
-        u8* const to = mylit + posL + inL - ll;
-        for (u32 x = 0; x < ll; x++) to[x] = from[x];
-        posL += __shfl_sync(ZB_FULL, inL, 31); posA += __shfl_sync(ZB_FULL, inA, 31);
+        if (i < nbSeq) {
+            const u8* const from = in + prevEnd;
+            u8* const to = mylit + posL + inL - ll;
+            for (u32 x = 0; x < ll; x++) to[x] = from[x];
+            myseq[i] = zb_pack_seq(code, ll, ml);
+        }
+        posL += __shfl_sync(ZB_FULL, inL, 31);
+        posA = __shfl_sync(ZB_FULL, myEnd, (int)(cnt - 1u));
+        (void)adv;
     }
     u32 const lastLits = bd.size - posA;
     for (u32 x = lane; x < lastLits; x += 32u) mylit[posL + x] = in[posA + x];
@@ -578,175 +638,61 @@ zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
     }
 }
 
-/* ------------------------------------------------------------------------------------------------
- * K1b (doubleFast) — the greedy selection of ZSTD_compressBlock_doubleFast_noDict_generic
- * (zstd_double_fast.c:105-323) over two candidate arrays: distL (8-byte hash) and distS (mls-byte hash).
- * Per probe position p, in the reference's order: repcode-1 at p+1 (:190-195), long match at p
- * (:206-213), short match at p (:222-225) upgraded to the long match at p+1 when longer (:254-271);
- * probes are spaced by `step` (1, +1 per 256 bytes without a match, :131); lowest lane wins; immediate
- * repcode-2 at lane 0 right after a match (:302-316).  Table candidates are tag-verified only: the
- * winning lane's bytes are checked while the match is extended, a false positive drops out.
- * ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(32 * PARSE_WARPS)
-zb_parse_dfast_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, u32 nbBlocks, ZbParams prm, ZbStrides sd,
-                      const u16* __restrict__ distLong, const u16* __restrict__ distShort,
-                      u64* __restrict__ seqs, ZbBlockMeta* __restrict__ meta, ZbSegMeta* __restrict__ segmeta)
+/* ------------------------------------------------------------------------------------------------ launchers */
+static cudaError_t zb_launch_walk(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 mls, u32 N, u32 insStep, const ZbStrides& sd,
+                                  u32 slotFirstBlock, u16* d_dist, u32* d_far, const u32* d_imageIn, u32* d_imageOut, cudaStream_t stream)
 {
-    u32 const lane = threadIdx.x & 31u;
-    u32 const g = blockIdx.x * PARSE_WARPS + (threadIdx.x >> 5);  /* one warp per segment, as in zb_parse_kernel */
-    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
-    u32 const b = g / segs, k = g % segs;
-    if (b >= nbBlocks) return;
-    ZbBlock const bd = blocks[b];
-    u64* const myseq = seqs + (size_t)b * sd.seq + (size_t)k * (ZB_PARSE_SEG / 4u);
-    const u16* const dLp = distLong + (size_t)b * sd.dist;
-    const u16* const dSp = distShort + (size_t)b * sd.dist;
-    const u8* const base = src + bd.srcOff - bd.histLen;
-    u32 const bs = bd.histLen, blockEnd = bd.histLen + bd.size;
-    ZbSeg sg; sg.hi = base; sg.lo = base; sg.split = 0;
-
-    if (bd.size < 7u) {                                        /* zstd_compress.c:3216 */
-        if (lane == 0 && k == 0) {
-            ZbBlockMeta m; m.nbSeq = 0; m.litSize = bd.size; m.litSecSize = 0; m.bodySize = bd.size;
-            m.type = ZB_BT_RAW; m.forceRaw = 1; m.rleByte = 0; m.pad = 0;
-            meta[b] = m;
-        }
-        return;
+    size_t const smem = (size_t)N * 4u + WALK_AUX_BYTES;
+    cudaError_t e = cudaSuccess;
+#define WALK_CASE(M) case M: \
+        e = cudaFuncSetAttribute(zb_walk_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e; \
+        zb_walk_kernel<M><<<nbChunks, ZB_BATCH, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
+    switch (mls) {
+    WALK_CASE(4) WALK_CASE(5) WALK_CASE(6) WALK_CASE(7)
+    default: e = cudaFuncSetAttribute(zb_walk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e;
+        zb_walk_kernel<8><<<nbChunks, ZB_BATCH, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
     }
-    u32 const ss = bs + k * ZB_PARSE_SEG;                      /* this warp's segment [ss, be) */
-    if (ss >= blockEnd) {
-        if (lane == 0) { ZbSegMeta z; z.nbSeq = 0; z.litSize = 0; z.trail = 0; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
-        return;
-    }
-    u32 const be = min(ss + ZB_PARSE_SEG, blockEnd);
-    u32 ip = ss, anchor = ss, searchStart = ss;
-    u32 rep1 = 0, rep2 = 0, nbSeq = 0;
-
-    while (ip + 9u <= be) {                                   /* a lane reads 8 bytes at p and at p+1 */
-        u32 const step = 1u + ((ip - searchStart) >> 8);                     /* kStepIncr = 1 << kSearchStrength */
-        u32 const p = ip + lane * step;
-        bool const act = (p + 9u <= be);
-        u32 const pp = act ? p : ip;
-        u32 const dL = act ? (u32)dLp[pp - bs] : 0u;
-        u32 const dS = act ? (u32)dSp[pp - bs] : 0u;
-        u32 const dL1 = act ? (u32)dLp[pp + 1u - bs] : 0u;
-        u64 const w = zb_ld64w3(base + pp);                                  /* bytes p .. p+7 */
-        u32 const cur = (u32)w, cur1 = (u32)(w >> 8);
-        bool const v2 = act && rep1 != 0u && (p + 1u >= rep1);
-        u32 const r2 = zb_ld32w2(base + (v2 ? pp + 1u - rep1 : pp));
-        u32 r3 = ~cur;
-        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
-        if (ip == anchor && rep2 != 0u) r3 = zb_ld32w2(base + (v3 ? pp - rep2 : pp));
-        /* 3 repcode-2, 2 repcode-1 (at p+1), 1 long candidate, 4 short candidate */
-        u32 hit = (v3 && r3 == cur) ? 3u : ((v2 && r2 == cur1) ? 2u : (dL ? 1u : (dS ? 4u : 0u)));
-        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
-        u32 ms = 0, offset = 0, mlen = 0, wtype = 0;
-        bool found = false;
-        while (tent) {
-            int const winner = __ffs((int)tent) - 1;
-            u32 const probe = __shfl_sync(ZB_FULL, p, winner);
-            wtype = __shfl_sync(ZB_FULL, hit, winner);
-            u32 const wL = __shfl_sync(ZB_FULL, dL, winner), wS = __shfl_sync(ZB_FULL, dS, winner), wL1 = __shfl_sync(ZB_FULL, dL1, winner);
-            if (wtype == 3u) { ms = probe; offset = rep2; mlen = 4u + zb_count_fwd<false>(sg, probe + 4u, rep2, be, lane); found = true; break; }
-            if (wtype == 2u) { ms = probe + 1u; offset = rep1; mlen = 4u + zb_count_fwd<false>(sg, probe + 5u, rep1, be, lane); found = true; break; }
-            if (wtype == 1u) {
-                u32 const f0 = zb_count_fwd<false>(sg, probe, wL, be, lane);
-                if (f0 >= 8u) {
-                    u32 const back = zb_back_coop<false>(sg, probe, wL, anchor, lane);
-                    ms = probe - back; offset = wL; mlen = back + f0; found = true; break;
-                }
-                /* tag collision on the long table: the lane may still have a short candidate */
-                if (lane == (u32)winner) hit = dS ? 4u : 0u;
-                if (wS == 0u) { tent &= ~(1u << winner); }
-                continue;
-            }
-            /* short candidate */
-            {   u32 const f0 = zb_count_fwd<false>(sg, probe, wS, be, lane);
-                if (f0 < 4u) { tent &= ~(1u << winner); if (lane == (u32)winner) hit = 0u; continue; }
-                u32 mp = probe, mo = wS, ml = f0;
-                if (wL1) {
-                    u32 const f1 = zb_count_fwd<false>(sg, probe + 1u, wL1, be, lane);
-                    if (f1 >= 8u && f1 > ml) { mp = probe + 1u; mo = wL1; ml = f1; }
-                }
-                u32 const back = zb_back_coop<false>(sg, mp, mo, anchor, lane);
-                ms = mp - back; offset = mo; mlen = back + ml; wtype = 1u; found = true; break;
-            }
-        }
-        if (!found) { ip += 32u * step; continue; }
-        u32 const litLen = ms - anchor;
-        u32 offBase;
-        if (wtype == 3u) { offBase = 1u; u32 const t = rep2; rep2 = rep1; rep1 = t; }
-        else if (wtype == 2u && litLen > 0u) offBase = 1u;
-        else { offBase = offset + 3u; rep2 = rep1; rep1 = offset; }
-        if (lane == 0) myseq[nbSeq] = zb_pack_seq(offBase, litLen, mlen);
-        nbSeq++;                                               /* the literal bytes are gathered by the merge kernel */
-        ip = ms + mlen; anchor = ip; searchStart = ip;
-    }
-    u32 const lastLits = be - anchor;
-    if (lane == 0) { ZbSegMeta z; z.nbSeq = nbSeq; z.litSize = 0; z.trail = lastLits; z.pad = 0; segmeta[(size_t)b * segs + k] = z; }
-}
-
-static void zb_launch_cand(const u8* d_src, const u8* d_dictEnd, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams& prm, const ZbStrides& sd, u16* d_dist,
-                           const u8* d_imageIn, u8* d_imageOut, cudaStream_t stream)
-{
-    size_t const smem = (size_t)3 << prm.hashLog;       /* u16 positions + u8 tags */
-    static bool optinDev[64];                                     /* the attribute is per device */
-    int dev = 0; cudaGetDevice(&dev);
-    bool& optin = optinDev[dev & 63];
-    if (!optin) {             /* hashLog 14: 48 KiB of table + the 2 KiB static ring exceeds the default 48 KiB limit */
-        cudaFuncSetAttribute(zb_cand_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(zb_cand_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(zb_cand_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(zb_cand_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(zb_cand_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        optin = true;
-    }
-    switch (prm.mls) {
-    case 4:  zb_cand_kernel<4><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
-    case 5:  zb_cand_kernel<5><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
-    case 6:  zb_cand_kernel<6><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
-    case 7:  zb_cand_kernel<7><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
-    default: zb_cand_kernel<8><<<nbBlocks, 32, smem, stream>>>(d_src, d_dictEnd, d_blocks, prm, sd, d_dist, d_imageIn, d_imageOut); break;
-    }
-}
-
-/* one-warp launch that primes a table from the dictionary tail and stores it (positions + tags) in d_image */
-extern "C" cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbBlock* d_dictBlock, const ZbParams* prm, u8* d_image, cudaStream_t stream)
-{
-    ZbStrides sd; sd.dist = ZB_BLOCK_MAX; sd.seq = ZB_SEQ_STRIDE; sd.lit = ZB_LIT_STRIDE; sd.body = ZB_BODY_STRIDE; sd.state = ZB_STATE_STRIDE;   /* unused: no block is walked */
-    zb_launch_cand(nullptr, d_dictEnd, d_dictBlock, 1, *prm, sd, nullptr, nullptr, d_image, stream);
+#undef WALK_CASE
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u8* d_image, const ZbBlock* d_blocks, u32 nbBlocks, const ZbParams* prm, const ZbStrides* sdp,
-                                       u16* d_dist, u16* d_dist2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta, cudaEvent_t evMid, cudaStream_t stream)
+/* one-CTA launches that walk the dictionary tail and store the table(s) in d_image: prm->tableN u32 of the (short) table,
+ * followed for doubleFast by prm->tableNLong u32 of the 8-byte-hash table */
+extern "C" cudaError_t zb_launch_dict_image(const u8* d_dictEnd, const ZbChunk* d_dictChunk, const ZbParams* prm, u32* d_image, cudaStream_t stream)
+{
+    ZbStrides sd; sd.dist = ZB_BLOCK_MAX; sd.seq = ZB_SEQ_STRIDE; sd.lit = ZB_LIT_STRIDE; sd.body = ZB_BODY_STRIDE; sd.state = ZB_STATE_STRIDE;   /* unused: no block is walked */
+    cudaError_t e = zb_launch_walk(nullptr, d_dictEnd, d_dictChunk, 1, prm->mls, prm->tableN, prm->insStep, sd, 0, nullptr, nullptr, nullptr, d_image, stream);
+    if (e == cudaSuccess && prm->strategy == 2)
+        e = zb_launch_walk(nullptr, d_dictEnd, d_dictChunk, 1, 8, prm->tableNLong, prm->insStep, sd, 0, nullptr, nullptr, nullptr, d_image + prm->tableN, stream);
+    return e;
+}
+
+extern "C" cudaError_t zb_launch_match(const u8* d_src, const u8* d_dictEnd, const u32* d_image, const ZbBlock* d_blocks, u32 nbBlocks,
+                                       const ZbChunk* d_chunks, u32 nbChunks, u32 slotFirstBlock, const ZbParams* prm, const ZbStrides* sdp,
+                                       u16* d_dist, u32* d_far, u16* d_dist2, u32* d_far2, u64* d_seqs, u8* d_lits, ZbBlockMeta* d_meta, ZbSegMeta* d_segmeta,
+                                       cudaEvent_t evMid, cudaStream_t stream)
 {
     if (nbBlocks == 0) return cudaSuccess;
     ZbStrides const sd = *sdp;
+    cudaError_t e;
+    u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
+    u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);                       /* one warp per segment */
     if (prm->strategy == 2) {
-        /* doubleFast: one candidate walk per table (both walks see the same per-block insertion phase) */
-        ZbParams pl = *prm; pl.mls = 8; pl.hashLog = prm->longHashLog; pl.insPeriod = prm->insPeriodLong; pl.longPass = 1;
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, pl, sd, d_dist, nullptr, nullptr, stream);
-        zb_launch_cand(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist2, nullptr, nullptr, stream);
+        /* doubleFast: one candidate walk per table */
+        e = zb_launch_walk(d_src, d_dictEnd, d_chunks, nbChunks, 8, prm->tableNLong, prm->insStep, sd, slotFirstBlock, d_dist, d_far, d_image ? d_image + prm->tableN : nullptr, nullptr, stream); if (e != cudaSuccess) return e;
+        e = zb_launch_walk(d_src, d_dictEnd, d_chunks, nbChunks, prm->mls, prm->tableN, prm->insStep, sd, slotFirstBlock, d_dist2, d_far2, d_image, nullptr, stream); if (e != cudaSuccess) return e;
         if (evMid) cudaEventRecord(evMid, stream);
-        u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
-        u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);
-        zb_parse_dfast_kernel<<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_dist, d_dist2, d_seqs, d_meta, d_segmeta);
-        if (segs == 1u && sd.dist <= 8192u)
-            zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
-        else
-            zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_src, d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        if (d_dictEnd) zb_parse_dfast_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_far, d_dist2, d_far2, d_seqs, d_meta, d_segmeta);
+        else           zb_parse_dfast_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_far, d_dist2, d_far2, d_seqs, d_meta, d_segmeta);
     } else {
-        zb_launch_cand(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_image, nullptr, stream);
+        e = zb_launch_walk(d_src, d_dictEnd, d_chunks, nbChunks, prm->mls, prm->tableN, prm->insStep, sd, slotFirstBlock, d_dist, d_far, d_image, nullptr, stream); if (e != cudaSuccess) return e;
         if (evMid) cudaEventRecord(evMid, stream);
-        u32 const segs = (sd.dist + ZB_PARSE_SEG - 1u) / ZB_PARSE_SEG;
-        u32 const sgrid = (u32)(((u64)nbBlocks * segs + PARSE_WARPS - 1) / PARSE_WARPS);                   /* one warp per segment */
-        if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_meta, d_segmeta);
-        else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_seqs, d_meta, d_segmeta);
-        if (segs == 1u && sd.dist <= 8192u)
-            zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
-        else
-            zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_src, d_blocks, sd, d_segmeta, d_seqs, d_lits, d_meta);
+        if (d_dictEnd) zb_parse_kernel<true><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, d_dictEnd, d_blocks, nbBlocks, *prm, sd, d_dist, d_far, d_seqs, d_meta, d_segmeta);
+        else           zb_parse_kernel<false><<<sgrid, 32 * PARSE_WARPS, 0, stream>>>(d_src, nullptr, d_blocks, nbBlocks, *prm, sd, d_dist, d_far, d_seqs, d_meta, d_segmeta);
     }
+    if (segs == 1u && sd.dist <= 8192u)
+        zb_merge_small_kernel<<<(nbBlocks + MERGE_THREADS / 32u - 1u) / (MERGE_THREADS / 32u), MERGE_THREADS, 0, stream>>>(d_src, d_blocks, nbBlocks, *prm, sd, d_segmeta, d_seqs, d_lits, d_meta);
+    else
+        zb_merge_segments_kernel<<<nbBlocks, MERGE_THREADS, 0, stream>>>(d_src, d_blocks, *prm, sd, d_segmeta, d_seqs, d_lits, d_meta);
     return cudaGetLastError();
 }

@@ -8,8 +8,8 @@
  * ZSTD_compressBlock_internal (:4365-4376).
  *
  *   1. LL/OF/ML codes + three histograms: all threads, shared-memory atomics
- *   2. per stream (three threads in three different warps): encoding type, normalised counts,
- *      NCount header, FSE table — serial, <=53 symbols, shared memory
+ *   2. per stream (one warp each): encoding type, normalised counts (largest remainders), NCount header, FSE table
+ *      (zb_entropy.cuh); predefined tables are built once per device by the host and copied
  *   3. tANS state chains: state(i) depends on state(i+1) (common/fse.h:463-470), so each of the three
  *      chains is walked backwards by one thread; it records (bits, nbBits) per sequence
  *   4. all threads: per-sequence bit counts -> suffix sum -> bit offsets -> pack (edge words atomicOr)
@@ -85,11 +85,19 @@ __device__ __forceinline__ u32 zbd_selectEncodingType(u32 mostFrequent, u32 nbSe
     return set_compressed;
 }
 
+/* the three predefined tables (format "Default Distributions"), built by the host once per device (zb_dict.cu) */
+__device__ ZbdFseCTable g_defaultCT[3];                          /* 0 = LL, 1 = OF, 2 = ML */
+extern "C" cudaError_t zb_upload_default_tables(const ZbdFseCTable* host3, cudaStream_t stream)
+{
+    return cudaMemcpyToSymbolAsync(g_defaultCT, host3, 3 * sizeof(ZbdFseCTable), 0, cudaMemcpyHostToDevice, stream);
+}
+
 struct ZbdStreamWork {
     u32 count[64];
     short norm[64];
     u8  nc[136];            /* NCount bytes (or the single rle symbol) */
-    u8  scratch[512 + 136];
+    u8  symAt[512];         /* table-build scratch: symbol of every cell */
+    u16 cum[66];
     u32 ncSize;
     u32 type;
     u32 finalState;
@@ -140,45 +148,51 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             atomicAdd(&wk[2].count[s.mlc], 1u);
         }
         __syncthreads();
-        /* ---- 2. per-stream tables: threads 0, 32, 64 ---- */
-        if ((tid & 31u) == 0 && tid < 96u) {
-            u32 const st = tid >> 5;
+        /* ---- 2. per-stream tables: warps 0, 1, 2 ---- */
+        if (tid < 96u) {
+            u32 const st = tid >> 5, lane = tid & 31u;
             ZbdStreamWork* const w = &wk[st];
             u32 const maxAll = st == 0 ? MaxLL : (st == 1 ? MaxOff : MaxML);
-            u32 max = maxAll; while (w->count[max] == 0) max--;
-            u32 mostFrequent = 0; for (u32 s = 0; s <= max; s++) mostFrequent = w->count[s] > mostFrequent ? w->count[s] : mostFrequent;
+            u32 const c0 = w->count[lane], c1 = (lane + 32u <= maxAll) ? w->count[lane + 32u] : 0u;
+            u32 const hiUsed = __ballot_sync(ZB_FULL, c1 != 0u), loUsed = __ballot_sync(ZB_FULL, c0 != 0u);
+            u32 const max = hiUsed ? 63u - (u32)__clz((int)hiUsed) : 31u - (u32)__clz((int)loUsed);
+            u32 mostFrequent = c0 > c1 ? c0 : c1;
+#pragma unroll
+            for (u32 o = 16; o > 0; o >>= 1) mostFrequent = ::max(mostFrequent, __shfl_xor_sync(ZB_FULL, mostFrequent, o));
             u32 const defLog = st == 1 ? 5u : 6u;
             bool const defAllowed = st == 1 ? (max <= DefaultMaxOff) : true;
             u32 const prevRepeat = (de != nullptr && (bd.flags & ZB_FLAG_DICT) && de->present) ? de->fseRepeat[st] : 0u;
             u32 const type = zbd_selectEncodingType(mostFrequent, nbSeq, defLog, defAllowed, prm.strategy, prevRepeat);
-            ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
-            u32 const lastCode = st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc);
-            w->type = type; w->err = 0; w->ncSize = 0;
-            if (type == set_repeat) {                                /* zstd_compress_sequences.c:260-262 : no table description */
-                const u32* from = reinterpret_cast<const u32*>(&de->fse[st]);
+            if (lane == 0) { w->type = type; w->err = 0; w->ncSize = 0; }
+            __syncwarp();
+            if (type == set_repeat || type == set_basic) {           /* a ready table: the dictionary's (zstd_compress_sequences.c:260-262) or the predefined one */
+                const u32* from = reinterpret_cast<const u32*>(type == set_repeat ? &de->fse[st] : &g_defaultCT[st]);
                 u32* to = reinterpret_cast<u32*>(&ct[st]);
-                for (u32 i = 0; i < sizeof(ZbdFseCTable) / 4u; i++) to[i] = from[i];
+                for (u32 i = lane; i < sizeof(ZbdFseCTable) / 4u; i += 32u) to[i] = from[i];
             } else if (type == set_rle) {                            /* zstd_compress_sequences.c:254-259 */
-                ZbdSeq const first = zbd_unpack(myseq[0]);
-                u32 const sym = st == 0 ? first.llc : (st == 1 ? first.ofc : first.mlc);
-                zbd_fse_buildCTable_rle(&ct[st], max);
-                w->nc[0] = (u8)sym; w->ncSize = 1;
-            } else if (type == set_basic) {
-                const short* dn = st == 0 ? c_LL_defaultNorm : (st == 1 ? c_OF_defaultNorm : c_ML_defaultNorm);
-                u32 const dmax = st == 0 ? MaxLL : (st == 1 ? DefaultMaxOff : MaxML);
-                for (u32 s = 0; s <= dmax; s++) w->norm[s] = dn[s];
-                zbd_fse_buildCTable(&ct[st], w->norm, dmax, defLog, w->scratch);
+                if (lane == 0) {
+                    ZbdSeq const first = zbd_unpack(myseq[0]);
+                    u32 const sym = st == 0 ? first.llc : (st == 1 ? first.ofc : first.mlc);
+                    zbd_fse_buildCTable_rle(&ct[st], max);
+                    w->nc[0] = (u8)sym; w->ncSize = 1;
+                }
             } else {
                 u32 const FSELog = st == 1 ? OffFSELog : (st == 0 ? LLFSELog : MLFSELog);
                 u32 nbSeq_1 = nbSeq;
                 u32 const tableLog = zbd_fse_optimalTableLog(FSELog, nbSeq, max, 2);
-                if (w->count[lastCode] > 1u) { w->count[lastCode]--; nbSeq_1--; }     /* :271-274 */
-                u32 const r = zbd_fse_normalize(w->norm, tableLog, w->count, nbSeq_1, max, nbSeq_1 >= 2048u);
-                if (r == ZBD_ERR || r == 0) w->err = 1;
+                {   /* the last sequence's symbols start the states and cost no bits (zstd_compress_sequences.c:271-274) */
+                    ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
+                    u32 const lastCode = st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc);
+                    if (w->count[lastCode] > 1u) { nbSeq_1--; __syncwarp(); if (lane == 0) w->count[lastCode]--; }
+                    __syncwarp();
+                }
+                u32 const r = zbw_fse_normalize(w->norm, tableLog, w->count, nbSeq_1, max, lane);
+                u32 ncs = 0;
+                if (r != ZBD_ERR) { if (lane == 0) ncs = zbd_fse_writeNCount(w->nc, w->norm, max, tableLog); ncs = __shfl_sync(ZB_FULL, ncs, 0); }
+                if (r == ZBD_ERR || ncs == ZBD_ERR) { if (lane == 0) w->err = 1; }
                 else {
-                    u32 const ncs = zbd_fse_writeNCount(w->nc, w->norm, max, tableLog);
-                    if (ncs == ZBD_ERR) w->err = 1;
-                    else { w->ncSize = ncs; zbd_fse_buildCTable(&ct[st], w->norm, max, tableLog, w->scratch); }
+                    if (lane == 0) w->ncSize = ncs;
+                    zbw_fse_buildCTable(&ct[st], w->norm, max, tableLog, w->symAt, w->cum, lane);
                 }
             }
         }
