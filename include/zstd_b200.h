@@ -104,8 +104,13 @@ ZSTDB200_API const char* ZSTD_versionString(void);
 
 /* =====================  2. B200 extensions (no reference counterpart)  ===================== */
 
-/* Compress one frame whose input and output already live in device memory (HBM).
- * `stream` is a cudaStream_t (NULL = default stream).  Synchronises once to read the size. */
+/* Compress one frame whose input and output already live in device memory (HBM).  The call returns when the frame is
+ * complete (it synchronises to read the size).
+ * `stream` is a cudaStream_t.  Non-NULL: all work of the call is enqueued on that stream, behind whatever the caller
+ * queued there before (the way to compress the output of a kernel that is still running).  NULL: the context's own
+ * NON-BLOCKING streams are used — they are NOT ordered after the legacy default stream or any other stream, so the
+ * producer of d_src must have completed (e.g. cudaStreamSynchronize) before the call.  Large NULL-stream calls run as
+ * several waves on several streams.  d_src needs no padding: no byte outside [d_src, d_src + srcSize) is read. */
 ZSTDB200_API size_t ZSTDB200_compressDevice(ZSTD_CCtx* cctx, void* d_dst, size_t dstCapacity,
                                             const void* d_src, size_t srcSize, int compressionLevel, void* stream);
 
@@ -145,7 +150,7 @@ ZSTDB200_API void ZSTDB200_getLastStats(const ZSTD_CCtx* cctx, ZSTDB200_stats* o
  * reference's seekable format (contrib/seekable_format/zstd_seekable_compression_format.md; its writer is
  * ZSTD_seekable_writeSeekTable, zstdseek_compress.c:297).  Append the bytes behind the frames and the reference's
  * ZSTD_seekable_* readers can decompress any range.  cSizes / dSizes: compressed and decompressed size of every frame
- * (each < 4 GiB).  Host code.  Returns 17 + 8 * nbFrames, or an error code. */
+ * (compressed < 4 GiB, decompressed <= 1 GiB each: the format's limit, zstd_seekable.h:19).  Host code.  Returns 17 + 8 * nbFrames, or an error code. */
 ZSTDB200_API size_t ZSTDB200_writeSeekTable(void* dst, size_t dstCapacity, const size_t* cSizes, const size_t* dSizes, size_t nbFrames);
 
 /* XXH64 (seed 0) as used for the frame checksum (lib/common/xxhash.h); host code, no GPU (test hook). */
@@ -166,7 +171,8 @@ ZSTDB200_API size_t ZSTDB200_describePlan(const size_t* frameSizes, size_t nbFra
  * that level.  ZSTDB200_setStrictLevels(1) turns that into ZSTD_error_parameter_unsupported for the whole process. */
 ZSTDB200_API void ZSTDB200_setStrictLevels(int on);
 
-/* Which CUDA device new contexts bind to (default: current device / LOCAL_RANK). */
+/* Which CUDA device contexts created FROM NOW ON belong to (default: the creating thread's current device).  A context
+ * keeps the device it was created for; every call restores the calling thread's current device before it returns. */
 ZSTDB200_API int  ZSTDB200_setDevice(int device);
 ZSTDB200_API int  ZSTDB200_deviceAvailable(void);
 

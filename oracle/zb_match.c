@@ -107,22 +107,25 @@ static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t 
                  u32 mls, u32 N, u32 insStep, u32* dist)
 {
     u32* const table = (u32*)calloc((size_t)N, sizeof(u32));
-    u32 const B = zbo_tun.batch ? zbo_tun.batch : ZB_BATCH;
-    u32 hh[ZB_BATCH_MAX], dOld[ZB_BATCH_MAX];
-    u8 act[ZB_BATCH_MAX], ins[ZB_BATCH_MAX];
-    size_t lastInt = low;                 /* last position seen whose candidate was a hit (the walk's start counts as one) */
+    u32 const B = ZB_BATCH;
+    u32 hh[ZB_BATCH], dOld[ZB_BATCH];
+    u8 act[ZB_BATCH], ins[ZB_BATCH];
+    /* walk coordinates: x = p - low + shift, shift chosen so that batch borders (frame positions that are multiples of
+     * the batch, dictionary positions counting backwards from the frame start) are multiples of B in x */
+    size_t const shift = D > low ? (B - (D - low) % B) % B : 0;
+    size_t lastHit = low;                 /* last position seen whose candidate was a hit (the walk's start counts as one) */
     size_t s = low;
+    /* a table entry: (key + 1) << 11 | tag, key = x with its position inside the batch reversed, so that of all
+     * insertions of one batch the LOWEST position has the largest key, and any batch beats the batches before it */
 #define BKT(h) ((u32)(((u64)(h) * N) >> 32))
-#define CAND(c, h, me) (((c) && (((c) ^ (h)) & 0x7FFu) == 0) ? (me) - ((c) >> 11) : 0u)
-#define ENTRY(h, me) (((me) << 11) | ((h) & 0x7FFu))
+#define KEYOF(x) (((x) & ~(B - 1u)) + (B - 1u) - ((x) & (B - 1u)))
+#define CAND(c, h, x) (((c) && (((c) ^ (h)) & 0x7FFu) == 0 && KEYOF(((c) >> 11) - 1u) < (x)) ? (x) - KEYOF(((c) >> 11) - 1u) : 0u)
     while (s < end) {
-        /* batch = [s, e): e = next multiple of B in frame coordinates (frame position = p - D; dictionary positions count backwards) */
         size_t e, n, i;
         u32 step;
-        if (s >= D) e = s + B - ((s - D) % B);
-        else { e = s + ((D - s) % B ? (D - s) % B : B); }
+        e = s + B - ((s - low + shift) % B);
         if (e > end) e = end;
-        if (s == D) lastInt = D;          /* the frame starts with a fresh acceleration state behind a dictionary */
+        if (s == D) lastHit = D;          /* the frame starts with a fresh acceleration state behind a dictionary */
         n = e - s;
         /* 1. every position reads its bucket (the table as the previous batch left it) */
         for (i = 0; i < n; i++) {
@@ -131,38 +134,38 @@ static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t 
             dOld[i] = 0; hh[i] = 0;
             if (act[i]) {
                 u32 const h = zb_hash(rd64(buf + q), mls, 32);
-                u32 const me = (u32)(q - low) + 1u;
                 hh[i] = h;
-                dOld[i] = CAND(table[BKT(h)], h, me);
+                dOld[i] = CAND(table[BKT(h)], h, (u32)(q - low + shift));
             }
         }
-        /* 2. which positions enter the table: those without a candidate, on the pattern ((p - low) % step) < 2,
-         *    step = insStep + one per 128 positions walked since the last hit (zstd_fast.c:234,:342-347) */
-        step = insStep + (u32)((s - lastInt) >> 7);
+        /* 2. positions without a candidate enter the table on the pattern ((p - low) % step) < 2,
+         *    step = insStep + one per 128 positions walked since the last hit (zstd_fast.c:234,:342-347);
+         *    of the batch's insertions into one bucket the lowest position stays */
+        step = insStep + (u32)((s - lastHit) >> 7);
         for (i = 0; i < n; i++) {
             size_t const q = s + i;
-            size_t const u = q - low;
-            ins[i] = act[i] && dOld[i] == 0 && (u % step) < 2;
-            if (dOld[i]) lastInt = q;
+            ins[i] = act[i] && dOld[i] == 0 && ((q - low) % step) < 2;
+            if (dOld[i]) lastHit = q;
         }
-        /* 3. look-ups see the old table plus the batch's insertions at lower positions (exact sequential order
-         *    inside a batch; only the decisions of 2. were taken on the old state) */
+        for (i = 0; i < n; i++) if (ins[i]) {
+            u32 const x = (u32)(s + i - low + shift);
+            u32 const entry = ((KEYOF(x) + 1u) << 11) | (hh[i] & 0x7FFu);
+            u32* const slot = &table[BKT(hh[i])];
+            if (entry > *slot) *slot = entry;
+        }
+        /* 3. a position that found nothing before looks again: an insertion of this batch at a lower position may serve it */
         for (i = 0; i < n; i++) {
             size_t const q = s + i;
-            u32 d = 0;
-            if (act[i]) {
-                u32 const me = (u32)(q - low) + 1u;
-                d = CAND(table[BKT(hh[i])], hh[i], me);
-                if (ins[i]) table[BKT(hh[i])] = ENTRY(hh[i], me);
-            }
+            u32 d = dOld[i];
+            if (act[i] && d == 0) d = CAND(table[BKT(hh[i])], hh[i], (u32)(q - low + shift));
             if (q >= outStart) dist[q - outStart] = d;
         }
         s = e;
     }
     free(table);
 #undef BKT
+#undef KEYOF
 #undef CAND
-#undef ENTRY
 }
 
 void zbo_walkChunk(const zbo_plan* plan, const u8* buf, size_t bufSize, size_t chunkStart, size_t chunkEnd, zbo_chunkCand* cc)

@@ -98,7 +98,15 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
 #define ZB_MAX_IMAGES 4
 
 /* ------------------------------------------------------------------ context */
-static int g_device = -1;
+#include <atomic>
+static std::atomic<int> g_device(-1);
+
+/* restores the calling thread's current device when a call returns (a context works on the device it was created for) */
+struct ZbDeviceGuard {
+    int prev;
+    ZbDeviceGuard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~ZbDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define ZB_WAVE_SLOTS_MAX 14u
 #define ZB_WAVE_SLOTS_DEFAULT 4u
@@ -119,7 +127,8 @@ struct ZSTD_CDict_s {
 };
 
 struct ZSTD_CCtx_s {
-    int device;
+    int device;                    /* -1 until the first call created the stream and events on bindDevice */
+    int bindDevice;                /* device captured by ZSTD_createCCtx */
     cudaStream_t stream;
     /* per-block workspace */
     size_t capBlocks, capFrames, capWaves;
@@ -161,7 +170,7 @@ struct ZSTD_CCtx_s {
 
 static double zb_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 
-extern "C" int ZSTDB200_setDevice(int device) { g_device = device; return 0; }
+extern "C" int ZSTDB200_setDevice(int device) { g_device.store(device); return 0; }
 extern "C" int ZSTDB200_deviceAvailable(void)
 {
     int n = 0;
@@ -174,6 +183,9 @@ extern "C" ZSTD_CCtx* ZSTD_createCCtx(void)
     ZSTD_CCtx* c = (ZSTD_CCtx*)calloc(1, sizeof(ZSTD_CCtx));
     if (!c) return NULL;
     c->device = -1;
+    /* the context belongs to the device that is selected NOW (ZSTDB200_setDevice, else the thread's current device) */
+    c->bindDevice = g_device.load();
+    if (c->bindDevice < 0) { int d = -1; if (cudaGetDevice(&d) == cudaSuccess) c->bindDevice = d; else cudaGetLastError(); }
     c->advLevel = 3;                                                         /* ZSTD_CLEVEL_DEFAULT */
     {   const char* s = getenv("ZSTDB200_SERIAL"); const char* w = getenv("ZSTDB200_WAVE_BLOCKS");
         c->devWaveBlocks = (s && atoi(s)) ? 0u : (w ? (u32)atoi(w) : 1024u);     /* 128 MiB waves: tests/wave_sweep.py */
@@ -193,20 +205,29 @@ static size_t zb_ctxInit(ZSTD_CCtx* c)
     if (c->device >= 0) { CK(cudaSetDevice(c->device)); return 0; }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZB_ERR(ZB_error_GENERIC); }
-    int dev = g_device;
+    int dev = c->bindDevice;
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
     CK(cudaSetDevice(dev));
-    c->device = dev;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    {   /* the predefined FSE tables live in device memory (one copy per device; re-uploading the same bytes is harmless) */
+    /* everything or nothing: a partial failure leaves the context uninitialised (device stays -1) */
+    cudaStream_t st = nullptr; cudaEvent_t ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess) {
+        /* the predefined FSE tables live in device memory (one copy per device; re-uploading the same bytes is harmless) */
         static ZbdFseCTable defaults[3]; static std::once_flag once;
         std::call_once(once, [] { zb_buildDefaultTables(defaults); });
-        CK(zb_upload_default_tables(defaults, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        e = zb_upload_default_tables(defaults, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evK0)); CK(cudaEventCreate(&c->evK1));
-    CK(cudaEventCreate(&c->evK2)); CK(cudaEventCreate(&c->evK3)); CK(cudaEventCreate(&c->evMid));
-    CK(cudaEventCreate(&c->evKEnd)); CK(cudaEventCreate(&c->evEnd));
+    if (e != cudaSuccess) {
+        for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+        if (st) cudaStreamDestroy(st);
+        cudaGetLastError();
+        return ZB_ERR(e == cudaErrorMemoryAllocation ? ZB_error_memory_allocation : ZB_error_GENERIC);
+    }
+    c->stream = st;
+    c->evStart = ev[0]; c->evK0 = ev[1]; c->evK1 = ev[2]; c->evK2 = ev[3]; c->evK3 = ev[4]; c->evMid = ev[5]; c->evKEnd = ev[6]; c->evEnd = ev[7];
+    c->device = dev;
     return 0;
 }
 
@@ -225,6 +246,7 @@ extern "C" size_t ZSTD_freeCDict(ZSTD_CDict* cd);
 extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 {
     if (!c) return 0;
+    ZbDeviceGuard guard;
     ZSTD_freeCDict(c->advLocalDict);
     if (c->device >= 0) {
         cudaSetDevice(c->device);
@@ -763,6 +785,7 @@ static size_t zb_compressFramesAny(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
 {
     if (!c) return ZB_ERR(ZB_error_GENERIC);
     if (nbFrames == 0) return 0;
+    ZbDeviceGuard guard;
     {   size_t const e = zb_ctxInit(c); if (zb_isErr(e)) return e; }
     memset(&c->stats, 0, sizeof(c->stats));
     if (deviceMemory) {
@@ -880,10 +903,11 @@ extern "C" size_t ZSTDB200_writeSeekTable(void* dstv, size_t dstCapacity, const 
     u8* const dst = (u8*)dstv;
     if (nbFrames > 0x8000000u) return ZB_ERR(ZB_error_srcSize_wrong);                         /* ZSTD_SEEKABLE_MAXFRAMES, zstd_seekable.h:20 */
     size_t const need = 8 + 8 * nbFrames + 9;
-    if (dstCapacity < need) return ZB_ERR(ZB_error_dstSize_tooSmall);
     if (!dst || (nbFrames && (!cSizes || !dSizes))) return ZB_ERR(ZB_error_GENERIC);
+    if (dstCapacity < need) return ZB_ERR(ZB_error_dstSize_tooSmall);
     auto w32 = [](u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); };
-    for (size_t f = 0; f < nbFrames; f++) if (cSizes[f] > 0xFFFFFFFFull || dSizes[f] > 0xFFFFFFFFull) return ZB_ERR(ZB_error_srcSize_wrong);   /* 32-bit fields */
+    for (size_t f = 0; f < nbFrames; f++)                           /* 32-bit fields; ZSTD_SEEKABLE_MAX_FRAME_DECOMPRESSED_SIZE = 1 GiB (zstd_seekable.h:19) */
+        if (cSizes[f] > 0xFFFFFFFFull || dSizes[f] > 0x40000000ull) return ZB_ERR(ZB_error_srcSize_wrong);
     w32(dst, 0x184D2A5Eu);                                                                     /* Skippable_Magic_Number */
     w32(dst + 4, (u32)(need - 8));                                                             /* Frame_Size */
     u8* p = dst + 8;

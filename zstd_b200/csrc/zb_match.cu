@@ -3,13 +3,12 @@
  * Replaces the CPU loops ZSTD_compressBlock_fast_noDict_generic / _extDict_generic
  * (/root/reference/lib/compress/zstd_fast.c:192-423, :709-960) and ZSTD_compressBlock_doubleFast_noDict_generic
  * (zstd_double_fast.c:105-323) with a data-parallel formulation:
- *   - K1a (one 1024-thread CTA per CHUNK of up to 4 blocks) keeps the chunk's hash table in shared memory — primed from
+ *   - K1a (one CTA per CHUNK of up to 4 blocks) keeps the chunk's hash table in shared memory — primed from
  *     the <=128 KiB in front of the chunk (zstd_fast.c:53-85 does this for dictionaries, zstdmt_compress.c:1182-1227 for
  *     job overlaps), then alive through all blocks of the chunk — and visits the positions in BATCHES of 1024: every
- *     position of a batch reads its bucket, positions that found no candidate are inserted, and look-ups see the batch's
- *     own insertions at lower positions through a per-batch chained index, so the result equals a sequential walk whose
- *     insertion decisions were taken on the table as the previous batch left it.  Two barriers per batch, no dependent
- *     global load: the walk does not depend on the parse;
+ *     position of a batch reads its bucket, positions that found no candidate are inserted (one atomicMax each: the
+ *     lowest position of a batch wins a bucket), and a position that found nothing looks once more after the batch's
+ *     insertions.  Two barriers per batch, no dependent global load: the walk does not depend on the parse;
  *   - K1b (one warp per 16 KiB segment of a block) does the greedy selection: 32 probe positions per step — pairs
  *     (p, p+1) spaced by `step` as in zstd_fast.c:225-229 — lowest matching lane wins (warp ballot); backward
  *     catch-up (:387-391) and forward extension (ZSTD_count, zstd_compress_internal.h:771) are warp-cooperative:
@@ -76,111 +75,151 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
  * dist[p] = distance from p to its candidate: the latest earlier position that was inserted into p's bucket and has
  * p's tag, 0 if none.  Distances >= 0xFFFF go to the `far` array (dist16 = ZB_FAR).
  * ---------------------------------------------------------------------------------------------- */
-#define WALK_HEADS 1024u
-#define WALK_NONE  0xFFFFFFFFu
-#define WALK_AUX_BYTES (2u * ZB_BATCH * 4u + 2u * WALK_HEADS * 4u + 2u * ZB_BATCH * 2u)     /* hsh + heads + nxt */
-
-/* candidate distance of the position `me` - 1 given a bucket's content c (0 = no candidate) */
-__device__ __forceinline__ u32 zb_cand(u32 c, u32 h, u32 me)
+/* A table entry is (key + 1) << 11 | tag.  key = walk coordinate x of the position with its offset inside the batch
+ * reversed: of all insertions of one batch into a bucket the LOWEST position has the largest key, and every batch beats
+ * the batches before it — so one shared-memory atomicMax per insertion arbitrates a batch, whatever the thread order. */
+#define ZB_TAG_MASK ((1u << ZB_TAG_BITS) - 1u)
+__device__ __forceinline__ u32 zb_walk_key(u32 x) { return (x & ~(ZB_BATCH - 1u)) + (ZB_BATCH - 1u) - (x & (ZB_BATCH - 1u)); }
+__device__ __forceinline__ u32 zb_walk_entry(u32 h, u32 x) { return ((zb_walk_key(x) + 1u) << ZB_TAG_BITS) | (h & ZB_TAG_MASK); }
+/* candidate distance of the position at walk coordinate x given a bucket's content c (0 = no candidate) */
+__device__ __forceinline__ u32 zb_walk_cand(u32 c, u32 h, u32 x)
 {
-    return (c != 0u && ((c ^ h) & ((1u << ZB_TAG_BITS) - 1u)) == 0u) ? me - (c >> ZB_TAG_BITS) : 0u;
+    u32 const px = zb_walk_key((c >> ZB_TAG_BITS) - 1u);          /* the reversal is its own inverse */
+    return (c != 0u && ((c ^ h) & ZB_TAG_MASK) == 0u && px < x) ? x - px : 0u;
 }
-__device__ __forceinline__ u32 zb_entry(u32 h, u32 me) { return (me << ZB_TAG_BITS) | (h & ((1u << ZB_TAG_BITS) - 1u)); }
 
-template <int MLS>
-__global__ void __launch_bounds__(ZB_BATCH, 2)
+/* P consecutive positions per thread, ZB_BATCH / P threads per CTA.  Per batch:
+ *   A  every position hashes its 8 bytes and reads its bucket (the table as the previous batch left it);
+ *   B  positions that found no candidate and lie on the insertion pattern atomicMax their entry into the bucket;
+ *   C  positions that found nothing in A look again: the batch's lowest insertion into their bucket may serve them.
+ * Two barriers per batch (A|B, B|C); C of one batch and A of the next share a region. */
+template <int MLS, int P>
+__global__ void __launch_bounds__(ZB_BATCH / P)
 zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbChunk* __restrict__ chunks, u32 insStep, u32 N, ZbStrides sd,
                u32 slotFirstBlock, u16* __restrict__ dist, u32* __restrict__ far,
                const u32* __restrict__ imageIn, u32* __restrict__ imageOut)
 {
-    extern __shared__ __align__(16) u32 smem[];
-    __shared__ u32 sLastHit[2];                                   /* rel position of the latest candidate hit, per batch parity */
+    constexpr u32 THREADS = ZB_BATCH / P;
+    extern __shared__ __align__(16) u32 table[];
+    __shared__ u32 sLastHit[2];                                   /* walk coordinate of the latest candidate hit: [k & 1] gets batch k's */
     u32 const t = threadIdx.x;
     ZbChunk const cd = chunks[blockIdx.x];
     bool const buildImage = imageOut != nullptr;
     u32 const D = cd.dictLen;                                     /* rel position of the frame's first byte when a dictionary is in front */
     u32 const H = cd.histLen;                                     /* rel position of the chunk's first byte */
-    u32 const total = buildImage ? D : H + cd.size;               /* positions [0, total) are walked; no read at or past total */
+    u32 const total = buildImage ? D : H + cd.size;               /* rel positions [0, total) are walked; no read at or past total */
     bool const fromImage = imageIn != nullptr && D != 0u && !buildImage;
-    /* a frame that is a single batch behind a dictionary image never reads its own insertions from the table:
-     * the image stays in global memory (config 5: a million 1 KiB records) */
-    bool const direct = fromImage && H == D && cd.size <= ZB_BATCH;
-    u32* const table = smem;
-    u32* const hsh   = table + (direct ? 0u : N);                 /* [2][ZB_BATCH] hash of each position of the batch */
-    u32* const heads = hsh + 2u * ZB_BATCH;                       /* [2][WALK_HEADS] chain heads of the batch index */
-    u16* const nxt   = reinterpret_cast<u16*>(heads + 2u * WALK_HEADS);   /* [2][ZB_BATCH] */
-
+    /* walk coordinate x = rel + shift: batch borders (frame positions that are multiples of the batch; dictionary
+     * positions count backwards from the frame start) are the multiples of ZB_BATCH in x */
+    u32 const shift = (ZB_BATCH - (D % ZB_BATCH)) % ZB_BATCH;
+    /* a frame that is a single batch behind a dictionary image never needs its own insertions later: the image stays
+     * in global memory and the batch's insertions go to a cleared private table (config 5: a million 1 KiB records) */
     const u8* const fbase = src + cd.srcOff - H;                  /* fbase + rel = the byte's address for rel >= D */
     const u8* const dbase = dictEnd - D;                          /* same for rel < D */
 
-    if (!direct) {
-        if (fromImage) for (u32 i = t; i < N; i += ZB_BATCH) table[i] = __ldg(imageIn + i);
-        else           for (u32 i = t; i < N; i += ZB_BATCH) table[i] = 0u;
-    }
-    for (u32 i = t; i < 2u * WALK_HEADS; i += ZB_BATCH) heads[i] = WALK_NONE;
-    if (t < 2u) sLastHit[t] = 0u;
+    if (fromImage) for (u32 i = t; i < N; i += THREADS) table[i] = __ldg(imageIn + i);
+    else           for (u32 i = t; i < N; i += THREADS) table[i] = 0u;
+    if (t < 2u) sLastHit[t] = shift;                              /* the walk's start counts as a hit */
     __syncthreads();
 
-    /* batch borders lie at D + k * ZB_BATCH: frame positions that are multiples of the batch */
-    u32 const phase = (ZB_BATCH - (D % ZB_BATCH)) % ZB_BATCH;
-    auto batchEnd = [&](u32 s0) { u32 const e0 = s0 + ZB_BATCH - ((s0 + phase) % ZB_BATCH); return e0 < total ? e0 : total; };
-    auto active = [&](u32 q) { return (q + 8u <= total) && !(q < D && q + 8u > D); };
-    auto load8 = [&](u32 q) { return zb_ld64u((q < D ? dbase : fbase) + q); };
-    u32 s = fromImage ? D : 0u;
-    u32 e = s < total ? batchEnd(s) : s;
-    u64 w = (s + t < e && active(s + t)) ? load8(s + t) : 0ull;
+    u32 const xEnd = total + shift;
+    u32 x0 = (fromImage ? D : 0u) + shift;                        /* first batch: may start inside a batch (x0 is its border) */
+    x0 &= ~(ZB_BATCH - 1u);
+    u32 const xLow = (fromImage ? D : 0u) + shift;                /* first walked coordinate */
+
+    /* the 11 bytes of a thread's P positions (+7): words realigned to the first position; wrd[] of the NEXT batch is in flight */
+    u32 wrd[3];
+    auto fetch = [&](u32 xb) {
+        u32 const xa = xb + P * t;                                /* first coordinate of the thread */
+        wrd[0] = wrd[1] = wrd[2] = 0u;
+        if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
+        u32 const rel = xa - shift;                               /* may wrap for xa < shift: handled by the slow path's checks */
+        bool const slow = (xa < xLow) || (D != 0u && rel < D && rel + P + 7u > D);
+        if (slow) return;                                         /* assembled byte-wise in the batch */
+        const u8* const a = (rel < D ? dbase : fbase) + rel;
+        const u8* const lim = (rel < D ? dbase + D : fbase + total);
+        const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
+        u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
+        u32 const w0 = __ldg(p);
+        u32 const w1 = (reinterpret_cast<const u8*>(p + 1) < lim) ? __ldg(p + 1) : 0u;
+        u32 const w2 = (reinterpret_cast<const u8*>(p + 2) < lim) ? __ldg(p + 2) : 0u;
+        u32 const w3 = (sh != 0u && reinterpret_cast<const u8*>(p + 3) < lim) ? __ldg(p + 3) : 0u;
+        wrd[0] = __funnelshift_r(w0, w1, sh); wrd[1] = __funnelshift_r(w1, w2, sh); wrd[2] = __funnelshift_r(w2, w3, sh);
+    };
+    fetch(x0);
     u32 const blockMask = (1u << cd.blockLog) - 1u;
-    for (u32 k = 0; s < total; k++) {
+    for (u32 k = 0; x0 < xEnd; k++, x0 += ZB_BATCH) {
         u32 const par = k & 1u;
-        u32 const q = s + t;
-        bool const act = (q < e) && active(q);
-        u32 const h = act ? zb_hash(w, MLS, 32u) : 0u;
-        u32 const bkt = __umulhi(h, N);
-        u32 const me = q + 1u;
-        u32 const old = act ? (direct ? __ldg(imageIn + bkt) : table[bkt]) : 0u;
-        u32 const dOld = zb_cand(old, h, me);
-        u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
-        if (D != 0u && s >= D && li < D) li = D;                  /* the frame starts with a fresh acceleration state behind a dictionary */
-        u32 const step = insStep + ((s - li) >> 7);
-        bool const ins = act && dOld == 0u && (q % step) < 2u;
-        u32* const myHeads = heads + par * WALK_HEADS;
-        u16* const myNxt = nxt + par * ZB_BATCH;
-        u32* const myHsh = hsh + par * ZB_BATCH;
-        u32 const slot = bkt & (WALK_HEADS - 1u);
-        myHsh[t] = h;
-        if (ins) myNxt[t] = (u16)atomicExch(&myHeads[slot], t);   /* 0xFFFF = end of chain */
-        {   u32 const hits = __ballot_sync(ZB_FULL, act && dOld != 0u);
-            if (hits && (t & 31u) == 31u - (u32)__clz((int)hits)) atomicMax(&sLastHit[par], q); }
-        /* next batch's bytes: in flight across the barriers */
-        u32 const sn = e, en = sn < total ? batchEnd(sn) : sn;
-        if (sn + t < en && active(sn + t)) w = load8(sn + t);
-        __syncthreads();
-        /* look-ups: the nearest inserted position below me in my bucket, else what the table held before the batch */
-        u32 best = WALK_NONE; bool higher = false;
-        if (act) {
-            u32 j = myHeads[slot];
-            while (j != WALK_NONE && j != 0xFFFFu) {
-                if (__umulhi(myHsh[j], N) == bkt) {
-                    if (j < t) { if (best == WALK_NONE || j > best) best = j; }
-                    else if (j > t) higher = true;
+        u32 const xa = x0 + P * t;
+        u32 h[P], bkt[P], old[P], dOld[P];
+        bool act[P];
+        /* ---- A ---- */
+        {   u32 const rel0 = xa - shift;
+            bool const slow = (xa < xLow) || (D != 0u && rel0 < D && rel0 + P + 7u > D);
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                u32 const x = xa + (u32)i, rel = x - shift;
+                act[i] = (x >= xLow) && (rel + 8u <= total) && !(rel < D && rel + 8u > D);
+                u64 v;
+                if (slow) v = act[i] ? zb_ld64u((rel < D ? dbase : fbase) + rel) : 0ull;
+                else {
+                    u32 const lo = i ? __funnelshift_r(wrd[0], wrd[1], 8u * (u32)i) : wrd[0];
+                    u32 const hi = i ? __funnelshift_r(wrd[1], wrd[2], 8u * (u32)i) : wrd[1];
+                    v = ((u64)hi << 32) | lo;
                 }
-                j = myNxt[j];
+                h[i] = zb_hash(v, MLS, 32u);
+                bkt[i] = __umulhi(h[i], N);
+                old[i] = act[i] ? table[bkt[i]] : 0u;
             }
         }
-        u32 const c = (best != WALK_NONE) ? zb_entry(myHsh[best], s + best + 1u) : old;
-        u32 const d = act ? zb_cand(c, h, me) : 0u;
-        if (!buildImage && q < e && q >= H) {
-            u32 const qb = q - H;                                 /* offset in the chunk */
-            size_t const idx = (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask);
-            if (d >= ZB_FAR) { dist[idx] = (u16)ZB_FAR; far[idx] = d; } else dist[idx] = (u16)d;
+        u32 hitX = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) { dOld[i] = zb_walk_cand(old[i], h[i], xa + (u32)i); if (dOld[i]) hitX = xa + (u32)i; }
+        u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
+        if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
+        u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
+        u32 const step = insStep + ((sWalk - li) >> 7);
+        {   u32 const wmax = __reduce_max_sync(ZB_FULL, hitX);
+            if (wmax && (t & 31u) == 0u) atomicMax(&sLastHit[par], wmax); }
+        fetch(x0 + ZB_BATCH);                                     /* next batch's bytes: in flight across the barriers */
+        /* insertion pattern ((rel) % step) < 2 for P consecutive positions: one division per thread */
+        u32 r0;
+        {   u32 const rel0 = xa - shift;
+            u32 const q = (u32)(__fdividef((float)rel0, (float)step));
+            int r = (int)rel0 - (int)(q * step);
+            if (r < 0) r += (int)step; else if (r >= (int)step) r -= (int)step;
+            r0 = (u32)r; }
+        __syncthreads();
+        /* ---- B ---- */
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            u32 ri = r0 + (u32)i; if (ri >= step) ri -= step; if (ri >= step) ri -= step;
+            bool const ins = act[i] && dOld[i] == 0u && (ri < 2u);
+            if (ins) atomicMax(&table[bkt[i]], zb_walk_entry(h[i], xa + (u32)i));
         }
-        if (ins && !higher && !direct) table[bkt] = zb_entry(h, me);   /* the highest inserted position of the batch owns the bucket */
-        heads[(par ^ 1u) * WALK_HEADS + t] = WALK_NONE;           /* WALK_HEADS == ZB_BATCH: one slot per thread */
         if (t == 0u) { u32 const a = sLastHit[par], b = sLastHit[par ^ 1u]; if (b > a) sLastHit[par] = b; }
         __syncthreads();
-        s = e; e = en;
+        /* ---- C ---- */
+        u32 d[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            d[i] = dOld[i];
+            if (act[i] && d[i] == 0u) d[i] = zb_walk_cand(table[bkt[i]], h[i], xa + (u32)i);
+        }
+        if (!buildImage && xa >= H + shift && xa < xEnd) {
+            u32 const qb = xa - shift - H;                        /* offset in the chunk: a multiple of P */
+            size_t const idx = (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask);
+            u32 o[P];
+#pragma unroll
+            for (int i = 0; i < P; i++) { o[i] = d[i] >= ZB_FAR ? ZB_FAR : d[i]; if (d[i] >= ZB_FAR && xa + (u32)i < xEnd) far[idx + i] = d[i]; }
+            if (P == 4 && xa + 4u <= xEnd) *reinterpret_cast<uint2*>(dist + idx) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+            else {
+#pragma unroll
+                for (int i = 0; i < P; i++) if (xa + (u32)i < xEnd) dist[idx + i] = (u16)o[i];
+            }
+        }
     }
-    if (buildImage) for (u32 i = t; i < N; i += ZB_BATCH) imageOut[i] = table[i];
+    if (buildImage) { __syncthreads(); for (u32 i = t; i < N; i += THREADS) imageOut[i] = table[i]; }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -639,18 +678,21 @@ zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
 }
 
 /* ------------------------------------------------------------------------------------------------ launchers */
+#ifndef WALK_P
+#define WALK_P 4
+#endif
 static cudaError_t zb_launch_walk(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 mls, u32 N, u32 insStep, const ZbStrides& sd,
                                   u32 slotFirstBlock, u16* d_dist, u32* d_far, const u32* d_imageIn, u32* d_imageOut, cudaStream_t stream)
 {
-    size_t const smem = (size_t)N * 4u + WALK_AUX_BYTES;
+    size_t const smem = (size_t)N * 4u;
     cudaError_t e = cudaSuccess;
 #define WALK_CASE(M) case M: \
-        e = cudaFuncSetAttribute(zb_walk_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e; \
-        zb_walk_kernel<M><<<nbChunks, ZB_BATCH, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
+        e = cudaFuncSetAttribute(zb_walk_kernel<M, WALK_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e; \
+        zb_walk_kernel<M, WALK_P><<<nbChunks, ZB_BATCH / WALK_P, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
     switch (mls) {
     WALK_CASE(4) WALK_CASE(5) WALK_CASE(6) WALK_CASE(7)
-    default: e = cudaFuncSetAttribute(zb_walk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e;
-        zb_walk_kernel<8><<<nbChunks, ZB_BATCH, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
+    default: e = cudaFuncSetAttribute(zb_walk_kernel<8, WALK_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e;
+        zb_walk_kernel<8, WALK_P><<<nbChunks, ZB_BATCH / WALK_P, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
     }
 #undef WALK_CASE
     return cudaGetLastError();
