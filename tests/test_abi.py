@@ -91,3 +91,37 @@ def test_header_is_valid_c99_and_links(tmp_path):
     subprocess.check_call(cmd)
     out = subprocess.check_output([str(exe)], text=True)
     assert out.split()[0] == "10506" and "too small" in out
+
+
+REF_EXAMPLES = "/root/reference/examples"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference tree absent (GPU box)")
+@pytest.mark.parametrize("example", ["simple_compression.c", "multiple_simple_compression.c", "dictionary_compression.c"])
+def test_reference_examples_compile_and_link_unmodified(tmp_path, example):
+    """The reference's own example programs (examples/simple_compression.c:28 ZSTD_compress, multiple_simple_compression.c:74
+    ZSTD_compressCCtx, dictionary_compression.c ZSTD_createCDict / ZSTD_compress_usingCDict), compiled UNMODIFIED against the
+    STOCK lib/zstd.h, link against this library alone: every compression symbol they use is exported with the reference's
+    signature.  (Compile + link only: running them needs a GPU.)"""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "zstd_b200")
+    exe = tmp_path / "example"
+    cmd = [gcc, "-O1", "-I", "/root/reference/lib", "-I", REF_EXAMPLES, os.path.join(REF_EXAMPLES, example), "-o", str(exe),
+           "-L", libdir, "-lzstd_b200", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    assert os.path.exists(exe)
+
+
+def test_soname_build_target(tmp_path):
+    """`make -C zstd_b200/csrc soname` produces the same code under the reference's shared-library name (lib/Makefile:85,145)"""
+    import shutil, subprocess
+    if not shutil.which("nvcc") or not shutil.which("readelf"):
+        pytest.skip("no nvcc / readelf")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "zstd_b200", "csrc"), "soname"])
+    out = subprocess.check_output(["readelf", "-d", os.path.join(root, "zstd_b200", "libzstd.so.1")], text=True)
+    assert "libzstd.so.1" in out and "SONAME" in out

@@ -33,7 +33,7 @@ def _worker(rank, world, port, q):
     frames = split_into_frames(len(src), 1 << 20)
     b, e = partition_frames([s for _, s in frames], world)[rank]
     local = b"".join(zref.oracle_compress(src[o:o + s], 1) for o, s in frames[b:e])
-    sizes, cat = gather_compressed(torch.frombuffer(bytearray(local), dtype=torch.uint8), dst=0)
+    sizes, cat, _ = gather_compressed(torch.frombuffer(bytearray(local), dtype=torch.uint8), dst=0)
     # per-frame sizes of all ranks, for one seek table over the gathered frames (contrib/seekable_format)
     mine = [zref.oracle_compress(src[o:o + s], 1) for o, s in frames[b:e]]
     gathered = gather_frame_sizes([len(f) for f in mine], [s for _, s in frames[b:e]], dst=0)

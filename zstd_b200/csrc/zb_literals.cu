@@ -120,7 +120,7 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides s
     /* ---------------- decisions (zstd_compress_literals.c:129-191, huf_compress.c:1359-1420) ----------------
      * `repeat` is the HUF_repeat mode of the previous block's table: only a frame's first block behind a
      * zstd-format dictionary has one (ZSTD_loadCEntropy, zstd_compress.c:4997-5005); 0 none, 1 check, 2 valid. */
-    u32 repeat = (de != nullptr && (blocks[b].flags & ZB_FLAG_DICT) && de->present) ? de->hufRepeat : 0u;
+    u32 repeat = (de != nullptr && (blocks[b].flags & ZB_FLAG_FIRST) && de->present) ? de->hufRepeat : 0u;
     bool const preferRepeat = (n <= 1024u);                      /* strategy < lazy, zstd_compress_literals.c:165 */
     u32 const lhSize = 3u + (n >= 1024u) + (n >= 16384u);
     u32 const nbStreams = (n < 256u || (repeat == 2u && lhSize == 3u)) ? 1u : 4u;     /* :142, :171 */

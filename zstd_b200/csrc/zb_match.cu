@@ -79,13 +79,102 @@ __device__ __forceinline__ u64 zb_pack_seq(u32 offBase, u32 litLen, u32 matchLen
  * reversed: of all insertions of one batch into a bucket the LOWEST position has the largest key, and every batch beats
  * the batches before it — so one shared-memory atomicMax per insertion arbitrates a batch, whatever the thread order. */
 #define ZB_TAG_MASK ((1u << ZB_TAG_BITS) - 1u)
-__device__ __forceinline__ u32 zb_walk_key(u32 x) { return (x & ~(ZB_BATCH - 1u)) + (ZB_BATCH - 1u) - (x & (ZB_BATCH - 1u)); }
+__device__ __forceinline__ u32 zb_walk_key(u32 x) { return (x | (ZB_BATCH - 1u)) - (x & (ZB_BATCH - 1u)); }   /* its own inverse */
 __device__ __forceinline__ u32 zb_walk_entry(u32 h, u32 x) { return ((zb_walk_key(x) + 1u) << ZB_TAG_BITS) | (h & ZB_TAG_MASK); }
-/* candidate distance of the position at walk coordinate x given a bucket's content c (0 = no candidate) */
+/* candidate distance of the position at walk coordinate x given a bucket's content c (0 = no candidate).
+ * An empty bucket (c = 0) decodes to a coordinate far above x. */
 __device__ __forceinline__ u32 zb_walk_cand(u32 c, u32 h, u32 x)
 {
-    u32 const px = zb_walk_key((c >> ZB_TAG_BITS) - 1u);          /* the reversal is its own inverse */
-    return (c != 0u && ((c ^ h) & ZB_TAG_MASK) == 0u && px < x) ? x - px : 0u;
+    u32 const px = zb_walk_key((c >> ZB_TAG_BITS) - 1u);
+    return (((c ^ h) & ZB_TAG_MASK) == 0u && px < x) ? x - px : 0u;
+}
+
+/* which of the P consecutive positions starting at rel0 lie on the insertion pattern (rel % step) < 2, as a bit mask */
+template <int P>
+__device__ __forceinline__ u32 zb_walk_pattern(u32 rel0, u32 step)
+{
+    if (step <= 2u) return (1u << P) - 1u;
+    u32 const q = (u32)__fdividef((float)rel0, (float)step);    /* rel0 < 2^21: exact up to +-1, fixed below */
+    int r = (int)rel0 - (int)(q * step);
+    if (r < 0) r += (int)step; else if (r >= (int)step) r -= (int)step;
+    u32 m = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) {                                /* r + i < 2 * step: the position is r + i or r + i - step into its period */
+        u32 const ri = (u32)r + (u32)i;
+        m |= ((ri < 2u) || (ri - step < 2u)) ? (1u << i) : 0u;
+    }
+    return m;
+}
+
+/* One batch of the walk for one thread: P consecutive positions from walk coordinate xa.
+ * INTERIOR: every position of the batch is walked, lies in the frame's own bytes and has its 8 bytes readable: no
+ * activity predicates, bytes come from the words prefetched in wrd[]. */
+template <int MLS, int P, bool INTERIOR>
+__device__ __forceinline__ void zb_walk_batch(u32* __restrict__ table, u32* sLastHit, u32 par, u32 xa, u32 x0, const u32 (&wrd)[3],
+                                              u32 N, u32 insStep, u32 shift, u32 D, u32 total, u32 xLow, u32 xEnd,
+                                              const u8* fbase, const u8* dbase, bool output, u16* __restrict__ distRow, u32* __restrict__ farRow,
+                                              u32& nextWordsFetched)
+{
+    (void)nextWordsFetched;
+    u32 h[P], bkt[P], old[P], dOld[P];
+    bool act[P];
+    /* ---- A: hash, read the bucket ---- */
+    {   u32 const rel0 = xa - shift;
+        bool const slow = !INTERIOR && ((xa < xLow) || (D != 0u && rel0 < D && rel0 + P + 7u > D) || (rel0 + P + 7u > total));
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            u32 const x = xa + (u32)i, rel = x - shift;
+            act[i] = INTERIOR ? true : ((x >= xLow) && (rel + 8u <= total) && !(rel < D && rel + 8u > D));
+            u64 v;
+            if (slow) v = act[i] ? zb_ld64u((rel < D ? dbase : fbase) + rel) : 0ull;
+            else {
+                u32 const lo = i ? __funnelshift_r(wrd[0], wrd[1], 8u * (u32)i) : wrd[0];
+                u32 const hi = i ? __funnelshift_r(wrd[1], wrd[2], 8u * (u32)i) : wrd[1];
+                v = ((u64)hi << 32) | lo;
+            }
+            h[i] = zb_hash(v, MLS, 32u);
+            bkt[i] = __umulhi(h[i], N);
+            old[i] = act[i] ? table[bkt[i]] : 0u;
+        }
+    }
+    u32 hitX = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) { dOld[i] = zb_walk_cand(old[i], h[i], xa + (u32)i); if (dOld[i]) hitX = xa + (u32)i; }
+    u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
+    if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
+    u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
+    u32 const step = insStep + ((sWalk - li) >> 7);
+    {   u32 const wmax = __reduce_max_sync(ZB_FULL, hitX);
+        if (wmax && (threadIdx.x & 31u) == 0u) atomicMax(&sLastHit[par], wmax); }
+    u32 const pat = zb_walk_pattern<P>(xa - shift, step);
+    __syncthreads();
+    /* ---- B: insertions ---- */
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        if (act[i] && dOld[i] == 0u && ((pat >> i) & 1u)) atomicMax(&table[bkt[i]], zb_walk_entry(h[i], xa + (u32)i));
+    if (threadIdx.x == 0u) { u32 const a = sLastHit[par], b = sLastHit[par ^ 1u]; if (b > a) sLastHit[par] = b; }
+    __syncthreads();
+    /* ---- C: second look, output ---- */
+    u32 d[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        d[i] = dOld[i];
+        if (act[i] && d[i] == 0u) d[i] = zb_walk_cand(table[bkt[i]], h[i], xa + (u32)i);
+    }
+    if (output && (INTERIOR || xa < xEnd)) {
+        u32 anyFar = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) anyFar |= d[i] >= ZB_FAR ? 1u : 0u;
+        if (anyFar) {
+#pragma unroll
+            for (int i = 0; i < P; i++) if (d[i] >= ZB_FAR) { if (INTERIOR || xa + (u32)i < xEnd) farRow[i] = d[i]; d[i] = ZB_FAR; }
+        }
+        if (P == 4 && (INTERIOR || xa + 4u <= xEnd)) *reinterpret_cast<uint2*>(distRow) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16));
+        else {
+#pragma unroll
+            for (int i = 0; i < P; i++) if (xa + (u32)i < xEnd) distRow[i] = (u16)d[i];
+        }
+    }
 }
 
 /* P consecutive positions per thread, ZB_BATCH / P threads per CTA.  Per batch:
@@ -112,8 +201,6 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     /* walk coordinate x = rel + shift: batch borders (frame positions that are multiples of the batch; dictionary
      * positions count backwards from the frame start) are the multiples of ZB_BATCH in x */
     u32 const shift = (ZB_BATCH - (D % ZB_BATCH)) % ZB_BATCH;
-    /* a frame that is a single batch behind a dictionary image never needs its own insertions later: the image stays
-     * in global memory and the batch's insertions go to a cleared private table (config 5: a million 1 KiB records) */
     const u8* const fbase = src + cd.srcOff - H;                  /* fbase + rel = the byte's address for rel >= D */
     const u8* const dbase = dictEnd - D;                          /* same for rel < D */
 
@@ -123,101 +210,52 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     __syncthreads();
 
     u32 const xEnd = total + shift;
-    u32 x0 = (fromImage ? D : 0u) + shift;                        /* first batch: may start inside a batch (x0 is its border) */
-    x0 &= ~(ZB_BATCH - 1u);
     u32 const xLow = (fromImage ? D : 0u) + shift;                /* first walked coordinate */
+    u32 x0 = xLow & ~(ZB_BATCH - 1u);                             /* border of the first batch */
+    /* interior batches: completely walked, completely in the frame's own bytes, all 8-byte reads inside [.., total) */
+    u32 const xIntLo = ((D + shift) > xLow ? (D + shift) : xLow);
+    u32 const xIntLoB = (xIntLo + ZB_BATCH - 1u) & ~(ZB_BATCH - 1u);
+    u32 const xIntHi = xEnd >= (ZB_BATCH + P + 8u) ? (xEnd - (P + 8u)) & ~(ZB_BATCH - 1u) : 0u;     /* batches [x0, x0 + B) with x0 + B <= xIntHi are interior */
 
-    /* the 11 bytes of a thread's P positions (+7): words realigned to the first position; wrd[] of the NEXT batch is in flight */
+    /* the 11 bytes of a thread's P positions (+7) as three words realigned to its first position */
     u32 wrd[3];
     auto fetch = [&](u32 xb) {
         u32 const xa = xb + P * t;                                /* first coordinate of the thread */
         wrd[0] = wrd[1] = wrd[2] = 0u;
         if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
-        u32 const rel = xa - shift;                               /* may wrap for xa < shift: handled by the slow path's checks */
-        bool const slow = (xa < xLow) || (D != 0u && rel < D && rel + P + 7u > D);
+        u32 const rel = xa - shift;
+        if (xb >= xIntLoB && xb + ZB_BATCH <= xIntHi) {           /* interior: no guards */
+            const u8* const a = fbase + rel;
+            const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
+            u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
+            u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+            wrd[0] = __funnelshift_r(w0, w1, sh); wrd[1] = __funnelshift_r(w1, w2, sh); wrd[2] = __funnelshift_r(w2, w3, sh);
+            return;
+        }
+        bool const slow = (xa < xLow) || (D != 0u && rel < D && rel + P + 7u > D) || (rel + P + 7u > total);
         if (slow) return;                                         /* assembled byte-wise in the batch */
         const u8* const a = (rel < D ? dbase : fbase) + rel;
-        const u8* const lim = (rel < D ? dbase + D : fbase + total);
         const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
         u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-        u32 const w0 = __ldg(p);
-        u32 const w1 = (reinterpret_cast<const u8*>(p + 1) < lim) ? __ldg(p + 1) : 0u;
-        u32 const w2 = (reinterpret_cast<const u8*>(p + 2) < lim) ? __ldg(p + 2) : 0u;
-        u32 const w3 = (sh != 0u && reinterpret_cast<const u8*>(p + 3) < lim) ? __ldg(p + 3) : 0u;
+        u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        u32 const w3 = sh ? __ldg(p + 3) : 0u;                    /* rel + P + 7 <= limit: the fourth word is only touched when it holds a needed byte */
         wrd[0] = __funnelshift_r(w0, w1, sh); wrd[1] = __funnelshift_r(w1, w2, sh); wrd[2] = __funnelshift_r(w2, w3, sh);
     };
     fetch(x0);
     u32 const blockMask = (1u << cd.blockLog) - 1u;
+    u32 dummy = 0;
     for (u32 k = 0; x0 < xEnd; k++, x0 += ZB_BATCH) {
         u32 const par = k & 1u;
         u32 const xa = x0 + P * t;
-        u32 h[P], bkt[P], old[P], dOld[P];
-        bool act[P];
-        /* ---- A ---- */
-        {   u32 const rel0 = xa - shift;
-            bool const slow = (xa < xLow) || (D != 0u && rel0 < D && rel0 + P + 7u > D);
-#pragma unroll
-            for (int i = 0; i < P; i++) {
-                u32 const x = xa + (u32)i, rel = x - shift;
-                act[i] = (x >= xLow) && (rel + 8u <= total) && !(rel < D && rel + 8u > D);
-                u64 v;
-                if (slow) v = act[i] ? zb_ld64u((rel < D ? dbase : fbase) + rel) : 0ull;
-                else {
-                    u32 const lo = i ? __funnelshift_r(wrd[0], wrd[1], 8u * (u32)i) : wrd[0];
-                    u32 const hi = i ? __funnelshift_r(wrd[1], wrd[2], 8u * (u32)i) : wrd[1];
-                    v = ((u64)hi << 32) | lo;
-                }
-                h[i] = zb_hash(v, MLS, 32u);
-                bkt[i] = __umulhi(h[i], N);
-                old[i] = act[i] ? table[bkt[i]] : 0u;
-            }
-        }
-        u32 hitX = 0;
-#pragma unroll
-        for (int i = 0; i < P; i++) { dOld[i] = zb_walk_cand(old[i], h[i], xa + (u32)i); if (dOld[i]) hitX = xa + (u32)i; }
-        u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
-        if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
-        u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
-        u32 const step = insStep + ((sWalk - li) >> 7);
-        {   u32 const wmax = __reduce_max_sync(ZB_FULL, hitX);
-            if (wmax && (t & 31u) == 0u) atomicMax(&sLastHit[par], wmax); }
-        fetch(x0 + ZB_BATCH);                                     /* next batch's bytes: in flight across the barriers */
-        /* insertion pattern ((rel) % step) < 2 for P consecutive positions: one division per thread */
-        u32 r0;
-        {   u32 const rel0 = xa - shift;
-            u32 const q = (u32)(__fdividef((float)rel0, (float)step));
-            int r = (int)rel0 - (int)(q * step);
-            if (r < 0) r += (int)step; else if (r >= (int)step) r -= (int)step;
-            r0 = (u32)r; }
-        __syncthreads();
-        /* ---- B ---- */
-#pragma unroll
-        for (int i = 0; i < P; i++) {
-            u32 ri = r0 + (u32)i; if (ri >= step) ri -= step; if (ri >= step) ri -= step;
-            bool const ins = act[i] && dOld[i] == 0u && (ri < 2u);
-            if (ins) atomicMax(&table[bkt[i]], zb_walk_entry(h[i], xa + (u32)i));
-        }
-        if (t == 0u) { u32 const a = sLastHit[par], b = sLastHit[par ^ 1u]; if (b > a) sLastHit[par] = b; }
-        __syncthreads();
-        /* ---- C ---- */
-        u32 d[P];
-#pragma unroll
-        for (int i = 0; i < P; i++) {
-            d[i] = dOld[i];
-            if (act[i] && d[i] == 0u) d[i] = zb_walk_cand(table[bkt[i]], h[i], xa + (u32)i);
-        }
-        if (!buildImage && xa >= H + shift && xa < xEnd) {
-            u32 const qb = xa - shift - H;                        /* offset in the chunk: a multiple of P */
-            size_t const idx = (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask);
-            u32 o[P];
-#pragma unroll
-            for (int i = 0; i < P; i++) { o[i] = d[i] >= ZB_FAR ? ZB_FAR : d[i]; if (d[i] >= ZB_FAR && xa + (u32)i < xEnd) far[idx + i] = d[i]; }
-            if (P == 4 && xa + 4u <= xEnd) *reinterpret_cast<uint2*>(dist + idx) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-            else {
-#pragma unroll
-                for (int i = 0; i < P; i++) if (xa + (u32)i < xEnd) dist[idx + i] = (u16)o[i];
-            }
-        }
+        u32 cur[3] = { wrd[0], wrd[1], wrd[2] };
+        fetch(x0 + ZB_BATCH);                                     /* next batch's bytes: in flight across this batch's barriers */
+        bool const output = !buildImage && x0 >= H + shift;       /* H + shift is a batch border: the whole batch lies in the history or in the chunk */
+        u32 const qb = xa - shift - H;                            /* offset in the chunk (a multiple of P) when output */
+        size_t const idx = output ? (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask) : 0;
+        if (x0 >= xIntLoB && x0 + ZB_BATCH <= xIntHi)
+            zb_walk_batch<MLS, P, true>(table, sLastHit, par, xa, x0, cur, N, insStep, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx, dummy);
+        else
+            zb_walk_batch<MLS, P, false>(table, sLastHit, par, xa, x0, cur, N, insStep, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx, dummy);
     }
     if (buildImage) { __syncthreads(); for (u32 i = t; i < N; i += THREADS) imageOut[i] = table[i]; }
 }

@@ -161,7 +161,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             for (u32 o = 16; o > 0; o >>= 1) mostFrequent = ::max(mostFrequent, __shfl_xor_sync(ZB_FULL, mostFrequent, o));
             u32 const defLog = st == 1 ? 5u : 6u;
             bool const defAllowed = st == 1 ? (max <= DefaultMaxOff) : true;
-            u32 const prevRepeat = (de != nullptr && (bd.flags & ZB_FLAG_DICT) && de->present) ? de->fseRepeat[st] : 0u;
+            u32 const prevRepeat = (de != nullptr && (bd.flags & ZB_FLAG_FIRST) && de->present) ? de->fseRepeat[st] : 0u;
             u32 const type = zbd_selectEncodingType(mostFrequent, nbSeq, defLog, defAllowed, prm.strategy, prevRepeat);
             if (lane == 0) { w->type = type; w->err = 0; w->ncSize = 0; }
             __syncwarp();

@@ -2,8 +2,9 @@
 
 A zstd stream may be any concatenation of frames (lib/zstd.h:160-162; precedent contrib/pzstd), so
 N ranks compress contiguous, equal-byte partitions of the frame list with no data-path exchange;
-the only collective is the final gather of the variable-length compressed buffers:
-all_gather(sizes) then gather of payloads padded to the largest size (NCCL on GPUs, gloo in CPU tests).
+the only exchange is the final gather of the variable-length compressed buffers: all_gather(sizes), then
+point-to-point transfers of exactly each rank's bytes into their final place on the destination rank
+(NCCL on GPUs, gloo in CPU tests).
 """
 from __future__ import annotations
 
@@ -33,23 +34,53 @@ def split_into_frames(total_size: int, frame_size: int) -> List[Tuple[int, int]]
     return [(o, min(frame_size, total_size - o)) for o in range(0, max(total_size, 1), frame_size)] if total_size else [(0, 0)]
 
 
-def gather_compressed(local: torch.Tensor, dst: int = 0, group=None):
-    """Gather variable-length uint8 tensors to rank `dst` in rank order.
-    Returns (list_of_sizes, concatenated tensor on dst or None elsewhere)."""
+def _all_sizes(n: int, device, group=None) -> List[int]:
+    """every rank's byte count, in rank order (one tiny all_gather + one host read)"""
+    ws = dist.get_world_size(group)
+    mine = torch.tensor([n], dtype=torch.int64, device=device)
+    allv = torch.empty(ws, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    return [int(v) for v in allv.tolist()]
+
+
+def gather_compressed(local: torch.Tensor, dst: int = 0, group=None, out: torch.Tensor = None, async_op: bool = False):
+    """Gather variable-length uint8 tensors to rank `dst` in rank order (what contrib/pzstd's writer thread does with
+    the frames of its workers, Pzstd.cpp:335): sizes by one all_gather, then every other rank SENDS exactly its bytes
+    and `dst` RECEIVES each payload straight at its final offset of one buffer — no padding, no concatenation copy;
+    all transfers are one batched group (NCCL: one grouped launch over NVLink, gloo in the CPU tests).
+    out: destination buffer on `dst` (>= sum of sizes); when `local` already is out[:n] the own part is not copied.
+    Returns (sizes, gathered tensor or None, works): with async_op=True the transfers may still be in flight, call
+    .wait() on every work (zstd_b200.sharding.wait_all) before touching `local` / the gathered bytes."""
     ws = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    size = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(size) for _ in range(ws)]
-    dist.all_gather(sizes, size, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(sizes) if sizes else 0
-    padded = torch.zeros(mx, dtype=torch.uint8, device=local.device)
-    padded[: local.numel()] = local
-    bufs = [torch.empty(mx, dtype=torch.uint8, device=local.device) for _ in range(ws)] if rank == dst else None
-    dist.gather(padded, bufs, dst=dst, group=group)
-    if rank != dst:
-        return sizes, None
-    return sizes, torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+    sizes = _all_sizes(local.numel(), local.device, group)
+    ops, gathered = [], None
+    if rank == dst:
+        total = sum(sizes)
+        if out is None:
+            out = torch.empty(total, dtype=torch.uint8, device=local.device)
+        assert out.numel() >= total
+        off = 0
+        for r in range(ws):
+            if r == rank:
+                if sizes[r] and out.data_ptr() + off != local.data_ptr():
+                    out[off:off + sizes[r]].copy_(local)
+            elif sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, out[off:off + sizes[r]], r, group))
+            off += sizes[r]
+        gathered = out[:total]
+    elif local.numel():
+        ops.append(dist.P2POp(dist.isend, local, dst, group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if not async_op:
+        wait_all(works)
+        works = []
+    return sizes, gathered, works
+
+
+def wait_all(works) -> None:
+    for w in works:
+        w.wait()
 
 
 def gather_frame_sizes(c_sizes: Sequence[int], d_sizes: Sequence[int], dst: int = 0, group=None):
