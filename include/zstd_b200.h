@@ -102,7 +102,35 @@ ZSTDB200_API int         ZSTD_defaultCLevel(void);
 ZSTDB200_API unsigned    ZSTD_versionNumber(void);
 ZSTDB200_API const char* ZSTD_versionString(void);
 
+/* lib/zstd.h:170-299 — decompression.  Every frame the format allows is accepted: this library's
+ * own and the reference encoder's at any level, concatenated frames, skippable frames, frames without a content size,
+ * window sizes up to 128 MiB (the reference decoder's default limit, ZSTD_WINDOWLOG_LIMIT_DEFAULT = 27).  Not yet:
+ * dictionaries (a frame that needs one fails with corruption_detected when it reaches into the missing history).
+ * The content checksum of a frame that carries one is verified (host buffers; checksum_wrong = 22).
+ * All decoding work is done by CUDA kernels (zb_decode.cu); no CPU fallback. */
+typedef struct ZSTD_DCtx_s ZSTD_DCtx;
+ZSTDB200_API size_t     ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize);
+ZSTDB200_API ZSTD_DCtx* ZSTD_createDCtx(void);
+ZSTDB200_API size_t     ZSTD_freeDCtx(ZSTD_DCtx* dctx);                                    /* accepts NULL */
+ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+/* lib/zstd.h:195-227 — header readers (host code).  ZSTD_CONTENTSIZE_UNKNOWN = (0ULL - 1), ZSTD_CONTENTSIZE_ERROR = (0ULL - 2). */
+ZSTDB200_API unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
+ZSTDB200_API size_t     ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
+
 /* =====================  2. B200 extensions (no reference counterpart)  ===================== */
+
+/* Decompress frames whose bytes are in device memory into device memory.  The block headers are followed by one device
+ * thread (a chain of dependent reads: about 1 us per block), everything else is block-parallel.  Content checksums are
+ * not verified on this path.  `stream`: as for ZSTDB200_compressDevice.  Returns the decompressed size. */
+ZSTDB200_API size_t ZSTDB200_decompressDevice(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream);
+typedef struct {
+    float kernel_ms;         /* literals kernel start -> execute kernel end */
+    float literals_ms, sequences_ms, execute_ms;
+    unsigned launches, nbBlocks, nbFrames;
+    size_t h2d_bytes, d2h_bytes;
+} ZSTDB200_dstats;
+ZSTDB200_API void ZSTDB200_getLastDStats(const ZSTD_DCtx* dctx, ZSTDB200_dstats* out);
+
 
 /* Compress one frame whose input and output already live in device memory (HBM).  The call returns when the frame is
  * complete (it synchronises to read the size).

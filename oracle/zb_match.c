@@ -14,17 +14,17 @@
  *     then lives through all blocks of the chunk, as the reference's table lives through a frame;
  *   - candidate lookup (phase 1, "walk") is decoupled from the greedy selection (phase 2, "parse"): the walk
  *     visits every position in BATCHES of ZB_BATCH consecutive positions.  All positions of a batch first read
- *     their bucket, then the batch's insertions are applied (highest position wins a bucket), then a position
- *     whose bucket now holds an insertion of the same batch that lies below it takes that one instead.  A batch
- *     is what one CTA does between two barriers; batches are sequential;
- *   - which positions a batch inserts depends on the data, not on the parse: a position whose candidate
- *     continues the candidate of its predecessor (same distance) lies inside a repeated region — the reference
- *     does not insert match interiors either (zstd_fast.c:403-408 inserts 2 positions per match) — and is
- *     skipped; the others follow the pattern (pos % step) < 2 where step grows by one per 128 bytes walked
- *     since the last such interior position (the reference's acceleration, :234,:342-347, which makes it leave
- *     the table alone inside incompressible regions), rounded down to a power of two;
- *   - table entries are (position + 1) << tagBits | tag: positions relative to the start of the chunk's
- *     history (21 bits: primeBytes + chunk <= 2 MiB), tag = the next hash bits; a candidate whose tag differs
+ *     their bucket, then the batch's insertions are applied (the LOWEST position wins a bucket), then a position
+ *     that found nothing looks again: the batch's insertion into its bucket may lie below it.  A batch is what
+ *     one CTA does between two barriers; batches are sequential;
+ *   - which positions a batch inserts depends on the data, not on the parse: a position that found a candidate
+ *     lies inside repeated content — the reference does not insert match interiors either (zstd_fast.c:403-408
+ *     inserts 2 positions per match) — and is skipped; the others follow the pattern (pos % step) < 2 where
+ *     step = insStep + one per 128 positions walked since the end of the last batch that saw a candidate hit
+ *     (the reference's acceleration, :234,:342-347, which makes it leave the table alone inside incompressible
+ *     regions);
+ *   - table entries are (key + 1) << tagBits | tag: key = the position relative to the start of the chunk's
+ *     history with its offset inside the batch reversed, tag = the low hash bits; a candidate whose tag differs
  *     is dropped by the walk, so the parse never loads it;
  *   - encoder repcodes start invalid in every parse segment; entropy tables are fresh per block.
  */
@@ -63,6 +63,7 @@ static size_t zb_count(const u8* ip, const u8* match, const u8* iend)
 
 /* experiment knobs (tools/exp_size.py only; all zero = what the product implements) */
 zbo_tunables zbo_tun = { 0, 0, 0, 0, 0, 0, 0, 0 };
+unsigned long long zbo_stat_hits = 0, zbo_stat_far = 0;   /* diagnostics of the last walks (tools/ only) */
 
 void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
 {
@@ -144,8 +145,9 @@ static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t 
         step = insStep + (u32)((s - lastHit) >> 7);
         for (i = 0; i < n; i++) {
             size_t const q = s + i;
-            ins[i] = act[i] && dOld[i] == 0 && ((q - low) % step) < 2;
-            if (dOld[i]) lastHit = q;
+            /* spare bit 0 (experiments only, tools/exp_size.py): also refresh a bucket whose candidate was a hit */
+            ins[i] = act[i] && (dOld[i] == 0 || (zbo_tun.spare & 1u)) && ((q - low) % step) < 2;
+            if (dOld[i]) lastHit = e;             /* the acceleration restarts behind a batch that saw a hit */
         }
         for (i = 0; i < n; i++) if (ins[i]) {
             u32 const x = (u32)(s + i - low + shift);
@@ -158,7 +160,7 @@ static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t 
             size_t const q = s + i;
             u32 d = dOld[i];
             if (act[i] && d == 0) d = CAND(table[BKT(hh[i])], hh[i], (u32)(q - low + shift));
-            if (q >= outStart) dist[q - outStart] = d;
+            if (q >= outStart) { dist[q - outStart] = d; if (d) zbo_stat_hits++; if (d >= 0xFFFFu) zbo_stat_far++; }
         }
         s = e;
     }

@@ -1,0 +1,104 @@
+"""CPU tests of the decompressor's format-level code (zstd_b200/csrc/zb_decode_core.cuh): tests/host_decode.cpp drives the
+same host+device functions the CUDA kernels call, block after block, and must reproduce the input of frames written by
+the reference encoder (every level, so Huffman treeless / FSE repeat modes, RLE tables, long offsets ...), by this repo's
+oracle, and of the reference's own golden decompression vectors (tests/golden/decompression*, copied from
+/root/reference/tests/golden-decompression*)."""
+import ctypes
+import glob
+import os
+import subprocess
+
+import pytest
+
+import zref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libzb_hostdecode.so")
+needs_ref = pytest.mark.skipif(not zref.have_ref(), reason="reference library not built")
+
+
+@pytest.fixture(scope="module")
+def H():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-Werror", "-Wno-unused-function", "-x", "c++",
+                           "-o", SO, os.path.join(HERE, "host_decode.cpp")])
+    h = ctypes.CDLL(SO)
+    h.zbh_decompress.restype = ctypes.c_size_t
+    h.zbh_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    return h
+
+
+def dec(H, frame, cap):
+    out = ctypes.create_string_buffer(cap + 16)
+    r = H.zbh_decompress(out, cap, frame, len(frame))
+    if r > (1 << 63):
+        return ("ERR", (1 << 64) - r)
+    return out.raw[:r]
+
+
+INPUTS = {
+    "empty": b"", "one": b"x", "tiny": b"hello hello hello hello", "zeros": bytes(500_000), "rand": zref.random_bytes(200_000, 1),
+    "period3": b"abc" * 50_000, "syn": zref.synthetic(300_000, 9), "syn-p90": zref.synthetic(1 << 20, 6, 0.9),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("level", [1, 3, -3, 5, 9, 15, 19])
+@pytest.mark.parametrize("name", sorted(INPUTS))
+def test_reference_frames(H, name, level):
+    data = INPUTS[name]
+    assert dec(H, zref.ref_compress(data, level), len(data)) == data
+
+
+@pytest.mark.parametrize("level", [1, 3, -3])
+@pytest.mark.parametrize("name", sorted(INPUTS))
+def test_oracle_frames(H, name, level):
+    data = INPUTS[name]
+    assert dec(H, zref.oracle_compress(data, level), len(data)) == data
+
+
+@needs_ref
+@pytest.mark.skipif(not zref.have_datagen(), reason="reference datagen binary not built")
+@pytest.mark.parametrize("p,level", [(50, 1), (90, 3), (30, -3), (50, 7), (90, 19)])
+def test_datagen_multi_block(H, p, level):
+    """8 MiB: 64 blocks, tables reused across blocks (treeless literals, repeat-mode sequence tables)"""
+    data = zref.datagen(8 << 20, p)
+    assert dec(H, zref.ref_compress(data, level), len(data)) == data
+
+
+@needs_ref
+def test_golden_inputs_all_levels(H):
+    for g in ("large-literal-and-match-lengths", "http", "PR-3517-block-splitter-corruption-test", "huffman-compressed-larger"):
+        data = zref.golden_input(g)
+        for level in (1, 3, 6, 12, 19, -5):
+            assert dec(H, zref.ref_compress(data, level), len(data)) == data, (g, level)
+
+
+@needs_ref
+def test_concatenated_and_skippable_frames(H):
+    a, b = b"abc" * 1000, zref.synthetic(300_000, 3)
+    skip = bytes([0x53, 0x2A, 0x4D, 0x18, 5, 0, 0, 0]) + b"xxxxx"
+    stream = zref.ref_compress(a, 3) + skip + zref.ref_compress(b, 1) + skip
+    assert dec(H, stream, len(a) + len(b)) == a + b
+
+
+def test_reference_golden_decompression_vectors(H):
+    for f in sorted(glob.glob(os.path.join(zref.GOLDEN, "decompression", "*.zst"))):
+        frame = open(f, "rb").read()
+        got = dec(H, frame, 1 << 21)
+        assert not isinstance(got, tuple), (f, got)
+        if zref.have_ref():
+            assert got == zref.ref_decompress(frame, 1 << 21), f
+    for f in sorted(glob.glob(os.path.join(zref.GOLDEN, "decompression-errors", "*.zst"))):
+        got = dec(H, open(f, "rb").read(), 1 << 21)
+        assert got == ("ERR", 20), (f, got)                     # corruption_detected, as the reference reports
+
+
+@needs_ref
+def test_truncated_and_garbage(H):
+    data = zref.synthetic(100_000, 5)
+    frame = zref.ref_compress(data, 3)
+    assert dec(H, frame[:-1], len(data))[0] == "ERR"
+    assert dec(H, frame[: len(frame) // 2], len(data))[0] == "ERR"
+    assert dec(H, b"\x00\x01\x02\x03\x04\x05\x06\x07", 100) == ("ERR", 10)          # prefix_unknown
+    assert dec(H, frame, len(data) - 1) == ("ERR", 70)                              # dstSize_tooSmall

@@ -8,7 +8,7 @@ name=$1; file=$2; flags=$3
 mkdir -p ../variants /tmp/zbv_$name
 make -s all
 objs=""
-for f in zb_api zb_dict zb_match zb_literals zb_sequences zb_stitch; do
+for f in zb_api zb_dict zb_match zb_literals zb_sequences zb_stitch zb_decode; do
   if [ "$f.cu" == "$file" ]; then
     nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v $flags -c $f.cu -o /tmp/zbv_$name/$f.o 2> /tmp/zbv_$name/$f.log
     grep "Used\|spill" /tmp/zbv_$name/$f.log | head -4 || true

@@ -38,6 +38,11 @@ class Stats(ctypes.Structure):
                 ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
 
 
+class DStats(ctypes.Structure):
+    _fields_ = [("kernel_ms", ctypes.c_float), ("literals_ms", ctypes.c_float), ("sequences_ms", ctypes.c_float), ("execute_ms", ctypes.c_float),
+                ("launches", ctypes.c_uint), ("nbBlocks", ctypes.c_uint), ("nbFrames", ctypes.c_uint), ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
+
+
 def lib() -> ctypes.CDLL:
     """Load libzstd_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
     global _lib
@@ -106,6 +111,23 @@ def lib() -> ctypes.CDLL:
     L.ZSTD_compressStream2.argtypes = [_vp, _vp, _vp, ctypes.c_int]
     L.ZSTDB200_compressFrames_usingCDict.restype = _sz
     L.ZSTDB200_compressFrames_usingCDict.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_int, _vp]
+    if hasattr(L, "ZSTD_createDCtx"):
+        L.ZSTD_createDCtx.restype = _vp
+        L.ZSTD_createDCtx.argtypes = []
+        L.ZSTD_freeDCtx.restype = _sz
+        L.ZSTD_freeDCtx.argtypes = [_vp]
+        L.ZSTD_decompressDCtx.restype = _sz
+        L.ZSTD_decompressDCtx.argtypes = [_vp, _vp, _sz, _vp, _sz]
+        L.ZSTD_decompress.restype = _sz
+        L.ZSTD_decompress.argtypes = [_vp, _sz, _vp, _sz]
+        L.ZSTD_getFrameContentSize.restype = ctypes.c_ulonglong
+        L.ZSTD_getFrameContentSize.argtypes = [_vp, _sz]
+        L.ZSTD_findFrameCompressedSize.restype = _sz
+        L.ZSTD_findFrameCompressedSize.argtypes = [_vp, _sz]
+        L.ZSTDB200_decompressDevice.restype = _sz
+        L.ZSTDB200_decompressDevice.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp]
+        L.ZSTDB200_getLastDStats.restype = None
+        L.ZSTDB200_getLastDStats.argtypes = [_vp, ctypes.POINTER(DStats)]
     _lib = L
     return L
 
@@ -262,6 +284,60 @@ class ZSTD_CCtx:
         s = Stats()
         lib().ZSTDB200_getLastStats(self._h, ctypes.byref(s))
         return s
+
+
+class ZSTD_DCtx:
+    """Reusable decompression context (lib/zstd.h:289-299): owns the device workspace and a stream."""
+
+    def __init__(self, device: Optional[int] = None):
+        L = lib()
+        if device is not None:
+            L.ZSTDB200_setDevice(int(device))
+        self._h = L.ZSTD_createDCtx()
+        if not self._h:
+            raise MemoryError("ZSTD_createDCtx failed")
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ZSTD_freeDCtx(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter teardown
+            pass
+
+    def decompress(self, frames, max_size: Optional[int] = None) -> bytes:
+        """ZSTD_decompressDCtx: one or more concatenated frames (host buffers).  max_size defaults to the content size
+        the first frame's header states."""
+        p, n, keep = _buf(frames)
+        if max_size is None:
+            cs = lib().ZSTD_getFrameContentSize(p, n)
+            if cs >= (1 << 64) - 2:
+                raise ZstdError(72, "content size unknown: pass max_size")
+            max_size = cs
+        dst = ctypes.create_string_buffer(max(max_size, 1))
+        r = _check(lib().ZSTD_decompressDCtx(self._h, dst, max_size, p, n))
+        return dst.raw[:r]
+
+    def decompress_device(self, d_dst: int, dst_capacity: int, d_src: int, src_size: int, stream: int = 0) -> int:
+        """Frames in device memory -> device memory (ints, e.g. torch.Tensor.data_ptr()).  Returns the decompressed size."""
+        return _check(lib().ZSTDB200_decompressDevice(self._h, d_dst, dst_capacity, d_src, src_size, stream))
+
+    def stats(self) -> DStats:
+        s = DStats()
+        lib().ZSTDB200_getLastDStats(self._h, ctypes.byref(s))
+        return s
+
+
+def ZSTD_decompress(frames, max_size: Optional[int] = None) -> bytes:
+    """lib/zstd.h:170 — temporary context, host buffers."""
+    d = ZSTD_DCtx()
+    try:
+        return d.decompress(frames, max_size)
+    finally:
+        d.close()
 
 
 def ZSTD_compress(src, level: int = 3) -> bytes:

@@ -171,6 +171,7 @@ struct ZSTD_CCtx_s {
 static double zb_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 
 extern "C" int ZSTDB200_setDevice(int device) { g_device.store(device); return 0; }
+extern "C" int zb_boundDevice(void) { return g_device.load(); }          /* for the decompression contexts (zb_decode.cu) */
 extern "C" int ZSTDB200_deviceAvailable(void)
 {
     int n = 0;

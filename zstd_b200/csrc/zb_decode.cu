@@ -1,0 +1,589 @@
+/* zb_decode.cu — GPU decompression of zstd frames: the other half of the block pipeline.
+ *
+ * Replaces, with a block-parallel formulation, what the reference does serially per frame:
+ *   ZSTD_decompress / ZSTD_decompressDCtx / ZSTD_decompressFrame  (/root/reference/lib/decompress/zstd_decompress.c:1011-1124)
+ *   ZSTD_decodeLiteralsBlock, ZSTD_decodeSeqHeaders, ZSTD_decompressSequences_body, ZSTD_execSequence
+ *                                                     (lib/decompress/zstd_decompress_block.c:343, :695, :1615, :1012)
+ *   HUF_decompress4X1 / HUF_readDTableX1              (lib/decompress/huf_decompress.c:602, :383)
+ * Any frame the format allows is accepted (this library's own and the reference encoder's, every level), window
+ * sizes up to 128 MiB, no dictionaries yet.  The format-level functions are in zb_decode_core.cuh.
+ *
+ *   D0  walker    frames and blocks of the input: block headers, section headers, which earlier block a treeless /
+ *                 repeat-mode block takes its tables from.  Host code for host buffers; one device thread per call
+ *                 for device buffers (a chain of dependent 3-byte reads).
+ *   D1  literals  one warp per block: raw / RLE copied, Huffman tree description -> decoding table in shared memory
+ *                 (a block that reuses a table re-reads the description of the block that defined it: no dependency
+ *                 between CTAs), the 1 or 4 streams decoded by one lane each.
+ *   D2  sequences one warp per block: the three FSE decoding tables by three lanes, the interleaved bitstream by one
+ *                 lane; emits packed (offset code, literal length, match length), the block's regenerated size and
+ *                 its repcode history as a FUNCTION of the history at its start.
+ *   D3  scan      output offset of every block (prefix sum of regenerated sizes) and the repcode history at every
+ *                 block's start (composition of the blocks' functions along each frame).
+ *   D4  execute   one warp per block, in ticket order: literal and match copies by 32 lanes.  A match that reaches into
+ *                 earlier blocks waits for the producer's progress counter, so blocks of a frame run concurrently, a
+ *                 typical offset behind each other.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/zstd_b200.h"
+#include "zb_common.h"
+#include "zb_decode_core.cuh"
+
+#define ZB_FULL 0xFFFFFFFFu
+#define ZBD_WARPS 4                    /* blocks per CTA in D1 / D2 / D4 */
+
+/* per block, written by D2 and D3 */
+typedef struct {
+    u32 regen;             /* regenerated size of the block */
+    u32 err;               /* 0 or a ZSTD error code */
+    u32 sumLL;
+    u32 pad;
+    ZbdRep transfer;       /* history at the block's end as a function of the history at its start */
+    ZbdRep start;          /* history at the block's start (D3) */
+    u64 dstOff;            /* first output byte of the block (D3) */
+    u64 frameOff;          /* first output byte of its frame (D3) */
+} ZbdBlockOut;
+
+/* ------------------------------------------------------------------------------------------------ D0 on the device */
+__global__ void zbd_walk_kernel(const u8* __restrict__ src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFrame* frames, u32 capF, u64* res)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u32 nb = 0, nf = 0; u64 lit = 0, seq = 0;
+    u32 const e = zbd_walk(src, size, blocks, capB, frames, capF, &nb, &nf, &lit, &seq);
+    res[0] = e; res[1] = nb; res[2] = nf; res[3] = lit; res[4] = seq;
+}
+
+/* ------------------------------------------------------------------------------------------------ D1 literals */
+struct ZbdLitWork {
+    u16 table[1u << ZBD_HUF_LOG_MAX];
+    u16 start[256];
+    u8  weights[256];
+    u32 fse[64];
+    short norm[16];
+    u16 next[16];
+    u32 nbSym, log, used;
+};
+
+__global__ void __launch_bounds__(32 * ZBD_WARPS)
+zbd_literals_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u8* __restrict__ lits, ZbdBlockOut* __restrict__ bout)
+{
+    __shared__ ZbdLitWork work[ZBD_WARPS];
+    u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    u32 const bi = blockIdx.x * ZBD_WARPS + w;
+    if (bi >= nbBlocks) return;
+    ZbdBlock const b = blocks[bi];
+    if (lane == 0) bout[bi].err = 0;
+    if (b.type != ZB_BT_COMPRESSED) return;
+    ZbdLitWork& wk = work[w];
+    const u8* const c = src + b.srcOff;
+    u8* const out = lits + b.litPos;
+    if (b.litType == 0u) { for (u32 i = lane; i < b.litRegen; i += 32u) out[i] = c[b.litHdr + i]; return; }
+    if (b.litType == 1u) { u8 const v = c[b.litHdr]; for (u32 i = lane; i < b.litRegen; i += 32u) out[i] = v; return; }
+    /* the tree description of the block that defined the table (this block itself unless treeless) */
+    ZbdBlock const sb = blocks[b.hufSrc];
+    if (lane == 0) {
+        u32 nbSym = 0, log = 0;
+        u32 const used = zbd_readHufWeights(wk.weights, &nbSym, &log, src + sb.srcOff + sb.litHdr, sb.litComp, wk.fse, wk.norm, wk.next);
+        if (used) zbd_hufStarts(wk.start, wk.weights, nbSym, log);
+        wk.nbSym = nbSym; wk.log = log; wk.used = used;
+    }
+    __syncwarp();
+    u32 const used = wk.used, log = wk.log, nbSym = wk.nbSym;
+    if (!used) { if (lane == 0) bout[bi].err = ZBD_CORRUPT; return; }
+    for (u32 s = 0; s < nbSym; s++) zbd_hufFill(wk.table, s, wk.start[s], wk.weights[s], log, lane, 32u);
+    __syncwarp();
+    u32 const desc = b.litType == 3u ? 0u : used;                  /* treeless: the streams follow the header directly */
+    u32 err = 0;
+    if (desc > b.litComp) err = ZBD_CORRUPT;
+    const u8* const s = c + b.litHdr + desc;
+    u32 const total = b.litComp - desc;
+    if (!err) {
+        if (b.litStreams == 1u) { if (lane == 0) err = zbd_hufDecodeStream(out, b.litRegen, s, total, wk.table, log); }
+        else if (total < 6u) err = ZBD_CORRUPT;
+        else {
+            u32 const s1 = zbd_le(s, 2), s2 = zbd_le(s + 2, 2), s3 = zbd_le(s + 4, 2);
+            u32 const seg = (b.litRegen + 3u) / 4u;
+            if (6u + s1 + s2 + s3 > total || 3u * seg > b.litRegen) err = ZBD_CORRUPT;
+            else if (lane < 4u) {
+                u32 const off = 6u + (lane > 0u ? s1 : 0u) + (lane > 1u ? s2 : 0u) + (lane > 2u ? s3 : 0u);
+                u32 const sz = lane == 0u ? s1 : (lane == 1u ? s2 : (lane == 2u ? s3 : total - 6u - s1 - s2 - s3));
+                u32 const cnt = lane < 3u ? seg : b.litRegen - 3u * seg;
+                err = zbd_hufDecodeStream(out + lane * seg, cnt, s + off, sz, wk.table, log);
+            }
+        }
+    }
+    err = __reduce_max_sync(ZB_FULL, err);
+    if (err && lane == 0) bout[bi].err = err;
+}
+
+/* ------------------------------------------------------------------------------------------------ D2 sequences */
+struct ZbdSeqWork {
+    u32 table[3][512];     /* LL (<= 512 cells), OF (<= 256), ML (<= 512) */
+    short norm[3][64];
+    u16 next[3][64];
+    u32 log[3], err[3];
+    u32 desc[3], bitstream, locErr;
+};
+__device__ __constant__ u32 c_maxSym[3] = { ZBD_LL_MAXSYM, ZBD_OF_MAXSYM, ZBD_ML_MAXSYM };
+__device__ __constant__ u32 c_maxLog[3] = { ZBD_LL_LOG_MAX, ZBD_OF_LOG_MAX, ZBD_ML_LOG_MAX };
+
+__global__ void __launch_bounds__(32 * ZBD_WARPS)
+zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout)
+{
+    __shared__ ZbdSeqWork work[ZBD_WARPS];
+    u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    u32 const bi = blockIdx.x * ZBD_WARPS + w;
+    if (bi >= nbBlocks) return;
+    ZbdBlock const b = blocks[bi];
+    ZbdSeqWork& wk = work[w];
+    ZbdRep ident; ident.r[0] = ZBD_SYM(0u, 0u); ident.r[1] = ZBD_SYM(1u, 0u); ident.r[2] = ZBD_SYM(2u, 0u);
+    if (b.type != ZB_BT_COMPRESSED || b.nbSeq == 0u) {
+        if (lane == 0) { ZbdBlockOut& o = bout[bi]; o.regen = b.type == ZB_BT_COMPRESSED ? b.litRegen : b.rawSize; o.sumLL = 0; o.transfer = ident; }
+        return;
+    }
+    /* three lanes: one decoding table each, from the section that defined it */
+    if (lane < 3u) {
+        u32 const st = lane;
+        u32 e = 0, log = 0;
+        if (b.eff[st] == 0u) {
+            log = st == 0u ? ZBD_LL_DEFAULT_LOG : (st == 1u ? ZBD_OF_DEFAULT_LOG : ZBD_ML_DEFAULT_LOG);
+            u32 const ms = st == 1u ? ZBD_OF_DEFAULT_MAXSYM : c_maxSym[st];
+            for (u32 s = 0; s <= ms; s++) wk.norm[st][s] = zbd_defaultNorm(st, s);
+            zbd_buildFseTable(wk.table[st], wk.norm[st], ms, log, wk.next[st]);
+        } else {
+            ZbdBlock const sb = blocks[b.fseSrc[st]];
+            const u8* const sec = src + sb.srcOff + sb.seqOff;
+            u32 const avail = sb.cSize - sb.seqOff;
+            u32 desc[3], bitstream;
+            if (zbd_locateDescriptions(&sb, sec, avail, desc, &bitstream, wk.norm[st])) e = ZBD_CORRUPT;
+            else if (b.eff[st] == 1u) {
+                u32 const sym = sec[desc[st]];
+                if (sym > c_maxSym[st]) e = ZBD_CORRUPT; else zbd_buildFseTableRle(wk.table[st], sym);
+            } else {
+                u32 ms = 0;
+                if (!zbd_readNCount(wk.norm[st], &ms, &log, c_maxSym[st], c_maxLog[st], sec + desc[st], avail - desc[st])) e = ZBD_CORRUPT;
+                else zbd_buildFseTable(wk.table[st], wk.norm[st], ms, log, wk.next[st]);
+            }
+        }
+        wk.log[st] = log; wk.err[st] = e;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        ZbdBlockOut& o = bout[bi];
+        u32 e = wk.err[0] | wk.err[1] | wk.err[2];
+        u32 sumLL = 0, sumML = 0; ZbdRep tr = ident;
+        if (!e) {
+            const u8* const sec = src + b.srcOff + b.seqOff;
+            u32 const avail = b.cSize - b.seqOff;
+            u32 desc[3], bitstream;
+            if (zbd_locateDescriptions(&b, sec, avail, desc, &bitstream, wk.norm[0])) e = ZBD_CORRUPT;
+            else e = zbd_decodeSequences(seqs + b.seqPos, b.nbSeq, sec + bitstream, avail - bitstream, wk.table[0], wk.log[0], wk.table[1], wk.log[1],
+                                         wk.table[2], wk.log[2], &sumLL, &sumML, &tr);
+            if (!e && (sumLL > b.litRegen || b.litRegen + sumML > ZB_BLOCK_MAX)) e = ZBD_CORRUPT;
+        }
+        o.regen = e ? 0u : b.litRegen + sumML; o.sumLL = sumLL; o.transfer = tr;
+        if (e) o.err = e;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ D3 scan
+ * One CTA.  Output offsets: prefix sum over all blocks of the call (frames are laid out back to back).  Histories: one
+ * warp per frame walks its blocks, 32 transfer functions per round.  res[0] = first error, res[1] = total output bytes. */
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS)
+zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames, u32 nbFrames, ZbdBlockOut* __restrict__ bout,
+                u64 dstCapacity, u32* __restrict__ progress, u32* __restrict__ ticket, u64* __restrict__ res)
+{
+    __shared__ u64 warpSum[SCAN_THREADS / 32];
+    __shared__ u64 carry;
+    __shared__ u32 firstErr;
+    u32 const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) { carry = 0; firstErr = 0; *ticket = 0; }
+    __syncthreads();
+    for (u32 b0 = 0; b0 < nbBlocks; b0 += SCAN_THREADS) {
+        u32 const i = b0 + tid;
+        u64 v = 0;
+        if (i < nbBlocks) { v = bout[i].regen; progress[i] = 0; if (bout[i].err) atomicMax(&firstErr, bout[i].err); }
+        u64 inc = v;
+#pragma unroll
+        for (u32 o = 1; o < 32u; o <<= 1) { u64 const x = __shfl_up_sync(ZB_FULL, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31u) warpSum[warp] = inc;
+        __syncthreads();
+        u64 base = carry;
+        for (u32 k = 0; k < warp; k++) base += warpSum[k];
+        if (i < nbBlocks) bout[i].dstOff = base + inc - v;
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1u) carry = base + inc;
+        __syncthreads();
+    }
+    u64 const total = carry;
+    /* per frame: content size, start offset, repcode histories */
+    for (u32 f = warp; f < nbFrames; f += SCAN_THREADS / 32u) {
+        ZbdFrame const fr = frames[f];
+        u64 const fOff = fr.nbBlocks ? bout[fr.firstBlock].dstOff : 0;
+        ZbdRep h; h.r[0] = 1u; h.r[1] = 4u; h.r[2] = 8u;            /* format: "Repeat Offsets" start values */
+        for (u32 k0 = 0; k0 < fr.nbBlocks; k0 += 32u) {
+            u32 const k = k0 + lane;
+            ZbdRep tr; tr.r[0] = tr.r[1] = tr.r[2] = 0;
+            if (k < fr.nbBlocks) tr = bout[fr.firstBlock + k].transfer;
+            ZbdRep mine = h;
+            u32 const n = min(32u, fr.nbBlocks - k0);
+            for (u32 j = 0; j < n; j++) {
+                if (lane == j) mine = h;                             /* history at the start of block k0 + j */
+                ZbdRep t; t.r[0] = __shfl_sync(ZB_FULL, tr.r[0], (int)j); t.r[1] = __shfl_sync(ZB_FULL, tr.r[1], (int)j); t.r[2] = __shfl_sync(ZB_FULL, tr.r[2], (int)j);
+                ZbdRep nx; nx.r[0] = zbd_rep_resolve(t.r[0], &h); nx.r[1] = zbd_rep_resolve(t.r[1], &h); nx.r[2] = zbd_rep_resolve(t.r[2], &h);
+                h = nx;
+            }
+            if (k < fr.nbBlocks) { ZbdBlockOut& o = bout[fr.firstBlock + k]; o.start = mine; o.frameOff = fOff; }
+        }
+        if (lane == 0 && fr.contentSize != ZBD_CONTENTSIZE_UNKNOWN) {
+            u64 const end = (fr.firstBlock + fr.nbBlocks < nbBlocks) ? bout[fr.firstBlock + fr.nbBlocks].dstOff : total;
+            if (end - fOff != fr.contentSize) atomicMax(&firstErr, ZBD_CORRUPT);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u32 e = firstErr;
+        if (!e && total > dstCapacity) e = 70u;                      /* dstSize_tooSmall */
+        res[0] = e; res[1] = total;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ D4 execute */
+__device__ __forceinline__ u32 zbd_ld_volatile(const u32* p) { u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void zbd_st_volatile(u32* p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+/* blocks until every byte of [absLo, absHi) that lies in blocks below `bi` has been written (absolute output offsets) */
+__device__ __forceinline__ void zbd_wait_range(const ZbdBlockOut* __restrict__ bout, const u32* progress, u32 bi, u32 firstBlock, u64 absLo, u64 absHi, u32 lane)
+{
+    if (lane == 0) {
+        u32 j = bi;
+        while (j > firstBlock) {
+            j--;
+            u64 const s = bout[j].dstOff;
+            u64 const e = s + bout[j].regen;
+            if (e <= absLo) break;                                   /* this block and everything below it lie in front of the range */
+            if (s >= absHi) continue;
+            u32 const need = (u32)((absHi < e ? absHi : e) - s);
+            while (zbd_ld_volatile(progress + j) < need) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * ZBD_WARPS)
+zbd_execute_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames,
+                   const u8* __restrict__ lits, const u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout,
+                   u8* __restrict__ dst, u32* progress, u32* ticket, u32* __restrict__ execErr)
+{
+    u32 const lane = threadIdx.x & 31u;
+    /* blocks are taken in ticket order: a block only ever waits for blocks with lower tickets, which have started */
+    u32 bi = 0;
+    if (lane == 0) bi = atomicAdd(ticket, 1u);
+    bi = __shfl_sync(ZB_FULL, bi, 0);
+    if (bi >= nbBlocks) return;
+    ZbdBlock const b = blocks[bi];
+    ZbdBlockOut const o = bout[bi];
+    u8* const out = dst + o.dstOff;
+    u32 const firstBlock = frames[b.frame].firstBlock;
+    if (b.type == ZB_BT_RAW) { for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = src[b.srcOff + i]; }
+    else if (b.type == ZB_BT_RLE) { u8 const v = src[b.srcOff]; for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = v; }
+    else {
+        const u8* lit = lits + b.litPos;
+        const u64* sq = seqs + b.seqPos;
+        ZbdRep rep = o.start;
+        u64 const inFrame = o.dstOff - o.frameOff;                   /* bytes of the frame in front of this block */
+        u32 op = 0, lp = 0, published = 0, err = 0;
+        for (u32 i = 0; i < b.nbSeq; i++) {
+            u64 const q = sq[i];
+            u32 const ll = ZBD_SEQ_LL(q), ml = ZBD_SEQ_ML(q);
+            u32 const off = zbd_rep_apply(&rep, ZBD_SEQ_OFF(q), ll, false);
+            for (u32 k = lane; k < ll; k += 32u) out[op + k] = lit[lp + k];
+            op += ll; lp += ll;
+            if (off == 0u || (u64)off > inFrame + op) { err = ZBD_CORRUPT; break; }
+            if (off > op) {                                          /* the match starts in an earlier block */
+                u64 const lo = o.dstOff + op - off;
+                u64 const span = ml < off ? ml : off;
+                zbd_wait_range(bout, progress, bi, firstBlock, lo, lo + span, lane);
+            } else __syncwarp();                                     /* this sequence's literals may be the match's source */
+            /* dst[op + k] = history[op - off + (k mod off)]: every source byte exists before this match begins */
+            {   const u8* const from = out + op - off;               /* may point into earlier blocks (same buffer) */
+                if (off >= ml) {
+                    if (off > op) { for (u32 k = lane; k < ml; k += 32u) out[op + k] = __ldcg(from + k); }
+                    else          { for (u32 k = lane; k < ml; k += 32u) out[op + k] = from[k]; }
+                } else {
+                    u32 r = lane % off; u32 const inc = 32u % off;
+                    for (u32 k = lane; k < ml; k += 32u) {
+                        out[op + k] = (off > op) ? __ldcg(from + r) : from[r];
+                        r += inc; if (r >= off) r -= off;
+                    }
+                }
+            }
+            op += ml;
+            if (op - published >= 2048u) {                           /* let the blocks behind this one advance */
+                __threadfence(); __syncwarp();
+                if (lane == 0) zbd_st_volatile(progress + bi, op);
+                published = op;
+            }
+        }
+        if (!err) { u32 const rest = b.litRegen - lp; for (u32 k = lane; k < rest; k += 32u) out[op + k] = lit[lp + k]; }
+        if (err && lane == 0) atomicMax(execErr, err);
+    }
+    __threadfence(); __syncwarp();
+    if (lane == 0) zbd_st_volatile(progress + bi, o.regen);          /* also on an error: nobody may wait for ever */
+}
+
+/* ------------------------------------------------------------------------------------------------ host driver */
+struct ZSTD_DCtx_s {
+    int device, bindDevice;
+    cudaStream_t stream;
+    ZbdBlock* d_blocks; ZbdFrame* d_frames; ZbdBlockOut* d_bout; u32* d_progress; size_t capBlocks, capFrames;
+    u8* d_lits; size_t capLits; u64* d_seqs; size_t capSeqs;
+    u8* d_in; size_t capIn; u8* d_out; size_t capOut;
+    u64* d_res; u32* d_ticket; u32* d_execErr;
+    u64* h_res;                  /* pinned: walker / scan results */
+    cudaEvent_t ev[6];
+    ZSTDB200_dstats stats;
+};
+extern "C" int zb_boundDevice(void);                                 /* zb_api.cu: ZSTDB200_setDevice's value, or -1 */
+
+#define DCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    if (getenv("ZSTDB200_DEBUG")) fprintf(stderr, "zstd_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    cudaGetLastError(); return ZB_ERR(e_ == cudaErrorMemoryAllocation ? ZB_error_memory_allocation : ZB_error_GENERIC); } } while (0)
+static inline bool zbd_isErr(size_t c) { return c > ZB_ERR(ZB_error_maxCode); }
+
+extern "C" ZSTD_DCtx* ZSTD_createDCtx(void)                          /* lib/zstd.h:289 */
+{
+    ZSTD_DCtx* d = (ZSTD_DCtx*)calloc(1, sizeof(ZSTD_DCtx));
+    if (!d) return NULL;
+    d->device = -1;
+    d->bindDevice = zb_boundDevice();
+    if (d->bindDevice < 0) { int dev = -1; if (cudaGetDevice(&dev) == cudaSuccess) d->bindDevice = dev; else cudaGetLastError(); }
+    return d;
+}
+extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts NULL, lib/zstd.h:290 */
+{
+    if (!d) return 0;
+    if (d->device >= 0) {
+        int prev = -1; cudaGetDevice(&prev);
+        cudaSetDevice(d->device);
+        cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_progress); cudaFree(d->d_lits); cudaFree(d->d_seqs);
+        cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res);
+        for (int i = 0; i < 6; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+        if (d->stream) cudaStreamDestroy(d->stream);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    free(d);
+    return 0;
+}
+static size_t zbd_ctxInit(ZSTD_DCtx* d)
+{
+    if (d->device >= 0) { DCK(cudaSetDevice(d->device)); return 0; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZB_ERR(ZB_error_GENERIC); }
+    int dev = d->bindDevice < 0 ? 0 : d->bindDevice;
+    DCK(cudaSetDevice(dev));
+    DCK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) DCK(cudaEventCreate(&d->ev[i]));
+    DCK(cudaMalloc(&d->d_res, 16 * sizeof(u64)));
+    DCK(cudaMallocHost(&d->h_res, 16 * sizeof(u64)));
+    d->d_ticket = (u32*)(d->d_res + 8); d->d_execErr = (u32*)(d->d_res + 9);
+    d->device = dev;
+    return 0;
+}
+template <typename T> static size_t zbd_grow(T** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) return 0;
+    cudaFree(*p); *p = NULL; *cap = 0;
+    size_t const n = need + need / 8 + 64;
+    DCK(cudaMalloc(p, n * sizeof(T)));
+    *cap = n;
+    return 0;
+}
+
+/* D1 .. D4 over descriptors that are already on the device; returns the output size */
+static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_src, u32 nb, u32 nf, cudaStream_t st)
+{
+    DCK(cudaMemsetAsync(d->d_execErr, 0, sizeof(u32), st));
+    DCK(cudaEventRecord(d->ev[1], st));
+    u32 const grid = (nb + ZBD_WARPS - 1u) / ZBD_WARPS;
+    zbd_literals_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_bout);
+    DCK(cudaEventRecord(d->ev[2], st));
+    zbd_sequences_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_seqs, d->d_bout);
+    DCK(cudaEventRecord(d->ev[3], st));
+    zbd_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(d->d_blocks, nb, d->d_frames, nf, d->d_bout, (u64)dstCapacity, d->d_progress, d->d_ticket, d->d_res);
+    DCK(cudaMemcpyAsync(d->h_res, d->d_res, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    DCK(cudaStreamSynchronize(st));                                  /* nothing is written to dst before the sizes are known to fit */
+    if (d->h_res[0]) return ZB_ERR((u32)d->h_res[0]);
+    size_t const total = (size_t)d->h_res[1];
+    DCK(cudaEventRecord(d->ev[4], st));
+    zbd_execute_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_frames, d->d_lits, d->d_seqs, d->d_bout, d_dst, d->d_progress, d->d_ticket, d->d_execErr);
+    DCK(cudaEventRecord(d->ev[5], st));
+    DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    DCK(cudaStreamSynchronize(st));
+    DCK(cudaGetLastError());
+    if ((u32)d->h_res[2]) return ZB_ERR((u32)d->h_res[2]);
+    {   float ms = 0;
+        cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]); d->stats.literals_ms = ms;
+        cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); d->stats.sequences_ms = ms;
+        cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); d->stats.execute_ms = ms;
+        cudaEventElapsedTime(&ms, d->ev[1], d->ev[5]); d->stats.kernel_ms = ms;
+        d->stats.nbBlocks = nb; d->stats.nbFrames = nf; d->stats.launches = 4; }
+    return total;
+}
+
+static size_t zbd_ensure(ZSTD_DCtx* d, u32 nb, u32 nf, u64 litBytes, u64 seqCount)
+{
+    if (nb > d->capBlocks) {
+        cudaFree(d->d_blocks); cudaFree(d->d_bout); cudaFree(d->d_progress); d->d_blocks = NULL; d->d_bout = NULL; d->d_progress = NULL; d->capBlocks = 0;
+        size_t const n = (size_t)nb + nb / 8 + 64;
+        DCK(cudaMalloc(&d->d_blocks, n * sizeof(ZbdBlock))); DCK(cudaMalloc(&d->d_bout, (n + 1) * sizeof(ZbdBlockOut))); DCK(cudaMalloc(&d->d_progress, n * sizeof(u32)));
+        d->capBlocks = n;
+    }
+    {   size_t const e = zbd_grow(&d->d_frames, &d->capFrames, (size_t)nf); if (zbd_isErr(e)) return e; }
+    {   size_t const e = zbd_grow(&d->d_lits, &d->capLits, (size_t)litBytes + 16); if (zbd_isErr(e)) return e; }
+    {   size_t const e = zbd_grow(&d->d_seqs, &d->capSeqs, (size_t)seqCount + 1); if (zbd_isErr(e)) return e; }
+    return 0;
+}
+
+
+/* host buffers: the walk runs on the host while the input is on its way to the device */
+static size_t zbd_decompressHost(ZSTD_DCtx* d, void* dst, size_t dstCapacity, const void* src, size_t srcSize)
+{
+    const u8* const in = (const u8*)src;
+    u32 nb = 0, nf = 0; u64 lit = 0, seq = 0;
+    cudaStream_t const st = d->stream;
+    u32 e = zbd_walk(in, srcSize, NULL, 0, NULL, 0, &nb, &nf, &lit, &seq);
+    if (e) return ZB_ERR(e);
+    std::vector<ZbdBlock> B(nb ? nb : 1); std::vector<ZbdFrame> F(nf ? nf : 1);
+    e = zbd_walk(in, srcSize, B.data(), nb, F.data(), nf, &nb, &nf, &lit, &seq);
+    if (e) return ZB_ERR(e);
+    if (nb == 0) return 0;
+    u64 known = 0; bool allKnown = true;
+    for (u32 f = 0; f < nf; f++) { if (F[f].contentSize == ZBD_CONTENTSIZE_UNKNOWN) allKnown = false; else known += F[f].contentSize; }
+    if (allKnown && known > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    {   size_t const r = zbd_grow(&d->d_in, &d->capIn, srcSize + 16); if (zbd_isErr(r)) return r; }
+    {   size_t const r = zbd_ensure(d, nb, nf, lit, seq); if (zbd_isErr(r)) return r; }
+    DCK(cudaEventRecord(d->ev[0], st));
+    DCK(cudaMemcpyAsync(d->d_in, in, srcSize, cudaMemcpyHostToDevice, st));
+    /* the output can not be larger than the blocks' maximum sizes */
+    size_t const outNeed = allKnown ? (size_t)known : (dstCapacity < (size_t)nb * ZB_BLOCK_MAX ? dstCapacity : (size_t)nb * ZB_BLOCK_MAX);
+    {   size_t const r = zbd_grow(&d->d_out, &d->capOut, outNeed + 16); if (zbd_isErr(r)) return r; }
+    DCK(cudaMemcpyAsync(d->d_blocks, B.data(), (size_t)nb * sizeof(ZbdBlock), cudaMemcpyHostToDevice, st));
+    DCK(cudaMemcpyAsync(d->d_frames, F.data(), (size_t)nf * sizeof(ZbdFrame), cudaMemcpyHostToDevice, st));
+    size_t const total = zbd_run(d, d->d_out, outNeed, d->d_in, nb, nf, st);
+    if (zbd_isErr(total)) return total;
+    if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    if (total) DCK(cudaMemcpy(dst, d->d_out, total, cudaMemcpyDeviceToHost));
+    /* frame checksums (format: "Content_Checksum"): XXH64 of the regenerated content, low 32 bits */
+    {   size_t off = 0;
+        for (u32 f = 0; f < nf; f++) {
+            u64 size = 0;
+            if (F[f].contentSize != ZBD_CONTENTSIZE_UNKNOWN) size = F[f].contentSize;
+            else { /* sizes of frames without the field: from the scan */
+                std::vector<ZbdBlockOut> tmp(2);
+                u32 const last = F[f].firstBlock + F[f].nbBlocks;
+                DCK(cudaMemcpy(&tmp[0], d->d_bout + F[f].firstBlock, sizeof(ZbdBlockOut), cudaMemcpyDeviceToHost));
+                u64 end = total;
+                if (last < nb) { DCK(cudaMemcpy(&tmp[1], d->d_bout + last, sizeof(ZbdBlockOut), cudaMemcpyDeviceToHost)); end = tmp[1].dstOff; }
+                size = end - tmp[0].dstOff;
+            }
+            if (F[f].hasChecksum) {
+                u32 const want = zbd_le(in + F[f].srcOff + F[f].cSize - 4, 4);
+                if ((u32)ZSTDB200_xxh64((const u8*)dst + off, (size_t)size) != want) return ZB_ERR(22);      /* checksum_wrong */
+            }
+            off += (size_t)size;
+        }
+    }
+    d->stats.h2d_bytes = srcSize; d->stats.d2h_bytes = total;
+    return total;
+}
+
+/* device buffers: the walk is a kernel (one thread follows the chain of block headers) */
+static size_t zbd_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, cudaStream_t st)
+{
+    u32 capB = (u32)(srcSize / 4096u) + 1024u, capF = 1024u;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        {   size_t const r = zbd_ensure(d, capB, capF, 0, 0); if (zbd_isErr(r)) return r; }
+        zbd_walk_kernel<<<1, 32, 0, st>>>((const u8*)d_src, (u64)srcSize, d->d_blocks, (u32)d->capBlocks, d->d_frames, (u32)d->capFrames, d->d_res);
+        DCK(cudaMemcpyAsync(d->h_res, d->d_res, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        DCK(cudaStreamSynchronize(st));
+        if (d->h_res[0]) return ZB_ERR((u32)d->h_res[0]);
+        if (d->h_res[1] <= d->capBlocks && d->h_res[2] <= d->capFrames) break;
+        capB = (u32)d->h_res[1]; capF = (u32)d->h_res[2];
+        if (attempt == 1) return ZB_ERR(ZB_error_GENERIC);
+    }
+    u32 const nb = (u32)d->h_res[1], nf = (u32)d->h_res[2];
+    if (nb == 0) return 0;
+    {   size_t const r = zbd_ensure(d, nb, nf, d->h_res[3], d->h_res[4]); if (zbd_isErr(r)) return r; }
+    return zbd_run(d, (u8*)d_dst, dstCapacity, (const u8*)d_src, nb, nf, st);
+}
+
+struct ZbdDeviceGuard { int prev; ZbdDeviceGuard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } } ~ZbdDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); } };
+
+extern "C" size_t ZSTD_decompressDCtx(ZSTD_DCtx* d, void* dst, size_t dstCapacity, const void* src, size_t srcSize)      /* lib/zstd.h:299 */
+{
+    if (!d) return ZB_ERR(ZB_error_GENERIC);
+    if (srcSize == 0) return 0;                                       /* zstd_decompress.c:1093 : an empty input is an empty output */
+    if (!src) return ZB_ERR(ZB_error_srcSize_wrong);
+    if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
+    ZbdDeviceGuard guard;
+    {   size_t const e = zbd_ctxInit(d); if (zbd_isErr(e)) return e; }
+    memset(&d->stats, 0, sizeof(d->stats));
+    return zbd_decompressHost(d, dst, dstCapacity, src, srcSize);
+}
+
+extern "C" size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize)                  /* lib/zstd.h:170 */
+{
+    ZSTD_DCtx* const d = ZSTD_createDCtx();
+    if (!d) return ZB_ERR(ZB_error_memory_allocation);
+    size_t const r = ZSTD_decompressDCtx(d, dst, dstCapacity, src, compressedSize);
+    ZSTD_freeDCtx(d);
+    return r;
+}
+
+extern "C" size_t ZSTDB200_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream)
+{
+    if (!d) return ZB_ERR(ZB_error_GENERIC);
+    if (srcSize == 0) return 0;
+    ZbdDeviceGuard guard;
+    {   size_t const e = zbd_ctxInit(d); if (zbd_isErr(e)) return e; }
+    memset(&d->stats, 0, sizeof(d->stats));
+    return zbd_decompressDevice(d, d_dst, dstCapacity, d_src, srcSize, stream ? (cudaStream_t)stream : d->stream);
+}
+
+extern "C" void ZSTDB200_getLastDStats(const ZSTD_DCtx* d, ZSTDB200_dstats* out) { if (d && out) *out = d->stats; }
+
+/* lib/zstd.h:205,227 : host helpers that only read headers */
+extern "C" unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize)
+{
+    ZbdFrameHeader h;
+    u32 const e = zbd_readFrameHeader(&h, (const u8*)src, srcSize);
+    if (e) return 0ULL - 2;                                           /* ZSTD_CONTENTSIZE_ERROR */
+    if (h.skippable) return 0;
+    return h.contentSize == ZBD_CONTENTSIZE_UNKNOWN ? 0ULL - 1 : h.contentSize;   /* ZSTD_CONTENTSIZE_UNKNOWN */
+}
+extern "C" size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize)
+{
+    const u8* const in = (const u8*)src;
+    ZbdFrameHeader h;
+    u32 const e = zbd_readFrameHeader(&h, in, srcSize);
+    if (e) return ZB_ERR(e);
+    if (h.skippable) return (8u + h.contentSize > srcSize) ? ZB_ERR(ZB_error_srcSize_wrong) : (size_t)(8u + h.contentSize);
+    size_t p = h.headerSize;
+    while (true) {
+        if (p + 3 > srcSize) return ZB_ERR(ZB_error_srcSize_wrong);
+        u32 const bh = zbd_le(in + p, 3);
+        u32 const type = (bh >> 1) & 3u, bsz = bh >> 3;
+        if (type == 3u) return ZB_ERR(ZBD_CORRUPT);
+        p += 3u + (type == ZB_BT_RLE ? 1u : bsz);
+        if (p > srcSize) return ZB_ERR(ZB_error_srcSize_wrong);
+        if (bh & 1u) break;
+    }
+    if (h.hasChecksum) { p += 4; if (p > srcSize) return ZB_ERR(ZB_error_srcSize_wrong); }
+    return p;
+}

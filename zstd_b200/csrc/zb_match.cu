@@ -89,38 +89,41 @@ __device__ __forceinline__ u32 zb_walk_cand(u32 c, u32 h, u32 x)
     return (((c ^ h) & ZB_TAG_MASK) == 0u && px < x) ? x - px : 0u;
 }
 
-/* which of the P consecutive positions starting at rel0 lie on the insertion pattern (rel % step) < 2, as a bit mask */
+/* which of the P (<= 4) consecutive positions starting at a position whose residue modulo `step` is r0 lie on the
+ * insertion pattern (rel % step) < 2, as a bit mask.  step >= 3: the pair that began at or before the first position
+ * (bits 0,1 for r0 = 0; bit 0 for r0 = 1) and the next pair, step - r0 positions on; a third pair lies beyond P. */
 template <int P>
-__device__ __forceinline__ u32 zb_walk_pattern(u32 rel0, u32 step)
+__device__ __forceinline__ u32 zb_walk_pattern_res(u32 r0, u32 step)
 {
     if (step <= 2u) return (1u << P) - 1u;
-    u32 const q = (u32)__fdividef((float)rel0, (float)step);    /* rel0 < 2^21: exact up to +-1, fixed below */
+    u32 const head = 3u >> (r0 < 2u ? r0 : 2u);
+    u32 const nxt = step - r0;
+    return (head | (3u << (nxt < 31u ? nxt : 31u))) & ((1u << P) - 1u);
+}
+/* residue of rel0 modulo step (rel0 < 2^22, step < 2^14: the float quotient is exact up to +-1, fixed below) */
+__device__ __forceinline__ u32 zb_walk_residue(u32 rel0, u32 step)
+{
+    u32 const q = (u32)__fdividef((float)rel0, (float)step);
     int r = (int)rel0 - (int)(q * step);
     if (r < 0) r += (int)step; else if (r >= (int)step) r -= (int)step;
-    u32 m = 0;
-#pragma unroll
-    for (int i = 0; i < P; i++) {                                /* r + i < 2 * step: the position is r + i or r + i - step into its period */
-        u32 const ri = (u32)r + (u32)i;
-        m |= ((ri < 2u) || (ri - step < 2u)) ? (1u << i) : 0u;
-    }
-    return m;
+    return (u32)r;
 }
 
 /* One batch of the walk for one thread: P consecutive positions from walk coordinate xa.
  * INTERIOR: every position of the batch is walked, lies in the frame's own bytes and has its 8 bytes readable: no
- * activity predicates, bytes come from the words prefetched in wrd[]. */
+ * activity predicates, bytes come from the words prefetched in wrd[].
+ * Returns whether any position of the CTA found a candidate in phase A (the barrier between A and B carries the OR). */
 template <int MLS, int P, bool INTERIOR>
-__device__ __forceinline__ void zb_walk_batch(u32* __restrict__ table, u32* sLastHit, u32 par, u32 xa, u32 x0, const u32 (&wrd)[3],
-                                              u32 N, u32 insStep, u32 shift, u32 D, u32 total, u32 xLow, u32 xEnd,
-                                              const u8* fbase, const u8* dbase, bool output, u16* __restrict__ distRow, u32* __restrict__ farRow,
-                                              u32& nextWordsFetched)
+__device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, const u32 (&wrd)[3], u32 pat,
+                                              u32 N, u32 shift, u32 D, u32 total, u32 xLow, u32 xEnd,
+                                              const u8* fbase, const u8* dbase, bool output, u16* __restrict__ distRow, u32* __restrict__ farRow)
 {
-    (void)nextWordsFetched;
-    u32 h[P], bkt[P], old[P], dOld[P];
+    u32 h[P], bkt[P], dOld[P];
     bool act[P];
     /* ---- A: hash, read the bucket ---- */
     {   u32 const rel0 = xa - shift;
         bool const slow = !INTERIOR && ((xa < xLow) || (D != 0u && rel0 < D && rel0 + P + 7u > D) || (rel0 + P + 7u > total));
+        u32 old[P];
 #pragma unroll
         for (int i = 0; i < P; i++) {
             u32 const x = xa + (u32)i, rel = x - shift;
@@ -136,23 +139,17 @@ __device__ __forceinline__ void zb_walk_batch(u32* __restrict__ table, u32* sLas
             bkt[i] = __umulhi(h[i], N);
             old[i] = act[i] ? table[bkt[i]] : 0u;
         }
-    }
-    u32 hitX = 0;
 #pragma unroll
-    for (int i = 0; i < P; i++) { dOld[i] = zb_walk_cand(old[i], h[i], xa + (u32)i); if (dOld[i]) hitX = xa + (u32)i; }
-    u32 li = sLastHit[par ^ 1u];                              /* latest hit of the batches before this one */
-    if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
-    u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
-    u32 const step = insStep + ((sWalk - li) >> 7);
-    {   u32 const wmax = __reduce_max_sync(ZB_FULL, hitX);
-        if (wmax && (threadIdx.x & 31u) == 0u) atomicMax(&sLastHit[par], wmax); }
-    u32 const pat = zb_walk_pattern<P>(xa - shift, step);
-    __syncthreads();
+        for (int i = 0; i < P; i++) dOld[i] = zb_walk_cand(old[i], h[i], xa + (u32)i);
+    }
+    u32 anyOld = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) anyOld |= dOld[i];
+    bool const anyHit = __syncthreads_or(anyOld != 0u) != 0;
     /* ---- B: insertions ---- */
 #pragma unroll
     for (int i = 0; i < P; i++)
         if (act[i] && dOld[i] == 0u && ((pat >> i) & 1u)) atomicMax(&table[bkt[i]], zb_walk_entry(h[i], xa + (u32)i));
-    if (threadIdx.x == 0u) { u32 const a = sLastHit[par], b = sLastHit[par ^ 1u]; if (b > a) sLastHit[par] = b; }
     __syncthreads();
     /* ---- C: second look, output ---- */
     u32 d[P];
@@ -169,28 +166,37 @@ __device__ __forceinline__ void zb_walk_batch(u32* __restrict__ table, u32* sLas
 #pragma unroll
             for (int i = 0; i < P; i++) if (d[i] >= ZB_FAR) { if (INTERIOR || xa + (u32)i < xEnd) farRow[i] = d[i]; d[i] = ZB_FAR; }
         }
-        if (P == 4 && (INTERIOR || xa + 4u <= xEnd)) *reinterpret_cast<uint2*>(distRow) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16));
-        else {
+        bool vec = false;
+        if constexpr (P == 4) { if (INTERIOR || xa + 4u <= xEnd) { *reinterpret_cast<uint2*>(distRow) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16)); vec = true; } }
+        if constexpr (P == 2) { if (INTERIOR || xa + 2u <= xEnd) { *reinterpret_cast<u32*>(distRow) = d[0] | (d[1] << 16); vec = true; } }
+        if (!vec) {
 #pragma unroll
             for (int i = 0; i < P; i++) if (xa + (u32)i < xEnd) distRow[i] = (u16)d[i];
         }
     }
+    return anyHit;
 }
 
 /* P consecutive positions per thread, ZB_BATCH / P threads per CTA.  Per batch:
  *   A  every position hashes its 8 bytes and reads its bucket (the table as the previous batch left it);
  *   B  positions that found no candidate and lie on the insertion pattern atomicMax their entry into the bucket;
  *   C  positions that found nothing in A look again: the batch's lowest insertion into their bucket may serve them.
- * Two barriers per batch (A|B, B|C); C of one batch and A of the next share a region. */
+ * Two barriers per batch (A|B, which also tells every thread whether the batch saw a hit, and B|C); C of one batch
+ * and A of the next share a region.  The input bytes of a batch are loaded two batches ahead. */
+#ifndef WALK_P_SMALL
+#define WALK_P_SMALL 4           /* positions per thread for tables <= 56 KiB (development knob: tools/build_variant.sh) */
+#endif
+#ifndef WALK_MINB_SMALL
+#define WALK_MINB_SMALL 4        /* CTAs per SM the register allocation of that variant leaves room for */
+#endif
 template <int MLS, int P>
-__global__ void __launch_bounds__(ZB_BATCH / P)
+__global__ void __launch_bounds__(ZB_BATCH / P, P == WALK_P_SMALL ? WALK_MINB_SMALL : 1)
 zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const ZbChunk* __restrict__ chunks, u32 insStep, u32 N, ZbStrides sd,
                u32 slotFirstBlock, u16* __restrict__ dist, u32* __restrict__ far,
                const u32* __restrict__ imageIn, u32* __restrict__ imageOut)
 {
     constexpr u32 THREADS = ZB_BATCH / P;
     extern __shared__ __align__(16) u32 table[];
-    __shared__ u32 sLastHit[2];                                   /* walk coordinate of the latest candidate hit: [k & 1] gets batch k's */
     u32 const t = threadIdx.x;
     ZbChunk const cd = chunks[blockIdx.x];
     bool const buildImage = imageOut != nullptr;
@@ -206,7 +212,6 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
 
     if (fromImage) for (u32 i = t; i < N; i += THREADS) table[i] = __ldg(imageIn + i);
     else           for (u32 i = t; i < N; i += THREADS) table[i] = 0u;
-    if (t < 2u) sLastHit[t] = shift;                              /* the walk's start counts as a hit */
     __syncthreads();
 
     u32 const xEnd = total + shift;
@@ -215,47 +220,64 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     /* interior batches: completely walked, completely in the frame's own bytes, all 8-byte reads inside [.., total) */
     u32 const xIntLo = ((D + shift) > xLow ? (D + shift) : xLow);
     u32 const xIntLoB = (xIntLo + ZB_BATCH - 1u) & ~(ZB_BATCH - 1u);
-    u32 const xIntHi = xEnd >= (ZB_BATCH + P + 8u) ? (xEnd - (P + 8u)) & ~(ZB_BATCH - 1u) : 0u;     /* batches [x0, x0 + B) with x0 + B <= xIntHi are interior */
+    /* a thread's P + 7 bytes lie in NW aligned words whatever its address modulo 4; the interior loads all NW of them */
+    constexpr u32 NW = (P + 7u + 3u + 3u) / 4u;
+    u32 const xIntHi = xEnd >= (ZB_BATCH + 4u * NW) ? (xEnd + P - 4u * NW) & ~(ZB_BATCH - 1u) : 0u;     /* batches [x0, x0 + B) with x0 + B <= xIntHi are interior */
 
-    /* the 11 bytes of a thread's P positions (+7) as three words realigned to its first position */
-    u32 wrd[3];
-    auto fetch = [&](u32 xb) {
+    /* the P + 7 bytes of a thread's positions as three words realigned to its first position */
+    auto fetch = [&](u32 xb, u32 (&w)[3]) {
         u32 const xa = xb + P * t;                                /* first coordinate of the thread */
-        wrd[0] = wrd[1] = wrd[2] = 0u;
-        if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
-        u32 const rel = xa - shift;
+        w[0] = w[1] = w[2] = 0u;
         if (xb >= xIntLoB && xb + ZB_BATCH <= xIntHi) {           /* interior: no guards */
-            const u8* const a = fbase + rel;
+            const u8* const a = fbase + (xa - shift);
             const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
             u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-            u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
-            wrd[0] = __funnelshift_r(w0, w1, sh); wrd[1] = __funnelshift_r(w1, w2, sh); wrd[2] = __funnelshift_r(w2, w3, sh);
+            u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = NW > 3u ? __ldg(p + 3) : 0u;
+            w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh); w[2] = __funnelshift_r(w2, w3, sh);
             return;
         }
+        if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
+        u32 const rel = xa - shift;
         bool const slow = (xa < xLow) || (D != 0u && rel < D && rel + P + 7u > D) || (rel + P + 7u > total);
         if (slow) return;                                         /* assembled byte-wise in the batch */
         const u8* const a = (rel < D ? dbase : fbase) + rel;
         const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
-        u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-        u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        u32 const w3 = sh ? __ldg(p + 3) : 0u;                    /* rel + P + 7 <= limit: the fourth word is only touched when it holds a needed byte */
-        wrd[0] = __funnelshift_r(w0, w1, sh); wrd[1] = __funnelshift_r(w1, w2, sh); wrd[2] = __funnelshift_r(w2, w3, sh);
+        u32 const al = (u32)(uintptr_t)a & 3u, sh = al * 8u;
+        /* rel + P + 7 <= limit: a word is only touched when it holds one of the thread's P + 7 bytes */
+        u32 const w0 = __ldg(p), w1 = __ldg(p + 1);
+        u32 const w2 = (al + P + 7u > 8u) ? __ldg(p + 2) : 0u;
+        u32 const w3 = (al + P + 7u > 12u) ? __ldg(p + 3) : 0u;
+        w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh); w[2] = __funnelshift_r(w2, w3, sh);
     };
-    fetch(x0);
+    u32 wA[3], wB[3];                                             /* bytes of the next batch and of the one after it */
+    fetch(x0, wA);
+    fetch(x0 + ZB_BATCH, wB);
     u32 const blockMask = (1u << cd.blockLog) - 1u;
-    u32 dummy = 0;
-    for (u32 k = 0; x0 < xEnd; k++, x0 += ZB_BATCH) {
-        u32 const par = k & 1u;
+    /* insertion pattern: the residue of the thread's first position modulo insStep follows the walk by addition; only a
+     * batch whose step was raised by the acceleration pays for a division */
+    u32 const stepInc = ZB_BATCH % insStep;
+    u32 r0 = (x0 + P * t + insStep * ZB_BATCH - shift) % insStep;
+    u32 li = shift;                                               /* coordinate the acceleration counts from: the walk's start, then the end of the last batch with a hit */
+    for (; x0 < xEnd; x0 += ZB_BATCH) {
         u32 const xa = x0 + P * t;
-        u32 cur[3] = { wrd[0], wrd[1], wrd[2] };
-        fetch(x0 + ZB_BATCH);                                     /* next batch's bytes: in flight across this batch's barriers */
+        u32 cur[3] = { wA[0], wA[1], wA[2] };
+        wA[0] = wB[0]; wA[1] = wB[1]; wA[2] = wB[2];
+        fetch(x0 + 2u * ZB_BATCH, wB);                            /* in flight across two batches' barriers */
+        if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
+        u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
+        u32 const step = insStep + ((sWalk - li) >> 7);
+        u32 const pat = zb_walk_pattern_res<P>(step == insStep ? r0 : zb_walk_residue(xa - shift, step), step);
         bool const output = !buildImage && x0 >= H + shift;       /* H + shift is a batch border: the whole batch lies in the history or in the chunk */
-        u32 const qb = xa - shift - H;                            /* offset in the chunk (a multiple of P) when output */
-        size_t const idx = output ? (size_t)(cd.firstBlock - slotFirstBlock + (qb >> cd.blockLog)) * sd.dist + (qb & blockMask) : 0;
+        /* a batch never straddles two blocks (block sizes are multiples of the batch, or the frame is a single block) */
+        u32 const qb0 = x0 - shift - H;                           /* offset of the batch in the chunk when output */
+        size_t const idx = output ? (size_t)(cd.firstBlock - slotFirstBlock + (qb0 >> cd.blockLog)) * sd.dist + (qb0 & blockMask) + P * t : 0;
+        bool hit;
         if (x0 >= xIntLoB && x0 + ZB_BATCH <= xIntHi)
-            zb_walk_batch<MLS, P, true>(table, sLastHit, par, xa, x0, cur, N, insStep, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx, dummy);
+            hit = zb_walk_batch<MLS, P, true>(table, xa, cur, pat, N, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx);
         else
-            zb_walk_batch<MLS, P, false>(table, sLastHit, par, xa, x0, cur, N, insStep, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx, dummy);
+            hit = zb_walk_batch<MLS, P, false>(table, xa, cur, pat, N, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx);
+        if (hit) li = x0 + ZB_BATCH;
+        r0 += stepInc; if (r0 >= insStep) r0 -= insStep;
     }
     if (buildImage) { __syncthreads(); for (u32 i = t; i < N; i += THREADS) imageOut[i] = table[i]; }
 }
@@ -716,24 +738,38 @@ zb_merge_small_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bl
 }
 
 /* ------------------------------------------------------------------------------------------------ launchers */
-#ifndef WALK_P
-#define WALK_P 4
-#endif
+/* Positions per thread (P) follow the table size: the table decides how many walk CTAs fit an SM (227 KiB of shared
+ * memory), and ZB_BATCH / P threads per CTA keep about 32 warps resident in every case — fast tables (<= 56 KiB): 4 CTAs of
+ * 256 threads; <= 113 KiB: 2 CTAs of 512; the doubleFast tables (128 / 200 KiB): one CTA of 1024.  The result does not
+ * depend on P (a batch is ZB_BATCH positions whatever the thread count). */
+template <int MLS, int P>
+static cudaError_t zb_launch_walk_p(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 N, u32 insStep, const ZbStrides& sd,
+                                    u32 slotFirstBlock, u16* d_dist, u32* d_far, const u32* d_imageIn, u32* d_imageOut, cudaStream_t stream)
+{
+    cudaError_t const e = cudaFuncSetAttribute(zb_walk_kernel<MLS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    zb_walk_kernel<MLS, P><<<nbChunks, ZB_BATCH / P, (size_t)N * 4u, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut);
+    return cudaGetLastError();
+}
+template <int MLS>
+static cudaError_t zb_launch_walk_m(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 N, u32 insStep, const ZbStrides& sd,
+                                    u32 slotFirstBlock, u16* d_dist, u32* d_far, const u32* d_imageIn, u32* d_imageOut, cudaStream_t stream)
+{
+    size_t const smem = (size_t)N * 4u;
+    if (smem <= 56u * 1024u)  return zb_launch_walk_p<MLS, WALK_P_SMALL>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    if (smem <= 113u * 1024u) return zb_launch_walk_p<MLS, 2>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    return zb_launch_walk_p<MLS, 1>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+}
 static cudaError_t zb_launch_walk(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 mls, u32 N, u32 insStep, const ZbStrides& sd,
                                   u32 slotFirstBlock, u16* d_dist, u32* d_far, const u32* d_imageIn, u32* d_imageOut, cudaStream_t stream)
 {
-    size_t const smem = (size_t)N * 4u;
-    cudaError_t e = cudaSuccess;
-#define WALK_CASE(M) case M: \
-        e = cudaFuncSetAttribute(zb_walk_kernel<M, WALK_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e; \
-        zb_walk_kernel<M, WALK_P><<<nbChunks, ZB_BATCH / WALK_P, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
     switch (mls) {
-    WALK_CASE(4) WALK_CASE(5) WALK_CASE(6) WALK_CASE(7)
-    default: e = cudaFuncSetAttribute(zb_walk_kernel<8, WALK_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e != cudaSuccess) return e;
-        zb_walk_kernel<8, WALK_P><<<nbChunks, ZB_BATCH / WALK_P, smem, stream>>>(d_src, d_dictEnd, d_chunks, insStep, N, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut); break;
+    case 4: return zb_launch_walk_m<4>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    case 5: return zb_launch_walk_m<5>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    case 6: return zb_launch_walk_m<6>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    case 7: return zb_launch_walk_m<7>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    default: return zb_launch_walk_m<8>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
     }
-#undef WALK_CASE
-    return cudaGetLastError();
 }
 
 /* one-CTA launches that walk the dictionary tail and store the table(s) in d_image: prm->tableN u32 of the (short) table,
