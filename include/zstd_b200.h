@@ -62,8 +62,9 @@ ZSTDB200_API unsigned    ZSTD_getDictID_fromCDict(const ZSTD_CDict* cdict);
 ZSTDB200_API unsigned    ZSTD_getDictID_fromDict(const void* dict, size_t dictSize);
 
 /* lib/zstd.h:337-603 — the advanced one-shot API most bindings use today: sticky parameters on the context, then
- * ZSTD_compress2.  Honoured: ZSTD_c_compressionLevel, ZSTD_c_checksumFlag (XXH64 of the content, computed on the
- * host while the GPU compresses — such a frame is bound by that serial pass, ~10 GB/s; host buffers only),
+ * ZSTD_compress2.  Honoured: ZSTD_c_compressionLevel, ZSTD_c_checksumFlag (XXH64 of the content: a serial recurrence per
+ * frame — hashed by host threads while the GPU compresses when the input is in host memory, ~10 GB/s per frame; by one
+ * warp per frame on the device for device buffers, ~1 GB/s per frame, all frames of a call side by side),
  * ZSTD_c_dictIDFlag, ZSTD_c_contentSizeFlag (the size is always written).  Accepted and ignored: ZSTD_c_nbWorkers,
  * ZSTD_c_jobSize, ZSTD_c_overlapLog.  windowLog .. strategy and the long-distance-matching parameters only at 0;
  * anything else returns ZSTD_error_parameter_unsupported (40).  ZSTD_CCtx_loadDictionary copies and digests the
@@ -83,13 +84,27 @@ ZSTDB200_API size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, 
 ZSTDB200_API size_t ZSTD_CCtx_refCDict(ZSTD_CCtx* cctx, const ZSTD_CDict* cdict);
 ZSTDB200_API size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
 
-/* lib/zstd.h:681-803 — only the one-shot form of the streaming call (:787): the first call carries the whole input,
- * asks for ZSTD_e_end and offers at least ZSTD_compressBound(input) bytes of room; it then behaves like
- * ZSTD_compress2 and returns 0.  Any other use returns ZSTD_error_stage_wrong (60): streaming is out of scope. */
+/* lib/zstd.h:681-862 — streaming.  The GPU works on whole frames, so the stream front end collects input in the context
+ * and emits FRAMES: ZSTD_e_continue buffers (256 MiB of input become a frame of their own), ZSTD_e_flush turns what is
+ * buffered into a frame now, ZSTD_e_end does the same and ends the session.  The output is therefore a sequence of frames —
+ * every zstd decoder reads it as the concatenation of their contents (lib/zstd.h:160-162) — where the reference writes one
+ * frame; ZSTD_getFrameContentSize() of such output describes its first frame only.  A session's first call that brings
+ * everything with ZSTD_e_end and room for ZSTD_compressBound(size) bytes is compressed straight from the caller's buffers.
+ * Return value as in the reference: > 0 while output is still waiting (call again with more room), 0 when flushed / ended;
+ * with ZSTD_e_continue a hint for the next input size. */
 typedef struct ZSTD_inBuffer_s  { const void* src; size_t size; size_t pos; } ZSTD_inBuffer;
 typedef struct ZSTD_outBuffer_s { void* dst; size_t size; size_t pos; } ZSTD_outBuffer;
 typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;
 ZSTDB200_API size_t ZSTD_compressStream2(ZSTD_CCtx* cctx, ZSTD_outBuffer* output, ZSTD_inBuffer* input, ZSTD_EndDirective endOp);
+typedef ZSTD_CCtx ZSTD_CStream;                       /* lib/zstd.h:822: the same object */
+ZSTDB200_API ZSTD_CStream* ZSTD_createCStream(void);
+ZSTDB200_API size_t ZSTD_freeCStream(ZSTD_CStream* zcs);
+ZSTDB200_API size_t ZSTD_initCStream(ZSTD_CStream* zcs, int compressionLevel);
+ZSTDB200_API size_t ZSTD_compressStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output, ZSTD_inBuffer* input);
+ZSTDB200_API size_t ZSTD_flushStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output);
+ZSTDB200_API size_t ZSTD_endStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output);
+ZSTDB200_API size_t ZSTD_CStreamInSize(void);
+ZSTDB200_API size_t ZSTD_CStreamOutSize(void);
 
 /* lib/zstd.h:236,242-246,114-120 ; lib/zstd_errors.h:106 */
 ZSTDB200_API size_t      ZSTD_compressBound(size_t srcSize);
@@ -104,8 +119,10 @@ ZSTDB200_API const char* ZSTD_versionString(void);
 
 /* lib/zstd.h:170-299 — decompression.  Every frame the format allows is accepted: this library's
  * own and the reference encoder's at any level, concatenated frames, skippable frames, frames without a content size,
- * window sizes up to 128 MiB (the reference decoder's default limit, ZSTD_WINDOWLOG_LIMIT_DEFAULT = 27).  Not yet:
- * dictionaries (a frame that needs one fails with corruption_detected when it reaches into the missing history).
+ * window sizes up to 128 MiB (the reference decoder's default limit, ZSTD_WINDOWLOG_LIMIT_DEFAULT = 27), raw-content
+ * and zstd-format dictionaries (ZSTD_decompress_usingDict, lib/zstd.h:955: the dictionary's content is the history in front
+ * of every frame, its entropy tables and repeat offsets what a frame's first blocks may reuse; dictionary_wrong = 32 when a
+ * frame names another dictionary ID).
  * The content checksum of a frame that carries one is verified (host buffers; checksum_wrong = 22).
  * All decoding work is done by CUDA kernels (zb_decode.cu); no CPU fallback. */
 typedef struct ZSTD_DCtx_s ZSTD_DCtx;
@@ -113,6 +130,8 @@ ZSTDB200_API size_t     ZSTD_decompress(void* dst, size_t dstCapacity, const voi
 ZSTDB200_API ZSTD_DCtx* ZSTD_createDCtx(void);
 ZSTDB200_API size_t     ZSTD_freeDCtx(ZSTD_DCtx* dctx);                                    /* accepts NULL */
 ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+ZSTDB200_API size_t     ZSTD_decompress_usingDict(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                                                  const void* dict, size_t dictSize);
 /* lib/zstd.h:195-227 — header readers (host code).  ZSTD_CONTENTSIZE_UNKNOWN = (0ULL - 1), ZSTD_CONTENTSIZE_ERROR = (0ULL - 2). */
 ZSTDB200_API unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
 ZSTDB200_API size_t     ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
@@ -123,6 +142,9 @@ ZSTDB200_API size_t     ZSTD_findFrameCompressedSize(const void* src, size_t src
  * thread (a chain of dependent reads: about 1 us per block), everything else is block-parallel.  Content checksums are
  * not verified on this path.  `stream`: as for ZSTDB200_compressDevice.  Returns the decompressed size. */
 ZSTDB200_API size_t ZSTDB200_decompressDevice(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream);
+/* same with a dictionary (host memory; uploaded by the call) */
+ZSTDB200_API size_t ZSTDB200_decompressDevice_usingDict(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize,
+                                                        const void* dict, size_t dictSize, void* stream);
 typedef struct {
     float kernel_ms;         /* literals kernel start -> execute kernel end */
     float literals_ms, sequences_ms, execute_ms;
@@ -142,11 +164,24 @@ ZSTDB200_API void ZSTDB200_getLastDStats(const ZSTD_DCtx* dctx, ZSTDB200_dstats*
 ZSTDB200_API size_t ZSTDB200_compressDevice(ZSTD_CCtx* cctx, void* d_dst, size_t dstCapacity,
                                             const void* d_src, size_t srcSize, int compressionLevel, void* stream);
 
+/* One frame compressed by several GPUs (the reference's counterpart: the jobs of ZSTDMT, zstdmt_compress.c:1168-1227 —
+ * every job reads an overlap of the input in front of it, only the first writes the frame header, only the last the end
+ * mark).  Each rank calls this for its share [partBegin, partBegin + partSize) of a frame of frameSize bytes; partBegin must
+ * be a multiple of ZSTDB200_framePartAlignment() and d_part must point at the frame's byte partBegin - min(partBegin,
+ * ZSTDB200_framePartHalo()): the rank needs that much of the preceding input.  The ranks' outputs, concatenated in
+ * order, are byte for byte the frame a single ZSTDB200_compressDevice call produces (zstd_b200/sharding.py gathers them).
+ * No content checksum (ZSTD_c_checksumFlag must be off). */
+ZSTDB200_API size_t ZSTDB200_framePartAlignment(void);
+ZSTDB200_API size_t ZSTDB200_framePartHalo(void);
+ZSTDB200_API size_t ZSTDB200_compressFramePart(ZSTD_CCtx* cctx, void* d_dst, size_t dstCapacity, const void* d_part,
+                                               size_t frameSize, size_t partBegin, size_t partSize, int compressionLevel, void* stream);
+
 /* Compress nbFrames independent inputs src[frameOffsets[i] .. +frameSizes[i]) into nbFrames
  * complete frames written back to back into dst (the decoder accepts the concatenation,
  * lib/zstd.h:160-162).  cSizes[i] (host array, may be NULL) receives each frame's size.
  * With dict != NULL every frame is compressed as ZSTD_compress_usingDict would (config 5).
- * `deviceMemory` != 0: src/dst are device pointers (dict and the offset arrays stay on the host). */
+ * `deviceMemory` != 0: src/dst are device pointers (dict and the offset arrays stay on the host).
+ * The context's sticky ZSTD_c_checksumFlag / ZSTD_c_dictIDFlag apply to every frame of the call (level and dictionary are arguments). */
 ZSTDB200_API size_t ZSTDB200_compressFrames(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
                                             const void* src, const size_t* frameOffsets, const size_t* frameSizes,
                                             size_t nbFrames, const void* dict, size_t dictSize,

@@ -1,0 +1,34 @@
+"""Device-resident decompression timing on one GPU: frames written by this library and by the reference encoder.
+   python tests/bench_decode.py [size_MiB]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch, zref, zstd_b200
+
+mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+c, d = zstd_b200.ZSTD_CCtx(), zstd_b200.ZSTD_DCtx()
+for p, level in ((50, 1), (90, 3), (30, -3)):
+    src = zref.datagen(mib << 20, p)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = zstd_b200.ZSTD_compressBound(len(src))
+    d_c = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = c.compress_device(d_c.data_ptr(), cap, d_src.data_ptr(), len(src), level)
+    d_out = torch.empty(len(src), dtype=torch.uint8, device="cuda")
+    for what in ("ours", "reference"):
+        if what == "reference":
+            if not zref.have_ref() or mib > 256:
+                continue
+            frame = zref.ref_compress(src, level)
+            d_c = torch.frombuffer(bytearray(frame), dtype=torch.uint8).cuda(); n = len(frame)
+        best = None
+        for _ in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            m = d.decompress_device(d_out.data_ptr(), len(src), d_c.data_ptr(), n)
+            ev1.record(); torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            best = ms if best is None else min(best, ms)
+        st = d.stats()
+        ok = m == len(src) and torch.equal(d_out, d_src)
+        print(f"P{p} level {level} {what:9s}: {len(src) >> 20} MiB <- {n} B  {best:.2f} ms = {len(src) / best / 1e6:.1f} GB/s  "
+              f"[kernels {st.kernel_ms:.2f}: literals {st.literals_ms:.2f} sequences {st.sequences_ms:.2f} execute {st.execute_ms:.2f}; {st.nbBlocks} blocks]  ok {ok}", flush=True)

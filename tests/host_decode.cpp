@@ -4,6 +4,7 @@
  * (and of this repo's oracle) in the CPU test suite.  Built by tests/test_host_decode.py with g++; nothing in the
  * product links against it.
  *   size_t zbh_decompress(void* dst, size_t cap, const void* src, size_t size)  -> bytes written, or (size_t)-code
+ *   size_t zbh_decompress_usingDict(dst, cap, src, size, dict, dictSize)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -14,13 +15,15 @@
 #define ERR(c) ((size_t)-(long)(c))
 
 struct BlockOut { std::vector<u8> lits; std::vector<u64> seqs; u32 sumLL, sumML; ZbdRep transfer; };
+static const u8* g_dict = NULL;            /* the call's dictionary (single-threaded test code) */
+static ZbdDictInfo g_di;
 
 /* Huffman decoding table of the block `src` (the block whose tree description is used) */
-static u32 buildHuf(std::vector<u16>& table, u32* logOut, u32* descBytes, const u8* in, const ZbdBlock& sb)
+static u32 buildHuf(std::vector<u16>& table, u32* logOut, u32* descBytes, const u8* in, const std::vector<ZbdBlock>& B, u32 src)
 {
     u8 weights[256]; u32 nbSym = 0, log = 0; u32 fse[64]; short norm[16]; u16 next[16];
-    const u8* const p = in + sb.srcOff + sb.litHdr;
-    u32 const used = zbd_readHufWeights(weights, &nbSym, &log, p, sb.litComp, fse, norm, next);
+    const u8* const p = src == ZBD_DICT ? g_dict + g_di.hufOff : in + B[src].srcOff + B[src].litHdr;
+    u32 const used = zbd_readHufWeights(weights, &nbSym, &log, p, src == ZBD_DICT ? g_di.hufLen : B[src].litComp, fse, norm, next);
     if (!used) return ZBD_CORRUPT;
     u16 start[256];
     zbd_hufStarts(start, weights, nbSym, log);
@@ -38,7 +41,7 @@ static u32 decodeLiterals(BlockOut& o, const u8* in, const std::vector<ZbdBlock>
     if (b.litType == 0) { memcpy(o.lits.data(), c + b.litHdr, b.litRegen); return ZBD_OK; }
     if (b.litType == 1) { memset(o.lits.data(), c[b.litHdr], b.litRegen); return ZBD_OK; }
     std::vector<u16> table; u32 log = 0, desc = 0;
-    if (buildHuf(table, &log, &desc, in, B[b.hufSrc])) return ZBD_CORRUPT;
+    if (buildHuf(table, &log, &desc, in, B, b.hufSrc)) return ZBD_CORRUPT;
     if (b.litType == 3) desc = 0;                               /* treeless: the streams start right behind the header */
     if (desc > b.litComp) return ZBD_CORRUPT;
     const u8* s = c + b.litHdr + desc;
@@ -68,6 +71,14 @@ static u32 buildSeqTable(std::vector<u32>& t, u32* logOut, u32 stream, const u8*
         u32 const log = stream == 0 ? ZBD_LL_DEFAULT_LOG : (stream == 1 ? ZBD_OF_DEFAULT_LOG : ZBD_ML_DEFAULT_LOG);
         u32 const ms = stream == 1 ? ZBD_OF_DEFAULT_MAXSYM : maxSym[stream];
         for (u32 s = 0; s <= ms; s++) norm[s] = zbd_defaultNorm(stream, s);
+        t.assign((size_t)1 << log, 0);
+        zbd_buildFseTable(t.data(), norm, ms, log, next);
+        *logOut = log;
+        return ZBD_OK;
+    }
+    if (b.fseSrc[stream] == ZBD_DICT) {
+        u32 ms = 0, log = 0;
+        if (!zbd_readNCount(norm, &ms, &log, maxSym[stream], maxLog[stream], g_dict + g_di.fseOff[stream], g_di.fseLen[stream])) return ZBD_CORRUPT;
         t.assign((size_t)1 << log, 0);
         zbd_buildFseTable(t.data(), norm, ms, log, next);
         *logOut = log;
@@ -109,21 +120,26 @@ static u32 decodeSeqs(BlockOut& o, const u8* in, const std::vector<ZbdBlock>& B,
                                T[2].data(), logs[2], &o.sumLL, &o.sumML, &o.transfer);
 }
 
-extern "C" size_t zbh_decompress(void* dstv, size_t cap, const void* srcv, size_t size)
+extern "C" size_t zbh_decompress_usingDict(void* dstv, size_t cap, const void* srcv, size_t size, const void* dictv, size_t dictSize)
 {
     const u8* const in = (const u8*)srcv;
     u8* const dst = (u8*)dstv;
+    g_dict = (const u8*)dictv; memset(&g_di, 0, sizeof(g_di));
+    if (g_dict && dictSize) { u32 const de = zbd_parseDict(&g_di, g_dict, dictSize); if (de) return ERR(de); }
+    const u8* const content = g_dict ? g_dict + g_di.contentOff : NULL;
+    size_t const contentSize = g_dict ? dictSize - g_di.contentOff : 0;
     u32 nb = 0, nf = 0;
     u64 litBytes = 0, seqCount = 0;
-    u32 e = zbd_walk(in, size, NULL, 0, NULL, 0, &nb, &nf, &litBytes, &seqCount);
+    u32 e = zbd_walk(in, size, NULL, 0, NULL, 0, &nb, &nf, &litBytes, &seqCount, g_di.entropy != 0, g_di.dictID);
     if (e) return ERR(e);
     std::vector<ZbdBlock> B(nb ? nb : 1); std::vector<ZbdFrame> F(nf ? nf : 1);
-    e = zbd_walk(in, size, B.data(), nb, F.data(), nf, &nb, &nf, &litBytes, &seqCount);
+    e = zbd_walk(in, size, B.data(), nb, F.data(), nf, &nb, &nf, &litBytes, &seqCount, g_di.entropy != 0, g_di.dictID);
     if (e) return ERR(e);
     size_t out = 0;
     for (u32 f = 0; f < nf; f++) {
         size_t const frameStart = out;
         ZbdRep rep; rep.r[0] = 1; rep.r[1] = 4; rep.r[2] = 8;
+        if (g_di.entropy) { rep.r[0] = g_di.rep[0]; rep.r[1] = g_di.rep[1]; rep.r[2] = g_di.rep[2]; }
         for (u32 bi = F[f].firstBlock; bi < F[f].firstBlock + F[f].nbBlocks; bi++) {
             const ZbdBlock& b = B[bi];
             if (b.type == ZB_BT_RAW) { if (out + b.rawSize > cap) return ERR(70); memcpy(dst + out, in + b.srcOff, b.rawSize); out += b.rawSize; continue; }
@@ -143,8 +159,12 @@ extern "C" size_t zbh_decompress(void* dstv, size_t cap, const void* srcv, size_
                 u32 const ll = ZBD_SEQ_LL(q), ml = ZBD_SEQ_ML(q);
                 u32 const off = zbd_rep_apply(&rep, ZBD_SEQ_OFF(q), ll, false);
                 memcpy(dst + out, o.lits.data() + lp, ll); out += ll; lp += ll;
-                if (off == 0 || off > out - frameStart) return ERR(ZBD_CORRUPT);
-                for (u32 k = 0; k < ml; k++) dst[out + k] = dst[out - off + (k % off)];     /* the gather form the kernel uses */
+                size_t const inFrame = out - frameStart;
+                if (off == 0 || off > inFrame + contentSize) return ERR(ZBD_CORRUPT);
+                for (u32 k = 0; k < ml; k++) {                      /* the gather form the kernel uses; positions in front of the frame are dictionary content */
+                    long long const sp = (long long)inFrame - (long long)off + (long long)(k % off);
+                    dst[out + k] = sp < 0 ? content[(long long)contentSize + sp] : dst[frameStart + sp];
+                }
                 out += ml;
             }
             memcpy(dst + out, o.lits.data() + lp, b.litRegen - lp); out += b.litRegen - lp;
@@ -154,3 +174,4 @@ extern "C" size_t zbh_decompress(void* dstv, size_t cap, const void* srcv, size_
     }
     return out;
 }
+extern "C" size_t zbh_decompress(void* dst, size_t cap, const void* src, size_t size) { return zbh_decompress_usingDict(dst, cap, src, size, NULL, 0); }

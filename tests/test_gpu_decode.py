@@ -1,6 +1,7 @@
 """GPU decompression (pytest -m gpu): ZSTD_decompress / ZSTD_decompressDCtx / ZSTDB200_decompressDevice through the C ABI
 must reproduce the input of this library's own frames and of the reference encoder's frames (every level), and must
 agree with the reference decoder on the reference's golden vectors."""
+import ctypes
 import glob
 import os
 
@@ -108,3 +109,34 @@ def test_device_buffers(cctx, dctx):
     assert n == len(src) and bytes(d_out.cpu().numpy()) == src
     st = dctx.stats()
     assert st.nbFrames == 2 and st.nbBlocks == 72
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["zdict", "raw"])
+def test_dictionaries(cctx, dctx, kind):
+    """ZSTD_decompress_usingDict: frames written with a dictionary by the reference (every level) and by this library"""
+    d = zref.golden_input("zdict-16k-synthetic-seed77") if kind == "zdict" else zref.synthetic(20_000, 5, 0.5)
+    L = zstd_b200.lib()
+    L.ZSTD_decompress_usingDict.restype = ctypes.c_size_t
+    L.ZSTD_decompress_usingDict.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+
+    def dec(frames, n):
+        out = ctypes.create_string_buffer(max(n, 1))
+        r = L.ZSTD_decompress_usingDict(dctx._h, out, n, frames, len(frames), d, len(d))
+        assert not L.ZSTD_isError(r), L.ZSTD_getErrorName(r)
+        return out.raw[:r]
+    for n in (0, 1, 100, 1000, 5000, 200_000):
+        src = zref.synthetic(n, 31, 0.5) if n else b""
+        for level in (1, 3, -3, 6, 19):
+            assert dec(zref.ref_compress_using_dict(src, d, level), n) == src, (n, level)
+        for level in (1, 3):
+            assert dec(cctx.compress_using_dict(src, d, level), n) == src, (n, level)
+    # config 5 in miniature: many records, one call
+    recs = [zref.synthetic(1024, 100 + i, 0.5) for i in range(300)]
+    stream = b"".join(zref.ref_compress_using_dict(r, d, 1) for r in recs)
+    assert dec(stream, 300 * 1024) == b"".join(recs)
+    if kind == "zdict":                                        # a frame that names another dictionary
+        other = bytearray(d); other[4] ^= 1
+        out = ctypes.create_string_buffer(2048)
+        r = L.ZSTD_decompress_usingDict(dctx._h, out, 2048, stream[:200], 200, bytes(other), len(other))
+        assert L.ZSTD_isError(r)

@@ -348,10 +348,93 @@ def test_compress2_dictionaries_and_stream2_oneshot(ctx):
     o = Buf(ctypes.cast(dst, ctypes.c_void_p), cap, 0); i = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(src), 0)
     r = L.ZSTD_compressStream2(c._h, ctypes.byref(o), ctypes.byref(i), 2)
     assert r == 0 and i.pos == len(src) and dst.raw[:o.pos] == zref.oracle_compress(src, 1)
-    o2 = Buf(ctypes.cast(dst, ctypes.c_void_p), 10, 0); i2 = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(src), 0)
-    r = L.ZSTD_compressStream2(c._h, ctypes.byref(o2), ctypes.byref(i2), 0)          # ZSTD_e_continue: not served
-    assert L.ZSTD_isError(r) and L.ZSTD_getErrorCode(r) == 60
     cd.close(); c.close()
+
+
+def _stream(c, chunks, directives, out_room):
+    """drive ZSTD_compressStream2 the way an application does: feed chunks[i] with directives[i], draining into buffers of
+    out_room bytes until the call reports completion; returns everything that came out"""
+    L = zstd_b200.lib()
+
+    class Buf(ctypes.Structure):
+        _fields_ = [("p", ctypes.c_void_p), ("size", ctypes.c_size_t), ("pos", ctypes.c_size_t)]
+    out = bytearray()
+    dst = ctypes.create_string_buffer(out_room)
+    for chunk, d in zip(chunks, directives):
+        sbuf = ctypes.create_string_buffer(chunk, max(len(chunk), 1))
+        i = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(chunk), 0)
+        for _ in range(100000):
+            o = Buf(ctypes.cast(dst, ctypes.c_void_p), out_room, 0)
+            r = L.ZSTD_compressStream2(c._h, ctypes.byref(o), ctypes.byref(i), d)
+            assert not L.ZSTD_isError(r), L.ZSTD_getErrorName(r)
+            out += dst.raw[:o.pos]
+            if i.pos == i.size and (d == 0 or r == 0):
+                break
+        else:
+            raise AssertionError("stream made no progress")
+    return bytes(out)
+
+
+def test_streaming_continue_flush_end():
+    """ZSTD_compressStream2 with ZSTD_e_continue / ZSTD_e_flush / ZSTD_e_end (lib/zstd.h:681-803): the output is a sequence of
+    frames whose contents concatenate to the input; each flush makes everything given so far decodable"""
+    src = zref.synthetic(700_000, 77, 0.5)
+    c = zstd_b200.ZSTD_CCtx()
+    c.set_parameter("compression_level", 1)
+    parts = [src[:100_000], src[100_000:100_001], src[100_001:450_000], b"", src[450_000:]]
+    # everything buffered, one frame at the end
+    got = _stream(c, parts, [0, 0, 0, 0, 2], out_room=1 << 20)
+    assert got == zref.oracle_compress(src, 1)
+    # a flush in the middle: two frames; small output buffers: the frames trickle out
+    got = _stream(c, parts, [0, 1, 0, 0, 2], out_room=4096)
+    assert got == zref.oracle_compress(src[:100_001], 1) + zref.oracle_compress(src[100_001:], 1)
+    if zref.have_ref():
+        assert zref.ref_decompress(got, len(src)) == src
+    # an empty session is an empty frame; the context is reusable afterwards
+    assert _stream(c, [b""], [2], out_room=64) == zref.oracle_compress(b"", 1)
+    # the older entry points
+    L = zstd_b200.lib()
+    L.ZSTD_initCStream.restype = ctypes.c_size_t; L.ZSTD_initCStream.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert L.ZSTD_initCStream(c._h, -3) == 0
+    assert _stream(c, [src[:5000], b""], [0, 2], out_room=1 << 16) == zref.oracle_compress(src[:5000], -3)
+    c.close()
+
+
+def test_checksums_device_buffers_and_many_frames(ctx):
+    """ZSTD_c_checksumFlag for device buffers (hashed by a warp per frame on the device) and for batch calls (host threads
+    for host buffers): every frame carries the XXH64 low word the reference decoder verifies"""
+    import torch
+    sizes = [0, 1, 31, 32, 33, 1000, 4096, 70_000, 300_001, 7]
+    src = zref.synthetic(sum(sizes), 5, 0.5)
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o); o += n
+    c = zstd_b200.ZSTD_CCtx()
+    c.set_parameter("checksum_flag", 1)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = sum(zstd_b200.ZSTD_compressBound(n) + 32 for n in sizes)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    total, csz = c.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), offs, sizes, level=1)
+    dev = bytes(d_dst[:total].cpu().numpy())
+    h_dst = ctypes.create_string_buffer(cap)
+    sbuf = ctypes.create_string_buffer(src, len(src))
+    total_h, csz_h = c.compress_frames(ctypes.addressof(h_dst), cap, ctypes.addressof(sbuf), offs, sizes, level=1, device_memory=False)
+    assert h_dst.raw[:total_h] == dev and csz == csz_h
+    pos = 0
+    for off, n, k in zip(offs, sizes, csz):
+        frame = dev[pos:pos + k]
+        assert frame == _with_checksum(zref.oracle_compress(src[off:off + n], 1), src[off:off + n])
+        pos += k
+    if zref.have_ref():
+        assert zref.ref_decompress(dev, len(src)) == src       # the reference decoder checks every checksum
+    # a big single frame in device memory goes through the wave executor
+    big = zref.synthetic(300 << 20, 9, 0.5) if os.environ.get("ZB_BIG_TESTS") else zref.synthetic(3 << 20, 9, 0.5)
+    d_big = torch.frombuffer(bytearray(big), dtype=torch.uint8).cuda()
+    capb = zstd_b200.ZSTD_compressBound(len(big)) + 8
+    d_out = torch.empty(capb, dtype=torch.uint8, device="cuda")
+    n = c.compress_device(d_out.data_ptr(), capb, d_big.data_ptr(), len(big), level=1)
+    assert bytes(d_out[:n].cpu().numpy()) == _with_checksum(zref.oracle_compress(big, 1), big)
+    c.close()
 
 
 def test_mixed_frame_lists(ctx):
@@ -373,3 +456,29 @@ def test_mixed_frame_lists(ctx):
         assert out[pos:pos + c] == zref.oracle_compress(src[off:off + n], 1), (off, n)
         pos += c
     assert pos == total
+
+
+@pytest.mark.parametrize("level", [1, 3])
+@pytest.mark.parametrize("size,world", [(5 * (512 << 10) + 12345, 3), (3 << 20, 8), (400_000, 2), (0, 2)])
+def test_one_frame_split_over_ranks(ctx, level, size, world):
+    """ZSTDB200_compressFramePart: the shares of one frame, each compressed from its own copy of (halo + share) as a rank
+    would hold it, concatenate to exactly the frame a single call produces"""
+    import torch
+    from zstd_b200.sharding import split_one_frame
+    L = zstd_b200.lib()
+    L.ZSTDB200_framePartHalo.restype = ctypes.c_size_t
+    L.ZSTDB200_framePartAlignment.restype = ctypes.c_size_t
+    halo, align = L.ZSTDB200_framePartHalo(), L.ZSTDB200_framePartAlignment()
+    src = zref.synthetic(size, 17, 0.5)
+    whole = ctx.compress(src, level)
+    out = b""
+    for begin, n in split_one_frame(size, world, align):
+        if begin < 0:
+            continue
+        lo = begin - min(begin, halo)
+        part = torch.frombuffer(bytearray(src[lo:begin + n]) or bytearray(1), dtype=torch.uint8).cuda()      # only what the rank holds
+        cap = zstd_b200.ZSTD_compressBound(n) + 64
+        d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        k = ctx.compress_frame_part(d_dst.data_ptr(), cap, part.data_ptr(), size, begin, n, level)
+        out += bytes(d_dst[:k].cpu().numpy())
+    assert out == whole

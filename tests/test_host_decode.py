@@ -102,3 +102,24 @@ def test_truncated_and_garbage(H):
     assert dec(H, frame[: len(frame) // 2], len(data))[0] == "ERR"
     assert dec(H, b"\x00\x01\x02\x03\x04\x05\x06\x07", 100) == ("ERR", 10)          # prefix_unknown
     assert dec(H, frame, len(data) - 1) == ("ERR", 70)                              # dstSize_tooSmall
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["zdict", "raw"])
+def test_dictionaries(H, kind):
+    d = zref.golden_input("zdict-16k-synthetic-seed77") if kind == "zdict" else zref.synthetic(20_000, 5, 0.5)
+    H.zbh_decompress_usingDict.restype = ctypes.c_size_t
+    H.zbh_decompress_usingDict.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+
+    def dd(frame, n):
+        out = ctypes.create_string_buffer(n + 16)
+        r = H.zbh_decompress_usingDict(out, n, frame, len(frame), d, len(d))
+        return ("ERR", (1 << 64) - r) if r > (1 << 63) else out.raw[:r]
+    for n in (0, 1, 100, 1000, 5000, 200_000):
+        src = zref.synthetic(n, 31, 0.5) if n else b""
+        for level in (1, 3, -3, 6, 19):
+            assert dd(zref.ref_compress_using_dict(src, d, level), n) == src, (n, level)
+        for level in (1, 3):
+            assert dd(zref.oracle_compress_using_dict(src, d, level), n) == src, (n, level)
+    recs = [zref.synthetic(1024, 100 + i, 0.5) for i in range(50)]
+    assert dd(b"".join(zref.ref_compress_using_dict(r, d, 1) for r in recs), 50 * 1024) == b"".join(recs)

@@ -127,4 +127,4 @@ def test_one_rule_for_all_datagen_types(p, level):
     ours = zref.oracle_compress(src, level)
     ref = zref.ref_compress(src, level)
     assert zref.ref_decompress(ours, len(src)) == src
-    assert abs(len(ours) - len(ref)) <= zref.SIZE_TOLERANCE * len(ref), f"{(len(ours) - len(ref)) / len(ref):+.4%}"
+    assert zref.size_delta_ok(len(ours), len(ref), len(src)), f"{(len(ours) - len(ref)) / len(ref):+.4%}"

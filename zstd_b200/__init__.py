@@ -257,6 +257,15 @@ class ZSTD_CCtx:
         """One frame, device pointers (ints, e.g. torch.Tensor.data_ptr()).  Returns compressed size."""
         return _check(lib().ZSTDB200_compressDevice(self._h, d_dst, dst_capacity, d_src, src_size, level, stream))
 
+    def compress_frame_part(self, d_dst: int, dst_capacity: int, d_part: int, frame_size: int, part_begin: int, part_size: int,
+                            level: int = 3, stream: int = 0) -> int:
+        """This rank's share of a frame several GPUs compress together (ZSTDB200_compressFramePart).  d_part: device address
+        of the frame's byte part_begin - min(part_begin, halo).  Returns the bytes this share contributes."""
+        L = lib()
+        L.ZSTDB200_compressFramePart.restype = _sz
+        L.ZSTDB200_compressFramePart.argtypes = [_vp, _vp, _sz, _vp, _sz, _sz, _sz, ctypes.c_int, _vp]
+        return _check(L.ZSTDB200_compressFramePart(self._h, d_dst, dst_capacity, d_part, frame_size, part_begin, part_size, level, stream))
+
     def compress_frames(self, dst: int, dst_capacity: int, src: int, offsets: Sequence[int], sizes: Sequence[int],
                         level: int = 3, device_memory: bool = True, dict_bytes=None, stream: int = 0):
         """Many independent frames in one call.  Returns (total_bytes, [compressed size per frame])."""

@@ -14,6 +14,7 @@
 #include <string.h>
 #include <vector>
 #include <mutex>
+#include <thread>
 #include <time.h>
 #include "../../include/zstd_b200.h"
 #include "zb_common.h"
@@ -162,6 +163,12 @@ struct ZSTD_CCtx_s {
     const ZSTD_CDict* advRefCDict; /* ZSTD_CCtx_refCDict: borrowed */
     /* per-call frame options, consumed by the planner */
     u32 callChecksum, callNoDictID;
+    u64 callPartBegin, callPartEnd;   /* ZSTDB200_compressFramePart: this call's share of the frame (0, 0 = all of it) */
+    /* streaming front end (ZSTD_compressStream2 with ZSTD_e_continue / ZSTD_e_flush): input collected on the host, compressed
+     * output waiting to be handed out */
+    u8* stIn; size_t stInSize, stInCap;
+    u8* stOut; size_t stOutSize, stOutPos, stOutCap;
+    int stFrames;                  /* frames produced in the current session */
 };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -249,6 +256,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (!c) return 0;
     ZbDeviceGuard guard;
     ZSTD_freeCDict(c->advLocalDict);
+    free(c->stIn); free(c->stOut);
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
@@ -333,8 +341,10 @@ static int g_strictLevels = 0;
  * that level); after ZSTDB200_setStrictLevels(1) such calls fail with parameter_unsupported instead. */
 extern "C" void ZSTDB200_setStrictLevels(int on) { g_strictLevels = on; }
 
+/* partBegin / partEnd: only the blocks that start inside [partBegin, partEnd) of the (single) frame are planned — one rank's
+ * share of a frame that several GPUs compress together (ZSTDB200_compressFramePart); the geometry is the whole frame's. */
 static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames, int level,
-                    size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep)
+                    size_t dictSize, size_t dictTail, u32 dictID, const u32* dictRep, u64 partBegin = 0, u64 partEnd = ~0ull)
 {
     P.frames.resize(nbFrames);
     P.blocks.reserve(nbFrames);
@@ -372,6 +382,7 @@ static void zb_plan(ZbPlan& P, u32 frameChecksum, const size_t* frameOffsets, co
         u64 pos = 0;
         do {
             u64 const bsz = (fsz - pos) < blockMax ? (fsz - pos) : blockMax;
+            if (pos < partBegin || pos >= partEnd) { pos += bsz; continue; }      /* another rank's block */
             if (pos % chunkBytes == 0) {                         /* a new chunk starts with this block */
                 ZbChunk ch; memset(&ch, 0, sizeof(ch));
                 ch.srcOff = fr.srcOff + pos; ch.size = (u32)((fsz - pos) < chunkBytes ? (fsz - pos) : chunkBytes);
@@ -534,11 +545,11 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
                                       const size_t* frameOffsets, const size_t* frameSizes, size_t nbFrames,
                                       const void* dict, size_t dictSize, const ZSTD_CDict* cdict, size_t* cSizes, int level, cudaStream_t stream)
 {
-    if (c->callChecksum) return ZB_ERR(ZB_error_parameter_unsupported);      /* the frame checksum is computed by the host: host-buffer calls only */
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
+    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL,
+            c->callPartBegin, c->callPartEnd ? c->callPartEnd : ~0ull);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
     {   size_t e = zb_ensureDesc(c, nbBlocks, nbFrames, 1, P.chunks.size()); if (zb_isErr(e)) return e;
@@ -553,6 +564,7 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
     {   size_t const e = zb_runBlocks(c, P, d_src, d_dictEnd, 0, nbBlocks, 0, (u32)P.chunks.size(), 0, stream, true, &launches); if (zb_isErr(e)) return e; }
     CK(zb_launch_stitch(d_src, c->d_blocks, nbBlocks, c->d_frames, c->d_body, P.sd.body, c->d_meta, c->d_outOffsets, NULL, c->d_totals, d_dst, dstCapacity, stream));
     launches += 2;
+    if (c->callChecksum) { CK(zb_launch_checksums(d_src, c->d_frames, (u32)nbFrames, c->d_outOffsets, d_dst, dstCapacity, stream)); launches++; }   /* device buffers: hashed on the device, a warp per frame */
     if (cSizes) { CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, stream)); launches++; }
     CK(cudaEventRecord(c->evKEnd, stream));
     CK(cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(u64), cudaMemcpyDeviceToHost, stream));
@@ -638,10 +650,10 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
     ZbPlan P;
-    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL);
+    zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL,
+            c->callPartBegin, c->callPartEnd ? c->callPartEnd : ~0ull);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
     u32 const nbBlocks = (u32)P.blocks.size();
-    if (c->callChecksum && (deviceMemory || nbFrames != 1)) return ZB_ERR(ZB_error_parameter_unsupported);   /* the checksum is a host pass over one frame */
     /* a wave is sized in bytes of input (and of workspace): calls made of small blocks get proportionally more blocks per wave */
     u32 const ZB_WAVE_BLOCKS = (u32)((u64)waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist) > (1u << 22) ? (1u << 22) : waveBlocks128 * (ZB_BLOCK_MAX / P.sd.dist));
     /* wave boundaries.  Host path: the call ends when the LAST wave has gone through every kernel, so the
@@ -730,7 +742,22 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
         }
     }
     double const hostEnq = zb_now() - hostT0;
-    u64 const xxh = (c->callChecksum && !err) ? zb_xxh64(src + frameOffsets[0], frameSizes[0]) : 0;      /* while the GPU works */
+    /* content checksums.  Host buffers: XXH64 on host threads while the GPU works (a serial recurrence per frame: ~10 GB/s
+     * per thread).  Device buffers: a warp per frame once the last wave is stitched. */
+    std::vector<u64> xxh;
+    if (c->callChecksum && !err && !deviceMemory) {
+        xxh.resize(nbFrames);
+        size_t const nt = nbFrames < 8 ? nbFrames : 8;
+        if (nt <= 1) xxh[0] = zb_xxh64(src + frameOffsets[0], frameSizes[0]);
+        else {
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nt; t++) th.emplace_back([&, t] { for (size_t f = t; f < nbFrames; f += nt) xxh[f] = zb_xxh64(src + frameOffsets[f], frameSizes[f]); });
+            for (size_t t = 0; t < nt; t++) th[t].join();
+        }
+    }
+    if (c->callChecksum && !err && deviceMemory) { CK(zb_launch_checksums(d_in, c->d_frames, (u32)nbFrames, c->d_outOffsets, d_out, outCap, lastStream)); launches++; }
+    bool const wantSizes = cSizes != NULL || (c->callChecksum && !deviceMemory);
+    std::vector<u64> fsz;
     u64 prev = 0, total = 0;
     if (download || timeline) {
         /* drain: as each wave's size becomes known, ship its bytes */
@@ -743,12 +770,12 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
             if (timeline) CK(cudaEventRecord(evD2H[w], download ? sD2H : lastStream));
         }
     }
-    if (!err && cSizes) {
+    if (!err && wantSizes) {
         CK(zb_launch_frame_sizes(c->d_frames, (u32)nbFrames, c->d_outOffsets, c->d_frameSizes, lastStream));
-        std::vector<u64> tmp(nbFrames);
-        CK(cudaMemcpyAsync(tmp.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, lastStream));
+        fsz.resize(nbFrames);
+        CK(cudaMemcpyAsync(fsz.data(), c->d_frameSizes, nbFrames * sizeof(u64), cudaMemcpyDeviceToHost, lastStream));
         CK(cudaStreamSynchronize(lastStream));
-        for (size_t f = 0; f < nbFrames; f++) cSizes[f] = (size_t)tmp[f];
+        if (cSizes) for (size_t f = 0; f < nbFrames; f++) cSizes[f] = (size_t)fsz[f];
     }
     /* the last wave's stitch is ordered behind every earlier one (evStitch chain) */
     if (download) { CK(cudaEventRecord(c->evEnd, sD2H)); CK(cudaStreamSynchronize(sD2H)); }
@@ -756,9 +783,14 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     for (u32 s = 0; s < slots; s++) if (c->waveStream[s]) CK(cudaStreamSynchronize(c->waveStream[s]));
     CK(cudaStreamSynchronize(sCopy));
     if (!err && nbWaves) total = c->h_totals[nbWaves - 1];
-    if (!err && c->callChecksum && total >= 4 && total <= dstCapacity) {                                  /* the 4 bytes the stitch kernel left free */
-        u32 const ck = (u32)xxh;
-        dst[total - 4] = (u8)ck; dst[total - 3] = (u8)(ck >> 8); dst[total - 2] = (u8)(ck >> 16); dst[total - 1] = (u8)(ck >> 24);
+    if (!err && c->callChecksum && !deviceMemory && total <= dstCapacity) {                               /* the 4 bytes the size scan left free behind every frame */
+        u64 end = 0;
+        for (size_t f = 0; f < nbFrames; f++) {
+            end += fsz[f];
+            if (end < 4 || end > total) break;
+            u32 const ck = (u32)xxh[f];
+            dst[end - 4] = (u8)ck; dst[end - 3] = (u8)(ck >> 8); dst[end - 2] = (u8)(ck >> 16); dst[end - 1] = (u8)(ck >> 24);
+        }
     }
     if (timeline) {
         fprintf(stderr, "zstd_b200 timeline (ms after the call's first enqueue; host enqueue loop took %.3f ms; %s)\n", 1e3 * hostEnq,
@@ -816,7 +848,11 @@ extern "C" size_t ZSTDB200_compressFrames(ZSTD_CCtx* c, void* dst, size_t dstCap
                                           size_t nbFrames, const void* dict, size_t dictSize,
                                           size_t* cSizes, int level, int deviceMemory, void* streamv)
 {
-    return zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, dict, dictSize, NULL, cSizes, level, deviceMemory, streamv);
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    c->callChecksum = (u32)c->advChecksum; c->callNoDictID = (u32)c->advNoDictID;      /* the sticky frame parameters of ZSTD_CCtx_setParameter apply */
+    size_t const r = zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, dict, dictSize, NULL, cSizes, level, deviceMemory, streamv);
+    c->callChecksum = 0; c->callNoDictID = 0;
+    return r;
 }
 
 extern "C" size_t ZSTDB200_compressFrames_usingCDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity,
@@ -825,7 +861,11 @@ extern "C" size_t ZSTDB200_compressFrames_usingCDict(ZSTD_CCtx* c, void* dst, si
                                                      size_t* cSizes, int deviceMemory, void* streamv)
 {
     if (!cdict) return ZB_ERR(ZB_error_dictionary_wrong);                        /* zstd_compress.c:5753 */
-    return zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, NULL, 0, cdict, cSizes, cdict->level, deviceMemory, streamv);
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    c->callChecksum = (u32)c->advChecksum; c->callNoDictID = (u32)c->advNoDictID;
+    size_t const r = zb_compressFramesAny(c, dst, dstCapacity, src, frameOffsets, frameSizes, nbFrames, NULL, 0, cdict, cSizes, cdict->level, deviceMemory, streamv);
+    c->callChecksum = 0; c->callNoDictID = 0;
+    return r;
 }
 
 /* ------------------------------------------------------------------ digested dictionaries (lib/zstd.h:967-995) */
@@ -885,6 +925,30 @@ extern "C" size_t ZSTD_compress_usingCDict(ZSTD_CCtx* c, void* dst, size_t dstCa
     if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
     if (dstCapacity < 18) return ZB_ERR(ZB_error_dstSize_tooSmall);
     return zb_compressFramesAny(c, dst, dstCapacity, src, &off, &srcSize, 1, NULL, 0, cdict, NULL, cdict->level, 0, NULL);
+}
+
+/* One rank's share of a frame that several GPUs compress together (the reference's counterpart are the jobs
+ * of ZSTDMT, zstdmt_compress.c:1168-1227: a job reads an overlap of preceding input and only the first writes the frame
+ * header, only the last the end mark).  Chunks are the unit: partBegin must be a multiple of ZSTDB200_framePartAlignment()
+ * (512 KiB), and the bytes [partBegin - ZSTDB200_framePartHalo(), partBegin + partSize) of the frame must be resident:
+ * d_part points at frame offset partBegin - min(partBegin, halo).  The ranks' outputs, concatenated in order, are byte
+ * for byte the frame one GPU would have produced. */
+extern "C" size_t ZSTDB200_framePartAlignment(void) { return (size_t)ZB_CHUNK_BLOCKS * ZB_BLOCK_MAX; }
+extern "C" size_t ZSTDB200_framePartHalo(void) { return ZB_PRIME_BYTES; }
+extern "C" size_t ZSTDB200_compressFramePart(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity, const void* d_part,
+                                             size_t frameSize, size_t partBegin, size_t partSize, int level, void* stream)
+{
+    if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (partBegin % ZSTDB200_framePartAlignment() || partBegin + partSize > frameSize || (partSize == 0 && frameSize != 0)) return ZB_ERR(ZB_error_srcSize_wrong);
+    if (c->advChecksum) return ZB_ERR(ZB_error_parameter_unsupported);          /* a content checksum needs the whole content in one place */
+    size_t const halo = partBegin < ZB_PRIME_BYTES ? partBegin : ZB_PRIME_BYTES;
+    const u8* const frameBase = (const u8*)d_part + halo - partBegin;          /* address frame offset 0 would have; only offsets >= partBegin - halo are touched */
+    size_t const off = 0;
+    c->callPartBegin = partBegin; c->callPartEnd = partBegin + partSize; c->callNoDictID = (u32)c->advNoDictID;
+    if (frameSize == 0) { c->callPartBegin = 0; c->callPartEnd = 1; }
+    size_t const r = zb_compressFramesAny(c, d_dst, dstCapacity, frameBase, &off, &frameSize, 1, NULL, 0, NULL, NULL, level, 1, stream);
+    c->callPartBegin = 0; c->callPartEnd = 0; c->callNoDictID = 0;
+    return r;
 }
 
 extern "C" size_t ZSTDB200_compressDevice(ZSTD_CCtx* c, void* d_dst, size_t dstCapacity,
@@ -978,6 +1042,7 @@ extern "C" size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* c, unsigned long long) 
 extern "C" size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective reset)                                   /* zstd_compress.c:1390; 1 session, 2 parameters, 3 both */
 {
     if (!c) return ZB_ERR(ZB_error_GENERIC);
+    if (reset == 1 || reset == 3) { c->stInSize = 0; c->stOutSize = 0; c->stOutPos = 0; c->stFrames = 0; }   /* an unfinished stream is dropped */
     if (reset == 2 || reset == 3) {
         c->advLevel = 3; c->advChecksum = 0; c->advNoDictID = 0;
         ZSTD_freeCDict(c->advLocalDict); c->advLocalDict = NULL; c->advRefCDict = NULL;
@@ -1016,19 +1081,99 @@ extern "C" size_t ZSTD_compress2(ZSTD_CCtx* c, void* dst, size_t dstCapacity, co
     return r;
 }
 
+/* Streaming (lib/zstd.h:681-862).  The unit of GPU work is a whole frame, so the stream front end collects input on the
+ * host and turns it into frames:
+ *   ZSTD_e_continue  input is taken into the context's buffer; whenever ZB_STREAM_FRAME bytes are there they become a frame;
+ *   ZSTD_e_flush     what is buffered becomes a frame now (the reference ends a block, here a frame ends: every byte given
+ *                    so far is decodable from the output, which is what a flush promises);
+ *   ZSTD_e_end       same, and the session is over once everything was handed out (an empty session yields an empty frame).
+ * The result is a sequence of frames — a valid zstd stream that every decoder reads as the concatenation of their contents
+ * (lib/zstd.h:160-162; contrib/pzstd writes the same shape) — not one frame as the reference's stream would be.
+ * The first call of a session carrying everything with ZSTD_e_end and room for ZSTD_compressBound() bytes is served without
+ * any buffering (the one-shot form, lib/zstd.h:787).  Return value: bytes still waiting to be handed out (0 = flushed). */
+#define ZB_STREAM_FRAME ((size_t)256 << 20)
+static size_t zb_streamHandOut(ZSTD_CCtx* c, ZSTD_outBuffer* out)
+{
+    size_t const have = c->stOutSize - c->stOutPos, room = out->size - out->pos;
+    size_t const n = have < room ? have : room;
+    if (n) { memcpy((u8*)out->dst + out->pos, c->stOut + c->stOutPos, n); out->pos += n; c->stOutPos += n; }
+    if (c->stOutPos == c->stOutSize) { c->stOutPos = 0; c->stOutSize = 0; }
+    return c->stOutSize - c->stOutPos;
+}
+static size_t zb_streamMakeFrame(ZSTD_CCtx* c)                        /* stIn -> one frame appended to stOut */
+{
+    size_t const bound = ZSTD_compressBound(c->stInSize) + 32;
+    if (c->stOutSize + bound > c->stOutCap) {
+        size_t const cap = c->stOutSize + bound;
+        u8* const p = (u8*)realloc(c->stOut, cap);
+        if (!p) return ZB_ERR(ZB_error_memory_allocation);
+        c->stOut = p; c->stOutCap = cap;
+    }
+    size_t const r = ZSTD_compress2(c, c->stOut + c->stOutSize, bound, c->stIn ? c->stIn : (const u8*)"", c->stInSize);
+    if (ZSTD_isError(r)) return r;
+    c->stOutSize += r; c->stInSize = 0; c->stFrames++;
+    return 0;
+}
 extern "C" size_t ZSTD_compressStream2(ZSTD_CCtx* c, ZSTD_outBuffer* out, ZSTD_inBuffer* in, ZSTD_EndDirective endOp)       /* zstd_compress.c:6176 */
 {
     if (!c || !out || !in) return ZB_ERR(ZB_error_GENERIC);
     if (out->pos > out->size) return ZB_ERR(ZB_error_dstSize_tooSmall);
     if (in->pos > in->size) return ZB_ERR(ZB_error_srcSize_wrong);
+    if ((int)endOp < 0 || (int)endOp > 2) return ZB_ERR(ZB_error_parameter_unsupported);
     size_t const n = in->size - in->pos, room = out->size - out->pos;
-    /* the one-shot form of lib/zstd.h:787: everything is here, the frame ends now, and the output surely fits */
-    if (endOp != ZSTD_e_end || room < ZSTD_compressBound(n)) return ZB_ERR(ZB_error_stage_wrong);
-    size_t const r = ZSTD_compress2(c, (u8*)out->dst + out->pos, room, (const u8*)in->src + in->pos, n);
-    if (ZSTD_isError(r)) return r;
-    in->pos = in->size; out->pos += r;
-    return 0;                                                                                /* frame complete, nothing left to flush */
+    bool const idle = c->stInSize == 0 && c->stOutSize == 0 && c->stFrames == 0;
+    if (idle && endOp == ZSTD_e_end && room >= ZSTD_compressBound(n)) {      /* one-shot: straight from the caller's buffers */
+        size_t const r = ZSTD_compress2(c, (u8*)out->dst + out->pos, room, (const u8*)in->src + in->pos, n);
+        if (ZSTD_isError(r)) return r;
+        in->pos = in->size; out->pos += r;
+        return 0;
+    }
+    /* output produced earlier goes first; input is only taken while nothing is waiting */
+    if (zb_streamHandOut(c, out) == 0) {
+        size_t take = n;
+        while (take) {
+            size_t const space = ZB_STREAM_FRAME - c->stInSize;
+            size_t const m = take < space ? take : space;
+            if (c->stInSize + m > c->stInCap) {
+                size_t cap = c->stInCap ? c->stInCap : ((size_t)1 << 20);
+                while (cap < c->stInSize + m) cap *= 2;
+                if (cap > ZB_STREAM_FRAME) cap = ZB_STREAM_FRAME;
+                u8* const p = (u8*)realloc(c->stIn, cap);
+                if (!p) return ZB_ERR(ZB_error_memory_allocation);
+                c->stIn = p; c->stInCap = cap;
+            }
+            memcpy(c->stIn + c->stInSize, (const u8*)in->src + in->pos, m);
+            c->stInSize += m; in->pos += m; take -= m;
+            if (c->stInSize == ZB_STREAM_FRAME) {                           /* a full frame's worth: compress it, hand out what fits */
+                size_t const e = zb_streamMakeFrame(c); if (ZSTD_isError(e)) return e;
+                if (zb_streamHandOut(c, out) != 0) break;                    /* the caller has to make room before more input is taken */
+            }
+        }
+        if (in->pos == in->size && endOp != ZSTD_e_continue && c->stOutSize == 0) {
+            if (c->stInSize || (endOp == ZSTD_e_end && c->stFrames == 0)) { size_t const e = zb_streamMakeFrame(c); if (ZSTD_isError(e)) return e; }
+            zb_streamHandOut(c, out);
+        }
+    }
+    size_t const waiting = c->stOutSize - c->stOutPos;
+    if (endOp == ZSTD_e_end && waiting == 0 && in->pos == in->size && c->stInSize == 0) c->stFrames = 0;   /* session over: the next call starts a new one */
+    if (endOp == ZSTD_e_continue) return waiting ? waiting : (ZB_STREAM_FRAME - c->stInSize);              /* a hint for the next input size, as the reference gives one */
+    return waiting + ((in->pos < in->size || c->stInSize) ? 1 : 0);                                        /* > 0 while the flush / end is incomplete */
 }
+/* the older streaming entry points are thin forms of the above (lib/zstd.h:832-862) */
+extern "C" ZSTD_CStream* ZSTD_createCStream(void) { return ZSTD_createCCtx(); }
+extern "C" size_t ZSTD_freeCStream(ZSTD_CStream* zcs) { return ZSTD_freeCCtx(zcs); }
+extern "C" size_t ZSTD_initCStream(ZSTD_CStream* zcs, int level)
+{
+    if (!zcs) return ZB_ERR(ZB_error_GENERIC);
+    ZSTD_CCtx_reset(zcs, ZSTD_reset_session_only);
+    ZSTD_CCtx_refCDict(zcs, NULL);
+    return ZSTD_CCtx_setParameter(zcs, ZSTD_c_compressionLevel, level);
+}
+extern "C" size_t ZSTD_compressStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output, ZSTD_inBuffer* input) { return ZSTD_compressStream2(zcs, output, input, ZSTD_e_continue); }
+extern "C" size_t ZSTD_flushStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output) { ZSTD_inBuffer in = { NULL, 0, 0 }; return ZSTD_compressStream2(zcs, output, &in, ZSTD_e_flush); }
+extern "C" size_t ZSTD_endStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output) { ZSTD_inBuffer in = { NULL, 0, 0 }; return ZSTD_compressStream2(zcs, output, &in, ZSTD_e_end); }
+extern "C" size_t ZSTD_CStreamInSize(void) { return ZB_BLOCK_MAX; }                                         /* lib/zstd.h:858 */
+extern "C" size_t ZSTD_CStreamOutSize(void) { return ZSTD_compressBound(ZB_BLOCK_MAX) + 3 + 4; }            /* lib/zstd.h:859 */
 
 /* ------------------------------------------------------------------ reference-identical entry points */
 extern "C" size_t ZSTD_compress_usingDict(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
@@ -1038,7 +1183,7 @@ extern "C" size_t ZSTD_compress_usingDict(ZSTD_CCtx* c, void* dst, size_t dstCap
     if (!c) return ZB_ERR(ZB_error_GENERIC);
     if (dstCapacity && !dst) return ZB_ERR(ZB_error_dstBuffer_null);
     if (dstCapacity < 18) return ZB_ERR(ZB_error_dstSize_tooSmall);             /* ZSTD_FRAMEHEADERSIZE_MAX, zstd_compress.c:4643 */
-    return ZSTDB200_compressFrames(c, dst, dstCapacity, src, &off, &srcSize, 1, dict, dict ? dictSize : 0, NULL, level, 0, NULL);
+    return zb_compressFramesAny(c, dst, dstCapacity, src, &off, &srcSize, 1, dict, dict ? dictSize : 0, NULL, NULL, level, 0, NULL);   /* the simple API ignores sticky parameters (lib/zstd.h:270-273) */
 }
 extern "C" size_t ZSTD_compressCCtx(ZSTD_CCtx* c, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
 {

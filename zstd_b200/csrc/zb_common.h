@@ -22,8 +22,12 @@ typedef uint64_t u64;
 #define ZB_BATCH         1024u               /* positions of one walk batch = threads of the walk CTA */
 #define ZB_TAG_BITS      11u                 /* table entry = (position + 1) << 11 | tag, positions relative to the chunk's history start */
 #define ZB_FAST_HASHLOG_MAX   14u
+#ifndef ZB_DFAST_SHORT_MAX
 #define ZB_DFAST_SHORT_MAX    51200u         /* buckets: 200 KiB of shared memory */
+#endif
+#ifndef ZB_DFAST_LONGLOG_MAX
 #define ZB_DFAST_LONGLOG_MAX  15u
+#endif
 #define ZB_FAR           0xFFFFu             /* dist16 value: the distance is in the far array */
 #define ZB_MAX_SEQ       (ZB_BLOCK_MAX / 4)  /* every sequence carries a match of >= 4 bytes */
 #define ZB_SEQ_STRIDE    (ZB_MAX_SEQ + 8)    /* u64 per block */

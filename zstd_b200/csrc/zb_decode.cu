@@ -6,7 +6,8 @@
  *                                                     (lib/decompress/zstd_decompress_block.c:343, :695, :1615, :1012)
  *   HUF_decompress4X1 / HUF_readDTableX1              (lib/decompress/huf_decompress.c:602, :383)
  * Any frame the format allows is accepted (this library's own and the reference encoder's, every level), window
- * sizes up to 128 MiB, no dictionaries yet.  The format-level functions are in zb_decode_core.cuh.
+ * sizes up to 128 MiB, raw-content and zstd-format dictionaries (ZSTD_decompress_usingDict, zstd_decompress.c:1133).
+ * The format-level functions are in zb_decode_core.cuh.
  *
  *   D0  walker    frames and blocks of the input: block headers, section headers, which earlier block a treeless /
  *                 repeat-mode block takes its tables from.  Host code for host buffers; one device thread per call
@@ -48,11 +49,11 @@ typedef struct {
 } ZbdBlockOut;
 
 /* ------------------------------------------------------------------------------------------------ D0 on the device */
-__global__ void zbd_walk_kernel(const u8* __restrict__ src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFrame* frames, u32 capF, u64* res)
+__global__ void zbd_walk_kernel(const u8* __restrict__ src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFrame* frames, u32 capF, u64* res, u32 dictEntropy, u32 dictID)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     u32 nb = 0, nf = 0; u64 lit = 0, seq = 0;
-    u32 const e = zbd_walk(src, size, blocks, capB, frames, capF, &nb, &nf, &lit, &seq);
+    u32 const e = zbd_walk(src, size, blocks, capB, frames, capF, &nb, &nf, &lit, &seq, dictEntropy != 0u, dictID);
     res[0] = e; res[1] = nb; res[2] = nf; res[3] = lit; res[4] = seq;
 }
 
@@ -68,7 +69,8 @@ struct ZbdLitWork {
 };
 
 __global__ void __launch_bounds__(32 * ZBD_WARPS)
-zbd_literals_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u8* __restrict__ lits, ZbdBlockOut* __restrict__ bout)
+zbd_literals_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u8* __restrict__ lits, ZbdBlockOut* __restrict__ bout,
+                    const u8* __restrict__ dict, ZbdDictInfo di)
 {
     __shared__ ZbdLitWork work[ZBD_WARPS];
     u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -83,10 +85,12 @@ zbd_literals_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blo
     if (b.litType == 0u) { for (u32 i = lane; i < b.litRegen; i += 32u) out[i] = c[b.litHdr + i]; return; }
     if (b.litType == 1u) { u8 const v = c[b.litHdr]; for (u32 i = lane; i < b.litRegen; i += 32u) out[i] = v; return; }
     /* the tree description of the block that defined the table (this block itself unless treeless) */
-    ZbdBlock const sb = blocks[b.hufSrc];
     if (lane == 0) {
         u32 nbSym = 0, log = 0;
-        u32 const used = zbd_readHufWeights(wk.weights, &nbSym, &log, src + sb.srcOff + sb.litHdr, sb.litComp, wk.fse, wk.norm, wk.next);
+        const u8* dp; u32 dn;
+        if (b.hufSrc == ZBD_DICT) { dp = dict + di.hufOff; dn = di.hufLen; }      /* the dictionary's table (format: "Dictionary Format") */
+        else { ZbdBlock const sb = blocks[b.hufSrc]; dp = src + sb.srcOff + sb.litHdr; dn = sb.litComp; }
+        u32 const used = zbd_readHufWeights(wk.weights, &nbSym, &log, dp, dn, wk.fse, wk.norm, wk.next);
         if (used) zbd_hufStarts(wk.start, wk.weights, nbSym, log);
         wk.nbSym = nbSym; wk.log = log; wk.used = used;
     }
@@ -131,7 +135,8 @@ __device__ __constant__ u32 c_maxSym[3] = { ZBD_LL_MAXSYM, ZBD_OF_MAXSYM, ZBD_ML
 __device__ __constant__ u32 c_maxLog[3] = { ZBD_LL_LOG_MAX, ZBD_OF_LOG_MAX, ZBD_ML_LOG_MAX };
 
 __global__ void __launch_bounds__(32 * ZBD_WARPS)
-zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout)
+zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout,
+                     const u8* __restrict__ dict, ZbdDictInfo di)
 {
     __shared__ ZbdSeqWork work[ZBD_WARPS];
     u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -153,6 +158,10 @@ zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ bl
             u32 const ms = st == 1u ? ZBD_OF_DEFAULT_MAXSYM : c_maxSym[st];
             for (u32 s = 0; s <= ms; s++) wk.norm[st][s] = zbd_defaultNorm(st, s);
             zbd_buildFseTable(wk.table[st], wk.norm[st], ms, log, wk.next[st]);
+        } else if (b.fseSrc[st] == ZBD_DICT) {
+            u32 ms = 0;
+            if (!zbd_readNCount(wk.norm[st], &ms, &log, c_maxSym[st], c_maxLog[st], dict + di.fseOff[st], di.fseLen[st])) e = ZBD_CORRUPT;
+            else zbd_buildFseTable(wk.table[st], wk.norm[st], ms, log, wk.next[st]);
         } else {
             ZbdBlock const sb = blocks[b.fseSrc[st]];
             const u8* const sec = src + sb.srcOff + sb.seqOff;
@@ -195,7 +204,7 @@ zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ bl
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS)
 zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames, u32 nbFrames, ZbdBlockOut* __restrict__ bout,
-                u64 dstCapacity, u32* __restrict__ progress, u32* __restrict__ ticket, u64* __restrict__ res)
+                u64 dstCapacity, u32* __restrict__ progress, u32* __restrict__ ticket, u64* __restrict__ res, ZbdDictInfo di)
 {
     __shared__ u64 warpSum[SCAN_THREADS / 32];
     __shared__ u64 carry;
@@ -225,6 +234,7 @@ zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFram
         ZbdFrame const fr = frames[f];
         u64 const fOff = fr.nbBlocks ? bout[fr.firstBlock].dstOff : 0;
         ZbdRep h; h.r[0] = 1u; h.r[1] = 4u; h.r[2] = 8u;            /* format: "Repeat Offsets" start values */
+        if (di.entropy) { h.r[0] = di.rep[0]; h.r[1] = di.rep[1]; h.r[2] = di.rep[2]; }      /* ... or the dictionary's */
         for (u32 k0 = 0; k0 < fr.nbBlocks; k0 += 32u) {
             u32 const k = k0 + lane;
             ZbdRep tr; tr.r[0] = tr.r[1] = tr.r[2] = 0;
@@ -278,7 +288,8 @@ __device__ __forceinline__ void zbd_wait_range(const ZbdBlockOut* __restrict__ b
 __global__ void __launch_bounds__(32 * ZBD_WARPS)
 zbd_execute_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames,
                    const u8* __restrict__ lits, const u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout,
-                   u8* __restrict__ dst, u32* progress, u32* ticket, u32* __restrict__ execErr)
+                   u8* __restrict__ dst, u32* progress, u32* ticket, u32* __restrict__ execErr,
+                   const u8* __restrict__ dictContent, u32 dictContentSize)
 {
     u32 const lane = threadIdx.x & 31u;
     /* blocks are taken in ticket order: a block only ever waits for blocks with lower tickets, which have started */
@@ -304,7 +315,23 @@ zbd_execute_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ bloc
             u32 const off = zbd_rep_apply(&rep, ZBD_SEQ_OFF(q), ll, false);
             for (u32 k = lane; k < ll; k += 32u) out[op + k] = lit[lp + k];
             op += ll; lp += ll;
-            if (off == 0u || (u64)off > inFrame + op) { err = ZBD_CORRUPT; break; }
+            if (off == 0u || (u64)off > inFrame + op + dictContentSize) { err = ZBD_CORRUPT; break; }
+            if ((u64)off > inFrame + op) {                           /* the match starts in the dictionary's content (format: a frame's history begins with it) */
+                u64 const here = inFrame + op;                        /* frame position of the match's first byte */
+                u32 const span = ml < off ? ml : off;
+                u64 const fromFrame = span > off - here ? span - (off - here) : 0;      /* source bytes that are the frame's own first bytes */
+                if (fromFrame && inFrame) zbd_wait_range(bout, progress, bi, firstBlock, o.frameOff, o.frameOff + fromFrame, lane);
+                else __syncwarp();
+                const u8* const frameBase = dst + o.frameOff;
+                u32 r = lane % off; u32 const inc = 32u % off;
+                for (u32 k = lane; k < ml; k += 32u) {
+                    long long const sp = (long long)here - (long long)off + (long long)r;
+                    out[op + k] = sp < 0 ? dictContent[(long long)dictContentSize + sp] : __ldcg(frameBase + sp);
+                    r += inc; if (r >= off) r -= off;
+                }
+                op += ml;
+                continue;
+            }
             if (off > op) {                                          /* the match starts in an earlier block */
                 u64 const lo = o.dstOff + op - off;
                 u64 const span = ml < off ? ml : off;
@@ -346,6 +373,8 @@ struct ZSTD_DCtx_s {
     u8* d_in; size_t capIn; u8* d_out; size_t capOut;
     u64* d_res; u32* d_ticket; u32* d_execErr;
     u64* h_res;                  /* pinned: walker / scan results */
+    u8* d_dict; size_t capDict;  /* the call's dictionary, whole (header + content) */
+    ZbdDictInfo di; size_t dictSize;
     cudaEvent_t ev[6];
     ZSTDB200_dstats stats;
 };
@@ -372,7 +401,7 @@ extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts 
         int prev = -1; cudaGetDevice(&prev);
         cudaSetDevice(d->device);
         cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_progress); cudaFree(d->d_lits); cudaFree(d->d_seqs);
-        cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res);
+        cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res); cudaFree(d->d_dict);
         for (int i = 0; i < 6; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
         if (d->stream) cudaStreamDestroy(d->stream);
         if (prev >= 0) cudaSetDevice(prev);
@@ -411,17 +440,18 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     DCK(cudaMemsetAsync(d->d_execErr, 0, sizeof(u32), st));
     DCK(cudaEventRecord(d->ev[1], st));
     u32 const grid = (nb + ZBD_WARPS - 1u) / ZBD_WARPS;
-    zbd_literals_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_bout);
+    zbd_literals_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_bout, d->d_dict, d->di);
     DCK(cudaEventRecord(d->ev[2], st));
-    zbd_sequences_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_seqs, d->d_bout);
+    zbd_sequences_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_seqs, d->d_bout, d->d_dict, d->di);
     DCK(cudaEventRecord(d->ev[3], st));
-    zbd_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(d->d_blocks, nb, d->d_frames, nf, d->d_bout, (u64)dstCapacity, d->d_progress, d->d_ticket, d->d_res);
+    zbd_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(d->d_blocks, nb, d->d_frames, nf, d->d_bout, (u64)dstCapacity, d->d_progress, d->d_ticket, d->d_res, d->di);
     DCK(cudaMemcpyAsync(d->h_res, d->d_res, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     DCK(cudaStreamSynchronize(st));                                  /* nothing is written to dst before the sizes are known to fit */
     if (d->h_res[0]) return ZB_ERR((u32)d->h_res[0]);
     size_t const total = (size_t)d->h_res[1];
     DCK(cudaEventRecord(d->ev[4], st));
-    zbd_execute_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_frames, d->d_lits, d->d_seqs, d->d_bout, d_dst, d->d_progress, d->d_ticket, d->d_execErr);
+    zbd_execute_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_frames, d->d_lits, d->d_seqs, d->d_bout, d_dst, d->d_progress, d->d_ticket, d->d_execErr,
+                                                              d->dictSize ? d->d_dict + d->di.contentOff : (const u8*)NULL, d->dictSize ? (u32)(d->dictSize - d->di.contentOff) : 0u);
     DCK(cudaEventRecord(d->ev[5], st));
     DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));
     DCK(cudaStreamSynchronize(st));
@@ -457,10 +487,10 @@ static size_t zbd_decompressHost(ZSTD_DCtx* d, void* dst, size_t dstCapacity, co
     const u8* const in = (const u8*)src;
     u32 nb = 0, nf = 0; u64 lit = 0, seq = 0;
     cudaStream_t const st = d->stream;
-    u32 e = zbd_walk(in, srcSize, NULL, 0, NULL, 0, &nb, &nf, &lit, &seq);
+    u32 e = zbd_walk(in, srcSize, NULL, 0, NULL, 0, &nb, &nf, &lit, &seq, d->di.entropy != 0, d->di.dictID);
     if (e) return ZB_ERR(e);
     std::vector<ZbdBlock> B(nb ? nb : 1); std::vector<ZbdFrame> F(nf ? nf : 1);
-    e = zbd_walk(in, srcSize, B.data(), nb, F.data(), nf, &nb, &nf, &lit, &seq);
+    e = zbd_walk(in, srcSize, B.data(), nb, F.data(), nf, &nb, &nf, &lit, &seq, d->di.entropy != 0, d->di.dictID);
     if (e) return ZB_ERR(e);
     if (nb == 0) return 0;
     u64 known = 0; bool allKnown = true;
@@ -509,7 +539,7 @@ static size_t zbd_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity
     u32 capB = (u32)(srcSize / 4096u) + 1024u, capF = 1024u;
     for (int attempt = 0; attempt < 2; attempt++) {
         {   size_t const r = zbd_ensure(d, capB, capF, 0, 0); if (zbd_isErr(r)) return r; }
-        zbd_walk_kernel<<<1, 32, 0, st>>>((const u8*)d_src, (u64)srcSize, d->d_blocks, (u32)d->capBlocks, d->d_frames, (u32)d->capFrames, d->d_res);
+        zbd_walk_kernel<<<1, 32, 0, st>>>((const u8*)d_src, (u64)srcSize, d->d_blocks, (u32)d->capBlocks, d->d_frames, (u32)d->capFrames, d->d_res, d->di.entropy, d->di.dictID);
         DCK(cudaMemcpyAsync(d->h_res, d->d_res, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st));
         DCK(cudaStreamSynchronize(st));
         if (d->h_res[0]) return ZB_ERR((u32)d->h_res[0]);
@@ -525,7 +555,23 @@ static size_t zbd_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity
 
 struct ZbdDeviceGuard { int prev; ZbdDeviceGuard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } } ~ZbdDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); } };
 
-extern "C" size_t ZSTD_decompressDCtx(ZSTD_DCtx* d, void* dst, size_t dstCapacity, const void* src, size_t srcSize)      /* lib/zstd.h:299 */
+/* the call's dictionary: parsed on the host (zbd_parseDict), uploaded whole; NULL / 0 = none.  A dictionary without the
+ * magic number — or shorter than 8 bytes — is raw content (zstd_decompress.c:1541-1560). */
+static size_t zbd_setDict(ZSTD_DCtx* d, const void* dict, size_t dictSize, cudaStream_t st)
+{
+    memset(&d->di, 0, sizeof(d->di)); d->dictSize = 0;
+    if (!dict || dictSize == 0) return 0;
+    u32 const e = zbd_parseDict(&d->di, (const u8*)dict, dictSize);
+    if (e) return ZB_ERR(e);
+    {   size_t const r = zbd_grow(&d->d_dict, &d->capDict, dictSize + 16); if (zbd_isErr(r)) return r; }
+    DCK(cudaMemcpyAsync(d->d_dict, dict, dictSize, cudaMemcpyHostToDevice, st));
+    DCK(cudaStreamSynchronize(st));                                    /* the caller's dictionary buffer is pageable memory that may change after the call */
+    d->dictSize = dictSize;
+    return 0;
+}
+
+extern "C" size_t ZSTD_decompress_usingDict(ZSTD_DCtx* d, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                                            const void* dict, size_t dictSize)                                            /* lib/zstd.h:955 */
 {
     if (!d) return ZB_ERR(ZB_error_GENERIC);
     if (srcSize == 0) return 0;                                       /* zstd_decompress.c:1093 : an empty input is an empty output */
@@ -534,7 +580,12 @@ extern "C" size_t ZSTD_decompressDCtx(ZSTD_DCtx* d, void* dst, size_t dstCapacit
     ZbdDeviceGuard guard;
     {   size_t const e = zbd_ctxInit(d); if (zbd_isErr(e)) return e; }
     memset(&d->stats, 0, sizeof(d->stats));
+    {   size_t const e = zbd_setDict(d, dict, dictSize, d->stream); if (zbd_isErr(e)) return e; }
     return zbd_decompressHost(d, dst, dstCapacity, src, srcSize);
+}
+extern "C" size_t ZSTD_decompressDCtx(ZSTD_DCtx* d, void* dst, size_t dstCapacity, const void* src, size_t srcSize)      /* lib/zstd.h:299 */
+{
+    return ZSTD_decompress_usingDict(d, dst, dstCapacity, src, srcSize, NULL, 0);
 }
 
 extern "C" size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize)                  /* lib/zstd.h:170 */
@@ -546,14 +597,21 @@ extern "C" size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src
     return r;
 }
 
-extern "C" size_t ZSTDB200_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream)
+extern "C" size_t ZSTDB200_decompressDevice_usingDict(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize,
+                                                      const void* dict, size_t dictSize, void* stream)
 {
     if (!d) return ZB_ERR(ZB_error_GENERIC);
     if (srcSize == 0) return 0;
     ZbdDeviceGuard guard;
     {   size_t const e = zbd_ctxInit(d); if (zbd_isErr(e)) return e; }
     memset(&d->stats, 0, sizeof(d->stats));
-    return zbd_decompressDevice(d, d_dst, dstCapacity, d_src, srcSize, stream ? (cudaStream_t)stream : d->stream);
+    cudaStream_t const st = stream ? (cudaStream_t)stream : d->stream;
+    {   size_t const e = zbd_setDict(d, dict, dictSize, st); if (zbd_isErr(e)) return e; }
+    return zbd_decompressDevice(d, d_dst, dstCapacity, d_src, srcSize, st);
+}
+extern "C" size_t ZSTDB200_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream)
+{
+    return ZSTDB200_decompressDevice_usingDict(d, d_dst, dstCapacity, d_src, srcSize, NULL, 0, stream);
 }
 
 extern "C" void ZSTDB200_getLastDStats(const ZSTD_DCtx* d, ZSTDB200_dstats* out) { if (d && out) *out = d->stats; }

@@ -22,6 +22,7 @@
 #define ZBD_OK 0u
 #define ZBD_CORRUPT 20u                /* ZSTD_error_corruption_detected */
 #define ZBD_NONE 0xFFFFFFFFu
+#define ZBD_DICT 0xFFFFFFFEu            /* "the table the dictionary brings" where a block index is expected */
 
 #define ZBD_MAGIC 0xFD2FB528u
 #define ZBD_MAGIC_SKIPPABLE 0x184D2A50u   /* .. 0x184D2A5F */
@@ -539,7 +540,10 @@ ZBD_HDN u32 zbd_decodeSequences(u64* seqs, u32 nbSeq, const u8* p, u32 size, con
  * capF frame descriptors but counts all of them (*nbB, *nbF): a caller whose arrays were too small calls again.
  * Skippable frames are stepped over.  Returns 0 or a ZSTD error code (10 prefix_unknown, 20 corruption_detected,
  * 72 srcSize_wrong, 14 / 16 frame parameter errors). ---- */
-ZBD_HDN u32 zbd_walk(const u8* src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFrame* frames, u32 capF, u32* nbB, u32* nbF, u64* litBytes, u64* seqCount)
+/* dictEntropy: the call's dictionary is a zstd-format one — a frame's first blocks may reuse its Huffman / FSE tables
+ * (format: "Dictionary Format"); dictID: its ID (0 = raw content or none): a frame that names another one is refused (32). */
+ZBD_HDN u32 zbd_walk(const u8* src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFrame* frames, u32 capF, u32* nbB, u32* nbF, u64* litBytes, u64* seqCount,
+                     bool dictEntropy = false, u32 dictID = 0)
 {
     u64 pos = 0, litPos = 0, seqPos = 0;
     u32 nb = 0, nf = 0;
@@ -558,7 +562,9 @@ ZBD_HDN u32 zbd_walk(const u8* src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFra
         fr.hasChecksum = fh.hasChecksum; fr.dictID = fh.dictID;
         u64 const blockMax = fh.windowSize < ZB_BLOCK_MAX ? fh.windowSize : ZB_BLOCK_MAX;
         u64 p = pos + fh.headerSize;
+        if (fh.dictID && dictID && fh.dictID != dictID) return 32u;   /* dictionary_wrong */
         u32 lastHuf = ZBD_NONE, lastEff[3] = { ZBD_NONE, ZBD_NONE, ZBD_NONE }, lastSrc[3] = { ZBD_NONE, ZBD_NONE, ZBD_NONE };
+        if (dictEntropy) { lastHuf = ZBD_DICT; for (u32 s = 0; s < 3u; s++) { lastEff[s] = 2u; lastSrc[s] = ZBD_DICT; } }
         bool first = true;
         while (true) {
             if (p + 3u > size) return 72u;
@@ -604,6 +610,48 @@ ZBD_HDN u32 zbd_walk(const u8* src, u64 size, ZbdBlock* blocks, u32 capB, ZbdFra
         pos = p;
     }
     *nbB = nb; *nbF = nf; *litBytes = litPos; *seqCount = seqPos;
+    return ZBD_OK;
+}
+
+/* ---- dictionary (format: "Dictionary Format"): magic 0xEC30A437, ID, Huffman tree description, FSE table descriptions of
+ * offsets, match lengths, literal lengths (in this order), three repeat offsets, content.  Anything else is raw content. ---- */
+typedef struct {
+    u32 entropy;           /* 1: a zstd-format dictionary */
+    u32 dictID;
+    u32 hufOff, hufLen;    /* tree description */
+    u32 fseOff[3], fseLen[3];   /* 0 = LL, 1 = OF, 2 = ML (the order of the kernels' streams, not of the file) */
+    u32 rep[3];
+    u32 contentOff;
+    u32 pad;
+} ZbdDictInfo;
+#define ZBD_MAGIC_DICT 0xEC30A437u
+/* returns 0, or 30 (dictionary_corrupted) */
+ZBD_HDN u32 zbd_parseDict(ZbdDictInfo* di, const u8* dict, u64 size)
+{
+    memset(di, 0, sizeof(*di));
+    if (size < 8 || zbd_le(dict, 4) != ZBD_MAGIC_DICT) return ZBD_OK;          /* raw content */
+    di->entropy = 1; di->dictID = zbd_le(dict + 4, 4);
+    u32 p = 8;
+    {   u8 weights[256]; u32 nbSym, log; u32 fse[64]; short norm[16]; u16 next[16];
+        u32 const used = zbd_readHufWeights(weights, &nbSym, &log, dict + p, (u32)(size - p > 0xFFFFu ? 0xFFFFu : size - p), fse, norm, next);
+        if (!used) return 30u;
+        di->hufOff = p; di->hufLen = used; p += used; }
+    u32 const order[3] = { 1u, 2u, 0u };                                        /* the file holds OF, ML, LL */
+    u32 const maxSym[3] = { ZBD_LL_MAXSYM, ZBD_OF_MAXSYM, ZBD_ML_MAXSYM }, maxLog[3] = { ZBD_LL_LOG_MAX, ZBD_OF_LOG_MAX, ZBD_ML_LOG_MAX };
+    for (u32 k = 0; k < 3u; k++) {
+        u32 const st = order[k];
+        short norm[64]; u32 ms, lg;
+        if (p >= size) return 30u;
+        u32 const used = zbd_readNCount(norm, &ms, &lg, maxSym[st], maxLog[st], dict + p, (u32)(size - p > 0xFFFFu ? 0xFFFFu : size - p));
+        if (!used) return 30u;
+        di->fseOff[st] = p; di->fseLen[st] = used; p += used;
+    }
+    if ((u64)p + 12u > size) return 30u;
+    for (u32 k = 0; k < 3u; k++) { di->rep[k] = zbd_le(dict + p + 4u * k, 4); }
+    p += 12u;
+    di->contentOff = p;
+    u64 const contentSize = size - p;
+    for (u32 k = 0; k < 3u; k++) if (di->rep[k] == 0 || di->rep[k] > contentSize) return 30u;
     return ZBD_OK;
 }
 

@@ -89,16 +89,21 @@ __device__ __forceinline__ u32 zb_walk_cand(u32 c, u32 h, u32 x)
     return (((c ^ h) & ZB_TAG_MASK) == 0u && px < x) ? x - px : 0u;
 }
 
-/* which of the P (<= 4) consecutive positions starting at a position whose residue modulo `step` is r0 lie on the
- * insertion pattern (rel % step) < 2, as a bit mask.  step >= 3: the pair that began at or before the first position
- * (bits 0,1 for r0 = 0; bit 0 for r0 = 1) and the next pair, step - r0 positions on; a third pair lies beyond P. */
+/* which of the P consecutive positions starting at a position whose residue modulo `step` is r0 lie on the insertion
+ * pattern (rel % step) < 2, as a bit mask.  step >= 3: the pair that began at or before the first position (bits 0,1
+ * for r0 = 0; bit 0 for r0 = 1), then a pair every `step` positions from step - r0 on. */
 template <int P>
 __device__ __forceinline__ u32 zb_walk_pattern_res(u32 r0, u32 step)
 {
     if (step <= 2u) return (1u << P) - 1u;
-    u32 const head = 3u >> (r0 < 2u ? r0 : 2u);
-    u32 const nxt = step - r0;
-    return (head | (3u << (nxt < 31u ? nxt : 31u))) & ((1u << P) - 1u);
+    u32 m = 3u >> (r0 < 2u ? r0 : 2u);
+    u32 nxt = step - r0;
+#pragma unroll
+    for (int k = 0; k < (P + 2) / 3; k++) {                       /* at most ceil(P / 3) further pairs start inside P positions */
+        m |= 3u << (nxt < 31u ? nxt : 31u);
+        nxt += step;
+    }
+    return m & ((1u << P) - 1u);
 }
 /* residue of rel0 modulo step (rel0 < 2^22, step < 2^14: the float quotient is exact up to +-1, fixed below) */
 __device__ __forceinline__ u32 zb_walk_residue(u32 rel0, u32 step)
@@ -113,8 +118,9 @@ __device__ __forceinline__ u32 zb_walk_residue(u32 rel0, u32 step)
  * INTERIOR: every position of the batch is walked, lies in the frame's own bytes and has its 8 bytes readable: no
  * activity predicates, bytes come from the words prefetched in wrd[].
  * Returns whether any position of the CTA found a candidate in phase A (the barrier between A and B carries the OR). */
+#define ZB_WALK_NWR(P) ((P) == 1 ? 2 : ((P) + 7 + 3) / 4)        /* realigned words that hold a thread's P + 7 bytes */
 template <int MLS, int P, bool INTERIOR>
-__device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, const u32 (&wrd)[3], u32 pat,
+__device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, const u32 (&wrd)[ZB_WALK_NWR(P)], u32 pat,
                                               u32 N, u32 shift, u32 D, u32 total, u32 xLow, u32 xEnd,
                                               const u8* fbase, const u8* dbase, bool output, u16* __restrict__ distRow, u32* __restrict__ farRow)
 {
@@ -131,8 +137,11 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
             u64 v;
             if (slow) v = act[i] ? zb_ld64u((rel < D ? dbase : fbase) + rel) : 0ull;
             else {
-                u32 const lo = i ? __funnelshift_r(wrd[0], wrd[1], 8u * (u32)i) : wrd[0];
-                u32 const hi = i ? __funnelshift_r(wrd[1], wrd[2], 8u * (u32)i) : wrd[1];
+                constexpr int NWR = ZB_WALK_NWR(P);
+                int const wi = i >> 2; u32 const sh = 8u * (u32)(i & 3);
+                int const w2 = wi + 2 < NWR ? wi + 2 : NWR - 1;           /* only read when i & 3: then wi + 2 < NWR */
+                u32 const lo = (i & 3) ? __funnelshift_r(wrd[wi], wrd[wi + 1], sh) : wrd[wi];
+                u32 const hi = (i & 3) ? __funnelshift_r(wrd[wi + 1], wrd[w2], sh) : wrd[wi + 1];
                 v = ((u64)hi << 32) | lo;
             }
             h[i] = zb_hash(v, MLS, 32u);
@@ -167,6 +176,7 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
             for (int i = 0; i < P; i++) if (d[i] >= ZB_FAR) { if (INTERIOR || xa + (u32)i < xEnd) farRow[i] = d[i]; d[i] = ZB_FAR; }
         }
         bool vec = false;
+        if constexpr (P == 8) { if (INTERIOR || xa + 8u <= xEnd) { *reinterpret_cast<uint4*>(distRow) = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16)); vec = true; } }
         if constexpr (P == 4) { if (INTERIOR || xa + 4u <= xEnd) { *reinterpret_cast<uint2*>(distRow) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16)); vec = true; } }
         if constexpr (P == 2) { if (INTERIOR || xa + 2u <= xEnd) { *reinterpret_cast<u32*>(distRow) = d[0] | (d[1] << 16); vec = true; } }
         if (!vec) {
@@ -185,6 +195,9 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
  * and A of the next share a region.  The input bytes of a batch are loaded two batches ahead. */
 #ifndef WALK_P_SMALL
 #define WALK_P_SMALL 4           /* positions per thread for tables <= 56 KiB (development knob: tools/build_variant.sh) */
+#endif
+#ifndef WALK_P_MID
+#define WALK_P_MID 2             /* tables of 56 .. 113 KiB: two CTAs per SM */
 #endif
 #ifndef WALK_MINB_SMALL
 #define WALK_MINB_SMALL 4        /* CTAs per SM the register allocation of that variant leaves room for */
@@ -222,34 +235,41 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     u32 const xIntLoB = (xIntLo + ZB_BATCH - 1u) & ~(ZB_BATCH - 1u);
     /* a thread's P + 7 bytes lie in NW aligned words whatever its address modulo 4; the interior loads all NW of them */
     constexpr u32 NW = (P + 7u + 3u + 3u) / 4u;
+    constexpr int NWR = ZB_WALK_NWR(P);
     u32 const xIntHi = xEnd >= (ZB_BATCH + 4u * NW) ? (xEnd + P - 4u * NW) & ~(ZB_BATCH - 1u) : 0u;     /* batches [x0, x0 + B) with x0 + B <= xIntHi are interior */
 
-    /* the P + 7 bytes of a thread's positions as three words realigned to its first position */
-    auto fetch = [&](u32 xb, u32 (&w)[3]) {
+    /* the P + 7 bytes of a thread's positions as words realigned to its first position */
+    auto fetch = [&](u32 xb, u32 (&w)[NWR]) {
         u32 const xa = xb + P * t;                                /* first coordinate of the thread */
-        w[0] = w[1] = w[2] = 0u;
+#pragma unroll
+        for (int k = 0; k < NWR; k++) w[k] = 0u;
+        u32 a[NW + 1];
         if (xb >= xIntLoB && xb + ZB_BATCH <= xIntHi) {           /* interior: no guards */
-            const u8* const a = fbase + (xa - shift);
-            const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
-            u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-            u32 const w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = NW > 3u ? __ldg(p + 3) : 0u;
-            w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh); w[2] = __funnelshift_r(w2, w3, sh);
+            const u8* const ad = fbase + (xa - shift);
+            const u32* const p = reinterpret_cast<const u32*>((uintptr_t)ad & ~(uintptr_t)3);
+            u32 const sh = ((u32)(uintptr_t)ad & 3u) * 8u;
+#pragma unroll
+            for (u32 k = 0; k < NW; k++) a[k] = __ldg(p + k);
+            a[NW] = 0u;
+#pragma unroll
+            for (int k = 0; k < NWR; k++) w[k] = __funnelshift_r(a[k], a[k + 1], sh);
             return;
         }
         if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
         u32 const rel = xa - shift;
         bool const slow = (xa < xLow) || (D != 0u && rel < D && rel + P + 7u > D) || (rel + P + 7u > total);
         if (slow) return;                                         /* assembled byte-wise in the batch */
-        const u8* const a = (rel < D ? dbase : fbase) + rel;
-        const u32* const p = reinterpret_cast<const u32*>((uintptr_t)a & ~(uintptr_t)3);
-        u32 const al = (u32)(uintptr_t)a & 3u, sh = al * 8u;
+        const u8* const ad = (rel < D ? dbase : fbase) + rel;
+        const u32* const p = reinterpret_cast<const u32*>((uintptr_t)ad & ~(uintptr_t)3);
+        u32 const al = (u32)(uintptr_t)ad & 3u, sh = al * 8u;
         /* rel + P + 7 <= limit: a word is only touched when it holds one of the thread's P + 7 bytes */
-        u32 const w0 = __ldg(p), w1 = __ldg(p + 1);
-        u32 const w2 = (al + P + 7u > 8u) ? __ldg(p + 2) : 0u;
-        u32 const w3 = (al + P + 7u > 12u) ? __ldg(p + 3) : 0u;
-        w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh); w[2] = __funnelshift_r(w2, w3, sh);
+#pragma unroll
+        for (u32 k = 0; k < NW; k++) a[k] = (al + P + 7u > 4u * k) ? __ldg(p + k) : 0u;
+        a[NW] = 0u;
+#pragma unroll
+        for (int k = 0; k < NWR; k++) w[k] = __funnelshift_r(a[k], a[k + 1], sh);
     };
-    u32 wA[3], wB[3];                                             /* bytes of the next batch and of the one after it */
+    u32 wA[NWR], wB[NWR];                                         /* bytes of the next batch and of the one after it */
     fetch(x0, wA);
     fetch(x0 + ZB_BATCH, wB);
     u32 const blockMask = (1u << cd.blockLog) - 1u;
@@ -260,8 +280,9 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     u32 li = shift;                                               /* coordinate the acceleration counts from: the walk's start, then the end of the last batch with a hit */
     for (; x0 < xEnd; x0 += ZB_BATCH) {
         u32 const xa = x0 + P * t;
-        u32 cur[3] = { wA[0], wA[1], wA[2] };
-        wA[0] = wB[0]; wA[1] = wB[1]; wA[2] = wB[2];
+        u32 cur[NWR];
+#pragma unroll
+        for (int k = 0; k < NWR; k++) { cur[k] = wA[k]; wA[k] = wB[k]; }
         fetch(x0 + 2u * ZB_BATCH, wB);                            /* in flight across two batches' barriers */
         if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
         u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
@@ -757,7 +778,7 @@ static cudaError_t zb_launch_walk_m(const u8* d_src, const u8* d_dictEnd, const 
 {
     size_t const smem = (size_t)N * 4u;
     if (smem <= 56u * 1024u)  return zb_launch_walk_p<MLS, WALK_P_SMALL>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
-    if (smem <= 113u * 1024u) return zb_launch_walk_p<MLS, 2>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
+    if (smem <= 113u * 1024u) return zb_launch_walk_p<MLS, WALK_P_MID>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
     return zb_launch_walk_p<MLS, 1>(d_src, d_dictEnd, d_chunks, nbChunks, N, insStep, sd, slotFirstBlock, d_dist, d_far, d_imageIn, d_imageOut, stream);
 }
 static cudaError_t zb_launch_walk(const u8* d_src, const u8* d_dictEnd, const ZbChunk* d_chunks, u32 nbChunks, u32 mls, u32 N, u32 insStep, const ZbStrides& sd,

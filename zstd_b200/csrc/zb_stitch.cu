@@ -182,6 +182,72 @@ extern "C" cudaError_t zb_launch_stitch(const u8* d_src, const ZbBlock* d_blocks
     return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Content checksum (format: "Content_Checksum" = low 32 bits of XXH64, seed 0, of the frame's content;
+ * the reference computes it chunk by chunk on the host, zstd_compress.c:4544, :5297-5303).
+ * XXH64 is four serial accumulator chains per input (acc = rotl(acc + x * P2, 31) * P1 over the 8-byte words of
+ * every 32-byte stripe): nothing to split inside one frame, so one warp takes a frame — all lanes load 256 bytes,
+ * lanes 0..3 run the chains — and the frames of a call are hashed side by side.  About 1 GB/s per frame. */
+__device__ __forceinline__ u64 zbx_rotl(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+#define ZBX_P1 0x9E3779B185EBCA87ull
+#define ZBX_P2 0xC2B2AE3D27D4EB4Full
+#define ZBX_P3 0x165667B19E3779F9ull
+#define ZBX_P4 0x85EBCA77C2B2AE63ull
+#define ZBX_P5 0x27D4EB2F165667C5ull
+__device__ __forceinline__ u64 zbx_round(u64 acc, u64 in) { return zbx_rotl(acc + in * ZBX_P2, 31) * ZBX_P1; }
+__device__ __forceinline__ u64 zbx_merge(u64 h, u64 v) { return (h ^ zbx_round(0, v)) * ZBX_P1 + ZBX_P4; }
+
+#define XXH_WARPS 4
+__global__ void __launch_bounds__(32 * XXH_WARPS)
+zb_checksum_kernel(const u8* __restrict__ src, const ZbFrame* __restrict__ frames, u32 nbFrames, const u64* __restrict__ outOffsets,
+                   u8* __restrict__ dst, u64 dstCapacity)
+{
+    u32 const lane = threadIdx.x & 31u;
+    u32 const f = blockIdx.x * XXH_WARPS + (threadIdx.x >> 5);
+    if (f >= nbFrames) return;
+    ZbFrame const fr = frames[f];
+    if (!fr.checksum) return;
+    const u8* const p = src + fr.srcOff;
+    u64 const len = fr.srcSize;
+    u64 const stripes = len >> 5;
+    u64 acc = lane == 0u ? ZBX_P1 + ZBX_P2 : (lane == 1u ? ZBX_P2 : (lane == 2u ? 0ull : 0ull - ZBX_P1));
+    u64 nextW = (lane < 4u * stripes) ? zb_ld64u(p + 8u * lane) : 0ull;
+    for (u64 s0 = 0; s0 < stripes; s0 += 8u) {
+        u64 const w = nextW;
+        u64 const nx = (s0 + 8u) * 4u + lane;                        /* this lane's word of the next 256 bytes */
+        nextW = (nx < 4u * stripes) ? zb_ld64u(p + 8u * nx) : 0ull;
+        u32 const n = (u32)(stripes - s0 < 8u ? stripes - s0 : 8u);
+        for (u32 s = 0; s < n; s++) {
+            u64 const x = __shfl_sync(ZB_FULL, w, (int)(4u * s + (lane & 3u)));
+            if (lane < 4u) acc = zbx_round(acc, x);
+        }
+    }
+    u64 const v1 = __shfl_sync(ZB_FULL, acc, 0), v2 = __shfl_sync(ZB_FULL, acc, 1), v3 = __shfl_sync(ZB_FULL, acc, 2), v4 = __shfl_sync(ZB_FULL, acc, 3);
+    if (lane != 0u) return;
+    u64 h;
+    if (len >= 32u) {
+        h = zbx_rotl(v1, 1) + zbx_rotl(v2, 7) + zbx_rotl(v3, 12) + zbx_rotl(v4, 18);
+        h = zbx_merge(h, v1); h = zbx_merge(h, v2); h = zbx_merge(h, v3); h = zbx_merge(h, v4);
+    } else h = ZBX_P5;
+    h += len;
+    u64 i = stripes << 5;
+    for (; i + 8u <= len; i += 8u) { h ^= zbx_round(0, zb_ld64u(p + i)); h = zbx_rotl(h, 27) * ZBX_P1 + ZBX_P4; }
+    if (i + 4u <= len) { h ^= (u64)zb_ld32u(p + i) * ZBX_P1; h = zbx_rotl(h, 23) * ZBX_P2 + ZBX_P3; i += 4u; }
+    for (; i < len; i++) { h ^= (u64)p[i] * ZBX_P5; h = zbx_rotl(h, 11) * ZBX_P1; }
+    h ^= h >> 33; h *= ZBX_P2; h ^= h >> 29; h *= ZBX_P3; h ^= h >> 32;
+    u64 const end = outOffsets[fr.firstBlock + fr.nbBlocks];          /* the frame's last 4 bytes were left free by the size scan */
+    if (end > dstCapacity || end < 4u) return;
+    u32 const ck = (u32)h;
+    dst[end - 4u] = (u8)ck; dst[end - 3u] = (u8)(ck >> 8); dst[end - 2u] = (u8)(ck >> 16); dst[end - 1u] = (u8)(ck >> 24);
+}
+
+extern "C" cudaError_t zb_launch_checksums(const u8* d_src, const ZbFrame* d_frames, u32 nbFrames, const u64* d_outOffsets, u8* d_dst, u64 dstCapacity, cudaStream_t stream)
+{
+    if (nbFrames == 0) return cudaSuccess;
+    zb_checksum_kernel<<<(nbFrames + XXH_WARPS - 1u) / XXH_WARPS, 32 * XXH_WARPS, 0, stream>>>(d_src, d_frames, nbFrames, d_outOffsets, d_dst, dstCapacity);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t zb_launch_frame_sizes(const ZbFrame* d_frames, u32 nbFrames, const u64* d_outOffsets,
                                              u64* d_frameSizes, cudaStream_t stream)
 {

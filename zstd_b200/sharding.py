@@ -34,6 +34,23 @@ def split_into_frames(total_size: int, frame_size: int) -> List[Tuple[int, int]]
     return [(o, min(frame_size, total_size - o)) for o in range(0, max(total_size, 1), frame_size)] if total_size else [(0, 0)]
 
 
+def split_one_frame(frame_size: int, world_size: int, alignment: int = 512 << 10) -> List[Tuple[int, int]]:
+    """(begin, size) per rank of ONE frame that the ranks compress together (ZSTDB200_compressFramePart; the reference's
+    precedent are ZSTDMT's jobs, zstdmt_compress.c:1168-1227): shares start on multiples of `alignment`
+    (ZSTDB200_framePartAlignment(): a chunk of the candidate walk), the last one takes the rest.  A rank also needs the
+    ZSTDB200_framePartHalo() bytes in front of its share.  A rank with nothing to do gets (-1, 0); an empty frame is
+    rank 0's."""
+    chunks = (frame_size + alignment - 1) // alignment
+    out, done = [], 0
+    for r in range(world_size):
+        n = (chunks * (r + 1)) // world_size - (chunks * r) // world_size
+        b = done * alignment
+        e = min(frame_size, (done + n) * alignment)
+        out.append((b, e - b) if (n or (r == 0 and frame_size == 0)) else (-1, 0))
+        done += n
+    return out
+
+
 def _all_sizes(n: int, device, group=None) -> List[int]:
     """every rank's byte count, in rank order (one tiny all_gather + one host read)"""
     ws = dist.get_world_size(group)
