@@ -146,8 +146,8 @@ ZSTDB200_API size_t ZSTDB200_decompressDevice(ZSTD_DCtx* dctx, void* d_dst, size
 ZSTDB200_API size_t ZSTDB200_decompressDevice_usingDict(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize,
                                                         const void* dict, size_t dictSize, void* stream);
 typedef struct {
-    float kernel_ms;         /* literals kernel start -> execute kernel end */
-    float literals_ms, sequences_ms, execute_ms;
+    float kernel_ms;         /* literals kernel start -> match kernel end */
+    float literals_ms, sequences_ms, place_ms, execute_ms;       /* D1, D2, D4 (literal placement), D5 (match copies) */
     unsigned launches, nbBlocks, nbFrames;
     size_t h2d_bytes, d2h_bytes;
 } ZSTDB200_dstats;

@@ -56,8 +56,8 @@ typedef struct { u32 offBase; u32 litLen; u32 matchLen; } zbo_seq;   /* matchLen
 #define ZB_BATCH          1024u            /* positions of one walk batch (= threads of the walk CTA) */
 #define ZB_BATCH_MAX      4096u
 #define ZB_FAST_HASHLOG_MAX  14u           /* fast: <= 12288 u32 buckets = 48 KiB of shared memory */
-#define ZB_DFAST_SHORT_MAX 51200u          /* dfast short table: 51200 x u32 = 200 KiB of shared memory */
-#define ZB_DFAST_LONGLOG_MAX  15u          /* dfast long table: 32768 x u32 = 128 KiB */
+#define ZB_DFAST_SHORT_MAX 28672u          /* dfast short table: 28672 x u32 = 112 KiB of shared memory */
+#define ZB_DFAST_LONGLOG_MAX  14u          /* dfast long table: 16384 x u32 = 64 KiB */
 #define ZB_WARP           32u
 #define ZB_PARSE_SEG      (16u << 10)      /* fast strategy: bytes of a block parsed by one warp (8 segments per 128 KiB block) */
 

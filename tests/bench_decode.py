@@ -31,4 +31,4 @@ for p, level in ((50, 1), (90, 3), (30, -3)):
         st = d.stats()
         ok = m == len(src) and torch.equal(d_out, d_src)
         print(f"P{p} level {level} {what:9s}: {len(src) >> 20} MiB <- {n} B  {best:.2f} ms = {len(src) / best / 1e6:.1f} GB/s  "
-              f"[kernels {st.kernel_ms:.2f}: literals {st.literals_ms:.2f} sequences {st.sequences_ms:.2f} execute {st.execute_ms:.2f}; {st.nbBlocks} blocks]  ok {ok}", flush=True)
+              f"[kernels {st.kernel_ms:.2f}: literals {st.literals_ms:.2f} sequences {st.sequences_ms:.2f} place {st.place_ms:.2f} matches {st.execute_ms:.2f}; {st.nbBlocks} blocks]  ok {ok}", flush=True)

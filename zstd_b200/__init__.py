@@ -39,8 +39,8 @@ class Stats(ctypes.Structure):
 
 
 class DStats(ctypes.Structure):
-    _fields_ = [("kernel_ms", ctypes.c_float), ("literals_ms", ctypes.c_float), ("sequences_ms", ctypes.c_float), ("execute_ms", ctypes.c_float),
-                ("launches", ctypes.c_uint), ("nbBlocks", ctypes.c_uint), ("nbFrames", ctypes.c_uint), ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
+    _fields_ = [("kernel_ms", ctypes.c_float), ("literals_ms", ctypes.c_float), ("sequences_ms", ctypes.c_float), ("place_ms", ctypes.c_float),
+                ("execute_ms", ctypes.c_float), ("launches", ctypes.c_uint), ("nbBlocks", ctypes.c_uint), ("nbFrames", ctypes.c_uint), ("h2d_bytes", _sz), ("d2h_bytes", _sz)]
 
 
 def lib() -> ctypes.CDLL:

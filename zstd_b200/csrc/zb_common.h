@@ -23,10 +23,10 @@ typedef uint64_t u64;
 #define ZB_TAG_BITS      11u                 /* table entry = (position + 1) << 11 | tag, positions relative to the chunk's history start */
 #define ZB_FAST_HASHLOG_MAX   14u
 #ifndef ZB_DFAST_SHORT_MAX
-#define ZB_DFAST_SHORT_MAX    51200u         /* buckets: 200 KiB of shared memory */
+#define ZB_DFAST_SHORT_MAX    28672u         /* buckets: 112 KiB of shared memory, two walk CTAs per SM */
 #endif
 #ifndef ZB_DFAST_LONGLOG_MAX
-#define ZB_DFAST_LONGLOG_MAX  15u
+#define ZB_DFAST_LONGLOG_MAX  14u            /* 64 KiB */
 #endif
 #define ZB_FAR           0xFFFFu             /* dist16 value: the distance is in the far array */
 #define ZB_MAX_SEQ       (ZB_BLOCK_MAX / 4)  /* every sequence carries a match of >= 4 bytes */

@@ -20,9 +20,13 @@
  *                 its repcode history as a FUNCTION of the history at its start.
  *   D3  scan      output offset of every block (prefix sum of regenerated sizes) and the repcode history at every
  *                 block's start (composition of the blocks' functions along each frame).
- *   D4  execute   one warp per block, in ticket order: literal and match copies by 32 lanes.  A match that reaches into
- *                 earlier blocks waits for the producer's progress counter, so blocks of a frame run concurrently, a
- *                 typical offset behind each other.
+ *   D4  place     one warp per block, all blocks at once: raw / RLE blocks and every literal run go to their final place,
+ *                 every match becomes (destination, offset, length) with its repcode resolved.  Nothing of the output is
+ *                 read, so no block waits for another.
+ *   D5  matches   one CTA per frame, its warps taking the frame's matches in order: LZ77 copies depend on earlier output,
+ *                 which makes a frame a sequential object; a completion ring in shared memory lets a match start as soon
+ *                 as no unfinished earlier match can write into its source, so matches with offsets beyond the few KiB
+ *                 in flight overlap.  Frames of a call run side by side.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -204,18 +208,18 @@ zbd_sequences_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ bl
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS)
 zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames, u32 nbFrames, ZbdBlockOut* __restrict__ bout,
-                u64 dstCapacity, u32* __restrict__ progress, u32* __restrict__ ticket, u64* __restrict__ res, ZbdDictInfo di)
+                u64 dstCapacity, u64* __restrict__ res, ZbdDictInfo di)
 {
     __shared__ u64 warpSum[SCAN_THREADS / 32];
     __shared__ u64 carry;
     __shared__ u32 firstErr;
     u32 const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) { carry = 0; firstErr = 0; *ticket = 0; }
+    if (tid == 0) { carry = 0; firstErr = 0; }
     __syncthreads();
     for (u32 b0 = 0; b0 < nbBlocks; b0 += SCAN_THREADS) {
         u32 const i = b0 + tid;
         u64 v = 0;
-        if (i < nbBlocks) { v = bout[i].regen; progress[i] = 0; if (bout[i].err) atomicMax(&firstErr, bout[i].err); }
+        if (i < nbBlocks) { v = bout[i].regen; if (bout[i].err) atomicMax(&firstErr, bout[i].err); }
         u64 inc = v;
 #pragma unroll
         for (u32 o = 1; o < 32u; o <<= 1) { u64 const x = __shfl_up_sync(ZB_FULL, inc, o); if (lane >= o) inc += x; }
@@ -262,120 +266,135 @@ zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFram
     }
 }
 
-/* ------------------------------------------------------------------------------------------------ D4 execute */
-__device__ __forceinline__ u32 zbd_ld_volatile(const u32* p) { u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ void zbd_st_volatile(u32* p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-
-/* blocks until every byte of [absLo, absHi) that lies in blocks below `bi` has been written (absolute output offsets) */
-__device__ __forceinline__ void zbd_wait_range(const ZbdBlockOut* __restrict__ bout, const u32* progress, u32 bi, u32 firstBlock, u64 absLo, u64 absHi, u32 lane)
-{
-    if (lane == 0) {
-        u32 j = bi;
-        while (j > firstBlock) {
-            j--;
-            u64 const s = bout[j].dstOff;
-            u64 const e = s + bout[j].regen;
-            if (e <= absLo) break;                                   /* this block and everything below it lie in front of the range */
-            if (s >= absHi) continue;
-            u32 const need = (u32)((absHi < e ? absHi : e) - s);
-            while (zbd_ld_volatile(progress + j) < need) __nanosleep(64);
-        }
-        __threadfence();
-    }
-    __syncwarp();
-}
-
+/* ------------------------------------------------------------------------------------------------ D4 place
+ * One warp per block, every block of the call at once: raw / RLE blocks are written; of a compressed block every literal run
+ * goes to its final place and every match becomes (absolute destination, offset, length) — the repcode history runs over the
+ * block's sequences from the start history D3 computed.  No byte of the output is READ here, so blocks do not depend on
+ * each other.  seqs[g] becomes offset | length << 28, matchPos[g] the match's first output byte. */
 __global__ void __launch_bounds__(32 * ZBD_WARPS)
-zbd_execute_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFrame* __restrict__ frames,
-                   const u8* __restrict__ lits, const u64* __restrict__ seqs, ZbdBlockOut* __restrict__ bout,
-                   u8* __restrict__ dst, u32* progress, u32* ticket, u32* __restrict__ execErr,
-                   const u8* __restrict__ dictContent, u32 dictContentSize)
+zbd_place_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const u8* __restrict__ lits, u64* __restrict__ seqs,
+                 u64* __restrict__ matchPos, const ZbdBlockOut* __restrict__ bout, u8* __restrict__ dst, u32 dictContentSize, u32* __restrict__ execErr)
 {
     u32 const lane = threadIdx.x & 31u;
-    /* blocks are taken in ticket order: a block only ever waits for blocks with lower tickets, which have started */
-    u32 bi = 0;
-    if (lane == 0) bi = atomicAdd(ticket, 1u);
-    bi = __shfl_sync(ZB_FULL, bi, 0);
+    u32 const bi = blockIdx.x * ZBD_WARPS + (threadIdx.x >> 5);
     if (bi >= nbBlocks) return;
     ZbdBlock const b = blocks[bi];
     ZbdBlockOut const o = bout[bi];
     u8* const out = dst + o.dstOff;
-    u32 const firstBlock = frames[b.frame].firstBlock;
-    if (b.type == ZB_BT_RAW) { for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = src[b.srcOff + i]; }
-    else if (b.type == ZB_BT_RLE) { u8 const v = src[b.srcOff]; for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = v; }
-    else {
-        const u8* lit = lits + b.litPos;
-        const u64* sq = seqs + b.seqPos;
-        ZbdRep rep = o.start;
-        u64 const inFrame = o.dstOff - o.frameOff;                   /* bytes of the frame in front of this block */
-        u32 op = 0, lp = 0, published = 0, err = 0;
-        for (u32 i = 0; i < b.nbSeq; i++) {
-            u64 const q = sq[i];
-            u32 const ll = ZBD_SEQ_LL(q), ml = ZBD_SEQ_ML(q);
-            u32 const off = zbd_rep_apply(&rep, ZBD_SEQ_OFF(q), ll, false);
-            for (u32 k = lane; k < ll; k += 32u) out[op + k] = lit[lp + k];
-            op += ll; lp += ll;
-            if (off == 0u || (u64)off > inFrame + op + dictContentSize) { err = ZBD_CORRUPT; break; }
-            if ((u64)off > inFrame + op) {                           /* the match starts in the dictionary's content (format: a frame's history begins with it) */
-                u64 const here = inFrame + op;                        /* frame position of the match's first byte */
-                u32 const span = ml < off ? ml : off;
-                u64 const fromFrame = span > off - here ? span - (off - here) : 0;      /* source bytes that are the frame's own first bytes */
-                if (fromFrame && inFrame) zbd_wait_range(bout, progress, bi, firstBlock, o.frameOff, o.frameOff + fromFrame, lane);
-                else __syncwarp();
-                const u8* const frameBase = dst + o.frameOff;
+    if (b.type == ZB_BT_RAW) { for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = src[b.srcOff + i]; return; }
+    if (b.type == ZB_BT_RLE) { u8 const v = src[b.srcOff]; for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = v; return; }
+    const u8* const lit = lits + b.litPos;
+    u64* const sq = seqs + b.seqPos;
+    u64* const mp = matchPos + b.seqPos;
+    ZbdRep rep = o.start;
+    u64 const inFrame = o.dstOff - o.frameOff;                       /* bytes of the frame in front of this block */
+    u32 op = 0, lp = 0, err = 0;
+    for (u32 i0 = 0; i0 < b.nbSeq; i0 += 32u) {
+        u32 const n = min(32u, b.nbSeq - i0);
+        u64 const q = (lane < n) ? sq[i0 + lane] : 0ull;
+        u32 const myLL = ZBD_SEQ_LL(q), myML = ZBD_SEQ_ML(q);
+        u32 myOff = 0, myOp = 0, myLp = 0;
+        /* the history and the positions are a serial walk (warp-uniform); lane j keeps sequence j's numbers */
+        for (u32 j = 0; j < n; j++) {
+            u32 const ob = __shfl_sync(ZB_FULL, ZBD_SEQ_OFF(q), (int)j), ll = __shfl_sync(ZB_FULL, myLL, (int)j), ml = __shfl_sync(ZB_FULL, myML, (int)j);
+            u32 const off = zbd_rep_apply(&rep, ob, ll, false);
+            if (lane == j) { myOff = off; myOp = op; myLp = lp; }
+            op += ll;
+            if (off == 0u || (u64)off > inFrame + op + dictContentSize) err = ZBD_CORRUPT;
+            op += ml; lp += ll;
+        }
+        if (err) break;
+        if (lane < n) { sq[i0 + lane] = (u64)myOff | ((u64)myML << 28); mp[i0 + lane] = o.dstOff + myOp + myLL; }
+        /* the literal runs: one after the other, 32 bytes a step */
+        for (u32 j = 0; j < n; j++) {
+            u32 const ll = __shfl_sync(ZB_FULL, myLL, (int)j), to = __shfl_sync(ZB_FULL, myOp, (int)j), from = __shfl_sync(ZB_FULL, myLp, (int)j);
+            for (u32 k = lane; k < ll; k += 32u) out[to + k] = lit[from + k];
+        }
+    }
+    if (!err) { u32 const rest = b.litRegen - lp; for (u32 k = lane; k < rest; k += 32u) out[op + k] = lit[lp + k]; }
+    if (err && lane == 0) atomicMax(execErr, err);
+}
+
+/* ------------------------------------------------------------------------------------------------ D5 matches
+ * One CTA per frame.  Its warps take the frame's matches round-robin, in order (match i goes to warp i mod W).  A match
+ * may start once no UNFINISHED earlier match can still write into its source: the first `F` matches are all finished
+ * (F is found by walking the ring of completion marks), so everything in front of match F's destination is final —
+ * literals were placed by D4 — and a match whose source ends there or earlier is free to go.  Matches with offsets
+ * larger than the few KiB in flight therefore overlap; a chain of short offsets runs at one match per completion.
+ * dst[p + k] = history[p - off + (k mod off)]: every source byte exists before the match begins. */
+#define ZBD_RING 256u                  /* completion marks kept: a warp may run at most this far ahead of the oldest unfinished match */
+template <int W>
+__global__ void __launch_bounds__(32 * W)
+zbd_matches_kernel(const ZbdBlock* __restrict__ blocks, const ZbdFrame* __restrict__ frames, const u64* __restrict__ seqs, const u64* __restrict__ matchPos,
+                   const ZbdBlockOut* __restrict__ bout, u8* __restrict__ dst, const u8* __restrict__ dictContent, u32 dictContentSize)
+{
+    __shared__ volatile u32 done[ZBD_RING];     /* done[i mod RING] = i + 1 once match i is finished */
+    u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    ZbdFrame const fr = frames[blockIdx.x];
+    if (fr.nbBlocks == 0) return;
+    ZbdBlock const b0 = blocks[fr.firstBlock], bl = blocks[fr.firstBlock + fr.nbBlocks - 1u];
+    u64 const g0 = b0.seqPos, g1 = bl.seqPos + (bl.type == ZB_BT_COMPRESSED ? bl.nbSeq : 0u);     /* the frame's matches: [g0, g1) of the call's sequence space */
+    u32 const n = (u32)(g1 - g0);
+    u64 const frameOff = bout[fr.firstBlock].frameOff;
+    u64 const frameEnd = bout[fr.firstBlock + fr.nbBlocks - 1u].dstOff + bout[fr.firstBlock + fr.nbBlocks - 1u].regen;
+    for (u32 i = threadIdx.x; i < ZBD_RING; i += 32u * W) done[i] = 0u;
+    __syncthreads();
+    u32 F = 0;                                   /* matches [0, F) are known to be finished (per warp, monotonic) */
+    for (u32 i = w; i < n; i += W) {
+        u64 const q = seqs[g0 + i];
+        u64 const pos = matchPos[g0 + i];
+        u32 const off = (u32)q & 0x0FFFFFFFu, ml = (u32)(q >> 28);
+        u64 const inFrame = pos - frameOff;      /* frame position of the match's first byte */
+        /* a block D4 gave up on (corrupt input: the call fails) leaves descriptors that must not be followed */
+        bool const sane = off != 0u && pos >= frameOff && pos + ml <= frameEnd && (u64)off <= inFrame + dictContentSize;
+        u32 const span = ml < off ? ml : off;
+        /* source = frame positions [inFrame - off, inFrame - off + span); the part below 0 is dictionary content */
+        u64 const srcEnd = inFrame + span > off ? inFrame + span - off : 0;
+        if (W > 1) {
+            while (F < i) {
+                if (done[F % ZBD_RING] >= F + 1u) { F++; continue; }          /* match F is finished (a later mark in its slot implies it): look at the next one */
+                if (i - F < ZBD_RING && matchPos[g0 + F] - frameOff >= srcEnd) break;   /* everything in front of the oldest unfinished match is final */
+                __nanosleep(20);
+            }
+            __threadfence_block();
+        }
+        u8* const out = dst + pos;
+        if (!sane) { }
+        else if ((u64)off > inFrame) {           /* starts in the dictionary */
+            const u8* const frameBase = dst + frameOff;
+            u32 r = lane % off; u32 const inc = 32u % off;
+            for (u32 k = lane; k < ml; k += 32u) {
+                long long const sp = (long long)inFrame - (long long)off + (long long)r;
+                out[k] = sp < 0 ? dictContent[(long long)dictContentSize + sp] : frameBase[sp];
+                r += inc; if (r >= off) r -= off;
+            }
+        } else {
+            const u8* const from = out - off;
+            if (off >= ml) { for (u32 k = lane; k < ml; k += 32u) out[k] = from[k]; }
+            else {
                 u32 r = lane % off; u32 const inc = 32u % off;
-                for (u32 k = lane; k < ml; k += 32u) {
-                    long long const sp = (long long)here - (long long)off + (long long)r;
-                    out[op + k] = sp < 0 ? dictContent[(long long)dictContentSize + sp] : __ldcg(frameBase + sp);
-                    r += inc; if (r >= off) r -= off;
-                }
-                op += ml;
-                continue;
-            }
-            if (off > op) {                                          /* the match starts in an earlier block */
-                u64 const lo = o.dstOff + op - off;
-                u64 const span = ml < off ? ml : off;
-                zbd_wait_range(bout, progress, bi, firstBlock, lo, lo + span, lane);
-            } else __syncwarp();                                     /* this sequence's literals may be the match's source */
-            /* dst[op + k] = history[op - off + (k mod off)]: every source byte exists before this match begins */
-            {   const u8* const from = out + op - off;               /* may point into earlier blocks (same buffer) */
-                if (off >= ml) {
-                    if (off > op) { for (u32 k = lane; k < ml; k += 32u) out[op + k] = __ldcg(from + k); }
-                    else          { for (u32 k = lane; k < ml; k += 32u) out[op + k] = from[k]; }
-                } else {
-                    u32 r = lane % off; u32 const inc = 32u % off;
-                    for (u32 k = lane; k < ml; k += 32u) {
-                        out[op + k] = (off > op) ? __ldcg(from + r) : from[r];
-                        r += inc; if (r >= off) r -= off;
-                    }
-                }
-            }
-            op += ml;
-            if (op - published >= 2048u) {                           /* let the blocks behind this one advance */
-                __threadfence(); __syncwarp();
-                if (lane == 0) zbd_st_volatile(progress + bi, op);
-                published = op;
+                for (u32 k = lane; k < ml; k += 32u) { out[k] = from[r]; r += inc; if (r >= off) r -= off; }
             }
         }
-        if (!err) { u32 const rest = b.litRegen - lp; for (u32 k = lane; k < rest; k += 32u) out[op + k] = lit[lp + k]; }
-        if (err && lane == 0) atomicMax(execErr, err);
+        if (W > 1) {
+            __threadfence_block(); __syncwarp();
+            if (lane == 0) done[i % ZBD_RING] = i + 1u;
+        } else __syncwarp();
     }
-    __threadfence(); __syncwarp();
-    if (lane == 0) zbd_st_volatile(progress + bi, o.regen);          /* also on an error: nobody may wait for ever */
 }
 
 /* ------------------------------------------------------------------------------------------------ host driver */
 struct ZSTD_DCtx_s {
     int device, bindDevice;
     cudaStream_t stream;
-    ZbdBlock* d_blocks; ZbdFrame* d_frames; ZbdBlockOut* d_bout; u32* d_progress; size_t capBlocks, capFrames;
-    u8* d_lits; size_t capLits; u64* d_seqs; size_t capSeqs;
+    ZbdBlock* d_blocks; ZbdFrame* d_frames; ZbdBlockOut* d_bout; size_t capBlocks, capFrames;
+    u8* d_lits; size_t capLits; u64* d_seqs; size_t capSeqs; u64* d_matchPos; size_t capMatchPos;
     u8* d_in; size_t capIn; u8* d_out; size_t capOut;
-    u64* d_res; u32* d_ticket; u32* d_execErr;
+    u64* d_res; u32* d_execErr;
     u64* h_res;                  /* pinned: walker / scan results */
     u8* d_dict; size_t capDict;  /* the call's dictionary, whole (header + content) */
     ZbdDictInfo di; size_t dictSize;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     ZSTDB200_dstats stats;
 };
 extern "C" int zb_boundDevice(void);                                 /* zb_api.cu: ZSTDB200_setDevice's value, or -1 */
@@ -400,9 +419,9 @@ extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts 
     if (d->device >= 0) {
         int prev = -1; cudaGetDevice(&prev);
         cudaSetDevice(d->device);
-        cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_progress); cudaFree(d->d_lits); cudaFree(d->d_seqs);
+        cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_lits); cudaFree(d->d_seqs); cudaFree(d->d_matchPos);
         cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res); cudaFree(d->d_dict);
-        for (int i = 0; i < 6; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+        for (int i = 0; i < 7; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
         if (d->stream) cudaStreamDestroy(d->stream);
         if (prev >= 0) cudaSetDevice(prev);
     }
@@ -417,10 +436,10 @@ static size_t zbd_ctxInit(ZSTD_DCtx* d)
     int dev = d->bindDevice < 0 ? 0 : d->bindDevice;
     DCK(cudaSetDevice(dev));
     DCK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 6; i++) DCK(cudaEventCreate(&d->ev[i]));
+    for (int i = 0; i < 7; i++) DCK(cudaEventCreate(&d->ev[i]));
     DCK(cudaMalloc(&d->d_res, 16 * sizeof(u64)));
     DCK(cudaMallocHost(&d->h_res, 16 * sizeof(u64)));
-    d->d_ticket = (u32*)(d->d_res + 8); d->d_execErr = (u32*)(d->d_res + 9);
+    d->d_execErr = (u32*)(d->d_res + 9);
     d->device = dev;
     return 0;
 }
@@ -435,7 +454,7 @@ template <typename T> static size_t zbd_grow(T** p, size_t* cap, size_t need)
 }
 
 /* D1 .. D4 over descriptors that are already on the device; returns the output size */
-static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_src, u32 nb, u32 nf, cudaStream_t st)
+static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_src, u32 nb, u32 nf, u64 seqCount, cudaStream_t st)
 {
     DCK(cudaMemsetAsync(d->d_execErr, 0, sizeof(u32), st));
     DCK(cudaEventRecord(d->ev[1], st));
@@ -444,14 +463,21 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     DCK(cudaEventRecord(d->ev[2], st));
     zbd_sequences_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_seqs, d->d_bout, d->d_dict, d->di);
     DCK(cudaEventRecord(d->ev[3], st));
-    zbd_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(d->d_blocks, nb, d->d_frames, nf, d->d_bout, (u64)dstCapacity, d->d_progress, d->d_ticket, d->d_res, d->di);
+    zbd_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(d->d_blocks, nb, d->d_frames, nf, d->d_bout, (u64)dstCapacity, d->d_res, d->di);
     DCK(cudaMemcpyAsync(d->h_res, d->d_res, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     DCK(cudaStreamSynchronize(st));                                  /* nothing is written to dst before the sizes are known to fit */
     if (d->h_res[0]) return ZB_ERR((u32)d->h_res[0]);
     size_t const total = (size_t)d->h_res[1];
     DCK(cudaEventRecord(d->ev[4], st));
-    zbd_execute_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_frames, d->d_lits, d->d_seqs, d->d_bout, d_dst, d->d_progress, d->d_ticket, d->d_execErr,
-                                                              d->dictSize ? d->d_dict + d->di.contentOff : (const u8*)NULL, d->dictSize ? (u32)(d->dictSize - d->di.contentOff) : 0u);
+    u32 const dictContent = d->dictSize ? (u32)(d->dictSize - d->di.contentOff) : 0u;
+    const u8* const d_dictContent = d->dictSize ? d->d_dict + d->di.contentOff : (const u8*)NULL;
+    zbd_place_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, dictContent, d->d_execErr);
+    DCK(cudaEventRecord(d->ev[6], st));
+    /* warps per frame by the work a frame holds: a long frame keeps a whole SM busy, a call of short records gives each a warp */
+    {   u64 const perFrame = seqCount / (nf ? nf : 1u);
+        if (perFrame >= 2048u)     zbd_matches_kernel<32><<<nf, 1024, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent);
+        else if (perFrame >= 128u) zbd_matches_kernel<4><<<nf, 128, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent);
+        else                       zbd_matches_kernel<1><<<nf, 32, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent); }
     DCK(cudaEventRecord(d->ev[5], st));
     DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));
     DCK(cudaStreamSynchronize(st));
@@ -460,23 +486,25 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     {   float ms = 0;
         cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]); d->stats.literals_ms = ms;
         cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); d->stats.sequences_ms = ms;
-        cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); d->stats.execute_ms = ms;
+        cudaEventElapsedTime(&ms, d->ev[4], d->ev[6]); d->stats.place_ms = ms;
+        cudaEventElapsedTime(&ms, d->ev[6], d->ev[5]); d->stats.execute_ms = ms;
         cudaEventElapsedTime(&ms, d->ev[1], d->ev[5]); d->stats.kernel_ms = ms;
-        d->stats.nbBlocks = nb; d->stats.nbFrames = nf; d->stats.launches = 4; }
+        d->stats.nbBlocks = nb; d->stats.nbFrames = nf; d->stats.launches = 5; }
     return total;
 }
 
 static size_t zbd_ensure(ZSTD_DCtx* d, u32 nb, u32 nf, u64 litBytes, u64 seqCount)
 {
     if (nb > d->capBlocks) {
-        cudaFree(d->d_blocks); cudaFree(d->d_bout); cudaFree(d->d_progress); d->d_blocks = NULL; d->d_bout = NULL; d->d_progress = NULL; d->capBlocks = 0;
+        cudaFree(d->d_blocks); cudaFree(d->d_bout); d->d_blocks = NULL; d->d_bout = NULL; d->capBlocks = 0;
         size_t const n = (size_t)nb + nb / 8 + 64;
-        DCK(cudaMalloc(&d->d_blocks, n * sizeof(ZbdBlock))); DCK(cudaMalloc(&d->d_bout, (n + 1) * sizeof(ZbdBlockOut))); DCK(cudaMalloc(&d->d_progress, n * sizeof(u32)));
+        DCK(cudaMalloc(&d->d_blocks, n * sizeof(ZbdBlock))); DCK(cudaMalloc(&d->d_bout, (n + 1) * sizeof(ZbdBlockOut)));
         d->capBlocks = n;
     }
     {   size_t const e = zbd_grow(&d->d_frames, &d->capFrames, (size_t)nf); if (zbd_isErr(e)) return e; }
     {   size_t const e = zbd_grow(&d->d_lits, &d->capLits, (size_t)litBytes + 16); if (zbd_isErr(e)) return e; }
     {   size_t const e = zbd_grow(&d->d_seqs, &d->capSeqs, (size_t)seqCount + 1); if (zbd_isErr(e)) return e; }
+    {   size_t const e = zbd_grow(&d->d_matchPos, &d->capMatchPos, (size_t)seqCount + 1); if (zbd_isErr(e)) return e; }
     return 0;
 }
 
@@ -505,7 +533,7 @@ static size_t zbd_decompressHost(ZSTD_DCtx* d, void* dst, size_t dstCapacity, co
     {   size_t const r = zbd_grow(&d->d_out, &d->capOut, outNeed + 16); if (zbd_isErr(r)) return r; }
     DCK(cudaMemcpyAsync(d->d_blocks, B.data(), (size_t)nb * sizeof(ZbdBlock), cudaMemcpyHostToDevice, st));
     DCK(cudaMemcpyAsync(d->d_frames, F.data(), (size_t)nf * sizeof(ZbdFrame), cudaMemcpyHostToDevice, st));
-    size_t const total = zbd_run(d, d->d_out, outNeed, d->d_in, nb, nf, st);
+    size_t const total = zbd_run(d, d->d_out, outNeed, d->d_in, nb, nf, seq, st);
     if (zbd_isErr(total)) return total;
     if (total > dstCapacity) return ZB_ERR(ZB_error_dstSize_tooSmall);
     if (total) DCK(cudaMemcpy(dst, d->d_out, total, cudaMemcpyDeviceToHost));
@@ -550,7 +578,7 @@ static size_t zbd_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity
     u32 const nb = (u32)d->h_res[1], nf = (u32)d->h_res[2];
     if (nb == 0) return 0;
     {   size_t const r = zbd_ensure(d, nb, nf, d->h_res[3], d->h_res[4]); if (zbd_isErr(r)) return r; }
-    return zbd_run(d, (u8*)d_dst, dstCapacity, (const u8*)d_src, nb, nf, st);
+    return zbd_run(d, (u8*)d_dst, dstCapacity, (const u8*)d_src, nb, nf, d->h_res[4], st);
 }
 
 struct ZbdDeviceGuard { int prev; ZbdDeviceGuard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } } ~ZbdDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); } };

@@ -197,7 +197,7 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
 #define WALK_P_SMALL 4           /* positions per thread for tables <= 56 KiB (development knob: tools/build_variant.sh) */
 #endif
 #ifndef WALK_P_MID
-#define WALK_P_MID 2             /* tables of 56 .. 113 KiB: two CTAs per SM */
+#define WALK_P_MID 4             /* tables of 56 .. 113 KiB: two CTAs per SM (measured on config 4: 10.2 ms with 4 positions per thread, 11.2 with 2) */
 #endif
 #ifndef WALK_MINB_SMALL
 #define WALK_MINB_SMALL 4        /* CTAs per SM the register allocation of that variant leaves room for */
