@@ -483,6 +483,29 @@ def run_ours(args):
         dist.all_reduce(tot)
     d2h_total, h2d_total = int(tot[0]), int(tot[1])
 
+    # ---- GPU decompression of what was produced (outside the timed region): the frames of rank 0 go back through
+    # ZSTDB200_decompressDevice and must equal the input, compared on the device ----
+    decode = None
+    if rank == 0 and wl.dict is None and hasattr(L, "ZSTD_createDCtx"):
+        try:
+            dctx = zstd_b200.ZSTD_DCtx(device=local)
+            d_comp = torch.frombuffer(bytearray(got_dev), dtype=torch.uint8).cuda()
+            d_back = torch.empty(size, dtype=torch.uint8, device="cuda")
+            best = None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                n_back = dctx.decompress_device(d_back.data_ptr(), size, d_comp.data_ptr(), len(got_dev))
+                e1.record(); torch.cuda.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            st = dctx.stats()
+            decode = {"gpu_roundtrip_ok": bool(n_back == size and torch.equal(d_back, d_src)), "value": round(size / best / 1e6, 2), "unit": "GB/s (output bytes, device buffers)",
+                      "ms": round(best, 3), "kernel_ms": {"literals": round(st.literals_ms, 3), "sequences": round(st.sequences_ms, 3), "place": round(st.place_ms, 3), "matches": round(st.execute_ms, 3)}}
+            dctx.close(); del d_comp, d_back
+        except Exception as ex:                                  # reported, never fatal for the compression line
+            decode = {"error": str(ex)}
+
     # ---- parity of what was timed (outside the timed region) ----
     assert bytes(h_dst[:ce].numpy()) == got_dev, "host-path and device-path frames differ"
     digest = hashlib.sha256(wl.src).hexdigest()
@@ -560,7 +583,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "api": "ZSTD_compressCCtx(host pinned src/dst)" if (wl.nframes == 1) else ("ZSTDB200_compressFrames_usingCDict" if cdict is not None else "ZSTDB200_compressFrames") + "(host pinned src/dst)"},
-            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+            "decode": decode, "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -15,6 +15,10 @@
 #define ERR(c) ((size_t)-(long)(c))
 
 struct BlockOut { std::vector<u8> lits; std::vector<u64> seqs; u32 sumLL, sumML; ZbdRep transfer; };
+/* dependency statistics of the last call (development: how parallel is the match stage of a frame?) */
+extern "C" { unsigned long long zbh_nbMatches, zbh_maxDepth, zbh_nearDeps, zbh_anyDeps; }
+
+static std::vector<unsigned long long> g_mStart, g_mEnd; static std::vector<unsigned> g_mDepth;
 static const u8* g_dict = NULL;            /* the call's dictionary (single-threaded test code) */
 static ZbdDictInfo g_di;
 
@@ -136,6 +140,7 @@ extern "C" size_t zbh_decompress_usingDict(void* dstv, size_t cap, const void* s
     e = zbd_walk(in, size, B.data(), nb, F.data(), nf, &nb, &nf, &litBytes, &seqCount, g_di.entropy != 0, g_di.dictID);
     if (e) return ERR(e);
     size_t out = 0;
+    zbh_nbMatches = zbh_maxDepth = zbh_nearDeps = zbh_anyDeps = 0; g_mStart.clear(); g_mEnd.clear(); g_mDepth.clear();
     for (u32 f = 0; f < nf; f++) {
         size_t const frameStart = out;
         ZbdRep rep; rep.r[0] = 1; rep.r[1] = 4; rep.r[2] = 8;
@@ -161,6 +166,15 @@ extern "C" size_t zbh_decompress_usingDict(void* dstv, size_t cap, const void* s
                 memcpy(dst + out, o.lits.data() + lp, ll); out += ll; lp += ll;
                 size_t const inFrame = out - frameStart;
                 if (off == 0 || off > inFrame + contentSize) return ERR(ZBD_CORRUPT);
+                if (ml && off <= inFrame) {                        /* which earlier matches wrote [src, src + min(ml, off))? */
+                    unsigned long long const ss = out - off, se = ss + (ml < off ? ml : off);
+                    size_t lo = 0, hi = g_mStart.size();
+                    while (lo < hi) { size_t const mid = (lo + hi) / 2; if (g_mEnd[mid] <= ss) lo = mid + 1; else hi = mid; }
+                    unsigned depth = 0; bool any = false, near = false;
+                    for (size_t j = lo; j < g_mStart.size() && g_mStart[j] < se; j++) { any = true; if (g_mDepth[j] > depth) depth = g_mDepth[j]; if (g_mStart.size() - j <= 32) near = true; }
+                    g_mStart.push_back(out); g_mEnd.push_back(out + ml); g_mDepth.push_back(depth + 1);
+                    zbh_nbMatches++; if (any) zbh_anyDeps++; if (near) zbh_nearDeps++; if (depth + 1 > zbh_maxDepth) zbh_maxDepth = depth + 1;
+                }
                 for (u32 k = 0; k < ml; k++) {                      /* the gather form the kernel uses; positions in front of the frame are dictionary content */
                     long long const sp = (long long)inFrame - (long long)off + (long long)(k % off);
                     dst[out + k] = sp < 0 ? content[(long long)contentSize + sp] : dst[frameStart + sp];

@@ -68,3 +68,21 @@ def test_gather_world_size_2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_split_one_frame_shares():
+    """shares of one frame for ZSTDB200_compressFramePart: aligned starts, contiguous, complete; idle ranks marked"""
+    from zstd_b200.sharding import split_one_frame
+    A = 512 << 10
+    for size, world in ((1 << 30, 8), (5 * A + 12345, 3), (3 << 20, 8), (400_000, 2), (0, 2), (A, 1), (A + 1, 4)):
+        parts = split_one_frame(size, world, A)
+        assert len(parts) == world
+        pos = 0
+        for b, n in parts:
+            if b < 0:
+                assert n == 0
+                continue
+            assert b == pos and b % A == 0
+            pos += n
+        assert pos == size
+        assert sum(1 for b, n in parts if b >= 0) >= 1

@@ -23,10 +23,10 @@
  *   D4  place     one warp per block, all blocks at once: raw / RLE blocks and every literal run go to their final place,
  *                 every match becomes (destination, offset, length) with its repcode resolved.  Nothing of the output is
  *                 read, so no block waits for another.
- *   D5  matches   one CTA per frame, its warps taking the frame's matches in order: LZ77 copies depend on earlier output,
- *                 which makes a frame a sequential object; a completion ring in shared memory lets a match start as soon
- *                 as no unfinished earlier match can write into its source, so matches with offsets beyond the few KiB
- *                 in flight overlap.  Frames of a call run side by side.
+ *   D5  matches   LZ77 copies read earlier output, which chains the matches of a frame — but a match depends only on the
+ *                 few matches that wrote its source bytes.  One lane per match, handed out in order over a ticket counter;
+ *                 a lane finds the writers of its source range through a tile index D4 left behind, waits for their
+ *                 completion flags, copies, raises its own.  Independent matches run across the whole GPU.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -270,10 +270,15 @@ zbd_scan_kernel(const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const ZbdFram
  * One warp per block, every block of the call at once: raw / RLE blocks are written; of a compressed block every literal run
  * goes to its final place and every match becomes (absolute destination, offset, length) — the repcode history runs over the
  * block's sequences from the start history D3 computed.  No byte of the output is READ here, so blocks do not depend on
- * each other.  seqs[g] becomes offset | length << 28, matchPos[g] the match's first output byte. */
+ * each other.  A match that begins in the dictionary's content gets those bytes here and continues as an ordinary match
+ * behind them.  seqs[g] becomes offset | length << 28, matchPos[g] the match's first output byte, and for every 64-byte
+ * tile of the output tileFirst[] the first match (in the call's match order) that ends behind the tile's first byte:
+ * what D5 needs to find the matches a source range depends on. */
+#define ZBD_TILE_LOG 6u
 __global__ void __launch_bounds__(32 * ZBD_WARPS)
 zbd_place_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks, u32 nbBlocks, const u8* __restrict__ lits, u64* __restrict__ seqs,
-                 u64* __restrict__ matchPos, const ZbdBlockOut* __restrict__ bout, u8* __restrict__ dst, u32 dictContentSize, u32* __restrict__ execErr)
+                 u64* __restrict__ matchPos, u32* __restrict__ tileFirst, const ZbdBlockOut* __restrict__ bout, u8* __restrict__ dst,
+                 const u8* __restrict__ dictContent, u32 dictContentSize, u32* __restrict__ execErr)
 {
     u32 const lane = threadIdx.x & 31u;
     u32 const bi = blockIdx.x * ZBD_WARPS + (threadIdx.x >> 5);
@@ -281,105 +286,170 @@ zbd_place_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks
     ZbdBlock const b = blocks[bi];
     ZbdBlockOut const o = bout[bi];
     u8* const out = dst + o.dstOff;
-    if (b.type == ZB_BT_RAW) { for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = src[b.srcOff + i]; return; }
-    if (b.type == ZB_BT_RLE) { u8 const v = src[b.srcOff]; for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = v; return; }
+    u32 const gFirst = (u32)b.seqPos;                                /* the call's match order: blocks in input order */
+    u32 const gNext = gFirst + (b.type == ZB_BT_COMPRESSED ? b.nbSeq : 0u);
+    /* tiles whose first byte lies in (lo, hi] of the output belong to match g */
+    auto tiles = [&](u64 lo, u64 hi, u32 g) {
+        for (u64 t = (lo >> ZBD_TILE_LOG) + 1u + lane; (t << ZBD_TILE_LOG) <= hi; t += 32u) tileFirst[t] = g;
+    };
+    if (b.type != ZB_BT_COMPRESSED) {
+        if (b.type == ZB_BT_RAW) { for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = src[b.srcOff + i]; }
+        else { u8 const v = src[b.srcOff]; for (u32 i = lane; i < b.rawSize; i += 32u) out[i] = v; }
+        if (o.dstOff == 0 && lane == 0) tileFirst[0] = gNext;
+        tiles(o.dstOff, o.dstOff + o.regen, gNext);                  /* no match ends in here: the next block's first one is the first behind these tiles */
+        return;
+    }
     const u8* const lit = lits + b.litPos;
     u64* const sq = seqs + b.seqPos;
     u64* const mp = matchPos + b.seqPos;
     ZbdRep rep = o.start;
     u64 const inFrame = o.dstOff - o.frameOff;                       /* bytes of the frame in front of this block */
-    u32 op = 0, lp = 0, err = 0;
+    u32 op = 0, lp = 0, err = 0, failedAt = 0;
+    if (o.dstOff == 0 && lane == 0) tileFirst[0] = gFirst;
     for (u32 i0 = 0; i0 < b.nbSeq; i0 += 32u) {
         u32 const n = min(32u, b.nbSeq - i0);
         u64 const q = (lane < n) ? sq[i0 + lane] : 0ull;
-        u32 const myLL = ZBD_SEQ_LL(q), myML = ZBD_SEQ_ML(q);
-        u32 myOff = 0, myOp = 0, myLp = 0;
+        u32 const myLL = ZBD_SEQ_LL(q);
+        u32 myML = ZBD_SEQ_ML(q), myOff = 0, myOp = 0, myLp = 0;
         /* the history and the positions are a serial walk (warp-uniform); lane j keeps sequence j's numbers */
         for (u32 j = 0; j < n; j++) {
             u32 const ob = __shfl_sync(ZB_FULL, ZBD_SEQ_OFF(q), (int)j), ll = __shfl_sync(ZB_FULL, myLL, (int)j), ml = __shfl_sync(ZB_FULL, myML, (int)j);
             u32 const off = zbd_rep_apply(&rep, ob, ll, false);
             if (lane == j) { myOff = off; myOp = op; myLp = lp; }
             op += ll;
-            if (off == 0u || (u64)off > inFrame + op + dictContentSize) err = ZBD_CORRUPT;
+            if (!err && (off == 0u || (u64)off > inFrame + op + dictContentSize)) { err = ZBD_CORRUPT; failedAt = i0 + j; }
             op += ml; lp += ll;
         }
         if (err) break;
-        if (lane < n) { sq[i0 + lane] = (u64)myOff | ((u64)myML << 28); mp[i0 + lane] = o.dstOff + myOp + myLL; }
         /* the literal runs: one after the other, 32 bytes a step */
         for (u32 j = 0; j < n; j++) {
             u32 const ll = __shfl_sync(ZB_FULL, myLL, (int)j), to = __shfl_sync(ZB_FULL, myOp, (int)j), from = __shfl_sync(ZB_FULL, myLp, (int)j);
             for (u32 k = lane; k < ll; k += 32u) out[to + k] = lit[from + k];
         }
+        if (lane < n) {
+            u32 mpos = myOp + myLL;                                  /* block-relative first byte of the match */
+            u64 const here = inFrame + mpos;                          /* its frame position */
+            if ((u64)myOff > here) {                                 /* begins in the dictionary: those bytes now, the rest is a match of the same offset */
+                u32 const fromDict = (u32)((u64)myOff - here) < myML ? (u32)((u64)myOff - here) : myML;
+                const u8* const dp = dictContent + dictContentSize - ((u64)myOff - here);
+                for (u32 k = 0; k < fromDict; k++) out[mpos + k] = dp[k];
+                mpos += fromDict; myML -= fromDict;
+            }
+            sq[i0 + lane] = (u64)myOff | ((u64)myML << 28);
+            mp[i0 + lane] = o.dstOff + mpos;
+            /* tiles that begin in (end of the match before, end of this match] */
+            u64 const lo = o.dstOff + myOp, hi = o.dstOff + myOp + myLL + ZBD_SEQ_ML(q);
+            for (u64 t = (lo >> ZBD_TILE_LOG) + 1u; (t << ZBD_TILE_LOG) <= hi; t++) tileFirst[t] = gFirst + i0 + lane;
+        }
     }
-    if (!err) { u32 const rest = b.litRegen - lp; for (u32 k = lane; k < rest; k += 32u) out[op + k] = lit[lp + k]; }
-    if (err && lane == 0) atomicMax(execErr, err);
+    if (err) {                                                       /* the call fails; D5 must not follow what is left of this block */
+        for (u32 i = failedAt - (failedAt % 32u) + lane; i < b.nbSeq; i += 32u) { sq[i] = 1ull; mp[i] = o.dstOff; }
+        if (lane == 0) atomicMax(execErr, err);
+        tiles(o.dstOff, o.dstOff + o.regen, gNext);
+        return;
+    }
+    u32 const rest = b.litRegen - lp;
+    for (u32 k = lane; k < rest; k += 32u) out[op + k] = lit[lp + k];
+    tiles(o.dstOff + op, o.dstOff + o.regen, gNext);                 /* behind the block's last match */
 }
 
 /* ------------------------------------------------------------------------------------------------ D5 matches
- * One CTA per frame.  Its warps take the frame's matches round-robin, in order (match i goes to warp i mod W).  A match
- * may start once no UNFINISHED earlier match can still write into its source: the first `F` matches are all finished
- * (F is found by walking the ring of completion marks), so everything in front of match F's destination is final —
- * literals were placed by D4 — and a match whose source ends there or earlier is free to go.  Matches with offsets
- * larger than the few KiB in flight therefore overlap; a chain of short offsets runs at one match per completion.
- * dst[p + k] = history[p - off + (k mod off)]: every source byte exists before the match begins. */
-#define ZBD_RING 256u                  /* completion marks kept: a warp may run at most this far ahead of the oldest unfinished match */
-template <int W>
-__global__ void __launch_bounds__(32 * W)
-zbd_matches_kernel(const ZbdBlock* __restrict__ blocks, const ZbdFrame* __restrict__ frames, const u64* __restrict__ seqs, const u64* __restrict__ matchPos,
-                   const ZbdBlockOut* __restrict__ bout, u8* __restrict__ dst, const u8* __restrict__ dictContent, u32 dictContentSize)
+ * LZ77 copies read earlier output, which makes a frame a chain; but a match only depends on the few matches that WROTE
+ * its source bytes (literals are in place since D4).  So: one LANE per match, matches handed out in order, 32 at a time
+ * per warp over a ticket counter (a match only ever waits for matches with lower numbers, which have been handed out).
+ * A lane looks up, through tileFirst[], the range of matches that may have written [source, source + length), waits for
+ * their completion flags, copies, raises its own flag.  Independent matches — nearly all of them when offsets exceed a
+ * few hundred bytes — run in parallel across the whole GPU; what remains serial is the longest chain of matches that copy
+ * from one another.  dst[p + k] = history[p - off + (k mod off)]. */
+__device__ __forceinline__ u32 zbd_ld_flag(const u8* p) { u32 v; asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void zbd_st_flag(u8* p) { asm volatile("st.volatile.global.u8 [%0], %1;" :: "l"(p), "r"(1u) : "memory"); }
+__device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord) { return __ldcg(reinterpret_cast<const u32*>(alignedWord)); }
+
+/* n bytes from `from` to `out`, the two ranges not overlapping; sources are read through L2 (they may have been written by
+ * another SM a moment ago), four words in flight at a time; a source word is only loaded when it holds a needed byte */
+__device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n)
 {
-    __shared__ volatile u32 done[ZBD_RING];     /* done[i mod RING] = i + 1 once match i is finished */
-    u32 const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    ZbdFrame const fr = frames[blockIdx.x];
-    if (fr.nbBlocks == 0) return;
-    ZbdBlock const b0 = blocks[fr.firstBlock], bl = blocks[fr.firstBlock + fr.nbBlocks - 1u];
-    u64 const g0 = b0.seqPos, g1 = bl.seqPos + (bl.type == ZB_BT_COMPRESSED ? bl.nbSeq : 0u);     /* the frame's matches: [g0, g1) of the call's sequence space */
-    u32 const n = (u32)(g1 - g0);
-    u64 const frameOff = bout[fr.firstBlock].frameOff;
-    u64 const frameEnd = bout[fr.firstBlock + fr.nbBlocks - 1u].dstOff + bout[fr.firstBlock + fr.nbBlocks - 1u].regen;
-    for (u32 i = threadIdx.x; i < ZBD_RING; i += 32u * W) done[i] = 0u;
-    __syncthreads();
-    u32 F = 0;                                   /* matches [0, F) are known to be finished (per warp, monotonic) */
-    for (u32 i = w; i < n; i += W) {
-        u64 const q = seqs[g0 + i];
-        u64 const pos = matchPos[g0 + i];
-        u32 const off = (u32)q & 0x0FFFFFFFu, ml = (u32)(q >> 28);
-        u64 const inFrame = pos - frameOff;      /* frame position of the match's first byte */
-        /* a block D4 gave up on (corrupt input: the call fails) leaves descriptors that must not be followed */
-        bool const sane = off != 0u && pos >= frameOff && pos + ml <= frameEnd && (u64)off <= inFrame + dictContentSize;
-        u32 const span = ml < off ? ml : off;
-        /* source = frame positions [inFrame - off, inFrame - off + span); the part below 0 is dictionary content */
-        u64 const srcEnd = inFrame + span > off ? inFrame + span - off : 0;
-        if (W > 1) {
-            while (F < i) {
-                if (done[F % ZBD_RING] >= F + 1u) { F++; continue; }          /* match F is finished (a later mark in its slot implies it): look at the next one */
-                if (i - F < ZBD_RING && matchPos[g0 + F] - frameOff >= srcEnd) break;   /* everything in front of the oldest unfinished match is final */
-                __nanosleep(20);
+    u32 k = 0;
+    while (k < n && (((uintptr_t)(out + k)) & 3u)) { out[k] = __ldcg(from + k); k++; }
+    if (k + 4u <= n) {
+        const u8* const a = from + k;
+        const u8* aw = (const u8*)((uintptr_t)a & ~(uintptr_t)3);
+        u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
+        if (sh == 0u) {
+            for (; k + 16u <= n; k += 16u, aw += 16) {
+                u32 const w0 = zbd_ldcg32(aw), w1 = zbd_ldcg32(aw + 4), w2 = zbd_ldcg32(aw + 8), w3 = zbd_ldcg32(aw + 12);
+                u32* const o = reinterpret_cast<u32*>(out + k); o[0] = w0; o[1] = w1; o[2] = w2; o[3] = w3;
             }
-            __threadfence_block();
-        }
-        u8* const out = dst + pos;
-        if (!sane) { }
-        else if ((u64)off > inFrame) {           /* starts in the dictionary */
-            const u8* const frameBase = dst + frameOff;
-            u32 r = lane % off; u32 const inc = 32u % off;
-            for (u32 k = lane; k < ml; k += 32u) {
-                long long const sp = (long long)inFrame - (long long)off + (long long)r;
-                out[k] = sp < 0 ? dictContent[(long long)dictContentSize + sp] : frameBase[sp];
-                r += inc; if (r >= off) r -= off;
-            }
+            for (; k + 4u <= n; k += 4u, aw += 4) *reinterpret_cast<u32*>(out + k) = zbd_ldcg32(aw);
         } else {
-            const u8* const from = out - off;
-            if (off >= ml) { for (u32 k = lane; k < ml; k += 32u) out[k] = from[k]; }
-            else {
-                u32 r = lane % off; u32 const inc = 32u % off;
-                for (u32 k = lane; k < ml; k += 32u) { out[k] = from[r]; r += inc; if (r >= off) r -= off; }
+            u32 w0 = zbd_ldcg32(aw);
+            for (; k + 16u <= n; k += 16u, aw += 16) {
+                u32 const w1 = zbd_ldcg32(aw + 4), w2 = zbd_ldcg32(aw + 8), w3 = zbd_ldcg32(aw + 12), w4 = zbd_ldcg32(aw + 16);
+                u32* const o = reinterpret_cast<u32*>(out + k);
+                o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+                w0 = w4;
             }
+            for (; k + 4u <= n; k += 4u) { aw += 4; u32 const w1 = zbd_ldcg32(aw); *reinterpret_cast<u32*>(out + k) = __funnelshift_r(w0, w1, sh); w0 = w1; }
         }
-        if (W > 1) {
-            __threadfence_block(); __syncwarp();
-            if (lane == 0) done[i % ZBD_RING] = i + 1u;
-        } else __syncwarp();
+    }
+    for (; k < n; k++) out[k] = __ldcg(from + k);
+}
+
+#define ZBD_MATCH_THREADS 256
+__global__ void __launch_bounds__(ZBD_MATCH_THREADS)
+zbd_matches_kernel(const u64* __restrict__ seqs, const u64* __restrict__ matchPos, const u32* __restrict__ tileFirst, u32 nbMatches, u64 totalOut,
+                   u8* __restrict__ dst, u8* done, u32* ticket)
+{
+    u32 const lane = threadIdx.x & 31u;
+    while (true) {
+        u32 grp = 0;
+        if (lane == 0) grp = atomicAdd(ticket, 1u);
+        grp = __shfl_sync(ZB_FULL, grp, 0);
+        if ((u64)grp * 32u >= nbMatches) return;
+        u32 const g = grp * 32u + lane;
+        u64 q = 0, pos = 0;
+        if (g < nbMatches) { q = seqs[g]; pos = matchPos[g]; }
+        u32 const off = (u32)q & 0x0FFFFFFFu, ml = (u32)(q >> 28);
+        bool pending = g < nbMatches && ml != 0u && off != 0u && (u64)off <= pos && pos + ml <= totalOut;
+        if (g < nbMatches && !pending) zbd_st_flag(done + g);        /* nothing to copy (an empty or a refused match): nobody may wait for it */
+        u64 const s = pos - off;
+        u32 const span = ml < off ? ml : off;
+        /* matches that may have written [s, s + span): from the first one ending behind the tile of s to the first one
+         * ending behind the first tile at or past the range's end (it may begin inside the range), never past g - 1 */
+        u32 j = 0, jhi = 0;
+        bool deps = false;
+        if (pending && g != 0u) {
+            j = tileFirst[s >> ZBD_TILE_LOG];
+            jhi = tileFirst[(s + span + ((1u << ZBD_TILE_LOG) - 1u)) >> ZBD_TILE_LOG];
+            if (jhi >= g) jhi = g - 1u;
+            deps = j < g && j <= jhi;
+        }
+        /* rounds: every waiting lane polls once (together, not each on its own: a lane spinning alone would starve the
+         * lanes of its warp that are ready); the lanes whose writers are all done copy side by side */
+        while (__any_sync(ZB_FULL, pending)) {
+            bool ready = false;
+            if (pending) {
+                while (deps && zbd_ld_flag(done + j) != 0u) { j++; if (j > jhi) deps = false; }
+                ready = !deps;
+            }
+            if (ready) {
+                __threadfence();
+                u8* const out = dst + pos;
+                const u8* const from = dst + s;
+                if (off >= ml) zbd_copy_disjoint(out, from, ml);
+                else if (off < 8u) {                                 /* a short pattern: read once, written ml times over */
+                    u64 pat = 0;
+                    for (u32 k = 0; k < off; k++) pat |= (u64)__ldcg(from + k) << (8u * k);
+                    u32 r = 0;
+                    for (u32 k = 0; k < ml; k++) { out[k] = (u8)(pat >> (8u * r)); r++; if (r == off) r = 0; }
+                } else {                                             /* the `off` bytes in front of the match, again and again: every piece a disjoint copy */
+                    for (u32 k = 0; k < ml; k += off) zbd_copy_disjoint(out + k, from, ml - k < off ? ml - k : off);
+                }
+                __threadfence();
+                zbd_st_flag(done + g);
+                pending = false;
+            } else if (pending) __nanosleep(32);
+        }
     }
 }
 
@@ -389,8 +459,9 @@ struct ZSTD_DCtx_s {
     cudaStream_t stream;
     ZbdBlock* d_blocks; ZbdFrame* d_frames; ZbdBlockOut* d_bout; size_t capBlocks, capFrames;
     u8* d_lits; size_t capLits; u64* d_seqs; size_t capSeqs; u64* d_matchPos; size_t capMatchPos;
+    u32* d_tileFirst; size_t capTiles; u8* d_done; size_t capDone; int smCount;
     u8* d_in; size_t capIn; u8* d_out; size_t capOut;
-    u64* d_res; u32* d_execErr;
+    u64* d_res; u32* d_execErr; u32* d_ticket;
     u64* h_res;                  /* pinned: walker / scan results */
     u8* d_dict; size_t capDict;  /* the call's dictionary, whole (header + content) */
     ZbdDictInfo di; size_t dictSize;
@@ -419,7 +490,7 @@ extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts 
     if (d->device >= 0) {
         int prev = -1; cudaGetDevice(&prev);
         cudaSetDevice(d->device);
-        cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_lits); cudaFree(d->d_seqs); cudaFree(d->d_matchPos);
+        cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_lits); cudaFree(d->d_seqs); cudaFree(d->d_matchPos); cudaFree(d->d_tileFirst); cudaFree(d->d_done);
         cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res); cudaFree(d->d_dict);
         for (int i = 0; i < 7; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
         if (d->stream) cudaStreamDestroy(d->stream);
@@ -439,7 +510,8 @@ static size_t zbd_ctxInit(ZSTD_DCtx* d)
     for (int i = 0; i < 7; i++) DCK(cudaEventCreate(&d->ev[i]));
     DCK(cudaMalloc(&d->d_res, 16 * sizeof(u64)));
     DCK(cudaMallocHost(&d->h_res, 16 * sizeof(u64)));
-    d->d_execErr = (u32*)(d->d_res + 9);
+    d->d_execErr = (u32*)(d->d_res + 9); d->d_ticket = (u32*)(d->d_res + 10);
+    if (cudaDeviceGetAttribute(&d->smCount, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d->smCount <= 0) d->smCount = 148;
     d->device = dev;
     return 0;
 }
@@ -471,13 +543,19 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     DCK(cudaEventRecord(d->ev[4], st));
     u32 const dictContent = d->dictSize ? (u32)(d->dictSize - d->di.contentOff) : 0u;
     const u8* const d_dictContent = d->dictSize ? d->d_dict + d->di.contentOff : (const u8*)NULL;
-    zbd_place_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, dictContent, d->d_execErr);
+    {   size_t const r = zbd_grow(&d->d_tileFirst, &d->capTiles, (total >> ZBD_TILE_LOG) + 4); if (zbd_isErr(r)) return r; }
+    {   size_t const r = zbd_grow(&d->d_done, &d->capDone, (size_t)seqCount + 4); if (zbd_isErr(r)) return r; }
+    DCK(cudaMemsetAsync(d->d_tileFirst, 0xFF, ((total >> ZBD_TILE_LOG) + 4) * sizeof(u32), st));
+    DCK(cudaMemsetAsync(d->d_done, 0, (size_t)seqCount + 4, st));
+    DCK(cudaMemsetAsync(d->d_ticket, 0, sizeof(u32), st));
+    zbd_place_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_seqs, d->d_matchPos, d->d_tileFirst, d->d_bout, d_dst,
+                                                      d_dictContent, dictContent, d->d_execErr);
     DCK(cudaEventRecord(d->ev[6], st));
-    /* warps per frame by the work a frame holds: a long frame keeps a whole SM busy, a call of short records gives each a warp */
-    {   u64 const perFrame = seqCount / (nf ? nf : 1u);
-        if (perFrame >= 2048u)     zbd_matches_kernel<32><<<nf, 1024, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent);
-        else if (perFrame >= 128u) zbd_matches_kernel<4><<<nf, 128, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent);
-        else                       zbd_matches_kernel<1><<<nf, 32, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_bout, d_dst, d_dictContent, dictContent); }
+    if (seqCount) {
+        u64 const groups = (seqCount + 31u) / 32u, warpsPerCta = ZBD_MATCH_THREADS / 32u;
+        u64 const want = (groups + warpsPerCta - 1u) / warpsPerCta, cap = (u64)d->smCount * 8u;       /* resident CTAs take tickets until the matches run out */
+        zbd_matches_kernel<<<(u32)(want < cap ? want : cap), ZBD_MATCH_THREADS, 0, st>>>(d->d_seqs, d->d_matchPos, d->d_tileFirst, (u32)seqCount, (u64)total, d_dst, d->d_done, d->d_ticket);
+    }
     DCK(cudaEventRecord(d->ev[5], st));
     DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));
     DCK(cudaStreamSynchronize(st));
