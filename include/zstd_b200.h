@@ -136,6 +136,17 @@ ZSTDB200_API size_t     ZSTD_decompress_usingDict(ZSTD_DCtx* dctx, void* dst, si
 ZSTDB200_API unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
 ZSTDB200_API size_t     ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
 
+/* lib/zstd.h:880-924 — streaming decompression.  Whole frames are decoded on the GPU: compressed bytes are collected in
+ * the context until a frame is complete, then decoded and handed out as the caller makes room.  Returns 0 when a frame has
+ * been decoded and handed out completely, else a hint (> 0) for the next call, or an error code. */
+typedef ZSTD_DCtx ZSTD_DStream;
+ZSTDB200_API ZSTD_DStream* ZSTD_createDStream(void);
+ZSTDB200_API size_t ZSTD_freeDStream(ZSTD_DStream* zds);
+ZSTDB200_API size_t ZSTD_initDStream(ZSTD_DStream* zds);
+ZSTDB200_API size_t ZSTD_decompressStream(ZSTD_DStream* zds, ZSTD_outBuffer* output, ZSTD_inBuffer* input);
+ZSTDB200_API size_t ZSTD_DStreamInSize(void);
+ZSTDB200_API size_t ZSTD_DStreamOutSize(void);
+
 /* =====================  2. B200 extensions (no reference counterpart)  ===================== */
 
 /* Decompress frames whose bytes are in device memory into device memory.  The block headers are followed by one device

@@ -108,7 +108,7 @@ static void walk(const u8* buf, size_t low, size_t outStart, size_t end, size_t 
                  u32 mls, u32 N, u32 insStep, u32* dist)
 {
     u32* const table = (u32*)calloc((size_t)N, sizeof(u32));
-    u32 const B = ZB_BATCH;
+    u32 const B = zbo_tun.batch ? zbo_tun.batch : ZB_BATCH;       /* experiments: smaller batches */
     u32 hh[ZB_BATCH], dOld[ZB_BATCH];
     u8 act[ZB_BATCH], ins[ZB_BATCH];
     /* walk coordinates: x = p - low + shift, shift chosen so that batch borders (frame positions that are multiples of

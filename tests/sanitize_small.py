@@ -34,3 +34,34 @@ for n in (16383, 16385, 16391, 131071, 131073, 147461, 400_003):
     for level in (1, 3):
         assert ctx.compress(src, level) == zref.oracle_compress(src, level)
 print("sanitize workload ok", total)
+# device source of EXACTLY srcSize bytes from cudaMalloc (no caching-allocator slack behind it): reads past the end would show
+import ctypes
+rt = ctypes.CDLL("libcudart.so")
+for n in (131072, 131072 * 4 + 8, 1000):
+    src = zref.synthetic(n, 3, 0.7)
+    p = ctypes.c_void_p()
+    assert rt.cudaMalloc(ctypes.byref(p), ctypes.c_size_t(n)) == 0
+    assert rt.cudaMemcpy(p, src, ctypes.c_size_t(n), 1) == 0
+    capn = zstd_b200.ZSTD_compressBound(n)
+    o = torch.empty(capn, dtype=torch.uint8, device="cuda")
+    for level in (1, 3):
+        k = ctx.compress_device(o.data_ptr(), capn, p.value, n, level)
+        assert bytes(o[:k].cpu().numpy()) == zref.oracle_compress(src, level)
+    rt.cudaFree(p)
+# checksums on the device, streaming, a frame in parts
+c2 = zstd_b200.ZSTD_CCtx(); c2.set_parameter("checksum_flag", 1)
+n = c2.compress_device(out.data_ptr(), cap, t.data_ptr(), len(src), level=1)
+c2.close()
+# decompression: own frames, dictionary frames, device path
+dctx = zstd_b200.ZSTD_DCtx()
+for src in cases:
+    for level in (1, 3):
+        assert dctx.decompress(ctx.compress(src, level), len(src)) == src
+big = zref.synthetic(600_000, 12, 0.5)
+f = ctx.compress(big, 1)
+d_in = torch.frombuffer(bytearray(f), dtype=torch.uint8).cuda()
+d_o = torch.empty(len(big), dtype=torch.uint8, device="cuda")
+assert dctx.decompress_device(d_o.data_ptr(), len(big), d_in.data_ptr(), len(f)) == len(big)
+assert bytes(d_o.cpu().numpy()) == big
+dctx.close()
+print("sanitize workload (round 2 additions) ok")

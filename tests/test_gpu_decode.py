@@ -140,3 +140,36 @@ def test_dictionaries(cctx, dctx, kind):
         out = ctypes.create_string_buffer(2048)
         r = L.ZSTD_decompress_usingDict(dctx._h, out, 2048, stream[:200], 200, bytes(other), len(other))
         assert L.ZSTD_isError(r)
+
+
+def test_streaming_decompression(cctx):
+    """ZSTD_decompressStream: input arriving in arbitrary pieces, output handed out through a small buffer; frames of both
+    encoders, several frames in one stream"""
+    L = zstd_b200.lib()
+
+    class Buf(ctypes.Structure):
+        _fields_ = [("p", ctypes.c_void_p), ("size", ctypes.c_size_t), ("pos", ctypes.c_size_t)]
+    L.ZSTD_createDStream.restype = ctypes.c_void_p
+    L.ZSTD_freeDStream.argtypes = [ctypes.c_void_p]
+    L.ZSTD_initDStream.restype = ctypes.c_size_t; L.ZSTD_initDStream.argtypes = [ctypes.c_void_p]
+    L.ZSTD_decompressStream.restype = ctypes.c_size_t; L.ZSTD_decompressStream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    a, b = zref.synthetic(300_000, 41, 0.5), zref.synthetic(70_001, 42, 0.7)
+    stream = cctx.compress(a, 1) + (zref.ref_compress(b, 5) if zref.have_ref() else cctx.compress(b, 3)) + cctx.compress(b"", 1)
+    zds = L.ZSTD_createDStream()
+    assert not L.ZSTD_isError(L.ZSTD_initDStream(zds))
+    out = bytearray()
+    room = ctypes.create_string_buffer(10_000)
+    pos, last = 0, None
+    for piece in (1, 7, 100, 50_000, 3, len(stream)):
+        chunk = stream[pos:pos + piece]; pos += len(chunk)
+        sbuf = ctypes.create_string_buffer(chunk, max(len(chunk), 1))
+        i = Buf(ctypes.cast(sbuf, ctypes.c_void_p), len(chunk), 0)
+        for _ in range(10_000):
+            o = Buf(ctypes.cast(room, ctypes.c_void_p), len(room), 0)
+            last = L.ZSTD_decompressStream(zds, ctypes.byref(o), ctypes.byref(i))
+            assert not L.ZSTD_isError(last), L.ZSTD_getErrorName(last)
+            out += room.raw[:o.pos]
+            if i.pos == i.size and o.pos < len(room):
+                break
+    assert last == 0 and bytes(out) == a + b
+    L.ZSTD_freeDStream(zds)

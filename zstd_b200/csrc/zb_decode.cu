@@ -33,6 +33,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <new>
 #include "../../include/zstd_b200.h"
 #include "zb_common.h"
 #include "zb_decode_core.cuh"
@@ -463,6 +464,8 @@ struct ZSTD_DCtx_s {
     u8* d_in; size_t capIn; u8* d_out; size_t capOut;
     u64* d_res; u32* d_execErr; u32* d_ticket;
     u64* h_res;                  /* pinned: walker / scan results */
+    /* streaming front end (ZSTD_decompressStream): compressed bytes collected until a frame is complete, output waiting to be handed out */
+    std::vector<u8>* dsIn; std::vector<u8>* dsOut; size_t dsOutPos;
     u8* d_dict; size_t capDict;  /* the call's dictionary, whole (header + content) */
     ZbdDictInfo di; size_t dictSize;
     cudaEvent_t ev[7];
@@ -496,6 +499,7 @@ extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts 
         if (d->stream) cudaStreamDestroy(d->stream);
         if (prev >= 0) cudaSetDevice(prev);
     }
+    delete d->dsIn; delete d->dsOut;
     free(d);
     return 0;
 }
@@ -750,4 +754,67 @@ extern "C" size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize)
     }
     if (h.hasChecksum) { p += 4; if (p > srcSize) return ZB_ERR(ZB_error_srcSize_wrong); }
     return p;
+}
+
+/* ------------------------------------------------------------------------------------------------ streaming (lib/zstd.h:880-924)
+ * The GPU decodes whole frames, so the stream front end collects compressed bytes until a frame is complete
+ * (ZSTD_findFrameCompressedSize), decodes it, and hands the result out as the caller makes room.  Return value as in the
+ * reference: 0 when a frame has been decoded and handed out completely, else a hint (> 0) for the next input size. */
+static size_t zbd_frameOutputBound(const u8* in, size_t size)          /* content size, or blocks x 128 KiB when the header does not say */
+{
+    ZbdFrameHeader h;
+    if (zbd_readFrameHeader(&h, in, size) || h.skippable) return 0;
+    if (h.contentSize != ZBD_CONTENTSIZE_UNKNOWN) return (size_t)h.contentSize;
+    size_t p = h.headerSize, blocks = 0;
+    while (p + 3 <= size) { u32 const bh = zbd_le(in + p, 3); blocks++; p += 3u + (((bh >> 1) & 3u) == ZB_BT_RLE ? 1u : (bh >> 3)); if (bh & 1u) break; }
+    return blocks * (size_t)ZB_BLOCK_MAX;
+}
+extern "C" ZSTD_DStream* ZSTD_createDStream(void) { return ZSTD_createDCtx(); }
+extern "C" size_t ZSTD_freeDStream(ZSTD_DStream* zds) { return ZSTD_freeDCtx(zds); }
+extern "C" size_t ZSTD_initDStream(ZSTD_DStream* zds)
+{
+    if (!zds) return ZB_ERR(ZB_error_GENERIC);
+    if (zds->dsIn) zds->dsIn->clear();
+    if (zds->dsOut) zds->dsOut->clear();
+    zds->dsOutPos = 0;
+    return 5;                                                          /* a frame header's first bytes, as the reference suggests (ZSTD_startingInputLength) */
+}
+extern "C" size_t ZSTD_DStreamInSize(void) { return ZB_BLOCK_MAX + 3; }  /* lib/zstd.h:922 */
+extern "C" size_t ZSTD_DStreamOutSize(void) { return ZB_BLOCK_MAX; }
+extern "C" size_t ZSTD_decompressStream(ZSTD_DStream* d, ZSTD_outBuffer* out, ZSTD_inBuffer* in)
+{
+    if (!d || !out || !in) return ZB_ERR(ZB_error_GENERIC);
+    if (out->pos > out->size) return ZB_ERR(ZB_error_dstSize_tooSmall);
+    if (in->pos > in->size) return ZB_ERR(ZB_error_srcSize_wrong);
+    if (!d->dsIn) { d->dsIn = new (std::nothrow) std::vector<u8>(); d->dsOut = new (std::nothrow) std::vector<u8>(); if (!d->dsIn || !d->dsOut) return ZB_ERR(ZB_error_memory_allocation); }
+    auto handOut = [&]() -> size_t {
+        size_t const have = d->dsOut->size() - d->dsOutPos, room = out->size - out->pos, n = have < room ? have : room;
+        if (n) { memcpy((u8*)out->dst + out->pos, d->dsOut->data() + d->dsOutPos, n); out->pos += n; d->dsOutPos += n; }
+        if (d->dsOutPos == d->dsOut->size()) { d->dsOut->clear(); d->dsOutPos = 0; }
+        return d->dsOut->size() - d->dsOutPos;
+    };
+    if (handOut() != 0) return d->dsOut->size() - d->dsOutPos;           /* room first: input is only taken while nothing is waiting */
+    d->dsIn->insert(d->dsIn->end(), (const u8*)in->src + in->pos, (const u8*)in->src + in->size);
+    in->pos = in->size;
+    bool decoded = false;
+    while (!d->dsIn->empty()) {
+        size_t const fs = ZSTD_findFrameCompressedSize(d->dsIn->data(), d->dsIn->size());
+        if (ZSTD_isError(fs)) {
+            if (ZSTD_getErrorCode(fs) == ZB_error_srcSize_wrong) break;   /* the frame is not complete yet */
+            return fs;
+        }
+        size_t const bound = zbd_frameOutputBound(d->dsIn->data(), fs);
+        size_t const base = d->dsOut->size();
+        d->dsOut->resize(base + bound + 1);
+        size_t const r = ZSTD_decompressDCtx(d, d->dsOut->data() + base, bound, d->dsIn->data(), fs);
+        if (ZSTD_isError(r)) { d->dsOut->resize(base); return r; }
+        d->dsOut->resize(base + r);
+        d->dsIn->erase(d->dsIn->begin(), d->dsIn->begin() + (ptrdiff_t)fs);
+        decoded = true;
+    }
+    size_t const waiting = handOut();
+    if (waiting) return waiting;
+    (void)decoded;
+    if (d->dsIn->empty()) return 0;                                      /* at a frame border with everything handed out */
+    return ZB_BLOCK_MAX + 3;                                             /* in the middle of a frame: more input, please */
 }
