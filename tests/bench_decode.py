@@ -5,6 +5,31 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch, zref, zstd_b200
 
+if len(sys.argv) > 1 and sys.argv[1] == "--json":              # bench.py's round-trip leg: one workload, one JSON line
+    import json
+    size, p, level, dev = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    torch.cuda.set_device(dev)
+    src = zref.datagen(size, p, 0) if zref.have_datagen() else zref.synthetic(size, 0, p / 100.0)
+    c, d = zstd_b200.ZSTD_CCtx(device=dev), zstd_b200.ZSTD_DCtx(device=dev)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    cap = zstd_b200.ZSTD_compressBound(size)
+    d_c = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = c.compress_device(d_c.data_ptr(), cap, d_src.data_ptr(), size, level)
+    d_out = torch.empty(size, dtype=torch.uint8, device="cuda")
+    best, m = None, 0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m = d.decompress_device(d_out.data_ptr(), size, d_c.data_ptr(), n)
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        best = t if best is None else min(best, t)
+    st = d.stats()
+    print(json.dumps({"gpu_roundtrip_ok": bool(m == size and torch.equal(d_out, d_src)), "value": round(size / best / 1e6, 3),
+                      "unit": "GB/s (output bytes, device buffers, ZSTDB200_decompressDevice)", "ms": round(best, 3), "compressed_bytes": int(n),
+                      "kernel_ms": {"literals": round(st.literals_ms, 3), "sequences": round(st.sequences_ms, 3), "place": round(st.place_ms, 3), "matches": round(st.execute_ms, 3)}}))
+    sys.exit(0)
+
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 c, d = zstd_b200.ZSTD_CCtx(), zstd_b200.ZSTD_DCtx()
 for p, level in ((50, 1), (90, 3), (30, -3)):

@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee $P/r2z_gputes
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee $P/r2z_smoke.txt
 timeout 400 python bench.py > $P/r2z_bench.json 2> $P/r2z_bench.err; tail -c 3500 $P/r2z_bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 2 > $P/r2z_bench_reference.json 2>/dev/null; cut -c1-400 $P/r2z_bench_reference.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $P/r2z_launches_bench_steps2.csv python bench.py --steps 2 --warmup 1 --no-cpu > $P/b_ncu.log 2>&1; tail -2 $P/r2z_launches_bench_steps2.csv | cut -c1-300
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $P/r2z_launches_bench_steps2.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-decode > $P/b_ncu.log 2>&1; tail -2 $P/r2z_launches_bench_steps2.csv | cut -c1-300
 ZSTDB200_SERIAL=1 timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:zb_ --csv --log-file $P/r2z_traffic_ncu.csv python tests/profile_one.py 1024 50 1 1 > $P/t_ncu.log 2>&1
 python tools/ncu_traffic.py $P/r2z_traffic_ncu.csv | tee $P/r2z_traffic.txt
 ZSTDB200_SERIAL=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"zb_walk|zb_parse" -c 2 -o $P/r2z_match_256 -f python tests/profile_one.py 256 50 1 1 > $P/n1.log 2>&1

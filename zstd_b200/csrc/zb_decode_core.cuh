@@ -451,6 +451,26 @@ ZBD_HDN u32 zbd_hufDecodeStream(u8* out, u32 count, const u8* p, u32 size, const
         u32 const e = table[zbd_back_peek(&bs, log)];
         out[i++] = (u8)e; bs.pos -= (int)(e >> 8);
     }
+    /* fast path: while at least 64 unread bits remain, one 8-byte load serves four symbols (4 x 11 bits <= the 57 bits a
+     * byte-aligned window is sure to hold below `pos`) — no underflow or refill tests inside */
+    u32 const mask = (1u << log) - 1u;
+    while (i + 4u <= count && bs.pos >= 64) {
+        int const wl = (bs.pos - 57) & ~7;
+        u64 const win = zbd_load64(p, (u32)wl >> 3, size);
+        u32 have = (u32)(bs.pos - wl);                            /* 57 .. 64 window bits lie below pos */
+        u32 w = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (u32 k = 0; k < 4u; k++) {
+            u32 const e = table[(u32)(win >> (have - log)) & mask];
+            w |= (e & 0xFFu) << (8u * k); have -= e >> 8;
+        }
+        *(u32*)(out + i) = w;
+        bs.pos = wl + (int)have;
+        i += 4u;
+    }
+    bs.winLo = 0x40000000;                                        /* the generic reader below starts with a fresh window */
     for (; i + 4u <= count; i += 4u) {
         u32 w = 0;
         for (u32 k = 0; k < 4u; k++) {
