@@ -11,7 +11,7 @@ import zref
 import zstd_b200
 from test_gpu_parity import CASES
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]      # a stuck kernel must fail the run, not hang it
 needs_ref = pytest.mark.skipif(not zref.have_ref(), reason="reference library not built")
 
 

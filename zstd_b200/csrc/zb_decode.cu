@@ -399,7 +399,7 @@ __device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n
 #define ZBD_MATCH_THREADS 256
 __global__ void __launch_bounds__(ZBD_MATCH_THREADS)
 zbd_matches_kernel(const u64* __restrict__ seqs, const u64* __restrict__ matchPos, const u32* __restrict__ tileFirst, u32 nbMatches, u64 totalOut,
-                   u8* __restrict__ dst, u8* done, u32* ticket)
+                   u8* __restrict__ dst, u8* done, u32* ticket, u32* __restrict__ execErr)
 {
     u32 const lane = threadIdx.x & 31u;
     while (true) {
@@ -427,7 +427,11 @@ zbd_matches_kernel(const u64* __restrict__ seqs, const u64* __restrict__ matchPo
         }
         /* rounds: every waiting lane polls once (together, not each on its own: a lane spinning alone would starve the
          * lanes of its warp that are ready); the lanes whose writers are all done copy side by side */
+        long long const t0 = clock64();
         while (__any_sync(ZB_FULL, pending)) {
+            /* a writer is always a match with a lower number that has been handed out, so every wait ends; should that ever
+             * be wrong the call fails (GENERIC) after ~30 s instead of hanging the device */
+            if (pending && clock64() - t0 > 60000000000ll) { atomicMax(execErr, (u32)ZB_error_GENERIC); zbd_st_flag(done + g); pending = false; continue; }
             bool ready = false;
             if (pending) {
                 while (deps && zbd_ld_flag(done + j) != 0u) { j++; if (j > jhi) deps = false; }
@@ -558,7 +562,7 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     if (seqCount) {
         u64 const groups = (seqCount + 31u) / 32u, warpsPerCta = ZBD_MATCH_THREADS / 32u;
         u64 const want = (groups + warpsPerCta - 1u) / warpsPerCta, cap = (u64)d->smCount * 8u;       /* resident CTAs take tickets until the matches run out */
-        zbd_matches_kernel<<<(u32)(want < cap ? want : cap), ZBD_MATCH_THREADS, 0, st>>>(d->d_seqs, d->d_matchPos, d->d_tileFirst, (u32)seqCount, (u64)total, d_dst, d->d_done, d->d_ticket);
+        zbd_matches_kernel<<<(u32)(want < cap ? want : cap), ZBD_MATCH_THREADS, 0, st>>>(d->d_seqs, d->d_matchPos, d->d_tileFirst, (u32)seqCount, (u64)total, d_dst, d->d_done, d->d_ticket, d->d_execErr);
     }
     DCK(cudaEventRecord(d->ev[5], st));
     DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));
