@@ -16,7 +16,8 @@
 
 struct BlockOut { std::vector<u8> lits; std::vector<u64> seqs; u32 sumLL, sumML; ZbdRep transfer; };
 /* dependency statistics of the last call (development: how parallel is the match stage of a frame?) */
-extern "C" { unsigned long long zbh_nbMatches, zbh_maxDepth, zbh_nearDeps, zbh_anyDeps; }
+extern "C" { unsigned long long zbh_nbMatches, zbh_maxDepth, zbh_nearDeps, zbh_anyDeps, zbh_tileDepth; }
+static std::vector<unsigned> g_tDepth;
 
 static std::vector<unsigned long long> g_mStart, g_mEnd; static std::vector<unsigned> g_mDepth;
 static const u8* g_dict = NULL;            /* the call's dictionary (single-threaded test code) */
@@ -140,7 +141,7 @@ extern "C" size_t zbh_decompress_usingDict(void* dstv, size_t cap, const void* s
     e = zbd_walk(in, size, B.data(), nb, F.data(), nf, &nb, &nf, &litBytes, &seqCount, g_di.entropy != 0, g_di.dictID);
     if (e) return ERR(e);
     size_t out = 0;
-    zbh_nbMatches = zbh_maxDepth = zbh_nearDeps = zbh_anyDeps = 0; g_mStart.clear(); g_mEnd.clear(); g_mDepth.clear();
+    zbh_nbMatches = zbh_maxDepth = zbh_nearDeps = zbh_anyDeps = zbh_tileDepth = 0; g_mStart.clear(); g_mEnd.clear(); g_mDepth.clear(); g_tDepth.clear();
     for (u32 f = 0; f < nf; f++) {
         size_t const frameStart = out;
         ZbdRep rep; rep.r[0] = 1; rep.r[1] = 4; rep.r[2] = 8;
@@ -172,6 +173,15 @@ extern "C" size_t zbh_decompress_usingDict(void* dstv, size_t cap, const void* s
                     while (lo < hi) { size_t const mid = (lo + hi) / 2; if (g_mEnd[mid] <= ss) lo = mid + 1; else hi = mid; }
                     unsigned depth = 0; bool any = false, near = false;
                     for (size_t j = lo; j < g_mStart.size() && g_mStart[j] < se; j++) { any = true; if (g_mDepth[j] > depth) depth = g_mDepth[j]; if (g_mStart.size() - j <= 32) near = true; }
+                    {   /* the kernel's conservative rule: every match from "first one ending behind the tile of ss" to "first one ending behind the first tile at or past se" */
+                        size_t a = 0, bnd = g_mStart.size(), c = 0, dnd = g_mStart.size();
+                        unsigned long long const t0 = (ss >> 6) << 6, t1 = ((se + 63) >> 6) << 6;
+                        while (a < bnd) { size_t const mid = (a + bnd) / 2; if (g_mEnd[mid] <= t0) a = mid + 1; else bnd = mid; }
+                        while (c < dnd) { size_t const mid = (c + dnd) / 2; if (g_mEnd[mid] <= t1) c = mid + 1; else dnd = mid; }
+                        unsigned dt = 0;
+                        for (size_t j = a; j <= c && j < g_mStart.size(); j++) if (g_tDepth[j] > dt) dt = g_tDepth[j];
+                        g_tDepth.push_back(dt + 1); if (dt + 1 > zbh_tileDepth) zbh_tileDepth = dt + 1;
+                    }
                     g_mStart.push_back(out); g_mEnd.push_back(out + ml); g_mDepth.push_back(depth + 1);
                     zbh_nbMatches++; if (any) zbh_anyDeps++; if (near) zbh_nearDeps++; if (depth + 1 > zbh_maxDepth) zbh_maxDepth = depth + 1;
                 }

@@ -15,6 +15,7 @@
 #include <vector>
 #include <mutex>
 #include <thread>
+#include <new>
 #include <time.h>
 #include "../../include/zstd_b200.h"
 #include "zb_common.h"
@@ -127,6 +128,8 @@ struct ZSTD_CDict_s {
     u32 nbImages; ZbParams imagePrm[ZB_MAX_IMAGES];
 };
 
+struct ZbPlan;
+static void zb_freePlan(struct ZbPlan* p);       /* defined behind ZbPlan */
 struct ZSTD_CCtx_s {
     int device;                    /* -1 until the first call created the stream and events on bindDevice */
     int bindDevice;                /* device captured by ZSTD_createCCtx */
@@ -164,6 +167,7 @@ struct ZSTD_CCtx_s {
     /* per-call frame options, consumed by the planner */
     u32 callChecksum, callNoDictID;
     u64 callPartBegin, callPartEnd;   /* ZSTDB200_compressFramePart: this call's share of the frame (0, 0 = all of it) */
+    struct ZbPlan* plan;           /* the call's plan; its vectors are reused (a million records are 100 MB of descriptors: fresh pages cost more than filling them) */
     /* streaming front end (ZSTD_compressStream2 with ZSTD_e_continue / ZSTD_e_flush): input collected on the host, compressed
      * output waiting to be handed out */
     u8* stIn; size_t stInSize, stInCap;
@@ -257,6 +261,7 @@ extern "C" size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     ZbDeviceGuard guard;
     ZSTD_freeCDict(c->advLocalDict);
     free(c->stIn); free(c->stOut);
+    zb_freePlan(c->plan);
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         zb_freeWorkspace(c);
@@ -333,8 +338,10 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides&
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
 struct ZbGroup { ZbParams prm; u32 b0, b1, c0, c1; const u32* image; };   /* image: tables walked over the dictionary tail, or NULL */
-struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbChunk> chunks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported; };
+struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbChunk> chunks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported;
+                void reset() { blocks.clear(); chunks.clear(); frames.clear(); groups.clear(); unsupported = false; } };   /* keeps its memory: a context plans call after call */
 
+static void zb_freePlan(ZbPlan* p) { delete p; }
 static int g_strictLevels = 0;
 /* Levels whose reference strategy is greedy or stronger (>= 5; 4 for frames <= 256 KiB / <= 16 KiB) have no counterpart here:
  * by default they are served by the strongest doubleFast row of their size class (larger output than the reference's at
@@ -547,7 +554,8 @@ static size_t zb_compressFramesDevice(ZSTD_CCtx* c, u8* d_dst, size_t dstCapacit
 {
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, stream, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
-    ZbPlan P;
+    if (!c->plan) { c->plan = new (std::nothrow) ZbPlan(); if (!c->plan) return ZB_ERR(ZB_error_memory_allocation); }
+    ZbPlan& P = *c->plan; P.reset();
     zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL,
             c->callPartBegin, c->callPartEnd ? c->callPartEnd : ~0ull);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);
@@ -649,7 +657,8 @@ static size_t zb_compressFramesWaves(ZSTD_CCtx* c, u8* dst, size_t dstCapacity, 
     {   size_t const e = getStream(ZB_WAVE_SLOTS_MAX, &sCopy); if (zb_isErr(e)) return e; }
     size_t effDict = 0, dictTail = 0; u32 dictID = 0; const u8* d_dictEnd = NULL;
     {   size_t const e = zb_prepareDict(c, dict, dictSize, cdict, sCopy, &effDict, &dictTail, &dictID, &d_dictEnd); if (zb_isErr(e)) return e; }
-    ZbPlan P;
+    if (!c->plan) { c->plan = new (std::nothrow) ZbPlan(); if (!c->plan) return ZB_ERR(ZB_error_memory_allocation); }
+    ZbPlan& P = *c->plan; P.reset();
     zb_plan(P, c->callChecksum, frameOffsets, frameSizes, nbFrames, level, effDict, dictTail, c->callNoDictID ? 0u : dictID, c->dictEntropy.present ? c->dictEntropy.rep : NULL,
             c->callPartBegin, c->callPartEnd ? c->callPartEnd : ~0ull);
     if (P.unsupported) return ZB_ERR(ZB_error_parameter_unsupported);

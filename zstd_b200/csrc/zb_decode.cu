@@ -24,9 +24,10 @@
  *                 every match becomes (destination, offset, length) with its repcode resolved.  Nothing of the output is
  *                 read, so no block waits for another.
  *   D5  matches   LZ77 copies read earlier output, which chains the matches of a frame — but a match depends only on the
- *                 few matches that wrote its source bytes.  One lane per match, handed out in order over a ticket counter;
- *                 a lane finds the writers of its source range through a tile index D4 left behind, waits for their
- *                 completion flags, copies, raises its own.  Independent matches run across the whole GPU.
+ *                 few matches that wrote its source bytes.  One CTA per frame, one LANE per match, matches handed out in
+ *                 order; a lane finds the writers of its source range through a tile index D4 left behind, waits for their
+ *                 completion flags (block-scope fences: writer and reader share an SM), copies, raises its own.  What stays
+ *                 serial is the longest chain of matches copying from one another; frames run side by side.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -366,79 +367,92 @@ __device__ __forceinline__ u32 zbd_ld_flag(const u8* p) { u32 v; asm volatile("l
 __device__ __forceinline__ void zbd_st_flag(u8* p) { asm volatile("st.volatile.global.u8 [%0], %1;" :: "l"(p), "r"(1u) : "memory"); }
 __device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord) { return __ldcg(reinterpret_cast<const u32*>(alignedWord)); }
 
-/* n bytes from `from` to `out`, the two ranges not overlapping; sources are read through L2 (they may have been written by
- * another SM a moment ago), four words in flight at a time; a source word is only loaded when it holds a needed byte */
+/* n bytes from `from` to `out`, the two ranges not overlapping.  Sources are read through L2 (another warp wrote them a
+ * moment ago); what limits a copy is the number of DEPENDENT round trips, so loads go out in groups: the head bytes that
+ * align the destination, then 32 bytes (nine aligned words) at a time, then the tail.  A source word is only loaded when it
+ * holds a needed byte. */
 __device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n)
 {
-    u32 k = 0;
-    while (k < n && (((uintptr_t)(out + k)) & 3u)) { out[k] = __ldcg(from + k); k++; }
-    if (k + 4u <= n) {
+    u32 head = (4u - ((u32)(uintptr_t)out & 3u)) & 3u; head = head < n ? head : n;
+    {   u32 const b0 = head > 0u ? __ldcg(from) : 0u, b1 = head > 1u ? __ldcg(from + 1) : 0u, b2 = head > 2u ? __ldcg(from + 2) : 0u;
+        if (head > 0u) out[0] = (u8)b0; if (head > 1u) out[1] = (u8)b1; if (head > 2u) out[2] = (u8)b2; }
+    u32 k = head;
+    while (k + 4u <= n) {                                         /* destination word-aligned from here */
+        u32 const words = (n - k) / 4u < 8u ? (n - k) / 4u : 8u;  /* this round: up to 8 words */
         const u8* const a = from + k;
-        const u8* aw = (const u8*)((uintptr_t)a & ~(uintptr_t)3);
+        const u8* const aw = (const u8*)((uintptr_t)a & ~(uintptr_t)3);
         u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-        if (sh == 0u) {
-            for (; k + 16u <= n; k += 16u, aw += 16) {
-                u32 const w0 = zbd_ldcg32(aw), w1 = zbd_ldcg32(aw + 4), w2 = zbd_ldcg32(aw + 8), w3 = zbd_ldcg32(aw + 12);
-                u32* const o = reinterpret_cast<u32*>(out + k); o[0] = w0; o[1] = w1; o[2] = w2; o[3] = w3;
-            }
-            for (; k + 4u <= n; k += 4u, aw += 4) *reinterpret_cast<u32*>(out + k) = zbd_ldcg32(aw);
-        } else {
-            u32 w0 = zbd_ldcg32(aw);
-            for (; k + 16u <= n; k += 16u, aw += 16) {
-                u32 const w1 = zbd_ldcg32(aw + 4), w2 = zbd_ldcg32(aw + 8), w3 = zbd_ldcg32(aw + 12), w4 = zbd_ldcg32(aw + 16);
-                u32* const o = reinterpret_cast<u32*>(out + k);
-                o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
-                w0 = w4;
-            }
-            for (; k + 4u <= n; k += 4u) { aw += 4; u32 const w1 = zbd_ldcg32(aw); *reinterpret_cast<u32*>(out + k) = __funnelshift_r(w0, w1, sh); w0 = w1; }
-        }
+        u32 w[9];
+#pragma unroll
+        for (u32 i = 0; i < 9u; i++) w[i] = (i < words || (i == words && sh)) ? zbd_ldcg32(aw + 4u * i) : 0u;
+        u32* const o = reinterpret_cast<u32*>(out + k);
+#pragma unroll
+        for (u32 i = 0; i < 8u; i++) if (i < words) o[i] = sh ? __funnelshift_r(w[i], w[i + 1], sh) : w[i];
+        k += 4u * words;
     }
-    for (; k < n; k++) out[k] = __ldcg(from + k);
+    {   u32 const t = n - k;                                       /* 0..3 tail bytes */
+        u32 const b0 = t > 0u ? __ldcg(from + k) : 0u, b1 = t > 1u ? __ldcg(from + k + 1) : 0u, b2 = t > 2u ? __ldcg(from + k + 2) : 0u;
+        if (t > 0u) out[k] = (u8)b0; if (t > 1u) out[k + 1] = (u8)b1; if (t > 2u) out[k + 2] = (u8)b2; }
 }
 
-#define ZBD_MATCH_THREADS 256
-__global__ void __launch_bounds__(ZBD_MATCH_THREADS)
-zbd_matches_kernel(const u64* __restrict__ seqs, const u64* __restrict__ matchPos, const u32* __restrict__ tileFirst, u32 nbMatches, u64 totalOut,
-                   u8* __restrict__ dst, u8* done, u32* ticket, u32* __restrict__ execErr)
+/* One CTA per frame: the matches of a frame form a wavefront that moves through the output (a match's source lies a
+ * typical offset behind it), so what decides the time of a frame is the longest chain of matches copying from one another
+ * times the latency of one hand-over.  Inside one CTA a hand-over is a block-scope fence and a flag — the writer and the
+ * reader share an SM — instead of a device-scope fence and a trip through L2 for every link.  Frames run side by side. */
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+zbd_matches_kernel(const ZbdBlock* __restrict__ blocks, const ZbdFrame* __restrict__ frames, const u64* __restrict__ seqs, const u64* __restrict__ matchPos,
+                   const u32* __restrict__ tileFirst, u64 totalOut, u8* __restrict__ dst, u8* done, u32* __restrict__ execErr)
 {
+    __shared__ u32 sTicket;
     u32 const lane = threadIdx.x & 31u;
+    ZbdFrame const fr = frames[blockIdx.x];
+    if (fr.nbBlocks == 0) return;
+    ZbdBlock const bl = blocks[fr.firstBlock + fr.nbBlocks - 1u];
+    u32 const g0 = (u32)blocks[fr.firstBlock].seqPos, g1 = (u32)bl.seqPos + (bl.type == ZB_BT_COMPRESSED ? bl.nbSeq : 0u);     /* the frame's matches */
+    if (threadIdx.x == 0) sTicket = 0;
+    __syncthreads();
     while (true) {
         u32 grp = 0;
-        if (lane == 0) grp = atomicAdd(ticket, 1u);
+        if (lane == 0) grp = atomicAdd(&sTicket, 1u);                /* matches are handed out in order: a lane only ever waits for matches that were handed out */
         grp = __shfl_sync(ZB_FULL, grp, 0);
-        if ((u64)grp * 32u >= nbMatches) return;
-        u32 const g = grp * 32u + lane;
+        if ((u64)g0 + (u64)grp * 32u >= g1) return;
+        u32 const g = g0 + grp * 32u + lane;
         u64 q = 0, pos = 0;
-        if (g < nbMatches) { q = seqs[g]; pos = matchPos[g]; }
+        if (g < g1) { q = seqs[g]; pos = matchPos[g]; }
         u32 const off = (u32)q & 0x0FFFFFFFu, ml = (u32)(q >> 28);
-        bool pending = g < nbMatches && ml != 0u && off != 0u && (u64)off <= pos && pos + ml <= totalOut;
-        if (g < nbMatches && !pending) zbd_st_flag(done + g);        /* nothing to copy (an empty or a refused match): nobody may wait for it */
+        bool pending = g < g1 && ml != 0u && off != 0u && (u64)off <= pos && pos + ml <= totalOut;
+        if (g < g1 && !pending) zbd_st_flag(done + g);               /* nothing to copy (an empty or a refused match): nobody may wait for it */
         u64 const s = pos - off;
         u32 const span = ml < off ? ml : off;
-        /* matches that may have written [s, s + span): from the first one ending behind the tile of s to the first one
-         * ending behind the first tile at or past the range's end (it may begin inside the range), never past g - 1 */
+        /* candidates for "wrote into [s, s + span)": from the first match ending behind the tile of s to the first one
+         * ending behind the first tile at or past the range's end, never past g - 1; each is then tested for real overlap */
         u32 j = 0, jhi = 0;
         bool deps = false;
-        if (pending && g != 0u) {
+        if (pending && g != g0) {
             j = tileFirst[s >> ZBD_TILE_LOG];
             jhi = tileFirst[(s + span + ((1u << ZBD_TILE_LOG) - 1u)) >> ZBD_TILE_LOG];
             if (jhi >= g) jhi = g - 1u;
+            if (j < g0) j = g0;                                      /* matches of earlier frames never write into this one */
             deps = j < g && j <= jhi;
         }
-        /* rounds: every waiting lane polls once (together, not each on its own: a lane spinning alone would starve the
-         * lanes of its warp that are ready); the lanes whose writers are all done copy side by side */
         long long const t0 = clock64();
         while (__any_sync(ZB_FULL, pending)) {
-            /* a writer is always a match with a lower number that has been handed out, so every wait ends; should that ever
-             * be wrong the call fails (GENERIC) after ~30 s instead of hanging the device */
+            /* every wait ends (see above); should that ever be wrong the call fails after ~30 s instead of hanging the device */
             if (pending && clock64() - t0 > 60000000000ll) { atomicMax(execErr, (u32)ZB_error_GENERIC); zbd_st_flag(done + g); pending = false; continue; }
             bool ready = false;
             if (pending) {
-                while (deps && zbd_ld_flag(done + j) != 0u) { j++; if (j > jhi) deps = false; }
+                while (deps) {
+                    if (zbd_ld_flag(done + j) == 0u) {               /* unfinished: does it touch the source at all? */
+                        u64 const pj = matchPos[j]; u32 const mj = (u32)(seqs[j] >> 28);
+                        if (pj < s + span && pj + mj > s) break;     /* yes: wait for it */
+                    }
+                    j++; if (j > jhi) deps = false;
+                }
                 ready = !deps;
             }
             if (ready) {
-                __threadfence();
+                __threadfence_block();
                 u8* const out = dst + pos;
                 const u8* const from = dst + s;
                 if (off >= ml) zbd_copy_disjoint(out, from, ml);
@@ -450,10 +464,10 @@ zbd_matches_kernel(const u64* __restrict__ seqs, const u64* __restrict__ matchPo
                 } else {                                             /* the `off` bytes in front of the match, again and again: every piece a disjoint copy */
                     for (u32 k = 0; k < ml; k += off) zbd_copy_disjoint(out + k, from, ml - k < off ? ml - k : off);
                 }
-                __threadfence();
+                __threadfence_block();
                 zbd_st_flag(done + g);
                 pending = false;
-            } else if (pending) __nanosleep(32);
+            }
         }
     }
 }
@@ -555,14 +569,14 @@ static size_t zbd_run(ZSTD_DCtx* d, u8* d_dst, size_t dstCapacity, const u8* d_s
     {   size_t const r = zbd_grow(&d->d_done, &d->capDone, (size_t)seqCount + 4); if (zbd_isErr(r)) return r; }
     DCK(cudaMemsetAsync(d->d_tileFirst, 0xFF, ((total >> ZBD_TILE_LOG) + 4) * sizeof(u32), st));
     DCK(cudaMemsetAsync(d->d_done, 0, (size_t)seqCount + 4, st));
-    DCK(cudaMemsetAsync(d->d_ticket, 0, sizeof(u32), st));
     zbd_place_kernel<<<grid, 32 * ZBD_WARPS, 0, st>>>(d_src, d->d_blocks, nb, d->d_lits, d->d_seqs, d->d_matchPos, d->d_tileFirst, d->d_bout, d_dst,
                                                       d_dictContent, dictContent, d->d_execErr);
     DCK(cudaEventRecord(d->ev[6], st));
-    if (seqCount) {
-        u64 const groups = (seqCount + 31u) / 32u, warpsPerCta = ZBD_MATCH_THREADS / 32u;
-        u64 const want = (groups + warpsPerCta - 1u) / warpsPerCta, cap = (u64)d->smCount * 8u;       /* resident CTAs take tickets until the matches run out */
-        zbd_matches_kernel<<<(u32)(want < cap ? want : cap), ZBD_MATCH_THREADS, 0, st>>>(d->d_seqs, d->d_matchPos, d->d_tileFirst, (u32)seqCount, (u64)total, d_dst, d->d_done, d->d_ticket, d->d_execErr);
+    if (seqCount) {                                                  /* threads per frame by the matches a frame holds */
+        u64 const perFrame = seqCount / (nf ? nf : 1u);
+        if (perFrame >= 8192u)     zbd_matches_kernel<1024><<<nf, 1024, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_tileFirst, (u64)total, d_dst, d->d_done, d->d_execErr);
+        else if (perFrame >= 256u) zbd_matches_kernel<128><<<nf, 128, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_tileFirst, (u64)total, d_dst, d->d_done, d->d_execErr);
+        else                       zbd_matches_kernel<32><<<nf, 32, 0, st>>>(d->d_blocks, d->d_frames, d->d_seqs, d->d_matchPos, d->d_tileFirst, (u64)total, d_dst, d->d_done, d->d_execErr);
     }
     DCK(cudaEventRecord(d->ev[5], st));
     DCK(cudaMemcpyAsync(d->h_res + 2, d->d_execErr, sizeof(u32), cudaMemcpyDeviceToHost, st));

@@ -238,21 +238,19 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
     constexpr int NWR = ZB_WALK_NWR(P);
     u32 const xIntHi = xEnd >= (ZB_BATCH + 4u * NW) ? (xEnd + P - 4u * NW) & ~(ZB_BATCH - 1u) : 0u;     /* batches [x0, x0 + B) with x0 + B <= xIntHi are interior */
 
-    /* the P + 7 bytes of a thread's positions as words realigned to its first position */
-    auto fetch = [&](u32 xb, u32 (&w)[NWR]) {
+    /* the aligned words that hold the P + 7 bytes of a thread's positions, and the shift that realigns them: the words are
+     * only touched (realigned) by the batch that uses them, two batches after the loads went out */
+    auto fetch = [&](u32 xb, u32 (&a)[NW], u32& sh) {
         u32 const xa = xb + P * t;                                /* first coordinate of the thread */
 #pragma unroll
-        for (int k = 0; k < NWR; k++) w[k] = 0u;
-        u32 a[NW + 1];
+        for (u32 k = 0; k < NW; k++) a[k] = 0u;
+        sh = 0u;
         if (xb >= xIntLoB && xb + ZB_BATCH <= xIntHi) {           /* interior: no guards */
             const u8* const ad = fbase + (xa - shift);
             const u32* const p = reinterpret_cast<const u32*>((uintptr_t)ad & ~(uintptr_t)3);
-            u32 const sh = ((u32)(uintptr_t)ad & 3u) * 8u;
+            sh = ((u32)(uintptr_t)ad & 3u) * 8u;
 #pragma unroll
             for (u32 k = 0; k < NW; k++) a[k] = __ldg(p + k);
-            a[NW] = 0u;
-#pragma unroll
-            for (int k = 0; k < NWR; k++) w[k] = __funnelshift_r(a[k], a[k + 1], sh);
             return;
         }
         if (xa + P <= xLow || xa >= xEnd) return;                 /* nothing of mine is walked */
@@ -261,29 +259,29 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
         if (slow) return;                                         /* assembled byte-wise in the batch */
         const u8* const ad = (rel < D ? dbase : fbase) + rel;
         const u32* const p = reinterpret_cast<const u32*>((uintptr_t)ad & ~(uintptr_t)3);
-        u32 const al = (u32)(uintptr_t)ad & 3u, sh = al * 8u;
+        u32 const al = (u32)(uintptr_t)ad & 3u;
+        sh = al * 8u;
         /* rel + P + 7 <= limit: a word is only touched when it holds one of the thread's P + 7 bytes */
 #pragma unroll
         for (u32 k = 0; k < NW; k++) a[k] = (al + P + 7u > 4u * k) ? __ldg(p + k) : 0u;
-        a[NW] = 0u;
-#pragma unroll
-        for (int k = 0; k < NWR; k++) w[k] = __funnelshift_r(a[k], a[k + 1], sh);
     };
-    u32 wA[NWR], wB[NWR];                                         /* bytes of the next batch and of the one after it */
-    fetch(x0, wA);
-    fetch(x0 + ZB_BATCH, wB);
+    u32 rawA[NW], rawB[NW], shA, shB;                             /* bytes of the next batch and of the one after it */
+    fetch(x0, rawA, shA);
+    fetch(x0 + ZB_BATCH, rawB, shB);
     u32 const blockMask = (1u << cd.blockLog) - 1u;
     /* insertion pattern: the residue of the thread's first position modulo insStep follows the walk by addition; only a
      * batch whose step was raised by the acceleration pays for a division */
     u32 const stepInc = ZB_BATCH % insStep;
     u32 r0 = (x0 + P * t + insStep * ZB_BATCH - shift) % insStep;
     u32 li = shift;                                               /* coordinate the acceleration counts from: the walk's start, then the end of the last batch with a hit */
-    for (; x0 < xEnd; x0 += ZB_BATCH) {
+    /* one batch: its words are realigned, the register set is refilled at once for the batch two ahead (no copies between
+     * the sets: the loop below alternates them), then the three phases run */
+    auto doBatch = [&](u32 (&raw)[NW], u32& sh) {
         u32 const xa = x0 + P * t;
         u32 cur[NWR];
 #pragma unroll
-        for (int k = 0; k < NWR; k++) { cur[k] = wA[k]; wA[k] = wB[k]; }
-        fetch(x0 + 2u * ZB_BATCH, wB);                            /* in flight across two batches' barriers */
+        for (int k = 0; k < NWR; k++) cur[k] = __funnelshift_r(raw[k], (u32)k + 1u < NW ? raw[(u32)k + 1u < NW ? k + 1 : k] : 0u, sh);
+        fetch(x0 + 2u * ZB_BATCH, raw, sh);                       /* in flight across two batches' barriers */
         if (D != 0u && x0 >= D + shift && li < D + shift) li = D + shift;   /* the frame starts with a fresh acceleration state behind a dictionary */
         u32 const sWalk = x0 > xLow ? x0 : xLow;                  /* first walked coordinate of the batch */
         u32 const step = insStep + ((sWalk - li) >> 7);
@@ -299,6 +297,12 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
             hit = zb_walk_batch<MLS, P, false>(table, xa, cur, pat, N, shift, D, total, xLow, xEnd, fbase, dbase, output, dist + idx, far + idx);
         if (hit) li = x0 + ZB_BATCH;
         r0 += stepInc; if (r0 >= insStep) r0 -= insStep;
+        x0 += ZB_BATCH;
+    };
+    while (x0 < xEnd) {
+        doBatch(rawA, shA);
+        if (x0 >= xEnd) break;
+        doBatch(rawB, shB);
     }
     if (buildImage) { __syncthreads(); for (u32 i = t; i < N; i += THREADS) imageOut[i] = table[i]; }
 }
