@@ -120,9 +120,10 @@ def datagen(size: int, p: int = 50, seed: int = 0) -> bytes:
     if not (os.path.exists(path) and os.path.getsize(path) == size):
         if not os.path.exists(DATAGEN):
             raise FileNotFoundError(DATAGEN)
-        with open(path + ".tmp", "wb") as f:
+        tmp = f"{path}.{os.getpid()}.tmp"                         # several ranks may want the same file at the same time
+        with open(tmp, "wb") as f:
             subprocess.check_call([DATAGEN, f"-g{size}", f"-P{p}", f"-s{seed}"], stdout=f)
-        os.replace(path + ".tmp", path)
+        os.replace(tmp, path)
     with open(path, "rb") as f:
         return f.read()
 

@@ -338,7 +338,35 @@ static size_t zb_ensureHeavy(ZSTD_CCtx* c, size_t nbSlotBlocks, const ZbStrides&
  * its repcodes start the block.  Parsing: zb_dict.cu. */
 /* ------------------------------------------------------------------ planning (ZSTD_compress_frameChunk, zstd_compress.c:4527) */
 struct ZbGroup { ZbParams prm; u32 b0, b1, c0, c1; const u32* image; };   /* image: tables walked over the dictionary tail, or NULL */
-struct ZbPlan { std::vector<ZbBlock> blocks; std::vector<ZbChunk> chunks; std::vector<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported;
+/* Descriptor arrays of a plan: page-locked (so that the upload of a million frames' descriptors is a DMA at PCIe speed, not a
+ * staged copy of pageable memory) and kept across calls.  Without a CUDA device (the CPU tests' ZSTDB200_describePlan)
+ * ordinary memory is used. */
+template <typename T> struct ZbVec {
+    T* p; size_t n, cap; bool pinned;
+    ZbVec() : p(NULL), n(0), cap(0), pinned(false) {}
+    ~ZbVec() { release(); }
+    ZbVec(const ZbVec&) = delete; ZbVec& operator=(const ZbVec&) = delete;
+    void release() { if (p) { if (pinned) cudaFreeHost(p); else free(p); } p = NULL; n = cap = 0; }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t const c = want < 2 * cap ? 2 * cap : want;
+        T* q = NULL; bool pin = true;
+        if (cudaMallocHost((void**)&q, c * sizeof(T)) != cudaSuccess) { cudaGetLastError(); pin = false; q = (T*)malloc(c * sizeof(T)); }
+        if (n) memcpy(q, p, n * sizeof(T));
+        size_t const keep = n;
+        release(); p = q; n = keep; cap = c; pinned = pin;
+    }
+    void push_back(const T& v) { if (n == cap) reserve(cap ? 2 * cap : 64); p[n++] = v; }
+    void resize(size_t m) { reserve(m); if (m > n) memset((void*)(p + n), 0, (m - n) * sizeof(T)); n = m; }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& back() { return p[n - 1]; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+struct ZbPlan { ZbVec<ZbBlock> blocks; ZbVec<ZbChunk> chunks; ZbVec<ZbFrame> frames; std::vector<ZbGroup> groups; ZbStrides sd; bool unsupported;
                 void reset() { blocks.clear(); chunks.clear(); frames.clear(); groups.clear(); unsupported = false; } };   /* keeps its memory: a context plans call after call */
 
 static void zb_freePlan(ZbPlan* p) { delete p; }
