@@ -368,47 +368,31 @@ __device__ __forceinline__ void zbd_st_flag(u8* p) { asm volatile("st.volatile.g
 __device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord) { return __ldcg(reinterpret_cast<const u32*>(alignedWord)); }
 
 /* n bytes from `from` to `out`, the two ranges not overlapping.  Sources are read through L2 (another warp wrote them a
- * moment ago); what a hand-over costs is the number of DEPENDENT round trips, so every load of a short copy goes out before
- * its first store: the head bytes that align the destination, up to eight words (nine aligned source words), the tail
- * bytes — one round trip for up to 38 bytes, one more per further 32.  A source word is only loaded when it holds a needed
- * byte. */
+ * moment ago); what limits a copy is the number of DEPENDENT round trips, so loads go out in groups: the head bytes that
+ * align the destination, then 32 bytes (nine aligned words) at a time, then the tail.  A source word is only loaded when it
+ * holds a needed byte. */
 __device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n)
 {
     u32 head = (4u - ((u32)(uintptr_t)out & 3u)) & 3u; head = head < n ? head : n;
-    u32 const words = (n - head) / 4u;
-    u32 const first = words < 8u ? words : 8u;                     /* words of the first round */
-    u32 const tailAt = head + 4u * words, tail = n - tailAt;       /* 0..3 tail bytes */
-    /* ---- loads of the first round ---- */
-    u32 const h0 = head > 0u ? __ldcg(from) : 0u, h1 = head > 1u ? __ldcg(from + 1) : 0u, h2 = head > 2u ? __ldcg(from + 2) : 0u;
-    const u8* const a = from + head;
-    const u8* const aw = (const u8*)((uintptr_t)a & ~(uintptr_t)3);
-    u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
-    u32 w[9];
+    {   u32 const b0 = head > 0u ? __ldcg(from) : 0u, b1 = head > 1u ? __ldcg(from + 1) : 0u, b2 = head > 2u ? __ldcg(from + 2) : 0u;
+        if (head > 0u) out[0] = (u8)b0; if (head > 1u) out[1] = (u8)b1; if (head > 2u) out[2] = (u8)b2; }
+    u32 k = head;
+    while (k + 4u <= n) {                                         /* destination word-aligned from here */
+        u32 const words = (n - k) / 4u < 8u ? (n - k) / 4u : 8u;  /* this round: up to 8 words */
+        const u8* const a = from + k;
+        const u8* const aw = (const u8*)((uintptr_t)a & ~(uintptr_t)3);
+        u32 const sh = ((u32)(uintptr_t)a & 3u) * 8u;
+        u32 w[9];
 #pragma unroll
-    for (u32 i = 0; i < 9u; i++) w[i] = (i < first || (i == first && sh && first)) ? zbd_ldcg32(aw + 4u * i) : 0u;
-    u32 const t0 = tail > 0u ? __ldcg(from + tailAt) : 0u, t1 = tail > 1u ? __ldcg(from + tailAt + 1) : 0u, t2 = tail > 2u ? __ldcg(from + tailAt + 2) : 0u;
-    /* ---- stores ---- */
-    if (head > 0u) out[0] = (u8)h0;
-    if (head > 1u) out[1] = (u8)h1;
-    if (head > 2u) out[2] = (u8)h2;
-    {   u32* const o = reinterpret_cast<u32*>(out + head);
+        for (u32 i = 0; i < 9u; i++) w[i] = (i < words || (i == words && sh)) ? zbd_ldcg32(aw + 4u * i) : 0u;
+        u32* const o = reinterpret_cast<u32*>(out + k);
 #pragma unroll
-        for (u32 i = 0; i < 8u; i++) if (i < first) o[i] = sh ? __funnelshift_r(w[i], w[i + 1], sh) : w[i]; }
-    if (tail > 0u) out[tailAt] = (u8)t0;
-    if (tail > 1u) out[tailAt + 1] = (u8)t1;
-    if (tail > 2u) out[tailAt + 2] = (u8)t2;
-    /* ---- further rounds of up to eight words ---- */
-    for (u32 done = first; done < words; ) {
-        u32 const cnt = words - done < 8u ? words - done : 8u;
-        const u8* const bw = aw + 4u * done;
-        u32 v[9];
-#pragma unroll
-        for (u32 i = 0; i < 9u; i++) v[i] = (i < cnt || (i == cnt && sh)) ? zbd_ldcg32(bw + 4u * i) : 0u;
-        u32* const o = reinterpret_cast<u32*>(out + head + 4u * done);
-#pragma unroll
-        for (u32 i = 0; i < 8u; i++) if (i < cnt) o[i] = sh ? __funnelshift_r(v[i], v[i + 1], sh) : v[i];
-        done += cnt;
+        for (u32 i = 0; i < 8u; i++) if (i < words) o[i] = sh ? __funnelshift_r(w[i], w[i + 1], sh) : w[i];
+        k += 4u * words;
     }
+    {   u32 const t = n - k;                                       /* 0..3 tail bytes */
+        u32 const b0 = t > 0u ? __ldcg(from + k) : 0u, b1 = t > 1u ? __ldcg(from + k + 1) : 0u, b2 = t > 2u ? __ldcg(from + k + 2) : 0u;
+        if (t > 0u) out[k] = (u8)b0; if (t > 1u) out[k + 1] = (u8)b1; if (t > 2u) out[k + 2] = (u8)b2; }
 }
 
 /* One CTA per frame: the matches of a frame form a wavefront that moves through the output (a match's source lies a
