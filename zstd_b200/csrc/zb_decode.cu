@@ -363,9 +363,47 @@ zbd_place_kernel(const u8* __restrict__ src, const ZbdBlock* __restrict__ blocks
  * their completion flags, copies, raises its own flag.  Independent matches — nearly all of them when offsets exceed a
  * few hundred bytes — run in parallel across the whole GPU; what remains serial is the longest chain of matches that copy
  * from one another.  dst[p + k] = history[p - off + (k mod off)]. */
-__device__ __forceinline__ u32 zbd_ld_flag(const u8* p) { u32 v; asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ void zbd_st_flag(u8* p) { asm volatile("st.volatile.global.u8 [%0], %1;" :: "l"(p), "r"(1u) : "memory"); }
-__device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord) { return __ldcg(reinterpret_cast<const u32*>(alignedWord)); }
+/* Hand-overs stay inside one CTA (a frame's matches are one CTA's), i.e. inside one SM and its L1: flags are read and
+ * written with CTA-scope relaxed accesses (they may be served by that L1), the copied bytes with ordinary loads — a line
+ * that was cached before a neighbouring warp wrote into it is updated by that write, both go through the same L1 — and
+ * block-scope fences order the two.  ZBD_LD_L2 = 1 routes everything through L2 instead (development switch). */
+#ifndef ZBD_LD_L2
+#define ZBD_LD_L2 0
+#endif
+__device__ __forceinline__ u32 zbd_ld_flag(const u8* p)
+{
+    u32 v;
+#if ZBD_LD_L2
+    asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
+    asm volatile("ld.relaxed.cta.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
+    return v;
+}
+__device__ __forceinline__ void zbd_st_flag(u8* p)
+{
+#if ZBD_LD_L2
+    asm volatile("st.volatile.global.u8 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+#else
+    asm volatile("st.relaxed.cta.global.u8 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+#endif
+}
+__device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord)
+{
+#if ZBD_LD_L2
+    return __ldcg(reinterpret_cast<const u32*>(alignedWord));
+#else
+    u32 v; asm volatile("ld.relaxed.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(alignedWord) : "memory"); return v;
+#endif
+}
+__device__ __forceinline__ u32 zbd_ld8(const u8* p)
+{
+#if ZBD_LD_L2
+    return __ldcg(p);
+#else
+    u32 v; asm volatile("ld.relaxed.cta.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+#endif
+}
 
 /* n bytes from `from` to `out`, the two ranges not overlapping.  Sources are read through L2 (another warp wrote them a
  * moment ago); what limits a copy is the number of DEPENDENT round trips, so loads go out in groups: the head bytes that
@@ -374,7 +412,7 @@ __device__ __forceinline__ u32 zbd_ldcg32(const u8* alignedWord) { return __ldcg
 __device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n)
 {
     u32 head = (4u - ((u32)(uintptr_t)out & 3u)) & 3u; head = head < n ? head : n;
-    {   u32 const b0 = head > 0u ? __ldcg(from) : 0u, b1 = head > 1u ? __ldcg(from + 1) : 0u, b2 = head > 2u ? __ldcg(from + 2) : 0u;
+    {   u32 const b0 = head > 0u ? zbd_ld8(from) : 0u, b1 = head > 1u ? zbd_ld8(from + 1) : 0u, b2 = head > 2u ? zbd_ld8(from + 2) : 0u;
         if (head > 0u) out[0] = (u8)b0; if (head > 1u) out[1] = (u8)b1; if (head > 2u) out[2] = (u8)b2; }
     u32 k = head;
     while (k + 4u <= n) {                                         /* destination word-aligned from here */
@@ -391,7 +429,7 @@ __device__ __forceinline__ void zbd_copy_disjoint(u8* out, const u8* from, u32 n
         k += 4u * words;
     }
     {   u32 const t = n - k;                                       /* 0..3 tail bytes */
-        u32 const b0 = t > 0u ? __ldcg(from + k) : 0u, b1 = t > 1u ? __ldcg(from + k + 1) : 0u, b2 = t > 2u ? __ldcg(from + k + 2) : 0u;
+        u32 const b0 = t > 0u ? zbd_ld8(from + k) : 0u, b1 = t > 1u ? zbd_ld8(from + k + 1) : 0u, b2 = t > 2u ? zbd_ld8(from + k + 2) : 0u;
         if (t > 0u) out[k] = (u8)b0; if (t > 1u) out[k + 1] = (u8)b1; if (t > 2u) out[k + 2] = (u8)b2; }
 }
 
@@ -458,7 +496,7 @@ zbd_matches_kernel(const ZbdBlock* __restrict__ blocks, const ZbdFrame* __restri
                 if (off >= ml) zbd_copy_disjoint(out, from, ml);
                 else if (off < 8u) {                                 /* a short pattern: read once, written ml times over */
                     u64 pat = 0;
-                    for (u32 k = 0; k < off; k++) pat |= (u64)__ldcg(from + k) << (8u * k);
+                    for (u32 k = 0; k < off; k++) pat |= (u64)zbd_ld8(from + k) << (8u * k);
                     u32 r = 0;
                     for (u32 k = 0; k < ml; k++) { out[k] = (u8)(pat >> (8u * r)); r++; if (r == off) r = 0; }
                 } else {                                             /* the `off` bytes in front of the match, again and again: every piece a disjoint copy */
