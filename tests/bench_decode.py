@@ -57,3 +57,27 @@ for p, level in ((50, 1), (90, 3), (30, -3)):
         ok = m == len(src) and torch.equal(d_out, d_src)
         print(f"P{p} level {level} {what:9s}: {len(src) >> 20} MiB <- {n} B  {best:.2f} ms = {len(src) / best / 1e6:.1f} GB/s  "
               f"[kernels {st.kernel_ms:.2f}: literals {st.literals_ms:.2f} sequences {st.sequences_ms:.2f} place {st.place_ms:.2f} matches {st.execute_ms:.2f}; {st.nbBlocks} blocks]  ok {ok}", flush=True)
+
+# many frames in one call: the match stage runs one CTA per frame, so frames decode side by side
+if mib >= 256:
+    for p, level, fs, what in ((30, -3, 64 << 20, "64 MiB frames (config 3's shape)"), (50, 1, 64 << 20, "64 MiB frames"), (50, 1, 1 << 20, "1 MiB frames"), (50, 1, 1024, "1 KiB records")):
+        n = (mib << 20) if fs >= (1 << 20) else (128 << 20)
+        src = zref.datagen(n, p)
+        d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+        offs = list(range(0, n, fs)); sizes = [fs] * len(offs)
+        cap = sum(zstd_b200.ZSTD_compressBound(x) + 32 for x in sizes)
+        d_c = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        total, csz = c.compress_frames(d_c.data_ptr(), cap, d_src.data_ptr(), offs, sizes, level=level)
+        d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        best = None
+        for _ in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            m = d.decompress_device(d_out.data_ptr(), n, d_c.data_ptr(), total)
+            ev1.record(); torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            best = ms if best is None else min(best, ms)
+        st = d.stats()
+        ok = m == n and torch.equal(d_out, d_src)
+        print(f"P{p} level {level}, {len(offs)} x {what}: {n >> 20} MiB <- {total} B  {best:.2f} ms = {n / best / 1e6:.1f} GB/s  "
+              f"[kernels {st.kernel_ms:.2f}: literals {st.literals_ms:.2f} sequences {st.sequences_ms:.2f} place {st.place_ms:.2f} matches {st.execute_ms:.2f}]  ok {ok}", flush=True)

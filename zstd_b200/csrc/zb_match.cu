@@ -489,24 +489,19 @@ zb_parse_dfast_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd
         u32 const p = ip + lane * step;
         bool const act = (p < se) && (p + 9u <= be);
         u32 const pp = act ? p : ip;
-        /* three candidate rows and two windows: independent loads, all sent before the first is looked at (far distances,
-         * the rare case, cost one more round trip below) */
-        u32 const dL16 = act ? (u32)dLp[pp - bs] : 0u;
-        u32 const dS16 = act ? (u32)dSp[pp - bs] : 0u;
-        u32 const dL116 = act ? (u32)dLp[pp + 1u - bs] : 0u;
-        u64 const w = zb_seg_ld64x<DICT>(sg, pp);                            /* bytes p .. p+7 */
-        bool const v2 = act && rep1 != 0u && (p + 1u >= rep1);
-        u32 const r2 = (u32)zb_seg_ld64x<DICT>(sg, v2 ? pp + 1u - rep1 : pp);
-        u32 const cur = (u32)w, cur1 = (u32)(w >> 8);
-        u32 r3 = ~cur;
-        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
-        if (ip == anchor && rep2 != 0u) r3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);
-        u32 dL = dL16 == ZB_FAR ? fLp[pp - bs] : dL16;
-        u32 dS = dS16 == ZB_FAR ? fSp[pp - bs] : dS16;
-        u32 dL1 = dL116 == ZB_FAR ? fLp[pp + 1u - bs] : dL116;
+        u32 dL = act ? zb_dist_at(dLp, fLp, pp - bs) : 0u;
+        u32 dS = act ? zb_dist_at(dSp, fSp, pp - bs) : 0u;
+        u32 dL1 = act ? zb_dist_at(dLp, fLp, pp + 1u - bs) : 0u;
         if (dL > pp) dL = 0u;                                  /* reaches past the visible history (window) */
         if (dS > pp) dS = 0u;
         if (dL1 > pp + 1u) dL1 = 0u;
+        u64 const w = zb_seg_ld64x<DICT>(sg, pp);                            /* bytes p .. p+7 */
+        u32 const cur = (u32)w, cur1 = (u32)(w >> 8);
+        bool const v2 = act && rep1 != 0u && (p + 1u >= rep1);
+        u32 const r2 = (u32)zb_seg_ld64x<DICT>(sg, v2 ? pp + 1u - rep1 : pp);
+        u32 r3 = ~cur;
+        bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
+        if (ip == anchor && rep2 != 0u) r3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);
         /* 3 repcode-2, 2 repcode-1 (at p+1), 1 long candidate, 4 short candidate */
         u32 hit = (v3 && r3 == cur) ? 3u : ((v2 && r2 == cur1) ? 2u : (dL ? 1u : (dS ? 4u : 0u)));
         u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
