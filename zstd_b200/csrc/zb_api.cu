@@ -82,7 +82,7 @@ static ZbParams zb_makeParams(const ZbCParams& cp)
         u32 const hl = cp.hashLog > ZB_FAST_HASHLOG_MAX ? ZB_FAST_HASHLOG_MAX : cp.hashLog;
         p.stepSize = cp.targetLength + !cp.targetLength + 1;     /* zstd_fast.c:200 */
         if (cp.targetLength == 0) { p.tableN = 3u << (hl - 2); p.insStep = 3; }
-        else                      { p.tableN = 7u << (hl - 3); p.insStep = p.stepSize; }
+        else                      { p.tableN = 7u << (hl - 3); p.insStep = p.stepSize >= 5u ? p.stepSize - 1u : p.stepSize; }   /* never the parse's own probe spacing from 5 on: equal periods lock the probed positions out of phase with the inserted ones (level -7: +8.6 % instead of -6.6 % on datagen -P90) */
     } else {
         p.stepSize = 1;
         p.tableN = 1u << cp.chainLog;                            /* short table (zstd_double_fast.c:116) */
