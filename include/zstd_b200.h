@@ -149,9 +149,10 @@ ZSTDB200_API size_t ZSTD_DStreamOutSize(void);
 
 /* =====================  2. B200 extensions (no reference counterpart)  ===================== */
 
-/* Decompress frames whose bytes are in device memory into device memory.  The block headers are followed by one device
- * thread (a chain of dependent reads: about 1 us per block), everything else is block-parallel.  Content checksums are
- * not verified on this path.  `stream`: as for ZSTDB200_compressDevice.  Returns the decompressed size. */
+/* Decompress frames whose bytes are in device memory into device memory.  The frame / block headers are a chain that has to
+ * be followed in order: for inputs of up to 512 MiB the compressed bytes are copied to a page-locked host buffer and walked
+ * there, beyond that one device thread follows them (about 1 us per block); everything else is block-parallel.  Content
+ * checksums are not verified on this path.  `stream`: as for ZSTDB200_compressDevice.  Returns the decompressed size. */
 ZSTDB200_API size_t ZSTDB200_decompressDevice(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, void* stream);
 /* same with a dictionary (host memory; uploaded by the call) */
 ZSTDB200_API size_t ZSTDB200_decompressDevice_usingDict(ZSTD_DCtx* dctx, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize,

@@ -109,6 +109,16 @@ def test_device_buffers(cctx, dctx):
     assert n == len(src) and bytes(d_out.cpu().numpy()) == src
     st = dctx.stats()
     assert st.nbFrames == 2 and st.nbBlocks == 72
+    # the same through the kernel walk (inputs beyond 512 MiB take it; forced here)
+    os.environ["ZSTDB200_HOSTWALK_MAX"] = "0"
+    try:
+        d2 = zstd_b200.ZSTD_DCtx()
+    finally:
+        del os.environ["ZSTDB200_HOSTWALK_MAX"]
+    d_out.zero_()
+    assert d2.decompress_device(d_out.data_ptr(), len(src), d_in.data_ptr(), len(frames)) == len(src)
+    assert bytes(d_out.cpu().numpy()) == src
+    d2.close()
 
 
 @needs_ref

@@ -40,6 +40,7 @@
 #include "zb_decode_core.cuh"
 
 #define ZB_FULL 0xFFFFFFFFu
+#define ZBD_HOSTWALK_MAX ((size_t)512 << 20)   /* device-resident inputs up to this size have their headers walked on the host (zbd_decompressDevice) */
 #define ZBD_WARPS 4                    /* blocks per CTA in D1 / D2 / D4 */
 
 /* per block, written by D2 and D3 */
@@ -522,6 +523,8 @@ struct ZSTD_DCtx_s {
     u64* h_res;                  /* pinned: walker / scan results */
     /* streaming front end (ZSTD_decompressStream): compressed bytes collected until a frame is complete, output waiting to be handed out */
     std::vector<u8>* dsIn; std::vector<u8>* dsOut; size_t dsOutPos;
+    size_t hostWalkMax;          /* ZBD_HOSTWALK_MAX, or ZSTDB200_HOSTWALK_MAX from the environment (tests: 0 forces the kernel walk) */
+    u8* h_stage; size_t capStage; /* page-locked copy of a device-resident input's compressed bytes, for the header walk */
     u8* d_dict; size_t capDict;  /* the call's dictionary, whole (header + content) */
     ZbdDictInfo di; size_t dictSize;
     cudaEvent_t ev[7];
@@ -539,6 +542,7 @@ extern "C" ZSTD_DCtx* ZSTD_createDCtx(void)                          /* lib/zstd
     ZSTD_DCtx* d = (ZSTD_DCtx*)calloc(1, sizeof(ZSTD_DCtx));
     if (!d) return NULL;
     d->device = -1;
+    {   const char* const e = getenv("ZSTDB200_HOSTWALK_MAX"); d->hostWalkMax = e ? (size_t)strtoull(e, NULL, 10) : ZBD_HOSTWALK_MAX; }
     d->bindDevice = zb_boundDevice();
     if (d->bindDevice < 0) { int dev = -1; if (cudaGetDevice(&dev) == cudaSuccess) d->bindDevice = dev; else cudaGetLastError(); }
     return d;
@@ -550,7 +554,7 @@ extern "C" size_t ZSTD_freeDCtx(ZSTD_DCtx* d)                        /* accepts 
         int prev = -1; cudaGetDevice(&prev);
         cudaSetDevice(d->device);
         cudaFree(d->d_blocks); cudaFree(d->d_frames); cudaFree(d->d_bout); cudaFree(d->d_lits); cudaFree(d->d_seqs); cudaFree(d->d_matchPos); cudaFree(d->d_tileFirst); cudaFree(d->d_done);
-        cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res); cudaFree(d->d_dict);
+        cudaFree(d->d_in); cudaFree(d->d_out); cudaFree(d->d_res); cudaFreeHost(d->h_res); cudaFree(d->d_dict); cudaFreeHost(d->h_stage);
         for (int i = 0; i < 7; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
         if (d->stream) cudaStreamDestroy(d->stream);
         if (prev >= 0) cudaSetDevice(prev);
@@ -700,8 +704,35 @@ static size_t zbd_decompressHost(ZSTD_DCtx* d, void* dst, size_t dstCapacity, co
 }
 
 /* device buffers: the walk is a kernel (one thread follows the chain of block headers) */
+/* device buffers.  The headers have to be followed one after the other wherever they are read: one device thread pays a
+ * memory round trip (~1 us) per header, the host ~0.1 us — so compressed inputs up to ZBD_HOSTWALK_MAX are copied to a
+ * page-locked staging buffer (at PCIe speed) and walked there (a call of 131072 one-KiB frames: 207 -> ~30 ms); beyond
+ * that the walk is a kernel (one thread follows the chain of block headers). */
 static size_t zbd_decompressDevice(ZSTD_DCtx* d, void* d_dst, size_t dstCapacity, const void* d_src, size_t srcSize, cudaStream_t st)
 {
+    if (srcSize <= d->hostWalkMax) {
+        if (srcSize > d->capStage) {
+            cudaFreeHost(d->h_stage); d->h_stage = NULL; d->capStage = 0;
+            size_t const n = srcSize + srcSize / 4 + 4096;
+            DCK(cudaMallocHost(&d->h_stage, n));
+            d->capStage = n;
+        }
+        DCK(cudaMemcpyAsync(d->h_stage, d_src, srcSize, cudaMemcpyDeviceToHost, st));
+        DCK(cudaStreamSynchronize(st));
+        const u8* const in = d->h_stage;
+        u32 nb = 0, nf = 0; u64 lit = 0, seq = 0;
+        u32 e = zbd_walk(in, srcSize, NULL, 0, NULL, 0, &nb, &nf, &lit, &seq, d->di.entropy != 0, d->di.dictID);
+        if (e) return ZB_ERR(e);
+        if (nb == 0) return 0;
+        std::vector<ZbdBlock> B(nb); std::vector<ZbdFrame> F(nf ? nf : 1);
+        e = zbd_walk(in, srcSize, B.data(), nb, F.data(), nf, &nb, &nf, &lit, &seq, d->di.entropy != 0, d->di.dictID);
+        if (e) return ZB_ERR(e);
+        {   size_t const r = zbd_ensure(d, nb, nf, lit, seq); if (zbd_isErr(r)) return r; }
+        DCK(cudaMemcpyAsync(d->d_blocks, B.data(), (size_t)nb * sizeof(ZbdBlock), cudaMemcpyHostToDevice, st));
+        DCK(cudaMemcpyAsync(d->d_frames, F.data(), (size_t)nf * sizeof(ZbdFrame), cudaMemcpyHostToDevice, st));
+        DCK(cudaStreamSynchronize(st));                               /* B and F are pageable and go out of scope */
+        return zbd_run(d, (u8*)d_dst, dstCapacity, (const u8*)d_src, nb, nf, seq, st);
+    }
     u32 capB = (u32)(srcSize / 4096u) + 1024u, capF = 1024u;
     for (int attempt = 0; attempt < 2; attempt++) {
         {   size_t const r = zbd_ensure(d, capB, capF, 0, 0); if (zbd_isErr(r)) return r; }
