@@ -14,9 +14,16 @@
 #include "zb_kernels.h"
 #include "zb_bitpack.cuh"
 
+#ifndef LIT_THREADS
 #define LIT_THREADS 128
+#endif
+#ifndef LIT_MIN_CTAS
 #define LIT_MIN_CTAS 12               /* 16 (32 registers) measured slower: 1.56 vs 1.40 ms */
+#endif
 #define LIT_WARPS (LIT_THREADS / 32)
+#ifndef LIT_AHEAD
+#define LIT_AHEAD 2                   /* 16-byte vectors of a thread's run requested ahead of the one in use */
+#endif
 
 /* block-wide histogram of src[0..n) into count[256]; returns nothing, count valid after the call */
 __device__ void zb_hist256(const u8* __restrict__ src, u32 n, u32 (*whist)[256], u32* count)   /* whist: LIT_WARPS private histograms */
@@ -83,8 +90,19 @@ __device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ li
     if (aBeg >= aEnd) { for (u32 i = end; i-- > beg; ) f(lit[i]); return; }
     for (u32 i = end; i-- > aEnd; ) f(lit[i]);
     const uint4* v4 = reinterpret_cast<const uint4*>(lit);
-    for (u32 k = aEnd / 16u; k-- > aBeg / 16u; ) {
-        uint4 const q = __ldg(v4 + k);
+    /* a thread's run is walked one 16-byte vector at a time, each needing the one before it consumed: the next LIT_AHEAD
+     * vectors are requested before the current one is used, so a round trip to L2 is paid once per run, not per vector */
+    u32 k = aEnd / 16u;
+    u32 const kLo = aBeg / 16u;
+    uint4 nx[LIT_AHEAD];
+#pragma unroll
+    for (u32 a = 0; a < LIT_AHEAD; a++) nx[a] = (k >= kLo + a + 1u) ? __ldg(v4 + (k - a - 1u)) : make_uint4(0, 0, 0, 0);
+    while (k > kLo) {
+        k--;
+        uint4 const q = nx[0];
+#pragma unroll
+        for (u32 a = 0; a + 1u < LIT_AHEAD; a++) nx[a] = nx[a + 1u];
+        if (k >= kLo + LIT_AHEAD) nx[LIT_AHEAD - 1u] = __ldg(v4 + (k - LIT_AHEAD));
         u32 const w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
         for (int t = 3; t >= 0; t--) { f((u8)(w[t] >> 24)); f((u8)(w[t] >> 16)); f((u8)(w[t] >> 8)); f((u8)w[t]); }

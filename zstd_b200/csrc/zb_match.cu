@@ -193,6 +193,9 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
  *   C  positions that found nothing in A look again: the batch's lowest insertion into their bucket may serve them.
  * Two barriers per batch (A|B, which also tells every thread whether the batch saw a hit, and B|C); C of one batch
  * and A of the next share a region.  The input bytes of a batch are loaded two batches ahead. */
+#ifndef WALK_STEADY
+#define WALK_STEADY 1            /* development switch: 0 = every batch takes the general path */
+#endif
 #ifndef WALK_P_SMALL
 #define WALK_P_SMALL 4           /* positions per thread for tables <= 56 KiB (development knob: tools/build_variant.sh) */
 #endif
@@ -299,7 +302,37 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
         r0 += stepInc; if (r0 >= insStep) r0 -= insStep;
         x0 += ZB_BATCH;
     };
+    /* the same batch in the walk's steady state — this batch, the one whose words are requested and everything between are
+     * interior batches of the frame's own bytes: none of doBatch's case distinctions apply, the words two batches ahead sit
+     * 2 * ZB_BATCH bytes behind this batch's, the output row moves with the walk.  Same results as doBatch, about half
+     * the instructions around the three phases. */
+    const u8* const tbase = fbase + P * t - shift;                /* tbase + x0 = address of the thread's first byte in the batch at x0 */
+    u16* const distT = dist + P * t;
+    u32* const farT = far + P * t;
+    auto steadyBatch = [&](u32 (&raw)[NW], u32 const sh) {
+        u32 const xa = x0 + P * t;
+        u32 cur[NWR];
+#pragma unroll
+        for (int k = 0; k < NWR; k++) cur[k] = __funnelshift_r(raw[k], (u32)k + 1u < NW ? raw[(u32)k + 1u < NW ? k + 1 : k] : 0u, sh);
+        {   const u32* const pw = reinterpret_cast<const u32*>((uintptr_t)(tbase + x0 + 2u * ZB_BATCH) & ~(uintptr_t)3);
+#pragma unroll
+            for (u32 k = 0; k < NW; k++) raw[k] = __ldg(pw + k);  /* the alignment (sh) is the same in every batch: batches are 1024 bytes apart */
+        }
+        u32 const step = insStep + ((x0 - li) >> 7);
+        u32 const pat = zb_walk_pattern_res<P>(step == insStep ? r0 : zb_walk_residue(xa - shift, step), step);
+        bool const output = !buildImage && x0 >= H + shift;
+        u32 const qb0 = x0 - shift - H;
+        size_t const row = output ? (size_t)(cd.firstBlock - slotFirstBlock + (qb0 >> cd.blockLog)) * sd.dist + (qb0 & blockMask) : 0;
+        if (zb_walk_batch<MLS, P, true>(table, xa, cur, pat, N, shift, D, total, xLow, xEnd, fbase, dbase, output, distT + row, farT + row)) li = x0 + ZB_BATCH;
+        r0 += stepInc; if (r0 >= insStep) r0 -= insStep;
+        x0 += ZB_BATCH;
+    };
     while (x0 < xEnd) {
+        /* pairs of steady-state batches (the two register sets keep their turns) */
+        if (WALK_STEADY && x0 >= xIntLoB && x0 + 4u * ZB_BATCH <= xIntHi) {
+            if (D != 0u && li < D + shift) li = D + shift;           /* as in doBatch: x0 >= xIntLoB >= D + shift */
+            do { steadyBatch(rawA, shA); steadyBatch(rawB, shB); } while (x0 + 4u * ZB_BATCH <= xIntHi);
+        }
         doBatch(rawA, shA);
         if (x0 >= xEnd) break;
         doBatch(rawB, shB);
@@ -572,6 +605,9 @@ __device__ __forceinline__ u32 zb_rep_code(ZbRepHist& h, u32 off, u32 ll)
     return off + 3u;
 }
 
+#ifndef MERGE_GATHER_V2
+#define MERGE_GATHER_V2 1          /* development switch: 0 = a warp per literal run */
+#endif
 #define MERGE_THREADS 256
 #define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
 #define MERGE_PER (MERGE_TILE / MERGE_THREADS)  /* consecutive sequences of a tile owned by one thread */
@@ -679,14 +715,52 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
         __syncthreads();
         if (tid == MERGE_THREADS - 1u) { baseL = offL; baseA = offA; }     /* totals up to the end of this tile */
         if (warp == 0u) {
-            /* the repcode history is a serial recurrence: lane 0 walks the tile while the other warps move literals */
-            if (lane == 0u) for (u32 i = 0; i < n; i++) sOff[i] = zb_rep_code(hist, sOff[i], sLen[i]);
-        } else {
+            /* the repcode history is a serial recurrence: lane 0 walks the tile (the next sequence's offset and literal
+             * length are requested before the current one is decided) while the other warps move literals */
+            if (lane == 0u) {
+                u32 o = sOff[0], l = sLen[0];
+                for (u32 i = 0; i < n; i++) {
+                    u32 const nx = i + 1u < n ? i + 1u : i;
+                    u32 const on = sOff[nx], ln = sLen[nx];
+                    sOff[i] = zb_rep_code(hist, o, l);
+                    o = on; l = ln;
+                }
+            }
+        } else if (!MERGE_GATHER_V2) {
             for (u32 i = warp - 1u; i < n; i += MERGE_THREADS / 32u - 1u) {
                 u32 const len = sLen[i];
                 const u8* const from = in + sPos[i];
                 u8* const to = mylit + sLit[i];
                 for (u32 x = lane; x < len; x += 32u) to[x] = from[x];
+            }
+        } else {
+            /* the tile's literal bytes [L0, L1) of the block's literal buffer, 8 at a time per thread: the run that holds
+             * a group's first byte is found by bisection over the runs' start offsets, later bytes step to the next
+             * non-empty run; all of a thread's loads are independent of one another.  Full groups leave as one 8-byte
+             * store (the buffer is 16-byte aligned), the partial groups at the tile's edges byte by byte. */
+            u32 const L0 = sLit[0], L1 = sLit[n - 1u] + sLen[n - 1u];
+            for (u32 g = (L0 >> 3) + (tid - 32u); (g << 3) < L1; g += MERGE_THREADS - 32u) {
+                u32 const jb = g << 3;
+                u32 const j0 = jb > L0 ? jb : L0, j1 = jb + 8u < L1 ? jb + 8u : L1;
+                u32 sq = 0;                                              /* largest index with sLit[sq] <= j0 (sLit[0] = L0 <= j0) */
+#pragma unroll
+                for (u32 stp = MERGE_TILE / 2u; stp > 0u; stp >>= 1) {
+                    u32 const c = sq + stp;
+                    if (c < n && sLit[c] <= j0) sq = c;
+                }
+                u32 runEnd = sLit[sq] + sLen[sq];
+                const u8* from = in + (sPos[sq] - sLit[sq]);             /* from[j] = the literal at buffer offset j while j lies in run sq */
+                u64 v = 0;
+#pragma unroll
+                for (u32 k = 0; k < 8u; k++) {
+                    u32 const j = jb + k;
+                    if (j >= j0 && j < j1) {
+                        while (j >= runEnd) { sq++; runEnd = sLit[sq] + sLen[sq]; from = in + (sPos[sq] - sLit[sq]); }
+                        v |= (u64)from[j] << (8u * k);
+                    }
+                }
+                if (j1 - j0 == 8u) *reinterpret_cast<u64*>(mylit + jb) = v;
+                else for (u32 j = j0; j < j1; j++) mylit[j] = (u8)(v >> (8u * (j - jb)));
             }
         }
         __syncthreads();

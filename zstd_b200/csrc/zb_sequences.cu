@@ -11,7 +11,7 @@
  *   2. per stream (one warp each): encoding type, normalised counts (largest remainders), NCount header, FSE table
  *      (zb_entropy.cuh); predefined tables are built once per device by the host and copied
  *   3. tANS state chains: state(i) depends on state(i+1) (common/fse.h:463-470), so each of the three
- *      chains is walked backwards by one thread; it records (bits, nbBits) per sequence
+ *      chains is walked backwards by one lane (the three lanes share a warp); it records (bits, nbBits) per sequence
  *   4. all threads: per-sequence bit counts -> suffix sum -> bit offsets -> pack (edge words atomicOr)
  */
 #include "zb_entropy.cuh"
@@ -19,7 +19,7 @@
 #include "zb_bitpack.cuh"
 
 #define SEQ_THREADS 128
-#define SEQ_TILE 2048u
+#define SEQ_TILE 512u                /* sequences whose chain steps are prepared at a time (3 x 2 KiB of shared memory) */
 #define MaxLL 35
 #define MaxML 52
 #define MaxOff 31
@@ -29,15 +29,14 @@
 #define OffFSELog 8
 
 /* format constants, common/zstd_internal.h:123-168 (RFC 8878) */
-__constant__ u8 c_LL_bits[MaxLL + 1] = { 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 1,1,1,1,2,2,3,3, 4,6,7,8,9,10,11,12, 13,14,15,16 };
-__constant__ u8 c_ML_bits[MaxML + 1] = { 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0, 0,0,0,0,0,0,0,0,
-                                         1,1,1,1,2,2,3,3, 4,4,5,7,8,9,10,11, 12,13,14,15,16 };
 __constant__ short c_LL_defaultNorm[MaxLL + 1] = { 4,3,2,2,2,2,2,2, 2,2,2,2,2,1,1,1, 2,2,2,2,2,2,2,2, 2,3,2,1,1,1,1,1, -1,-1,-1,-1 };
 __constant__ short c_ML_defaultNorm[MaxML + 1] = { 1,4,3,2,2,2,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1,
                                                    1,1,1,1,1,1,1,1, 1,1,1,1,1,1,-1,-1, -1,-1,-1,-1,-1 };
 __constant__ short c_OF_defaultNorm[DefaultMaxOff + 1] = { 1,1,1,1,1,1,2,2, 2,1,1,1,1,1,1,1, 1,1,1,1,1,1,1,1, -1,-1,-1,-1,-1 };
 
-/* closed forms of the code tables in zstd_compress_internal.h:520-549 */
+/* closed forms of the code tables in zstd_compress_internal.h:520-549 and of the extra-bit counts (LL_bits / ML_bits,
+ * common/zstd_internal.h:123-137): only used to fill the CTA's look-up tables for values below 64 (LL) / 128 (ML); above
+ * that the code is highbit + 19 (+ 36) and carries highbit extra bits */
 __device__ __forceinline__ u32 zbd_ll_code(u32 ll)
 {
     if (ll > 63u) return zb_hb32(ll) + 19u;
@@ -57,16 +56,30 @@ __device__ __forceinline__ u32 zbd_ml_code(u32 mlBase)
     if (mlBase < 96u) return 40u + ((mlBase - 64u) >> 4);
     return 42u;
 }
-struct ZbdSeq { u32 offBase, litLen, mlBase, llc, ofc, mlc; };
-__device__ __forceinline__ ZbdSeq zbd_unpack(u64 q)
+__device__ __forceinline__ u32 zbd_ll_lut_entry(u32 ll)       /* ll < 64: code | extra bits << 8 */
+{
+    u32 const c = zbd_ll_code(ll);
+    return c | ((c < 16u ? 0u : (c < 20u ? 1u : (c < 22u ? 2u : (c < 24u ? 3u : 4u)))) << 8);
+}
+__device__ __forceinline__ u32 zbd_ml_lut_entry(u32 mlBase)   /* mlBase < 128 */
+{
+    u32 const c = zbd_ml_code(mlBase);
+    return c | ((c < 32u ? 0u : (c < 36u ? 1u : (c < 38u ? 2u : (c < 40u ? 3u : (c < 42u ? 4u : 5u))))) << 8);
+}
+struct ZbdCodeLut { u16 ll[64]; u16 ml[128]; };               /* shared memory, filled once per CTA: the branches of the closed forms diverge */
+struct ZbdSeq { u32 offBase, litLen, mlBase, llc, ofc, mlc, llBits, mlBits; };
+__device__ __forceinline__ ZbdSeq zbd_unpack(u64 q, const ZbdCodeLut& lut)
 {
     ZbdSeq s;
     s.offBase = (u32)(q & 0xFFFFFFu);
     s.litLen = (u32)((q >> 24) & 0x3FFFFu);
     s.mlBase = (u32)((q >> 42) & 0x3FFFFu) - 3u;
-    s.llc = zbd_ll_code(s.litLen);
+    u32 const le = lut.ll[s.litLen < 63u ? s.litLen : 63u], lh = zb_hb32(s.litLen | 1u);
+    u32 const me = lut.ml[s.mlBase < 127u ? s.mlBase : 127u], mh = zb_hb32(s.mlBase | 1u);
+    bool const lBig = s.litLen > 63u, mBig = s.mlBase > 127u;
+    s.llc = lBig ? lh + 19u : (le & 0xFFu);  s.llBits = lBig ? lh : (le >> 8);
+    s.mlc = mBig ? mh + 36u : (me & 0xFFu);  s.mlBits = mBig ? mh : (me >> 8);
     s.ofc = zb_hb32(s.offBase);
-    s.mlc = zbd_ml_code(s.mlBase);
     return s;
 }
 
@@ -112,8 +125,10 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     __shared__ ZbdFseCTable ct[3];                 /* 0 = LL, 1 = OF, 2 = ML */
     __shared__ ZbdStreamWork wk[3];
     __shared__ u32 chunkBits[SEQ_THREADS];
-    __shared__ u32 codeTile[SEQ_TILE];             /* llCode | ofCode << 8 | mlCode << 16 of one tile of sequences */
+    __shared__ u32 stepTile[3][SEQ_TILE + 3u];     /* per chain and sequence of a tile: deltaNbBits (20 bits, >= 0) | deltaFindState << 20 (signed), from word 1 on (word 0 is read, never used);
+                                                    * odd stride: the three chains read different banks */
     __shared__ u32 sh_cSize, sh_hdrEnd, sh_streamSize;
+    __shared__ ZbdCodeLut lut;
 
     u32 const tid = threadIdx.x;
     u32 const b = blockIdx.x;
@@ -140,9 +155,10 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
     } else {
         /* ---- 1. codes + histograms ---- */
         for (u32 i = tid; i < 192u; i += SEQ_THREADS) wk[i >> 6].count[i & 63u] = 0;
+        for (u32 i = tid; i < 192u; i += SEQ_THREADS) { if (i < 64u) lut.ll[i] = (u16)zbd_ll_lut_entry(i); else lut.ml[i - 64u] = (u16)zbd_ml_lut_entry(i - 64u); }
         __syncthreads();
         for (u32 i = tid; i < nbSeq; i += SEQ_THREADS) {
-            ZbdSeq const s = zbd_unpack(myseq[i]);
+            ZbdSeq const s = zbd_unpack(myseq[i], lut);
             atomicAdd(&wk[0].count[s.llc], 1u);
             atomicAdd(&wk[1].count[s.ofc], 1u);
             atomicAdd(&wk[2].count[s.mlc], 1u);
@@ -171,7 +187,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
                 for (u32 i = lane; i < sizeof(ZbdFseCTable) / 4u; i += 32u) to[i] = from[i];
             } else if (type == set_rle) {                            /* zstd_compress_sequences.c:254-259 */
                 if (lane == 0) {
-                    ZbdSeq const first = zbd_unpack(myseq[0]);
+                    ZbdSeq const first = zbd_unpack(myseq[0], lut);
                     u32 const sym = st == 0 ? first.llc : (st == 1 ? first.ofc : first.mlc);
                     zbd_fse_buildCTable_rle(&ct[st], max);
                     w->nc[0] = (u8)sym; w->ncSize = 1;
@@ -181,7 +197,7 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
                 u32 nbSeq_1 = nbSeq;
                 u32 const tableLog = zbd_fse_optimalTableLog(FSELog, nbSeq, max, 2);
                 {   /* the last sequence's symbols start the states and cost no bits (zstd_compress_sequences.c:271-274) */
-                    ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1]);
+                    ZbdSeq const last = zbd_unpack(myseq[nbSeq - 1], lut);
                     u32 const lastCode = st == 0 ? last.llc : (st == 1 ? last.ofc : last.mlc);
                     if (w->count[lastCode] > 1u) { nbSeq_1--; __syncwarp(); if (lane == 0) w->count[lastCode]--; }
                     __syncwarp();
@@ -200,34 +216,47 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         bool const err = wk[0].err | wk[1].err | wk[2].err;
         if (err) { if (tid == 0) { meta[b].type = ZB_BT_RAW; meta[b].bodySize = bd.size; } return; }
 
-        /* ---- 3. state chains: threads 0, 32, 64.  The only loop-carried value of a chain is `state`
-         * (common/fse.h:463-470); everything else is prepared in parallel: the sequences are walked last to
-         * first in tiles whose LL/OF/ML codes all threads put into shared memory, so a chain step is two
-         * shared-memory look-ups of the table row plus the next-state look-up. ---- */
+        /* ---- 3. state chains.  The only loop-carried value of a chain is `state` (common/fse.h:463-470): everything
+         * else is prepared in parallel.  The sequences are walked last to first in tiles; all threads turn a tile's
+         * LL/OF/ML codes into the chains' per-step words (the symbol's deltaNbBits | deltaFindState << 20), then lanes
+         * 0, 1, 2 of ONE warp walk the three chains side by side — a lane that walks alone costs a whole warp's issue
+         * slot per instruction, three lanes in one warp cost the same slot once.  A step is: word of the next step
+         * requested, bits shed, record stored, next-state look-up. ---- */
         {
             u32 state = 0;
-            u32 const st = tid >> 5;
-            bool const chain = ((tid & 31u) == 0) && tid < 96u;
-            const ZbdFseCTable* const t = &ct[st < 3u ? st : 0u];
-            u16* const rec = myst + (size_t)(st < 3u ? st : 0u) * sd.state;
+            bool const chain = tid < 3u;
+            u32 const st = chain ? tid : 0u;
+            const u16* const ns = ct[st].nextState;
+            const u32* const tw = stepTile[st] + 1;
+            u16* const rec = myst + (size_t)st * sd.state;
             u32 const nbTiles = (nbSeq + SEQ_TILE - 1u) / SEQ_TILE;
             for (u32 tile = nbTiles; tile-- > 0; ) {
                 u32 const t0 = tile * SEQ_TILE, t1 = min(t0 + SEQ_TILE, nbSeq);
                 for (u32 i = t0 + tid; i < t1; i += SEQ_THREADS) {
-                    ZbdSeq const s = zbd_unpack(myseq[i]);
-                    codeTile[i - t0] = s.llc | (s.ofc << 8) | (s.mlc << 16);
+                    ZbdSeq const s = zbd_unpack(myseq[i], lut);
+                    stepTile[0][i - t0 + 1u] = ct[0].deltaNbBits[s.llc] | ((u32)ct[0].deltaFindState[s.llc] << 20);
+                    stepTile[1][i - t0 + 1u] = ct[1].deltaNbBits[s.ofc] | ((u32)ct[1].deltaFindState[s.ofc] << 20);
+                    stepTile[2][i - t0 + 1u] = ct[2].deltaNbBits[s.mlc] | ((u32)ct[2].deltaFindState[s.mlc] << 20);
                 }
                 __syncthreads();
                 if (chain) {
-                    u32 i = t1;
-                    if (t1 == nbSeq) { i--; state = zbd_fse_initState2(t, (codeTile[i - t0] >> (8u * st)) & 0xFFu); }   /* last sequence: no bits */
-                    while (i-- > t0) {
-                        u32 const sym = (codeTile[i - t0] >> (8u * st)) & 0xFFu;
-                        u32 const dnb = t->deltaNbBits[sym];
-                        int const dfs = t->deltaFindState[sym];
-                        u32 const nb = (state + dnb) >> 16;
-                        rec[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-                        state = t->nextState[(int)(state >> nb) + dfs];
+                    u32 cnt = t1 - t0;                                   /* steps of this tile, last sequence first */
+                    const u32* pw = tw + cnt;                            /* pw[-1] = word of the sequence in turn */
+                    u16* pr = rec + t1;
+                    if (t1 == nbSeq) {                                   /* last sequence: its symbols start the states and cost no bits */
+                        u32 const w0 = pw[-1], dnb = w0 & 0xFFFFFu;
+                        u32 const nbOut = (dnb + (1u << 15)) >> 16;
+                        state = ns[(int)(((nbOut << 16) - dnb) >> nbOut) + ((int)w0 >> 20)];
+                        cnt--; pw--; pr--;
+                    }
+                    u32 w = pw[-1];                                      /* tw[-1] exists (padding word): no guard */
+                    while (cnt) {
+                        cnt--; pw--; pr--;
+                        u32 const wn = pw[-1];                           /* next step's word, in flight during this step */
+                        u32 const nb = (state + (w & 0xFFFFFu)) >> 16;
+                        *pr = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+                        state = ns[(int)(state >> nb) + ((int)w >> 20)];
+                        w = wn;
                     }
                 }
                 __syncthreads();
@@ -249,8 +278,8 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
         u32 const cBeg = min(tid * cs, nbSeq), cEnd = min((tid + 1u) * cs, nbSeq);
         u32 bits = 0;
         for (u32 i = cBeg; i < cEnd; i++) {
-            ZbdSeq const s = zbd_unpack(myseq[i]);
-            bits += c_LL_bits[s.llc] + c_ML_bits[s.mlc] + s.ofc;
+            ZbdSeq const s = zbd_unpack(myseq[i], lut);
+            bits += s.llBits + s.mlBits + s.ofc;
             if (i + 1u < nbSeq) bits += (myst[i] >> 12) + (myst[sd.state + i] >> 12) + (myst[2u * sd.state + i] >> 12);
         }
         chunkBits[tid] = bits;
@@ -280,14 +309,14 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
             __syncthreads();
             ZbdParW pw; zbd_pw_init(&pw, ow, (u64)hdrEnd * 8u + bitOff);
             for (u32 i = cEnd; i-- > cBeg; ) {                 /* last sequence first, zstd_compress_sequences.c:311-370 */
-                ZbdSeq const s = zbd_unpack(myseq[i]);
+                ZbdSeq const s = zbd_unpack(myseq[i], lut);
                 if (i + 1u < nbSeq) {
                     u32 const rOF = myst[sd.state + i], rML = myst[2u * sd.state + i], rLL = myst[i];
                     zbd_pw_add(&pw, rOF & 0xFFFu, rOF >> 12);
                     zbd_pw_add(&pw, rML & 0xFFFu, rML >> 12);
                     zbd_pw_add(&pw, rLL & 0xFFFu, rLL >> 12);
                 }
-                u32 const llb = c_LL_bits[s.llc], mlb = c_ML_bits[s.mlc];
+                u32 const llb = s.llBits, mlb = s.mlBits;
                 zbd_pw_add(&pw, s.litLen & ((1u << llb) - 1u), llb);
                 zbd_pw_add(&pw, s.mlBase & ((1u << mlb) - 1u), mlb);
                 zbd_pw_add(&pw, s.offBase & ((1u << s.ofc) - 1u), s.ofc);
