@@ -19,7 +19,9 @@
 #include "zb_bitpack.cuh"
 
 #define SEQ_THREADS 128
+#ifndef SEQ_TILE
 #define SEQ_TILE 512u                /* sequences whose chain steps are prepared at a time (3 x 2 KiB of shared memory) */
+#endif
 #define MaxLL 35
 #define MaxML 52
 #define MaxOff 31
