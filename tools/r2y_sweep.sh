@@ -1,14 +1,10 @@
 #!/bin/bash
-# One GPU call: previous build ("base") against the current one, per kernel, on configs 2 and 4; which file a difference in
-# the output bytes comes from (only when there is one); GPU tests and the bench line of the current build.
+# One GPU call: an earlier build against the current one and its variants, per kernel (tests/variant_sweep.py), then the GPU
+# tests and the bench line of the current build.   usage: tools/r2y_sweep.sh TAG "c2 variants..." "c4 variants..."
 set -x
 mkdir -p gpurun_out
-O=gpurun_out
-timeout 600 python tests/variant_sweep.py c2 base default 2>&1 | grep -v Warning | tee $O/r2y_sweep_c2.txt
-if [ "$(grep -o 'crc [0-9a-f]*' $O/r2y_sweep_c2.txt | sort -u | wc -l)" != "1" ]; then
-  timeout 600 python tests/variant_sweep.py c2 seq lit walk merge 2>&1 | grep -v Warning | tee -a $O/r2y_sweep_c2.txt
-fi
-timeout 300 python tests/variant_sweep.py c2 lit1 lit256 seq1k walk8 2>&1 | grep -v Warning | tee -a $O/r2y_sweep_c2.txt
-timeout 600 python tests/variant_sweep.py c4 base default 2>&1 | grep -v Warning | tee $O/r2y_sweep_c4.txt
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/r2y_gputests.txt
-timeout 600 python bench.py > $O/r2y_bench.json 2> $O/r2y_bench.err; tail -3 $O/r2y_bench.err; cat $O/r2y_bench.json
+O=gpurun_out; T=${1:-r2y}
+timeout 900 python tests/variant_sweep.py c2 $2 2>&1 | grep -v Warning | tee $O/${T}_sweep_c2.txt
+[ -n "$3" ] && timeout 600 python tests/variant_sweep.py c4 $3 2>&1 | grep -v Warning | tee $O/${T}_sweep_c4.txt
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/${T}_gputests.txt
+timeout 600 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err; tail -3 $O/${T}_bench.err; cut -c1-900 $O/${T}_bench.json

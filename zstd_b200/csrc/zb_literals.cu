@@ -21,6 +21,9 @@
 #define LIT_MIN_CTAS 12               /* 16 (32 registers) measured slower: 1.56 vs 1.40 ms */
 #endif
 #define LIT_WARPS (LIT_THREADS / 32)
+#ifndef LIT_PACK2
+#define LIT_PACK2 1                   /* the stream packer looks for a full word once per two codes, without a branch */
+#endif
 #ifndef LIT_AHEAD
 #define LIT_AHEAD 2                   /* 16-byte vectors of a thread's run requested ahead of the one in use */
 #endif
@@ -83,15 +86,17 @@ __device__ void zb_hist_stats(const u32* count, u32* red, u32* largestOut, u32* 
 /* Visit the symbols of lit[beg, end) from the LAST to the first (the order the Huffman stream is
  * written in, huf_compress.c:1056-1118) with 16-byte aligned vector loads: a thread's run is
  * contiguous, so byte loads would cost one request per symbol. */
-template <typename F>
-__device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ lit, u32 beg, u32 end, F f)
+struct ZbNoop { __device__ __forceinline__ void operator()() const {} };
+template <typename F, typename G = ZbNoop>
+__device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ lit, u32 beg, u32 end, F f, G every2 = G())
 {
+    /* every2() runs after at most two symbols (the packer's flush point) */
     u32 const aBeg = (beg + 15u) & ~15u, aEnd = end & ~15u;
-    if (aBeg >= aEnd) { for (u32 i = end; i-- > beg; ) f(lit[i]); return; }
-    for (u32 i = end; i-- > aEnd; ) f(lit[i]);
+    if (aBeg >= aEnd) { for (u32 i = end; i-- > beg; ) { f(lit[i]); every2(); } return; }
+    for (u32 i = end; i-- > aEnd; ) { f(lit[i]); every2(); }
     const uint4* v4 = reinterpret_cast<const uint4*>(lit);
     /* a thread's run is walked one 16-byte vector at a time, each needing the one before it consumed: the next LIT_AHEAD
-     * vectors are requested before the current one is used, so a round trip to L2 is paid once per run, not per vector */
+     * vectors are requested before the current one is used */
     u32 k = aEnd / 16u;
     u32 const kLo = aBeg / 16u;
     uint4 nx[LIT_AHEAD];
@@ -105,9 +110,9 @@ __device__ __forceinline__ void zb_for_each_symbol_rev(const u8* __restrict__ li
         if (k >= kLo + LIT_AHEAD) nx[LIT_AHEAD - 1u] = __ldg(v4 + (k - LIT_AHEAD));
         u32 const w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
-        for (int t = 3; t >= 0; t--) { f((u8)(w[t] >> 24)); f((u8)(w[t] >> 16)); f((u8)(w[t] >> 8)); f((u8)w[t]); }
+        for (int t = 3; t >= 0; t--) { f((u8)(w[t] >> 24)); f((u8)(w[t] >> 16)); every2(); f((u8)(w[t] >> 8)); f((u8)w[t]); every2(); }
     }
-    for (u32 i = aBeg; i-- > beg; ) f(lit[i]);
+    for (u32 i = aBeg; i-- > beg; ) { f(lit[i]); every2(); }
 }
 
 __global__ void __launch_bounds__(LIT_THREADS, LIT_MIN_CTAS)
@@ -291,7 +296,11 @@ zb_literals_kernel(const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides s
         u32 sOff = lhSize + hSize + (nbStreams == 4u ? 6u : 0u);
         for (u32 k = 0; k < s; k++) sOff += sh_streamSize[k];
         ZbdParW pw; zbd_pw_init(&pw, reinterpret_cast<u32*>(out), (u64)sOff * 8u + bitOff);
+#if LIT_PACK2
+        zb_for_each_symbol_rev(lit, cBeg, cEnd, [&](u8 sym) { u32 const e = enc[sym]; zbd_pw_put(&pw, e & 0xFFFFu, e >> 16); }, [&]() { zbd_pw_flush(&pw); });
+#else
         zb_for_each_symbol_rev(lit, cBeg, cEnd, [&](u8 sym) { u32 const e = enc[sym]; zbd_pw_add(&pw, e & 0xFFFFu, e >> 16); });
+#endif
         if (j == 0) zbd_pw_add(&pw, 1u, 1u);
         zbd_pw_finish(&pw);
     }

@@ -176,6 +176,9 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
             for (int i = 0; i < P; i++) if (d[i] >= ZB_FAR) { if (INTERIOR || xa + (u32)i < xEnd) farRow[i] = d[i]; d[i] = ZB_FAR; }
         }
         bool vec = false;
+        if constexpr (P == 16) { if (INTERIOR || xa + 16u <= xEnd) { uint4* const o4 = reinterpret_cast<uint4*>(distRow);
+                                     o4[0] = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16));
+                                     o4[1] = make_uint4(d[8] | (d[9] << 16), d[10] | (d[11] << 16), d[12] | (d[13] << 16), d[14] | (d[15] << 16)); vec = true; } }
         if constexpr (P == 8) { if (INTERIOR || xa + 8u <= xEnd) { *reinterpret_cast<uint4*>(distRow) = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16)); vec = true; } }
         if constexpr (P == 4) { if (INTERIOR || xa + 4u <= xEnd) { *reinterpret_cast<uint2*>(distRow) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16)); vec = true; } }
         if constexpr (P == 2) { if (INTERIOR || xa + 2u <= xEnd) { *reinterpret_cast<u32*>(distRow) = d[0] | (d[1] << 16); vec = true; } }
@@ -197,7 +200,7 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
 #define WALK_STEADY 1            /* development switch: 0 = every batch takes the general path */
 #endif
 #ifndef WALK_P_SMALL
-#define WALK_P_SMALL 4           /* positions per thread for tables <= 56 KiB (development knob: tools/build_variant.sh) */
+#define WALK_P_SMALL 8           /* positions per thread for tables <= 56 KiB: 128 threads per CTA (2.62 ms per GiB against 2.72 with 4; development knob: tools/build_variant.sh) */
 #endif
 #ifndef WALK_P_MID
 #define WALK_P_MID 4             /* tables of 56 .. 113 KiB: two CTAs per SM (measured on config 4: 10.2 ms with 4 positions per thread, 11.2 with 2) */
@@ -348,6 +351,9 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * with 4-byte check (:102-141).  Lowest lane wins.  A segment owns the match starts inside it; a match may run
  * past the segment's end up to the block's end (the merge kernel resolves what that covers).
  * ---------------------------------------------------------------------------------------------- */
+#ifndef PARSE_LAZY_PRE2
+#define PARSE_LAZY_PRE2 0         /* development switch */
+#endif
 #ifndef PARSE_WARPS
 #define PARSE_WARPS 8            /* = ZB_PARSE_SEGS: the eight segments of a full block share a CTA */
 #endif
@@ -413,7 +419,13 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
          * repcode windows are contiguous across lanes */
         u32 pre, cur, pre2, cur2;
         zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
+#if PARSE_LAZY_PRE2
+        /* the repcode window's 4 bytes in front are only needed by a lane whose repcode matched: asked for there */
+        cur2 = DICT ? zb_seg_ld32<DICT>(sg, v2 ? pp - rep1 : pp) : zb_ld32w2(sg.hi + (v2 ? pp - rep1 : pp));
+        pre2 = 0u;
+#else
         zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
+#endif
         u32 cur3 = ~cur;
         if (ip == anchor && rep2 != 0u) cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
         u32 const d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
@@ -423,6 +435,9 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
         u32 myback = 0, mymore = 0;
         if (hit == 2u) {
+#if PARSE_LAZY_PRE2
+            { u32 unused; zb_seg_pre_cur<DICT>(sg, p - rep1, &pre2, &unused); }
+#endif
             u32 const x = pre ^ pre2;
             u32 const bm = x ? ((u32)__clz((int)x) >> 3) : 4u;
             u32 lim = p - anchor; lim = lim < 4u ? lim : 4u;
@@ -605,19 +620,20 @@ __device__ __forceinline__ u32 zb_rep_code(ZbRepHist& h, u32 off, u32 ll)
     return off + 3u;
 }
 
-#ifndef MERGE_GATHER_V2
-#define MERGE_GATHER_V2 1          /* development switch: 0 = a warp per literal run */
-#endif
 #define MERGE_THREADS 256
+#ifndef MERGE_MIN_CTAS
+#define MERGE_MIN_CTAS 5
+#endif
 #define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
 #define MERGE_PER (MERGE_TILE / MERGE_THREADS)  /* consecutive sequences of a tile owned by one thread */
 #define SEG_SLOTS (ZB_PARSE_SEG / 4u)
-__global__ void __launch_bounds__(MERGE_THREADS)
+__global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS)
 zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ blocks, ZbParams prm, ZbStrides sd, const ZbSegMeta* __restrict__ segmeta,
                          u64* __restrict__ seqs, u8* __restrict__ lits, ZbBlockMeta* __restrict__ meta)
 {
     __shared__ u32 sPos[MERGE_TILE], sLit[MERGE_TILE], sLen[MERGE_TILE], sOff[MERGE_TILE];
-    __shared__ u32 wsumL[MERGE_THREADS / 32], wsumA[MERGE_THREADS / 32];
+    __shared__ u32 wsumL[MERGE_THREADS / 32], wsumA[MERGE_THREADS / 32], wmaxU[MERGE_THREADS / 32], wmaxK[MERGE_THREADS / 32];
+    __shared__ u32 sR2[MERGE_TILE], sRep[3];
     __shared__ u32 baseL, baseA, carryEnd;
     __shared__ u32 gFirst[ZB_PARSE_SEGS], gCnt[ZB_PARSE_SEGS], gBase[ZB_PARSE_SEGS], gCur[ZB_PARSE_SEGS], gPm[ZB_PARSE_SEGS], gPl[ZB_PARSE_SEGS];
     __shared__ u32 gTotal;
@@ -677,15 +693,25 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
         }
     }
     u32 const nbSeq = gTotal;
-    if (tid == 0) { baseL = 0; baseA = 0; }
-    ZbRepHist hist; hist.r1 = 0; hist.r2 = 0; hist.r3 = 0;
-    if (bd.flags & ZB_FLAG_FIRST) { hist.r1 = prm.codeRep[0]; hist.r2 = prm.codeRep[1]; hist.r3 = prm.codeRep[2]; }
+    if (tid == 0) {
+        baseL = 0; baseA = 0;
+        bool const first = (bd.flags & ZB_FLAG_FIRST) != 0u;
+        sRep[0] = first ? prm.codeRep[0] : 0u; sRep[1] = first ? prm.codeRep[1] : 0u; sRep[2] = first ? prm.codeRep[2] : 0u;
+    }
     __syncthreads();
-    /* ---- 3. literals + repcodes, a tile of sequences at a time ---- */
+    /* ---- 3. literals + repcodes, a tile of sequences at a time ----
+     * The repcode history (r1, r2, r3) is a serial recurrence in ZSTD_updateRep's form, but its solution is not:
+     *   - after any sequence r1 is that sequence's offset, so "r1 before sequence i" is the offset of sequence i-1;
+     *   - a sequence leaves the history alone (U) iff it has literals and repeats r1; every other sequence sets r2 to the r1
+     *     it found: "r2 before i" is the r1 found by the last non-U sequence before i;
+     *   - a non-U sequence whose offset is the r2 it found swaps r1 and r2 and keeps r3 (K = U or swap); every other sets r3
+     *     to the r2 it found: "r3 before i" is the r2 found by the last non-K sequence before i.
+     * Two "index of the last flagged element before me" scans (maximum scans) over the tile give every sequence the history
+     * it meets; its code follows from ZSTD_storeSeq's rules.  The history passes from tile to tile through sRep. */
     for (u32 t0 = 0; t0 < nbSeq; t0 += MERGE_TILE) {
         u32 const n = min(MERGE_TILE, nbSeq - t0);
         /* every thread owns MERGE_PER consecutive sequences of the tile */
-        u32 ll[MERGE_PER], adv[MERGE_PER], ml[MERGE_PER], myL = 0, myA = 0;
+        u32 ll[MERGE_PER], adv[MERGE_PER], ml[MERGE_PER], off[MERGE_PER], myL = 0, myA = 0;
 #pragma unroll
         for (u32 j = 0; j < MERGE_PER; j++) {
             u32 const i = tid * MERGE_PER + j;
@@ -693,7 +719,8 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
             ll[j] = (u32)((q >> 24) & 0x3FFFFu);
             ml[j] = (u32)(q >> 42);
             adv[j] = ll[j] + ml[j];
-            if (i < n) sOff[i] = (u32)q & 0xFFFFFFu;
+            off[j] = (u32)q & 0xFFFFFFu;
+            if (i < n) sOff[i] = off[j];
             myL += ll[j]; myA += adv[j];
         }
         u32 inL = myL, inA = myA;                                /* inclusive scan over the warp, then over the warps */
@@ -703,6 +730,7 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
             if (lane >= o) { inL += a; inA += c; }
         }
         if (lane == 31u) { wsumL[warp] = inL; wsumA[warp] = inA; }
+        u32 const R1 = sRep[0], R2 = sRep[1], R3 = sRep[2];      /* history at the tile's start */
         __syncthreads();
         u32 offL = baseL + inL - myL, offA = baseA + inA - myA;
         for (u32 w = 0; w < warp; w++) { offL += wsumL[w]; offA += wsumA[w]; }
@@ -712,34 +740,68 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
             if (i < n) { sPos[i] = offA; sLit[i] = offL; sLen[i] = ll[j]; }
             offL += ll[j]; offA += adv[j];
         }
-        __syncthreads();
+        /* r1 before each of my sequences, U flags, first scan */
+        u32 prevOff[MERGE_PER], r2b[MERGE_PER], r3b[MERGE_PER], bef[MERGE_PER];
+        bool U[MERGE_PER], K[MERGE_PER];
+        u32 run = 0;
+#pragma unroll
+        for (u32 j = 0; j < MERGE_PER; j++) {
+            u32 const i = tid * MERGE_PER + j;
+            prevOff[j] = j ? off[j - 1u] : (i == 0u ? R1 : ((i < n) ? sOff[i - 1u] : 0u));
+            U[j] = ll[j] > 0u && off[j] == prevOff[j];
+            bef[j] = run;                                            /* 1 + index of the last non-U sequence of mine before this one */
+            if (i < n && !U[j]) run = i + 1u;
+        }
+        {   u32 inc = run;
+#pragma unroll
+            for (u32 o = 1; o < 32u; o <<= 1) { u32 const x = __shfl_up_sync(ZB_FULL, inc, o); if (lane >= o) inc = max(inc, x); }
+            if (lane == 31u) wmaxU[warp] = inc;
+            u32 ex = __shfl_up_sync(ZB_FULL, inc, 1); if (lane == 0u) ex = 0u;
+            __syncthreads();                                         /* also: sPos / sLit / sLen / sOff of the tile are complete */
+            for (u32 w = 0; w < warp; w++) ex = max(ex, wmaxU[w]);
+#pragma unroll
+            for (u32 j = 0; j < MERGE_PER; j++) {
+                u32 const i = tid * MERGE_PER + j;
+                u32 const m = max(bef[j], ex);                       /* 1 + index of the last non-U sequence before i, 0: none in this tile */
+                r2b[j] = m == 0u ? R2 : (m == 1u ? R1 : sOff[m - 2u]);   /* the r1 that sequence found */
+                if (i < n) sR2[i] = r2b[j];
+            }
+        }
         if (tid == MERGE_THREADS - 1u) { baseL = offL; baseA = offA; }     /* totals up to the end of this tile */
-        if (warp == 0u) {
-            /* the repcode history is a serial recurrence: lane 0 walks the tile (the next sequence's offset and literal
-             * length are requested before the current one is decided) while the other warps move literals */
-            if (lane == 0u) {
-                u32 o = sOff[0], l = sLen[0];
-                for (u32 i = 0; i < n; i++) {
-                    u32 const nx = i + 1u < n ? i + 1u : i;
-                    u32 const on = sOff[nx], ln = sLen[nx];
-                    sOff[i] = zb_rep_code(hist, o, l);
-                    o = on; l = ln;
-                }
+        run = 0;
+#pragma unroll
+        for (u32 j = 0; j < MERGE_PER; j++) {
+            u32 const i = tid * MERGE_PER + j;
+            K[j] = U[j] || off[j] == r2b[j];
+            bef[j] = run;
+            if (i < n && !K[j]) run = i + 1u;
+        }
+        {   u32 inc = run;
+#pragma unroll
+            for (u32 o = 1; o < 32u; o <<= 1) { u32 const x = __shfl_up_sync(ZB_FULL, inc, o); if (lane >= o) inc = max(inc, x); }
+            if (lane == 31u) wmaxK[warp] = inc;
+            u32 ex = __shfl_up_sync(ZB_FULL, inc, 1); if (lane == 0u) ex = 0u;
+            __syncthreads();                                         /* also: sR2 of the tile is complete, every thread holds R1..R3 */
+            for (u32 w = 0; w < warp; w++) ex = max(ex, wmaxK[w]);
+#pragma unroll
+            for (u32 j = 0; j < MERGE_PER; j++) {
+                u32 const i = tid * MERGE_PER + j;
+                u32 const m = max(bef[j], ex);
+                r3b[j] = m == 0u ? R3 : sR2[m - 1u];                 /* the r2 that sequence found */
+                bool const swp = !U[j] && off[j] == r2b[j];
+                u32 c = off[j] + 3u;
+                if (ll[j] > 0u) { if (U[j]) c = 1u; else if (swp) c = 2u; else if (off[j] == r3b[j]) c = 3u; }
+                else            { if (swp) c = 1u; else if (off[j] == r3b[j]) c = 2u; else if (prevOff[j] > 1u && off[j] == prevOff[j] - 1u) c = 3u; }
+                if (i < n) myseq[t0 + i] = zb_pack_seq(c, ll[j], ml[j]);
+                if (i == n - 1u) { sRep[0] = off[j]; sRep[1] = U[j] ? r2b[j] : prevOff[j]; sRep[2] = K[j] ? r3b[j] : r2b[j]; }   /* read again only behind the tile's last barrier */
             }
-        } else if (!MERGE_GATHER_V2) {
-            for (u32 i = warp - 1u; i < n; i += MERGE_THREADS / 32u - 1u) {
-                u32 const len = sLen[i];
-                const u8* const from = in + sPos[i];
-                u8* const to = mylit + sLit[i];
-                for (u32 x = lane; x < len; x += 32u) to[x] = from[x];
-            }
-        } else {
-            /* the tile's literal bytes [L0, L1) of the block's literal buffer, 8 at a time per thread: the run that holds
-             * a group's first byte is found by bisection over the runs' start offsets, later bytes step to the next
-             * non-empty run; all of a thread's loads are independent of one another.  Full groups leave as one 8-byte
-             * store (the buffer is 16-byte aligned), the partial groups at the tile's edges byte by byte. */
-            u32 const L0 = sLit[0], L1 = sLit[n - 1u] + sLen[n - 1u];
-            for (u32 g = (L0 >> 3) + (tid - 32u); (g << 3) < L1; g += MERGE_THREADS - 32u) {
+        }
+        /* the tile's literal bytes [L0, L1) of the block's literal buffer, 8 at a time per thread: the run that holds
+         * a group's first byte is found by bisection over the runs' start offsets, later bytes step to the next
+         * non-empty run; all of a thread's loads are independent of one another.  Full groups leave as one 8-byte
+         * store (the buffer is 16-byte aligned), the partial groups at the tile's edges byte by byte. */
+        {   u32 const L0 = sLit[0], L1 = sLit[n - 1u] + sLen[n - 1u];
+            for (u32 g = (L0 >> 3) + tid; (g << 3) < L1; g += MERGE_THREADS) {
                 u32 const jb = g << 3;
                 u32 const j0 = jb > L0 ? jb : L0, j1 = jb + 8u < L1 ? jb + 8u : L1;
                 u32 sq = 0;                                              /* largest index with sLit[sq] <= j0 (sLit[0] = L0 <= j0) */
@@ -763,13 +825,7 @@ zb_merge_segments_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__
                 else for (u32 j = j0; j < j1; j++) mylit[j] = (u8)(v >> (8u * (j - jb)));
             }
         }
-        __syncthreads();
-#pragma unroll
-        for (u32 j = 0; j < MERGE_PER; j++) {
-            u32 const i = tid * MERGE_PER + j;
-            if (i < n) myseq[t0 + i] = zb_pack_seq(sOff[i], ll[j], ml[j]);
-        }
-        __syncthreads();
+        __syncthreads();                                             /* the shared arrays are free for the next tile, sRep is its history */
     }
     u32 const litSeq = baseL, consumed = baseA;                   /* literals in sequences, bytes covered by sequences */
     u32 const lastLits = bd.size - consumed;
