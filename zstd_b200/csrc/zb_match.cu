@@ -352,7 +352,7 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * past the segment's end up to the block's end (the merge kernel resolves what that covers).
  * ---------------------------------------------------------------------------------------------- */
 #ifndef PARSE_LAZY_PRE2
-#define PARSE_LAZY_PRE2 0         /* development switch */
+#define PARSE_LAZY_PRE2 1         /* 0 = both halves of the repcode window are loaded at the top of every step (5.49 against 5.43 ms per GiB) */
 #endif
 #ifndef PARSE_WARPS
 #define PARSE_WARPS 8            /* = ZB_PARSE_SEGS: the eight segments of a full block share a CTA */
