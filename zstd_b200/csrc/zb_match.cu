@@ -21,6 +21,10 @@
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
+#ifndef WALK_FAST_BC
+#define WALK_FAST_BC 1           /* development switch: 0 = entries and the second look through zb_walk_entry / zb_walk_cand */
+#endif
+
 /* matched bytes starting at rel positions (a, a - offset), never reading at or past `be` */
 template <bool DICT>
 __device__ __forceinline__ u32 zb_count_fwd(const ZbSeg& sg, u32 a, u32 offset, u32 be, u32 lane)
@@ -156,6 +160,28 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
     for (int i = 0; i < P; i++) anyOld |= dOld[i];
     bool const anyHit = __syncthreads_or(anyOld != 0u) != 0;
     /* ---- B: insertions ---- */
+#if WALK_FAST_BC
+    /* a thread's first coordinate is a multiple of P, so the reversed in-batch offsets of its positions count down from
+     * position 0's: key(xa + i) = key(xa) - i; an entry is (Y1 - i) << TAG_BITS | tag with Y1 = key(xa) + 1 */
+    u32 const Y1 = zb_walk_key(xa) + 1u;
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        if (act[i] && dOld[i] == 0u && ((pat >> i) & 1u)) atomicMax(&table[bkt[i]], ((Y1 - (u32)i) << ZB_TAG_BITS) | (h[i] & ZB_TAG_MASK));
+    __syncthreads();
+    /* ---- C: second look, output.  A position without a candidate can only have gained one from this batch's insertions
+     * (its bucket held no entry with its tag before, and what was there came from earlier batches): inside one batch the
+     * distance is the difference of the keys, so the look is shift, add, tag test, sign test ---- */
+    u32 d[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        d[i] = dOld[i];
+        if (act[i] && d[i] == 0u) {
+            u32 const c = table[bkt[i]];
+            int const dd = (int)((c >> ZB_TAG_BITS) - Y1 + (u32)i);        /* key(candidate) - key(me) */
+            d[i] = ((((c ^ h[i]) & ZB_TAG_MASK) == 0u) && dd > 0) ? (u32)dd : 0u;
+        }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < P; i++)
         if (act[i] && dOld[i] == 0u && ((pat >> i) & 1u)) atomicMax(&table[bkt[i]], zb_walk_entry(h[i], xa + (u32)i));
@@ -167,6 +193,7 @@ __device__ __forceinline__ bool zb_walk_batch(u32* __restrict__ table, u32 xa, c
         d[i] = dOld[i];
         if (act[i] && d[i] == 0u) d[i] = zb_walk_cand(table[bkt[i]], h[i], xa + (u32)i);
     }
+#endif
     if (output && (INTERIOR || xa < xEnd)) {
         u32 anyFar = 0;
 #pragma unroll
@@ -351,6 +378,9 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * with 4-byte check (:102-141).  Lowest lane wins.  A segment owns the match starts inside it; a match may run
  * past the segment's end up to the block's end (the merge kernel resolves what that covers).
  * ---------------------------------------------------------------------------------------------- */
+#ifndef PARSE_BITREP
+#define PARSE_BITREP 1            /* development switch: 0 = every step takes the general (window) path */
+#endif
 #ifndef PARSE_LAZY_PRE2
 #define PARSE_LAZY_PRE2 1         /* 0 = both halves of the repcode window are loaded at the top of every step (5.49 against 5.43 ms per GiB) */
 #endif
@@ -414,6 +444,42 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
          * rare far distance costs one more round trip, below) */
         u32 const d16 = act ? (u32)mydist[pp - bs] : 0u;
         bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
+        u32 hit, d, myback = 0, mymore = 0;
+        if (PARSE_BITREP && step == 2u) {
+            /* probe positions ip .. ip + 31 are consecutive (p = ip + lane): the repcode test "4 bytes at p equal the 4 bytes
+             * at p - rep1" for all of them is 35 byte comparisons — lane L compares byte ip + L (lanes 0..2 also byte
+             * ip + 32 + L), two ballots make the comparison results a 35-bit mask E, and E & E>>1 & E>>2 & E>>3 has bit L
+             * set where position ip + L matches: two byte loads per lane instead of two unaligned 8-byte windows.
+             * Backward catch-up of such a hit: bit L-1 of E says whether the byte in front matches too. */
+            u32 eq = 0, eq2 = 0;
+            {   u32 const q = ip + lane, q2 = q + 32u;
+                bool const c1 = rep1 != 0u && q >= rep1 && q < be, c2 = lane < 3u && rep1 != 0u && q2 >= rep1 && q2 < be;
+                if (DICT) {
+                    if (c1) eq = zb_seg_byte<DICT>(sg, q) == zb_seg_byte<DICT>(sg, q - rep1) ? 1u : 0u;
+                    if (c2) eq2 = zb_seg_byte<DICT>(sg, q2) == zb_seg_byte<DICT>(sg, q2 - rep1) ? 1u : 0u;
+                } else {
+                    const u8* const A = sg.hi + q;                      /* one address for the four loads */
+                    const u8* const B = A - rep1;
+                    if (c1) eq = A[0] == B[0] ? 1u : 0u;
+                    if (c2) eq2 = A[32] == B[32] ? 1u : 0u;
+                }
+            }
+            u32 cur = 0, cur3 = 1;
+            if (ip == anchor && rep2 != 0u) {                  /* warp-uniform condition; only lane 0's answer counts */
+                cur = (u32)zb_seg_ld64x<DICT>(sg, pp);
+                cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);
+            }
+            d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
+            u32 const Elo = __ballot_sync(ZB_FULL, eq != 0u), Ehi = __ballot_sync(ZB_FULL, eq2 != 0u);
+            u64 const E = ((u64)Ehi << 32) | Elo;
+            u64 const M = E & (E >> 1) & (E >> 2) & (E >> 3);
+            bool const v1 = act && d != 0u && p >= d;
+            bool const hit2 = act && ((u32)(M >> lane) & 1u);
+            hit = (v3 && cur3 == cur) ? 3u : (hit2 ? 2u : (v1 ? 1u : 0u));
+            /* the whole catch-up is left to zb_back_coop, which is only called where the byte in front is known to match
+             * (or unknown: lane 0) and there is room behind the anchor */
+            mymore = (hit == 2u && p > anchor && (lane == 0u || ((Elo >> (lane - 1u)) & 1u))) ? 1u : 0u;
+        } else {
         bool const v2 = act && rep1 != 0u && p >= rep1;
         /* dist[] only holds tag-verified candidates, so a step needs no random load: the current window and the
          * repcode windows are contiguous across lanes */
@@ -428,12 +494,10 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
 #endif
         u32 cur3 = ~cur;
         if (ip == anchor && rep2 != 0u) cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
-        u32 const d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
+        d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
         bool const v1 = act && d != 0u && p >= d;
-        u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
-        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
+        hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
-        u32 myback = 0, mymore = 0;
         if (hit == 2u) {
 #if PARSE_LAZY_PRE2
             { u32 unused; zb_seg_pre_cur<DICT>(sg, p - rep1, &pre2, &unused); }
@@ -445,6 +509,8 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
             myback = bm < lim ? bm : lim;
             mymore = (bm == 4u && lim == 4u) ? 1u : 0u;
         }
+        }
+        u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
         /* lowest lane first.  A table hit (type 1) is only tag-verified by K1a: its bytes are checked while
          * the match is extended (one round trip, this lane only); a false positive drops out and the next
          * lane is tried — the result is "lowest lane whose hit is real", what the oracle computes. */
