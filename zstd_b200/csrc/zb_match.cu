@@ -378,12 +378,6 @@ zb_walk_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, const
  * with 4-byte check (:102-141).  Lowest lane wins.  A segment owns the match starts inside it; a match may run
  * past the segment's end up to the block's end (the merge kernel resolves what that covers).
  * ---------------------------------------------------------------------------------------------- */
-#ifndef PARSE_BITREP
-#define PARSE_BITREP 1            /* development switch: 0 = every step takes the general (window) path */
-#endif
-#ifndef PARSE_LAZY_PRE2
-#define PARSE_LAZY_PRE2 1         /* 0 = both halves of the repcode window are loaded at the top of every step (5.49 against 5.43 ms per GiB) */
-#endif
 #ifndef PARSE_WARPS
 #define PARSE_WARPS 8            /* = ZB_PARSE_SEGS: the eight segments of a full block share a CTA */
 #endif
@@ -444,71 +438,29 @@ zb_parse_kernel(const u8* __restrict__ src, const u8* __restrict__ dictEnd, cons
          * rare far distance costs one more round trip, below) */
         u32 const d16 = act ? (u32)mydist[pp - bs] : 0u;
         bool const v3 = (lane == 0u) && (ip == anchor) && (rep2 != 0u);
-        u32 hit, d, myback = 0, mymore = 0;
-        if (PARSE_BITREP && step == 2u) {
-            /* probe positions ip .. ip + 31 are consecutive (p = ip + lane): the repcode test "4 bytes at p equal the 4 bytes
-             * at p - rep1" for all of them is 35 byte comparisons — lane L compares byte ip + L (lanes 0..2 also byte
-             * ip + 32 + L), two ballots make the comparison results a 35-bit mask E, and E & E>>1 & E>>2 & E>>3 has bit L
-             * set where position ip + L matches: two byte loads per lane instead of two unaligned 8-byte windows.
-             * Backward catch-up of such a hit: bit L-1 of E says whether the byte in front matches too. */
-            u32 eq = 0, eq2 = 0;
-            {   u32 const q = ip + lane, q2 = q + 32u;
-                bool const c1 = rep1 != 0u && q >= rep1 && q < be, c2 = lane < 3u && rep1 != 0u && q2 >= rep1 && q2 < be;
-                if (DICT) {
-                    if (c1) eq = zb_seg_byte<DICT>(sg, q) == zb_seg_byte<DICT>(sg, q - rep1) ? 1u : 0u;
-                    if (c2) eq2 = zb_seg_byte<DICT>(sg, q2) == zb_seg_byte<DICT>(sg, q2 - rep1) ? 1u : 0u;
-                } else {
-                    const u8* const A = sg.hi + q;                      /* one address for the four loads */
-                    const u8* const B = A - rep1;
-                    if (c1) eq = A[0] == B[0] ? 1u : 0u;
-                    if (c2) eq2 = A[32] == B[32] ? 1u : 0u;
-                }
-            }
-            u32 cur = 0, cur3 = 1;
-            if (ip == anchor && rep2 != 0u) {                  /* warp-uniform condition; only lane 0's answer counts */
-                cur = (u32)zb_seg_ld64x<DICT>(sg, pp);
-                cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);
-            }
-            d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
-            u32 const Elo = __ballot_sync(ZB_FULL, eq != 0u), Ehi = __ballot_sync(ZB_FULL, eq2 != 0u);
-            u64 const E = ((u64)Ehi << 32) | Elo;
-            u64 const M = E & (E >> 1) & (E >> 2) & (E >> 3);
-            bool const v1 = act && d != 0u && p >= d;
-            bool const hit2 = act && ((u32)(M >> lane) & 1u);
-            hit = (v3 && cur3 == cur) ? 3u : (hit2 ? 2u : (v1 ? 1u : 0u));
-            /* the whole catch-up is left to zb_back_coop, which is only called where the byte in front is known to match
-             * (or unknown: lane 0) and there is room behind the anchor */
-            mymore = (hit == 2u && p > anchor && (lane == 0u || ((Elo >> (lane - 1u)) & 1u))) ? 1u : 0u;
-        } else {
         bool const v2 = act && rep1 != 0u && p >= rep1;
         /* dist[] only holds tag-verified candidates, so a step needs no random load: the current window and the
-         * repcode windows are contiguous across lanes */
-        u32 pre, cur, pre2, cur2;
+         * repcode window are contiguous across lanes.  The repcode window's 4 bytes in front of the position are only
+         * needed by a lane whose repcode matched: asked for there */
+        u32 pre, cur;
         zb_seg_pre_cur<DICT>(sg, pp, &pre, &cur);
-#if PARSE_LAZY_PRE2
-        /* the repcode window's 4 bytes in front are only needed by a lane whose repcode matched: asked for there */
-        cur2 = DICT ? zb_seg_ld32<DICT>(sg, v2 ? pp - rep1 : pp) : zb_ld32w2(sg.hi + (v2 ? pp - rep1 : pp));
-        pre2 = 0u;
-#else
-        zb_seg_pre_cur<DICT>(sg, v2 ? pp - rep1 : pp, &pre2, &cur2);
-#endif
+        u32 const cur2 = DICT ? zb_seg_ld32<DICT>(sg, v2 ? pp - rep1 : pp) : zb_ld32w2(sg.hi + (v2 ? pp - rep1 : pp));
         u32 cur3 = ~cur;
         if (ip == anchor && rep2 != 0u) cur3 = (u32)zb_seg_ld64x<DICT>(sg, v3 ? pp - rep2 : pp);     /* warp-uniform condition */
-        d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
+        u32 const d = d16 == ZB_FAR ? myfar[pp - bs] : d16;
         bool const v1 = act && d != 0u && p >= d;
-        hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
+        u32 const hit = (v3 && cur3 == cur) ? 3u : ((v2 && cur2 == cur) ? 2u : (v1 ? 1u : 0u));
         /* backward catch-up (zstd_fast.c:387-391) of a repcode-1 hit: first 4 bytes in-lane from the windows */
+        u32 myback = 0, mymore = 0;
         if (hit == 2u) {
-#if PARSE_LAZY_PRE2
-            { u32 unused; zb_seg_pre_cur<DICT>(sg, p - rep1, &pre2, &unused); }
-#endif
+            u32 pre2, unused;
+            zb_seg_pre_cur<DICT>(sg, p - rep1, &pre2, &unused);
             u32 const x = pre ^ pre2;
             u32 const bm = x ? ((u32)__clz((int)x) >> 3) : 4u;
             u32 lim = p - anchor; lim = lim < 4u ? lim : 4u;
             u32 const src0 = p - rep1; lim = lim < src0 ? lim : src0;
             myback = bm < lim ? bm : lim;
             mymore = (bm == 4u && lim == 4u) ? 1u : 0u;
-        }
         }
         u32 tent = __ballot_sync(ZB_FULL, hit != 0u);
         /* lowest lane first.  A table hit (type 1) is only tag-verified by K1a: its bytes are checked while
@@ -688,7 +640,7 @@ __device__ __forceinline__ u32 zb_rep_code(ZbRepHist& h, u32 off, u32 ll)
 
 #define MERGE_THREADS 256
 #ifndef MERGE_MIN_CTAS
-#define MERGE_MIN_CTAS 5
+#define MERGE_MIN_CTAS 6           /* 40 registers (parse + merge 5.46 ms per GiB against 5.49 with 5 and 5.65 with 4) */
 #endif
 #define MERGE_TILE 1024u                       /* sequences scanned and gathered per round */
 #define MERGE_PER (MERGE_TILE / MERGE_THREADS)  /* consecutive sequences of a tile owned by one thread */
