@@ -10,9 +10,8 @@
  *   1. LL/OF/ML codes + three histograms: all threads, shared-memory atomics
  *   2. per stream (one warp each): encoding type, normalised counts (largest remainders), NCount header, FSE table
  *      (zb_entropy.cuh); predefined tables are built once per device by the host and copied
- *   3. tANS state chains: state(i) depends on state(i+1) (common/fse.h:463-470), but only through the few bits a step
- *      keeps: a chain's tile is walked in segments by several lanes at once from a guessed state and the segments' heads
- *      are redone with the true one until the walks meet; (bits, nbBits) are recorded per sequence
+ *   3. tANS state chains: state(i) depends on state(i+1) (common/fse.h:463-470), so each of the three
+ *      chains is walked backwards by one lane (the three lanes share a warp); it records (bits, nbBits) per sequence
  *   4. all threads: per-sequence bit counts -> suffix sum -> bit offsets -> pack (edge words atomicOr)
  */
 #include "zb_entropy.cuh"
@@ -23,7 +22,6 @@
 #ifndef SEQ_TILE
 #define SEQ_TILE 512u                /* sequences whose chain steps are prepared at a time (3 x 2 KiB of shared memory) */
 #endif
-#define SEQ_SEGS 10u                 /* segments a chain's tile is walked in at once: 3 chains x 10 lanes of one warp */
 #define MaxLL 35
 #define MaxML 52
 #define MaxOff 31
@@ -133,8 +131,6 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
                                                     * odd stride: the three chains read different banks */
     __shared__ u32 sh_cSize, sh_hdrEnd, sh_streamSize;
     __shared__ ZbdCodeLut lut;
-    __shared__ u16 specState[3][SEQ_TILE];         /* per chain: the state after each step of the tile, as the segment walks left it */
-    __shared__ u32 chainState[3];                  /* per chain: the state that enters the next tile's first step */
 
     u32 const tid = threadIdx.x;
     u32 const b = blockIdx.x;
@@ -224,22 +220,17 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
 
         /* ---- 3. state chains.  The only loop-carried value of a chain is `state` (common/fse.h:463-470): everything
          * else is prepared in parallel.  The sequences are walked last to first in tiles; all threads turn a tile's
-         * LL/OF/ML codes into the chains' per-step words (the symbol's deltaNbBits | deltaFindState << 20).
-         * A step maps the state to nextState[(state >> nbBits) + delta]: it sheds nbBits of what the state knew, so two
-         * walks over the same symbols that start from different states meet after a few steps (tableLog bits shed) and
-         * are identical from there on.  A tile's steps are therefore cut into SEQ_SEGS segments per chain and walked by
-         * 3 x SEQ_SEGS lanes of one warp at once, every lane starting from the tile's incoming state (right for the
-         * first segment only) and keeping the state after each step; then one lane per chain goes through the segments in
-         * order and redoes the head of each with the true state until it meets the recorded one.  Same records as one
-         * serial walk, a fraction of its dependent steps. ---- */
+         * LL/OF/ML codes into the chains' per-step words (the symbol's deltaNbBits | deltaFindState << 20), then lanes
+         * 0, 1, 2 of ONE warp walk the three chains side by side — a lane that walks alone costs a whole warp's issue
+         * slot per instruction, three lanes in one warp cost the same slot once.  A step is: word of the next step
+         * requested, bits shed, record stored, next-state look-up. ---- */
         {
-            u32 const st = tid / SEQ_SEGS, sg = tid % SEQ_SEGS;      /* chain and segment of the lanes of warp 0 */
-            bool const walker = tid < 3u * SEQ_SEGS;
-            u32 const cst = walker ? st : 0u;
-            const u16* const ns = ct[cst].nextState;
-            const u32* const tw = stepTile[cst] + 1;
-            u16* const spec = specState[cst];
-            u16* const rec = myst + (size_t)cst * sd.state;
+            u32 state = 0;
+            bool const chain = tid < 3u;
+            u32 const st = chain ? tid : 0u;
+            const u16* const ns = ct[st].nextState;
+            const u32* const tw = stepTile[st] + 1;
+            u16* const rec = myst + (size_t)st * sd.state;
             u32 const nbTiles = (nbSeq + SEQ_TILE - 1u) / SEQ_TILE;
             for (u32 tile = nbTiles; tile-- > 0; ) {
                 u32 const t0 = tile * SEQ_TILE, t1 = min(t0 + SEQ_TILE, nbSeq);
@@ -250,53 +241,29 @@ zb_sequences_kernel(const u8* __restrict__ src, const ZbBlock* __restrict__ bloc
                     stepTile[2][i - t0 + 1u] = ct[2].deltaNbBits[s.mlc] | ((u32)ct[2].deltaFindState[s.mlc] << 20);
                 }
                 __syncthreads();
-                if (tid < 32u) {
-                    /* steps of this tile: local indices m-1 down to 0 (the block's last sequence only starts the states) */
-                    u32 m = t1 - t0;
-                    if (t1 == nbSeq) {
-                        m--;
-                        if (walker && sg == 0u) {
-                            u32 const w0 = tw[m], dnb = w0 & 0xFFFFFu;
-                            u32 const nbOut = (dnb + (1u << 15)) >> 16;
-                            chainState[cst] = ns[(int)(((nbOut << 16) - dnb) >> nbOut) + ((int)w0 >> 20)];
-                        }
+                if (chain) {
+                    u32 cnt = t1 - t0;                                   /* steps of this tile, last sequence first */
+                    const u32* pw = tw + cnt;                            /* pw[-1] = word of the sequence in turn */
+                    u16* pr = rec + t1;
+                    if (t1 == nbSeq) {                                   /* last sequence: its symbols start the states and cost no bits */
+                        u32 const w0 = pw[-1], dnb = w0 & 0xFFFFFu;
+                        u32 const nbOut = (dnb + (1u << 15)) >> 16;
+                        state = ns[(int)(((nbOut << 16) - dnb) >> nbOut) + ((int)w0 >> 20)];
+                        cnt--; pw--; pr--;
                     }
-                    __syncwarp();
-                    u32 const segLen = (m + SEQ_SEGS - 1u) / SEQ_SEGS;
-                    u32 const lo = min(sg * segLen, m), hi = min(lo + segLen, m);   /* my segment: steps hi-1 down to lo */
-                    if (walker) {
-                        u32 state = chainState[cst];
-                        for (u32 j = hi; j-- > lo; ) {
-                            u32 const w = tw[j];
-                            u32 const nb = (state + (w & 0xFFFFFu)) >> 16;
-                            rec[t0 + j] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-                            state = ns[(int)(state >> nb) + ((int)w >> 20)];
-                            spec[j] = (u16)state;
-                        }
-                    }
-                    __syncwarp();
-                    if (walker && sg == 0u && m > 0u) {
-                        /* the segment that holds step m-1 was walked from the true state; the others are joined one by one */
-                        u32 const top = (m - 1u) / segLen;
-                        u32 state = spec[top * segLen];
-                        for (u32 k = top; k-- > 0u; ) {
-                            u32 const klo = k * segLen;
-                            for (u32 j = klo + segLen; j-- > klo; ) {
-                                u32 const w = tw[j];
-                                u32 const nb = (state + (w & 0xFFFFFu)) >> 16;
-                                rec[t0 + j] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-                                state = ns[(int)(state >> nb) + ((int)w >> 20)];
-                                if (state == spec[j]) break;             /* the recorded walk is the true one from here on */
-                                spec[j] = (u16)state;
-                            }
-                            state = spec[klo];
-                        }
-                        chainState[cst] = state;
+                    u32 w = pw[-1];                                      /* tw[-1] exists (padding word): no guard */
+                    while (cnt) {
+                        cnt--; pw--; pr--;
+                        u32 const wn = pw[-1];                           /* next step's word, in flight during this step */
+                        u32 const nb = (state + (w & 0xFFFFFu)) >> 16;
+                        *pr = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+                        state = ns[(int)(state >> nb) + ((int)w >> 20)];
+                        w = wn;
                     }
                 }
                 __syncthreads();
             }
-            if (tid < 3u) wk[tid].finalState = chainState[tid];
+            if (chain) wk[st].finalState = state;
         }
         __syncthreads();
 
