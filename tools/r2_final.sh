@@ -15,3 +15,4 @@ timeout 150 python bench.py --config 5 --steps 5 --warmup 3 --no-cpu > $P/r2u_be
 ZSTDB200_SERIAL=1 timeout 200 ncu --set full --import-source on --clock-control none -k regex:"zb_walk|zb_parse|zb_merge|zb_literals|zb_sequences" -c 5 -o $P/r2u_all_256 -f python tests/profile_one.py 256 50 1 1 > $P/n1.log 2>&1
 ncu -i $P/r2u_all_256.ncu-rep --page raw --csv > $P/r2u_ncu_full_all_256MiB.csv 2>/dev/null
 timeout 150 python bench.py --config 3 --scale 0.25 --steps 5 --warmup 3 --no-cpu > $P/r2u_bench_c3_quarter.json 2> $P/r2u_bench_c3.err; cut -c1-400 $P/r2u_bench_c3_quarter.json
+timeout 120 python tests/wave_sweep.py c2 3 2>&1 | grep -v Warning | tee $P/r2u_wave_sweep.txt
